@@ -1,0 +1,136 @@
+/*
+ * cc4_state.h — packed per-episode state of the batched CC4 engine (shared by device kernels and the host-side
+ * canonical exporter).  One episode = one Cc4Dyn record (read + written every tick, staged through shared memory
+ * by the warp that owns the episode) + one Cc4Stat record (written at reset; read on Restore / export only).
+ * Records of consecutive episodes are contiguous in HBM, so a warp moves its record with 128-bit coalesced accesses.
+ *
+ * Field semantics cite the reference (paths under CybORG/).
+ */
+#pragma once
+#include <stdint.h>
+
+#define CC4_NSUB 9
+#define CC4_NSLOT 137        /* 128 regular host slots (subnet*16 + {server k | 6 + user k}), routers 128+subnet, internet host 136 */
+#define CC4_SLOT_ROUTER 128
+#define CC4_SLOT_INTERNET 136
+#define CC4_NRED 6
+#define CC4_NBLUE 5
+#define CC4_MAXGREEN 80
+
+#define CC4_PROC_CAP 1024    /* process entries per episode (CSR pool over the 128 regular hosts) */
+#define CC4_SESS_CAP 160     /* red sessions per episode (all six agents) */
+#define CC4_PORT_CAP 384     /* (red abstract session, host) known-port entries */
+#define CC4_SUS_CAP 256      /* blue suspicious-pid entries */
+#define CC4_FSM_CAP 64       /* hosts known to one red agent's FSM */
+#define CC4_SS_CAP 48        /* server_session ids known to one red agent */
+#define CC4_OENT_CAP 64      /* observation entries of one red agent in one tick */
+
+/* process entry (Simulator/Process.py:12): pid | kind<<16 | root<<20 | svc<<21 | dead<<22
+ * svc  = this process backs host.services[kind] (Host.py:124);
+ * dead = tombstone of a stopped service's removed process: keeps Service.process for a stopped OT service
+ *        (State.stop_service State.py:467); skipped by everything that iterates host.processes. */
+#define P_PID(w) ((w) & 0xFFFFu)
+#define P_KIND(w) (((w) >> 16) & 0xFu)
+#define P_ROOT(w) (((w) >> 20) & 1u)
+#define P_SVC(w) (((w) >> 21) & 1u)
+#define P_DEAD(w) (((w) >> 22) & 1u)
+#define P_MAKE(pid, kind, root, svc) ((uint32_t)(pid) | (uint32_t)(kind) << 16 | (uint32_t)(root) << 20 | (uint32_t)(svc) << 21)
+#define P_DEADBIT (1u << 22)
+#define P_ROOTBIT (1u << 20)
+
+/* process kinds == service codes for 0..8 (oracle/canon.py PK) */
+enum { K_SSHD, K_OT, K_APACHE2, K_MYSQLD, K_SMTP, K_D_APACHE, K_D_TOMCAT, K_D_HARAKA, K_D_VSFTPD, K_SESSION, K_SHELL, K_REDABS };
+
+/* svc64: host.services in dict order (Host.py:124, Service.py:4): entry i = bits [7i,7i+7) = code | (reliability/20)<<4,
+ * code 15 = empty; bit 63 = the OT service is stopped (the only service the CC4 action set can stop, Impact.py:38). */
+#define SVC_EMPTY 0x7FFFFFFFFFFFFFFFull
+#define SVC_ENTRY(v, i) ((uint32_t)((v) >> (7 * (i))) & 0x7Fu)
+#define SVC_OT_STOPPED (1ull << 63)
+
+/* red session (Shared/Session.py:6,120): pid | ident<<16 | host<<24 ; flags: agent | abstract<<3 | root<<4 */
+#define S_PID(w) ((w) & 0xFFFFu)
+#define S_ID(w) (((w) >> 16) & 0xFFu)
+#define S_HOST(w) (((w) >> 24) & 0x7Fu)
+#define S_MAKE(pid, id, host) ((uint32_t)(pid) | (uint32_t)(id) << 16 | (uint32_t)(host) << 24)
+#define SF_AGENT(f) ((f) & 7u)
+#define SF_ABS(f) (((f) >> 3) & 1u)
+#define SF_ROOT(f) (((f) >> 4) & 1u)
+
+/* known ports of a RedAbstractSession (Session.py:125-133): mask | host<<6 | ident<<13 | agent<<21 */
+#define PT_MASK(w) ((w) & 0x3Fu)
+#define PT_HOST(w) (((w) >> 6) & 0x7Fu)
+#define PT_ID(w) (((w) >> 13) & 0xFFu)
+#define PT_AGENT(w) (((w) >> 21) & 7u)
+#define PT_MAKE(mask, host, id, agent) ((uint32_t)(mask) | (uint32_t)(host) << 6 | (uint32_t)(id) << 13 | (uint32_t)(agent) << 21)
+
+/* FSM entry (FiniteStateRedAgent.host_states, FiniteStateRedAgent.py:36): slot | hostname_known<<7 | state<<8 */
+#define F_SLOT(w) ((w) & 0x7Fu)
+#define F_HN(w) (((w) >> 7) & 1u)
+#define F_STATE(w) (((w) >> 8) & 0xFu)
+#define F_MAKE(slot, hn, state) ((uint16_t)((slot) | (hn) << 7 | (state) << 8))
+
+/* in-flight action (SimulationController.actions_in_progress :246): code | host<<6 | subnet<<14 | session<<18 | ticks<<26 */
+#define IP_NONE 63u
+#define IP_CODE(w) ((w) & 63u)
+#define IP_HOST(w) (((w) >> 6) & 0xFFu)
+#define IP_SUBNET(w) (((w) >> 14) & 0xFu)
+#define IP_SESSION(w) (((w) >> 18) & 0xFFu)
+#define IP_TICKS(w) (((w) >> 26) & 0xFu)
+#define IP_MAKE(code, host, subnet, session, ticks) ((uint32_t)(code) | (uint32_t)((host) & 0xFF) << 6 | (uint32_t)((subnet) & 0xF) << 14 | (uint32_t)((session) & 0xFF) << 18 | (uint32_t)(ticks) << 26)
+
+/* blue suspicious pid (VelociraptorServer.sus_pids Session.py:154-165): pid | slot<<16 | agent<<24 */
+#define SU_PID(w) ((w) & 0xFFFFu)
+#define SU_SLOT(w) (((w) >> 16) & 0xFFu)
+#define SU_AGENT(w) (((w) >> 24) & 7u)
+#define SU_MAKE(pid, slot, agent) ((uint32_t)(pid) | (uint32_t)(slot) << 16 | (uint32_t)(agent) << 24)
+
+/* host event bits (Simulator/HostEvents.py:7) */
+#define EV_PROC 1u
+#define EV_NET 2u
+#define EV_OLDPROC 4u
+#define EV_OLDNET 8u
+
+struct __attribute__((aligned(16))) Cc4Dyn {
+    /* ---- hosts ---- */
+    uint32_t procs[CC4_PROC_CAP];       /* CSR pool: host h owns [pstart[h], pstart[h+1]) in host.processes order */
+    uint64_t svc64[128];
+    uint16_t pstart[136];               /* 129 used */
+    uint8_t ev[144];                    /* 137 used */
+    /* ---- red sessions: one pool in creation order; an agent's state.sessions[agent] dict order is the pool order */
+    uint32_t sess[CC4_SESS_CAP];
+    uint32_t ports[CC4_PORT_CAP];
+    uint32_t sus[CC4_SUS_CAP];
+    uint8_t sessf[CC4_SESS_CAP];
+    /* ---- red knowledge (Shared/ActionSpace.py:170-212) ---- */
+    uint32_t ip_known[CC4_NRED][4];
+    uint32_t hn_known[CC4_NRED][4];
+    uint16_t fsm[CC4_NRED][CC4_FSM_CAP];
+    uint8_t ss[CC4_NRED][CC4_SS_CAP];   /* known server_session ids in dict order */
+    uint32_t inprog[16];                /* actors 0..10 (blue 0-4, red 5-10) */
+    uint16_t sn_known[8];
+    uint16_t blocks[12];                /* blocks[to] bit from (State.blocks State.py:148); 9 used */
+    uint8_t n_ss[8];
+    uint8_t n_fsm[8];
+    uint8_t sess_count[8];              /* state.sessions_count[red agent] (stale after Restore, RestoreFromBackup.py:9-19) */
+    uint8_t msgs[8];
+    uint8_t green_host[CC4_MAXGREEN];   /* static after reset, staged with the record because every tick needs it */
+    uint8_t nuser[8], nserver[8];
+    uint16_t n_sess, n_ports, n_sus, step;
+    uint8_t phase, done, fsm_started, red_active, ngreen, pad0[3];
+    uint32_t err;
+    uint32_t pad1[3];
+};
+
+struct __attribute__((aligned(16))) Cc4Stat {
+    uint32_t o_procs[CC4_PROC_CAP];     /* Host.create_backup Host.py:316 (original_processes) */
+    uint64_t o_svc64[128];              /* original_services */
+    uint16_t o_pstart[136];
+    uint16_t router_pid[16];            /* pid of the blue session process on each router (0 = none), internet host has none */
+    uint8_t blue_parent[8];
+    uint8_t red_start[8];
+};
+
+#ifdef __cplusplus
+static_assert(sizeof(Cc4Dyn) % 16 == 0, "Cc4Dyn must be a multiple of 16 bytes");
+static_assert(sizeof(Cc4Stat) % 16 == 0, "Cc4Stat must be a multiple of 16 bytes");
+#endif

@@ -1,0 +1,110 @@
+/*
+ * cc4_b200.h — C-ABI of the B200-native batched CybORG CC4 step engine.
+ *
+ * The reference (cage-challenge/cage-challenge-4, pure Python) has no FFI seam; its boundary for this path is
+ * the Python call chain  BlueFlatWrapper.step -> CybORG.parallel_step -> SimulationController.step
+ * (CybORG/Agents/Wrappers/BlueFlatWrapper.py:80, CybORG/env.py:95, CybORG/Simulator/SimulationController.py:211).
+ * The entry points below are what a ctypes binding placed behind those methods calls (INTEGRATION.md shows it).
+ *
+ * Conventions: extern "C", plain pointers and sizes, no torch / C++ types.  Every function returns 0 on
+ * success and a negative cc4_status on failure; cc4_last_error() returns a thread-local message.  Pointers
+ * named *_dev are device pointers on the handle's device (borrowed for the duration of the call; work is
+ * enqueued on `stream`, which is a cudaStream_t passed as void*; NULL = the legacy default stream).
+ * Pointers named *_host are host pointers.  A handle is bound to one device and is not thread-safe.
+ */
+#ifndef CC4_B200_H
+#define CC4_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cc4_handle cc4_handle;
+
+enum cc4_status { CC4_OK = 0, CC4_ERR_ARG = -1, CC4_ERR_CUDA = -2, CC4_ERR_STATE = -3 };
+
+/* per-episode sticky error bits (cc4_error_flags) */
+enum {
+    CC4_E_TAPE_SITE = 1,   /* tape replay: the engine's draw does not match the recorded site / range */
+    CC4_E_TAPE_END = 2,    /* tape replay: an actor's segment ran out */
+    CC4_E_CAPACITY = 4,    /* a fixed-size table overflowed (the episode's results are no longer exact) */
+    CC4_E_UNREACHABLE = 8, /* a branch on which the reference itself raises an exception was reached */
+    CC4_E_TAPE_LEFT = 16   /* tape replay: an actor's segment was not fully consumed */
+};
+
+#define CC4_N_BLUE 5
+#define CC4_OBS_LEN 210   /* BlueFlatWrapper.py:128-170: 1 + 3*59 + 32 (agents 0-3 use the first 92 = 1 + 59 + 32) */
+#define CC4_MASK_LEN 242  /* BlueFixedActionWrapper.py:233-309: 82 actions (agents 0-3) / 242 (agent 4) */
+#define CC4_N_ACTORS 91   /* tape actor ids: blue 0-4, red 5-10, green 11-90 */
+
+/* step flags */
+#define CC4_STEP_OBS 1      /* write the 5 observation vectors            (BlueFlatWrapper.observation_change :172) */
+#define CC4_STEP_REWARD 2   /* write the team reward                      (BlueRewardMachine.calculate_reward :70) */
+#define CC4_STEP_ALL 3
+
+/* One recorded RNG draw of the reference (tape mode; layout shared with oracle/cc4_oracle.h). */
+typedef struct {
+    uint64_t val;   /* kind 0: integer in [0,n); kind 1: IEEE-754 bits of a double in [0,1) */
+    uint16_t n;
+    uint8_t site;
+    uint8_t kind;
+    uint32_t pad;
+} cc4_draw;
+
+/* Replaces: CybORG(scenario_generator, seed) + SimulationController.__init__ (env.py:53-77, SimulationController.py:60-151).
+ * n_envs independent episodes; episode i uses the RNG stream (seed, first_episode + i), so results do not depend
+ * on how episodes are sharded over devices.  steps = EnterpriseScenarioGenerator(steps=...), 500 in the challenge.
+ * rng_mode 0: Philox4x32-10 counter RNG (production); 1: replay of recorded reference draws (parity tests). */
+int cc4_create(int n_envs, int device, uint64_t seed, uint64_t first_episode, int steps, int rng_mode, cc4_handle **out);
+int cc4_destroy(cc4_handle *h);
+
+/* Packed per-episode state sizes in bytes (dynamic = read+written every tick, static = written at reset). */
+int cc4_state_bytes(cc4_handle *h, size_t *dyn_bytes, size_t *stat_bytes);
+
+/* Tape mode only: recs_dev[n_recs]; seg_off_dev[n_envs][n_segs + 1] absolute offsets into recs_dev, segment 0 =
+ * reset, segment 1 + tick*CC4_N_ACTORS + actor = that actor's draws in that tick (oracle/ref_harness.py). */
+int cc4_set_tape(cc4_handle *h, const cc4_draw *recs_dev, const uint32_t *seg_off_dev, uint32_t n_segs);
+
+/* Replaces: CybORG.reset -> SimulationController.reset -> EnterpriseScenarioGenerator.create_scenario + State.__init__
+ * (env.py:218, SimulationController.py:153-209, EnterpriseScenarioGenerator.py:123, State.py:66) and the wrappers'
+ * reset outputs (BlueFlatWrapper.reset :61, BlueFixedActionWrapper.reset :76).
+ * obs_dev: uint8 [n_envs][5][210] or NULL; mask_dev: uint8 [n_envs][5][242] or NULL. */
+int cc4_reset(cc4_handle *h, uint8_t *obs_dev, uint8_t *mask_dev, void *stream);
+
+/* Replaces: BlueFlatWrapper.step -> CybORG.parallel_step -> SimulationController.step (+ send_messages,
+ * observation_change x5, BlueRewardMachine) for every episode of the batch.
+ * actions_dev int32 [n_envs][5] BlueFixedActionWrapper indices; msgs_dev uint8 [n_envs][5] (bit i = message[i]) or NULL;
+ * obs_dev uint8 [n_envs][5][210]; reward_dev float [n_envs] (team reward = BlueRewardMachine + action_cost, identical
+ * for the 5 blue agents, SimulationController.py:1118); done_dev uint8 [n_envs].  Outputs may be NULL. */
+int cc4_step(cc4_handle *h, const int32_t *actions_dev, const uint8_t *msgs_dev, uint8_t *obs_dev, float *reward_dev,
+             uint8_t *done_dev, int flags, void *stream);
+
+/* Same call with HOST buffers: copies actions/messages host->device, steps, copies obs/reward/done back and
+ * synchronises the stream (the e2e path bench.py times; host buffers should be pinned for full speed). */
+int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const uint8_t *msgs_host, uint8_t *obs_host,
+                  float *reward_host, uint8_t *done_host, int flags, void *stream);
+
+/* n_ticks fused ticks with the synthetic uniform-random blue policy of the benchmark (indices drawn on device from
+ * Philox keyed (policy_seed, episode, tick); BASELINE config "FiniteStateRed + random blue").  reward_sum_dev float
+ * [n_envs] is incremented by each tick's reward (may be NULL).  State is kept in shared memory across the ticks. */
+int cc4_rollout(cc4_handle *h, int n_ticks, uint64_t policy_seed, float *reward_sum_dev, int flags, void *stream);
+
+/* Per-episode error bits: out_host uint32 [n_envs] (synchronises). */
+int cc4_error_flags(cc4_handle *h, uint32_t *out_host);
+
+/* Canonical flattened state of one episode (layout: oracle/canon.py) for parity tests: out_host int32 [cap];
+ * *n_out = number of values.  Synchronises the device. */
+int cc4_export_canon(cc4_handle *h, int env, int32_t *out_host, int cap, int *n_out);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int cc4_launch_count(cc4_handle *h, uint64_t *out);
+
+const char *cc4_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -14,7 +14,10 @@ Stream layout (all int32):
       active, sessions_count, nsess, (ident, slot, is_red_abstract, is_root, pid)*nsess   in dict order (State.py:305)
       n, ip-known slots sorted; n, hostname-known slots sorted; subnet-known mask        (ActionSpace.py:170)
       n, server_session ids that are True, in dict order
-      n, (slot, fsm_state, hostname_known)*n   FiniteStateRedAgent.host_states in insertion order (slot -1 = None key)
+      n, (slot, fsm_state, hostname_known)*n   FiniteStateRedAgent.host_states in insertion order (slot -1 = None key),
+                                                as it stands once the agent has digested this tick's observation
+                                                (FiniteStateRedAgent.py:91-93; the reference does that lazily at the
+                                                start of the next tick, the engines do it eagerly)
       n, (ident, slot, portmask)*n sorted      RedAbstractSession.ports                   (Session.py:125)
       inprog_code, inprog_remaining            (-1, 0 when nothing in flight)             (SimulationController.py:246)
   per blue agent 0..4:

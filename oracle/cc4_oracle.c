@@ -887,6 +887,7 @@ static int exec_red(cc4o_env *e, int r, const act_t *a)
     switch (a->code) {
     case AC_DRS: {     /* DiscoverRemoteSystems.py:39 -> Pingsweep.execute Pingsweep.py:31-64 */
         int sn = a->subnet, succ = SUCC_UNKNOWN;
+        if (!S) return SUCC_FALSE;                     /* session vanished after filter_actions: Pingsweep.py:36-39 */
         if (sn == S_INT) return succ;                  /* root_internet_host_0 does not respond to ping */
         for (int k = 0; k < e->nuser[sn] + e->nserver[sn]; k++) {
             int slot = k < e->nuser[sn] ? sn * 16 + 6 + k : sn * 16 + (k - e->nuser[sn]);
@@ -897,7 +898,7 @@ static int exec_red(cc4o_env *e, int r, const act_t *a)
         return succ;
     }
     case AC_AGGR: case AC_STEALTH: {   /* DiscoverNetworkServices.py:44-86 -> Portscan.py:23-65 */
-        if (S->type != 1) return SUCC_FALSE;
+        if (!S || S->type != 1) return SUCC_FALSE;
         if (blocking(e, S->host, a->host)) return SUCC_FALSE;
         host_t *h = &e->hosts[a->host];
         double rate = a->code == AC_AGGR ? 0.75 : 0.25;
@@ -913,6 +914,7 @@ static int exec_red(cc4o_env *e, int r, const act_t *a)
         return SUCC_TRUE;
     }
     case AC_DD: {      /* DiscoverDeception.py:44-101 */
+        if (!S) return SUCC_FALSE;
         host_t *h = &e->hosts[a->host];
         int rep = 0;
         for (int i = 0; i < h->nproc; i++) {
@@ -924,7 +926,7 @@ static int exec_red(cc4o_env *e, int r, const act_t *a)
         return SUCC_TRUE;
     }
     case AC_EXPLOIT: { /* ExploitRemoteService.py:149-202 */
-        if (S->type != 1) return SUCC_FALSE;
+        if (!S || S->type != 1) return SUCC_FALSE;
         if (!S->has_ports[a->host]) return SUCC_FALSE;
         if (blocking(e, S->host, a->host)) return SUCC_FALSE;
         int ports = S->ports[a->host];
@@ -993,7 +995,7 @@ static int exec_red(cc4o_env *e, int r, const act_t *a)
         for (int i = 0; i < n; i++) if (e->sess[actor][on[i]].root) { tgt = on[i]; break; }
         if (tgt < 0) {
             tgt = on[rng_int(e, actor, ST_PRIV_SESS, (uint32_t)n)];
-            if (S->type != 1) return SUCC_FALSE;       /* DefaultEscalateActionSelector :37-48 */
+            if (!S || S->type != 1) return SUCC_FALSE; /* DefaultEscalateActionSelector :37-48 */
             sess_t *T = &e->sess[actor][tgt];
             T->root = 1;                                /* EscalateAction.__upgrade_session EscalateAction.py:54-87 */
             int pi = find_proc(&e->hosts[a->host], T->pid);
@@ -1003,7 +1005,7 @@ static int exec_red(cc4o_env *e, int r, const act_t *a)
         obs_entry(e, r, 0, a->host, 0, 0, 0, 1);
         if (T->type == 1) know_session(e, r, T->id);
         /* ExploreHost EscalateAction.py:90-106 with Host.info = _between_subnet_links :418-468 */
-        if (slot_is_server(a->host) && (a->host & 15) == 0) {
+        if (S && slot_is_server(a->host) && (a->host & 15) == 0) {   /* ExploreHost needs self.session too :99-104 */
             uint16_t lk = LINKS[slot_subnet(a->host)];
             for (int oi = 0; oi < e->norder; oi++) { int s = e->order[oi]; if (s < 128 && (s & 15) == 0 && (lk >> slot_subnet(s) & 1)) obs_entry(e, r, 0, s, 1, 0, 0, 0); }
         }
@@ -1017,6 +1019,7 @@ static int exec_red(cc4o_env *e, int r, const act_t *a)
         int sv = -1;
         for (int i = 0; i < h->nsvc; i++) if (h->svcs[i].code == K_OT && h->svcs[i].active) sv = i;
         if (sv < 0) return SUCC_FALSE;
+        if (!S) return SUCC_FALSE;                      /* TargetedLocalAction.py:14-21 needs the acting session too */
         h->svcs[sv].active = 0;                         /* Host.stop_service Host.py:296-301 */
         int pi = find_proc(h, h->svcs[sv].pid);          /* State.remove_process State.py:390-418 */
         if (pi >= 0) {
@@ -1173,13 +1176,18 @@ int cc4o_step(cc4o_env *e, const int32_t *actions, const uint8_t *msgs, uint8_t 
     }
     /* 3+4. execute: priority-1 actions (Block/AllowTrafficZone) first, then agent order; actions whose session
        no longer exists are dropped :398-404, :466-486 */
+    uint8_t dropped[NAG];   /* filter_actions runs on the whole list BEFORE anything executes */
+    for (int k = 0; k < n_agents(e); k++) {
+        int a = agent_iter(e, k);
+        int sid = a < A_RED0 ? 0 : a < A_GREEN0 ? ex[a].session : 0;
+        dropped[a] = action_has_session(ex[a].code) && find_sess(e, a, sid) < 0;
+    }
     for (int pass = 0; pass < 2; pass++) {
         for (int k = 0; k < n_agents(e); k++) {
             int a = agent_iter(e, k);
             int prio1 = ex[a].code == AC_BLOCK || ex[a].code == AC_ALLOW;
             if ((pass == 0) != prio1) continue;
-            int sid = a < A_RED0 ? 0 : a < A_GREEN0 ? ex[a].session : 0;
-            if (action_has_session(ex[a].code) && find_sess(e, a, sid) < 0) continue;
+            if (dropped[a]) continue;
             if (a < A_RED0) exec_blue(e, a, &ex[a]);
             else if (a < A_GREEN0) { int s = exec_red(e, a - A_RED0, &ex[a]); obs_push(e, a - A_RED0, s, &ex[a]); }
             else e->green_succ[a - A_GREEN0] = exec_green(e, a - A_GREEN0, &ex[a]);
@@ -1251,7 +1259,14 @@ int cc4o_export(cc4o_env *e, int32_t *out, int cap)
         PUT(c); for (int s = 0; s < NSLOT; s++) if (e->hn_known[r][s]) PUT(s);
         PUT(e->sn_known[r]);
         PUT(e->n_ss[r]); for (int i = 0; i < e->n_ss[r]; i++) PUT(e->ss[r][i]);
-        PUT(e->n_fsm[r]); for (int i = 0; i < e->n_fsm[r]; i++) { PUT(e->fsm[r][i].slot); PUT(e->fsm[r][i].state); PUT(e->fsm[r][i].hn); }
+        {   /* FSM view AFTER the agent has digested this tick's observation (what get_action will do first thing next
+               tick, FiniteStateRedAgent.py:91-93); inactive agents are not asked (AgentInterface.py:133-136) */
+            static fsm_t sv[MAXFSM]; int sn_ = e->n_fsm[r], serr = e->err; char smsg[256];
+            memcpy(sv, e->fsm[r], sizeof sv); memcpy(smsg, e->errmsg, sizeof smsg);
+            if (e->active[a]) { fsm_transition(e, r); fsm_process_obs(e, r); fsm_session_removal(e, r); }
+            PUT(e->n_fsm[r]); for (int i = 0; i < e->n_fsm[r]; i++) { PUT(e->fsm[r][i].slot); PUT(e->fsm[r][i].state); PUT(e->fsm[r][i].hn); }
+            memcpy(e->fsm[r], sv, sizeof sv); e->n_fsm[r] = sn_; e->err = serr; memcpy(e->errmsg, smsg, sizeof smsg);
+        }
         /* ports sorted by (ident, slot) */
         int np = 0;
         for (int i = 0; i < e->nsess[a]; i++) if (e->sess[a][i].type == 1) for (int s = 0; s < NSLOT; s++) np += e->sess[a][i].has_ports[s];

@@ -333,7 +333,7 @@ class RefEpisode:
                     snk |= 1 << SUBNET_IDX[st.subnets_cidr_to_name[c]]
             ssk = [int(k) for k, v in asp.server_session.items() if v]
             fsm = []
-            for ip, hs in getattr(ai.agent, "host_states", {}).items():
+            for ip, hs in self._fsm_view(name).items():
                 slot = -1 if ip is None else host_slot(st.ip_addresses[ipaddress.IPv4Address(ip)])
                 fsm.append((slot, FSM_STATES.index(hs["state"]), int(hs["hostname"] is not None)))
             ports = []
@@ -358,6 +358,28 @@ class RefEpisode:
             blue.append(dict(sus=sus, inprog=_inprog(self.ctrl, name)))
         out["blue"] = blue
         return out
+
+    def _fsm_view(self, name: str) -> dict:
+        """FiniteStateRedAgent.host_states as it will be right after the agent digests this tick's observation
+        (the first thing get_action does next tick, FiniteStateRedAgent.py:91-93), computed with the reference's
+        own methods on a copy.  Inactive agents are not asked for an action (AgentInterface.py:133-136)."""
+        import copy
+        ai = self.ctrl.agent_interfaces[name]
+        agent = ai.agent
+        if not hasattr(agent, "host_states"):
+            return {}
+        if not ai.active:
+            return agent.host_states
+        twin = copy.copy(agent)
+        twin.host_states = copy.deepcopy(agent.host_states)
+        twin.host_service_decoy_status = copy.deepcopy(agent.host_service_decoy_status)
+        obs = copy.deepcopy(self.ctrl.get_last_observation(name).data)
+        success = obs.pop("success", None)
+        action = obs.pop("action", None)
+        twin._host_state_transition(action, success)
+        twin._process_new_observations(obs)
+        twin._session_removal_state_change(obs)
+        return twin.host_states
 
     def canon(self) -> list[int]:
         return encode(self.state())
