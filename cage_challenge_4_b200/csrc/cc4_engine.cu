@@ -1,0 +1,668 @@
+/*
+ * cc4_engine.cu — kernels and C-ABI (include/cc4_b200.h) of the B200-native batched CC4 step engine.
+ *
+ * Kernels (sm_100a, one warp per episode, the episode's packed record staged in shared memory):
+ *   k_reset   EnterpriseScenarioGenerator.create_scenario + State.__init__ + controller reset
+ *   k_step    one SimulationController.step tick for every episode (+ observation vectors, reward, done)
+ *   k_rollout n fused ticks with the benchmark's synthetic random blue policy (state stays in shared memory)
+ * Citations are file:line under /root/reference/CybORG/.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "cc4_device.cuh"
+
+namespace cc4 {
+
+constexpr int WARPS_PER_BLOCK = 4;
+constexpr int DYN_U4 = (int)(sizeof(Cc4Dyn) / 16);
+
+struct WarpSmem {
+    Cc4Dyn dyn;
+    Scratch x;
+};
+
+struct Params {
+    Cc4Dyn *dyn; Cc4Stat *stat;
+    int n_envs, steps, rng_mode;
+    uint32_t k0, k1hi; uint64_t first_episode;
+    const cc4_draw *tape; const uint32_t *seg_off; uint32_t n_segs;
+};
+
+/* ---- record movement: 128-bit coalesced ---- */
+__device__ __forceinline__ void w_load(Cc4Dyn *dst, const Cc4Dyn *src)
+{
+    const uint4 *g = reinterpret_cast<const uint4 *>(src);
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+#pragma unroll 4
+    for (int i = lane_id(); i < DYN_U4; i += 32) d[i] = __ldg(g + i);
+    __syncwarp();
+}
+__device__ __forceinline__ void w_store(Cc4Dyn *dst, const Cc4Dyn *src)
+{
+    __syncwarp();
+    const uint4 *d = reinterpret_cast<const uint4 *>(src);
+    uint4 *g = reinterpret_cast<uint4 *>(dst);
+#pragma unroll 4
+    for (int i = lane_id(); i < DYN_U4; i += 32) g[i] = d[i];
+}
+
+__device__ __forceinline__ void make_ctx(Ctx &c, WarpSmem *w, const Params &p, int env)
+{
+    uint64_t ep = p.first_episode + (uint64_t)env;
+    c.s = &w->dyn; c.x = &w->x; c.st = p.stat + env;
+    c.steps = p.steps; c.rng_mode = p.rng_mode;
+    c.k0 = p.k0; c.k1 = p.k1hi ^ (uint32_t)(ep >> 32); c.ep_lo = (uint32_t)ep;
+    c.tape = p.tape; c.seg = p.seg_off ? p.seg_off + (size_t)env * (p.n_segs + 1) : nullptr; c.n_segs = p.n_segs;
+    c.tick = 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* observation vectors: BlueFlatWrapper.observation_change BlueFlatWrapper.py:172-256 (lane per element) */
+/* ------------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ uint8_t obs_element(const Cc4Dyn *s, int b, int p)
+{
+    int nsub = b == 4 ? 3 : 1, body = 1 + 59 * nsub;
+    if (p == 0) return s->phase;
+    if (p < body) {
+        int q = p - 1, i = q / 59, o = q % 59, sn = blue_sorted_subnet(b, i);
+        if (o < 9) return c_sorted_subnets[o] == sn;
+        if (o < 18) return (s->blocks[sn] >> c_sorted_subnets[o - 9]) & 1;
+        if (o < 27) return !((c_comms_adj[s->phase][sn] >> c_sorted_subnets[o - 18]) & 1);
+        if (o < 43) { int h = sn * 16 + (o - 27); return host_exists(s, h) && (s->ev[h] & (EV_PROC | EV_OLDPROC)) != 0; }
+        int h = sn * 16 + (o - 43);
+        return host_exists(s, h) && (s->ev[h] & (EV_NET | EV_OLDNET)) != 0;
+    }
+    int q = p - body;
+    if (q >= 32) return 0;
+    int k = q >> 3, other = k < b ? k : k + 1;   /* the other four agents in sorted order, SimulationController.py:781-804 */
+    return (s->msgs[other] >> (q & 7)) & 1;
+}
+__device__ void w_write_obs(const Cc4Dyn *s, uint8_t *obs /* [5][210] of this episode */)
+{
+    /* 1050 bytes; 4 bytes per lane per iteration, written as one aligned 32-bit word (210*5 = 1050, base is 2-byte
+       aligned only for odd episodes, so use byte stores for the ragged tail) */
+    for (int i = lane_id(); i < CC4_N_BLUE * CC4_OBS_LEN; i += 32) obs[i] = obs_element(s, i / CC4_OBS_LEN, i % CC4_OBS_LEN);
+}
+__device__ void w_write_mask(const Cc4Dyn *s, uint8_t *mask)
+{
+    for (int i = lane_id(); i < CC4_N_BLUE * CC4_MASK_LEN; i += 32) {
+        int b = i / CC4_MASK_LEN, k = i % CC4_MASK_LEN, m = 0;
+        if (k < (b == 4 ? 242 : 82)) blue_decode(s, b, k, &m);
+        mask[i] = (uint8_t)m;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* end-turn Monitor for all five blue agents (Monitor.py:35-74), lane per host                      */
+/* ------------------------------------------------------------------------------------------------ */
+__device__ void w_monitor_all(Ctx &c)
+{
+    Cc4Dyn *s = c.s;
+    for (int h = lane_id(); h < CC4_NSLOT; h += 32) {
+        if (blue_of_subnet(slot_subnet(h)) < 0) continue;     /* contractor network and internet have no blue agent */
+        uint32_t e = s->ev[h];
+        s->ev[h] = (uint8_t)((e & (EV_PROC | EV_NET)) << 2);
+    }
+    __syncwarp();
+    if (lane_id() == 0) {
+        Scratch *x = c.x;
+        for (int i = 0; i < x->n_evpid; i++) {
+            int slot = x->evpid[i] >> 16, b = blue_of_subnet(slot_subnet(slot));
+            if (s->n_sus >= CC4_SUS_CAP) { fail(c, CC4_E_CAPACITY); break; }
+            s->sus[s->n_sus++] = SU_MAKE(x->evpid[i] & 0xFFFFu, slot, b);
+        }
+        x->n_evpid = 0;
+    }
+    __syncwarp();
+}
+/* a blue agent's own Monitor action (same code path, one agent) */
+__device__ void monitor_one(Ctx &c, int b)
+{
+    Cc4Dyn *s = c.s; Scratch *x = c.x;
+    for (int h = 0; h < CC4_NSLOT; h++) if (blue_of_subnet(slot_subnet(h)) == b) { uint32_t e = s->ev[h]; s->ev[h] = (uint8_t)((e & (EV_PROC | EV_NET)) << 2); }
+    int w = 0;
+    for (int i = 0; i < x->n_evpid; i++) {
+        int slot = x->evpid[i] >> 16;
+        if (blue_of_subnet(slot_subnet(slot)) != b) { x->evpid[w++] = x->evpid[i]; continue; }
+        if (s->n_sus >= CC4_SUS_CAP) { fail(c, CC4_E_CAPACITY); continue; }
+        s->sus[s->n_sus++] = SU_MAKE(x->evpid[i] & 0xFFFFu, slot, b);
+    }
+    x->n_evpid = w;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* one tick: SimulationController.step SimulationController.py:211-315                              */
+/* ------------------------------------------------------------------------------------------------ */
+__device__ void w_tick(Ctx &c, const int32_t *actions /* [5] */, const uint8_t *msgs /* [5] or null */, float *reward_out, uint8_t *done_out)
+{
+    Cc4Dyn *s = c.s; Scratch *x = c.x;
+    const int lane = lane_id();
+    c.tick = s->step;
+    for (int i = lane; i <= NAG; i += 32) x->ctr[i] = 0;
+    if (lane < 8) { x->n_oent[lane] = 0; x->have_first[lane] = 0; x->succ0[lane] = SUCC_UNKNOWN; x->has_act0[lane] = 0; }
+    if (lane == 0) { x->n_evpid = 0; x->reward = 0; }
+    __syncwarp();
+
+    Act sub[11];
+    int cost = 0;
+    if (lane == 0) {
+        /* mission phase: State.check_next_phase_on_update_step State.py:514-544, phases EnterpriseScenarioGenerator.py:854-860 */
+        int q = c.steps / 3, rem = c.steps % 3, l0 = q + (rem >= 1), l1 = q + (rem == 2);
+        int np = c.tick < l0 ? 0 : c.tick < l0 + l1 ? 1 : 2;
+        if (c.tick >= c.steps) fail(c, CC4_E_UNREACHABLE);
+        if (np > s->phase) s->phase = (uint8_t)np;
+    }
+    __syncwarp();
+
+    /* ---- 1. policies (:236-248).  green: lane per agent (EnterpriseGreenAgent.py:42-78); the whole green action is
+       resolved here except its phishing side effect, which is replayed in agent order below.  This is legal because
+       nothing a blue action does (executed before green) is visible to the draws themselves, but the OUTCOME of a green
+       action depends on blue's Restore / Block of the same tick, so the evaluation happens after the blue phase. ---- */
+    if (lane == 0) {
+        for (int b = 0; b < CC4_NBLUE; b++) { sub[b] = blue_decode(s, b, actions[b], nullptr); if (sub[b].code == AC_RESTORE) cost -= 1; }   /* Restore.py:70, :310-311 */
+        for (int r = 0; r < CC4_NRED; r++) {
+            Act a = { AC_SLEEP, -1, -1, 0 };
+            if (s->red_active >> r & 1) a = red_policy(c, r);
+            sub[A_RED0 + r] = a;
+        }
+        /* ---- 2. duration queue (:245-265) for blue and red; green actions always last one tick ---- */
+        for (int a = 0; a < 11; a++) {
+            uint32_t ip = s->inprog[a];
+            if (IP_CODE(ip) == IP_NONE) ip = IP_MAKE(sub[a].code, sub[a].host < 0 ? 255 : sub[a].host, sub[a].subnet < 0 ? 15 : sub[a].subnet, sub[a].session, c_duration[sub[a].code]);
+            int ticks = (int)IP_TICKS(ip) - 1;
+            if (ticks < 1) {
+                sub[a].code = IP_CODE(ip); sub[a].host = IP_HOST(ip) == 255 ? -1 : (int)IP_HOST(ip); sub[a].subnet = IP_SUBNET(ip) == 15 ? -1 : (int)IP_SUBNET(ip); sub[a].session = IP_SESSION(ip);
+                s->inprog[a] = IP_NONE;
+            } else {
+                s->inprog[a] = (ip & ~(0xFu << 26)) | (uint32_t)ticks << 26;
+                sub[a].code = AC_SLEEP; sub[a].host = sub[a].subnet = -1; sub[a].session = 0;
+                if (a >= A_RED0) { Act none = { AC_SLEEP, -1, -1, 0 }; obs_push(c, a - A_RED0, SUCC_INPROG, false, none); }
+            }
+            x->cur_code[a] = (uint8_t)sub[a].code;
+            if (a >= A_RED0) x->cur_host[a] = (uint8_t)(sub[a].host < 0 ? 255 : sub[a].host);
+        }
+        /* filter_actions (:466-486) looks at the sessions as they are BEFORE anything executes; blue / green sessions never go away */
+        for (int r = 0; r < CC4_NRED; r++) {
+            int code = sub[A_RED0 + r].code;
+            x->dropped[A_RED0 + r] = !(code == AC_SLEEP || code == AC_INVALID) && sess_find(s, r, sub[A_RED0 + r].session) < 0;
+        }
+        /* ---- 3. execution: priority-1 ControlTraffic first (ControlTraffic.py:19), then agent order ---- */
+        for (int pass = 0; pass < 2; pass++)
+            for (int b = 0; b < CC4_NBLUE; b++) {
+                bool prio1 = sub[b].code == AC_BLOCK || sub[b].code == AC_ALLOW;
+                if ((pass == 0) != prio1) continue;
+                if (sub[b].code == AC_MONITOR) monitor_one(c, b); else exec_blue(c, b, sub[b]);
+            }
+    }
+    __syncwarp();
+    /* green agents, lane per agent */
+    {
+        int rew = 0;
+        uint32_t *ev_words = reinterpret_cast<uint32_t *>(s->ev);
+        for (int g = lane; g < s->ngreen; g += 32) rew += green_tick(c, g, ev_words);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rew += __shfl_xor_sync(0xFFFFFFFFu, rew, o);
+        if (lane == 0) x->reward += rew;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int g = 0; g < s->ngreen; g++) if (x->green_phish[g]) do_phishing(c, g);
+        for (int r = 0; r < CC4_NRED; r++) {
+            int a = A_RED0 + r;
+            if (x->dropped[a]) continue;
+            int succ = exec_red(c, r, sub[a]);
+            obs_push(c, r, succ, true, sub[a]);
+        }
+        /* ---- 4. reassignment (:278) ---- */
+        reassign(c);
+    }
+    __syncwarp();
+    /* ---- 5. end-turn actions (:281-286): Monitor for blue, RedSessionCheck for active red ---- */
+    w_monitor_all(c);
+    if (lane == 0) {
+        for (int r = 0; r < CC4_NRED; r++) if (s->red_active >> r & 1) red_session_check(c, r);
+        /* the FSM agents digest the tick's observation now instead of at the start of the next tick */
+        for (int r = 0; r < CC4_NRED; r++) if (s->red_active >> r & 1) fsm_digest(c, r);
+        /* ---- 6. counters, done (:297-300), reward (BlueRewardMachine.py:70-121) ---- */
+        s->step++;
+        s->done = s->step >= c.steps - 1;
+        int rew = x->reward;
+        for (int r = 0; r < CC4_NRED; r++) {
+            /* `success and isinstance(action, Impact)` BlueRewardMachine.py:118: a TernaryEnum member is always truthy
+               (Enums.py:5-24), so every Impact that comes due costs RIA while the agent holds a session */
+            if (x->cur_code[A_RED0 + r] == AC_IMPACT && (s->red_active >> r & 1)) rew += c_reward[s->phase][x->cur_host[A_RED0 + r] >> 4][2];
+        }
+        for (int b = 0; b < CC4_NBLUE; b++) s->msgs[b] = msgs ? msgs[b] : 0;
+        if (reward_out) *reward_out = (float)(rew + cost);
+        if (done_out) *done_out = s->done;
+        if (c.rng_mode == 1) {
+            for (int a = 0; a < NAG; a++) {
+                uint32_t seg = 1u + (uint32_t)c.tick * NAG + (uint32_t)a;
+                if (seg < c.n_segs && x->ctr[a] != c.seg[seg + 1] - c.seg[seg]) fail(c, CC4_E_TAPE_LEFT);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* kernels                                                                                          */
+/* ------------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_step(Params p, const int32_t *actions, const uint8_t *msgs, uint8_t *obs, float *reward, uint8_t *done, int flags)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpSmem *w = reinterpret_cast<WarpSmem *>(smem_raw) + (threadIdx.x >> 5);
+    int env = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (env >= p.n_envs) return;
+    Ctx c; make_ctx(c, w, p, env);
+    w_load(&w->dyn, p.dyn + env);
+    w_tick(c, actions + (size_t)env * 5, msgs ? msgs + (size_t)env * 5 : nullptr,
+           (flags & CC4_STEP_REWARD) && reward ? reward + env : nullptr, done ? done + env : nullptr);
+    if ((flags & CC4_STEP_OBS) && obs) w_write_obs(&w->dyn, obs + (size_t)env * CC4_N_BLUE * CC4_OBS_LEN);
+    w_store(p.dyn + env, &w->dyn);
+}
+
+/* fused ticks with the benchmark's synthetic blue policy: index ~ U{0..81} (agents 0-3) / U{0..241} (agent 4),
+ * Philox keyed (policy_seed, episode, tick) exactly as oracle/cc4_oracle.c cc4o_run_episodes */
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_rollout(Params p, int n_ticks, uint32_t pk0, uint32_t pk1, float *reward_sum, int flags)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpSmem *w = reinterpret_cast<WarpSmem *>(smem_raw) + (threadIdx.x >> 5);
+    int env = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (env >= p.n_envs) return;
+    Ctx c; make_ctx(c, w, p, env);
+    w_load(&w->dyn, p.dyn + env);
+    uint64_t ep = p.first_episode + (uint64_t)env;
+    float total = 0.f;
+    __shared__ int32_t act_s[WARPS_PER_BLOCK][8];
+    __shared__ float rew_s[WARPS_PER_BLOCK];
+    int32_t *act = act_s[threadIdx.x >> 5];
+    for (int t = 0; t < n_ticks; t++) {
+        if (w->dyn.done) break;
+        if (lane_id() == 0) {
+            uint32_t tk = w->dyn.step;
+            uint32_t c1[4] = { tk, 0xB10Eu, (uint32_t)ep, (uint32_t)(ep >> 32) }, c2[4] = { tk, 0xB10Fu, (uint32_t)ep, (uint32_t)(ep >> 32) };
+            philox4x32_10(c1, pk0, pk1); philox4x32_10(c2, pk0, pk1);
+            for (int b = 0; b < 4; b++) act[b] = (int32_t)__umulhi(c1[b], 82u);
+            act[4] = (int32_t)__umulhi(c2[0], 242u);
+        }
+        __syncwarp();
+        w_tick(c, act, nullptr, &rew_s[threadIdx.x >> 5], nullptr);
+        if (lane_id() == 0) total += rew_s[threadIdx.x >> 5];
+    }
+    if ((flags & CC4_STEP_REWARD) && reward_sum && lane_id() == 0) reward_sum[env] += total;
+    w_store(p.dyn + env, &w->dyn);
+}
+
+/* ---- reset ---- */
+struct ResetTmp {
+    uint32_t procs[128][8];
+    uint8_t np[128];
+    uint32_t used[288];          /* bitmap over pids 1000..9999, EnterpriseScenarioGenerator._generate_pid :563-578 */
+    uint16_t router_pid[16];
+};
+struct ResetSmem {
+    Cc4Dyn dyn;
+    Scratch x;
+    ResetTmp t;
+};
+
+__device__ int gen_pid(Ctx &c, ResetTmp *t)
+{
+    for (int guard = 0; guard < 64; guard++) {
+        int v = (int)rng_int(c, NAG, ST_R_PID, 9000);
+        if (c.s->err & CC4_E_TAPE_END) return 1000 + v;
+        if (!(t->used[v >> 5] >> (v & 31) & 1)) { t->used[v >> 5] |= 1u << (v & 31); return 1000 + v; }
+    }
+    fail(c, CC4_E_CAPACITY);
+    return 1000;
+}
+__device__ void gen_host(Ctx &c, ResetTmp *t, int slot)
+{   /* _generate_linux_host_services :530-561 + _generate_linux_host_processes :580-629 */
+    Cc4Dyn *s = c.s;
+    int sn = slot >> 4, n = 0;
+    uint64_t v = SVC_EMPTY;
+    uint32_t pids[9]; int codes[9];
+    codes[n] = K_SSHD; pids[n++] = gen_pid(c, t);
+    if (sn == S_OZA || sn == S_OZB) { codes[n] = K_OT; pids[n++] = gen_pid(c, t); }
+    int opt[3] = { K_APACHE2, K_MYSQLD, K_SMTP }, nopt = 3; uint32_t optpid[3];
+    for (int i = 0; i < 3; i++) optpid[i] = gen_pid(c, t);
+    int nadd = (int)rng_int(c, NAG, ST_R_NADDON, 4);
+    for (int i = 0; i < nadd; i++) {
+        int k = (int)rng_int(c, NAG, ST_R_ADDON, (uint32_t)nopt);
+        codes[n] = opt[k]; pids[n++] = optpid[k];
+        for (int j = k; j + 1 < nopt; j++) { opt[j] = opt[j + 1]; optpid[j] = optpid[j + 1]; }
+        nopt--;
+    }
+    for (int i = 0; i < n; i++) { v = svc_set(v, i, (uint32_t)codes[i] | 5u << 4); t->procs[slot][i] = P_MAKE(pids[i], codes[i], 0, 1); }
+    t->np[slot] = (uint8_t)n;
+    s->svc64[slot] = v;
+}
+__device__ int tmp_create_pid(Ctx &c, ResetTmp *t, int slot)
+{
+    uint32_t mx = 0;
+    for (int i = 0; i < t->np[slot]; i++) if (P_PID(t->procs[slot][i]) > mx) mx = P_PID(t->procs[slot][i]);
+    return (int)(mx + 1 + rng_int(c, NAG, ST_CREATE_PID, 9));
+}
+__device__ void tmp_add_session_proc(Ctx &c, ResetTmp *t, int slot, int kind)
+{
+    if (slot >= CC4_SLOT_ROUTER) { t->router_pid[slot - CC4_SLOT_ROUTER] = (uint16_t)(1 + rng_int(c, NAG, ST_CREATE_PID, 9)); return; }
+    int pid = tmp_create_pid(c, t, slot);
+    t->procs[slot][t->np[slot]++] = P_MAKE(pid, kind, 0, 0);
+}
+
+__global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *mask)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ResetSmem *w = reinterpret_cast<ResetSmem *>(smem_raw);
+    int env = blockIdx.x;
+    if (env >= p.n_envs) return;
+    Ctx c; c.s = &w->dyn; c.x = &w->x; c.st = p.stat + env;
+    {
+        uint64_t ep = p.first_episode + (uint64_t)env;
+        c.steps = p.steps; c.rng_mode = p.rng_mode; c.k0 = p.k0; c.k1 = p.k1hi ^ (uint32_t)(ep >> 32); c.ep_lo = (uint32_t)ep;
+        c.tape = p.tape; c.seg = p.seg_off ? p.seg_off + (size_t)env * (p.n_segs + 1) : nullptr; c.n_segs = p.n_segs; c.tick = -1;
+    }
+    uint32_t *z = reinterpret_cast<uint32_t *>(w);
+    for (int i = lane_id(); i < (int)(sizeof(ResetSmem) / 4); i += 32) z[i] = 0;
+    __syncwarp();
+    if (lane_id() == 0) {
+        Cc4Dyn *s = c.s; ResetTmp *t = &w->t; Cc4Stat *st = c.st;
+        for (int h = 0; h < 128; h++) s->svc64[h] = SVC_EMPTY;
+        for (int a = 0; a < 16; a++) s->inprog[a] = IP_NONE;
+        /* hosts, EnterpriseScenarioGenerator._generate_hosts :312-371 */
+        for (int sn = 0; sn < 8; sn++) {
+            s->nuser[sn] = (uint8_t)(3 + rng_int(c, NAG, ST_R_NUSER, 8));
+            for (int i = 0; i < s->nuser[sn]; i++) gen_host(c, t, sn * 16 + 6 + i);
+            s->nserver[sn] = (uint8_t)(1 + rng_int(c, NAG, ST_R_NSERVER, 6));
+            for (int i = 0; i < s->nserver[sn]; i++) gen_host(c, t, sn * 16 + i);
+        }
+        /* blue agents :631-698 */
+        for (int b = 0; b < CC4_NBLUE; b++) {
+            int n = 0;
+            for (int i = 0; i < (b == 4 ? 3 : 1); i++) { int sn = b < 4 ? b : S_PAZ + i; n += 1 + s->nuser[sn] + s->nserver[sn]; }
+            int pk = (int)rng_int(c, NAG, ST_R_BLUE_PARENT, (uint32_t)n), parent = -1;
+            for (int i = 0, k = 0; i < (b == 4 ? 3 : 1) && parent < 0; i++) {
+                int sn = b < 4 ? b : S_PAZ + i, nu = s->nuser[sn], m = 1 + nu + s->nserver[sn];
+                if (pk < k + m) { int j = pk - k; parent = j == 0 ? CC4_SLOT_ROUTER + sn : j <= nu ? sn * 16 + 6 + (j - 1) : sn * 16 + (j - 1 - nu); }
+                k += m;
+            }
+            st->blue_parent[b] = (uint8_t)parent;
+        }
+        /* green agents :700-749 */
+        int ng = 0;
+        for (int sn = 0; sn < 8; sn++) for (int k = 0; k < s->nuser[sn]; k++) s->green_host[ng++] = (uint8_t)(sn * 16 + 6 + k);
+        s->ngreen = (uint8_t)ng;
+        /* red agents :751-812 */
+        for (int r = 0; r < CC4_NRED; r++) {
+            int ns = r == 5 ? 3 : 1;
+            int si = (int)rng_int(c, NAG, ST_R_RED_SUBNET, (uint32_t)ns);
+            int sn = r == 0 ? S_CON : r <= 4 ? r - 1 : S_PAZ + si;
+            int k = (int)rng_int(c, NAG, ST_R_RED_HOST, (uint32_t)(s->nuser[sn] + s->nserver[sn]));
+            st->red_start[r] = (uint8_t)(k < s->nuser[sn] ? sn * 16 + 6 + k : sn * 16 + (k - s->nuser[sn]));
+        }
+        /* State.__init__ State.py:108-134: session processes (Host.add_session Host.py:189-196) */
+        for (int b = 0; b < CC4_NBLUE; b++) {
+            tmp_add_session_proc(c, t, st->blue_parent[b], K_SESSION);
+            for (int i = 0; i < (b == 4 ? 3 : 1); i++) {
+                int sn = b < 4 ? b : S_PAZ + i;
+                if (st->blue_parent[b] != CC4_SLOT_ROUTER + sn) tmp_add_session_proc(c, t, CC4_SLOT_ROUTER + sn, K_SESSION);
+                for (int k = 0; k < s->nuser[sn]; k++) if (st->blue_parent[b] != sn * 16 + 6 + k) tmp_add_session_proc(c, t, sn * 16 + 6 + k, K_SESSION);
+                for (int k = 0; k < s->nserver[sn]; k++) if (st->blue_parent[b] != sn * 16 + k) tmp_add_session_proc(c, t, sn * 16 + k, K_SESSION);
+            }
+        }
+        for (int g = 0; g < ng; g++) tmp_add_session_proc(c, t, s->green_host[g], K_SESSION);
+        {
+            int h = st->red_start[0], pid = tmp_create_pid(c, t, h);
+            t->procs[h][t->np[h]++] = P_MAKE(pid, K_REDABS, 0, 0);
+            s->sess[0] = S_MAKE(pid, 0, h); s->sessf[0] = (uint8_t)(0 | 1 << 3); s->n_sess = 1; s->sess_count[0] = 1; s->red_active = 1;
+        }
+        /* pack the CSR pool in slot order; Host.create_backup Host.py:316-371 */
+        int tot = 0;
+        for (int h = 0; h < 128; h++) { s->pstart[h] = (uint16_t)tot; for (int i = 0; i < t->np[h]; i++) s->procs[tot++] = t->procs[h][i]; }
+        s->pstart[128] = (uint16_t)tot;
+        for (int i = 0; i < tot; i++) st->o_procs[i] = s->procs[i];
+        for (int h = 0; h <= 128; h++) st->o_pstart[h] = s->pstart[h];
+        for (int h = 0; h < 128; h++) st->o_svc64[h] = s->svc64[h];
+        for (int i = 0; i < 16; i++) st->router_pid[i] = t->router_pid[i];
+        /* initial knowledge: AgentInterface.set_init_obs AgentInterface.py:110-117 with the OSINT of :784-785 */
+        for (int r = 0; r < CC4_NRED; r++) { int h = st->red_start[r]; set128(s->ip_known[r], h); set128(s->hn_known[r], h); s->sn_known[r] |= (uint16_t)(1u << (h >> 4)); }
+        s->ss[0][0] = 0; s->n_ss[0] = 1;
+        /* red_agent_0 digests its initial observation (its start host becomes 'U', FiniteStateRedAgent.py:221-224) */
+        s->fsm[0][0] = F_MAKE(st->red_start[0], 1, F_U); s->n_fsm[0] = 1; s->fsm_started = 1;
+        if (c.rng_mode == 1 && c.n_segs > 0 && c.x->ctr[NAG] != c.seg[1] - c.seg[0]) fail(c, CC4_E_TAPE_LEFT);
+    }
+    __syncwarp();
+    if (obs) w_write_obs(&w->dyn, obs + (size_t)env * CC4_N_BLUE * CC4_OBS_LEN);
+    if (mask) w_write_mask(&w->dyn, mask + (size_t)env * CC4_N_BLUE * CC4_MASK_LEN);
+    w_store(p.dyn + env, &w->dyn);
+}
+
+}  // namespace cc4
+
+/* ================================================================================================ */
+/* host side: C-ABI                                                                                 */
+/* ================================================================================================ */
+using namespace cc4;
+
+static thread_local char g_err[512];
+static int set_err(int code, const char *fmt, const char *detail)
+{
+    snprintf(g_err, sizeof g_err, fmt, detail);
+    return code;
+}
+#define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return set_err(CC4_ERR_CUDA, #expr ": %s", cudaGetErrorString(e_)); } while (0)
+
+struct cc4_handle {
+    Params p;
+    int device;
+    uint64_t launches;
+    int32_t *stage_actions; uint8_t *stage_msgs, *stage_obs, *stage_done; float *stage_reward;   /* device staging for cc4_step_host */
+};
+
+extern "C" const char *cc4_last_error(void) { return g_err; }
+
+extern "C" int cc4_create(int n_envs, int device, uint64_t seed, uint64_t first_episode, int steps, int rng_mode, cc4_handle **out)
+{
+    if (!out || n_envs <= 0 || steps < 3 || steps > 60000 || (rng_mode != 0 && rng_mode != 1)) return set_err(CC4_ERR_ARG, "cc4_create: bad argument%s", "");
+    CUDA_TRY(cudaSetDevice(device));
+    cc4_handle *h = new (std::nothrow) cc4_handle();
+    if (!h) return set_err(CC4_ERR_STATE, "cc4_create: out of host memory%s", "");
+    memset(h, 0, sizeof *h);
+    h->device = device;
+    h->p.n_envs = n_envs; h->p.steps = steps; h->p.rng_mode = rng_mode;
+    h->p.k0 = (uint32_t)seed; h->p.k1hi = (uint32_t)(seed >> 32); h->p.first_episode = first_episode;
+    CUDA_TRY(cudaMalloc(&h->p.dyn, sizeof(Cc4Dyn) * (size_t)n_envs));
+    CUDA_TRY(cudaMalloc(&h->p.stat, sizeof(Cc4Stat) * (size_t)n_envs));
+    CUDA_TRY(cudaMemset(h->p.dyn, 0, sizeof(Cc4Dyn) * (size_t)n_envs));
+    CUDA_TRY(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * WARPS_PER_BLOCK)));
+    CUDA_TRY(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * WARPS_PER_BLOCK)));
+    CUDA_TRY(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResetSmem)));
+    *out = h;
+    return CC4_OK;
+}
+
+extern "C" int cc4_destroy(cc4_handle *h)
+{
+    if (!h) return CC4_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->p.dyn); cudaFree(h->p.stat);
+    cudaFree(h->stage_actions); cudaFree(h->stage_msgs); cudaFree(h->stage_obs); cudaFree(h->stage_done); cudaFree(h->stage_reward);
+    delete h;
+    return CC4_OK;
+}
+
+extern "C" int cc4_state_bytes(cc4_handle *h, size_t *dyn_bytes, size_t *stat_bytes)
+{
+    (void)h;
+    if (dyn_bytes) *dyn_bytes = sizeof(Cc4Dyn);
+    if (stat_bytes) *stat_bytes = sizeof(Cc4Stat);
+    return CC4_OK;
+}
+
+extern "C" int cc4_set_tape(cc4_handle *h, const cc4_draw *recs_dev, const uint32_t *seg_off_dev, uint32_t n_segs)
+{
+    if (!h) return set_err(CC4_ERR_ARG, "cc4_set_tape: null handle%s", "");
+    h->p.tape = recs_dev; h->p.seg_off = seg_off_dev; h->p.n_segs = n_segs;
+    return CC4_OK;
+}
+
+extern "C" int cc4_reset(cc4_handle *h, uint8_t *obs_dev, uint8_t *mask_dev, void *stream)
+{
+    if (!h) return set_err(CC4_ERR_ARG, "cc4_reset: null handle%s", "");
+    if (h->p.rng_mode == 1 && !h->p.tape) return set_err(CC4_ERR_STATE, "cc4_reset: tape mode without cc4_set_tape%s", "");
+    CUDA_TRY(cudaSetDevice(h->device));
+    k_reset<<<h->p.n_envs, 32, sizeof(ResetSmem), (cudaStream_t)stream>>>(h->p, obs_dev, mask_dev);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CC4_OK;
+}
+
+extern "C" int cc4_step(cc4_handle *h, const int32_t *actions_dev, const uint8_t *msgs_dev, uint8_t *obs_dev, float *reward_dev,
+                        uint8_t *done_dev, int flags, void *stream)
+{
+    if (!h || !actions_dev) return set_err(CC4_ERR_ARG, "cc4_step: null handle or actions%s", "");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int blocks = (h->p.n_envs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * WARPS_PER_BLOCK, (cudaStream_t)stream>>>(h->p, actions_dev, msgs_dev, obs_dev, reward_dev, done_dev, flags);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CC4_OK;
+}
+
+extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const uint8_t *msgs_host, uint8_t *obs_host, float *reward_host,
+                             uint8_t *done_host, int flags, void *stream)
+{
+    if (!h || !actions_host) return set_err(CC4_ERR_ARG, "cc4_step_host: null handle or actions%s", "");
+    CUDA_TRY(cudaSetDevice(h->device));
+    size_t n = (size_t)h->p.n_envs;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!h->stage_actions) {
+        CUDA_TRY(cudaMalloc(&h->stage_actions, n * 5 * sizeof(int32_t)));
+        CUDA_TRY(cudaMalloc(&h->stage_msgs, n * 5));
+        CUDA_TRY(cudaMalloc(&h->stage_obs, n * CC4_N_BLUE * CC4_OBS_LEN));
+        CUDA_TRY(cudaMalloc(&h->stage_done, n));
+        CUDA_TRY(cudaMalloc(&h->stage_reward, n * sizeof(float)));
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->stage_actions, actions_host, n * 5 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (msgs_host) CUDA_TRY(cudaMemcpyAsync(h->stage_msgs, msgs_host, n * 5, cudaMemcpyHostToDevice, st));
+    int rc = cc4_step(h, h->stage_actions, msgs_host ? h->stage_msgs : nullptr, obs_host ? h->stage_obs : nullptr,
+                      reward_host ? h->stage_reward : nullptr, done_host ? h->stage_done : nullptr, flags, stream);
+    if (rc) return rc;
+    if (obs_host && (flags & CC4_STEP_OBS)) CUDA_TRY(cudaMemcpyAsync(obs_host, h->stage_obs, n * CC4_N_BLUE * CC4_OBS_LEN, cudaMemcpyDeviceToHost, st));
+    if (reward_host && (flags & CC4_STEP_REWARD)) CUDA_TRY(cudaMemcpyAsync(reward_host, h->stage_reward, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host, h->stage_done, n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return CC4_OK;
+}
+
+extern "C" int cc4_rollout(cc4_handle *h, int n_ticks, uint64_t policy_seed, float *reward_sum_dev, int flags, void *stream)
+{
+    if (!h || n_ticks < 0) return set_err(CC4_ERR_ARG, "cc4_rollout: bad argument%s", "");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int blocks = (h->p.n_envs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    k_rollout<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * WARPS_PER_BLOCK, (cudaStream_t)stream>>>(
+        h->p, n_ticks, (uint32_t)policy_seed ^ 0x5EEDu, (uint32_t)(policy_seed >> 32), reward_sum_dev, flags);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CC4_OK;
+}
+
+extern "C" int cc4_launch_count(cc4_handle *h, uint64_t *out)
+{
+    if (!h || !out) return set_err(CC4_ERR_ARG, "cc4_launch_count: null%s", "");
+    *out = h->launches;
+    return CC4_OK;
+}
+
+extern "C" int cc4_error_flags(cc4_handle *h, uint32_t *out_host)
+{
+    if (!h || !out_host) return set_err(CC4_ERR_ARG, "cc4_error_flags: null%s", "");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy2D(out_host, sizeof(uint32_t), reinterpret_cast<const char *>(h->p.dyn) + offsetof(Cc4Dyn, err), sizeof(Cc4Dyn),
+                          sizeof(uint32_t), (size_t)h->p.n_envs, cudaMemcpyDeviceToHost));
+    return CC4_OK;
+}
+
+/* canonical export (layout: oracle/canon.py); decoding the packed record on the host */
+extern "C" int cc4_export_canon(cc4_handle *h, int env, int32_t *out, int cap, int *n_out)
+{
+    if (!h || !out || !n_out || env < 0 || env >= h->p.n_envs) return set_err(CC4_ERR_ARG, "cc4_export_canon: bad argument%s", "");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    static thread_local Cc4Dyn d; static thread_local Cc4Stat st;
+    CUDA_TRY(cudaMemcpy(&d, h->p.dyn + env, sizeof d, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&st, h->p.stat + env, sizeof st, cudaMemcpyDeviceToHost));
+    int n = 0;
+#define PUT(v) do { if (n < cap) out[n] = (int32_t)(v); n++; } while (0)
+    PUT(d.phase); PUT(d.step);
+    for (int s = 0; s < 9; s++) PUT(d.blocks[s]);
+    int nh = 9;
+    for (int sn = 0; sn < 8; sn++) nh += d.nuser[sn] + d.nserver[sn];
+    PUT(nh);
+    for (int slot = 0; slot < CC4_NSLOT; slot++) {
+        if (slot < 128) {
+            int sn = slot >> 4, k = slot & 15;
+            if (!(k < 6 ? k < d.nserver[sn] : (k - 6) < d.nuser[sn])) continue;
+            PUT(slot); PUT(d.ev[slot]);
+            int np = 0;
+            for (int i = d.pstart[slot]; i < d.pstart[slot + 1]; i++) np += !P_DEAD(d.procs[i]);
+            PUT(np);
+            for (int i = d.pstart[slot]; i < d.pstart[slot + 1]; i++) { uint32_t w = d.procs[i]; if (P_DEAD(w)) continue; PUT(P_PID(w)); PUT(P_KIND(w)); PUT(P_ROOT(w)); }
+            uint64_t v = d.svc64[slot];
+            int ns = 0; while (ns < 9 && (SVC_ENTRY(v, ns) & 15u) != 15u) ns++;
+            PUT(ns);
+            for (int i = 0; i < ns; i++) {
+                uint32_t e = SVC_ENTRY(v, i), code = e & 15u, pid = 0;
+                for (int j = d.pstart[slot]; j < d.pstart[slot + 1]; j++) if (P_KIND(d.procs[j]) == code && P_SVC(d.procs[j])) pid = P_PID(d.procs[j]);
+                PUT(code); PUT(pid); PUT(!(code == K_OT && (v & SVC_OT_STOPPED))); PUT((e >> 4) * 20);
+            }
+        } else {
+            PUT(slot); PUT(d.ev[slot]);
+            int pid = slot < CC4_SLOT_INTERNET ? st.router_pid[slot - CC4_SLOT_ROUTER] : 0;
+            if (pid) { PUT(1); PUT(pid); PUT(K_SESSION); PUT(0); } else PUT(0);
+            PUT(0);
+        }
+    }
+    for (int r = 0; r < CC4_NRED; r++) {
+        int ns = 0;
+        for (int i = 0; i < d.n_sess; i++) ns += SF_AGENT(d.sessf[i]) == (uint32_t)r;
+        PUT(d.red_active >> r & 1); PUT(d.sess_count[r]); PUT(ns);
+        for (int i = 0; i < d.n_sess; i++) if (SF_AGENT(d.sessf[i]) == (uint32_t)r) { PUT(S_ID(d.sess[i])); PUT(S_HOST(d.sess[i])); PUT(SF_ABS(d.sessf[i])); PUT(SF_ROOT(d.sessf[i])); PUT(S_PID(d.sess[i])); }
+        int cnt = 0; for (int s = 0; s < 128; s++) cnt += (d.ip_known[r][s >> 5] >> (s & 31)) & 1;
+        PUT(cnt); for (int s = 0; s < 128; s++) if ((d.ip_known[r][s >> 5] >> (s & 31)) & 1) PUT(s);
+        cnt = 0; for (int s = 0; s < 128; s++) cnt += (d.hn_known[r][s >> 5] >> (s & 31)) & 1;
+        PUT(cnt); for (int s = 0; s < 128; s++) if ((d.hn_known[r][s >> 5] >> (s & 31)) & 1) PUT(s);
+        PUT(d.sn_known[r]);
+        PUT(d.n_ss[r]); for (int i = 0; i < d.n_ss[r]; i++) PUT(d.ss[r][i]);
+        PUT(d.n_fsm[r]); for (int i = 0; i < d.n_fsm[r]; i++) { PUT(F_SLOT(d.fsm[r][i])); PUT(F_STATE(d.fsm[r][i])); PUT(F_HN(d.fsm[r][i])); }
+        /* ports sorted by (ident, slot) */
+        int np = 0;
+        for (int i = 0; i < d.n_ports; i++) np += PT_AGENT(d.ports[i]) == (uint32_t)r;
+        PUT(np);
+        for (int id = 0; id < 256; id++) for (int s = 0; s < 128; s++) for (int i = 0; i < d.n_ports; i++) {
+            uint32_t w = d.ports[i];
+            if (PT_AGENT(w) == (uint32_t)r && PT_ID(w) == (uint32_t)id && PT_HOST(w) == (uint32_t)s) { PUT(id); PUT(s); PUT(PT_MASK(w)); }
+        }
+        uint32_t ip = d.inprog[A_RED0 + r];
+        if (IP_CODE(ip) == IP_NONE) { PUT(-1); PUT(0); } else { PUT(IP_CODE(ip)); PUT(IP_TICKS(ip)); }
+    }
+    for (int b = 0; b < CC4_NBLUE; b++) {
+        int cnt = 0;
+        for (int i = 0; i < d.n_sus; i++) cnt += SU_AGENT(d.sus[i]) == (uint32_t)b;
+        PUT(cnt);
+        for (int s = 0; s < CC4_NSLOT; s++) for (int i = 0; i < d.n_sus; i++) if (SU_AGENT(d.sus[i]) == (uint32_t)b && SU_SLOT(d.sus[i]) == (uint32_t)s) { PUT(s); PUT(SU_PID(d.sus[i])); }
+        uint32_t ip = d.inprog[b];
+        if (IP_CODE(ip) == IP_NONE) { PUT(-1); PUT(0); } else { PUT(IP_CODE(ip)); PUT(IP_TICKS(ip)); }
+    }
+#undef PUT
+    *n_out = n;
+    return CC4_OK;
+}

@@ -1,0 +1,126 @@
+"""Batched CC4 environment: N concurrent episodes stepped by the CUDA engine through the C-ABI.
+
+Mirrors the call surface of the reference's wrapped environment
+(CybORG/Agents/Wrappers/BlueFlatWrapper.py:61 reset, :80 step) with a leading batch dimension:
+    reset() -> obs uint8 [N,5,210], mask bool [N,5,242]
+    step(actions int32 [N,5], messages uint8 [N,5]) -> obs, reward float32 [N], done bool [N]
+Agents 0-3 use the first 92 observation entries / 82 actions (BlueFlatWrapper.py:128-170,
+BlueFixedActionWrapper.py:233-309); agent 4 uses 210 / 242.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native
+
+N_BLUE, OBS_LEN, MASK_LEN = 5, 210, 242
+N_ACTIONS = (82, 82, 82, 82, 242)
+OBS_SIZES = (92, 92, 92, 92, 210)
+SLEEP_INDEX = (49, 49, 49, 49, 145)
+STEP_OBS, STEP_REWARD, STEP_ALL = 1, 2, 3
+DRAW_DTYPE = np.dtype([("val", "<u8"), ("n", "<u2"), ("site", "u1"), ("kind", "u1"), ("pad", "<u4")])
+
+
+class BatchedCC4:
+    """N independent CC4 episodes on one GPU.  Episode i draws from the RNG stream (seed, first_episode + i)."""
+
+    def __init__(self, num_envs: int, device: int | str | torch.device = 0, seed: int = 0, steps: int = 500,
+                 first_episode: int = 0, rng: str = "philox"):
+        if not torch.cuda.is_available():
+            raise _native.NativeError("BatchedCC4 needs a CUDA device (there is no CPU fallback)")
+        self._L = _native.load()
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.num_envs, self.steps, self.seed, self.first_episode = int(num_envs), int(steps), int(seed), int(first_episode)
+        self.rng = rng
+        h = C.c_void_p()
+        _native.check(self._L.cc4_create(self.num_envs, self.device.index or 0, self.seed & (2**64 - 1), self.first_episode,
+                                         self.steps, 1 if rng == "tape" else 0, C.byref(h)), "cc4_create")
+        self._h = h
+        n = self.num_envs
+        self.obs = torch.zeros((n, N_BLUE, OBS_LEN), dtype=torch.uint8, device=self.device)
+        self.mask = torch.zeros((n, N_BLUE, MASK_LEN), dtype=torch.uint8, device=self.device)
+        self.reward = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        self._tape = None
+        self._pinned = None
+
+    # -- life cycle --------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cc4_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- API ---------------------------------------------------------------------------------------
+    def state_bytes(self) -> tuple[int, int]:
+        d, s = C.c_size_t(), C.c_size_t()
+        _native.check(self._L.cc4_state_bytes(self._h, C.byref(d), C.byref(s)), "cc4_state_bytes")
+        return d.value, s.value
+
+    def set_tape(self, recs: np.ndarray, seg_off: np.ndarray):
+        """recs: DRAW_DTYPE [R]; seg_off uint32 [N, n_segs + 1] absolute offsets (tape mode)."""
+        assert recs.dtype == DRAW_DTYPE and seg_off.dtype == np.uint32 and seg_off.shape[0] == self.num_envs
+        recs_t = torch.from_numpy(recs.view(np.uint8).reshape(-1).copy()).to(self.device)
+        seg_t = torch.from_numpy(seg_off.astype(np.int64)).to(torch.int32).to(self.device)  # same bits as uint32
+        seg_t = torch.from_numpy(seg_off.view(np.int32).copy()).to(self.device)
+        self._tape = (recs_t, seg_t)
+        _native.check(self._L.cc4_set_tape(self._h, recs_t.data_ptr(), seg_t.data_ptr(), seg_off.shape[1] - 1), "cc4_set_tape")
+
+    def reset(self):
+        _native.check(self._L.cc4_reset(self._h, self.obs.data_ptr(), self.mask.data_ptr(), self._stream()), "cc4_reset")
+        return self.obs, self.mask.bool()
+
+    def step(self, actions: torch.Tensor, messages: torch.Tensor | None = None, flags: int = STEP_ALL):
+        assert actions.dtype == torch.int32 and actions.is_cuda and actions.shape == (self.num_envs, N_BLUE) and actions.is_contiguous()
+        mp = 0
+        if messages is not None:
+            assert messages.dtype == torch.uint8 and messages.is_cuda and messages.shape == (self.num_envs, N_BLUE) and messages.is_contiguous()
+            mp = messages.data_ptr()
+        _native.check(self._L.cc4_step(self._h, actions.data_ptr(), mp, self.obs.data_ptr(), self.reward.data_ptr(),
+                                       self.done.data_ptr(), flags, self._stream()), "cc4_step")
+        return self.obs, self.reward, self.done
+
+    def step_host(self, actions: np.ndarray | torch.Tensor, messages=None, flags: int = STEP_ALL):
+        """The same tick with HOST buffers (pinned torch tensors or numpy arrays): H2D + kernel + D2H + sync inside."""
+        n = self.num_envs
+        if self._pinned is None:
+            self._pinned = dict(obs=torch.zeros((n, N_BLUE, OBS_LEN), dtype=torch.uint8).pin_memory(),
+                                reward=torch.zeros(n, dtype=torch.float32).pin_memory(),
+                                done=torch.zeros(n, dtype=torch.uint8).pin_memory())
+        p = self._pinned
+        a_ptr = actions.data_ptr() if isinstance(actions, torch.Tensor) else actions.ctypes.data
+        m_ptr = 0 if messages is None else (messages.data_ptr() if isinstance(messages, torch.Tensor) else messages.ctypes.data)
+        _native.check(self._L.cc4_step_host(self._h, a_ptr, m_ptr, p["obs"].data_ptr(), p["reward"].data_ptr(),
+                                            p["done"].data_ptr(), flags, self._stream()), "cc4_step_host")
+        return p["obs"], p["reward"], p["done"]
+
+    def rollout(self, n_ticks: int, policy_seed: int = 0, reward_sum: torch.Tensor | None = None, flags: int = STEP_REWARD):
+        rp = 0 if reward_sum is None else reward_sum.data_ptr()
+        _native.check(self._L.cc4_rollout(self._h, int(n_ticks), int(policy_seed), rp, flags, self._stream()), "cc4_rollout")
+
+    def error_flags(self) -> np.ndarray:
+        out = np.zeros(self.num_envs, dtype=np.uint32)
+        _native.check(self._L.cc4_error_flags(self._h, out.ctypes.data), "cc4_error_flags")
+        return out
+
+    def export_canon(self, env: int) -> np.ndarray:
+        buf = np.zeros(32768, dtype=np.int32)
+        n = C.c_int(0)
+        _native.check(self._L.cc4_export_canon(self._h, int(env), buf.ctypes.data, len(buf), C.byref(n)), "cc4_export_canon")
+        return buf[:n.value].copy()
+
+    def launch_count(self) -> int:
+        v = C.c_uint64(0)
+        _native.check(self._L.cc4_launch_count(self._h, C.byref(v)), "cc4_launch_count")
+        return v.value

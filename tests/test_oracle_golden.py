@@ -1,0 +1,97 @@
+"""The C oracle against the golden trajectories recorded from the live reference (oracle/ref_harness.py).
+
+Every fixture holds the reference's RNG tape, the blue inputs, and after reset and after every tick the canonical
+state (oracle/canon.py), the five observation vectors, the team reward and the done flag.  The oracle must reproduce
+all of it bit-for-bit.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import canon
+import oracle_py as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FILES = sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+
+
+@pytest.mark.parametrize("name", FILES)
+def test_oracle_replays_reference(name):
+    fx = np.load(os.path.join(GOLDEN, name))
+    env = O.OracleEnv(steps=int(fx["steps"]), tape=O.tape_from_fixture(fx))
+    env.reset()
+    off = fx["canon_off"]
+
+    def check_state(t):
+        exp, got = fx["canon"][off[t]:off[t + 1]], env.export()
+        if len(exp) != len(got) or np.any(exp != got):
+            pytest.fail(f"{name} after tick {t - 1}: " + "; ".join(canon.diff(canon.decode(exp), canon.decode(got))[:8]))
+
+    assert env.error() == (0, "")
+    check_state(0)
+    assert np.array_equal(env.observe(), fx["obs"][0])
+    assert np.array_equal(env.mask(), fx["mask"])
+    for t in range(len(fx["actions"])):
+        rc, obs, rew, done = env.step(fx["actions"][t], fx["msgs"][t])
+        assert env.error() == (0, ""), f"tick {t}"
+        check_state(t + 1)
+        assert np.array_equal(obs, fx["obs"][t + 1]), f"tick {t}: observation"
+        assert rew == fx["reward"][t], f"tick {t}: reward"
+        assert done == fx["done"][t], f"tick {t}: done"
+    assert fx["done"][-1] == (len(fx["actions"]) == int(fx["steps"]) - 1)
+
+
+def test_oracle_detects_a_corrupted_tape():
+    fx = dict(np.load(os.path.join(GOLDEN, FILES[-1])))
+    recs, seg = O.tape_from_fixture(fx)
+    first_tick = int(seg[1])
+    recs["site"][first_tick] ^= 1     # first draw of tick 0
+    env = O.OracleEnv(steps=int(fx["steps"]), tape=(recs, seg))
+    env.reset()
+    env.step(fx["actions"][0], fx["msgs"][0])
+    assert env.error()[0] & 1
+
+
+def test_reward_table_matches_reference_tables():
+    """BlueRewardMachine.py:35-65 == README tables; checked through the oracle's observable reward: a failing
+    GreenLocalWork / GreenAccessService can only produce values from the table."""
+    fx = np.load(os.path.join(GOLDEN, FILES[0]))
+    assert set(np.unique(fx["reward"])) <= set(float(x) for x in range(-200, 1)) | {-0.5}
+
+
+def test_philox_mode_is_deterministic_and_sharding_invariant():
+    a = O.OracleEnv(seed=7, episode=3, steps=100)
+    b = O.OracleEnv(seed=7, episode=3, steps=100)
+    a.reset(), b.reset()
+    assert np.array_equal(a.export(), b.export())
+    rng = np.random.default_rng(0)
+    for _ in range(40):
+        act = [int(rng.integers(0, n)) for n in (82, 82, 82, 82, 242)]
+        ra, rb = a.step(act), b.step(act)
+        assert ra[2] == rb[2] and np.array_equal(ra[1], rb[1])
+    assert np.array_equal(a.export(), b.export())
+    assert a.error()[0] == 0
+    c = O.OracleEnv(seed=7, episode=4, steps=100)
+    c.reset()
+    assert not np.array_equal(a.export()[:400], c.export()[:400])
+
+
+def test_mission_phase_split():
+    """EnterpriseScenarioGenerator._generate_mission_phases :854-860 (reference test_mission_phase.py:95-101)."""
+    for steps, changes in ((9, (3, 6)), (10, (4, 7)), (11, (4, 8)), (100, (34, 67)), (500, (167, 334))):
+        env = O.OracleEnv(seed=1, episode=0, steps=steps)
+        env.reset()
+        phases = []
+        for t in range(steps - 1):
+            env.step([49, 49, 49, 49, 145])
+            phases.append(int(env.export()[0]))
+        got = tuple(i for i in range(1, len(phases)) if phases[i] != phases[i - 1])
+        assert got == tuple(c for c in changes if c < steps - 1), (steps, got)
+
+
+def test_episode_length_and_done():
+    env = O.OracleEnv(seed=2, episode=0, steps=30)
+    env.reset()
+    dones = [env.step([49, 49, 49, 49, 145])[3] for _ in range(29)]
+    assert dones == [0] * 28 + [1]      # EnterpriseScenarioGenerator.determine_done :862-871
