@@ -23,9 +23,15 @@ def _diff(exp, got):
     return "; ".join(canon.diff(canon.decode(exp), canon.decode(got))[:8])
 
 
-def test_tape_replay_of_reference_episodes():
-    """All golden episodes in ONE batch (ragged lengths): state, observations, reward, done after every tick."""
-    fxs = [np.load(os.path.join(GOLDEN, f)) for f in FILES]
+STEPS = sorted({int(np.load(os.path.join(GOLDEN, f))["steps"]) for f in FILES})
+
+
+@pytest.mark.parametrize("steps", STEPS)
+def test_tape_replay_of_reference_episodes(steps):
+    """All golden episodes of one episode length in ONE batch (ragged tick counts): state, observations, reward,
+    done after every tick."""
+    names = [f for f in FILES if int(np.load(os.path.join(GOLDEN, f))["steps"]) == steps]
+    fxs = [np.load(os.path.join(GOLDEN, f)) for f in names]
     n = len(fxs)
     T = max(len(fx["actions"]) for fx in fxs)
     recs_all, segs = [], []
@@ -38,16 +44,16 @@ def test_tape_replay_of_reference_episodes():
         segs.append(full + np.uint32(base))
         recs_all.append(recs)
         base += len(recs)
-    env = _engine(n, device=0, steps=500, rng="tape")
+    env = _engine(n, device=0, steps=steps, rng="tape")
     env.set_tape(np.concatenate(recs_all), np.stack(segs))
     obs, mask = env.reset()
     obs, mask = obs.cpu().numpy(), mask.cpu().numpy()
     for i, fx in enumerate(fxs):
-        assert np.array_equal(obs[i], fx["obs"][0]), FILES[i]
-        assert np.array_equal(mask[i].astype(np.uint8), fx["mask"]), FILES[i]
+        assert np.array_equal(obs[i], fx["obs"][0]), names[i]
+        assert np.array_equal(mask[i].astype(np.uint8), fx["mask"]), names[i]
         off = fx["canon_off"]
         exp, got = fx["canon"][off[0]:off[1]], env.export_canon(i)
-        assert np.array_equal(exp, got), f"{FILES[i]} reset: {_diff(exp, got)}"
+        assert np.array_equal(exp, got), f"{names[i]} reset: {_diff(exp, got)}"
     assert not env.error_flags().any()
     alive = np.ones(n, dtype=bool)
     for t in range(T):
@@ -65,15 +71,15 @@ def test_tape_replay_of_reference_episodes():
         for i, fx in enumerate(fxs):
             if not alive[i]:
                 continue
-            assert np.array_equal(o[i], fx["obs"][t + 1]), f"{FILES[i]} tick {t}: observation"
-            assert r[i] == fx["reward"][t], f"{FILES[i]} tick {t}: reward {r[i]} != {fx['reward'][t]}"
-            assert d[i] == fx["done"][t], f"{FILES[i]} tick {t}: done"
+            assert np.array_equal(o[i], fx["obs"][t + 1]), f"{names[i]} tick {t}: observation"
+            assert r[i] == fx["reward"][t], f"{names[i]} tick {t}: reward {r[i]} != {fx['reward'][t]}"
+            assert d[i] == fx["done"][t], f"{names[i]} tick {t}: done"
             if flags is not None:
-                assert flags[i] == 0, f"{FILES[i]} tick {t}: error flags {flags[i]}"
+                assert flags[i] == 0, f"{names[i]} tick {t}: error flags {flags[i]}"
             if t % 10 == 0 or t == len(fx["actions"]) - 1:
                 off = fx["canon_off"]
                 exp, got = fx["canon"][off[t + 1]:off[t + 2]], env.export_canon(i)
-                assert np.array_equal(exp, got), f"{FILES[i]} tick {t}: {_diff(exp, got)}"
+                assert np.array_equal(exp, got), f"{names[i]} tick {t}: {_diff(exp, got)}"
 
 
 @pytest.mark.parametrize("n,ticks,seed", [(256, 120, 11), (37, 499, 5)])
