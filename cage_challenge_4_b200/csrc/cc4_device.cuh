@@ -93,14 +93,20 @@ struct Act { int code, host, subnet, session; };
 /* per-warp scratch (shared memory, not persisted) */
 struct Scratch {
     uint16_t ctr[NAG + 1];                       /* per-actor draw counter / tape position of this tick; [NAG] = reset */
-    uint16_t oent[CC4_NRED][CC4_OENT_CAP];       /* observation entries: slot | key_ip<<8 | iface<<9 | subnet_if<<10 | syshost<<11 | sess<<12 */
+    uint16_t oent[CC4_NRED][CC4_OENT_CAP];       /* explicit observation entries: slot | key_ip<<8 | iface<<9 | subnet_if<<10 | syshost<<11 | sess<<12 */
     uint8_t n_oent[8];
     uint8_t have_first[8], succ0[8], has_act0[8];
     uint32_t act0[8];                             /* IP_MAKE(code, host, subnet, session, 0) */
     uint32_t evpid[16]; int n_evpid;              /* (slot<<16 | pid) carried by this tick's process_creation events */
-    uint8_t cur_code[NAG], cur_host[16];          /* self.action[agent][0] of the tick (code; host for red Impact) */
-    uint8_t dropped[NAG];
-    uint8_t green_act[CC4_MAXGREEN], green_phish[CC4_MAXGREEN];
+    uint32_t subw[11];                            /* this tick's due action per blue / red actor (IP_MAKE, ticks = 0) */
+    uint8_t dropped[16];
+    /* session-pool digests, rebuilt by w_scan_sessions */
+    uint32_t sess_hosts[CC4_NRED][4];             /* hosts on which agent r holds a session */
+    int n_red[8];                                 /* sessions per agent */
+    uint32_t has0, newss, misplaced;              /* bit r: agent r has ident 0 / has an abstract session whose id it does not know yet / has a session on a foreign subnet */
+    uint32_t hostagents[32];                      /* byte h = mask of red agents with a session on host h (built on demand for phishing) */
+    uint32_t phish[3];                            /* green agents whose local work triggered a phishing email this tick */
+    uint32_t ssmask[CC4_NRED][8];                 /* bit id: server_session id known to agent r (mirror of Cc4Dyn.ss, rebuilt every tick) */
     int reward;
 };
 
@@ -113,7 +119,7 @@ struct Ctx {
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-__device__ __forceinline__ void fail(Ctx &c, uint32_t flag) { c.s->err |= flag; }
+__device__ __forceinline__ void fail(Ctx &c, uint32_t flag) { atomicOr(&c.s->err, flag); }
 
 /* ------------------------------------------------------------------------------------------------ */
 /* RNG: Philox4x32-10 keyed (seed, episode) with counter (draw index, actor, tick+1) or tape replay  */
@@ -129,7 +135,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
 }
-__device__ __forceinline__ uint64_t tape_next(Ctx &c, int actor, int site, int kind, uint32_t n)
+__device__ __noinline__ uint64_t tape_next(Ctx &c, int actor, int site, int kind, uint32_t n)
 {
     uint32_t seg = actor == NAG ? 0u : 1u + (uint32_t)c.tick * NAG + (uint32_t)actor;
     if (seg >= c.n_segs) { fail(c, CC4_E_TAPE_END); return 0; }
@@ -140,18 +146,18 @@ __device__ __forceinline__ uint64_t tape_next(Ctx &c, int actor, int site, int k
     c.x->ctr[actor]++;
     return d.val;
 }
-__device__ __forceinline__ void philox_draw(Ctx &c, int actor, uint32_t o[4])
+__device__ __noinline__ void philox_draw(Ctx &c, int actor, uint32_t o[4])
 {
     o[0] = c.x->ctr[actor]++; o[1] = (uint32_t)actor; o[2] = actor == NAG ? 0u : (uint32_t)c.tick + 1u; o[3] = c.ep_lo;
     philox4x32_10(o, c.k0, c.k1);
 }
-__device__ __forceinline__ uint32_t rng_int(Ctx &c, int actor, int site, uint32_t n)
+__device__ __noinline__ uint32_t rng_int(Ctx &c, int actor, int site, uint32_t n)
 {
     if (c.rng_mode == 1) { uint64_t v = tape_next(c, actor, site, 0, n); return v < n ? (uint32_t)v : 0u; }
     uint32_t o[4]; philox_draw(c, actor, o);
     return __umulhi(o[0], n);
 }
-__device__ __forceinline__ double rng_f64(Ctx &c, int actor, int site, uint32_t n)
+__device__ __noinline__ double rng_f64(Ctx &c, int actor, int site, uint32_t n)
 {
     if (c.rng_mode == 1) return __longlong_as_double((long long)tape_next(c, actor, site, 1, n));
     uint32_t o[4]; philox_draw(c, actor, o);
@@ -177,33 +183,33 @@ __device__ __forceinline__ void set128(uint32_t *b, int i) { b[i >> 5] |= 1u << 
 /* ---- process pool (lane 0) ---- */
 __device__ __forceinline__ int p_begin(const Cc4Dyn *s, int h) { return s->pstart[h]; }
 __device__ __forceinline__ int p_end(const Cc4Dyn *s, int h) { return s->pstart[h + 1]; }
-__device__ void proc_append(Ctx &c, int h, uint32_t w)
+__device__ __noinline__ void proc_append(Ctx &c, int h, uint32_t w)
 {   /* host.processes.append */
     Cc4Dyn *s = c.s;
     int tot = s->pstart[128];
     if (tot >= CC4_PROC_CAP) { fail(c, CC4_E_CAPACITY); return; }
     int at = s->pstart[h + 1];
-    for (int i = tot; i > at; i--) s->procs[i] = s->procs[i - 1];
+    _Pragma("unroll 1") for (int i = tot; i > at; i--) s->procs[i] = s->procs[i - 1];
     s->procs[at] = w;
-    for (int j = h + 1; j <= 128; j++) s->pstart[j]++;
+    _Pragma("unroll 1") for (int j = h + 1; j <= 128; j++) s->pstart[j]++;
 }
-__device__ void proc_delete(Ctx &c, int h, int idx)
+__device__ __noinline__ void proc_delete(Ctx &c, int h, int idx)
 {
     Cc4Dyn *s = c.s;
     int tot = s->pstart[128];
-    for (int i = idx; i + 1 < tot; i++) s->procs[i] = s->procs[i + 1];
-    for (int j = h + 1; j <= 128; j++) s->pstart[j]--;
+    _Pragma("unroll 1") for (int i = idx; i + 1 < tot; i++) s->procs[i] = s->procs[i + 1];
+    _Pragma("unroll 1") for (int j = h + 1; j <= 128; j++) s->pstart[j]--;
 }
-__device__ int proc_find(const Cc4Dyn *s, int h, uint32_t pid)
+__device__ __noinline__ int proc_find(const Cc4Dyn *s, int h, uint32_t pid)
 {   /* Host.get_process Host.py:251 (tombstones are not processes) */
-    for (int i = p_begin(s, h); i < p_end(s, h); i++) if (!P_DEAD(s->procs[i]) && P_PID(s->procs[i]) == pid) return i;
+    _Pragma("unroll 1") for (int i = p_begin(s, h); i < p_end(s, h); i++) if (!P_DEAD(s->procs[i]) && P_PID(s->procs[i]) == pid) return i;
     return -1;
 }
-__device__ int create_pid(Ctx &c, int actor, int h)
+__device__ __noinline__ int create_pid(Ctx &c, int actor, int h)
 {   /* Host.create_pid Host.py:198-200 */
     const Cc4Dyn *s = c.s;
     uint32_t mx = 0;
-    for (int i = p_begin(s, h); i < p_end(s, h); i++) if (!P_DEAD(s->procs[i]) && P_PID(s->procs[i]) > mx) mx = P_PID(s->procs[i]);
+    _Pragma("unroll 1") for (int i = p_begin(s, h); i < p_end(s, h); i++) if (!P_DEAD(s->procs[i]) && P_PID(s->procs[i]) > mx) mx = P_PID(s->procs[i]);
     uint32_t pid = mx + 1 + rng_int(c, actor, ST_CREATE_PID, 9);
     if (pid > 0xFFFFu) { fail(c, CC4_E_CAPACITY); pid = 0xFFFFu; }
     return (int)pid;
@@ -215,31 +221,31 @@ __device__ __forceinline__ bool svc_active(uint64_t v, uint32_t entry) { return 
 __device__ __forceinline__ uint64_t svc_set(uint64_t v, int i, uint32_t entry) { return (v & ~(0x7Full << (7 * i))) | ((uint64_t)entry << (7 * i)); }
 
 /* ---- red session pool (lane 0) ---- */
-__device__ int sess_find(const Cc4Dyn *s, int r, int id)
+__device__ __noinline__ int sess_find(const Cc4Dyn *s, int r, int id)
 {
-    for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_ID(s->sess[i]) == (uint32_t)id) return i;
+    _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_ID(s->sess[i]) == (uint32_t)id) return i;
     return -1;
 }
-__device__ int sess_count_agent(const Cc4Dyn *s, int r) { int n = 0; for (int i = 0; i < s->n_sess; i++) n += SF_AGENT(s->sessf[i]) == (uint32_t)r; return n; }
-__device__ void ports_drop(Cc4Dyn *s, int r, int id)
+__device__ __noinline__ int sess_count_agent(const Cc4Dyn *s, int r) { int n = 0; for (int i = 0; i < s->n_sess; i++) n += SF_AGENT(s->sessf[i]) == (uint32_t)r; return n; }
+__device__ __noinline__ void ports_drop(Cc4Dyn *s, int r, int id)
 {
     int w = 0;
-    for (int i = 0; i < s->n_ports; i++) { uint32_t p = s->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)id) continue; s->ports[w++] = p; }
+    _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = s->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)id) continue; s->ports[w++] = p; }
     s->n_ports = (uint16_t)w;
 }
-__device__ void sess_delete(Cc4Dyn *s, int idx)
+__device__ __noinline__ void sess_delete(Cc4Dyn *s, int idx)
 {
     ports_drop(s, SF_AGENT(s->sessf[idx]), S_ID(s->sess[idx]));
-    for (int i = idx; i + 1 < s->n_sess; i++) { s->sess[i] = s->sess[i + 1]; s->sessf[i] = s->sessf[i + 1]; }
+    _Pragma("unroll 1") for (int i = idx; i + 1 < s->n_sess; i++) { s->sess[i] = s->sess[i + 1]; s->sessf[i] = s->sessf[i + 1]; }
     s->n_sess--;
 }
 /* State.add_session State.py:305-323 for a red agent; returns the ident */
-__device__ int sess_add(Ctx &c, int r, int host, int abstract, int root, int pid)
+__device__ __noinline__ int sess_add(Ctx &c, int r, int host, int abstract, int root, int pid)
 {
     Cc4Dyn *s = c.s;
     if (s->n_sess >= CC4_SESS_CAP) { fail(c, CC4_E_CAPACITY); return 0; }
     int id = 0, any = 0;
-    for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r) { any = 1; if ((int)S_ID(s->sess[i]) >= id) id = S_ID(s->sess[i]); }
+    _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r) { any = 1; if ((int)S_ID(s->sess[i]) >= id) id = S_ID(s->sess[i]); }
     id = any ? id + 1 : 0;
     if (id > 255) { fail(c, CC4_E_CAPACITY); id = 255; }
     if (s->sess_count[r] < 255) s->sess_count[r]++;
@@ -248,14 +254,14 @@ __device__ int sess_add(Ctx &c, int r, int host, int abstract, int root, int pid
     s->n_sess++;
     return id;
 }
-__device__ bool red_on_host(const Cc4Dyn *s, int r, int host)
+__device__ __noinline__ bool red_on_host(const Cc4Dyn *s, int r, int host)
 {
-    for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_HOST(s->sess[i]) == (uint32_t)host) return true;
+    _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_HOST(s->sess[i]) == (uint32_t)host) return true;
     return false;
 }
-__device__ int session_from_pid(const Cc4Dyn *s, int host, uint32_t pid)
+__device__ __noinline__ int session_from_pid(const Cc4Dyn *s, int host, uint32_t pid)
 {   /* State.get_session_from_pid State.py:420-444; blue / green session processes are never removed */
-    for (int i = 0; i < s->n_sess; i++) if (S_HOST(s->sess[i]) == (uint32_t)host && S_PID(s->sess[i]) == pid) return i;
+    _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (S_HOST(s->sess[i]) == (uint32_t)host && S_PID(s->sess[i]) == pid) return i;
     return -1;
 }
 __device__ __forceinline__ bool blocking(const Cc4Dyn *s, int src_slot, int other_slot)
@@ -264,25 +270,26 @@ __device__ __forceinline__ bool blocking(const Cc4Dyn *s, int src_slot, int othe
 }
 
 /* ---- observation bookkeeping for one red agent (ObservationSet / ActionSpace.update ActionSpace.py:170-212) ---- */
-__device__ void obs_entry(Ctx &c, int r, int key_ip, int slot, int iface, int subnet_if, int syshost, int sess)
+__device__ __noinline__ void obs_entry(Ctx &c, int r, int key_ip, int slot, int iface, int subnet_if, int syshost, int sess)
 {
     Cc4Dyn *s = c.s; Scratch *x = c.x;
     if (syshost) set128(s->hn_known[r], slot);
     if (iface) set128(s->ip_known[r], slot);
     if (subnet_if) s->sn_known[r] |= (uint16_t)(1u << slot_subnet(slot));
     uint16_t key = (uint16_t)(slot | key_ip << 8), fl = (uint16_t)(iface << 9 | subnet_if << 10 | syshost << 11 | sess << 12);
-    for (int i = 0; i < x->n_oent[r]; i++) if ((x->oent[r][i] & 0x1FF) == key) { x->oent[r][i] |= fl; return; }
+    _Pragma("unroll 1") for (int i = 0; i < x->n_oent[r]; i++) if ((x->oent[r][i] & 0x1FF) == key) { x->oent[r][i] |= fl; return; }
     if (x->n_oent[r] >= CC4_OENT_CAP) { fail(c, CC4_E_CAPACITY); return; }
     x->oent[r][x->n_oent[r]++] = key | fl;
 }
-__device__ void know_session(Ctx &c, int r, int id)
+__device__ __noinline__ void know_session(Ctx &c, int r, int id)
 {
     Cc4Dyn *s = c.s;
-    for (int i = 0; i < s->n_ss[r]; i++) if (s->ss[r][i] == id) return;
+    _Pragma("unroll 1") for (int i = 0; i < s->n_ss[r]; i++) if (s->ss[r][i] == id) return;
     if (s->n_ss[r] >= CC4_SS_CAP) { fail(c, CC4_E_CAPACITY); return; }
     s->ss[r][s->n_ss[r]++] = (uint8_t)id;
+    c.x->ssmask[r][id >> 5] |= 1u << (id & 31);
 }
-__device__ void obs_push(Ctx &c, int r, int succ, bool has_act, const Act &a)
+__device__ __noinline__ void obs_push(Ctx &c, int r, int succ, bool has_act, const Act &a)
 {
     Scratch *x = c.x;
     if (x->have_first[r]) return;
@@ -293,17 +300,33 @@ __device__ void obs_push(Ctx &c, int r, int succ, bool has_act, const Act &a)
 /* ------------------------------------------------------------------------------------------------ */
 /* FiniteStateRedAgent bookkeeping, applied eagerly at the end of the tick (FiniteStateRedAgent.py:91-93) */
 /* ------------------------------------------------------------------------------------------------ */
-__device__ int fsm_find(const Cc4Dyn *s, int r, int slot) { for (int i = 0; i < s->n_fsm[r]; i++) if ((int)F_SLOT(s->fsm[r][i]) == slot) return i; return -1; }
+__device__ __noinline__ int fsm_find(const Cc4Dyn *s, int r, int slot) { for (int i = 0; i < s->n_fsm[r]; i++) if ((int)F_SLOT(s->fsm[r][i]) == slot) return i; return -1; }
 
-__device__ void fsm_digest(Ctx &c, int r)
+/* End of tick for one ACTIVE red agent, run by lane r (agents are independent here): the RedSessionCheck observation
+ * (RedSessionCheck._all_red_sessions_observation RedSessionCheck.py:57-63: one hostname-keyed entry with Sessions,
+ * Interface+Subnet and System info per session host) is represented by the host mask x->sess_hosts[r] instead of
+ * explicit entries; ActionSpace.update (ActionSpace.py:170-212) and the FSM bookkeeping consume the mask. */
+__device__ __noinline__ void agent_end_turn(Ctx &c, int r)
 {
     Cc4Dyn *s = c.s; Scratch *x = c.x;
+    const uint32_t *rsc = x->sess_hosts[r];
+    uint32_t snk = s->sn_known[r];
+    _Pragma("unroll 1") for (int w = 0; w < 4; w++) {
+        uint32_t m = rsc[w];
+        s->hn_known[r][w] |= m; s->ip_known[r][w] |= m;
+        if (m & 0xFFFFu) snk |= 1u << (2 * w);
+        if (m >> 16) snk |= 1u << (2 * w + 1);
+    }
+    s->sn_known[r] = (uint16_t)snk;
+    if (x->newss >> r & 1)
+        _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && SF_ABS(s->sessf[i])) know_session(c, r, S_ID(s->sess[i]));
+
     /* _host_state_transition :124-167 */
     if (x->has_act0[r] && x->succ0[r] != SUCC_INPROG) {
         int code = IP_CODE(x->act0[r]), ahost = IP_HOST(x->act0[r]), asub = IP_SUBNET(x->act0[r]), col = -1;
-        for (int k = 0; k < 9; k++) if (c_fsm_col_code[k] == code) col = k;
+        _Pragma("unroll 1") for (int k = 0; k < 9; k++) if (c_fsm_col_code[k] == code) col = k;
         if (col >= 0 && col != 8) {
-            for (int i = 0; i < s->n_fsm[r]; i++) {
+            _Pragma("unroll 1") for (int i = 0; i < s->n_fsm[r]; i++) {
                 uint16_t f = s->fsm[r][i];
                 bool hit;
                 if (col == 0) hit = (int)(F_SLOT(f) >> 4) == asub;
@@ -318,14 +341,17 @@ __device__ void fsm_digest(Ctx &c, int r)
             }
         }
     }
-    /* _process_new_observations :190-250 */
+    /* _process_new_observations :190-250, explicit entries first (they precede the RedSessionCheck observation) */
     int started = (s->fsm_started >> r) & 1;
-    for (int i = 0; i < x->n_oent[r]; i++) {
+    uint32_t seen[4] = { rsc[0], rsc[1], rsc[2], rsc[3] };
+    _Pragma("unroll 1") for (int i = 0; i < x->n_oent[r]; i++) {
         uint16_t e = x->oent[r][i];
-        int slot = e & 0xFF, key_ip = (e >> 8) & 1, iface = (e >> 9) & 1, syshost = (e >> 11) & 1;
+        int slot = e & 0xFF, key_ip = (e >> 8) & 1, syshost = (e >> 11) & 1;
+        int iface = ((e >> 9) & 1) || (!key_ip && bit128(rsc, slot));   /* a hostname-keyed entry merges with the RedSessionCheck entry of the same host */
         int hn = !key_ip || syshost;
+        if ((e >> 12) & 1) { if (iface) seen[slot >> 5] |= 1u << (slot & 31); else fail(c, CC4_E_UNREACHABLE); }
         int resolved = key_ip || iface;
-        if (!resolved) { for (int j = 0; j < s->n_fsm[r]; j++) if (F_HN(s->fsm[r][j]) && (int)F_SLOT(s->fsm[r][j]) == slot) { resolved = 1; break; } }
+        if (!resolved) { _Pragma("unroll 1") for (int j = 0; j < s->n_fsm[r]; j++) if (F_HN(s->fsm[r][j]) && (int)F_SLOT(s->fsm[r][j]) == slot) { resolved = 1; break; } }
         if (!resolved) { fail(c, CC4_E_UNREACHABLE); continue; }   /* would create host_states[None] */
         int idx = fsm_find(s, r, slot);
         if (idx < 0) {
@@ -334,43 +360,58 @@ __device__ void fsm_digest(Ctx &c, int r)
             s->fsm[r][idx] = F_MAKE(slot, hn, started ? F_K : F_U);
         } else if (hn && !F_HN(s->fsm[r][idx])) s->fsm[r][idx] |= 1u << 7;
     }
-    /* _session_removal_state_change :169-188 */
-    for (int i = 0; i < s->n_fsm[r]; i++) {
+    /* host masks of the FSM list: present / hostname known / state in {U, UD, R, RD} */
+    uint32_t fa[4] = { 0, 0, 0, 0 }, fh[4] = { 0, 0, 0, 0 }, fu[4] = { 0, 0, 0, 0 };
+    _Pragma("unroll 1") for (int i = 0; i < s->n_fsm[r]; i++) {
         uint16_t f = s->fsm[r][i];
-        int st = F_STATE(f);
-        if (st < F_U || st > F_RD) continue;
-        bool seen = false;
-        for (int j = 0; j < x->n_oent[r]; j++) {
-            uint16_t e = x->oent[r][j];
-            if (!((e >> 12) & 1)) continue;
-            if (!((e >> 9) & 1)) { fail(c, CC4_E_UNREACHABLE); continue; }
-            if ((e & 0xFF) == F_SLOT(f)) seen = true;
-        }
-        if (!seen) s->fsm[r][i] = F_MAKE(F_SLOT(f), F_HN(f), F_KD);
+        uint32_t w = F_SLOT(f) >> 5, b = 1u << (F_SLOT(f) & 31);
+        fa[w] |= b;
+        if (F_HN(f)) fh[w] |= b;
+        if (F_STATE(f) >= F_U && F_STATE(f) <= F_RD) fu[w] |= b;
     }
-    s->fsm_started |= (uint8_t)(1u << r);
+    /* RedSessionCheck entries in state.sessions[agent] order: hosts the FSM has not seen yet */
+    if ((rsc[0] & ~fa[0]) | (rsc[1] & ~fa[1]) | (rsc[2] & ~fa[2]) | (rsc[3] & ~fa[3])) {
+        _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) {
+            if (SF_AGENT(s->sessf[i]) != (uint32_t)r) continue;
+            uint32_t h = S_HOST(s->sess[i]), w = h >> 5, b = 1u << (h & 31);
+            if (fa[w] & b) continue;
+            if (s->n_fsm[r] >= CC4_FSM_CAP) { fail(c, CC4_E_CAPACITY); break; }
+            s->fsm[r][s->n_fsm[r]++] = F_MAKE(h, 1, started ? F_K : F_U);
+            fa[w] |= b; fh[w] |= b;
+            if (!started) fu[w] |= b;
+        }
+    }
+    /* ... and hosts whose hostname the FSM learns from them */
+    if ((rsc[0] & ~fh[0]) | (rsc[1] & ~fh[1]) | (rsc[2] & ~fh[2]) | (rsc[3] & ~fh[3]))
+        _Pragma("unroll 1") for (int i = 0; i < s->n_fsm[r]; i++) if (bit128(rsc, F_SLOT(s->fsm[r][i]))) s->fsm[r][i] |= 1u << 7;
+    /* _session_removal_state_change :169-188 */
+    if ((fu[0] & ~seen[0]) | (fu[1] & ~seen[1]) | (fu[2] & ~seen[2]) | (fu[3] & ~seen[3]))
+        _Pragma("unroll 1") for (int i = 0; i < s->n_fsm[r]; i++) {
+            uint16_t f = s->fsm[r][i];
+            if (F_STATE(f) >= F_U && F_STATE(f) <= F_RD && !bit128(seen, F_SLOT(f))) s->fsm[r][i] = F_MAKE(F_SLOT(f), F_HN(f), F_KD);
+        }
 }
 
 /* FiniteStateRedAgent._choose_host_and_action :296-336 + replace_action_if_invalid SimulationController.py:1068-1112 */
-__device__ Act red_policy(Ctx &c, int r)
+__device__ __noinline__ Act red_policy(Ctx &c, int r)
 {
     Cc4Dyn *s = c.s;
     int actor = A_RED0 + r;
     Act a = { AC_SLEEP, -1, -1, 0 };
     if (IP_CODE(s->inprog[actor]) != IP_NONE) return a;     /* last observation was IN_PROGRESS :100-102 */
     int nk = 0;
-    for (int i = 0; i < s->n_fsm[r]; i++) nk += F_STATE(s->fsm[r][i]) != F_F;
+    _Pragma("unroll 1") for (int i = 0; i < s->n_fsm[r]; i++) nk += F_STATE(s->fsm[r][i]) != F_F;
     if (nk == 0) { fail(c, CC4_E_UNREACHABLE); return a; }
     int pick = (int)rng_int(c, actor, ST_FSM_HOST, (uint32_t)nk);
     uint16_t f = 0;
-    for (int i = 0, k = 0; i < s->n_fsm[r]; i++) if (F_STATE(s->fsm[r][i]) != F_F) { if (k == pick) { f = s->fsm[r][i]; break; } k++; }
+    _Pragma("unroll 1") for (int i = 0, k = 0; i < s->n_fsm[r]; i++) if (F_STATE(s->fsm[r][i]) != F_F) { if (k == pick) { f = s->fsm[r][i]; break; } k++; }
     int st = F_STATE(f), slot = F_SLOT(f);
     int cols[9], p4[9], nc = 0, tot = 0;
-    for (int i = 0; i < 9; i++) { int col = c_red_aspace_cols[i]; int p = c_fsm_prob4[st][col]; if (p >= 0) { cols[nc] = col; p4[nc] = p; tot += p; nc++; } }
+    _Pragma("unroll 1") for (int i = 0; i < 9; i++) { int col = c_red_aspace_cols[i]; int p = c_fsm_prob4[st][col]; if (p >= 0) { cols[nc] = col; p4[nc] = p; tot += p; nc++; } }
     double u = rng_f64(c, actor, ST_FSM_ACTION, (uint32_t)nc);
     int k = 0, cum = 0;
     /* numpy Generator.choice(p): idx = searchsorted(cumsum(p) / sum, u, side='right') */
-    for (k = 0; k < nc; k++) { cum += p4[k]; if (!((double)cum / (double)tot <= u)) break; }
+    _Pragma("unroll 1") for (k = 0; k < nc; k++) { cum += p4[k]; if (!((double)cum / (double)tot <= u)) break; }
     if (k >= nc) k = nc - 1;
     int col = cols[k];
     a.code = c_fsm_col_code[col];
@@ -378,7 +419,7 @@ __device__ Act red_policy(Ctx &c, int r)
     if (col == 0) {
         int no = __popc(s->sn_known[r]);
         int pk = (int)rng_int(c, actor, ST_FSM_PARAM, (uint32_t)no);
-        for (int sn = 0, j = 0; sn < 9; sn++) if (s->sn_known[r] >> sn & 1) { if (j == pk) { a.subnet = sn; break; } j++; }
+        _Pragma("unroll 1") for (int sn = 0, j = 0; sn < 9; sn++) if (s->sn_known[r] >> sn & 1) { if (j == pk) { a.subnet = sn; break; } j++; }
         PICK_SESSION(); (void)rng_int(c, actor, ST_FSM_PARAM, 1);
     } else if (col <= 3) { PICK_SESSION(); (void)rng_int(c, actor, ST_FSM_PARAM, 1); a.host = slot; }
     else { if (col >= 5 && !F_HN(f)) fail(c, CC4_E_UNREACHABLE); a.host = slot; PICK_SESSION(); (void)rng_int(c, actor, ST_FSM_PARAM, 1); }
@@ -392,7 +433,7 @@ __device__ Act red_policy(Ctx &c, int r)
 /* blue: index decoding (BlueFixedActionWrapper._populate_action_space :233-309) and actions         */
 /* ------------------------------------------------------------------------------------------------ */
 __device__ __forceinline__ int blue_sorted_subnet(int b, int i) { return b < 4 ? b : (i == 0 ? S_ADM : i == 1 ? S_OFF : S_PAZ); }
-__device__ Act blue_decode(const Cc4Dyn *s, int b, int idx, int *mask_out)
+__device__ __noinline__ Act blue_decode(const Cc4Dyn *s, int b, int idx, int *mask_out)
 {
     Act a = { AC_SLEEP, -1, -1, 0 };
     int n = b == 4 ? 3 : 1, H = 16 * n, T = 8 * n, m = 1, hostidx = -1, tidx = -1, code = AC_SLEEP;
@@ -412,7 +453,7 @@ __device__ Act blue_decode(const Cc4Dyn *s, int b, int idx, int *mask_out)
     }
     if (tidx >= 0) {
         int dst = blue_sorted_subnet(b, tidx >> 3), j = tidx & 7, src = -1;
-        for (int p = 0, k = 0; p < 9; p++) { if (c_sorted_subnets[p] == dst) continue; if (k == j) { src = c_sorted_subnets[p]; break; } k++; }
+        _Pragma("unroll 1") for (int p = 0, k = 0; p < 9; p++) { if (c_sorted_subnets[p] == dst) continue; if (k == j) { src = c_sorted_subnets[p]; break; } k++; }
         a.subnet = dst; a.host = src;
     }
     a.code = code;
@@ -420,7 +461,7 @@ __device__ Act blue_decode(const Cc4Dyn *s, int b, int idx, int *mask_out)
     return a;
 }
 
-__device__ void ev_procpid(Ctx &c, int slot, int pid)
+__device__ __noinline__ void ev_procpid(Ctx &c, int slot, int pid)
 {
     c.s->ev[slot] |= EV_PROC;
     /* only hosts some blue agent monitors ever have their event pids read (Monitor.py:66-70) */
@@ -430,7 +471,7 @@ __device__ void ev_procpid(Ctx &c, int slot, int pid)
 }
 
 /* StopProcess.execute_targeteted_local_action + kill_process StopProcess.py:23-58 */
-__device__ void stop_process(Ctx &c, int actor, int h, uint32_t pid)
+__device__ __noinline__ void stop_process(Ctx &c, int actor, int h, uint32_t pid)
 {
     Cc4Dyn *s = c.s;
     int pi = proc_find(s, h, pid);
@@ -440,7 +481,7 @@ __device__ void stop_process(Ctx &c, int actor, int h, uint32_t pid)
     int si = session_from_pid(s, h, pid);
     /* a stopped OT service keeps Service.process; a pid collision with it takes the reference down a path that
        re-labels the killed process as the service's (StopProcess.py:37-42): not modelled */
-    for (int i = p_begin(s, h); i < p_end(s, h); i++) if (P_DEAD(s->procs[i]) && P_PID(s->procs[i]) == pid) fail(c, CC4_E_UNREACHABLE);
+    _Pragma("unroll 1") for (int i = p_begin(s, h); i < p_end(s, h); i++) if (P_DEAD(s->procs[i]) && P_PID(s->procs[i]) == pid) fail(c, CC4_E_UNREACHABLE);
     proc_delete(c, h, pi);
     if (P_SVC(w)) {
         int np = create_pid(c, actor, h);
@@ -454,28 +495,28 @@ __device__ void stop_process(Ctx &c, int actor, int h, uint32_t pid)
 }
 
 /* RestoreFromBackup.py:9-19 + Host.restore Host.py:373-429 */
-__device__ void do_restore(Ctx &c, int h)
+__device__ __noinline__ void do_restore(Ctx &c, int h)
 {
     Cc4Dyn *s = c.s; const Cc4Stat *st = c.st;
-    for (int i = 0; i < s->n_sess;) if (S_HOST(s->sess[i]) == (uint32_t)h) sess_delete(s, i); else i++;
+    _Pragma("unroll 1") for (int i = 0; i < s->n_sess;) if (S_HOST(s->sess[i]) == (uint32_t)h) sess_delete(s, i); else i++;
     s->ev[h] = 0;
     int ob = st->o_pstart[h], on = st->o_pstart[h + 1] - ob, cb = s->pstart[h], cn = s->pstart[h + 1] - cb, tot = s->pstart[128];
     int d = on - cn;
     if (tot + d > CC4_PROC_CAP) { fail(c, CC4_E_CAPACITY); return; }
     if (d > 0) for (int i = tot - 1; i >= cb + cn; i--) s->procs[i + d] = s->procs[i];
     if (d < 0) for (int i = cb + cn; i < tot; i++) s->procs[i + d] = s->procs[i];
-    for (int i = 0; i < on; i++) s->procs[cb + i] = st->o_procs[ob + i];
-    for (int j = h + 1; j <= 128; j++) s->pstart[j] = (uint16_t)(s->pstart[j] + d);
+    _Pragma("unroll 1") for (int i = 0; i < on; i++) s->procs[cb + i] = st->o_procs[ob + i];
+    _Pragma("unroll 1") for (int j = h + 1; j <= 128; j++) s->pstart[j] = (uint16_t)(s->pstart[j] + d);
     s->svc64[h] = st->o_svc64[h];
 }
 
 /* DecoyAction.execute DecoyAction.py:47-112 with DeployDecoy.CANDIDATE_DECOYS DeployDecoy.py:27 */
-__device__ void do_decoy(Ctx &c, int b, int h)
+__device__ __noinline__ void do_decoy(Ctx &c, int b, int h)
 {
     Cc4Dyn *s = c.s;
     int actor = A_BLUE0 + b;
     int used = 0;
-    for (int i = p_begin(s, h); i < p_end(s, h); i++) { if (P_DEAD(s->procs[i])) continue; int pb = c_kind_portbit[P_KIND(s->procs[i])]; if (pb >= 0) used |= 1 << pb; }
+    _Pragma("unroll 1") for (int i = p_begin(s, h); i < p_end(s, h); i++) { if (P_DEAD(s->procs[i])) continue; int pb = c_kind_portbit[P_KIND(s->procs[i])]; if (pb >= 0) used |= 1 << pb; }
     int fac[4], nf = 0;
     if (!(used & PB_80)) fac[nf++] = K_D_APACHE;
     if (!(used & PB_443)) fac[nf++] = K_D_TOMCAT;
@@ -484,22 +525,22 @@ __device__ void do_decoy(Ctx &c, int b, int h)
     int kind = fac[rng_int(c, actor, ST_DECOY_FACTORY, (uint32_t)nf)];
     int pid = create_pid(c, actor, h);
     /* host.services[name] = Service(pid): an earlier process of the same decoy stops being the service's process */
-    for (int i = p_begin(s, h); i < p_end(s, h); i++) if (P_KIND(s->procs[i]) == (uint32_t)kind && P_SVC(s->procs[i])) s->procs[i] &= ~(1u << 21);
+    _Pragma("unroll 1") for (int i = p_begin(s, h); i < p_end(s, h); i++) if (P_KIND(s->procs[i]) == (uint32_t)kind && P_SVC(s->procs[i])) s->procs[i] &= ~(1u << 21);
     proc_append(c, h, P_MAKE(pid, kind, 0, 1));
     uint64_t v = s->svc64[h];
     int n = svc_count(v), at = -1;
-    for (int i = 0; i < n; i++) if ((SVC_ENTRY(v, i) & 15u) == (uint32_t)kind) at = i;
+    _Pragma("unroll 1") for (int i = 0; i < n; i++) if ((SVC_ENTRY(v, i) & 15u) == (uint32_t)kind) at = i;
     if (at < 0) { if (n >= 9) { fail(c, CC4_E_CAPACITY); return; } at = n; }
     s->svc64[h] = svc_set(v, at, (uint32_t)kind | 5u << 4);
 }
 
-__device__ void exec_blue(Ctx &c, int b, const Act &a)
+__device__ __noinline__ void exec_blue(Ctx &c, int b, const Act &a)
 {
     Cc4Dyn *s = c.s;
     switch (a.code) {
     case AC_REMOVE: {   /* Remove.py:42-69 */
         int n = s->n_sus;
-        for (int i = 0; i < n; i++) { uint32_t w = s->sus[i]; if (SU_AGENT(w) == (uint32_t)b && SU_SLOT(w) == (uint32_t)a.host) stop_process(c, A_BLUE0 + b, a.host, SU_PID(w)); }
+        _Pragma("unroll 1") for (int i = 0; i < n; i++) { uint32_t w = s->sus[i]; if (SU_AGENT(w) == (uint32_t)b && SU_SLOT(w) == (uint32_t)a.host) stop_process(c, A_BLUE0 + b, a.host, SU_PID(w)); }
         break;
     }
     case AC_RESTORE: do_restore(c, a.host); break;        /* Restore.py:38-68 */
@@ -513,22 +554,24 @@ __device__ void exec_blue(Ctx &c, int b, const Act &a)
 /* ------------------------------------------------------------------------------------------------ */
 /* green                                                                                            */
 /* ------------------------------------------------------------------------------------------------ */
-/* PhishingEmail._create_new_session PhishingEmail.py:42-113 (lane 0, in green-agent order) */
-__device__ void do_phishing(Ctx &c, int g)
+/* PhishingEmail._create_new_session PhishingEmail.py:42-113 (lane 0, in green-agent order); x->hostagents is current */
+__device__ __noinline__ void do_phishing(Ctx &c, int g)
 {
     Cc4Dyn *s = c.s;
+    const uint8_t *ha = reinterpret_cast<const uint8_t *>(c.x->hostagents);
     int actor = A_GREEN0 + g, gh = s->green_host[g], gsn = gh >> 4;
-    for (int i = 0; i < s->n_sess; i++) if (S_HOST(s->sess[i]) == (uint32_t)gh) return;
+    if (ha[gh]) return;
     /* hosts in state.hosts order (per subnet: users, then servers), agents in order on each host */
     int src = -1, nc = 0;
     uint8_t cand[CC4_SESS_CAP];
-    for (int sn = 0; sn < 8; sn++) {
+    _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) {
         int nu = s->nuser[sn], nh = nu + s->nserver[sn];
-        for (int k = 0; k < nh; k++) {
+        if (!(c.x->hostagents[4 * sn] | c.x->hostagents[4 * sn + 1] | c.x->hostagents[4 * sn + 2] | c.x->hostagents[4 * sn + 3])) continue;
+        _Pragma("unroll 1") for (int k = 0; k < nh; k++) {
             int h = k < nu ? sn * 16 + 6 + k : sn * 16 + (k - nu);
-            uint32_t agents = 0;
-            for (int i = 0; i < s->n_sess; i++) if (S_HOST(s->sess[i]) == (uint32_t)h) agents |= 1u << SF_AGENT(s->sessf[i]);
-            for (int r = 0; r < CC4_NRED; r++) {
+            uint32_t agents = ha[h];
+            if (!agents) continue;
+            _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
                 if (!(agents >> r & 1)) continue;
                 if (sn == gsn) { src = r; break; }
                 if (nc < CC4_SESS_CAP) cand[nc++] = (uint8_t)r;
@@ -539,71 +582,69 @@ __device__ void do_phishing(Ctx &c, int g)
     int pid = create_pid(c, actor, gh);
     proc_append(c, gh, P_MAKE(pid, K_REDABS, 0, 0));
     sess_add(c, src, gh, 1, 0, pid);
+    reinterpret_cast<uint8_t *>(c.x->hostagents)[gh] |= (uint8_t)(1u << src);
 }
 
 /* k-th server (creation order: subnets ascending, server_host_0..) among the allowed subnets; GreenAccessService.py:94-115 */
 __device__ __forceinline__ int nth_allowed_server(const Cc4Dyn *s, uint32_t allowed, int k)
 {
-    for (int sn = 0; sn < 8; sn++) if (allowed >> sn & 1) { int n = s->nserver[sn]; if (k < n) return sn * 16 + k; k -= n; }
+    _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) if (allowed >> sn & 1) { int n = s->nserver[sn]; if (k < n) return sn * 16 + k; k -= n; }
     return 0;
 }
 
 /* one green agent's tick (EnterpriseGreenAgent.get_action :42-78, GreenLocalWork.py:60-125, GreenAccessService.py:137-217);
  * event bits are OR-ed atomically, the phishing side effect is deferred (flag) because it is order dependent */
-__device__ int green_tick(Ctx &c, int g, uint32_t *ev_words)
+__device__ __noinline__ int green_tick(Ctx &c, int g, uint32_t *ev_words, bool *phish)
 {
     Cc4Dyn *s = c.s;
     int actor = A_GREEN0 + g, gh = s->green_host[g], gsn = gh >> 4;
     uint32_t choice = rng_int(c, actor, ST_GREEN_ACT, 3);
-    c.x->green_phish[g] = 0;
+    *phish = false;
     if (choice == 1) {
-        c.x->green_act[g] = AC_G_LOCAL;
         uint64_t v = s->svc64[gh];
         int n = svc_count(v), na = 0;
-        for (int i = 0; i < n; i++) na += svc_active(v, SVC_ENTRY(v, i));
+        _Pragma("unroll 1") for (int i = 0; i < n; i++) na += svc_active(v, SVC_ENTRY(v, i));
         if (na == 0) return c_reward[s->phase][gsn][0];
         int pick = (int)rng_int(c, actor, ST_LW_SERVICE, (uint32_t)na), rel = 0;
-        for (int i = 0, k = 0; i < n; i++) { uint32_t e = SVC_ENTRY(v, i); if (!svc_active(v, e)) continue; if (k == pick) { rel = (int)(e >> 4) * 20; break; } k++; }
+        _Pragma("unroll 1") for (int i = 0, k = 0; i < n; i++) { uint32_t e = SVC_ENTRY(v, i); if (!svc_active(v, e)) continue; if (k == pick) { rel = (int)(e >> 4) * 20; break; } k++; }
         if ((int)rng_int(c, actor, ST_LW_RELIAB, 100) >= rel) return c_reward[s->phase][gsn][0];
         if (rng_f64(c, actor, ST_LW_FP, 0) < 0.01) atomicOr(&ev_words[gh >> 2], EV_PROC << ((gh & 3) * 8));
-        if (rng_f64(c, actor, ST_LW_PHISH, 0) < 0.01) c.x->green_phish[g] = 1;
+        if (rng_f64(c, actor, ST_LW_PHISH, 0) < 0.01) *phish = true;
         return 0;
     }
     if (choice == 0) {
-        c.x->green_act[g] = AC_G_ACCESS;
         uint32_t allowed = c_green_allowed[s->phase][gsn];
         int nd = 0;
-        for (int sn = 0; sn < 8; sn++) if (allowed >> sn & 1) nd += s->nserver[sn];
+        _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) if (allowed >> sn & 1) nd += s->nserver[sn];
         int d = nth_allowed_server(s, allowed, (int)rng_int(c, actor, ST_AS_DEST, (uint32_t)nd)), dsn = d >> 4;
         if ((s->blocks[gsn] >> dsn & 1) || (s->blocks[dsn] >> gsn & 1)) { atomicOr(&ev_words[d >> 2], EV_NET << ((d & 3) * 8)); return c_reward[s->phase][gsn][1]; }
         if (rng_f64(c, actor, ST_AS_FP, 0) < 0.01) atomicOr(&ev_words[d >> 2], EV_NET << ((d & 3) * 8));
         return 0;
     }
-    c.x->green_act[g] = AC_SLEEP;
     return 0;
 }
 
 /* ------------------------------------------------------------------------------------------------ */
 /* red actions (lane 0)                                                                             */
 /* ------------------------------------------------------------------------------------------------ */
-__device__ int route(int src, int dst, int *out)
+__device__ __noinline__ int route(int src, int dst, int *out)
 {   /* hosts on the tree path src -> dst (Action.py:101-117, topology EnterpriseScenarioGenerator.py:373-416) */
     int n = 0;
     if (src == dst) { out[n++] = src; return n; }
     int ca[4], na = 0, cb[4], nb = 0;
-    for (int v = slot_subnet(src); v >= 0; v = c_tree_parent[v]) ca[na++] = v;
-    for (int v = slot_subnet(dst); v >= 0; v = c_tree_parent[v]) cb[nb++] = v;
+    _Pragma("unroll 1") for (int v = slot_subnet(src); v >= 0; v = c_tree_parent[v]) ca[na++] = v;
+    _Pragma("unroll 1") for (int v = slot_subnet(dst); v >= 0; v = c_tree_parent[v]) cb[nb++] = v;
     int ia = na - 1, ib = nb - 1;
     while (ia > 0 && ib > 0 && ca[ia - 1] == cb[ib - 1]) { ia--; ib--; }
     if (src < CC4_SLOT_ROUTER) out[n++] = src;
-    for (int i = 0; i <= ia; i++) out[n++] = ca[i] == S_INT ? CC4_SLOT_INTERNET : CC4_SLOT_ROUTER + ca[i];
-    for (int i = ib - 1; i >= 0; i--) out[n++] = cb[i] == S_INT ? CC4_SLOT_INTERNET : CC4_SLOT_ROUTER + cb[i];
+    _Pragma("unroll 1") for (int i = 0; i <= ia; i++) out[n++] = ca[i] == S_INT ? CC4_SLOT_INTERNET : CC4_SLOT_ROUTER + ca[i];
+    _Pragma("unroll 1") for (int i = ib - 1; i >= 0; i--) out[n++] = cb[i] == S_INT ? CC4_SLOT_INTERNET : CC4_SLOT_ROUTER + cb[i];
     if (dst < CC4_SLOT_ROUTER) out[n++] = dst;
     return n;
 }
 
 /* ExploitAction._create_new_session ExploitAction.py:212-262 */
-__device__ int exploit_new_session(Ctx &c, int r, int target)
+__device__ __noinline__ int exploit_new_session(Ctx &c, int r, int target)
 {
     int pid = create_pid(c, A_RED0 + r, target);
     proc_append(c, target, P_MAKE(pid, K_SHELL, 0, 0));
@@ -611,7 +652,7 @@ __device__ int exploit_new_session(Ctx &c, int r, int target)
     return pid;
 }
 
-__device__ int exec_red(Ctx &c, int r, const Act &a)
+__device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
 {
     Cc4Dyn *s = c.s;
     int actor = A_RED0 + r;
@@ -624,7 +665,7 @@ __device__ int exec_red(Ctx &c, int r, const Act &a)
         if (sn == S_INT) return SUCC_UNKNOWN;
         int nu = s->nuser[sn], nh = nu + s->nserver[sn];
         if (red_allowed(r, sn))     /* _filter_obs SimulationController.py:1054 drops interfaces of foreign subnets */
-            for (int k = 0; k < nh; k++) obs_entry(c, r, 1, k < nu ? sn * 16 + 6 + k : sn * 16 + (k - nu), 1, 1, 0, 0);
+            _Pragma("unroll 1") for (int k = 0; k < nh; k++) obs_entry(c, r, 1, k < nu ? sn * 16 + 6 + k : sn * 16 + (k - nu), 1, 1, 0, 0);
         return SUCC_TRUE;
     }
     case AC_AGGR: case AC_STEALTH: {   /* DiscoverNetworkServices.py:44-86 -> Portscan.py:23-65 */
@@ -633,7 +674,7 @@ __device__ int exec_red(Ctx &c, int r, const Act &a)
         double rate = a.code == AC_AGGR ? 0.75 : 0.25;
         double u = rng_f64(c, actor, ST_PORTSCAN, 0);
         int mask = 0, any = 0, h = a.host;
-        for (int i = p_begin(s, h); i < p_end(s, h); i++) {
+        _Pragma("unroll 1") for (int i = p_begin(s, h); i < p_end(s, h); i++) {
             uint32_t w = s->procs[i];
             if (P_DEAD(w)) continue;
             int pb = c_kind_portbit[P_KIND(w)];
@@ -643,7 +684,7 @@ __device__ int exec_red(Ctx &c, int r, const Act &a)
         }
         if (any) {
             int at = -1;
-            for (int i = 0; i < s->n_ports; i++) { uint32_t p = s->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)a.session && PT_HOST(p) == (uint32_t)h) { at = i; break; } }
+            _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = s->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)a.session && PT_HOST(p) == (uint32_t)h) { at = i; break; } }
             if (at < 0) { if (s->n_ports >= CC4_PORT_CAP) { fail(c, CC4_E_CAPACITY); at = 0; } else at = s->n_ports++; }
             s->ports[at] = PT_MAKE(mask, h, a.session, r);
             obs_entry(c, r, 1, h, 1, 0, 0, 0);
@@ -653,7 +694,7 @@ __device__ int exec_red(Ctx &c, int r, const Act &a)
     case AC_DD: {      /* DiscoverDeception.py:44-101 */
         if (si < 0) return SUCC_FALSE;
         int rep = 0, h = a.host;
-        for (int i = p_begin(s, h); i < p_end(s, h); i++) {
+        _Pragma("unroll 1") for (int i = p_begin(s, h); i < p_end(s, h); i++) {
             uint32_t w = s->procs[i];
             if (P_DEAD(w)) continue;
             bool decoy = P_KIND(w) >= K_D_APACHE && P_KIND(w) <= K_D_VSFTPD;
@@ -666,7 +707,7 @@ __device__ int exec_red(Ctx &c, int r, const Act &a)
     case AC_EXPLOIT: { /* ExploitRemoteService.py:149-202 */
         if (si < 0 || !S_abs) return SUCC_FALSE;
         int ports = -1, target = a.host, src = S_host;
-        for (int i = 0; i < s->n_ports; i++) { uint32_t p = s->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)a.session && PT_HOST(p) == (uint32_t)target) { ports = PT_MASK(p); break; } }
+        _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = s->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)a.session && PT_HOST(p) == (uint32_t)target) { ports = PT_MASK(p); break; } }
         if (ports < 0) return SUCC_FALSE;
         if (blocking(s, src, target)) return SUCC_FALSE;
         enum { X_HTTP, X_HTTPS, X_SSH, X_SQL, X_HARAKA };
@@ -680,17 +721,17 @@ __device__ int exec_red(Ctx &c, int r, const Act &a)
         int sel = opt[0];
         if (no > 1) {
             int top = 0;
-            for (int i = 1; i < no; i++) if (w10[i] > w10[top]) top = i;
-            for (int i = top; i + 1 < no; i++) opt[i] = opt[i + 1];
+            _Pragma("unroll 1") for (int i = 1; i < no; i++) if (w10[i] > w10[top]) top = i;
+            _Pragma("unroll 1") for (int i = top; i + 1 < no; i++) opt[i] = opt[i + 1];
             no--;
             sel = opt[rng_int(c, actor, ST_EXP_OTHER, (uint32_t)no)];
             (void)rng_f64(c, actor, ST_EXP_TOP, 0);
         }
         if (sel == X_SSH) {   /* SSHBruteForce.execute SSHBruteForce.py:24-84 */
             int hops[12], nh = route(src, target, hops);
-            for (int i = 0; i < nh; i++) if (0.05 < rng_f64(c, actor, ST_SSH_HOP, 0)) s->ev[hops[i]] |= EV_NET;
+            _Pragma("unroll 1") for (int i = 0; i < nh; i++) if (0.05 < rng_f64(c, actor, ST_SSH_HOP, 0)) s->ev[hops[i]] |= EV_NET;
             int vp = -1;
-            for (int i = p_begin(s, target); i < p_end(s, target); i++) if (!P_DEAD(s->procs[i]) && P_KIND(s->procs[i]) == K_SSHD) { vp = i; break; }
+            _Pragma("unroll 1") for (int i = p_begin(s, target); i < p_end(s, target); i++) if (!P_DEAD(s->procs[i]) && P_KIND(s->procs[i]) == K_SSHD) { vp = i; break; }
             if (vp < 0) return SUCC_FALSE;
             s->ev[target] |= EV_NET;
             int pid = exploit_new_session(c, r, target);
@@ -701,7 +742,7 @@ __device__ int exec_red(Ctx &c, int r, const Act &a)
         }
         /* ExploitAction.sim_exploit ExploitAction.py:48-116 */
         int vk = -1;
-        for (int i = p_begin(s, target); i < p_end(s, target) && vk < 0; i++) {
+        _Pragma("unroll 1") for (int i = p_begin(s, target); i < p_end(s, target) && vk < 0; i++) {
             uint32_t w = s->procs[i];
             if (P_DEAD(w)) continue;
             int k = P_KIND(w);
@@ -725,11 +766,11 @@ __device__ int exec_red(Ctx &c, int r, const Act &a)
     }
     case AC_PRIVESC: { /* PrivilegeEscalate.py:127-179 */
         int h = a.host, n = 0, tgt = -1;
-        for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_HOST(s->sess[i]) == (uint32_t)h) { n++; if (tgt < 0 && SF_ROOT(s->sessf[i])) tgt = i; }
+        _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_HOST(s->sess[i]) == (uint32_t)h) { n++; if (tgt < 0 && SF_ROOT(s->sessf[i])) tgt = i; }
         if (n == 0) return SUCC_FALSE;
         if (tgt < 0) {
             int pk = (int)rng_int(c, actor, ST_PRIV_SESS, (uint32_t)n);
-            for (int i = 0, k = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_HOST(s->sess[i]) == (uint32_t)h) { if (k == pk) { tgt = i; break; } k++; }
+            _Pragma("unroll 1") for (int i = 0, k = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_HOST(s->sess[i]) == (uint32_t)h) { if (k == pk) { tgt = i; break; } k++; }
             if (si < 0 || !S_abs) return SUCC_FALSE;
             s->sessf[tgt] |= 1u << 4;      /* EscalateAction.__upgrade_session EscalateAction.py:54-87 */
             int pi = proc_find(s, h, S_PID(s->sess[tgt]));
@@ -739,23 +780,23 @@ __device__ int exec_red(Ctx &c, int r, const Act &a)
         if (SF_ABS(s->sessf[tgt])) know_session(c, r, S_ID(s->sess[tgt]));
         if (si >= 0 && (h & 15) == 0) {   /* ExploreHost EscalateAction.py:90-106, Host.info = _between_subnet_links :418-468 */
             uint32_t lk = c_links[h >> 4];
-            for (int sn = 0; sn < 8; sn++) if (lk >> sn & 1) obs_entry(c, r, 0, sn * 16, 1, 0, 0, 0);
+            _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) if (lk >> sn & 1) obs_entry(c, r, 0, sn * 16, 1, 0, 0, 0);
         }
         return SUCC_TRUE;
     }
     case AC_IMPACT: case AC_DEGRADE: {   /* Impact.py:38-88, DegradeServices.py:38-82 */
         int h = a.host, any = 0, root = 0;
-        for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_HOST(s->sess[i]) == (uint32_t)h) { any = 1; root |= SF_ROOT(s->sessf[i]); }
+        _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_HOST(s->sess[i]) == (uint32_t)h) { any = 1; root |= SF_ROOT(s->sessf[i]); }
         if (!any || !root) return SUCC_FALSE;
         uint64_t v = s->svc64[h];
         int n = svc_count(v);
         if (a.code == AC_IMPACT) {
             int has_ot = 0;
-            for (int i = 0; i < n; i++) has_ot |= (SVC_ENTRY(v, i) & 15u) == K_OT;
+            _Pragma("unroll 1") for (int i = 0; i < n; i++) has_ot |= (SVC_ENTRY(v, i) & 15u) == K_OT;
             if (!has_ot || (v & SVC_OT_STOPPED)) return SUCC_FALSE;
             if (si < 0) return SUCC_FALSE;     /* StopService is a TargetedLocalAction: TargetedLocalAction.py:14-21 */
             s->svc64[h] = v | SVC_OT_STOPPED;  /* Host.stop_service Host.py:296-301 */
-            for (int i = p_begin(s, h); i < p_end(s, h); i++) {   /* State.remove_process State.py:390-418 */
+            _Pragma("unroll 1") for (int i = p_begin(s, h); i < p_end(s, h); i++) {   /* State.remove_process State.py:390-418 */
                 uint32_t w = s->procs[i];
                 if (!P_DEAD(w) && P_KIND(w) == K_OT && P_SVC(w)) {
                     int s2 = session_from_pid(s, h, P_PID(w));
@@ -766,7 +807,7 @@ __device__ int exec_red(Ctx &c, int r, const Act &a)
             }
         } else {
             int na = 0;
-            for (int i = 0; i < n; i++) { uint32_t e = SVC_ENTRY(v, i); if (!svc_active(v, e)) continue; na++; uint32_t rel = e >> 4; rel = rel > 0 ? rel - 1 : 0; v = svc_set(v, i, (e & 15u) | rel << 4); }
+            _Pragma("unroll 1") for (int i = 0; i < n; i++) { uint32_t e = SVC_ENTRY(v, i); if (!svc_active(v, e)) continue; na++; uint32_t rel = e >> 4; rel = rel > 0 ? rel - 1 : 0; v = svc_set(v, i, (e & 15u) | rel << 4); }
             if (na == 0) return SUCC_FALSE;
             s->svc64[h] = v;
         }
@@ -778,42 +819,32 @@ __device__ int exec_red(Ctx &c, int r, const Act &a)
     }
 }
 
-/* RedSessionCheck.execute RedSessionCheck.py:9-63 */
-__device__ void red_session_check(Ctx &c, int r)
+/* RedSessionCheck._choose_new_primary_session RedSessionCheck.py:34-55 (lane 0; agent r holds n sessions, none with ident 0) */
+__device__ __noinline__ void rsc_reelect(Ctx &c, int r, int n)
 {
     Cc4Dyn *s = c.s;
-    Act rsc = { AC_RSC, -1, -1, 0 };
-    obs_push(c, r, SUCC_TRUE, true, rsc);
-    if (s->sess_count[r] == 0) return;
-    int n = sess_count_agent(s, r);
-    if (n == 0) { fail(c, CC4_E_UNREACHABLE); return; }
-    if (sess_find(s, r, 0) < 0) {
-        int pk = (int)rng_int(c, A_RED0 + r, ST_RSC_PRIMARY, (uint32_t)n), at = -1;
-        for (int i = 0, k = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r) { if (k == pk) { at = i; break; } k++; }
-        uint32_t w = s->sess[at]; uint8_t f = s->sessf[at];
-        int old_id = S_ID(w);
-        for (int i = 0; i < s->n_ports; i++) { uint32_t p = s->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)old_id) s->ports[i] = PT_MAKE(PT_MASK(p), PT_HOST(p), 0, r); }
-        for (int i = at; i + 1 < s->n_sess; i++) { s->sess[i] = s->sess[i + 1]; s->sessf[i] = s->sessf[i + 1]; }
-        s->sess[s->n_sess - 1] = S_MAKE(S_PID(w), 0, S_HOST(w)); s->sessf[s->n_sess - 1] = f;
-    }
-    for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r) {
-        obs_entry(c, r, 0, S_HOST(s->sess[i]), 1, 1, 1, 1);
-        if (SF_ABS(s->sessf[i])) know_session(c, r, S_ID(s->sess[i]));
-    }
+    int pk = (int)rng_int(c, A_RED0 + r, ST_RSC_PRIMARY, (uint32_t)n), at = -1;
+    _Pragma("unroll 1") for (int i = 0, k = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r) { if (k == pk) { at = i; break; } k++; }
+    if (at < 0) { fail(c, CC4_E_UNREACHABLE); return; }
+    uint32_t w = s->sess[at]; uint8_t f = s->sessf[at];
+    int old_id = S_ID(w);
+    _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = s->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)old_id) s->ports[i] = PT_MAKE(PT_MASK(p), PT_HOST(p), 0, r); }
+    _Pragma("unroll 1") for (int i = at; i + 1 < s->n_sess; i++) { s->sess[i] = s->sess[i + 1]; s->sessf[i] = s->sessf[i + 1]; }
+    s->sess[s->n_sess - 1] = S_MAKE(S_PID(w), 0, S_HOST(w)); s->sessf[s->n_sess - 1] = f;
 }
 
 /* SimulationController.different_subnet_agent_reassignment :820-903 */
-__device__ void reassign(Ctx &c)
+__device__ __noinline__ void reassign(Ctx &c)
 {
     Cc4Dyn *s = c.s; Scratch *x = c.x;
     uint8_t list[32]; int n = 0;   /* (agent, ident) pairs, agents ascending then dict order */
     uint8_t lid[32];
-    for (int r = 0; r < CC4_NRED; r++)
-        for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && !red_allowed(r, S_HOST(s->sess[i]) >> 4)) {
+    _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++)
+        _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && !red_allowed(r, S_HOST(s->sess[i]) >> 4)) {
             if (n >= 32) { fail(c, CC4_E_CAPACITY); break; }
             list[n] = (uint8_t)r; lid[n] = (uint8_t)S_ID(s->sess[i]); n++;
         }
-    for (int k = 0; k < n; k++) {
+    _Pragma("unroll 1") for (int k = 0; k < n; k++) {
         int r = list[k], si = sess_find(s, r, lid[k]);
         uint32_t w = s->sess[si]; uint8_t f = s->sessf[si];
         int host = S_HOST(w), nr = red_of_subnet(host >> 4);
@@ -821,7 +852,7 @@ __device__ void reassign(Ctx &c)
         sess_delete(s, si);
         int nid = sess_add(c, nr, host, 1, SF_ROOT(f), S_PID(w));
         if (s->sess_count[r] > 0) s->sess_count[r]--;
-        for (int i = 0; i < x->n_oent[r]; i++) {
+        _Pragma("unroll 1") for (int i = 0; i < x->n_oent[r]; i++) {
             uint16_t e = x->oent[r][i];
             if (((e >> 8) & 1) && (e & 0xFF) == host) {
                 if (!((e >> 12) & 1)) { fail(c, CC4_E_UNREACHABLE); break; }
@@ -833,9 +864,6 @@ __device__ void reassign(Ctx &c)
             }
         }
     }
-    uint8_t act = 0;
-    for (int i = 0; i < s->n_sess; i++) act |= (uint8_t)(1u << SF_AGENT(s->sessf[i]));
-    s->red_active = act;    /* :896-903: an agent is active iff it holds a session */
 }
 
 }  // namespace cc4

@@ -85,11 +85,11 @@ __device__ void w_write_obs(const Cc4Dyn *s, uint8_t *obs /* [5][210] of this ep
 {
     /* 1050 bytes; 4 bytes per lane per iteration, written as one aligned 32-bit word (210*5 = 1050, base is 2-byte
        aligned only for odd episodes, so use byte stores for the ragged tail) */
-    for (int i = lane_id(); i < CC4_N_BLUE * CC4_OBS_LEN; i += 32) obs[i] = obs_element(s, i / CC4_OBS_LEN, i % CC4_OBS_LEN);
+    _Pragma("unroll 1") for (int i = lane_id(); i < CC4_N_BLUE * CC4_OBS_LEN; i += 32) obs[i] = obs_element(s, i / CC4_OBS_LEN, i % CC4_OBS_LEN);
 }
 __device__ void w_write_mask(const Cc4Dyn *s, uint8_t *mask)
 {
-    for (int i = lane_id(); i < CC4_N_BLUE * CC4_MASK_LEN; i += 32) {
+    _Pragma("unroll 1") for (int i = lane_id(); i < CC4_N_BLUE * CC4_MASK_LEN; i += 32) {
         int b = i / CC4_MASK_LEN, k = i % CC4_MASK_LEN, m = 0;
         if (k < (b == 4 ? 242 : 82)) blue_decode(s, b, k, &m);
         mask[i] = (uint8_t)m;
@@ -102,7 +102,7 @@ __device__ void w_write_mask(const Cc4Dyn *s, uint8_t *mask)
 __device__ void w_monitor_all(Ctx &c)
 {
     Cc4Dyn *s = c.s;
-    for (int h = lane_id(); h < CC4_NSLOT; h += 32) {
+    _Pragma("unroll 1") for (int h = lane_id(); h < CC4_NSLOT; h += 32) {
         if (blue_of_subnet(slot_subnet(h)) < 0) continue;     /* contractor network and internet have no blue agent */
         uint32_t e = s->ev[h];
         s->ev[h] = (uint8_t)((e & (EV_PROC | EV_NET)) << 2);
@@ -110,7 +110,7 @@ __device__ void w_monitor_all(Ctx &c)
     __syncwarp();
     if (lane_id() == 0) {
         Scratch *x = c.x;
-        for (int i = 0; i < x->n_evpid; i++) {
+        _Pragma("unroll 1") for (int i = 0; i < x->n_evpid; i++) {
             int slot = x->evpid[i] >> 16, b = blue_of_subnet(slot_subnet(slot));
             if (s->n_sus >= CC4_SUS_CAP) { fail(c, CC4_E_CAPACITY); break; }
             s->sus[s->n_sus++] = SU_MAKE(x->evpid[i] & 0xFFFFu, slot, b);
@@ -123,9 +123,9 @@ __device__ void w_monitor_all(Ctx &c)
 __device__ void monitor_one(Ctx &c, int b)
 {
     Cc4Dyn *s = c.s; Scratch *x = c.x;
-    for (int h = 0; h < CC4_NSLOT; h++) if (blue_of_subnet(slot_subnet(h)) == b) { uint32_t e = s->ev[h]; s->ev[h] = (uint8_t)((e & (EV_PROC | EV_NET)) << 2); }
+    _Pragma("unroll 1") for (int h = 0; h < CC4_NSLOT; h++) if (blue_of_subnet(slot_subnet(h)) == b) { uint32_t e = s->ev[h]; s->ev[h] = (uint8_t)((e & (EV_PROC | EV_NET)) << 2); }
     int w = 0;
-    for (int i = 0; i < x->n_evpid; i++) {
+    _Pragma("unroll 1") for (int i = 0; i < x->n_evpid; i++) {
         int slot = x->evpid[i] >> 16;
         if (blue_of_subnet(slot_subnet(slot)) != b) { x->evpid[w++] = x->evpid[i]; continue; }
         if (s->n_sus >= CC4_SUS_CAP) { fail(c, CC4_E_CAPACITY); continue; }
@@ -135,21 +135,65 @@ __device__ void monitor_one(Ctx &c, int b)
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* session-pool digests (lane per session)                                                          */
+/* ------------------------------------------------------------------------------------------------ */
+__device__ void w_scan_sessions(Ctx &c)
+{
+    Cc4Dyn *s = c.s; Scratch *x = c.x;
+    const int lane = lane_id();
+    if (lane < 24) (&x->sess_hosts[0][0])[lane] = 0;
+    if (lane < 8) x->n_red[lane] = 0;
+    if (lane == 8) { x->has0 = 0; x->newss = 0; x->misplaced = 0; }
+    __syncwarp();
+    const int n = s->n_sess;
+    _Pragma("unroll 1") for (int i = lane; i < n; i += 32) {
+        uint32_t w = s->sess[i], f = s->sessf[i], r = SF_AGENT(f), h = S_HOST(w), id = S_ID(w);
+        atomicOr(&x->sess_hosts[r][h >> 5], 1u << (h & 31));
+        atomicAdd(&x->n_red[r], 1);
+        if (id == 0) atomicOr(&x->has0, 1u << r);
+        if (!red_allowed((int)r, (int)(h >> 4))) atomicOr(&x->misplaced, 1u << r);
+        if (SF_ABS(f) && !(x->ssmask[r][id >> 5] >> (id & 31) & 1)) atomicOr(&x->newss, 1u << r);
+    }
+    __syncwarp();
+}
+__device__ void w_build_hostagents(Ctx &c)
+{
+    Cc4Dyn *s = c.s; Scratch *x = c.x;
+    x->hostagents[lane_id()] = 0;
+    __syncwarp();
+    _Pragma("unroll 1") for (int i = lane_id(); i < s->n_sess; i += 32) {
+        uint32_t h = S_HOST(s->sess[i]);
+        atomicOr(&x->hostagents[h >> 2], (1u << SF_AGENT(s->sessf[i])) << ((h & 3) * 8));
+    }
+    __syncwarp();
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* one tick: SimulationController.step SimulationController.py:211-315                              */
 /* ------------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ Act unpack_act(uint32_t w)
+{
+    Act a = { (int)IP_CODE(w), IP_HOST(w) == 255 ? -1 : (int)IP_HOST(w), IP_SUBNET(w) == 15 ? -1 : (int)IP_SUBNET(w), (int)IP_SESSION(w) };
+    return a;
+}
+__device__ __forceinline__ uint32_t pack_act(const Act &a, int ticks) { return IP_MAKE(a.code, a.host < 0 ? 255 : a.host, a.subnet < 0 ? 15 : a.subnet, a.session, ticks); }
+
 __device__ void w_tick(Ctx &c, const int32_t *actions /* [5] */, const uint8_t *msgs /* [5] or null */, float *reward_out, uint8_t *done_out)
 {
     Cc4Dyn *s = c.s; Scratch *x = c.x;
     const int lane = lane_id();
     c.tick = s->step;
-    for (int i = lane; i <= NAG; i += 32) x->ctr[i] = 0;
+    _Pragma("unroll 1") for (int i = lane; i <= NAG; i += 32) x->ctr[i] = 0;
     if (lane < 8) { x->n_oent[lane] = 0; x->have_first[lane] = 0; x->succ0[lane] = SUCC_UNKNOWN; x->has_act0[lane] = 0; }
-    if (lane == 0) { x->n_evpid = 0; x->reward = 0; }
+    (&x->ssmask[0][0])[lane] = 0;
+    if (lane < 16) (&x->ssmask[0][0])[32 + lane] = 0;
     __syncwarp();
-
-    Act sub[11];
-    int cost = 0;
+    _Pragma("unroll 1") for (int i = lane; i < CC4_NRED * CC4_SS_CAP; i += 32) {
+        int r = i / CC4_SS_CAP, k = i % CC4_SS_CAP;
+        if (k < s->n_ss[r]) { uint32_t id = s->ss[r][k]; atomicOr(&x->ssmask[r][id >> 5], 1u << (id & 31)); }
+    }
     if (lane == 0) {
+        x->n_evpid = 0; x->reward = 0;
         /* mission phase: State.check_next_phase_on_update_step State.py:514-544, phases EnterpriseScenarioGenerator.py:854-860 */
         int q = c.steps / 3, rem = c.steps % 3, l0 = q + (rem >= 1), l1 = q + (rem == 2);
         int np = c.tick < l0 ? 0 : c.tick < l0 + l1 ? 1 : 2;
@@ -158,89 +202,131 @@ __device__ void w_tick(Ctx &c, const int32_t *actions /* [5] */, const uint8_t *
     }
     __syncwarp();
 
-    /* ---- 1. policies (:236-248).  green: lane per agent (EnterpriseGreenAgent.py:42-78); the whole green action is
-       resolved here except its phishing side effect, which is replayed in agent order below.  This is legal because
-       nothing a blue action does (executed before green) is visible to the draws themselves, but the OUTCOME of a green
-       action depends on blue's Restore / Block of the same tick, so the evaluation happens after the blue phase. ---- */
-    if (lane == 0) {
-        for (int b = 0; b < CC4_NBLUE; b++) { sub[b] = blue_decode(s, b, actions[b], nullptr); if (sub[b].code == AC_RESTORE) cost -= 1; }   /* Restore.py:70, :310-311 */
-        for (int r = 0; r < CC4_NRED; r++) {
-            Act a = { AC_SLEEP, -1, -1, 0 };
-            if (s->red_active >> r & 1) a = red_policy(c, r);
-            sub[A_RED0 + r] = a;
+    /* ---- 1. policies (:236-248) and 2. duration queue (:245-265): one lane per blue / red actor.  The scripted red
+       agents only read their own knowledge and draw from their own stream, so the six run side by side. ---- */
+    int cost = 0;
+    if (lane < 11) {
+        Act a = { AC_SLEEP, -1, -1, 0 };
+        if (lane < A_RED0) { a = blue_decode(s, lane, actions[lane], nullptr); if (a.code == AC_RESTORE) cost = -1; }   /* Restore.py:70, :310-311 */
+        else if (s->red_active >> (lane - A_RED0) & 1) a = red_policy(c, lane - A_RED0);
+        uint32_t ip = s->inprog[lane];
+        if (IP_CODE(ip) == IP_NONE) ip = pack_act(a, c_duration[a.code]);
+        int ticks = (int)IP_TICKS(ip) - 1;
+        if (ticks < 1) { x->subw[lane] = ip & ~(0xFu << 26); s->inprog[lane] = IP_NONE; }
+        else {
+            s->inprog[lane] = (ip & ~(0xFu << 26)) | (uint32_t)ticks << 26;
+            Act none = { AC_SLEEP, -1, -1, 0 };
+            x->subw[lane] = pack_act(none, 0);
+            if (lane >= A_RED0) obs_push(c, lane - A_RED0, SUCC_INPROG, false, none);
         }
-        /* ---- 2. duration queue (:245-265) for blue and red; green actions always last one tick ---- */
-        for (int a = 0; a < 11; a++) {
-            uint32_t ip = s->inprog[a];
-            if (IP_CODE(ip) == IP_NONE) ip = IP_MAKE(sub[a].code, sub[a].host < 0 ? 255 : sub[a].host, sub[a].subnet < 0 ? 15 : sub[a].subnet, sub[a].session, c_duration[sub[a].code]);
-            int ticks = (int)IP_TICKS(ip) - 1;
-            if (ticks < 1) {
-                sub[a].code = IP_CODE(ip); sub[a].host = IP_HOST(ip) == 255 ? -1 : (int)IP_HOST(ip); sub[a].subnet = IP_SUBNET(ip) == 15 ? -1 : (int)IP_SUBNET(ip); sub[a].session = IP_SESSION(ip);
-                s->inprog[a] = IP_NONE;
-            } else {
-                s->inprog[a] = (ip & ~(0xFu << 26)) | (uint32_t)ticks << 26;
-                sub[a].code = AC_SLEEP; sub[a].host = sub[a].subnet = -1; sub[a].session = 0;
-                if (a >= A_RED0) { Act none = { AC_SLEEP, -1, -1, 0 }; obs_push(c, a - A_RED0, SUCC_INPROG, false, none); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o);
+    __syncwarp();
+    /* filter_actions (:466-486) looks at the sessions as they are BEFORE anything executes; blue / green sessions never go away */
+    _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
+        uint32_t w = x->subw[A_RED0 + r];
+        bool needs = !(IP_CODE(w) == AC_SLEEP || IP_CODE(w) == AC_INVALID), found = false;
+        if (needs) {
+            uint32_t id = IP_SESSION(w);
+            _Pragma("unroll 1") for (int base = 0; base < s->n_sess && !found; base += 32) {
+                int i = base + lane;
+                bool m = i < s->n_sess && SF_AGENT(s->sessf[i]) == (uint32_t)r && S_ID(s->sess[i]) == id;
+                found = __any_sync(0xFFFFFFFFu, m);
             }
-            x->cur_code[a] = (uint8_t)sub[a].code;
-            if (a >= A_RED0) x->cur_host[a] = (uint8_t)(sub[a].host < 0 ? 255 : sub[a].host);
         }
-        /* filter_actions (:466-486) looks at the sessions as they are BEFORE anything executes; blue / green sessions never go away */
-        for (int r = 0; r < CC4_NRED; r++) {
-            int code = sub[A_RED0 + r].code;
-            x->dropped[A_RED0 + r] = !(code == AC_SLEEP || code == AC_INVALID) && sess_find(s, r, sub[A_RED0 + r].session) < 0;
-        }
-        /* ---- 3. execution: priority-1 ControlTraffic first (ControlTraffic.py:19), then agent order ---- */
-        for (int pass = 0; pass < 2; pass++)
-            for (int b = 0; b < CC4_NBLUE; b++) {
-                bool prio1 = sub[b].code == AC_BLOCK || sub[b].code == AC_ALLOW;
-                if ((pass == 0) != prio1) continue;
-                if (sub[b].code == AC_MONITOR) monitor_one(c, b); else exec_blue(c, b, sub[b]);
+        if (lane == 0) x->dropped[A_RED0 + r] = needs && !found;
+    }
+    __syncwarp();
+    /* ---- 3. execution: priority-1 ControlTraffic first (ControlTraffic.py:19), then agent order ---- */
+    if (lane == 0) {
+        _Pragma("unroll 1") for (int pass = 0; pass < 2; pass++)
+            _Pragma("unroll 1") for (int b = 0; b < CC4_NBLUE; b++) {
+                Act a = unpack_act(x->subw[b]);
+                bool prio1 = a.code == AC_BLOCK || a.code == AC_ALLOW;
+                if ((pass == 0) != prio1 || a.code == AC_SLEEP) continue;
+                if (a.code == AC_MONITOR) monitor_one(c, b); else exec_blue(c, b, a);
             }
     }
     __syncwarp();
-    /* green agents, lane per agent */
+    /* green agents, lane per agent (EnterpriseGreenAgent.py:42-78); the phishing side effect is order dependent and
+       replayed below in agent order */
     {
         int rew = 0;
         uint32_t *ev_words = reinterpret_cast<uint32_t *>(s->ev);
-        for (int g = lane; g < s->ngreen; g += 32) rew += green_tick(c, g, ev_words);
+        const int ng = s->ngreen;
+        uint32_t any_phish = 0;
+        _Pragma("unroll 1") for (int k = 0; k < 3; k++) {
+            int g = k * 32 + lane;
+            bool ph = false;
+            if (g < ng) rew += green_tick(c, g, ev_words, &ph);
+            uint32_t bal = __ballot_sync(0xFFFFFFFFu, ph);
+            if (lane == 0) x->phish[k] = bal;
+            any_phish |= bal;
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) rew += __shfl_xor_sync(0xFFFFFFFFu, rew, o);
         if (lane == 0) x->reward += rew;
+        __syncwarp();
+        if (any_phish) {
+            w_build_hostagents(c);
+            if (lane == 0)
+                _Pragma("unroll 1") for (int k = 0; k < 3; k++) { uint32_t m = x->phish[k]; while (m) { int b = __ffs(m) - 1; m &= m - 1; do_phishing(c, k * 32 + b); } }
+            __syncwarp();
+        }
     }
-    __syncwarp();
     if (lane == 0) {
-        for (int g = 0; g < s->ngreen; g++) if (x->green_phish[g]) do_phishing(c, g);
-        for (int r = 0; r < CC4_NRED; r++) {
+        _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
             int a = A_RED0 + r;
             if (x->dropped[a]) continue;
-            int succ = exec_red(c, r, sub[a]);
-            obs_push(c, r, succ, true, sub[a]);
+            Act act = unpack_act(x->subw[a]);
+            int succ = exec_red(c, r, act);
+            obs_push(c, r, succ, true, act);
         }
-        /* ---- 4. reassignment (:278) ---- */
-        reassign(c);
     }
     __syncwarp();
+    /* ---- 4. reassignment (:278) ---- */
+    w_scan_sessions(c);
+    if (x->misplaced) {
+        if (lane == 0) reassign(c);
+        __syncwarp();
+        w_scan_sessions(c);
+    }
+    uint32_t active = 0;
+    _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) active |= (x->n_red[r] > 0) << r;    /* :896-903: active iff it holds a session */
     /* ---- 5. end-turn actions (:281-286): Monitor for blue, RedSessionCheck for active red ---- */
     w_monitor_all(c);
     if (lane == 0) {
-        for (int r = 0; r < CC4_NRED; r++) if (s->red_active >> r & 1) red_session_check(c, r);
+        s->red_active = (uint8_t)active;
+        /* RedSessionCheck re-elects a primary session when ident 0 is gone (changes the session order: serial) */
+        _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++)
+            if ((active >> r & 1) && s->sess_count[r] != 0 && !(x->has0 >> r & 1)) rsc_reelect(c, r, x->n_red[r]);
+    }
+    __syncwarp();
+    if (lane < CC4_NRED && (active >> lane & 1)) {
+        Act rsc = { AC_RSC, -1, -1, 0 };
+        obs_push(c, lane, SUCC_TRUE, true, rsc);
         /* the FSM agents digest the tick's observation now instead of at the start of the next tick */
-        for (int r = 0; r < CC4_NRED; r++) if (s->red_active >> r & 1) fsm_digest(c, r);
+        agent_end_turn(c, lane);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        s->fsm_started |= (uint8_t)active;
         /* ---- 6. counters, done (:297-300), reward (BlueRewardMachine.py:70-121) ---- */
         s->step++;
         s->done = s->step >= c.steps - 1;
         int rew = x->reward;
-        for (int r = 0; r < CC4_NRED; r++) {
+        _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
             /* `success and isinstance(action, Impact)` BlueRewardMachine.py:118: a TernaryEnum member is always truthy
                (Enums.py:5-24), so every Impact that comes due costs RIA while the agent holds a session */
-            if (x->cur_code[A_RED0 + r] == AC_IMPACT && (s->red_active >> r & 1)) rew += c_reward[s->phase][x->cur_host[A_RED0 + r] >> 4][2];
+            uint32_t w = x->subw[A_RED0 + r];
+            if (IP_CODE(w) == AC_IMPACT && (active >> r & 1)) rew += c_reward[s->phase][IP_HOST(w) >> 4][2];
         }
-        for (int b = 0; b < CC4_NBLUE; b++) s->msgs[b] = msgs ? msgs[b] : 0;
+        _Pragma("unroll 1") for (int b = 0; b < CC4_NBLUE; b++) s->msgs[b] = msgs ? msgs[b] : 0;
         if (reward_out) *reward_out = (float)(rew + cost);
         if (done_out) *done_out = s->done;
         if (c.rng_mode == 1) {
-            for (int a = 0; a < NAG; a++) {
+            _Pragma("unroll 1") for (int a = 0; a < NAG; a++) {
                 uint32_t seg = 1u + (uint32_t)c.tick * NAG + (uint32_t)a;
                 if (seg < c.n_segs && x->ctr[a] != c.seg[seg + 1] - c.seg[seg]) fail(c, CC4_E_TAPE_LEFT);
             }
@@ -283,13 +369,13 @@ k_rollout(Params p, int n_ticks, uint32_t pk0, uint32_t pk1, float *reward_sum, 
     __shared__ int32_t act_s[WARPS_PER_BLOCK][8];
     __shared__ float rew_s[WARPS_PER_BLOCK];
     int32_t *act = act_s[threadIdx.x >> 5];
-    for (int t = 0; t < n_ticks; t++) {
+    _Pragma("unroll 1") for (int t = 0; t < n_ticks; t++) {
         if (w->dyn.done) break;
         if (lane_id() == 0) {
             uint32_t tk = w->dyn.step;
             uint32_t c1[4] = { tk, 0xB10Eu, (uint32_t)ep, (uint32_t)(ep >> 32) }, c2[4] = { tk, 0xB10Fu, (uint32_t)ep, (uint32_t)(ep >> 32) };
             philox4x32_10(c1, pk0, pk1); philox4x32_10(c2, pk0, pk1);
-            for (int b = 0; b < 4; b++) act[b] = (int32_t)__umulhi(c1[b], 82u);
+            _Pragma("unroll 1") for (int b = 0; b < 4; b++) act[b] = (int32_t)__umulhi(c1[b], 82u);
             act[4] = (int32_t)__umulhi(c2[0], 242u);
         }
         __syncwarp();
@@ -315,7 +401,7 @@ struct ResetSmem {
 
 __device__ int gen_pid(Ctx &c, ResetTmp *t)
 {
-    for (int guard = 0; guard < 64; guard++) {
+    _Pragma("unroll 1") for (int guard = 0; guard < 64; guard++) {
         int v = (int)rng_int(c, NAG, ST_R_PID, 9000);
         if (c.s->err & CC4_E_TAPE_END) return 1000 + v;
         if (!(t->used[v >> 5] >> (v & 31) & 1)) { t->used[v >> 5] |= 1u << (v & 31); return 1000 + v; }
@@ -332,22 +418,22 @@ __device__ void gen_host(Ctx &c, ResetTmp *t, int slot)
     codes[n] = K_SSHD; pids[n++] = gen_pid(c, t);
     if (sn == S_OZA || sn == S_OZB) { codes[n] = K_OT; pids[n++] = gen_pid(c, t); }
     int opt[3] = { K_APACHE2, K_MYSQLD, K_SMTP }, nopt = 3; uint32_t optpid[3];
-    for (int i = 0; i < 3; i++) optpid[i] = gen_pid(c, t);
+    _Pragma("unroll 1") for (int i = 0; i < 3; i++) optpid[i] = gen_pid(c, t);
     int nadd = (int)rng_int(c, NAG, ST_R_NADDON, 4);
-    for (int i = 0; i < nadd; i++) {
+    _Pragma("unroll 1") for (int i = 0; i < nadd; i++) {
         int k = (int)rng_int(c, NAG, ST_R_ADDON, (uint32_t)nopt);
         codes[n] = opt[k]; pids[n++] = optpid[k];
-        for (int j = k; j + 1 < nopt; j++) { opt[j] = opt[j + 1]; optpid[j] = optpid[j + 1]; }
+        _Pragma("unroll 1") for (int j = k; j + 1 < nopt; j++) { opt[j] = opt[j + 1]; optpid[j] = optpid[j + 1]; }
         nopt--;
     }
-    for (int i = 0; i < n; i++) { v = svc_set(v, i, (uint32_t)codes[i] | 5u << 4); t->procs[slot][i] = P_MAKE(pids[i], codes[i], 0, 1); }
+    _Pragma("unroll 1") for (int i = 0; i < n; i++) { v = svc_set(v, i, (uint32_t)codes[i] | 5u << 4); t->procs[slot][i] = P_MAKE(pids[i], codes[i], 0, 1); }
     t->np[slot] = (uint8_t)n;
     s->svc64[slot] = v;
 }
 __device__ int tmp_create_pid(Ctx &c, ResetTmp *t, int slot)
 {
     uint32_t mx = 0;
-    for (int i = 0; i < t->np[slot]; i++) if (P_PID(t->procs[slot][i]) > mx) mx = P_PID(t->procs[slot][i]);
+    _Pragma("unroll 1") for (int i = 0; i < t->np[slot]; i++) if (P_PID(t->procs[slot][i]) > mx) mx = P_PID(t->procs[slot][i]);
     return (int)(mx + 1 + rng_int(c, NAG, ST_CREATE_PID, 9));
 }
 __device__ void tmp_add_session_proc(Ctx &c, ResetTmp *t, int slot, int kind)
@@ -370,25 +456,25 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
         c.tape = p.tape; c.seg = p.seg_off ? p.seg_off + (size_t)env * (p.n_segs + 1) : nullptr; c.n_segs = p.n_segs; c.tick = -1;
     }
     uint32_t *z = reinterpret_cast<uint32_t *>(w);
-    for (int i = lane_id(); i < (int)(sizeof(ResetSmem) / 4); i += 32) z[i] = 0;
+    _Pragma("unroll 1") for (int i = lane_id(); i < (int)(sizeof(ResetSmem) / 4); i += 32) z[i] = 0;
     __syncwarp();
     if (lane_id() == 0) {
         Cc4Dyn *s = c.s; ResetTmp *t = &w->t; Cc4Stat *st = c.st;
-        for (int h = 0; h < 128; h++) s->svc64[h] = SVC_EMPTY;
-        for (int a = 0; a < 16; a++) s->inprog[a] = IP_NONE;
+        _Pragma("unroll 1") for (int h = 0; h < 128; h++) s->svc64[h] = SVC_EMPTY;
+        _Pragma("unroll 1") for (int a = 0; a < 16; a++) s->inprog[a] = IP_NONE;
         /* hosts, EnterpriseScenarioGenerator._generate_hosts :312-371 */
-        for (int sn = 0; sn < 8; sn++) {
+        _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) {
             s->nuser[sn] = (uint8_t)(3 + rng_int(c, NAG, ST_R_NUSER, 8));
-            for (int i = 0; i < s->nuser[sn]; i++) gen_host(c, t, sn * 16 + 6 + i);
+            _Pragma("unroll 1") for (int i = 0; i < s->nuser[sn]; i++) gen_host(c, t, sn * 16 + 6 + i);
             s->nserver[sn] = (uint8_t)(1 + rng_int(c, NAG, ST_R_NSERVER, 6));
-            for (int i = 0; i < s->nserver[sn]; i++) gen_host(c, t, sn * 16 + i);
+            _Pragma("unroll 1") for (int i = 0; i < s->nserver[sn]; i++) gen_host(c, t, sn * 16 + i);
         }
         /* blue agents :631-698 */
-        for (int b = 0; b < CC4_NBLUE; b++) {
+        _Pragma("unroll 1") for (int b = 0; b < CC4_NBLUE; b++) {
             int n = 0;
-            for (int i = 0; i < (b == 4 ? 3 : 1); i++) { int sn = b < 4 ? b : S_PAZ + i; n += 1 + s->nuser[sn] + s->nserver[sn]; }
+            _Pragma("unroll 1") for (int i = 0; i < (b == 4 ? 3 : 1); i++) { int sn = b < 4 ? b : S_PAZ + i; n += 1 + s->nuser[sn] + s->nserver[sn]; }
             int pk = (int)rng_int(c, NAG, ST_R_BLUE_PARENT, (uint32_t)n), parent = -1;
-            for (int i = 0, k = 0; i < (b == 4 ? 3 : 1) && parent < 0; i++) {
+            _Pragma("unroll 1") for (int i = 0, k = 0; i < (b == 4 ? 3 : 1) && parent < 0; i++) {
                 int sn = b < 4 ? b : S_PAZ + i, nu = s->nuser[sn], m = 1 + nu + s->nserver[sn];
                 if (pk < k + m) { int j = pk - k; parent = j == 0 ? CC4_SLOT_ROUTER + sn : j <= nu ? sn * 16 + 6 + (j - 1) : sn * 16 + (j - 1 - nu); }
                 k += m;
@@ -397,10 +483,10 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
         }
         /* green agents :700-749 */
         int ng = 0;
-        for (int sn = 0; sn < 8; sn++) for (int k = 0; k < s->nuser[sn]; k++) s->green_host[ng++] = (uint8_t)(sn * 16 + 6 + k);
+        _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) for (int k = 0; k < s->nuser[sn]; k++) s->green_host[ng++] = (uint8_t)(sn * 16 + 6 + k);
         s->ngreen = (uint8_t)ng;
         /* red agents :751-812 */
-        for (int r = 0; r < CC4_NRED; r++) {
+        _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
             int ns = r == 5 ? 3 : 1;
             int si = (int)rng_int(c, NAG, ST_R_RED_SUBNET, (uint32_t)ns);
             int sn = r == 0 ? S_CON : r <= 4 ? r - 1 : S_PAZ + si;
@@ -408,16 +494,16 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
             st->red_start[r] = (uint8_t)(k < s->nuser[sn] ? sn * 16 + 6 + k : sn * 16 + (k - s->nuser[sn]));
         }
         /* State.__init__ State.py:108-134: session processes (Host.add_session Host.py:189-196) */
-        for (int b = 0; b < CC4_NBLUE; b++) {
+        _Pragma("unroll 1") for (int b = 0; b < CC4_NBLUE; b++) {
             tmp_add_session_proc(c, t, st->blue_parent[b], K_SESSION);
-            for (int i = 0; i < (b == 4 ? 3 : 1); i++) {
+            _Pragma("unroll 1") for (int i = 0; i < (b == 4 ? 3 : 1); i++) {
                 int sn = b < 4 ? b : S_PAZ + i;
                 if (st->blue_parent[b] != CC4_SLOT_ROUTER + sn) tmp_add_session_proc(c, t, CC4_SLOT_ROUTER + sn, K_SESSION);
-                for (int k = 0; k < s->nuser[sn]; k++) if (st->blue_parent[b] != sn * 16 + 6 + k) tmp_add_session_proc(c, t, sn * 16 + 6 + k, K_SESSION);
-                for (int k = 0; k < s->nserver[sn]; k++) if (st->blue_parent[b] != sn * 16 + k) tmp_add_session_proc(c, t, sn * 16 + k, K_SESSION);
+                _Pragma("unroll 1") for (int k = 0; k < s->nuser[sn]; k++) if (st->blue_parent[b] != sn * 16 + 6 + k) tmp_add_session_proc(c, t, sn * 16 + 6 + k, K_SESSION);
+                _Pragma("unroll 1") for (int k = 0; k < s->nserver[sn]; k++) if (st->blue_parent[b] != sn * 16 + k) tmp_add_session_proc(c, t, sn * 16 + k, K_SESSION);
             }
         }
-        for (int g = 0; g < ng; g++) tmp_add_session_proc(c, t, s->green_host[g], K_SESSION);
+        _Pragma("unroll 1") for (int g = 0; g < ng; g++) tmp_add_session_proc(c, t, s->green_host[g], K_SESSION);
         {
             int h = st->red_start[0], pid = tmp_create_pid(c, t, h);
             t->procs[h][t->np[h]++] = P_MAKE(pid, K_REDABS, 0, 0);
@@ -425,14 +511,14 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
         }
         /* pack the CSR pool in slot order; Host.create_backup Host.py:316-371 */
         int tot = 0;
-        for (int h = 0; h < 128; h++) { s->pstart[h] = (uint16_t)tot; for (int i = 0; i < t->np[h]; i++) s->procs[tot++] = t->procs[h][i]; }
+        _Pragma("unroll 1") for (int h = 0; h < 128; h++) { s->pstart[h] = (uint16_t)tot; for (int i = 0; i < t->np[h]; i++) s->procs[tot++] = t->procs[h][i]; }
         s->pstart[128] = (uint16_t)tot;
-        for (int i = 0; i < tot; i++) st->o_procs[i] = s->procs[i];
-        for (int h = 0; h <= 128; h++) st->o_pstart[h] = s->pstart[h];
-        for (int h = 0; h < 128; h++) st->o_svc64[h] = s->svc64[h];
-        for (int i = 0; i < 16; i++) st->router_pid[i] = t->router_pid[i];
+        _Pragma("unroll 1") for (int i = 0; i < tot; i++) st->o_procs[i] = s->procs[i];
+        _Pragma("unroll 1") for (int h = 0; h <= 128; h++) st->o_pstart[h] = s->pstart[h];
+        _Pragma("unroll 1") for (int h = 0; h < 128; h++) st->o_svc64[h] = s->svc64[h];
+        _Pragma("unroll 1") for (int i = 0; i < 16; i++) st->router_pid[i] = t->router_pid[i];
         /* initial knowledge: AgentInterface.set_init_obs AgentInterface.py:110-117 with the OSINT of :784-785 */
-        for (int r = 0; r < CC4_NRED; r++) { int h = st->red_start[r]; set128(s->ip_known[r], h); set128(s->hn_known[r], h); s->sn_known[r] |= (uint16_t)(1u << (h >> 4)); }
+        _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) { int h = st->red_start[r]; set128(s->ip_known[r], h); set128(s->hn_known[r], h); s->sn_known[r] |= (uint16_t)(1u << (h >> 4)); }
         s->ss[0][0] = 0; s->n_ss[0] = 1;
         /* red_agent_0 digests its initial observation (its start host becomes 'U', FiniteStateRedAgent.py:221-224) */
         s->fsm[0][0] = F_MAKE(st->red_start[0], 1, F_U); s->n_fsm[0] = 1; s->fsm_started = 1;
