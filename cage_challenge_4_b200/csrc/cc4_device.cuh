@@ -107,6 +107,7 @@ struct Scratch {
     uint32_t hostagents[32];                      /* byte h = mask of red agents with a session on host h (built on demand for phishing) */
     uint32_t phish[3];                            /* green agents whose local work triggered a phishing email this tick */
     uint32_t ssmask[CC4_NRED][8];                 /* bit id: server_session id known to agent r (mirror of Cc4Dyn.ss, rebuilt every tick) */
+    uint32_t obsbits[40];                         /* observation vectors as bit strings [5][8] */
     int reward;
 };
 

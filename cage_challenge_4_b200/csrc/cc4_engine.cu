@@ -81,11 +81,62 @@ __device__ __forceinline__ uint8_t obs_element(const Cc4Dyn *s, int b, int p)
     int k = q >> 3, other = k < b ? k : k + 1;   /* the other four agents in sorted order, SimulationController.py:781-804 */
     return (s->msgs[other] >> (q & 7)) & 1;
 }
-__device__ void w_write_obs(const Cc4Dyn *s, uint8_t *obs /* [5][210] of this episode */)
+/* The five vectors are first assembled as bit strings (bit p of agent b = element p, the phase is added to byte 0
+ * afterwards), then expanded to bytes two at a time (an episode's 1050-byte block is only 2-byte aligned). */
+__device__ void w_write_obs(const Cc4Dyn *s, uint32_t *bits /* scratch [5][8] */, uint8_t *obs /* [5][210] of this episode */)
 {
-    /* 1050 bytes; 4 bytes per lane per iteration, written as one aligned 32-bit word (210*5 = 1050, base is 2-byte
-       aligned only for odd episodes, so use byte stores for the ragged tail) */
-    _Pragma("unroll 1") for (int i = lane_id(); i < CC4_N_BLUE * CC4_OBS_LEN; i += 32) obs[i] = obs_element(s, i / CC4_OBS_LEN, i % CC4_OBS_LEN);
+    const int lane = lane_id();
+    /* per-subnet 16-bit host masks: malicious-process / network-connection alerts (old + current events) */
+    uint32_t procm[4], netm[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int h = i * 32 + lane;
+        uint32_t e = host_exists(s, h) ? s->ev[h] : 0u;
+        procm[i] = __ballot_sync(0xFFFFFFFFu, (e & (EV_PROC | EV_OLDPROC)) != 0);
+        netm[i] = __ballot_sync(0xFFFFFFFFu, (e & (EV_NET | EV_OLDNET)) != 0);
+    }
+    bits[lane] = 0;
+    if (lane < 8) bits[32 + lane] = 0;
+    __syncwarp();
+    if (lane < 7) {   /* one lane per (agent, subnet) block of 59 bits */
+        int b = lane < 4 ? lane : 4, i = lane < 4 ? 0 : lane - 4, sn = blue_sorted_subnet(b, i);
+        uint32_t blk = s->blocks[sn], adj = c_comms_adj[s->phase][sn];
+        uint64_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            int o = c_sorted_subnets[j];
+            v |= (uint64_t)(o == sn) << j | (uint64_t)(blk >> o & 1) << (9 + j) | (uint64_t)(!(adj >> o & 1)) << (18 + j);
+        }
+        int pair = sn >> 1;   /* select without indexing the register arrays dynamically */
+        uint32_t pw = pair == 0 ? procm[0] : pair == 1 ? procm[1] : pair == 2 ? procm[2] : procm[3];
+        uint32_t nw = pair == 0 ? netm[0] : pair == 1 ? netm[1] : pair == 2 ? netm[2] : netm[3];
+        uint32_t pm = (sn & 1) ? pw >> 16 : pw & 0xFFFFu, nm = (sn & 1) ? nw >> 16 : nw & 0xFFFFu;
+        v |= (uint64_t)pm << 27 | (uint64_t)nm << 43;
+        int off = 1 + 59 * i, sh = off & 31;
+        uint32_t *w = bits + b * 8 + (off >> 5);
+        atomicOr(&w[0], (uint32_t)(v << sh));
+        atomicOr(&w[1], (uint32_t)(v >> (32 - sh)));
+        if (sh + 59 > 64) atomicOr(&w[2], (uint32_t)(v >> (64 - sh)));
+    }
+    if (lane >= 8 && lane < 13) {   /* messages from the other four agents in sorted order, SimulationController.py:781-804 */
+        int b = lane - 8, off = 1 + 59 * (b == 4 ? 3 : 1), sh = off & 31;
+        uint32_t m = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) m |= (uint32_t)s->msgs[k < b ? k : k + 1] << (8 * k);
+        uint32_t *w = bits + b * 8 + (off >> 5);
+        atomicOr(&w[0], m << sh);
+        if (sh) atomicOr(&w[1], m >> (32 - sh));
+    }
+    __syncwarp();
+    uint16_t *out = reinterpret_cast<uint16_t *>(obs);
+    const uint32_t phase = s->phase;
+    _Pragma("unroll 1") for (int hw = lane; hw < CC4_N_BLUE * CC4_OBS_LEN / 2; hw += 32) {
+        int b = hw / (CC4_OBS_LEN / 2), p = (hw - b * (CC4_OBS_LEN / 2)) * 2;
+        uint32_t two = (bits[b * 8 + (p >> 5)] >> (p & 31)) & 3u;     /* p is even, so both bits sit in one word */
+        uint32_t v = (two & 1u) | (two & 2u) << 7;
+        if (p == 0) v |= phase;
+        out[hw] = (uint16_t)v;
+    }
 }
 __device__ void w_write_mask(const Cc4Dyn *s, uint8_t *mask)
 {
@@ -349,7 +400,7 @@ k_step(Params p, const int32_t *actions, const uint8_t *msgs, uint8_t *obs, floa
     w_load(&w->dyn, p.dyn + env);
     w_tick(c, actions + (size_t)env * 5, msgs ? msgs + (size_t)env * 5 : nullptr,
            (flags & CC4_STEP_REWARD) && reward ? reward + env : nullptr, done ? done + env : nullptr);
-    if ((flags & CC4_STEP_OBS) && obs) w_write_obs(&w->dyn, obs + (size_t)env * CC4_N_BLUE * CC4_OBS_LEN);
+    if ((flags & CC4_STEP_OBS) && obs) w_write_obs(&w->dyn, w->x.obsbits, obs + (size_t)env * CC4_N_BLUE * CC4_OBS_LEN);
     w_store(p.dyn + env, &w->dyn);
 }
 
@@ -525,7 +576,7 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
         if (c.rng_mode == 1 && c.n_segs > 0 && c.x->ctr[NAG] != c.seg[1] - c.seg[0]) fail(c, CC4_E_TAPE_LEFT);
     }
     __syncwarp();
-    if (obs) w_write_obs(&w->dyn, obs + (size_t)env * CC4_N_BLUE * CC4_OBS_LEN);
+    if (obs) w_write_obs(&w->dyn, w->x.obsbits, obs + (size_t)env * CC4_N_BLUE * CC4_OBS_LEN);
     if (mask) w_write_mask(&w->dyn, mask + (size_t)env * CC4_N_BLUE * CC4_MASK_LEN);
     w_store(p.dyn + env, &w->dyn);
 }
