@@ -170,7 +170,7 @@ def main():
 
     n = args.envs
     env = BatchedCC4(n, device=local_rank, seed=0, steps=500, first_episode=rank * n)
-    dyn_bytes, stat_bytes = env.state_bytes()
+    dyn_bytes, cold_bytes, stat_bytes = env.state_bytes()
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     pool = [torch.stack([torch.randint(0, k, (n,), generator=g, device=dev) for k in (82, 82, 82, 82, 242)], 1).to(torch.int32).contiguous()
             for _ in range(16)]
@@ -262,8 +262,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": which, "kernel": "k_step",
                          "kernel_ms": kernel_ms, "bytes_per_env_step": b_step,
-                         "formula": "2*sizeof(Cc4Dyn) + 608 B io per episode-tick (DESIGN.md)"},
-            "state_bytes": {"dynamic": dyn_bytes, "static": stat_bytes},
+                         "formula": "2*sizeof(hot record) + 608 B io per episode-tick; the cold record is touched in place by rare transitions only (DESIGN.md)"},
+            "state_bytes": {"hot": dyn_bytes, "cold": cold_bytes, "static": stat_bytes},
             "score": {"episodes": int(score[2].item()), "mean_return": float(score[0] / score[2])},
             "error_episodes": int((errs != 0).sum()),
         }

@@ -31,7 +31,7 @@ def load():
     vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
     L.cc4_create.argtypes = [i32, i32, u64, u64, i32, i32, C.POINTER(vp)]
     L.cc4_destroy.argtypes = [vp]
-    L.cc4_state_bytes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.cc4_state_bytes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.cc4_set_tape.argtypes = [vp, vp, vp, C.c_uint32]
     L.cc4_reset.argtypes = [vp, vp, vp, vp]
     L.cc4_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]

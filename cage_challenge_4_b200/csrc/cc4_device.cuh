@@ -112,7 +112,7 @@ struct Scratch {
 };
 
 struct Ctx {
-    Cc4Dyn *s; Scratch *x; Cc4Stat *st;
+    Cc4Dyn *s; Scratch *x; Cc4Stat *st; Cc4Cold *k;
     int tick;                 /* state step_count at the start of the tick; -1 during reset */
     int steps, rng_mode;
     uint32_t k0, k1, ep_lo;
@@ -181,36 +181,29 @@ __device__ __forceinline__ int blue_of_subnet(int sn) { return sn <= S_OZB ? sn 
 __device__ __forceinline__ bool bit128(const uint32_t *b, int i) { return (b[i >> 5] >> (i & 31)) & 1u; }
 __device__ __forceinline__ void set128(uint32_t *b, int i) { b[i >> 5] |= 1u << (i & 31); }
 
-/* ---- process pool (lane 0) ---- */
-__device__ __forceinline__ int p_begin(const Cc4Dyn *s, int h) { return s->pstart[h]; }
-__device__ __forceinline__ int p_end(const Cc4Dyn *s, int h) { return s->pstart[h + 1]; }
+/* ---- process lists (lane 0; the slabs live in the cold record) ---- */
 __device__ __noinline__ void proc_append(Ctx &c, int h, uint32_t w)
 {   /* host.processes.append */
-    Cc4Dyn *s = c.s;
-    int tot = s->pstart[128];
-    if (tot >= CC4_PROC_CAP) { fail(c, CC4_E_CAPACITY); return; }
-    int at = s->pstart[h + 1];
-    _Pragma("unroll 1") for (int i = tot; i > at; i--) s->procs[i] = s->procs[i - 1];
-    s->procs[at] = w;
-    _Pragma("unroll 1") for (int j = h + 1; j <= 128; j++) s->pstart[j]++;
+    int n = c.s->nproc[h];
+    if (n >= CC4_PSLAB) { fail(c, CC4_E_CAPACITY); return; }
+    c.k->procs[h][n] = w;
+    c.s->nproc[h] = (uint8_t)(n + 1);
 }
 __device__ __noinline__ void proc_delete(Ctx &c, int h, int idx)
 {
-    Cc4Dyn *s = c.s;
-    int tot = s->pstart[128];
-    _Pragma("unroll 1") for (int i = idx; i + 1 < tot; i++) s->procs[i] = s->procs[i + 1];
-    _Pragma("unroll 1") for (int j = h + 1; j <= 128; j++) s->pstart[j]--;
+    int n = c.s->nproc[h];
+    _Pragma("unroll 1") for (int i = idx; i + 1 < n; i++) c.k->procs[h][i] = c.k->procs[h][i + 1];
+    c.s->nproc[h] = (uint8_t)(n - 1);
 }
-__device__ __noinline__ int proc_find(const Cc4Dyn *s, int h, uint32_t pid)
+__device__ __noinline__ int proc_find(const Ctx &c, int h, uint32_t pid)
 {   /* Host.get_process Host.py:251 (tombstones are not processes) */
-    _Pragma("unroll 1") for (int i = p_begin(s, h); i < p_end(s, h); i++) if (!P_DEAD(s->procs[i]) && P_PID(s->procs[i]) == pid) return i;
+    _Pragma("unroll 1") for (int i = 0; i < c.s->nproc[h]; i++) { uint32_t w = c.k->procs[h][i]; if (!P_DEAD(w) && P_PID(w) == pid) return i; }
     return -1;
 }
 __device__ __noinline__ int create_pid(Ctx &c, int actor, int h)
 {   /* Host.create_pid Host.py:198-200 */
-    const Cc4Dyn *s = c.s;
     uint32_t mx = 0;
-    _Pragma("unroll 1") for (int i = p_begin(s, h); i < p_end(s, h); i++) if (!P_DEAD(s->procs[i]) && P_PID(s->procs[i]) > mx) mx = P_PID(s->procs[i]);
+    _Pragma("unroll 1") for (int i = 0; i < c.s->nproc[h]; i++) { uint32_t w = c.k->procs[h][i]; if (!P_DEAD(w) && P_PID(w) > mx) mx = P_PID(w); }
     uint32_t pid = mx + 1 + rng_int(c, actor, ST_CREATE_PID, 9);
     if (pid > 0xFFFFu) { fail(c, CC4_E_CAPACITY); pid = 0xFFFFu; }
     return (int)pid;
@@ -228,15 +221,17 @@ __device__ __noinline__ int sess_find(const Cc4Dyn *s, int r, int id)
     return -1;
 }
 __device__ __noinline__ int sess_count_agent(const Cc4Dyn *s, int r) { int n = 0; for (int i = 0; i < s->n_sess; i++) n += SF_AGENT(s->sessf[i]) == (uint32_t)r; return n; }
-__device__ __noinline__ void ports_drop(Cc4Dyn *s, int r, int id)
+__device__ __noinline__ void ports_drop(Ctx &c, int r, int id)
 {
+    Cc4Dyn *s = c.s;
     int w = 0;
-    _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = s->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)id) continue; s->ports[w++] = p; }
+    _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = c.k->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)id) continue; if (w != i) c.k->ports[w] = p; w++; }
     s->n_ports = (uint16_t)w;
 }
-__device__ __noinline__ void sess_delete(Cc4Dyn *s, int idx)
+__device__ __noinline__ void sess_delete(Ctx &c, int idx)
 {
-    ports_drop(s, SF_AGENT(s->sessf[idx]), S_ID(s->sess[idx]));
+    Cc4Dyn *s = c.s;
+    if (SF_ABS(s->sessf[idx])) ports_drop(c, SF_AGENT(s->sessf[idx]), S_ID(s->sess[idx]));
     _Pragma("unroll 1") for (int i = idx; i + 1 < s->n_sess; i++) { s->sess[i] = s->sess[i + 1]; s->sessf[i] = s->sessf[i + 1]; }
     s->n_sess--;
 }
@@ -475,14 +470,14 @@ __device__ __noinline__ void ev_procpid(Ctx &c, int slot, int pid)
 __device__ __noinline__ void stop_process(Ctx &c, int actor, int h, uint32_t pid)
 {
     Cc4Dyn *s = c.s;
-    int pi = proc_find(s, h, pid);
+    int pi = proc_find(c, h, pid);
     if (pi < 0) return;
-    uint32_t w = s->procs[pi];
+    uint32_t w = c.k->procs[h][pi];
     if (P_ROOT(w)) return;
     int si = session_from_pid(s, h, pid);
     /* a stopped OT service keeps Service.process; a pid collision with it takes the reference down a path that
        re-labels the killed process as the service's (StopProcess.py:37-42): not modelled */
-    _Pragma("unroll 1") for (int i = p_begin(s, h); i < p_end(s, h); i++) if (P_DEAD(s->procs[i]) && P_PID(s->procs[i]) == pid) fail(c, CC4_E_UNREACHABLE);
+    _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) if (P_DEAD(c.k->procs[h][i]) && P_PID(c.k->procs[h][i]) == pid) fail(c, CC4_E_UNREACHABLE);
     proc_delete(c, h, pi);
     if (P_SVC(w)) {
         int np = create_pid(c, actor, h);
@@ -491,7 +486,7 @@ __device__ __noinline__ void stop_process(Ctx &c, int actor, int h, uint32_t pid
     }
     if (si < 0) return;
     int r = SF_AGENT(s->sessf[si]);
-    sess_delete(s, si);
+    sess_delete(c, si);
     if (s->sess_count[r] > 0) s->sess_count[r]--;
 }
 
@@ -499,15 +494,11 @@ __device__ __noinline__ void stop_process(Ctx &c, int actor, int h, uint32_t pid
 __device__ __noinline__ void do_restore(Ctx &c, int h)
 {
     Cc4Dyn *s = c.s; const Cc4Stat *st = c.st;
-    _Pragma("unroll 1") for (int i = 0; i < s->n_sess;) if (S_HOST(s->sess[i]) == (uint32_t)h) sess_delete(s, i); else i++;
+    _Pragma("unroll 1") for (int i = 0; i < s->n_sess;) if (S_HOST(s->sess[i]) == (uint32_t)h) sess_delete(c, i); else i++;
     s->ev[h] = 0;
-    int ob = st->o_pstart[h], on = st->o_pstart[h + 1] - ob, cb = s->pstart[h], cn = s->pstart[h + 1] - cb, tot = s->pstart[128];
-    int d = on - cn;
-    if (tot + d > CC4_PROC_CAP) { fail(c, CC4_E_CAPACITY); return; }
-    if (d > 0) for (int i = tot - 1; i >= cb + cn; i--) s->procs[i + d] = s->procs[i];
-    if (d < 0) for (int i = cb + cn; i < tot; i++) s->procs[i + d] = s->procs[i];
-    _Pragma("unroll 1") for (int i = 0; i < on; i++) s->procs[cb + i] = st->o_procs[ob + i];
-    _Pragma("unroll 1") for (int j = h + 1; j <= 128; j++) s->pstart[j] = (uint16_t)(s->pstart[j] + d);
+    int on = st->o_nproc[h];
+    _Pragma("unroll 1") for (int i = 0; i < on; i++) c.k->procs[h][i] = st->o_procs[h][i];
+    s->nproc[h] = (uint8_t)on;
     s->svc64[h] = st->o_svc64[h];
 }
 
@@ -517,7 +508,7 @@ __device__ __noinline__ void do_decoy(Ctx &c, int b, int h)
     Cc4Dyn *s = c.s;
     int actor = A_BLUE0 + b;
     int used = 0;
-    _Pragma("unroll 1") for (int i = p_begin(s, h); i < p_end(s, h); i++) { if (P_DEAD(s->procs[i])) continue; int pb = c_kind_portbit[P_KIND(s->procs[i])]; if (pb >= 0) used |= 1 << pb; }
+    _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) { uint32_t w = c.k->procs[h][i]; if (P_DEAD(w)) continue; int pb = c_kind_portbit[P_KIND(w)]; if (pb >= 0) used |= 1 << pb; }
     int fac[4], nf = 0;
     if (!(used & PB_80)) fac[nf++] = K_D_APACHE;
     if (!(used & PB_443)) fac[nf++] = K_D_TOMCAT;
@@ -526,7 +517,7 @@ __device__ __noinline__ void do_decoy(Ctx &c, int b, int h)
     int kind = fac[rng_int(c, actor, ST_DECOY_FACTORY, (uint32_t)nf)];
     int pid = create_pid(c, actor, h);
     /* host.services[name] = Service(pid): an earlier process of the same decoy stops being the service's process */
-    _Pragma("unroll 1") for (int i = p_begin(s, h); i < p_end(s, h); i++) if (P_KIND(s->procs[i]) == (uint32_t)kind && P_SVC(s->procs[i])) s->procs[i] &= ~(1u << 21);
+    _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) { uint32_t w = c.k->procs[h][i]; if (P_KIND(w) == (uint32_t)kind && P_SVC(w)) c.k->procs[h][i] = w & ~(1u << 21); }
     proc_append(c, h, P_MAKE(pid, kind, 0, 1));
     uint64_t v = s->svc64[h];
     int n = svc_count(v), at = -1;
@@ -541,7 +532,7 @@ __device__ __noinline__ void exec_blue(Ctx &c, int b, const Act &a)
     switch (a.code) {
     case AC_REMOVE: {   /* Remove.py:42-69 */
         int n = s->n_sus;
-        _Pragma("unroll 1") for (int i = 0; i < n; i++) { uint32_t w = s->sus[i]; if (SU_AGENT(w) == (uint32_t)b && SU_SLOT(w) == (uint32_t)a.host) stop_process(c, A_BLUE0 + b, a.host, SU_PID(w)); }
+        _Pragma("unroll 1") for (int i = 0; i < n; i++) { uint32_t w = c.k->sus[i]; if (SU_AGENT(w) == (uint32_t)b && SU_SLOT(w) == (uint32_t)a.host) stop_process(c, A_BLUE0 + b, a.host, SU_PID(w)); }
         break;
     }
     case AC_RESTORE: do_restore(c, a.host); break;        /* Restore.py:38-68 */
@@ -675,8 +666,8 @@ __device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
         double rate = a.code == AC_AGGR ? 0.75 : 0.25;
         double u = rng_f64(c, actor, ST_PORTSCAN, 0);
         int mask = 0, any = 0, h = a.host;
-        _Pragma("unroll 1") for (int i = p_begin(s, h); i < p_end(s, h); i++) {
-            uint32_t w = s->procs[i];
+        _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) {
+            uint32_t w = c.k->procs[h][i];
             if (P_DEAD(w)) continue;
             int pb = c_kind_portbit[P_KIND(w)];
             if (pb < 0) continue;
@@ -685,9 +676,9 @@ __device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
         }
         if (any) {
             int at = -1;
-            _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = s->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)a.session && PT_HOST(p) == (uint32_t)h) { at = i; break; } }
+            _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = c.k->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)a.session && PT_HOST(p) == (uint32_t)h) { at = i; break; } }
             if (at < 0) { if (s->n_ports >= CC4_PORT_CAP) { fail(c, CC4_E_CAPACITY); at = 0; } else at = s->n_ports++; }
-            s->ports[at] = PT_MAKE(mask, h, a.session, r);
+            c.k->ports[at] = PT_MAKE(mask, h, a.session, r);
             obs_entry(c, r, 1, h, 1, 0, 0, 0);
         }
         return SUCC_TRUE;
@@ -695,8 +686,8 @@ __device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
     case AC_DD: {      /* DiscoverDeception.py:44-101 */
         if (si < 0) return SUCC_FALSE;
         int rep = 0, h = a.host;
-        _Pragma("unroll 1") for (int i = p_begin(s, h); i < p_end(s, h); i++) {
-            uint32_t w = s->procs[i];
+        _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) {
+            uint32_t w = c.k->procs[h][i];
             if (P_DEAD(w)) continue;
             bool decoy = P_KIND(w) >= K_D_APACHE && P_KIND(w) <= K_D_VSFTPD;
             if (rng_f64(c, actor, ST_DD_TP, 0) <= 0.5 && decoy) rep = 1;
@@ -708,7 +699,7 @@ __device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
     case AC_EXPLOIT: { /* ExploitRemoteService.py:149-202 */
         if (si < 0 || !S_abs) return SUCC_FALSE;
         int ports = -1, target = a.host, src = S_host;
-        _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = s->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)a.session && PT_HOST(p) == (uint32_t)target) { ports = PT_MASK(p); break; } }
+        _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = c.k->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)a.session && PT_HOST(p) == (uint32_t)target) { ports = PT_MASK(p); break; } }
         if (ports < 0) return SUCC_FALSE;
         if (blocking(s, src, target)) return SUCC_FALSE;
         enum { X_HTTP, X_HTTPS, X_SSH, X_SQL, X_HARAKA };
@@ -732,7 +723,7 @@ __device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
             int hops[12], nh = route(src, target, hops);
             _Pragma("unroll 1") for (int i = 0; i < nh; i++) if (0.05 < rng_f64(c, actor, ST_SSH_HOP, 0)) s->ev[hops[i]] |= EV_NET;
             int vp = -1;
-            _Pragma("unroll 1") for (int i = p_begin(s, target); i < p_end(s, target); i++) if (!P_DEAD(s->procs[i]) && P_KIND(s->procs[i]) == K_SSHD) { vp = i; break; }
+            _Pragma("unroll 1") for (int i = 0; i < s->nproc[target]; i++) { uint32_t w = c.k->procs[target][i]; if (!P_DEAD(w) && P_KIND(w) == K_SSHD) { vp = i; break; } }
             if (vp < 0) return SUCC_FALSE;
             s->ev[target] |= EV_NET;
             int pid = exploit_new_session(c, r, target);
@@ -743,8 +734,8 @@ __device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
         }
         /* ExploitAction.sim_exploit ExploitAction.py:48-116 */
         int vk = -1;
-        _Pragma("unroll 1") for (int i = p_begin(s, target); i < p_end(s, target) && vk < 0; i++) {
-            uint32_t w = s->procs[i];
+        _Pragma("unroll 1") for (int i = 0; i < s->nproc[target] && vk < 0; i++) {
+            uint32_t w = c.k->procs[target][i];
             if (P_DEAD(w)) continue;
             int k = P_KIND(w);
             if (sel == X_HTTP && (k == K_APACHE2 || k == K_D_APACHE || k == K_D_VSFTPD)) vk = k;
@@ -774,8 +765,8 @@ __device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
             _Pragma("unroll 1") for (int i = 0, k = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_HOST(s->sess[i]) == (uint32_t)h) { if (k == pk) { tgt = i; break; } k++; }
             if (si < 0 || !S_abs) return SUCC_FALSE;
             s->sessf[tgt] |= 1u << 4;      /* EscalateAction.__upgrade_session EscalateAction.py:54-87 */
-            int pi = proc_find(s, h, S_PID(s->sess[tgt]));
-            if (pi >= 0) s->procs[pi] |= P_ROOTBIT; else fail(c, CC4_E_UNREACHABLE);
+            int pi = proc_find(c, h, S_PID(s->sess[tgt]));
+            if (pi >= 0) c.k->procs[h][pi] |= P_ROOTBIT; else fail(c, CC4_E_UNREACHABLE);
         }
         obs_entry(c, r, 0, h, 0, 0, 0, 1);
         if (SF_ABS(s->sessf[tgt])) know_session(c, r, S_ID(s->sess[tgt]));
@@ -797,12 +788,12 @@ __device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
             if (!has_ot || (v & SVC_OT_STOPPED)) return SUCC_FALSE;
             if (si < 0) return SUCC_FALSE;     /* StopService is a TargetedLocalAction: TargetedLocalAction.py:14-21 */
             s->svc64[h] = v | SVC_OT_STOPPED;  /* Host.stop_service Host.py:296-301 */
-            _Pragma("unroll 1") for (int i = p_begin(s, h); i < p_end(s, h); i++) {   /* State.remove_process State.py:390-418 */
-                uint32_t w = s->procs[i];
+            _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) {   /* State.remove_process State.py:390-418 */
+                uint32_t w = c.k->procs[h][i];
                 if (!P_DEAD(w) && P_KIND(w) == K_OT && P_SVC(w)) {
                     int s2 = session_from_pid(s, h, P_PID(w));
-                    s->procs[i] = w | P_DEADBIT;
-                    if (s2 >= 0) sess_delete(s, s2);
+                    c.k->procs[h][i] = w | P_DEADBIT;
+                    if (s2 >= 0) sess_delete(c, s2);
                     break;
                 }
             }
@@ -829,7 +820,7 @@ __device__ __noinline__ void rsc_reelect(Ctx &c, int r, int n)
     if (at < 0) { fail(c, CC4_E_UNREACHABLE); return; }
     uint32_t w = s->sess[at]; uint8_t f = s->sessf[at];
     int old_id = S_ID(w);
-    _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = s->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)old_id) s->ports[i] = PT_MAKE(PT_MASK(p), PT_HOST(p), 0, r); }
+    _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = c.k->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)old_id) c.k->ports[i] = PT_MAKE(PT_MASK(p), PT_HOST(p), 0, r); }
     _Pragma("unroll 1") for (int i = at; i + 1 < s->n_sess; i++) { s->sess[i] = s->sess[i + 1]; s->sessf[i] = s->sessf[i + 1]; }
     s->sess[s->n_sess - 1] = S_MAKE(S_PID(w), 0, S_HOST(w)); s->sessf[s->n_sess - 1] = f;
 }
@@ -850,7 +841,7 @@ __device__ __noinline__ void reassign(Ctx &c)
         uint32_t w = s->sess[si]; uint8_t f = s->sessf[si];
         int host = S_HOST(w), nr = red_of_subnet(host >> 4);
         if (nr < 0) { fail(c, CC4_E_UNREACHABLE); continue; }
-        sess_delete(s, si);
+        sess_delete(c, si);
         int nid = sess_add(c, nr, host, 1, SF_ROOT(f), S_PID(w));
         if (s->sess_count[r] > 0) s->sess_count[r]--;
         _Pragma("unroll 1") for (int i = 0; i < x->n_oent[r]; i++) {

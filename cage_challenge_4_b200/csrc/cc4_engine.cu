@@ -17,7 +17,7 @@
 
 namespace cc4 {
 
-constexpr int WARPS_PER_BLOCK = 4;
+constexpr int WARPS_PER_BLOCK = 8;
 constexpr int DYN_U4 = (int)(sizeof(Cc4Dyn) / 16);
 
 struct WarpSmem {
@@ -26,7 +26,7 @@ struct WarpSmem {
 };
 
 struct Params {
-    Cc4Dyn *dyn; Cc4Stat *stat;
+    Cc4Dyn *dyn; Cc4Stat *stat; Cc4Cold *cold;
     int n_envs, steps, rng_mode;
     uint32_t k0, k1hi; uint64_t first_episode;
     const cc4_draw *tape; const uint32_t *seg_off; uint32_t n_segs;
@@ -53,7 +53,7 @@ __device__ __forceinline__ void w_store(Cc4Dyn *dst, const Cc4Dyn *src)
 __device__ __forceinline__ void make_ctx(Ctx &c, WarpSmem *w, const Params &p, int env)
 {
     uint64_t ep = p.first_episode + (uint64_t)env;
-    c.s = &w->dyn; c.x = &w->x; c.st = p.stat + env;
+    c.s = &w->dyn; c.x = &w->x; c.st = p.stat + env; c.k = p.cold + env;
     c.steps = p.steps; c.rng_mode = p.rng_mode;
     c.k0 = p.k0; c.k1 = p.k1hi ^ (uint32_t)(ep >> 32); c.ep_lo = (uint32_t)ep;
     c.tape = p.tape; c.seg = p.seg_off ? p.seg_off + (size_t)env * (p.n_segs + 1) : nullptr; c.n_segs = p.n_segs;
@@ -164,7 +164,7 @@ __device__ void w_monitor_all(Ctx &c)
         _Pragma("unroll 1") for (int i = 0; i < x->n_evpid; i++) {
             int slot = x->evpid[i] >> 16, b = blue_of_subnet(slot_subnet(slot));
             if (s->n_sus >= CC4_SUS_CAP) { fail(c, CC4_E_CAPACITY); break; }
-            s->sus[s->n_sus++] = SU_MAKE(x->evpid[i] & 0xFFFFu, slot, b);
+            c.k->sus[s->n_sus++] = SU_MAKE(x->evpid[i] & 0xFFFFu, slot, b);
         }
         x->n_evpid = 0;
     }
@@ -180,7 +180,7 @@ __device__ void monitor_one(Ctx &c, int b)
         int slot = x->evpid[i] >> 16;
         if (blue_of_subnet(slot_subnet(slot)) != b) { x->evpid[w++] = x->evpid[i]; continue; }
         if (s->n_sus >= CC4_SUS_CAP) { fail(c, CC4_E_CAPACITY); continue; }
-        s->sus[s->n_sus++] = SU_MAKE(x->evpid[i] & 0xFFFFu, slot, b);
+        c.k->sus[s->n_sus++] = SU_MAKE(x->evpid[i] & 0xFFFFu, slot, b);
     }
     x->n_evpid = w;
 }
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
     ResetSmem *w = reinterpret_cast<ResetSmem *>(smem_raw);
     int env = blockIdx.x;
     if (env >= p.n_envs) return;
-    Ctx c; c.s = &w->dyn; c.x = &w->x; c.st = p.stat + env;
+    Ctx c; c.s = &w->dyn; c.x = &w->x; c.st = p.stat + env; c.k = p.cold + env;
     {
         uint64_t ep = p.first_episode + (uint64_t)env;
         c.steps = p.steps; c.rng_mode = p.rng_mode; c.k0 = p.k0; c.k1 = p.k1hi ^ (uint32_t)(ep >> 32); c.ep_lo = (uint32_t)ep;
@@ -560,13 +560,12 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
             t->procs[h][t->np[h]++] = P_MAKE(pid, K_REDABS, 0, 0);
             s->sess[0] = S_MAKE(pid, 0, h); s->sessf[0] = (uint8_t)(0 | 1 << 3); s->n_sess = 1; s->sess_count[0] = 1; s->red_active = 1;
         }
-        /* pack the CSR pool in slot order; Host.create_backup Host.py:316-371 */
-        int tot = 0;
-        _Pragma("unroll 1") for (int h = 0; h < 128; h++) { s->pstart[h] = (uint16_t)tot; for (int i = 0; i < t->np[h]; i++) s->procs[tot++] = t->procs[h][i]; }
-        s->pstart[128] = (uint16_t)tot;
-        _Pragma("unroll 1") for (int i = 0; i < tot; i++) st->o_procs[i] = s->procs[i];
-        _Pragma("unroll 1") for (int h = 0; h <= 128; h++) st->o_pstart[h] = s->pstart[h];
-        _Pragma("unroll 1") for (int h = 0; h < 128; h++) st->o_svc64[h] = s->svc64[h];
+        /* process lists + Host.create_backup Host.py:316-371 */
+        _Pragma("unroll 1") for (int h = 0; h < 128; h++) {
+            s->nproc[h] = t->np[h]; st->o_nproc[h] = t->np[h];
+            _Pragma("unroll 1") for (int i = 0; i < t->np[h]; i++) { c.k->procs[h][i] = t->procs[h][i]; st->o_procs[h][i] = t->procs[h][i]; }
+            st->o_svc64[h] = s->svc64[h];
+        }
         _Pragma("unroll 1") for (int i = 0; i < 16; i++) st->router_pid[i] = t->router_pid[i];
         /* initial knowledge: AgentInterface.set_init_obs AgentInterface.py:110-117 with the OSINT of :784-785 */
         _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) { int h = st->red_start[r]; set128(s->ip_known[r], h); set128(s->hn_known[r], h); s->sn_known[r] |= (uint16_t)(1u << (h >> 4)); }
@@ -617,6 +616,7 @@ extern "C" int cc4_create(int n_envs, int device, uint64_t seed, uint64_t first_
     h->p.k0 = (uint32_t)seed; h->p.k1hi = (uint32_t)(seed >> 32); h->p.first_episode = first_episode;
     CUDA_TRY(cudaMalloc(&h->p.dyn, sizeof(Cc4Dyn) * (size_t)n_envs));
     CUDA_TRY(cudaMalloc(&h->p.stat, sizeof(Cc4Stat) * (size_t)n_envs));
+    CUDA_TRY(cudaMalloc(&h->p.cold, sizeof(Cc4Cold) * (size_t)n_envs));
     CUDA_TRY(cudaMemset(h->p.dyn, 0, sizeof(Cc4Dyn) * (size_t)n_envs));
     CUDA_TRY(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * WARPS_PER_BLOCK)));
     CUDA_TRY(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * WARPS_PER_BLOCK)));
@@ -629,16 +629,17 @@ extern "C" int cc4_destroy(cc4_handle *h)
 {
     if (!h) return CC4_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->p.dyn); cudaFree(h->p.stat);
+    cudaFree(h->p.dyn); cudaFree(h->p.stat); cudaFree(h->p.cold);
     cudaFree(h->stage_actions); cudaFree(h->stage_msgs); cudaFree(h->stage_obs); cudaFree(h->stage_done); cudaFree(h->stage_reward);
     delete h;
     return CC4_OK;
 }
 
-extern "C" int cc4_state_bytes(cc4_handle *h, size_t *dyn_bytes, size_t *stat_bytes)
+extern "C" int cc4_state_bytes(cc4_handle *h, size_t *hot_bytes, size_t *cold_bytes, size_t *stat_bytes)
 {
     (void)h;
-    if (dyn_bytes) *dyn_bytes = sizeof(Cc4Dyn);
+    if (hot_bytes) *hot_bytes = sizeof(Cc4Dyn);
+    if (cold_bytes) *cold_bytes = sizeof(Cc4Cold);
     if (stat_bytes) *stat_bytes = sizeof(Cc4Stat);
     return CC4_OK;
 }
@@ -734,9 +735,10 @@ extern "C" int cc4_export_canon(cc4_handle *h, int env, int32_t *out, int cap, i
     if (!h || !out || !n_out || env < 0 || env >= h->p.n_envs) return set_err(CC4_ERR_ARG, "cc4_export_canon: bad argument%s", "");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaDeviceSynchronize());
-    static thread_local Cc4Dyn d; static thread_local Cc4Stat st;
+    static thread_local Cc4Dyn d; static thread_local Cc4Stat st; static thread_local Cc4Cold cold;
     CUDA_TRY(cudaMemcpy(&d, h->p.dyn + env, sizeof d, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(&st, h->p.stat + env, sizeof st, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&cold, h->p.cold + env, sizeof cold, cudaMemcpyDeviceToHost));
     int n = 0;
 #define PUT(v) do { if (n < cap) out[n] = (int32_t)(v); n++; } while (0)
     PUT(d.phase); PUT(d.step);
@@ -750,15 +752,15 @@ extern "C" int cc4_export_canon(cc4_handle *h, int env, int32_t *out, int cap, i
             if (!(k < 6 ? k < d.nserver[sn] : (k - 6) < d.nuser[sn])) continue;
             PUT(slot); PUT(d.ev[slot]);
             int np = 0;
-            for (int i = d.pstart[slot]; i < d.pstart[slot + 1]; i++) np += !P_DEAD(d.procs[i]);
+            for (int i = 0; i < d.nproc[slot]; i++) np += !P_DEAD(cold.procs[slot][i]);
             PUT(np);
-            for (int i = d.pstart[slot]; i < d.pstart[slot + 1]; i++) { uint32_t w = d.procs[i]; if (P_DEAD(w)) continue; PUT(P_PID(w)); PUT(P_KIND(w)); PUT(P_ROOT(w)); }
+            for (int i = 0; i < d.nproc[slot]; i++) { uint32_t w = cold.procs[slot][i]; if (P_DEAD(w)) continue; PUT(P_PID(w)); PUT(P_KIND(w)); PUT(P_ROOT(w)); }
             uint64_t v = d.svc64[slot];
             int ns = 0; while (ns < 9 && (SVC_ENTRY(v, ns) & 15u) != 15u) ns++;
             PUT(ns);
             for (int i = 0; i < ns; i++) {
                 uint32_t e = SVC_ENTRY(v, i), code = e & 15u, pid = 0;
-                for (int j = d.pstart[slot]; j < d.pstart[slot + 1]; j++) if (P_KIND(d.procs[j]) == code && P_SVC(d.procs[j])) pid = P_PID(d.procs[j]);
+                for (int j = 0; j < d.nproc[slot]; j++) if (P_KIND(cold.procs[slot][j]) == code && P_SVC(cold.procs[slot][j])) pid = P_PID(cold.procs[slot][j]);
                 PUT(code); PUT(pid); PUT(!(code == K_OT && (v & SVC_OT_STOPPED))); PUT((e >> 4) * 20);
             }
         } else {
@@ -782,10 +784,10 @@ extern "C" int cc4_export_canon(cc4_handle *h, int env, int32_t *out, int cap, i
         PUT(d.n_fsm[r]); for (int i = 0; i < d.n_fsm[r]; i++) { PUT(F_SLOT(d.fsm[r][i])); PUT(F_STATE(d.fsm[r][i])); PUT(F_HN(d.fsm[r][i])); }
         /* ports sorted by (ident, slot) */
         int np = 0;
-        for (int i = 0; i < d.n_ports; i++) np += PT_AGENT(d.ports[i]) == (uint32_t)r;
+        for (int i = 0; i < d.n_ports; i++) np += PT_AGENT(cold.ports[i]) == (uint32_t)r;
         PUT(np);
         for (int id = 0; id < 256; id++) for (int s = 0; s < 128; s++) for (int i = 0; i < d.n_ports; i++) {
-            uint32_t w = d.ports[i];
+            uint32_t w = cold.ports[i];
             if (PT_AGENT(w) == (uint32_t)r && PT_ID(w) == (uint32_t)id && PT_HOST(w) == (uint32_t)s) { PUT(id); PUT(s); PUT(PT_MASK(w)); }
         }
         uint32_t ip = d.inprog[A_RED0 + r];
@@ -793,9 +795,9 @@ extern "C" int cc4_export_canon(cc4_handle *h, int env, int32_t *out, int cap, i
     }
     for (int b = 0; b < CC4_NBLUE; b++) {
         int cnt = 0;
-        for (int i = 0; i < d.n_sus; i++) cnt += SU_AGENT(d.sus[i]) == (uint32_t)b;
+        for (int i = 0; i < d.n_sus; i++) cnt += SU_AGENT(cold.sus[i]) == (uint32_t)b;
         PUT(cnt);
-        for (int s = 0; s < CC4_NSLOT; s++) for (int i = 0; i < d.n_sus; i++) if (SU_AGENT(d.sus[i]) == (uint32_t)b && SU_SLOT(d.sus[i]) == (uint32_t)s) { PUT(s); PUT(SU_PID(d.sus[i])); }
+        for (int s = 0; s < CC4_NSLOT; s++) for (int i = 0; i < d.n_sus; i++) if (SU_AGENT(cold.sus[i]) == (uint32_t)b && SU_SLOT(cold.sus[i]) == (uint32_t)s) { PUT(s); PUT(SU_PID(cold.sus[i])); }
         uint32_t ip = d.inprog[b];
         if (IP_CODE(ip) == IP_NONE) { PUT(-1); PUT(0); } else { PUT(IP_CODE(ip)); PUT(IP_TICKS(ip)); }
     }

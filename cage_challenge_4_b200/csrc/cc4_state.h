@@ -17,7 +17,8 @@
 #define CC4_NBLUE 5
 #define CC4_MAXGREEN 80
 
-#define CC4_PROC_CAP 1024    /* process entries per episode (CSR pool over the 128 regular hosts) */
+#define CC4_PSLAB 24         /* process entries per host (tombstones included) */
+#define CC4_OSLAB 8          /* processes a host can have at reset: <= 5 services + blue + green + red session */
 #define CC4_SESS_CAP 160     /* red sessions per episode (all six agents) */
 #define CC4_PORT_CAP 384     /* (red abstract session, host) known-port entries */
 #define CC4_SUS_CAP 256      /* blue suspicious-pid entries */
@@ -90,30 +91,27 @@ enum { K_SSHD, K_OT, K_APACHE2, K_MYSQLD, K_SMTP, K_D_APACHE, K_D_TOMCAT, K_D_HA
 #define EV_OLDPROC 4u
 #define EV_OLDNET 8u
 
+/* HOT record: read and written every tick, staged through shared memory by the warp that owns the episode. */
 struct __attribute__((aligned(16))) Cc4Dyn {
-    /* ---- hosts ---- */
-    uint32_t procs[CC4_PROC_CAP];       /* CSR pool: host h owns [pstart[h], pstart[h+1]) in host.processes order */
     uint64_t svc64[128];
-    uint16_t pstart[136];               /* 129 used */
-    uint8_t ev[144];                    /* 137 used */
     /* ---- red sessions: one pool in creation order; an agent's state.sessions[agent] dict order is the pool order */
     uint32_t sess[CC4_SESS_CAP];
-    uint32_t ports[CC4_PORT_CAP];
-    uint32_t sus[CC4_SUS_CAP];
-    uint8_t sessf[CC4_SESS_CAP];
     /* ---- red knowledge (Shared/ActionSpace.py:170-212) ---- */
     uint32_t ip_known[CC4_NRED][4];
     uint32_t hn_known[CC4_NRED][4];
-    uint16_t fsm[CC4_NRED][CC4_FSM_CAP];
-    uint8_t ss[CC4_NRED][CC4_SS_CAP];   /* known server_session ids in dict order */
     uint32_t inprog[16];                /* actors 0..10 (blue 0-4, red 5-10) */
+    uint16_t fsm[CC4_NRED][CC4_FSM_CAP];
     uint16_t sn_known[8];
     uint16_t blocks[12];                /* blocks[to] bit from (State.blocks State.py:148); 9 used */
+    uint8_t ev[144];                    /* 137 used */
+    uint8_t sessf[CC4_SESS_CAP];
+    uint8_t ss[CC4_NRED][CC4_SS_CAP];   /* known server_session ids in dict order */
+    uint8_t nproc[128];                 /* entries used in Cc4Cold.procs[h] (tombstones included) */
+    uint8_t green_host[CC4_MAXGREEN];   /* static after reset, staged with the record because every tick needs it */
     uint8_t n_ss[8];
     uint8_t n_fsm[8];
     uint8_t sess_count[8];              /* state.sessions_count[red agent] (stale after Restore, RestoreFromBackup.py:9-19) */
     uint8_t msgs[8];
-    uint8_t green_host[CC4_MAXGREEN];   /* static after reset, staged with the record because every tick needs it */
     uint8_t nuser[8], nserver[8];
     uint16_t n_sess, n_ports, n_sus, step;
     uint8_t phase, done, fsm_started, red_active, ngreen, pad0[3];
@@ -121,10 +119,19 @@ struct __attribute__((aligned(16))) Cc4Dyn {
     uint32_t pad1[3];
 };
 
+/* COLD record: dynamic state that only the rare transitions touch (process lists on exploit / decoy / remove / restore,
+ * known ports on scans and exploits, suspicious pids on detection and Remove).  It stays in HBM and is accessed in place
+ * by the lane that executes the transition; it is NOT streamed every tick. */
+struct __attribute__((aligned(16))) Cc4Cold {
+    uint32_t procs[128][CC4_PSLAB];     /* host.processes in order (Host.py:117) */
+    uint32_t ports[CC4_PORT_CAP];
+    uint32_t sus[CC4_SUS_CAP];
+};
+
 struct __attribute__((aligned(16))) Cc4Stat {
-    uint32_t o_procs[CC4_PROC_CAP];     /* Host.create_backup Host.py:316 (original_processes) */
+    uint32_t o_procs[128][CC4_OSLAB];   /* Host.create_backup Host.py:316 (original_processes) */
     uint64_t o_svc64[128];              /* original_services */
-    uint16_t o_pstart[136];
+    uint8_t o_nproc[128];
     uint16_t router_pid[16];            /* pid of the blue session process on each router (0 = none), internet host has none */
     uint8_t blue_parent[8];
     uint8_t red_start[8];
@@ -133,4 +140,5 @@ struct __attribute__((aligned(16))) Cc4Stat {
 #ifdef __cplusplus
 static_assert(sizeof(Cc4Dyn) % 16 == 0, "Cc4Dyn must be a multiple of 16 bytes");
 static_assert(sizeof(Cc4Stat) % 16 == 0, "Cc4Stat must be a multiple of 16 bytes");
+static_assert(sizeof(Cc4Cold) % 16 == 0, "Cc4Cold must be a multiple of 16 bytes");
 #endif

@@ -63,10 +63,11 @@ class BatchedCC4:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # -- API ---------------------------------------------------------------------------------------
-    def state_bytes(self) -> tuple[int, int]:
-        d, s = C.c_size_t(), C.c_size_t()
-        _native.check(self._L.cc4_state_bytes(self._h, C.byref(d), C.byref(s)), "cc4_state_bytes")
-        return d.value, s.value
+    def state_bytes(self) -> tuple[int, int, int]:
+        """(hot, cold, static) bytes per episode; only the hot record is streamed every tick."""
+        d, k, s = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _native.check(self._L.cc4_state_bytes(self._h, C.byref(d), C.byref(k), C.byref(s)), "cc4_state_bytes")
+        return d.value, k.value, s.value
 
     def set_tape(self, recs: np.ndarray, seg_off: np.ndarray):
         """recs: DRAW_DTYPE [R]; seg_off uint32 [N, n_segs + 1] absolute offsets (tape mode)."""

@@ -61,8 +61,9 @@ typedef struct {
 int cc4_create(int n_envs, int device, uint64_t seed, uint64_t first_episode, int steps, int rng_mode, cc4_handle **out);
 int cc4_destroy(cc4_handle *h);
 
-/* Packed per-episode state sizes in bytes (dynamic = read+written every tick, static = written at reset). */
-int cc4_state_bytes(cc4_handle *h, size_t *dyn_bytes, size_t *stat_bytes);
+/* Packed per-episode state sizes in bytes: hot = the record streamed through shared memory every tick (read + written),
+ * cold = dynamic state touched in place by rare transitions only, stat = written at reset (read on Restore / export). */
+int cc4_state_bytes(cc4_handle *h, size_t *hot_bytes, size_t *cold_bytes, size_t *stat_bytes);
 
 /* Tape mode only: recs_dev[n_recs]; seg_off_dev[n_envs][n_segs + 1] absolute offsets into recs_dev, segment 0 =
  * reset, segment 1 + tick*CC4_N_ACTORS + actor = that actor's draws in that tick (oracle/ref_harness.py). */
