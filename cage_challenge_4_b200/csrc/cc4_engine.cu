@@ -27,7 +27,7 @@ struct WarpSmem {
 
 struct Params {
     Cc4Dyn *dyn; Cc4Stat *stat; Cc4Cold *cold;
-    int n_envs, steps, rng_mode;
+    int n_envs, n_alloc, steps, rng_mode;   /* n_alloc = n_envs rounded up to a whole block: every warp of the grid owns an episode */
     uint32_t k0, k1hi; uint64_t first_episode;
     const cc4_draw *tape; const uint32_t *seg_off; uint32_t n_segs;
 };
@@ -229,7 +229,11 @@ __device__ __forceinline__ Act unpack_act(uint32_t w)
 }
 __device__ __forceinline__ uint32_t pack_act(const Act &a, int ticks) { return IP_MAKE(a.code, a.host < 0 ? 255 : a.host, a.subnet < 0 ? 15 : a.subnet, a.session, ticks); }
 
-__device__ void w_tick(Ctx &c, const int32_t *actions /* [5] */, const uint8_t *msgs /* [5] or null */, float *reward_out, uint8_t *done_out)
+/* PHASE_SYNC keeps the warps of a block in the same phase of the tick: they then share the instruction cache lines of
+ * that phase instead of thrashing it (ncu: stall_no_inst was the top stall reason without it). */
+#define PHASE_SYNC() __syncthreads()
+#define N_PHASE_SYNC 7
+__device__ void w_tick(Ctx &c, const int32_t *actions /* [5] or null = all Sleep */, const uint8_t *msgs /* [5] or null */, float *reward_out, uint8_t *done_out)
 {
     Cc4Dyn *s = c.s; Scratch *x = c.x;
     const int lane = lane_id();
@@ -252,13 +256,14 @@ __device__ void w_tick(Ctx &c, const int32_t *actions /* [5] */, const uint8_t *
         if (np > s->phase) s->phase = (uint8_t)np;
     }
     __syncwarp();
+    PHASE_SYNC();
 
     /* ---- 1. policies (:236-248) and 2. duration queue (:245-265): one lane per blue / red actor.  The scripted red
        agents only read their own knowledge and draw from their own stream, so the six run side by side. ---- */
     int cost = 0;
     if (lane < 11) {
         Act a = { AC_SLEEP, -1, -1, 0 };
-        if (lane < A_RED0) { a = blue_decode(s, lane, actions[lane], nullptr); if (a.code == AC_RESTORE) cost = -1; }   /* Restore.py:70, :310-311 */
+        if (lane < A_RED0) { a = blue_decode(s, lane, actions ? actions[lane] : (lane == 4 ? 145 : 49), nullptr); if (a.code == AC_RESTORE) cost = -1; }   /* Restore.py:70, :310-311 */
         else if (s->red_active >> (lane - A_RED0) & 1) a = red_policy(c, lane - A_RED0);
         uint32_t ip = s->inprog[lane];
         if (IP_CODE(ip) == IP_NONE) ip = pack_act(a, c_duration[a.code]);
@@ -274,6 +279,7 @@ __device__ void w_tick(Ctx &c, const int32_t *actions /* [5] */, const uint8_t *
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o);
     __syncwarp();
+    PHASE_SYNC();
     /* filter_actions (:466-486) looks at the sessions as they are BEFORE anything executes; blue / green sessions never go away */
     _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
         uint32_t w = x->subw[A_RED0 + r];
@@ -300,6 +306,7 @@ __device__ void w_tick(Ctx &c, const int32_t *actions /* [5] */, const uint8_t *
             }
     }
     __syncwarp();
+    PHASE_SYNC();
     /* green agents, lane per agent (EnterpriseGreenAgent.py:42-78); the phishing side effect is order dependent and
        replayed below in agent order */
     {
@@ -326,6 +333,7 @@ __device__ void w_tick(Ctx &c, const int32_t *actions /* [5] */, const uint8_t *
             __syncwarp();
         }
     }
+    PHASE_SYNC();
     if (lane == 0) {
         _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
             int a = A_RED0 + r;
@@ -336,6 +344,7 @@ __device__ void w_tick(Ctx &c, const int32_t *actions /* [5] */, const uint8_t *
         }
     }
     __syncwarp();
+    PHASE_SYNC();
     /* ---- 4. reassignment (:278) ---- */
     w_scan_sessions(c);
     if (x->misplaced) {
@@ -345,6 +354,7 @@ __device__ void w_tick(Ctx &c, const int32_t *actions /* [5] */, const uint8_t *
     }
     uint32_t active = 0;
     _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) active |= (x->n_red[r] > 0) << r;    /* :896-903: active iff it holds a session */
+    PHASE_SYNC();
     /* ---- 5. end-turn actions (:281-286): Monitor for blue, RedSessionCheck for active red ---- */
     w_monitor_all(c);
     if (lane == 0) {
@@ -361,6 +371,7 @@ __device__ void w_tick(Ctx &c, const int32_t *actions /* [5] */, const uint8_t *
         agent_end_turn(c, lane);
     }
     __syncwarp();
+    PHASE_SYNC();
     if (lane == 0) {
         s->fsm_started |= (uint8_t)active;
         /* ---- 6. counters, done (:297-300), reward (BlueRewardMachine.py:70-121) ---- */
@@ -395,12 +406,13 @@ k_step(Params p, const int32_t *actions, const uint8_t *msgs, uint8_t *obs, floa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpSmem *w = reinterpret_cast<WarpSmem *>(smem_raw) + (threadIdx.x >> 5);
     int env = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    if (env >= p.n_envs) return;
+    const bool valid = env < p.n_envs;     /* padding episodes (n_envs..n_alloc) run with Sleep inputs and write no outputs */
     Ctx c; make_ctx(c, w, p, env);
     w_load(&w->dyn, p.dyn + env);
-    w_tick(c, actions + (size_t)env * 5, msgs ? msgs + (size_t)env * 5 : nullptr,
-           (flags & CC4_STEP_REWARD) && reward ? reward + env : nullptr, done ? done + env : nullptr);
-    if ((flags & CC4_STEP_OBS) && obs) w_write_obs(&w->dyn, w->x.obsbits, obs + (size_t)env * CC4_N_BLUE * CC4_OBS_LEN);
+    w_tick(c, valid ? actions + (size_t)env * 5 : nullptr, valid && msgs ? msgs + (size_t)env * 5 : nullptr,
+           valid && (flags & CC4_STEP_REWARD) && reward ? reward + env : nullptr, valid && done ? done + env : nullptr);
+    PHASE_SYNC();
+    if (valid && (flags & CC4_STEP_OBS) && obs) w_write_obs(&w->dyn, w->x.obsbits, obs + (size_t)env * CC4_N_BLUE * CC4_OBS_LEN);
     w_store(p.dyn + env, &w->dyn);
 }
 
@@ -412,7 +424,7 @@ k_rollout(Params p, int n_ticks, uint32_t pk0, uint32_t pk1, float *reward_sum, 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpSmem *w = reinterpret_cast<WarpSmem *>(smem_raw) + (threadIdx.x >> 5);
     int env = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    if (env >= p.n_envs) return;
+    const bool valid = env < p.n_envs;
     Ctx c; make_ctx(c, w, p, env);
     w_load(&w->dyn, p.dyn + env);
     uint64_t ep = p.first_episode + (uint64_t)env;
@@ -421,7 +433,11 @@ k_rollout(Params p, int n_ticks, uint32_t pk0, uint32_t pk1, float *reward_sum, 
     __shared__ float rew_s[WARPS_PER_BLOCK];
     int32_t *act = act_s[threadIdx.x >> 5];
     _Pragma("unroll 1") for (int t = 0; t < n_ticks; t++) {
-        if (w->dyn.done) break;
+        if (__syncthreads_and(w->dyn.done)) break;
+        if (w->dyn.done) {      /* this episode is over but a sibling warp still runs: keep in step with the block's barriers */
+            _Pragma("unroll 1") for (int k = 0; k < N_PHASE_SYNC; k++) PHASE_SYNC();
+            continue;
+        }
         if (lane_id() == 0) {
             uint32_t tk = w->dyn.step;
             uint32_t c1[4] = { tk, 0xB10Eu, (uint32_t)ep, (uint32_t)(ep >> 32) }, c2[4] = { tk, 0xB10Fu, (uint32_t)ep, (uint32_t)(ep >> 32) };
@@ -433,7 +449,7 @@ k_rollout(Params p, int n_ticks, uint32_t pk0, uint32_t pk1, float *reward_sum, 
         w_tick(c, act, nullptr, &rew_s[threadIdx.x >> 5], nullptr);
         if (lane_id() == 0) total += rew_s[threadIdx.x >> 5];
     }
-    if ((flags & CC4_STEP_REWARD) && reward_sum && lane_id() == 0) reward_sum[env] += total;
+    if (valid && (flags & CC4_STEP_REWARD) && reward_sum && lane_id() == 0) reward_sum[env] += total;
     w_store(p.dyn + env, &w->dyn);
 }
 
@@ -499,7 +515,7 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ResetSmem *w = reinterpret_cast<ResetSmem *>(smem_raw);
     int env = blockIdx.x;
-    if (env >= p.n_envs) return;
+    const bool valid = env < p.n_envs;
     Ctx c; c.s = &w->dyn; c.x = &w->x; c.st = p.stat + env; c.k = p.cold + env;
     {
         uint64_t ep = p.first_episode + (uint64_t)env;
@@ -575,8 +591,8 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
         if (c.rng_mode == 1 && c.n_segs > 0 && c.x->ctr[NAG] != c.seg[1] - c.seg[0]) fail(c, CC4_E_TAPE_LEFT);
     }
     __syncwarp();
-    if (obs) w_write_obs(&w->dyn, w->x.obsbits, obs + (size_t)env * CC4_N_BLUE * CC4_OBS_LEN);
-    if (mask) w_write_mask(&w->dyn, mask + (size_t)env * CC4_N_BLUE * CC4_MASK_LEN);
+    if (valid && obs) w_write_obs(&w->dyn, w->x.obsbits, obs + (size_t)env * CC4_N_BLUE * CC4_OBS_LEN);
+    if (valid && mask) w_write_mask(&w->dyn, mask + (size_t)env * CC4_N_BLUE * CC4_MASK_LEN);
     w_store(p.dyn + env, &w->dyn);
 }
 
@@ -612,12 +628,12 @@ extern "C" int cc4_create(int n_envs, int device, uint64_t seed, uint64_t first_
     if (!h) return set_err(CC4_ERR_STATE, "cc4_create: out of host memory%s", "");
     memset(h, 0, sizeof *h);
     h->device = device;
-    h->p.n_envs = n_envs; h->p.steps = steps; h->p.rng_mode = rng_mode;
+    h->p.n_envs = n_envs; h->p.n_alloc = (n_envs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK * WARPS_PER_BLOCK; h->p.steps = steps; h->p.rng_mode = rng_mode;
     h->p.k0 = (uint32_t)seed; h->p.k1hi = (uint32_t)(seed >> 32); h->p.first_episode = first_episode;
-    CUDA_TRY(cudaMalloc(&h->p.dyn, sizeof(Cc4Dyn) * (size_t)n_envs));
-    CUDA_TRY(cudaMalloc(&h->p.stat, sizeof(Cc4Stat) * (size_t)n_envs));
-    CUDA_TRY(cudaMalloc(&h->p.cold, sizeof(Cc4Cold) * (size_t)n_envs));
-    CUDA_TRY(cudaMemset(h->p.dyn, 0, sizeof(Cc4Dyn) * (size_t)n_envs));
+    CUDA_TRY(cudaMalloc(&h->p.dyn, sizeof(Cc4Dyn) * (size_t)h->p.n_alloc));
+    CUDA_TRY(cudaMalloc(&h->p.stat, sizeof(Cc4Stat) * (size_t)h->p.n_alloc));
+    CUDA_TRY(cudaMalloc(&h->p.cold, sizeof(Cc4Cold) * (size_t)h->p.n_alloc));
+    CUDA_TRY(cudaMemset(h->p.dyn, 0, sizeof(Cc4Dyn) * (size_t)h->p.n_alloc));
     CUDA_TRY(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * WARPS_PER_BLOCK)));
     CUDA_TRY(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * WARPS_PER_BLOCK)));
     CUDA_TRY(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResetSmem)));
@@ -656,7 +672,7 @@ extern "C" int cc4_reset(cc4_handle *h, uint8_t *obs_dev, uint8_t *mask_dev, voi
     if (!h) return set_err(CC4_ERR_ARG, "cc4_reset: null handle%s", "");
     if (h->p.rng_mode == 1 && !h->p.tape) return set_err(CC4_ERR_STATE, "cc4_reset: tape mode without cc4_set_tape%s", "");
     CUDA_TRY(cudaSetDevice(h->device));
-    k_reset<<<h->p.n_envs, 32, sizeof(ResetSmem), (cudaStream_t)stream>>>(h->p, obs_dev, mask_dev);
+    k_reset<<<h->p.n_alloc, 32, sizeof(ResetSmem), (cudaStream_t)stream>>>(h->p, obs_dev, mask_dev);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return CC4_OK;
@@ -667,7 +683,7 @@ extern "C" int cc4_step(cc4_handle *h, const int32_t *actions_dev, const uint8_t
 {
     if (!h || !actions_dev) return set_err(CC4_ERR_ARG, "cc4_step: null handle or actions%s", "");
     CUDA_TRY(cudaSetDevice(h->device));
-    int blocks = (h->p.n_envs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    int blocks = h->p.n_alloc / WARPS_PER_BLOCK;
     k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * WARPS_PER_BLOCK, (cudaStream_t)stream>>>(h->p, actions_dev, msgs_dev, obs_dev, reward_dev, done_dev, flags);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -704,7 +720,7 @@ extern "C" int cc4_rollout(cc4_handle *h, int n_ticks, uint64_t policy_seed, flo
 {
     if (!h || n_ticks < 0) return set_err(CC4_ERR_ARG, "cc4_rollout: bad argument%s", "");
     CUDA_TRY(cudaSetDevice(h->device));
-    int blocks = (h->p.n_envs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    int blocks = h->p.n_alloc / WARPS_PER_BLOCK;
     k_rollout<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * WARPS_PER_BLOCK, (cudaStream_t)stream>>>(
         h->p, n_ticks, (uint32_t)policy_seed ^ 0x5EEDu, (uint32_t)(policy_seed >> 32), reward_sum_dev, flags);
     h->launches++;
