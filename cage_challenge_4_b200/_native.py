@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcc4_b200.so")
 
 EXPORTS = [
-    "cc4_create", "cc4_destroy", "cc4_state_bytes", "cc4_set_tape", "cc4_reset", "cc4_step", "cc4_step_host",
+    "cc4_create", "cc4_destroy", "cc4_set_episode_base", "cc4_state_bytes", "cc4_set_tape", "cc4_reset", "cc4_step", "cc4_step_host",
     "cc4_rollout", "cc4_error_flags", "cc4_export_canon", "cc4_launch_count", "cc4_last_error",
 ]
 
@@ -31,6 +31,7 @@ def load():
     vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
     L.cc4_create.argtypes = [i32, i32, u64, u64, i32, i32, C.POINTER(vp)]
     L.cc4_destroy.argtypes = [vp]
+    L.cc4_set_episode_base.argtypes = [vp, u64, u64]
     L.cc4_state_bytes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.cc4_set_tape.argtypes = [vp, vp, vp, C.c_uint32]
     L.cc4_reset.argtypes = [vp, vp, vp, vp]

@@ -651,6 +651,13 @@ extern "C" int cc4_destroy(cc4_handle *h)
     return CC4_OK;
 }
 
+extern "C" int cc4_set_episode_base(cc4_handle *h, uint64_t seed, uint64_t first_episode)
+{
+    if (!h) return set_err(CC4_ERR_ARG, "cc4_set_episode_base: null handle%s", "");
+    h->p.k0 = (uint32_t)seed; h->p.k1hi = (uint32_t)(seed >> 32); h->p.first_episode = first_episode;
+    return CC4_OK;
+}
+
 extern "C" int cc4_state_bytes(cc4_handle *h, size_t *hot_bytes, size_t *cold_bytes, size_t *stat_bytes)
 {
     (void)h;

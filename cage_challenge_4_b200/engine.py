@@ -78,6 +78,14 @@ class BatchedCC4:
         self._tape = (recs_t, seg_t)
         _native.check(self._L.cc4_set_tape(self._h, recs_t.data_ptr(), seg_t.data_ptr(), seg_off.shape[1] - 1), "cc4_set_tape")
 
+    def set_episode_base(self, seed: int | None = None, first_episode: int | None = None):
+        """Re-key the RNG streams used by the next reset(): episode i becomes (seed, first_episode + i)."""
+        if seed is not None:
+            self.seed = int(seed)
+        if first_episode is not None:
+            self.first_episode = int(first_episode)
+        _native.check(self._L.cc4_set_episode_base(self._h, self.seed & (2**64 - 1), self.first_episode), "cc4_set_episode_base")
+
     def reset(self):
         _native.check(self._L.cc4_reset(self._h, self.obs.data_ptr(), self.mask.data_ptr(), self._stream()), "cc4_reset")
         return self.obs, self.mask.bool()

@@ -61,6 +61,10 @@ typedef struct {
 int cc4_create(int n_envs, int device, uint64_t seed, uint64_t first_episode, int steps, int rng_mode, cc4_handle **out);
 int cc4_destroy(cc4_handle *h);
 
+/* Re-key the handle: the next cc4_reset generates episodes (seed, first_episode + i).  This is how consecutive resets
+ * produce fresh scenarios, as consecutive CybORG.reset() calls do by continuing one RNG (env.py:218-236). */
+int cc4_set_episode_base(cc4_handle *h, uint64_t seed, uint64_t first_episode);
+
 /* Packed per-episode state sizes in bytes: hot = the record streamed through shared memory every tick (read + written),
  * cold = dynamic state touched in place by rare transitions only, stat = written at reset (read on Restore / export). */
 int cc4_state_bytes(cc4_handle *h, size_t *hot_bytes, size_t *cold_bytes, size_t *stat_bytes);
