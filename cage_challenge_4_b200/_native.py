@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcc4_b200.so")
 
 EXPORTS = [
-    "cc4_create", "cc4_destroy", "cc4_set_episode_base", "cc4_state_bytes", "cc4_set_tape", "cc4_reset", "cc4_step", "cc4_step_host",
+    "cc4_create", "cc4_destroy", "cc4_set_episode_base", "cc4_state_bytes", "cc4_set_tape", "cc4_reset", "cc4_reset_host", "cc4_step", "cc4_step_host",
     "cc4_rollout", "cc4_error_flags", "cc4_export_canon", "cc4_launch_count", "cc4_last_error",
 ]
 
@@ -35,6 +35,7 @@ def load():
     L.cc4_state_bytes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.cc4_set_tape.argtypes = [vp, vp, vp, C.c_uint32]
     L.cc4_reset.argtypes = [vp, vp, vp, vp]
+    L.cc4_reset_host.argtypes = [vp, vp, vp, vp]
     L.cc4_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
     L.cc4_step_host.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
     L.cc4_rollout.argtypes = [vp, i32, u64, vp, i32, vp]

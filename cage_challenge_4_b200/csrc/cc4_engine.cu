@@ -615,7 +615,7 @@ struct cc4_handle {
     Params p;
     int device;
     uint64_t launches;
-    int32_t *stage_actions; uint8_t *stage_msgs, *stage_obs, *stage_done; float *stage_reward;   /* device staging for cc4_step_host */
+    int32_t *stage_actions; uint8_t *stage_msgs, *stage_obs, *stage_mask, *stage_done; float *stage_reward;   /* device staging for cc4_step_host */
 };
 
 extern "C" const char *cc4_last_error(void) { return g_err; }
@@ -646,7 +646,7 @@ extern "C" int cc4_destroy(cc4_handle *h)
     if (!h) return CC4_OK;
     cudaSetDevice(h->device);
     cudaFree(h->p.dyn); cudaFree(h->p.stat); cudaFree(h->p.cold);
-    cudaFree(h->stage_actions); cudaFree(h->stage_msgs); cudaFree(h->stage_obs); cudaFree(h->stage_done); cudaFree(h->stage_reward);
+    cudaFree(h->stage_actions); cudaFree(h->stage_msgs); cudaFree(h->stage_obs); cudaFree(h->stage_mask); cudaFree(h->stage_done); cudaFree(h->stage_reward);
     delete h;
     return CC4_OK;
 }
@@ -685,6 +685,35 @@ extern "C" int cc4_reset(cc4_handle *h, uint8_t *obs_dev, uint8_t *mask_dev, voi
     return CC4_OK;
 }
 
+static int ensure_staging(cc4_handle *h)
+{
+    if (h->stage_actions) return CC4_OK;
+    size_t n = (size_t)h->p.n_envs;
+    CUDA_TRY(cudaMalloc(&h->stage_actions, n * 5 * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&h->stage_msgs, n * 5));
+    CUDA_TRY(cudaMalloc(&h->stage_obs, n * CC4_N_BLUE * CC4_OBS_LEN));
+    CUDA_TRY(cudaMalloc(&h->stage_mask, n * CC4_N_BLUE * CC4_MASK_LEN));
+    CUDA_TRY(cudaMalloc(&h->stage_done, n));
+    CUDA_TRY(cudaMalloc(&h->stage_reward, n * sizeof(float)));
+    return CC4_OK;
+}
+
+extern "C" int cc4_reset_host(cc4_handle *h, uint8_t *obs_host, uint8_t *mask_host, void *stream)
+{
+    if (!h) return set_err(CC4_ERR_ARG, "cc4_reset_host: null handle%s", "");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = ensure_staging(h);
+    if (rc) return rc;
+    size_t n = (size_t)h->p.n_envs;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = cc4_reset(h, obs_host ? h->stage_obs : nullptr, mask_host ? h->stage_mask : nullptr, stream);
+    if (rc) return rc;
+    if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, h->stage_obs, n * CC4_N_BLUE * CC4_OBS_LEN, cudaMemcpyDeviceToHost, st));
+    if (mask_host) CUDA_TRY(cudaMemcpyAsync(mask_host, h->stage_mask, n * CC4_N_BLUE * CC4_MASK_LEN, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return CC4_OK;
+}
+
 extern "C" int cc4_step(cc4_handle *h, const int32_t *actions_dev, const uint8_t *msgs_dev, uint8_t *obs_dev, float *reward_dev,
                         uint8_t *done_dev, int flags, void *stream)
 {
@@ -704,13 +733,7 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
     CUDA_TRY(cudaSetDevice(h->device));
     size_t n = (size_t)h->p.n_envs;
     cudaStream_t st = (cudaStream_t)stream;
-    if (!h->stage_actions) {
-        CUDA_TRY(cudaMalloc(&h->stage_actions, n * 5 * sizeof(int32_t)));
-        CUDA_TRY(cudaMalloc(&h->stage_msgs, n * 5));
-        CUDA_TRY(cudaMalloc(&h->stage_obs, n * CC4_N_BLUE * CC4_OBS_LEN));
-        CUDA_TRY(cudaMalloc(&h->stage_done, n));
-        CUDA_TRY(cudaMalloc(&h->stage_reward, n * sizeof(float)));
-    }
+    { int rc0 = ensure_staging(h); if (rc0) return rc0; }
     CUDA_TRY(cudaMemcpyAsync(h->stage_actions, actions_host, n * 5 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     if (msgs_host) CUDA_TRY(cudaMemcpyAsync(h->stage_msgs, msgs_host, n * 5, cudaMemcpyHostToDevice, st));
     int rc = cc4_step(h, h->stage_actions, msgs_host ? h->stage_msgs : nullptr, obs_host ? h->stage_obs : nullptr,

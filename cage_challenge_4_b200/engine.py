@@ -46,6 +46,7 @@ class BatchedCC4:
         self.done = torch.zeros(n, dtype=torch.uint8, device=self.device)
         self._tape = None
         self._pinned = None
+        self._pinned_reset = None
 
     # -- life cycle --------------------------------------------------------------------------------
     def close(self):
@@ -89,6 +90,16 @@ class BatchedCC4:
     def reset(self):
         _native.check(self._L.cc4_reset(self._h, self.obs.data_ptr(), self.mask.data_ptr(), self._stream()), "cc4_reset")
         return self.obs, self.mask.bool()
+
+    def reset_host(self):
+        """reset() with HOST outputs (pinned): obs uint8 [N,5,210], mask uint8 [N,5,242]."""
+        n = self.num_envs
+        if self._pinned_reset is None:
+            self._pinned_reset = dict(obs=torch.zeros((n, N_BLUE, OBS_LEN), dtype=torch.uint8).pin_memory(),
+                                      mask=torch.zeros((n, N_BLUE, MASK_LEN), dtype=torch.uint8).pin_memory())
+        p = self._pinned_reset
+        _native.check(self._L.cc4_reset_host(self._h, p["obs"].data_ptr(), p["mask"].data_ptr(), self._stream()), "cc4_reset_host")
+        return p["obs"], p["mask"]
 
     def step(self, actions: torch.Tensor, messages: torch.Tensor | None = None, flags: int = STEP_ALL):
         assert actions.dtype == torch.int32 and actions.is_cuda and actions.shape == (self.num_envs, N_BLUE) and actions.is_contiguous()

@@ -79,6 +79,9 @@ int cc4_set_tape(cc4_handle *h, const cc4_draw *recs_dev, const uint32_t *seg_of
  * obs_dev: uint8 [n_envs][5][210] or NULL; mask_dev: uint8 [n_envs][5][242] or NULL. */
 int cc4_reset(cc4_handle *h, uint8_t *obs_dev, uint8_t *mask_dev, void *stream);
 
+/* Same call with HOST buffers (copies the outputs device->host and synchronises the stream). */
+int cc4_reset_host(cc4_handle *h, uint8_t *obs_host, uint8_t *mask_host, void *stream);
+
 /* Replaces: BlueFlatWrapper.step -> CybORG.parallel_step -> SimulationController.step (+ send_messages,
  * observation_change x5, BlueRewardMachine) for every episode of the batch.
  * actions_dev int32 [n_envs][5] BlueFixedActionWrapper indices; msgs_dev uint8 [n_envs][5] (bit i = message[i]) or NULL;

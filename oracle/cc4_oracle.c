@@ -1337,3 +1337,49 @@ long cc4o_run_episodes(uint64_t seed, uint64_t first_episode, int n_eps, int ste
     if (ret_sum) *ret_sum = total;
     return ticks;
 }
+
+/* capacity probe (sizing of the CUDA engine's fixed tables): runs the same episodes as cc4o_run_episodes and
+ * records the maxima over all ticks of
+ *   hw[0] processes on one host          hw[1] red sessions of all agents      hw[2] largest session ident
+ *   hw[3] (abstract session, host) known-port entries                          hw[4] suspicious pids of all blue agents
+ *   hw[5] FSM hosts of one red agent     hw[6] server_session ids of one agent hw[7] observation entries of one agent in a tick
+ *   hw[8] event pids pending in a tick   hw[9] services on one host            hw[10] episodes with an error flag */
+void cc4o_capacity_probe(uint64_t seed, uint64_t first_episode, int n_eps, int steps, int *hw)
+{
+    for (int i = 0; i < 11; i++) hw[i] = 0;
+    cc4o_env *e = cc4o_create(seed, first_episode, steps, 0);
+#define HW(i, v) do { int v_ = (v); if (v_ > hw[i]) hw[i] = v_; } while (0)
+    for (int k = 0; k < n_eps; k++) {
+        e->episode = first_episode + (uint64_t)k;
+        cc4o_reset(e);
+        for (int t = 0; t < steps - 1; t++) {
+            int32_t act[NBLUE]; uint8_t msg[NBLUE] = { 0 }; float r; uint8_t d;
+            uint32_t c[4] = { (uint32_t)t, 0xB10Eu, (uint32_t)e->episode, (uint32_t)(e->episode >> 32) };
+            philox4x32_10(c, (uint32_t)seed ^ 0x5EEDu, (uint32_t)(seed >> 32));
+            uint32_t c2[4] = { (uint32_t)t, 0xB10Fu, (uint32_t)e->episode, (uint32_t)(e->episode >> 32) };
+            philox4x32_10(c2, (uint32_t)seed ^ 0x5EEDu, (uint32_t)(seed >> 32));
+            for (int b = 0; b < 4; b++) act[b] = (int32_t)(((uint64_t)c[b] * 82) >> 32);
+            act[4] = (int32_t)(((uint64_t)c2[0] * 242) >> 32);
+            /* pending event pids are consumed by the end-turn Monitor inside the step: count them via the sus growth */
+            int sus0 = 0; for (int b = 0; b < NBLUE; b++) sus0 += e->n_sus[b];
+            cc4o_step(e, act, msg, NULL, &r, &d);
+            int sus1 = 0; for (int b = 0; b < NBLUE; b++) sus1 += e->n_sus[b];
+            HW(8, sus1 - sus0); HW(4, sus1);
+            int ns = 0, np = 0;
+            for (int s = 0; s < 128; s++) { HW(0, e->hosts[s].nproc); HW(9, e->hosts[s].nsvc); }
+            for (int rr = 0; rr < NRED; rr++) {
+                int a = A_RED0 + rr;
+                ns += e->nsess[a];
+                for (int i = 0; i < e->nsess[a]; i++) {
+                    HW(2, e->sess[a][i].id);
+                    if (e->sess[a][i].type == 1) for (int s = 0; s < NSLOT; s++) np += e->sess[a][i].has_ports[s];
+                }
+                HW(5, e->n_fsm[rr]); HW(6, e->n_ss[rr]); HW(7, e->obs[rr].n);
+            }
+            HW(1, ns); HW(3, np);
+        }
+        if (e->err) hw[10]++;
+    }
+#undef HW
+    cc4o_destroy(e);
+}
