@@ -172,8 +172,11 @@ def main():
     env = BatchedCC4(n, device=local_rank, seed=0, steps=500, first_episode=rank * n)
     dyn_bytes, cold_bytes, stat_bytes = env.state_bytes()
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    pool = [torch.stack([torch.randint(0, k, (n,), generator=g, device=dev) for k in (82, 82, 82, 82, 242)], 1).to(torch.int32).contiguous()
-            for _ in range(16)]
+    # one fresh uniform-random action tensor per tick (a short repeating pool would make every episode re-issue the same
+    # few actions, e.g. dozens of decoys on one host, which is not the workload BASELINE names)
+    n_pool = min(max(args.steps, args.e2e_steps, 16), 512)
+    pool = [torch.stack([torch.randint(0, k, (n,), generator=g, device=dev, dtype=torch.int32) for k in (82, 82, 82, 82, 242)], 1).contiguous()
+            for _ in range(n_pool)]
     ret = torch.zeros(n, dtype=torch.float64, device=dev)
 
     def barrier():
@@ -203,35 +206,34 @@ def main():
     sampler.start()
     l0 = env.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the dominant kernel (k_step) is also timed alone, launch by launch, with CUDA events on the launching stream
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0.record()
     for i in range(args.steps):
-        one_step(i)
+        if tick == EPISODE_TICKS:            # every episode of the batch is done: reset (inside the timed region)
+            env.reset()
+            tick = 0
+        kev[i][0].record()
+        obs, rew, done = env.step(pool[i % len(pool)], None, STEP_ALL)
+        kev[i][1].record()
+        ret.add_(rew)
+        tick += 1
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = env.launch_count() - l0
-
-    # kernel-only average duration of the dominant kernel (k_step) for the roofline, CUDA events on the launching stream
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 20
-    torch.cuda.synchronize()
-    k0.record()
-    for i in range(reps):
-        env.step(pool[i % len(pool)], None, STEP_ALL)
-    k1.record()
-    torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / reps
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     clocks = sampler.stop()
 
     # end to end through the public host-buffer API: pinned actions in, pinned obs / reward / done out
-    host_pool = [p.cpu().pin_memory() for p in pool[:4]]
+    host_pool = [p.cpu().pin_memory() for p in pool[:max(args.e2e_steps, 4)]]
     env.reset()
     for i in range(3):
-        env.step_host(host_pool[i % 4])
+        env.step_host(host_pool[i % len(host_pool)])
     barrier()
     t0 = time.perf_counter()
     for i in range(args.e2e_steps):
-        o, r, d = env.step_host(host_pool[i % 4])
+        o, r, d = env.step_host(host_pool[i % len(host_pool)])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     h2d = n * N_BLUE * 4

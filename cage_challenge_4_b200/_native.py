@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcc4_b200.so")
+# CC4_B200_LIB selects another build of the same C-ABI (tuning variants built by tools/build_variants.py)
+LIB_PATH = os.environ.get("CC4_B200_LIB") or os.path.join(HERE, "libcc4_b200.so")
 
 EXPORTS = [
     "cc4_create", "cc4_destroy", "cc4_set_episode_base", "cc4_state_bytes", "cc4_set_tape", "cc4_reset", "cc4_reset_host", "cc4_step", "cc4_step_host",

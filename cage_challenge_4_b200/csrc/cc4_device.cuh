@@ -89,6 +89,15 @@ __constant__ uint8_t c_duration[32] = { 1, 1, 2, 3, 5, 2, 1, 1, 1, 1, 1, 1, 3, 2
 #define PB_443 32
 
 struct Act { int code, host, subnet, session; };
+/* actions travel between functions as one packed word (IP_MAKE layout, cc4_state.h) so that they stay in registers */
+#define ACT_VALID (1u << 31)   /* blue_decode: the index is a valid (mask True) action */
+__device__ __forceinline__ Act unpack_act(uint32_t w)
+{
+    Act a = { (int)IP_CODE(w), IP_HOST(w) == 255 ? -1 : (int)IP_HOST(w), IP_SUBNET(w) == 15 ? -1 : (int)IP_SUBNET(w), (int)IP_SESSION(w) };
+    return a;
+}
+__device__ __forceinline__ uint32_t pack_act(const Act &a, int ticks) { return IP_MAKE(a.code, a.host < 0 ? 255 : a.host, a.subnet < 0 ? 15 : a.subnet, a.session, ticks); }
+#define ACT_SLEEP_WORD IP_MAKE(AC_SLEEP, 255, 15, 0, 0)
 
 /* per-warp scratch (shared memory, not persisted) */
 struct Scratch {
@@ -109,21 +118,41 @@ struct Scratch {
     uint32_t ssmask[CC4_NRED][8];                 /* bit id: server_session id known to agent r (mirror of Cc4Dyn.ss, rebuilt every tick) */
     uint32_t obsbits[40];                         /* observation vectors as bit strings [5][8] */
     int reward;
+    uint32_t blk_id[12];                          /* cached Philox block per serial stream: actors 0..10, [11] = reset */
+    uint32_t blk[12][4];
+    uint32_t et[CC4_NRED][4][4];                  /* agent_end_turn work masks per red agent: seen / present / hostname / user+ */
 };
 
-struct Ctx {
-    Cc4Dyn *s; Scratch *x; Cc4Stat *st; Cc4Cold *k;
+/* per-warp context (shared memory): everything a device function needs besides the record and the scratch */
+struct WarpCtx {
+    Cc4Stat *st; Cc4Cold *k;
+    const cc4_draw *tape; const uint32_t *seg; uint32_t n_segs;
     int tick;                 /* state step_count at the start of the tick; -1 during reset */
     int steps, rng_mode;
-    uint32_t k0, k1, ep_lo;
-    const cc4_draw *tape; const uint32_t *seg; uint32_t n_segs;
+    uint32_t k0, k1, ep_lo, pad;
 };
+struct __align__(16) WarpSmem {
+    Cc4Dyn dyn;
+    Scratch x;
+    WarpCtx c;
+};
+/* A warp's WarpSmem lives in dynamic shared memory; device functions receive its byte offset (`Cx`, one register) and
+ * address it through the __shared__ symbol, so every access is a shared-memory instruction and nothing about the
+ * context is passed through the thread stack (ncu r01a: the stack-resident context cost 24 % long-scoreboard stalls). */
+extern __shared__ __align__(16) unsigned char smem_raw[];
+typedef uint32_t Cx;
+#define WS(c) (reinterpret_cast<WarpSmem *>(smem_raw + (c)))
+#define DYN(c) (&WS(c)->dyn)
+#define SCR(c) (&WS(c)->x)
+#define WC(c) (&WS(c)->c)
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-__device__ __forceinline__ void fail(Ctx &c, uint32_t flag) { atomicOr(&c.s->err, flag); }
+__device__ __forceinline__ void fail(Cx c, uint32_t flag) { atomicOr(&DYN(c)->err, flag); }
 
 /* ------------------------------------------------------------------------------------------------ */
-/* RNG: Philox4x32-10 keyed (seed, episode) with counter (draw index, actor, tick+1) or tape replay  */
+/* RNG.  Production: every (actor, tick) owns a stream of 32-bit words; word j is element j&3 of the    */
+/* Philox4x32-10 block with key (seed, episode) and counter (j>>2, actor, tick+1, episode).  An integer */
+/* draw consumes one word, a double two (53 bits).  Parity: replay of the reference's recorded draws.  */
 /* ------------------------------------------------------------------------------------------------ */
 __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
 {
@@ -136,33 +165,52 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
 }
-__device__ __noinline__ uint64_t tape_next(Ctx &c, int actor, int site, int kind, uint32_t n)
+__device__ __noinline__ uint64_t tape_next(Cx c, int actor, int site, int kind, uint32_t n)
 {
-    uint32_t seg = actor == NAG ? 0u : 1u + (uint32_t)c.tick * NAG + (uint32_t)actor;
-    if (seg >= c.n_segs) { fail(c, CC4_E_TAPE_END); return 0; }
-    uint32_t i = c.seg[seg] + c.x->ctr[actor];
-    if (i >= c.seg[seg + 1]) { fail(c, CC4_E_TAPE_END); return 0; }
-    cc4_draw d = c.tape[i];
+    uint32_t seg = actor == NAG ? 0u : 1u + (uint32_t)WC(c)->tick * NAG + (uint32_t)actor;
+    if (seg >= WC(c)->n_segs) { fail(c, CC4_E_TAPE_END); return 0; }
+    uint32_t i = WC(c)->seg[seg] + SCR(c)->ctr[actor];
+    if (i >= WC(c)->seg[seg + 1]) { fail(c, CC4_E_TAPE_END); return 0; }
+    cc4_draw d = WC(c)->tape[i];
     if (d.site != site || d.kind != kind || d.n != n) fail(c, CC4_E_TAPE_SITE);
-    c.x->ctr[actor]++;
+    SCR(c)->ctr[actor]++;
     return d.val;
 }
-__device__ __noinline__ void philox_draw(Ctx &c, int actor, uint32_t o[4])
+/* block `blk` of the actor's stream for this tick (registers only) */
+__device__ __noinline__ uint4 philox_block(Cx c, int actor, uint32_t blk)
 {
-    o[0] = c.x->ctr[actor]++; o[1] = (uint32_t)actor; o[2] = actor == NAG ? 0u : (uint32_t)c.tick + 1u; o[3] = c.ep_lo;
-    philox4x32_10(o, c.k0, c.k1);
+    const WarpCtx *g = WC(c);
+    uint32_t o[4] = { blk, (uint32_t)actor, actor == NAG ? 0u : (uint32_t)g->tick + 1u, g->ep_lo };
+    philox4x32_10(o, g->k0, g->k1);
+    return make_uint4(o[0], o[1], o[2], o[3]);
 }
-__device__ __noinline__ uint32_t rng_int(Ctx &c, int actor, int site, uint32_t n)
+__device__ __forceinline__ uint32_t u4_word(const uint4 &v, uint32_t i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+/* next word of the actor's stream.  Blue / red actors and the reset stream (serial callers) keep their current block in
+ * the scratch; green actors (lane-parallel in green_tick, which keeps its block in registers) recompute on the rare
+ * serial follow-ups (phishing). */
+__device__ __noinline__ uint32_t rng_word(Cx c, int actor)
 {
-    if (c.rng_mode == 1) { uint64_t v = tape_next(c, actor, site, 0, n); return v < n ? (uint32_t)v : 0u; }
-    uint32_t o[4]; philox_draw(c, actor, o);
-    return __umulhi(o[0], n);
+    Scratch *x = SCR(c);
+    uint32_t j = x->ctr[actor]++;
+    int slot = actor < A_GREEN0 ? actor : actor == NAG ? 11 : -1;
+    if (slot < 0) { uint4 v = philox_block(c, actor, j >> 2); return u4_word(v, j & 3u); }
+    if (x->blk_id[slot] != (j >> 2)) {
+        uint4 v = philox_block(c, actor, j >> 2);
+        x->blk_id[slot] = j >> 2; x->blk[slot][0] = v.x; x->blk[slot][1] = v.y; x->blk[slot][2] = v.z; x->blk[slot][3] = v.w;
+    }
+    return x->blk[slot][j & 3u];
 }
-__device__ __noinline__ double rng_f64(Ctx &c, int actor, int site, uint32_t n)
+__device__ __forceinline__ double f64_from_words(uint32_t hi, uint32_t lo) { return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) / 9007199254740992.0; }
+__device__ __noinline__ uint32_t rng_int(Cx c, int actor, int site, uint32_t n)
 {
-    if (c.rng_mode == 1) return __longlong_as_double((long long)tape_next(c, actor, site, 1, n));
-    uint32_t o[4]; philox_draw(c, actor, o);
-    return ((double)(o[0] >> 5) * 67108864.0 + (double)(o[1] >> 6)) / 9007199254740992.0;
+    if (WC(c)->rng_mode == 1) { uint64_t v = tape_next(c, actor, site, 0, n); return v < n ? (uint32_t)v : 0u; }
+    return __umulhi(rng_word(c, actor), n);
+}
+__device__ __noinline__ double rng_f64(Cx c, int actor, int site, uint32_t n)
+{
+    if (WC(c)->rng_mode == 1) return __longlong_as_double((long long)tape_next(c, actor, site, 1, n));
+    uint32_t hi = rng_word(c, actor), lo = rng_word(c, actor);
+    return f64_from_words(hi, lo);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -182,28 +230,28 @@ __device__ __forceinline__ bool bit128(const uint32_t *b, int i) { return (b[i >
 __device__ __forceinline__ void set128(uint32_t *b, int i) { b[i >> 5] |= 1u << (i & 31); }
 
 /* ---- process lists (lane 0; the slabs live in the cold record) ---- */
-__device__ __noinline__ void proc_append(Ctx &c, int h, uint32_t w)
+__device__ __noinline__ void proc_append(Cx c, int h, uint32_t w)
 {   /* host.processes.append */
-    int n = c.s->nproc[h];
+    int n = DYN(c)->nproc[h];
     if (n >= CC4_PSLAB) { fail(c, CC4_E_CAPACITY); return; }
-    c.k->procs[h][n] = w;
-    c.s->nproc[h] = (uint8_t)(n + 1);
+    WC(c)->k->procs[h][n] = w;
+    DYN(c)->nproc[h] = (uint8_t)(n + 1);
 }
-__device__ __noinline__ void proc_delete(Ctx &c, int h, int idx)
+__device__ __noinline__ void proc_delete(Cx c, int h, int idx)
 {
-    int n = c.s->nproc[h];
-    _Pragma("unroll 1") for (int i = idx; i + 1 < n; i++) c.k->procs[h][i] = c.k->procs[h][i + 1];
-    c.s->nproc[h] = (uint8_t)(n - 1);
+    int n = DYN(c)->nproc[h];
+    _Pragma("unroll 1") for (int i = idx; i + 1 < n; i++) WC(c)->k->procs[h][i] = WC(c)->k->procs[h][i + 1];
+    DYN(c)->nproc[h] = (uint8_t)(n - 1);
 }
-__device__ __noinline__ int proc_find(const Ctx &c, int h, uint32_t pid)
+__device__ __noinline__ int proc_find(Cx c, int h, uint32_t pid)
 {   /* Host.get_process Host.py:251 (tombstones are not processes) */
-    _Pragma("unroll 1") for (int i = 0; i < c.s->nproc[h]; i++) { uint32_t w = c.k->procs[h][i]; if (!P_DEAD(w) && P_PID(w) == pid) return i; }
+    _Pragma("unroll 1") for (int i = 0; i < DYN(c)->nproc[h]; i++) { uint32_t w = WC(c)->k->procs[h][i]; if (!P_DEAD(w) && P_PID(w) == pid) return i; }
     return -1;
 }
-__device__ __noinline__ int create_pid(Ctx &c, int actor, int h)
+__device__ __noinline__ int create_pid(Cx c, int actor, int h)
 {   /* Host.create_pid Host.py:198-200 */
     uint32_t mx = 0;
-    _Pragma("unroll 1") for (int i = 0; i < c.s->nproc[h]; i++) { uint32_t w = c.k->procs[h][i]; if (!P_DEAD(w) && P_PID(w) > mx) mx = P_PID(w); }
+    _Pragma("unroll 1") for (int i = 0; i < DYN(c)->nproc[h]; i++) { uint32_t w = WC(c)->k->procs[h][i]; if (!P_DEAD(w) && P_PID(w) > mx) mx = P_PID(w); }
     uint32_t pid = mx + 1 + rng_int(c, actor, ST_CREATE_PID, 9);
     if (pid > 0xFFFFu) { fail(c, CC4_E_CAPACITY); pid = 0xFFFFu; }
     return (int)pid;
@@ -221,24 +269,24 @@ __device__ __noinline__ int sess_find(const Cc4Dyn *s, int r, int id)
     return -1;
 }
 __device__ __noinline__ int sess_count_agent(const Cc4Dyn *s, int r) { int n = 0; for (int i = 0; i < s->n_sess; i++) n += SF_AGENT(s->sessf[i]) == (uint32_t)r; return n; }
-__device__ __noinline__ void ports_drop(Ctx &c, int r, int id)
+__device__ __noinline__ void ports_drop(Cx c, int r, int id)
 {
-    Cc4Dyn *s = c.s;
+    Cc4Dyn *s = DYN(c);
     int w = 0;
-    _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = c.k->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)id) continue; if (w != i) c.k->ports[w] = p; w++; }
+    _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = WC(c)->k->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)id) continue; if (w != i) WC(c)->k->ports[w] = p; w++; }
     s->n_ports = (uint16_t)w;
 }
-__device__ __noinline__ void sess_delete(Ctx &c, int idx)
+__device__ __noinline__ void sess_delete(Cx c, int idx)
 {
-    Cc4Dyn *s = c.s;
+    Cc4Dyn *s = DYN(c);
     if (SF_ABS(s->sessf[idx])) ports_drop(c, SF_AGENT(s->sessf[idx]), S_ID(s->sess[idx]));
     _Pragma("unroll 1") for (int i = idx; i + 1 < s->n_sess; i++) { s->sess[i] = s->sess[i + 1]; s->sessf[i] = s->sessf[i + 1]; }
     s->n_sess--;
 }
 /* State.add_session State.py:305-323 for a red agent; returns the ident */
-__device__ __noinline__ int sess_add(Ctx &c, int r, int host, int abstract, int root, int pid)
+__device__ __noinline__ int sess_add(Cx c, int r, int host, int abstract, int root, int pid)
 {
-    Cc4Dyn *s = c.s;
+    Cc4Dyn *s = DYN(c);
     if (s->n_sess >= CC4_SESS_CAP) { fail(c, CC4_E_CAPACITY); return 0; }
     int id = 0, any = 0;
     _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r) { any = 1; if ((int)S_ID(s->sess[i]) >= id) id = S_ID(s->sess[i]); }
@@ -266,9 +314,9 @@ __device__ __forceinline__ bool blocking(const Cc4Dyn *s, int src_slot, int othe
 }
 
 /* ---- observation bookkeeping for one red agent (ObservationSet / ActionSpace.update ActionSpace.py:170-212) ---- */
-__device__ __noinline__ void obs_entry(Ctx &c, int r, int key_ip, int slot, int iface, int subnet_if, int syshost, int sess)
+__device__ __noinline__ void obs_entry(Cx c, int r, int key_ip, int slot, int iface, int subnet_if, int syshost, int sess)
 {
-    Cc4Dyn *s = c.s; Scratch *x = c.x;
+    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     if (syshost) set128(s->hn_known[r], slot);
     if (iface) set128(s->ip_known[r], slot);
     if (subnet_if) s->sn_known[r] |= (uint16_t)(1u << slot_subnet(slot));
@@ -277,20 +325,20 @@ __device__ __noinline__ void obs_entry(Ctx &c, int r, int key_ip, int slot, int 
     if (x->n_oent[r] >= CC4_OENT_CAP) { fail(c, CC4_E_CAPACITY); return; }
     x->oent[r][x->n_oent[r]++] = key | fl;
 }
-__device__ __noinline__ void know_session(Ctx &c, int r, int id)
+__device__ __noinline__ void know_session(Cx c, int r, int id)
 {
-    Cc4Dyn *s = c.s;
+    Cc4Dyn *s = DYN(c);
     _Pragma("unroll 1") for (int i = 0; i < s->n_ss[r]; i++) if (s->ss[r][i] == id) return;
     if (s->n_ss[r] >= CC4_SS_CAP) { fail(c, CC4_E_CAPACITY); return; }
     s->ss[r][s->n_ss[r]++] = (uint8_t)id;
-    c.x->ssmask[r][id >> 5] |= 1u << (id & 31);
+    SCR(c)->ssmask[r][id >> 5] |= 1u << (id & 31);
 }
-__device__ __noinline__ void obs_push(Ctx &c, int r, int succ, bool has_act, const Act &a)
+__device__ __forceinline__ void obs_push(Cx c, int r, int succ, bool has_act, uint32_t aw)
 {
-    Scratch *x = c.x;
+    Scratch *x = SCR(c);
     if (x->have_first[r]) return;
     x->have_first[r] = 1; x->succ0[r] = (uint8_t)succ; x->has_act0[r] = has_act;
-    x->act0[r] = IP_MAKE(a.code, a.host < 0 ? 255 : a.host, a.subnet < 0 ? 15 : a.subnet, a.session, 0);
+    x->act0[r] = aw & 0x03FFFFFFu;
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -302,9 +350,9 @@ __device__ __noinline__ int fsm_find(const Cc4Dyn *s, int r, int slot) { for (in
  * (RedSessionCheck._all_red_sessions_observation RedSessionCheck.py:57-63: one hostname-keyed entry with Sessions,
  * Interface+Subnet and System info per session host) is represented by the host mask x->sess_hosts[r] instead of
  * explicit entries; ActionSpace.update (ActionSpace.py:170-212) and the FSM bookkeeping consume the mask. */
-__device__ __noinline__ void agent_end_turn(Ctx &c, int r)
+__device__ __noinline__ void agent_end_turn(Cx c, int r)
 {
-    Cc4Dyn *s = c.s; Scratch *x = c.x;
+    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     const uint32_t *rsc = x->sess_hosts[r];
     uint32_t snk = s->sn_known[r];
     _Pragma("unroll 1") for (int w = 0; w < 4; w++) {
@@ -339,7 +387,8 @@ __device__ __noinline__ void agent_end_turn(Ctx &c, int r)
     }
     /* _process_new_observations :190-250, explicit entries first (they precede the RedSessionCheck observation) */
     int started = (s->fsm_started >> r) & 1;
-    uint32_t seen[4] = { rsc[0], rsc[1], rsc[2], rsc[3] };
+    uint32_t *seen = x->et[r][0], *fa = x->et[r][1], *fh = x->et[r][2], *fu = x->et[r][3];   /* shared scratch: indexed dynamically */
+    _Pragma("unroll") for (int w = 0; w < 4; w++) { seen[w] = rsc[w]; fa[w] = 0; fh[w] = 0; fu[w] = 0; }
     _Pragma("unroll 1") for (int i = 0; i < x->n_oent[r]; i++) {
         uint16_t e = x->oent[r][i];
         int slot = e & 0xFF, key_ip = (e >> 8) & 1, syshost = (e >> 11) & 1;
@@ -357,7 +406,6 @@ __device__ __noinline__ void agent_end_turn(Ctx &c, int r)
         } else if (hn && !F_HN(s->fsm[r][idx])) s->fsm[r][idx] |= 1u << 7;
     }
     /* host masks of the FSM list: present / hostname known / state in {U, UD, R, RD} */
-    uint32_t fa[4] = { 0, 0, 0, 0 }, fh[4] = { 0, 0, 0, 0 }, fu[4] = { 0, 0, 0, 0 };
     _Pragma("unroll 1") for (int i = 0; i < s->n_fsm[r]; i++) {
         uint16_t f = s->fsm[r][i];
         uint32_t w = F_SLOT(f) >> 5, b = 1u << (F_SLOT(f) & 31);
@@ -388,29 +436,34 @@ __device__ __noinline__ void agent_end_turn(Ctx &c, int r)
         }
 }
 
-/* FiniteStateRedAgent._choose_host_and_action :296-336 + replace_action_if_invalid SimulationController.py:1068-1112 */
-__device__ __noinline__ Act red_policy(Ctx &c, int r)
+/* FiniteStateRedAgent._choose_host_and_action :296-336 + replace_action_if_invalid SimulationController.py:1068-1112.
+ * Returns the packed action (ticks = 0). */
+__device__ __noinline__ uint32_t red_policy(Cx c, int r)
 {
-    Cc4Dyn *s = c.s;
+    Cc4Dyn *s = DYN(c);
     int actor = A_RED0 + r;
-    Act a = { AC_SLEEP, -1, -1, 0 };
-    if (IP_CODE(s->inprog[actor]) != IP_NONE) return a;     /* last observation was IN_PROGRESS :100-102 */
+    if (IP_CODE(s->inprog[actor]) != IP_NONE) return ACT_SLEEP_WORD;     /* last observation was IN_PROGRESS :100-102 */
+    const int nf = s->n_fsm[r];
     int nk = 0;
-    _Pragma("unroll 1") for (int i = 0; i < s->n_fsm[r]; i++) nk += F_STATE(s->fsm[r][i]) != F_F;
-    if (nk == 0) { fail(c, CC4_E_UNREACHABLE); return a; }
+    _Pragma("unroll 1") for (int i = 0; i < nf; i++) nk += F_STATE(s->fsm[r][i]) != F_F;
+    if (nk == 0) { fail(c, CC4_E_UNREACHABLE); return ACT_SLEEP_WORD; }
     int pick = (int)rng_int(c, actor, ST_FSM_HOST, (uint32_t)nk);
-    uint16_t f = 0;
-    _Pragma("unroll 1") for (int i = 0, k = 0; i < s->n_fsm[r]; i++) if (F_STATE(s->fsm[r][i]) != F_F) { if (k == pick) { f = s->fsm[r][i]; break; } k++; }
+    uint32_t f = 0;
+    _Pragma("unroll 1") for (int i = 0, k = 0; i < nf; i++) { uint32_t e = s->fsm[r][i]; if (F_STATE(e) != F_F) { if (k == pick) { f = e; break; } k++; } }
     int st = F_STATE(f), slot = F_SLOT(f);
-    int cols[9], p4[9], nc = 0, tot = 0;
-    _Pragma("unroll 1") for (int i = 0; i < 9; i++) { int col = c_red_aspace_cols[i]; int p = c_fsm_prob4[st][col]; if (p >= 0) { cols[nc] = col; p4[nc] = p; tot += p; nc++; } }
+    /* options in action-space order (c_red_aspace_cols); numpy Generator.choice(p): idx = searchsorted(cumsum(p) / sum, u, side='right') */
+    int nc = 0, tot = 0;
+    _Pragma("unroll 1") for (int i = 0; i < 9; i++) { int p = c_fsm_prob4[st][c_red_aspace_cols[i]]; if (p >= 0) { tot += p; nc++; } }
     double u = rng_f64(c, actor, ST_FSM_ACTION, (uint32_t)nc);
-    int k = 0, cum = 0;
-    /* numpy Generator.choice(p): idx = searchsorted(cumsum(p) / sum, u, side='right') */
-    _Pragma("unroll 1") for (k = 0; k < nc; k++) { cum += p4[k]; if (!((double)cum / (double)tot <= u)) break; }
-    if (k >= nc) k = nc - 1;
-    int col = cols[k];
-    a.code = c_fsm_col_code[col];
+    int col = -1, cum = 0, last = -1;
+    _Pragma("unroll 1") for (int i = 0; i < 9 && col < 0; i++) {
+        int cc = c_red_aspace_cols[i], p = c_fsm_prob4[st][cc];
+        if (p < 0) continue;
+        last = cc; cum += p;
+        if (!((double)cum / (double)tot <= u)) col = cc;
+    }
+    if (col < 0) col = last;
+    Act a = { c_fsm_col_code[col], -1, -1, 0 };
     #define PICK_SESSION() do { if (s->n_ss[r] == 0) fail(c, CC4_E_UNREACHABLE); else a.session = s->ss[r][rng_int(c, actor, ST_FSM_PARAM, s->n_ss[r])]; } while (0)
     if (col == 0) {
         int no = __popc(s->sn_known[r]);
@@ -422,14 +475,15 @@ __device__ __noinline__ Act red_policy(Ctx &c, int r)
     #undef PICK_SESSION
     if (col >= 1 && col <= 4 && !bit128(s->ip_known[r], a.host)) a.code = AC_INVALID;
     if (col >= 5 && !bit128(s->hn_known[r], a.host)) a.code = AC_INVALID;
-    return a;
+    return pack_act(a, 0);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
 /* blue: index decoding (BlueFixedActionWrapper._populate_action_space :233-309) and actions         */
 /* ------------------------------------------------------------------------------------------------ */
 __device__ __forceinline__ int blue_sorted_subnet(int b, int i) { return b < 4 ? b : (i == 0 ? S_ADM : i == 1 ? S_OFF : S_PAZ); }
-__device__ __noinline__ Act blue_decode(const Cc4Dyn *s, int b, int idx, int *mask_out)
+/* index -> packed action (ticks = 0) | ACT_VALID when the index is a mask-True entry */
+__device__ __noinline__ uint32_t blue_decode(const Cc4Dyn *s, int b, int idx)
 {
     Act a = { AC_SLEEP, -1, -1, 0 };
     int n = b == 4 ? 3 : 1, H = 16 * n, T = 8 * n, m = 1, hostidx = -1, tidx = -1, code = AC_SLEEP;
@@ -453,31 +507,30 @@ __device__ __noinline__ Act blue_decode(const Cc4Dyn *s, int b, int idx, int *ma
         a.subnet = dst; a.host = src;
     }
     a.code = code;
-    if (mask_out) *mask_out = m;
-    return a;
+    return pack_act(a, 0) | (m ? ACT_VALID : 0u);
 }
 
-__device__ __noinline__ void ev_procpid(Ctx &c, int slot, int pid)
+__device__ __noinline__ void ev_procpid(Cx c, int slot, int pid)
 {
-    c.s->ev[slot] |= EV_PROC;
+    DYN(c)->ev[slot] |= EV_PROC;
     /* only hosts some blue agent monitors ever have their event pids read (Monitor.py:66-70) */
     if (pid >= 0 && blue_of_subnet(slot_subnet(slot)) >= 0) {
-        if (c.x->n_evpid < 16) c.x->evpid[c.x->n_evpid++] = (uint32_t)slot << 16 | (uint32_t)pid; else fail(c, CC4_E_CAPACITY);
+        if (SCR(c)->n_evpid < 16) SCR(c)->evpid[SCR(c)->n_evpid++] = (uint32_t)slot << 16 | (uint32_t)pid; else fail(c, CC4_E_CAPACITY);
     }
 }
 
 /* StopProcess.execute_targeteted_local_action + kill_process StopProcess.py:23-58 */
-__device__ __noinline__ void stop_process(Ctx &c, int actor, int h, uint32_t pid)
+__device__ __noinline__ void stop_process(Cx c, int actor, int h, uint32_t pid)
 {
-    Cc4Dyn *s = c.s;
+    Cc4Dyn *s = DYN(c);
     int pi = proc_find(c, h, pid);
     if (pi < 0) return;
-    uint32_t w = c.k->procs[h][pi];
+    uint32_t w = WC(c)->k->procs[h][pi];
     if (P_ROOT(w)) return;
     int si = session_from_pid(s, h, pid);
     /* a stopped OT service keeps Service.process; a pid collision with it takes the reference down a path that
        re-labels the killed process as the service's (StopProcess.py:37-42): not modelled */
-    _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) if (P_DEAD(c.k->procs[h][i]) && P_PID(c.k->procs[h][i]) == pid) fail(c, CC4_E_UNREACHABLE);
+    _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) if (P_DEAD(WC(c)->k->procs[h][i]) && P_PID(WC(c)->k->procs[h][i]) == pid) fail(c, CC4_E_UNREACHABLE);
     proc_delete(c, h, pi);
     if (P_SVC(w)) {
         int np = create_pid(c, actor, h);
@@ -491,24 +544,24 @@ __device__ __noinline__ void stop_process(Ctx &c, int actor, int h, uint32_t pid
 }
 
 /* RestoreFromBackup.py:9-19 + Host.restore Host.py:373-429 */
-__device__ __noinline__ void do_restore(Ctx &c, int h)
+__device__ __noinline__ void do_restore(Cx c, int h)
 {
-    Cc4Dyn *s = c.s; const Cc4Stat *st = c.st;
+    Cc4Dyn *s = DYN(c); const Cc4Stat *st = WC(c)->st;
     _Pragma("unroll 1") for (int i = 0; i < s->n_sess;) if (S_HOST(s->sess[i]) == (uint32_t)h) sess_delete(c, i); else i++;
     s->ev[h] = 0;
     int on = st->o_nproc[h];
-    _Pragma("unroll 1") for (int i = 0; i < on; i++) c.k->procs[h][i] = st->o_procs[h][i];
+    _Pragma("unroll 1") for (int i = 0; i < on; i++) WC(c)->k->procs[h][i] = st->o_procs[h][i];
     s->nproc[h] = (uint8_t)on;
     s->svc64[h] = st->o_svc64[h];
 }
 
 /* DecoyAction.execute DecoyAction.py:47-112 with DeployDecoy.CANDIDATE_DECOYS DeployDecoy.py:27 */
-__device__ __noinline__ void do_decoy(Ctx &c, int b, int h)
+__device__ __noinline__ void do_decoy(Cx c, int b, int h)
 {
-    Cc4Dyn *s = c.s;
+    Cc4Dyn *s = DYN(c);
     int actor = A_BLUE0 + b;
     int used = 0;
-    _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) { uint32_t w = c.k->procs[h][i]; if (P_DEAD(w)) continue; int pb = c_kind_portbit[P_KIND(w)]; if (pb >= 0) used |= 1 << pb; }
+    _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) { uint32_t w = WC(c)->k->procs[h][i]; if (P_DEAD(w)) continue; int pb = c_kind_portbit[P_KIND(w)]; if (pb >= 0) used |= 1 << pb; }
     int fac[4], nf = 0;
     if (!(used & PB_80)) fac[nf++] = K_D_APACHE;
     if (!(used & PB_443)) fac[nf++] = K_D_TOMCAT;
@@ -517,7 +570,7 @@ __device__ __noinline__ void do_decoy(Ctx &c, int b, int h)
     int kind = fac[rng_int(c, actor, ST_DECOY_FACTORY, (uint32_t)nf)];
     int pid = create_pid(c, actor, h);
     /* host.services[name] = Service(pid): an earlier process of the same decoy stops being the service's process */
-    _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) { uint32_t w = c.k->procs[h][i]; if (P_KIND(w) == (uint32_t)kind && P_SVC(w)) c.k->procs[h][i] = w & ~(1u << 21); }
+    _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) { uint32_t w = WC(c)->k->procs[h][i]; if (P_KIND(w) == (uint32_t)kind && P_SVC(w)) WC(c)->k->procs[h][i] = w & ~(1u << 21); }
     proc_append(c, h, P_MAKE(pid, kind, 0, 1));
     uint64_t v = s->svc64[h];
     int n = svc_count(v), at = -1;
@@ -526,13 +579,14 @@ __device__ __noinline__ void do_decoy(Ctx &c, int b, int h)
     s->svc64[h] = svc_set(v, at, (uint32_t)kind | 5u << 4);
 }
 
-__device__ __noinline__ void exec_blue(Ctx &c, int b, const Act &a)
+__device__ __noinline__ void exec_blue(Cx c, int b, uint32_t aw)
 {
-    Cc4Dyn *s = c.s;
+    Cc4Dyn *s = DYN(c);
+    const Act a = unpack_act(aw);
     switch (a.code) {
     case AC_REMOVE: {   /* Remove.py:42-69 */
         int n = s->n_sus;
-        _Pragma("unroll 1") for (int i = 0; i < n; i++) { uint32_t w = c.k->sus[i]; if (SU_AGENT(w) == (uint32_t)b && SU_SLOT(w) == (uint32_t)a.host) stop_process(c, A_BLUE0 + b, a.host, SU_PID(w)); }
+        _Pragma("unroll 1") for (int i = 0; i < n; i++) { uint32_t w = WC(c)->k->sus[i]; if (SU_AGENT(w) == (uint32_t)b && SU_SLOT(w) == (uint32_t)a.host) stop_process(c, A_BLUE0 + b, a.host, SU_PID(w)); }
         break;
     }
     case AC_RESTORE: do_restore(c, a.host); break;        /* Restore.py:38-68 */
@@ -547,10 +601,10 @@ __device__ __noinline__ void exec_blue(Ctx &c, int b, const Act &a)
 /* green                                                                                            */
 /* ------------------------------------------------------------------------------------------------ */
 /* PhishingEmail._create_new_session PhishingEmail.py:42-113 (lane 0, in green-agent order); x->hostagents is current */
-__device__ __noinline__ void do_phishing(Ctx &c, int g)
+__device__ __noinline__ void do_phishing(Cx c, int g)
 {
-    Cc4Dyn *s = c.s;
-    const uint8_t *ha = reinterpret_cast<const uint8_t *>(c.x->hostagents);
+    Cc4Dyn *s = DYN(c);
+    const uint8_t *ha = reinterpret_cast<const uint8_t *>(SCR(c)->hostagents);
     int actor = A_GREEN0 + g, gh = s->green_host[g], gsn = gh >> 4;
     if (ha[gh]) return;
     /* hosts in state.hosts order (per subnet: users, then servers), agents in order on each host */
@@ -558,7 +612,7 @@ __device__ __noinline__ void do_phishing(Ctx &c, int g)
     uint8_t cand[CC4_SESS_CAP];
     _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) {
         int nu = s->nuser[sn], nh = nu + s->nserver[sn];
-        if (!(c.x->hostagents[4 * sn] | c.x->hostagents[4 * sn + 1] | c.x->hostagents[4 * sn + 2] | c.x->hostagents[4 * sn + 3])) continue;
+        if (!(SCR(c)->hostagents[4 * sn] | SCR(c)->hostagents[4 * sn + 1] | SCR(c)->hostagents[4 * sn + 2] | SCR(c)->hostagents[4 * sn + 3])) continue;
         _Pragma("unroll 1") for (int k = 0; k < nh; k++) {
             int h = k < nu ? sn * 16 + 6 + k : sn * 16 + (k - nu);
             uint32_t agents = ha[h];
@@ -574,7 +628,7 @@ __device__ __noinline__ void do_phishing(Ctx &c, int g)
     int pid = create_pid(c, actor, gh);
     proc_append(c, gh, P_MAKE(pid, K_REDABS, 0, 0));
     sess_add(c, src, gh, 1, 0, pid);
-    reinterpret_cast<uint8_t *>(c.x->hostagents)[gh] |= (uint8_t)(1u << src);
+    reinterpret_cast<uint8_t *>(SCR(c)->hostagents)[gh] |= (uint8_t)(1u << src);
 }
 
 /* k-th server (creation order: subnets ascending, server_host_0..) among the allowed subnets; GreenAccessService.py:94-115 */
@@ -585,35 +639,49 @@ __device__ __forceinline__ int nth_allowed_server(const Cc4Dyn *s, uint32_t allo
 }
 
 /* one green agent's tick (EnterpriseGreenAgent.get_action :42-78, GreenLocalWork.py:60-125, GreenAccessService.py:137-217);
- * event bits are OR-ed atomically, the phishing side effect is deferred (flag) because it is order dependent */
-__device__ __noinline__ int green_tick(Ctx &c, int g, uint32_t *ev_words, bool *phish)
+ * event bits are OR-ed atomically, the phishing side effect is deferred (bit 8 of the result) because it is order
+ * dependent.  Result: bits 0-7 = reward penalty (LWF / ASF, BlueRewardMachine.py:35-65) as a positive number.
+ * The agent's Philox block stays in registers: 4 words cover Sleep / AccessService, LocalWork needs a second block. */
+#define GREEN_PHISH 0x100
+__device__ __noinline__ int green_tick(Cx c, int g, uint32_t *ev_words)
 {
-    Cc4Dyn *s = c.s;
-    int actor = A_GREEN0 + g, gh = s->green_host[g], gsn = gh >> 4;
-    uint32_t choice = rng_int(c, actor, ST_GREEN_ACT, 3);
-    *phish = false;
+    Cc4Dyn *s = DYN(c);
+    const int actor = A_GREEN0 + g, gh = s->green_host[g], gsn = gh >> 4;
+    const bool tape = WC(c)->rng_mode == 1;
+    uint4 blk = tape ? make_uint4(0, 0, 0, 0) : philox_block(c, actor, 0);
+    uint32_t j = 0;
+    auto word = [&]() -> uint32_t {
+        if (j == 4) blk = philox_block(c, actor, 1);
+        uint32_t w = u4_word(blk, j & 3u); j++; return w;
+    };
+    auto gi = [&](int site, uint32_t n) -> uint32_t { return tape ? rng_int(c, actor, site, n) : __umulhi(word(), n); };
+    auto gf = [&](int site) -> double { if (tape) return rng_f64(c, actor, site, 0); uint32_t hi = word(), lo = word(); return f64_from_words(hi, lo); };
+    int out = 0;
+    uint32_t choice = gi(ST_GREEN_ACT, 3);
     if (choice == 1) {
         uint64_t v = s->svc64[gh];
         int n = svc_count(v), na = 0;
         _Pragma("unroll 1") for (int i = 0; i < n; i++) na += svc_active(v, SVC_ENTRY(v, i));
-        if (na == 0) return c_reward[s->phase][gsn][0];
-        int pick = (int)rng_int(c, actor, ST_LW_SERVICE, (uint32_t)na), rel = 0;
-        _Pragma("unroll 1") for (int i = 0, k = 0; i < n; i++) { uint32_t e = SVC_ENTRY(v, i); if (!svc_active(v, e)) continue; if (k == pick) { rel = (int)(e >> 4) * 20; break; } k++; }
-        if ((int)rng_int(c, actor, ST_LW_RELIAB, 100) >= rel) return c_reward[s->phase][gsn][0];
-        if (rng_f64(c, actor, ST_LW_FP, 0) < 0.01) atomicOr(&ev_words[gh >> 2], EV_PROC << ((gh & 3) * 8));
-        if (rng_f64(c, actor, ST_LW_PHISH, 0) < 0.01) *phish = true;
-        return 0;
-    }
-    if (choice == 0) {
+        if (na == 0) out = -c_reward[s->phase][gsn][0];
+        else {
+            int pick = (int)gi(ST_LW_SERVICE, (uint32_t)na), rel = 0;
+            _Pragma("unroll 1") for (int i = 0, k = 0; i < n; i++) { uint32_t e = SVC_ENTRY(v, i); if (!svc_active(v, e)) continue; if (k == pick) { rel = (int)(e >> 4) * 20; break; } k++; }
+            if ((int)gi(ST_LW_RELIAB, 100) >= rel) out = -c_reward[s->phase][gsn][0];
+            else {
+                if (gf(ST_LW_FP) < 0.01) atomicOr(&ev_words[gh >> 2], EV_PROC << ((gh & 3) * 8));
+                if (gf(ST_LW_PHISH) < 0.01) out = GREEN_PHISH;
+            }
+        }
+    } else if (choice == 0) {
         uint32_t allowed = c_green_allowed[s->phase][gsn];
         int nd = 0;
         _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) if (allowed >> sn & 1) nd += s->nserver[sn];
-        int d = nth_allowed_server(s, allowed, (int)rng_int(c, actor, ST_AS_DEST, (uint32_t)nd)), dsn = d >> 4;
-        if ((s->blocks[gsn] >> dsn & 1) || (s->blocks[dsn] >> gsn & 1)) { atomicOr(&ev_words[d >> 2], EV_NET << ((d & 3) * 8)); return c_reward[s->phase][gsn][1]; }
-        if (rng_f64(c, actor, ST_AS_FP, 0) < 0.01) atomicOr(&ev_words[d >> 2], EV_NET << ((d & 3) * 8));
-        return 0;
+        int d = nth_allowed_server(s, allowed, (int)gi(ST_AS_DEST, (uint32_t)nd)), dsn = d >> 4;
+        if ((s->blocks[gsn] >> dsn & 1) || (s->blocks[dsn] >> gsn & 1)) { atomicOr(&ev_words[d >> 2], EV_NET << ((d & 3) * 8)); out = -c_reward[s->phase][gsn][1]; }
+        else if (gf(ST_AS_FP) < 0.01) atomicOr(&ev_words[d >> 2], EV_NET << ((d & 3) * 8));
     }
-    return 0;
+    if (!tape) SCR(c)->ctr[actor] = (uint16_t)j;
+    return out;
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -636,7 +704,7 @@ __device__ __noinline__ int route(int src, int dst, int *out)
 }
 
 /* ExploitAction._create_new_session ExploitAction.py:212-262 */
-__device__ __noinline__ int exploit_new_session(Ctx &c, int r, int target)
+__device__ __noinline__ int exploit_new_session(Cx c, int r, int target)
 {
     int pid = create_pid(c, A_RED0 + r, target);
     proc_append(c, target, P_MAKE(pid, K_SHELL, 0, 0));
@@ -644,9 +712,10 @@ __device__ __noinline__ int exploit_new_session(Ctx &c, int r, int target)
     return pid;
 }
 
-__device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
+__device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
 {
-    Cc4Dyn *s = c.s;
+    Cc4Dyn *s = DYN(c);
+    const Act a = unpack_act(aw);
     int actor = A_RED0 + r;
     int si = (a.code == AC_SLEEP || a.code == AC_INVALID) ? -1 : sess_find(s, r, a.session);
     int S_host = si >= 0 ? (int)S_HOST(s->sess[si]) : -1, S_abs = si >= 0 ? (int)SF_ABS(s->sessf[si]) : 0;
@@ -667,7 +736,7 @@ __device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
         double u = rng_f64(c, actor, ST_PORTSCAN, 0);
         int mask = 0, any = 0, h = a.host;
         _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) {
-            uint32_t w = c.k->procs[h][i];
+            uint32_t w = WC(c)->k->procs[h][i];
             if (P_DEAD(w)) continue;
             int pb = c_kind_portbit[P_KIND(w)];
             if (pb < 0) continue;
@@ -676,9 +745,9 @@ __device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
         }
         if (any) {
             int at = -1;
-            _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = c.k->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)a.session && PT_HOST(p) == (uint32_t)h) { at = i; break; } }
+            _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = WC(c)->k->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)a.session && PT_HOST(p) == (uint32_t)h) { at = i; break; } }
             if (at < 0) { if (s->n_ports >= CC4_PORT_CAP) { fail(c, CC4_E_CAPACITY); at = 0; } else at = s->n_ports++; }
-            c.k->ports[at] = PT_MAKE(mask, h, a.session, r);
+            WC(c)->k->ports[at] = PT_MAKE(mask, h, a.session, r);
             obs_entry(c, r, 1, h, 1, 0, 0, 0);
         }
         return SUCC_TRUE;
@@ -687,7 +756,7 @@ __device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
         if (si < 0) return SUCC_FALSE;
         int rep = 0, h = a.host;
         _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) {
-            uint32_t w = c.k->procs[h][i];
+            uint32_t w = WC(c)->k->procs[h][i];
             if (P_DEAD(w)) continue;
             bool decoy = P_KIND(w) >= K_D_APACHE && P_KIND(w) <= K_D_VSFTPD;
             if (rng_f64(c, actor, ST_DD_TP, 0) <= 0.5 && decoy) rep = 1;
@@ -699,7 +768,7 @@ __device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
     case AC_EXPLOIT: { /* ExploitRemoteService.py:149-202 */
         if (si < 0 || !S_abs) return SUCC_FALSE;
         int ports = -1, target = a.host, src = S_host;
-        _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = c.k->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)a.session && PT_HOST(p) == (uint32_t)target) { ports = PT_MASK(p); break; } }
+        _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = WC(c)->k->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)a.session && PT_HOST(p) == (uint32_t)target) { ports = PT_MASK(p); break; } }
         if (ports < 0) return SUCC_FALSE;
         if (blocking(s, src, target)) return SUCC_FALSE;
         enum { X_HTTP, X_HTTPS, X_SSH, X_SQL, X_HARAKA };
@@ -723,7 +792,7 @@ __device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
             int hops[12], nh = route(src, target, hops);
             _Pragma("unroll 1") for (int i = 0; i < nh; i++) if (0.05 < rng_f64(c, actor, ST_SSH_HOP, 0)) s->ev[hops[i]] |= EV_NET;
             int vp = -1;
-            _Pragma("unroll 1") for (int i = 0; i < s->nproc[target]; i++) { uint32_t w = c.k->procs[target][i]; if (!P_DEAD(w) && P_KIND(w) == K_SSHD) { vp = i; break; } }
+            _Pragma("unroll 1") for (int i = 0; i < s->nproc[target]; i++) { uint32_t w = WC(c)->k->procs[target][i]; if (!P_DEAD(w) && P_KIND(w) == K_SSHD) { vp = i; break; } }
             if (vp < 0) return SUCC_FALSE;
             s->ev[target] |= EV_NET;
             int pid = exploit_new_session(c, r, target);
@@ -735,7 +804,7 @@ __device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
         /* ExploitAction.sim_exploit ExploitAction.py:48-116 */
         int vk = -1;
         _Pragma("unroll 1") for (int i = 0; i < s->nproc[target] && vk < 0; i++) {
-            uint32_t w = c.k->procs[target][i];
+            uint32_t w = WC(c)->k->procs[target][i];
             if (P_DEAD(w)) continue;
             int k = P_KIND(w);
             if (sel == X_HTTP && (k == K_APACHE2 || k == K_D_APACHE || k == K_D_VSFTPD)) vk = k;
@@ -766,7 +835,7 @@ __device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
             if (si < 0 || !S_abs) return SUCC_FALSE;
             s->sessf[tgt] |= 1u << 4;      /* EscalateAction.__upgrade_session EscalateAction.py:54-87 */
             int pi = proc_find(c, h, S_PID(s->sess[tgt]));
-            if (pi >= 0) c.k->procs[h][pi] |= P_ROOTBIT; else fail(c, CC4_E_UNREACHABLE);
+            if (pi >= 0) WC(c)->k->procs[h][pi] |= P_ROOTBIT; else fail(c, CC4_E_UNREACHABLE);
         }
         obs_entry(c, r, 0, h, 0, 0, 0, 1);
         if (SF_ABS(s->sessf[tgt])) know_session(c, r, S_ID(s->sess[tgt]));
@@ -789,10 +858,10 @@ __device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
             if (si < 0) return SUCC_FALSE;     /* StopService is a TargetedLocalAction: TargetedLocalAction.py:14-21 */
             s->svc64[h] = v | SVC_OT_STOPPED;  /* Host.stop_service Host.py:296-301 */
             _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) {   /* State.remove_process State.py:390-418 */
-                uint32_t w = c.k->procs[h][i];
+                uint32_t w = WC(c)->k->procs[h][i];
                 if (!P_DEAD(w) && P_KIND(w) == K_OT && P_SVC(w)) {
                     int s2 = session_from_pid(s, h, P_PID(w));
-                    c.k->procs[h][i] = w | P_DEADBIT;
+                    WC(c)->k->procs[h][i] = w | P_DEADBIT;
                     if (s2 >= 0) sess_delete(c, s2);
                     break;
                 }
@@ -812,23 +881,23 @@ __device__ __noinline__ int exec_red(Ctx &c, int r, const Act &a)
 }
 
 /* RedSessionCheck._choose_new_primary_session RedSessionCheck.py:34-55 (lane 0; agent r holds n sessions, none with ident 0) */
-__device__ __noinline__ void rsc_reelect(Ctx &c, int r, int n)
+__device__ __noinline__ void rsc_reelect(Cx c, int r, int n)
 {
-    Cc4Dyn *s = c.s;
+    Cc4Dyn *s = DYN(c);
     int pk = (int)rng_int(c, A_RED0 + r, ST_RSC_PRIMARY, (uint32_t)n), at = -1;
     _Pragma("unroll 1") for (int i = 0, k = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r) { if (k == pk) { at = i; break; } k++; }
     if (at < 0) { fail(c, CC4_E_UNREACHABLE); return; }
     uint32_t w = s->sess[at]; uint8_t f = s->sessf[at];
     int old_id = S_ID(w);
-    _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = c.k->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)old_id) c.k->ports[i] = PT_MAKE(PT_MASK(p), PT_HOST(p), 0, r); }
+    _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = WC(c)->k->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)old_id) WC(c)->k->ports[i] = PT_MAKE(PT_MASK(p), PT_HOST(p), 0, r); }
     _Pragma("unroll 1") for (int i = at; i + 1 < s->n_sess; i++) { s->sess[i] = s->sess[i + 1]; s->sessf[i] = s->sessf[i + 1]; }
     s->sess[s->n_sess - 1] = S_MAKE(S_PID(w), 0, S_HOST(w)); s->sessf[s->n_sess - 1] = f;
 }
 
 /* SimulationController.different_subnet_agent_reassignment :820-903 */
-__device__ __noinline__ void reassign(Ctx &c)
+__device__ __noinline__ void reassign(Cx c)
 {
-    Cc4Dyn *s = c.s; Scratch *x = c.x;
+    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     uint8_t list[32]; int n = 0;   /* (agent, ident) pairs, agents ascending then dict order */
     uint8_t lid[32];
     _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++)
@@ -848,8 +917,7 @@ __device__ __noinline__ void reassign(Ctx &c)
             uint16_t e = x->oent[r][i];
             if (((e >> 8) & 1) && (e & 0xFF) == host) {
                 if (!((e >> 12) & 1)) { fail(c, CC4_E_UNREACHABLE); break; }
-                Act none = { AC_SLEEP, -1, -1, 0 };
-                obs_push(c, nr, SUCC_UNKNOWN, false, none);
+                obs_push(c, nr, SUCC_UNKNOWN, false, ACT_SLEEP_WORD);
                 obs_entry(c, nr, 1, host, (e >> 9) & 1, (e >> 10) & 1, (e >> 11) & 1, 1);
                 know_session(c, nr, nid);
                 break;

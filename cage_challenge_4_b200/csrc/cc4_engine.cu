@@ -17,13 +17,14 @@
 
 namespace cc4 {
 
-constexpr int WARPS_PER_BLOCK = 8;
+#ifndef CC4_WARPS_PER_BLOCK
+#define CC4_WARPS_PER_BLOCK 8
+#endif
+#ifndef CC4_SYNC_MASK
+#define CC4_SYNC_MASK 0x7F      /* bit i: block barrier i of the tick is enabled (tuning knob, see PHASE_SYNC) */
+#endif
+constexpr int WARPS_PER_BLOCK = CC4_WARPS_PER_BLOCK;
 constexpr int DYN_U4 = (int)(sizeof(Cc4Dyn) / 16);
-
-struct WarpSmem {
-    Cc4Dyn dyn;
-    Scratch x;
-};
 
 struct Params {
     Cc4Dyn *dyn; Cc4Stat *stat; Cc4Cold *cold;
@@ -50,14 +51,20 @@ __device__ __forceinline__ void w_store(Cc4Dyn *dst, const Cc4Dyn *src)
     for (int i = lane_id(); i < DYN_U4; i += 32) g[i] = d[i];
 }
 
-__device__ __forceinline__ void make_ctx(Ctx &c, WarpSmem *w, const Params &p, int env)
+__device__ __forceinline__ Cx make_ctx(int warp, const Params &p, int env, int tick)
 {
-    uint64_t ep = p.first_episode + (uint64_t)env;
-    c.s = &w->dyn; c.x = &w->x; c.st = p.stat + env; c.k = p.cold + env;
-    c.steps = p.steps; c.rng_mode = p.rng_mode;
-    c.k0 = p.k0; c.k1 = p.k1hi ^ (uint32_t)(ep >> 32); c.ep_lo = (uint32_t)ep;
-    c.tape = p.tape; c.seg = p.seg_off ? p.seg_off + (size_t)env * (p.n_segs + 1) : nullptr; c.n_segs = p.n_segs;
-    c.tick = 0;
+    Cx c = (Cx)(warp * (int)sizeof(WarpSmem));
+    if (lane_id() == 0) {
+        uint64_t ep = p.first_episode + (uint64_t)env;
+        WarpCtx *g = WC(c);
+        g->st = p.stat + env; g->k = p.cold + env;
+        g->steps = p.steps; g->rng_mode = p.rng_mode;
+        g->k0 = p.k0; g->k1 = p.k1hi ^ (uint32_t)(ep >> 32); g->ep_lo = (uint32_t)ep;
+        g->tape = p.tape; g->seg = p.seg_off ? p.seg_off + (size_t)env * (p.n_segs + 1) : nullptr; g->n_segs = p.n_segs;
+        g->tick = tick;
+    }
+    __syncwarp();
+    return c;
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -141,18 +148,17 @@ __device__ void w_write_obs(const Cc4Dyn *s, uint32_t *bits /* scratch [5][8] */
 __device__ void w_write_mask(const Cc4Dyn *s, uint8_t *mask)
 {
     _Pragma("unroll 1") for (int i = lane_id(); i < CC4_N_BLUE * CC4_MASK_LEN; i += 32) {
-        int b = i / CC4_MASK_LEN, k = i % CC4_MASK_LEN, m = 0;
-        if (k < (b == 4 ? 242 : 82)) blue_decode(s, b, k, &m);
-        mask[i] = (uint8_t)m;
+        int b = i / CC4_MASK_LEN, k = i % CC4_MASK_LEN;
+        mask[i] = (uint8_t)(k < (b == 4 ? 242 : 82) ? blue_decode(s, b, k) >> 31 : 0u);
     }
 }
 
 /* ------------------------------------------------------------------------------------------------ */
 /* end-turn Monitor for all five blue agents (Monitor.py:35-74), lane per host                      */
 /* ------------------------------------------------------------------------------------------------ */
-__device__ void w_monitor_all(Ctx &c)
+__device__ void w_monitor_all(Cx c)
 {
-    Cc4Dyn *s = c.s;
+    Cc4Dyn *s = DYN(c);
     _Pragma("unroll 1") for (int h = lane_id(); h < CC4_NSLOT; h += 32) {
         if (blue_of_subnet(slot_subnet(h)) < 0) continue;     /* contractor network and internet have no blue agent */
         uint32_t e = s->ev[h];
@@ -160,27 +166,27 @@ __device__ void w_monitor_all(Ctx &c)
     }
     __syncwarp();
     if (lane_id() == 0) {
-        Scratch *x = c.x;
+        Scratch *x = SCR(c);
         _Pragma("unroll 1") for (int i = 0; i < x->n_evpid; i++) {
             int slot = x->evpid[i] >> 16, b = blue_of_subnet(slot_subnet(slot));
             if (s->n_sus >= CC4_SUS_CAP) { fail(c, CC4_E_CAPACITY); break; }
-            c.k->sus[s->n_sus++] = SU_MAKE(x->evpid[i] & 0xFFFFu, slot, b);
+            WC(c)->k->sus[s->n_sus++] = SU_MAKE(x->evpid[i] & 0xFFFFu, slot, b);
         }
         x->n_evpid = 0;
     }
     __syncwarp();
 }
 /* a blue agent's own Monitor action (same code path, one agent) */
-__device__ void monitor_one(Ctx &c, int b)
+__device__ void monitor_one(Cx c, int b)
 {
-    Cc4Dyn *s = c.s; Scratch *x = c.x;
+    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     _Pragma("unroll 1") for (int h = 0; h < CC4_NSLOT; h++) if (blue_of_subnet(slot_subnet(h)) == b) { uint32_t e = s->ev[h]; s->ev[h] = (uint8_t)((e & (EV_PROC | EV_NET)) << 2); }
     int w = 0;
     _Pragma("unroll 1") for (int i = 0; i < x->n_evpid; i++) {
         int slot = x->evpid[i] >> 16;
         if (blue_of_subnet(slot_subnet(slot)) != b) { x->evpid[w++] = x->evpid[i]; continue; }
         if (s->n_sus >= CC4_SUS_CAP) { fail(c, CC4_E_CAPACITY); continue; }
-        c.k->sus[s->n_sus++] = SU_MAKE(x->evpid[i] & 0xFFFFu, slot, b);
+        WC(c)->k->sus[s->n_sus++] = SU_MAKE(x->evpid[i] & 0xFFFFu, slot, b);
     }
     x->n_evpid = w;
 }
@@ -188,9 +194,9 @@ __device__ void monitor_one(Ctx &c, int b)
 /* ------------------------------------------------------------------------------------------------ */
 /* session-pool digests (lane per session)                                                          */
 /* ------------------------------------------------------------------------------------------------ */
-__device__ void w_scan_sessions(Ctx &c)
+__device__ void w_scan_sessions(Cx c)
 {
-    Cc4Dyn *s = c.s; Scratch *x = c.x;
+    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     const int lane = lane_id();
     if (lane < 24) (&x->sess_hosts[0][0])[lane] = 0;
     if (lane < 8) x->n_red[lane] = 0;
@@ -207,9 +213,9 @@ __device__ void w_scan_sessions(Ctx &c)
     }
     __syncwarp();
 }
-__device__ void w_build_hostagents(Ctx &c)
+__device__ void w_build_hostagents(Cx c)
 {
-    Cc4Dyn *s = c.s; Scratch *x = c.x;
+    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     x->hostagents[lane_id()] = 0;
     __syncwarp();
     _Pragma("unroll 1") for (int i = lane_id(); i < s->n_sess; i += 32) {
@@ -222,25 +228,19 @@ __device__ void w_build_hostagents(Ctx &c)
 /* ------------------------------------------------------------------------------------------------ */
 /* one tick: SimulationController.step SimulationController.py:211-315                              */
 /* ------------------------------------------------------------------------------------------------ */
-__device__ __forceinline__ Act unpack_act(uint32_t w)
-{
-    Act a = { (int)IP_CODE(w), IP_HOST(w) == 255 ? -1 : (int)IP_HOST(w), IP_SUBNET(w) == 15 ? -1 : (int)IP_SUBNET(w), (int)IP_SESSION(w) };
-    return a;
-}
-__device__ __forceinline__ uint32_t pack_act(const Act &a, int ticks) { return IP_MAKE(a.code, a.host < 0 ? 255 : a.host, a.subnet < 0 ? 15 : a.subnet, a.session, ticks); }
-
 /* PHASE_SYNC keeps the warps of a block in the same phase of the tick: they then share the instruction cache lines of
  * that phase instead of thrashing it (ncu: stall_no_inst was the top stall reason without it). */
-#define PHASE_SYNC() __syncthreads()
-#define N_PHASE_SYNC 7
-__device__ void w_tick(Ctx &c, const int32_t *actions /* [5] or null = all Sleep */, const uint8_t *msgs /* [5] or null */, float *reward_out, uint8_t *done_out)
+#define PHASE_SYNC(i) do { if ((CC4_SYNC_MASK >> (i)) & 1) __syncthreads(); } while (0)
+constexpr int N_PHASE_SYNC = __builtin_popcount(CC4_SYNC_MASK & 0x7F);
+__device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep */, const uint8_t *msgs /* [5] or null */, float *reward_out, uint8_t *done_out)
 {
-    Cc4Dyn *s = c.s; Scratch *x = c.x;
+    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     const int lane = lane_id();
-    c.tick = s->step;
+    WC(c)->tick = s->step;
     _Pragma("unroll 1") for (int i = lane; i <= NAG; i += 32) x->ctr[i] = 0;
     if (lane < 8) { x->n_oent[lane] = 0; x->have_first[lane] = 0; x->succ0[lane] = SUCC_UNKNOWN; x->has_act0[lane] = 0; }
     (&x->ssmask[0][0])[lane] = 0;
+    if (lane < 12) x->blk_id[lane] = 0xFFFFFFFFu;
     if (lane < 16) (&x->ssmask[0][0])[32 + lane] = 0;
     __syncwarp();
     _Pragma("unroll 1") for (int i = lane; i < CC4_NRED * CC4_SS_CAP; i += 32) {
@@ -250,36 +250,35 @@ __device__ void w_tick(Ctx &c, const int32_t *actions /* [5] or null = all Sleep
     if (lane == 0) {
         x->n_evpid = 0; x->reward = 0;
         /* mission phase: State.check_next_phase_on_update_step State.py:514-544, phases EnterpriseScenarioGenerator.py:854-860 */
-        int q = c.steps / 3, rem = c.steps % 3, l0 = q + (rem >= 1), l1 = q + (rem == 2);
-        int np = c.tick < l0 ? 0 : c.tick < l0 + l1 ? 1 : 2;
-        if (c.tick >= c.steps) fail(c, CC4_E_UNREACHABLE);
+        int q = WC(c)->steps / 3, rem = WC(c)->steps % 3, l0 = q + (rem >= 1), l1 = q + (rem == 2);
+        int np = WC(c)->tick < l0 ? 0 : WC(c)->tick < l0 + l1 ? 1 : 2;
+        if (WC(c)->tick >= WC(c)->steps) fail(c, CC4_E_UNREACHABLE);
         if (np > s->phase) s->phase = (uint8_t)np;
     }
     __syncwarp();
-    PHASE_SYNC();
+    PHASE_SYNC(0);
 
     /* ---- 1. policies (:236-248) and 2. duration queue (:245-265): one lane per blue / red actor.  The scripted red
        agents only read their own knowledge and draw from their own stream, so the six run side by side. ---- */
     int cost = 0;
     if (lane < 11) {
-        Act a = { AC_SLEEP, -1, -1, 0 };
-        if (lane < A_RED0) { a = blue_decode(s, lane, actions ? actions[lane] : (lane == 4 ? 145 : 49), nullptr); if (a.code == AC_RESTORE) cost = -1; }   /* Restore.py:70, :310-311 */
-        else if (s->red_active >> (lane - A_RED0) & 1) a = red_policy(c, lane - A_RED0);
+        uint32_t aw = ACT_SLEEP_WORD;
+        if (lane < A_RED0) { aw = blue_decode(s, lane, actions ? actions[lane] : (lane == 4 ? 145 : 49)) & ~ACT_VALID; if (IP_CODE(aw) == AC_RESTORE) cost = -1; }   /* Restore.py:70, :310-311 */
+        else if (s->red_active >> (lane - A_RED0) & 1) aw = red_policy(c, lane - A_RED0);
         uint32_t ip = s->inprog[lane];
-        if (IP_CODE(ip) == IP_NONE) ip = pack_act(a, c_duration[a.code]);
+        if (IP_CODE(ip) == IP_NONE) ip = aw | (uint32_t)c_duration[IP_CODE(aw)] << 26;
         int ticks = (int)IP_TICKS(ip) - 1;
         if (ticks < 1) { x->subw[lane] = ip & ~(0xFu << 26); s->inprog[lane] = IP_NONE; }
         else {
             s->inprog[lane] = (ip & ~(0xFu << 26)) | (uint32_t)ticks << 26;
-            Act none = { AC_SLEEP, -1, -1, 0 };
-            x->subw[lane] = pack_act(none, 0);
-            if (lane >= A_RED0) obs_push(c, lane - A_RED0, SUCC_INPROG, false, none);
+            x->subw[lane] = ACT_SLEEP_WORD;
+            if (lane >= A_RED0) obs_push(c, lane - A_RED0, SUCC_INPROG, false, ACT_SLEEP_WORD);
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o);
     __syncwarp();
-    PHASE_SYNC();
+    PHASE_SYNC(1);
     /* filter_actions (:466-486) looks at the sessions as they are BEFORE anything executes; blue / green sessions never go away */
     _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
         uint32_t w = x->subw[A_RED0 + r];
@@ -299,14 +298,14 @@ __device__ void w_tick(Ctx &c, const int32_t *actions /* [5] or null = all Sleep
     if (lane == 0) {
         _Pragma("unroll 1") for (int pass = 0; pass < 2; pass++)
             _Pragma("unroll 1") for (int b = 0; b < CC4_NBLUE; b++) {
-                Act a = unpack_act(x->subw[b]);
-                bool prio1 = a.code == AC_BLOCK || a.code == AC_ALLOW;
-                if ((pass == 0) != prio1 || a.code == AC_SLEEP) continue;
-                if (a.code == AC_MONITOR) monitor_one(c, b); else exec_blue(c, b, a);
+                uint32_t aw = x->subw[b], code = IP_CODE(aw);
+                bool prio1 = code == AC_BLOCK || code == AC_ALLOW;
+                if ((pass == 0) != prio1 || code == AC_SLEEP) continue;
+                if (code == AC_MONITOR) monitor_one(c, b); else exec_blue(c, b, aw);
             }
     }
     __syncwarp();
-    PHASE_SYNC();
+    PHASE_SYNC(2);
     /* green agents, lane per agent (EnterpriseGreenAgent.py:42-78); the phishing side effect is order dependent and
        replayed below in agent order */
     {
@@ -316,9 +315,9 @@ __device__ void w_tick(Ctx &c, const int32_t *actions /* [5] or null = all Sleep
         uint32_t any_phish = 0;
         _Pragma("unroll 1") for (int k = 0; k < 3; k++) {
             int g = k * 32 + lane;
-            bool ph = false;
-            if (g < ng) rew += green_tick(c, g, ev_words, &ph);
-            uint32_t bal = __ballot_sync(0xFFFFFFFFu, ph);
+            int gr = g < ng ? green_tick(c, g, ev_words) : 0;
+            rew -= gr & 0xFF;
+            uint32_t bal = __ballot_sync(0xFFFFFFFFu, (gr & GREEN_PHISH) != 0);
             if (lane == 0) x->phish[k] = bal;
             any_phish |= bal;
         }
@@ -333,18 +332,18 @@ __device__ void w_tick(Ctx &c, const int32_t *actions /* [5] or null = all Sleep
             __syncwarp();
         }
     }
-    PHASE_SYNC();
+    PHASE_SYNC(3);
     if (lane == 0) {
         _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
             int a = A_RED0 + r;
             if (x->dropped[a]) continue;
-            Act act = unpack_act(x->subw[a]);
-            int succ = exec_red(c, r, act);
-            obs_push(c, r, succ, true, act);
+            uint32_t aw = x->subw[a];
+            int succ = exec_red(c, r, aw);
+            obs_push(c, r, succ, true, aw);
         }
     }
     __syncwarp();
-    PHASE_SYNC();
+    PHASE_SYNC(4);
     /* ---- 4. reassignment (:278) ---- */
     w_scan_sessions(c);
     if (x->misplaced) {
@@ -354,7 +353,7 @@ __device__ void w_tick(Ctx &c, const int32_t *actions /* [5] or null = all Sleep
     }
     uint32_t active = 0;
     _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) active |= (x->n_red[r] > 0) << r;    /* :896-903: active iff it holds a session */
-    PHASE_SYNC();
+    PHASE_SYNC(5);
     /* ---- 5. end-turn actions (:281-286): Monitor for blue, RedSessionCheck for active red ---- */
     w_monitor_all(c);
     if (lane == 0) {
@@ -365,18 +364,17 @@ __device__ void w_tick(Ctx &c, const int32_t *actions /* [5] or null = all Sleep
     }
     __syncwarp();
     if (lane < CC4_NRED && (active >> lane & 1)) {
-        Act rsc = { AC_RSC, -1, -1, 0 };
-        obs_push(c, lane, SUCC_TRUE, true, rsc);
+        obs_push(c, lane, SUCC_TRUE, true, IP_MAKE(AC_RSC, 255, 15, 0, 0));
         /* the FSM agents digest the tick's observation now instead of at the start of the next tick */
         agent_end_turn(c, lane);
     }
     __syncwarp();
-    PHASE_SYNC();
+    PHASE_SYNC(6);
     if (lane == 0) {
         s->fsm_started |= (uint8_t)active;
         /* ---- 6. counters, done (:297-300), reward (BlueRewardMachine.py:70-121) ---- */
         s->step++;
-        s->done = s->step >= c.steps - 1;
+        s->done = s->step >= WC(c)->steps - 1;
         int rew = x->reward;
         _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
             /* `success and isinstance(action, Impact)` BlueRewardMachine.py:118: a TernaryEnum member is always truthy
@@ -387,10 +385,10 @@ __device__ void w_tick(Ctx &c, const int32_t *actions /* [5] or null = all Sleep
         _Pragma("unroll 1") for (int b = 0; b < CC4_NBLUE; b++) s->msgs[b] = msgs ? msgs[b] : 0;
         if (reward_out) *reward_out = (float)(rew + cost);
         if (done_out) *done_out = s->done;
-        if (c.rng_mode == 1) {
+        if (WC(c)->rng_mode == 1) {
             _Pragma("unroll 1") for (int a = 0; a < NAG; a++) {
-                uint32_t seg = 1u + (uint32_t)c.tick * NAG + (uint32_t)a;
-                if (seg < c.n_segs && x->ctr[a] != c.seg[seg + 1] - c.seg[seg]) fail(c, CC4_E_TAPE_LEFT);
+                uint32_t seg = 1u + (uint32_t)WC(c)->tick * NAG + (uint32_t)a;
+                if (seg < WC(c)->n_segs && x->ctr[a] != WC(c)->seg[seg + 1] - WC(c)->seg[seg]) fail(c, CC4_E_TAPE_LEFT);
             }
         }
     }
@@ -401,17 +399,16 @@ __device__ void w_tick(Ctx &c, const int32_t *actions /* [5] or null = all Sleep
 /* kernels                                                                                          */
 /* ------------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_step(Params p, const int32_t *actions, const uint8_t *msgs, uint8_t *obs, float *reward, uint8_t *done, int flags)
+k_step(Params p, int env0, const int32_t *actions, const uint8_t *msgs, uint8_t *obs, float *reward, uint8_t *done, int flags)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpSmem *w = reinterpret_cast<WarpSmem *>(smem_raw) + (threadIdx.x >> 5);
-    int env = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int env = env0 + blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);   /* env0: first episode of this launch (chunked host path) */
     const bool valid = env < p.n_envs;     /* padding episodes (n_envs..n_alloc) run with Sleep inputs and write no outputs */
-    Ctx c; make_ctx(c, w, p, env);
+    Cx c = make_ctx(threadIdx.x >> 5, p, env, 0);
+    WarpSmem *w = WS(c);
     w_load(&w->dyn, p.dyn + env);
     w_tick(c, valid ? actions + (size_t)env * 5 : nullptr, valid && msgs ? msgs + (size_t)env * 5 : nullptr,
            valid && (flags & CC4_STEP_REWARD) && reward ? reward + env : nullptr, valid && done ? done + env : nullptr);
-    PHASE_SYNC();
+    PHASE_SYNC(7);
     if (valid && (flags & CC4_STEP_OBS) && obs) w_write_obs(&w->dyn, w->x.obsbits, obs + (size_t)env * CC4_N_BLUE * CC4_OBS_LEN);
     w_store(p.dyn + env, &w->dyn);
 }
@@ -421,11 +418,10 @@ k_step(Params p, const int32_t *actions, const uint8_t *msgs, uint8_t *obs, floa
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_rollout(Params p, int n_ticks, uint32_t pk0, uint32_t pk1, float *reward_sum, int flags)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpSmem *w = reinterpret_cast<WarpSmem *>(smem_raw) + (threadIdx.x >> 5);
     int env = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const bool valid = env < p.n_envs;
-    Ctx c; make_ctx(c, w, p, env);
+    Cx c = make_ctx(threadIdx.x >> 5, p, env, 0);
+    WarpSmem *w = WS(c);
     w_load(&w->dyn, p.dyn + env);
     uint64_t ep = p.first_episode + (uint64_t)env;
     float total = 0.f;
@@ -435,7 +431,7 @@ k_rollout(Params p, int n_ticks, uint32_t pk0, uint32_t pk1, float *reward_sum, 
     _Pragma("unroll 1") for (int t = 0; t < n_ticks; t++) {
         if (__syncthreads_and(w->dyn.done)) break;
         if (w->dyn.done) {      /* this episode is over but a sibling warp still runs: keep in step with the block's barriers */
-            _Pragma("unroll 1") for (int k = 0; k < N_PHASE_SYNC; k++) PHASE_SYNC();
+            _Pragma("unroll 1") for (int k = 0; k < N_PHASE_SYNC; k++) __syncthreads();
             continue;
         }
         if (lane_id() == 0) {
@@ -461,24 +457,23 @@ struct ResetTmp {
     uint16_t router_pid[16];
 };
 struct ResetSmem {
-    Cc4Dyn dyn;
-    Scratch x;
+    WarpSmem w;
     ResetTmp t;
 };
 
-__device__ int gen_pid(Ctx &c, ResetTmp *t)
+__device__ int gen_pid(Cx c, ResetTmp *t)
 {
     _Pragma("unroll 1") for (int guard = 0; guard < 64; guard++) {
         int v = (int)rng_int(c, NAG, ST_R_PID, 9000);
-        if (c.s->err & CC4_E_TAPE_END) return 1000 + v;
+        if (DYN(c)->err & CC4_E_TAPE_END) return 1000 + v;
         if (!(t->used[v >> 5] >> (v & 31) & 1)) { t->used[v >> 5] |= 1u << (v & 31); return 1000 + v; }
     }
     fail(c, CC4_E_CAPACITY);
     return 1000;
 }
-__device__ void gen_host(Ctx &c, ResetTmp *t, int slot)
+__device__ void gen_host(Cx c, ResetTmp *t, int slot)
 {   /* _generate_linux_host_services :530-561 + _generate_linux_host_processes :580-629 */
-    Cc4Dyn *s = c.s;
+    Cc4Dyn *s = DYN(c);
     int sn = slot >> 4, n = 0;
     uint64_t v = SVC_EMPTY;
     uint32_t pids[9]; int codes[9];
@@ -497,13 +492,13 @@ __device__ void gen_host(Ctx &c, ResetTmp *t, int slot)
     t->np[slot] = (uint8_t)n;
     s->svc64[slot] = v;
 }
-__device__ int tmp_create_pid(Ctx &c, ResetTmp *t, int slot)
+__device__ int tmp_create_pid(Cx c, ResetTmp *t, int slot)
 {
     uint32_t mx = 0;
     _Pragma("unroll 1") for (int i = 0; i < t->np[slot]; i++) if (P_PID(t->procs[slot][i]) > mx) mx = P_PID(t->procs[slot][i]);
     return (int)(mx + 1 + rng_int(c, NAG, ST_CREATE_PID, 9));
 }
-__device__ void tmp_add_session_proc(Ctx &c, ResetTmp *t, int slot, int kind)
+__device__ void tmp_add_session_proc(Cx c, ResetTmp *t, int slot, int kind)
 {
     if (slot >= CC4_SLOT_ROUTER) { t->router_pid[slot - CC4_SLOT_ROUTER] = (uint16_t)(1 + rng_int(c, NAG, ST_CREATE_PID, 9)); return; }
     int pid = tmp_create_pid(c, t, slot);
@@ -512,21 +507,18 @@ __device__ void tmp_add_session_proc(Ctx &c, ResetTmp *t, int slot, int kind)
 
 __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *mask)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    ResetSmem *w = reinterpret_cast<ResetSmem *>(smem_raw);
+    ResetSmem *rs = reinterpret_cast<ResetSmem *>(smem_raw);
+    WarpSmem *w = &rs->w;
     int env = blockIdx.x;
     const bool valid = env < p.n_envs;
-    Ctx c; c.s = &w->dyn; c.x = &w->x; c.st = p.stat + env; c.k = p.cold + env;
-    {
-        uint64_t ep = p.first_episode + (uint64_t)env;
-        c.steps = p.steps; c.rng_mode = p.rng_mode; c.k0 = p.k0; c.k1 = p.k1hi ^ (uint32_t)(ep >> 32); c.ep_lo = (uint32_t)ep;
-        c.tape = p.tape; c.seg = p.seg_off ? p.seg_off + (size_t)env * (p.n_segs + 1) : nullptr; c.n_segs = p.n_segs; c.tick = -1;
-    }
-    uint32_t *z = reinterpret_cast<uint32_t *>(w);
+    uint32_t *z = reinterpret_cast<uint32_t *>(rs);
     _Pragma("unroll 1") for (int i = lane_id(); i < (int)(sizeof(ResetSmem) / 4); i += 32) z[i] = 0;
     __syncwarp();
+    Cx c = make_ctx(0, p, env, -1);
+    if (lane_id() < 12) SCR(c)->blk_id[lane_id()] = 0xFFFFFFFFu;
+    __syncwarp();
     if (lane_id() == 0) {
-        Cc4Dyn *s = c.s; ResetTmp *t = &w->t; Cc4Stat *st = c.st;
+        Cc4Dyn *s = DYN(c); ResetTmp *t = &rs->t; Cc4Stat *st = WC(c)->st;
         _Pragma("unroll 1") for (int h = 0; h < 128; h++) s->svc64[h] = SVC_EMPTY;
         _Pragma("unroll 1") for (int a = 0; a < 16; a++) s->inprog[a] = IP_NONE;
         /* hosts, EnterpriseScenarioGenerator._generate_hosts :312-371 */
@@ -579,7 +571,7 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
         /* process lists + Host.create_backup Host.py:316-371 */
         _Pragma("unroll 1") for (int h = 0; h < 128; h++) {
             s->nproc[h] = t->np[h]; st->o_nproc[h] = t->np[h];
-            _Pragma("unroll 1") for (int i = 0; i < t->np[h]; i++) { c.k->procs[h][i] = t->procs[h][i]; st->o_procs[h][i] = t->procs[h][i]; }
+            _Pragma("unroll 1") for (int i = 0; i < t->np[h]; i++) { WC(c)->k->procs[h][i] = t->procs[h][i]; st->o_procs[h][i] = t->procs[h][i]; }
             st->o_svc64[h] = s->svc64[h];
         }
         _Pragma("unroll 1") for (int i = 0; i < 16; i++) st->router_pid[i] = t->router_pid[i];
@@ -588,7 +580,7 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
         s->ss[0][0] = 0; s->n_ss[0] = 1;
         /* red_agent_0 digests its initial observation (its start host becomes 'U', FiniteStateRedAgent.py:221-224) */
         s->fsm[0][0] = F_MAKE(st->red_start[0], 1, F_U); s->n_fsm[0] = 1; s->fsm_started = 1;
-        if (c.rng_mode == 1 && c.n_segs > 0 && c.x->ctr[NAG] != c.seg[1] - c.seg[0]) fail(c, CC4_E_TAPE_LEFT);
+        if (WC(c)->rng_mode == 1 && WC(c)->n_segs > 0 && SCR(c)->ctr[NAG] != WC(c)->seg[1] - WC(c)->seg[0]) fail(c, CC4_E_TAPE_LEFT);
     }
     __syncwarp();
     if (valid && obs) w_write_obs(&w->dyn, w->x.obsbits, obs + (size_t)env * CC4_N_BLUE * CC4_OBS_LEN);
@@ -616,6 +608,7 @@ struct cc4_handle {
     int device;
     uint64_t launches;
     int32_t *stage_actions; uint8_t *stage_msgs, *stage_obs, *stage_mask, *stage_done; float *stage_reward;   /* device staging for cc4_step_host */
+    cudaStream_t pipe[2]; cudaEvent_t ev_in, ev_out[2];   /* chunk pipeline of cc4_step_host */
 };
 
 extern "C" const char *cc4_last_error(void) { return g_err; }
@@ -646,6 +639,8 @@ extern "C" int cc4_destroy(cc4_handle *h)
     if (!h) return CC4_OK;
     cudaSetDevice(h->device);
     cudaFree(h->p.dyn); cudaFree(h->p.stat); cudaFree(h->p.cold);
+    for (int i = 0; i < 2; i++) { if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]); if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]); }
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
     cudaFree(h->stage_actions); cudaFree(h->stage_msgs); cudaFree(h->stage_obs); cudaFree(h->stage_mask); cudaFree(h->stage_done); cudaFree(h->stage_reward);
     delete h;
     return CC4_OK;
@@ -720,29 +715,57 @@ extern "C" int cc4_step(cc4_handle *h, const int32_t *actions_dev, const uint8_t
     if (!h || !actions_dev) return set_err(CC4_ERR_ARG, "cc4_step: null handle or actions%s", "");
     CUDA_TRY(cudaSetDevice(h->device));
     int blocks = h->p.n_alloc / WARPS_PER_BLOCK;
-    k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * WARPS_PER_BLOCK, (cudaStream_t)stream>>>(h->p, actions_dev, msgs_dev, obs_dev, reward_dev, done_dev, flags);
+    k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * WARPS_PER_BLOCK, (cudaStream_t)stream>>>(h->p, 0, actions_dev, msgs_dev, obs_dev, reward_dev, done_dev, flags);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return CC4_OK;
 }
 
+/* Host-buffer tick.  The batch is cut into chunks that flow through two internal streams: the device->host copy of
+ * chunk i (observations dominate: 1 050 B per episode) overlaps the kernel of chunk i+1, so the call costs about
+ * max(kernel, copy) instead of their sum.  The call is synchronous with respect to `stream`. */
+#ifndef CC4_HOST_CHUNKS
+#define CC4_HOST_CHUNKS 8
+#endif
 extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const uint8_t *msgs_host, uint8_t *obs_host, float *reward_host,
                              uint8_t *done_host, int flags, void *stream)
 {
     if (!h || !actions_host) return set_err(CC4_ERR_ARG, "cc4_step_host: null handle or actions%s", "");
     CUDA_TRY(cudaSetDevice(h->device));
-    size_t n = (size_t)h->p.n_envs;
-    cudaStream_t st = (cudaStream_t)stream;
     { int rc0 = ensure_staging(h); if (rc0) return rc0; }
-    CUDA_TRY(cudaMemcpyAsync(h->stage_actions, actions_host, n * 5 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    if (msgs_host) CUDA_TRY(cudaMemcpyAsync(h->stage_msgs, msgs_host, n * 5, cudaMemcpyHostToDevice, st));
-    int rc = cc4_step(h, h->stage_actions, msgs_host ? h->stage_msgs : nullptr, obs_host ? h->stage_obs : nullptr,
-                      reward_host ? h->stage_reward : nullptr, done_host ? h->stage_done : nullptr, flags, stream);
-    if (rc) return rc;
-    if (obs_host && (flags & CC4_STEP_OBS)) CUDA_TRY(cudaMemcpyAsync(obs_host, h->stage_obs, n * CC4_N_BLUE * CC4_OBS_LEN, cudaMemcpyDeviceToHost, st));
-    if (reward_host && (flags & CC4_STEP_REWARD)) CUDA_TRY(cudaMemcpyAsync(reward_host, h->stage_reward, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host, h->stage_done, n, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    const size_t n = (size_t)h->p.n_envs;
+    cudaStream_t user = (cudaStream_t)stream;
+    if (!h->pipe[0]) {
+        for (int i = 0; i < 2; i++) { CUDA_TRY(cudaStreamCreateWithFlags(&h->pipe[i], cudaStreamNonBlocking)); CUDA_TRY(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming)); }
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    }
+    /* order after whatever the caller queued on its stream (an earlier reset / device-side step) */
+    CUDA_TRY(cudaEventRecord(h->ev_in, user));
+    for (int i = 0; i < 2; i++) CUDA_TRY(cudaStreamWaitEvent(h->pipe[i], h->ev_in, 0));
+    const bool want_obs = obs_host && (flags & CC4_STEP_OBS), want_rew = reward_host && (flags & CC4_STEP_REWARD);
+    size_t chunk = (n + CC4_HOST_CHUNKS - 1) / CC4_HOST_CHUNKS;
+    chunk = (chunk + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK * WARPS_PER_BLOCK;
+    if (chunk < 2048) chunk = 2048;     /* small batches: one chunk (a launch per few hundred episodes would be launch bound) */
+    int k = 0;
+    for (size_t e0 = 0; e0 < n; e0 += chunk, k ^= 1) {
+        size_t cnt = n - e0 < chunk ? n - e0 : chunk;
+        cudaStream_t st = h->pipe[k];
+        CUDA_TRY(cudaMemcpyAsync(h->stage_actions + e0 * 5, actions_host + e0 * 5, cnt * 5 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        if (msgs_host) CUDA_TRY(cudaMemcpyAsync(h->stage_msgs + e0 * 5, msgs_host + e0 * 5, cnt * 5, cudaMemcpyHostToDevice, st));
+        int blocks = (int)((cnt + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+        Params p = h->p;
+        if ((size_t)p.n_envs > e0 + cnt) p.n_envs = (int)(e0 + cnt);     /* episodes past the chunk belong to a later launch */
+        k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * WARPS_PER_BLOCK, st>>>(
+            p, (int)e0, h->stage_actions, msgs_host ? h->stage_msgs : nullptr, want_obs ? h->stage_obs : nullptr,
+            want_rew ? h->stage_reward : nullptr, done_host ? h->stage_done : nullptr, flags);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+        if (want_obs) CUDA_TRY(cudaMemcpyAsync(obs_host + e0 * CC4_N_BLUE * CC4_OBS_LEN, h->stage_obs + e0 * CC4_N_BLUE * CC4_OBS_LEN, cnt * CC4_N_BLUE * CC4_OBS_LEN, cudaMemcpyDeviceToHost, st));
+        if (want_rew) CUDA_TRY(cudaMemcpyAsync(reward_host + e0, h->stage_reward + e0, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host + e0, h->stage_done + e0, cnt, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < 2; i++) { CUDA_TRY(cudaEventRecord(h->ev_out[i], h->pipe[i])); CUDA_TRY(cudaStreamWaitEvent(user, h->ev_out[i], 0)); }
+    CUDA_TRY(cudaStreamSynchronize(user));
     return CC4_OK;
 }
 

@@ -162,6 +162,7 @@ struct cc4o_env {
     uint64_t seed, episode; int steps, rng_mode;
     const cc4o_draw *tape; const uint32_t *seg_off; uint32_t n_segs;
     uint32_t seg_pos[NAG]; uint32_t reset_pos; uint32_t draw_ctr[NAG + 1];
+    uint32_t blk_id[NAG + 1]; uint32_t blk[NAG + 1][4];   /* cached Philox block per stream */
     int err; char errmsg[256];
     /* scenario */
     int nuser[8], nserver[8];
@@ -231,15 +232,23 @@ static int tape_next(cc4o_env *e, int actor, int site, int kind, uint32_t n, uin
     return 0;
 }
 
-static void philox_draw(cc4o_env *e, int actor, uint32_t out[4])
+/* Production RNG of the engine (not the reference's): every (actor, tick) owns a stream of 32-bit words; word j is
+ * element j&3 of the Philox4x32-10 block with key (seed, episode) and counter (j>>2, actor, tick+1, episode).
+ * An integer draw consumes one word, a double two. */
+static uint32_t rng_word(cc4o_env *e, int actor)
 {
-    uint32_t c[4];
-    c[0] = e->draw_ctr[actor]++;
-    c[1] = (uint32_t)actor;
-    c[2] = actor == NAG ? 0u : (uint32_t)e->step_count + 1u;
-    c[3] = (uint32_t)e->episode;
-    philox4x32_10(c, (uint32_t)e->seed, (uint32_t)(e->seed >> 32) ^ (uint32_t)(e->episode >> 32));
-    memcpy(out, c, sizeof c);
+    uint32_t j = e->draw_ctr[actor]++;
+    if (e->blk_id[actor] != (j >> 2)) {
+        uint32_t c[4];
+        c[0] = j >> 2;
+        c[1] = (uint32_t)actor;
+        c[2] = actor == NAG ? 0u : (uint32_t)e->step_count + 1u;
+        c[3] = (uint32_t)e->episode;
+        philox4x32_10(c, (uint32_t)e->seed, (uint32_t)(e->seed >> 32) ^ (uint32_t)(e->episode >> 32));
+        memcpy(e->blk[actor], c, sizeof c);
+        e->blk_id[actor] = j >> 2;
+    }
+    return e->blk[actor][j & 3u];
 }
 
 static uint32_t rng_int(cc4o_env *e, int actor, int site, uint32_t n)
@@ -248,8 +257,7 @@ static uint32_t rng_int(cc4o_env *e, int actor, int site, uint32_t n)
         uint64_t v; tape_next(e, actor, site, 0, n, &v);
         return v < n ? (uint32_t)v : 0;
     }
-    uint32_t o[4]; philox_draw(e, actor, o);
-    return (uint32_t)(((uint64_t)o[0] * n) >> 32);
+    return (uint32_t)(((uint64_t)rng_word(e, actor) * n) >> 32);
 }
 
 static double rng_f64(cc4o_env *e, int actor, int site, uint32_t n)
@@ -258,8 +266,8 @@ static double rng_f64(cc4o_env *e, int actor, int site, uint32_t n)
         uint64_t v; tape_next(e, actor, site, 1, n, &v);
         double d; memcpy(&d, &v, 8); return d;
     }
-    uint32_t o[4]; philox_draw(e, actor, o);
-    return ((double)(o[0] >> 5) * 67108864.0 + (double)(o[1] >> 6)) / 9007199254740992.0;
+    uint32_t hi = rng_word(e, actor), lo = rng_word(e, actor);
+    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) / 9007199254740992.0;
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -428,7 +436,7 @@ int cc4o_reset(cc4o_env *e)
 {
     init_tables();
     e->err = 0; e->errmsg[0] = 0;
-    e->reset_pos = 0; memset(e->seg_pos, 0, sizeof e->seg_pos); memset(e->draw_ctr, 0, sizeof e->draw_ctr);
+    e->reset_pos = 0; memset(e->seg_pos, 0, sizeof e->seg_pos); memset(e->draw_ctr, 0, sizeof e->draw_ctr); memset(e->blk_id, 0xFF, sizeof e->blk_id);
     e->n_used = 0; e->norder = 0; e->ngreen = 0;
     memset(e->hosts, 0, sizeof e->hosts);
     for (int a = 0; a < NAG; a++) { e->nsess[a] = 0; e->sess_count[a] = 0; e->active[a] = 0; e->inprog[a].code = AC_NONE; e->inprog_ticks[a] = 0; e->cur_action[a].code = AC_SLEEP; }
@@ -1133,7 +1141,7 @@ int cc4o_observe(cc4o_env *e, uint8_t *obs)
 int cc4o_step(cc4o_env *e, const int32_t *actions, const uint8_t *msgs, uint8_t *obs, float *reward, uint8_t *done)
 {
     int nact = A_GREEN0 + e->ngreen;
-    memset(e->seg_pos, 0, sizeof e->seg_pos); memset(e->draw_ctr, 0, sizeof e->draw_ctr);
+    memset(e->seg_pos, 0, sizeof e->seg_pos); memset(e->draw_ctr, 0, sizeof e->draw_ctr); memset(e->blk_id, 0xFF, sizeof e->blk_id);
     /* mission phase, State.check_next_phase_on_update_step State.py:514-544, _generate_mission_phases :854-860 */
     {
         int q = e->steps / 3, rem = e->steps % 3, l0 = q + (rem >= 1), l1 = q + (rem == 2);
