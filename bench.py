@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 
 N_BLUE = 5
 B_IO = 20 + 5 + (4 * 92 + 210) + 4 + 1      # actions + messages + 5 observation vectors + reward + done
+SVC_BYTES = 128 * 8                          # per-host service table: read in place every tick by the green agents (not staged)
 EPISODE_TICKS = 499                          # steps=500 -> done at step_count >= 499 (EnterpriseScenarioGenerator.py:870)
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch at 65536 episodes from the committed
 # `ncu --set full` capture (profiles/), or None when no capture matches the current kernel
@@ -251,7 +252,7 @@ def main():
         peak, which = load_peaks()
         total_envs = n * world
         env_sps = total_envs * args.steps / (ms / 1e3)
-        b_step = 2 * dyn_bytes + B_IO
+        b_step = 2 * dyn_bytes + SVC_BYTES + B_IO
         achieved = b_step * n / (kernel_ms / 1e3) / 1e9
         line = {
             "metric": "agent-steps/sec", "value": env_sps * N_BLUE, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
@@ -264,7 +265,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": which, "kernel": "k_step",
                          "kernel_ms": kernel_ms, "bytes_per_env_step": b_step,
-                         "formula": "2*sizeof(hot record) + 608 B io per episode-tick; the cold record is touched in place by rare transitions only (DESIGN.md)"},
+                         "formula": "2*sizeof(hot record) + 1024 B service table (read in place) + 608 B io per episode-tick; the rest of the cold record is touched by rare transitions only (DESIGN.md)"},
             "state_bytes": {"hot": dyn_bytes, "cold": cold_bytes, "static": stat_bytes},
             "score": {"episodes": int(score[2].item()), "mean_return": float(score[0] / score[2])},
             "error_episodes": int((errs != 0).sum()),

@@ -109,18 +109,23 @@ struct Scratch {
     uint32_t evpid[16]; int n_evpid;              /* (slot<<16 | pid) carried by this tick's process_creation events */
     uint32_t subw[11];                            /* this tick's due action per blue / red actor (IP_MAKE, ticks = 0) */
     uint8_t dropped[16];
+    int16_t act_si[8];                            /* pool index of the session each red agent's due action names, resolved lane-parallel before the red phase */
+    int sess_moved;                               /* a session was deleted since act_si was resolved (indices may have shifted) */
     /* session-pool digests, rebuilt by w_scan_sessions */
     uint32_t sess_hosts[CC4_NRED][4];             /* hosts on which agent r holds a session */
     int n_red[8];                                 /* sessions per agent */
     uint32_t has0, newss, misplaced;              /* bit r: agent r has ident 0 / has an abstract session whose id it does not know yet / has a session on a foreign subnet */
-    uint32_t hostagents[32];                      /* byte h = mask of red agents with a session on host h (built on demand for phishing) */
-    uint32_t phish[3];                            /* green agents whose local work triggered a phishing email this tick */
     uint32_t ssmask[CC4_NRED][8];                 /* bit id: server_session id known to agent r (mirror of Cc4Dyn.ss, rebuilt every tick) */
-    uint32_t obsbits[40];                         /* observation vectors as bit strings [5][8] */
     int reward;
-    uint32_t blk_id[12];                          /* cached Philox block per serial stream: actors 0..10, [11] = reset */
-    uint32_t blk[12][4];
-    uint32_t et[CC4_NRED][4][4];                  /* agent_end_turn work masks per red agent: seen / present / hostname / user+ */
+    uint32_t blk_id[CC4_NRED + 1];                /* cached Philox block per serial stream: red agents 0..5, [6] = reset */
+    uint32_t blk[CC4_NRED + 1][4];
+    union {                                       /* three phase-local areas that are never live together */
+        struct { uint32_t hostagents[32];         /* byte h = mask of red agents with a session on host h (built on demand for phishing) */
+                 uint32_t phish[3], pad;          /* green agents whose local work triggered a phishing email this tick */
+                 uint64_t as_cum[8]; } g;         /* per source subnet: byte sn = number of allowed destination servers in subnets <= sn (GreenAccessService) */
+        uint32_t et[CC4_NRED][4][4];              /* agent_end_turn work masks per red agent: seen / present / hostname / user+ */
+        uint32_t obsbits[40];                     /* observation vectors as one bit string (w_write_obs) */
+    };
 };
 
 /* per-warp context (shared memory): everything a device function needs besides the record and the scratch */
@@ -192,7 +197,7 @@ __device__ __noinline__ uint32_t rng_word(Cx c, int actor)
 {
     Scratch *x = SCR(c);
     uint32_t j = x->ctr[actor]++;
-    int slot = actor < A_GREEN0 ? actor : actor == NAG ? 11 : -1;
+    int slot = actor == NAG ? CC4_NRED : (actor >= A_RED0 && actor < A_GREEN0) ? actor - A_RED0 : -1;   /* blue / green draws are rare: uncached */
     if (slot < 0) { uint4 v = philox_block(c, actor, j >> 2); return u4_word(v, j & 3u); }
     if (x->blk_id[slot] != (j >> 2)) {
         uint4 v = philox_block(c, actor, j >> 2);
@@ -229,30 +234,50 @@ __device__ __forceinline__ int blue_of_subnet(int sn) { return sn <= S_OZB ? sn 
 __device__ __forceinline__ bool bit128(const uint32_t *b, int i) { return (b[i >> 5] >> (i & 31)) & 1u; }
 __device__ __forceinline__ void set128(uint32_t *b, int i) { b[i >> 5] |= 1u << (i & 31); }
 
-/* ---- process lists (lane 0; the slabs live in the cold record) ---- */
+/* ---- process lists (lane 0; they live in the cold record's arena, cc4_state.h) ---- */
+#define NPROC(c, h) ((int)PD_CNT(WC(c)->k->pdir[h]))
+#define PROCS(c, h) (WC(c)->k->parena + PD_OFF(WC(c)->k->pdir[h]))
 __device__ __noinline__ void proc_append(Cx c, int h, uint32_t w)
 {   /* host.processes.append */
-    int n = DYN(c)->nproc[h];
-    if (n >= CC4_PSLAB) { fail(c, CC4_E_CAPACITY); return; }
-    WC(c)->k->procs[h][n] = w;
-    DYN(c)->nproc[h] = (uint8_t)(n + 1);
+    Cc4Cold *k = WC(c)->k;
+    uint32_t d = k->pdir[h], off = PD_OFF(d), n = PD_CNT(d), capl = PD_CAPL(d);
+    if (n == (1u << capl)) {            /* block full: move the list to a block of twice the size */
+        uint32_t top = k->arena_top, ncap = 2u << capl;
+        if (top + ncap > CC4_ARENA || n >= PD_MAXCNT) { fail(c, CC4_E_CAPACITY); return; }
+        _Pragma("unroll 1") for (uint32_t i = 0; i < n; i++) k->parena[top + i] = k->parena[off + i];
+        k->arena_top = top + ncap; off = top; capl++;
+    }
+    k->parena[off + n] = w;
+    k->pdir[h] = PD_MAKE(off, n + 1, capl);
+    if (P_PID(w) > k->pmax[h]) k->pmax[h] = (uint16_t)P_PID(w);
+}
+__device__ __noinline__ void proc_rescan_max(Cx c, int h)
+{
+    Cc4Cold *k = WC(c)->k;
+    const uint32_t *pp = k->parena + PD_OFF(k->pdir[h]); const int n = (int)PD_CNT(k->pdir[h]);
+    uint32_t mx = 0;
+    _Pragma("unroll 1") for (int i = 0; i < n; i++) { uint32_t w = pp[i]; if (!P_DEAD(w) && P_PID(w) > mx) mx = P_PID(w); }
+    k->pmax[h] = (uint16_t)mx;
 }
 __device__ __noinline__ void proc_delete(Cx c, int h, int idx)
 {
-    int n = DYN(c)->nproc[h];
-    _Pragma("unroll 1") for (int i = idx; i + 1 < n; i++) WC(c)->k->procs[h][i] = WC(c)->k->procs[h][i + 1];
-    DYN(c)->nproc[h] = (uint8_t)(n - 1);
+    Cc4Cold *k = WC(c)->k;
+    uint32_t d = k->pdir[h], *pp = k->parena + PD_OFF(d);
+    int n = (int)PD_CNT(d);
+    const uint32_t gone = pp[idx];
+    _Pragma("unroll 1") for (int i = idx; i + 1 < n; i++) pp[i] = pp[i + 1];
+    k->pdir[h] = PD_MAKE(PD_OFF(d), n - 1, PD_CAPL(d));
+    if (!P_DEAD(gone) && P_PID(gone) == k->pmax[h]) proc_rescan_max(c, h);
 }
 __device__ __noinline__ int proc_find(Cx c, int h, uint32_t pid)
 {   /* Host.get_process Host.py:251 (tombstones are not processes) */
-    _Pragma("unroll 1") for (int i = 0; i < DYN(c)->nproc[h]; i++) { uint32_t w = WC(c)->k->procs[h][i]; if (!P_DEAD(w) && P_PID(w) == pid) return i; }
+    const uint32_t *pp = PROCS(c, h); const int n = NPROC(c, h);
+    _Pragma("unroll 1") for (int i = 0; i < n; i++) { uint32_t w = pp[i]; if (!P_DEAD(w) && P_PID(w) == pid) return i; }
     return -1;
 }
 __device__ __noinline__ int create_pid(Cx c, int actor, int h)
 {   /* Host.create_pid Host.py:198-200 */
-    uint32_t mx = 0;
-    _Pragma("unroll 1") for (int i = 0; i < DYN(c)->nproc[h]; i++) { uint32_t w = WC(c)->k->procs[h][i]; if (!P_DEAD(w) && P_PID(w) > mx) mx = P_PID(w); }
-    uint32_t pid = mx + 1 + rng_int(c, actor, ST_CREATE_PID, 9);
+    uint32_t pid = (uint32_t)WC(c)->k->pmax[h] + 1 + rng_int(c, actor, ST_CREATE_PID, 9);
     if (pid > 0xFFFFu) { fail(c, CC4_E_CAPACITY); pid = 0xFFFFu; }
     return (int)pid;
 }
@@ -282,6 +307,7 @@ __device__ __noinline__ void sess_delete(Cx c, int idx)
     if (SF_ABS(s->sessf[idx])) ports_drop(c, SF_AGENT(s->sessf[idx]), S_ID(s->sess[idx]));
     _Pragma("unroll 1") for (int i = idx; i + 1 < s->n_sess; i++) { s->sess[i] = s->sess[i + 1]; s->sessf[i] = s->sessf[i + 1]; }
     s->n_sess--;
+    SCR(c)->sess_moved = 1;
 }
 /* State.add_session State.py:305-323 for a red agent; returns the ident */
 __device__ __noinline__ int sess_add(Cx c, int r, int host, int abstract, int root, int pid)
@@ -365,53 +391,53 @@ __device__ __noinline__ void agent_end_turn(Cx c, int r)
     if (x->newss >> r & 1)
         _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && SF_ABS(s->sessf[i])) know_session(c, r, S_ID(s->sess[i]));
 
-    /* _host_state_transition :124-167 */
-    if (x->has_act0[r] && x->succ0[r] != SUCC_INPROG) {
-        int code = IP_CODE(x->act0[r]), ahost = IP_HOST(x->act0[r]), asub = IP_SUBNET(x->act0[r]), col = -1;
-        _Pragma("unroll 1") for (int k = 0; k < 9; k++) if (c_fsm_col_code[k] == code) col = k;
-        if (col >= 0 && col != 8) {
-            _Pragma("unroll 1") for (int i = 0; i < s->n_fsm[r]; i++) {
-                uint16_t f = s->fsm[r][i];
-                bool hit;
-                if (col == 0) hit = (int)(F_SLOT(f) >> 4) == asub;
-                else if (col <= 4) hit = (int)F_SLOT(f) == ahost;
-                else hit = F_HN(f) && (int)F_SLOT(f) == ahost;
-                if (!hit) continue;
-                int st = F_STATE(f), nx = x->succ0[r] == SUCC_TRUE ? c_fsm_succ[st][col] : c_fsm_fail[st][col];
-                if (nx == F_U && !red_allowed(r, F_SLOT(f) >> 4)) nx = F_F;
-                if (nx < 0) nx = st;
-                s->fsm[r][i] = F_MAKE(F_SLOT(f), F_HN(f), nx);
-                if (col != 0) break;
-            }
-        }
-    }
-    /* _process_new_observations :190-250, explicit entries first (they precede the RedSessionCheck observation) */
+    /* _host_state_transition :124-167, fused with one pass that digests the FSM list into host masks:
+       present / hostname known / state in {U, UD, R, RD} */
     int started = (s->fsm_started >> r) & 1;
     uint32_t *seen = x->et[r][0], *fa = x->et[r][1], *fh = x->et[r][2], *fu = x->et[r][3];   /* shared scratch: indexed dynamically */
     _Pragma("unroll") for (int w = 0; w < 4; w++) { seen[w] = rsc[w]; fa[w] = 0; fh[w] = 0; fu[w] = 0; }
+    {
+        int col = -1, ahost = 0, asub = 0;
+        const bool succ = x->succ0[r] == SUCC_TRUE;
+        if (x->has_act0[r] && x->succ0[r] != SUCC_INPROG) {
+            int code = IP_CODE(x->act0[r]);
+            ahost = IP_HOST(x->act0[r]); asub = IP_SUBNET(x->act0[r]);
+            col = code >= AC_DRS && code <= AC_DEGRADE ? code - AC_DRS : -1;      /* columns follow the action codes; Withdraw (8) never transitions */
+        }
+        const int nf = s->n_fsm[r];
+        _Pragma("unroll 1") for (int i = 0; i < nf; i++) {
+            uint32_t f = s->fsm[r][i], slot = F_SLOT(f), st = F_STATE(f);
+            if (col >= 0) {
+                bool hit = col == 0 ? (int)(slot >> 4) == asub : col <= 4 ? (int)slot == ahost : (F_HN(f) && (int)slot == ahost);
+                if (hit) {
+                    int nx = succ ? c_fsm_succ[st][col] : c_fsm_fail[st][col];
+                    if (nx == F_U && !red_allowed(r, slot >> 4)) nx = F_F;
+                    if (nx >= 0) { st = (uint32_t)nx; s->fsm[r][i] = F_MAKE(slot, F_HN(f), st); }
+                    if (col != 0) col = -1;         /* host-targeted actions move the first matching host only */
+                }
+            }
+            uint32_t w = slot >> 5, bit = 1u << (slot & 31);
+            fa[w] |= bit;
+            if (F_HN(f)) fh[w] |= bit;
+            if (st >= F_U && st <= F_RD) fu[w] |= bit;
+        }
+    }
+    /* _process_new_observations :190-250, explicit entries first (they precede the RedSessionCheck observation) */
     _Pragma("unroll 1") for (int i = 0; i < x->n_oent[r]; i++) {
         uint16_t e = x->oent[r][i];
         int slot = e & 0xFF, key_ip = (e >> 8) & 1, syshost = (e >> 11) & 1;
         int iface = ((e >> 9) & 1) || (!key_ip && bit128(rsc, slot));   /* a hostname-keyed entry merges with the RedSessionCheck entry of the same host */
         int hn = !key_ip || syshost;
-        if ((e >> 12) & 1) { if (iface) seen[slot >> 5] |= 1u << (slot & 31); else fail(c, CC4_E_UNREACHABLE); }
-        int resolved = key_ip || iface;
-        if (!resolved) { _Pragma("unroll 1") for (int j = 0; j < s->n_fsm[r]; j++) if (F_HN(s->fsm[r][j]) && (int)F_SLOT(s->fsm[r][j]) == slot) { resolved = 1; break; } }
-        if (!resolved) { fail(c, CC4_E_UNREACHABLE); continue; }   /* would create host_states[None] */
-        int idx = fsm_find(s, r, slot);
-        if (idx < 0) {
+        uint32_t w = (uint32_t)slot >> 5, bit = 1u << (slot & 31);
+        if ((e >> 12) & 1) { if (iface) seen[w] |= bit; else fail(c, CC4_E_UNREACHABLE); }
+        if (!(key_ip || iface || (fh[w] & bit))) { fail(c, CC4_E_UNREACHABLE); continue; }   /* would create host_states[None] */
+        if (!(fa[w] & bit)) {
             if (s->n_fsm[r] >= CC4_FSM_CAP) { fail(c, CC4_E_CAPACITY); continue; }
-            idx = s->n_fsm[r]++;
-            s->fsm[r][idx] = F_MAKE(slot, hn, started ? F_K : F_U);
-        } else if (hn && !F_HN(s->fsm[r][idx])) s->fsm[r][idx] |= 1u << 7;
-    }
-    /* host masks of the FSM list: present / hostname known / state in {U, UD, R, RD} */
-    _Pragma("unroll 1") for (int i = 0; i < s->n_fsm[r]; i++) {
-        uint16_t f = s->fsm[r][i];
-        uint32_t w = F_SLOT(f) >> 5, b = 1u << (F_SLOT(f) & 31);
-        fa[w] |= b;
-        if (F_HN(f)) fh[w] |= b;
-        if (F_STATE(f) >= F_U && F_STATE(f) <= F_RD) fu[w] |= b;
+            s->fsm[r][s->n_fsm[r]++] = F_MAKE(slot, hn, started ? F_K : F_U);
+            fa[w] |= bit;
+            if (hn) fh[w] |= bit;
+            if (!started) fu[w] |= bit;
+        } else if (hn && !(fh[w] & bit)) { s->fsm[r][fsm_find(s, r, slot)] |= 1u << 7; fh[w] |= bit; }
     }
     /* RedSessionCheck entries in state.sessions[agent] order: hosts the FSM has not seen yet */
     if ((rsc[0] & ~fa[0]) | (rsc[1] & ~fa[1]) | (rsc[2] & ~fa[2]) | (rsc[3] & ~fa[3])) {
@@ -525,12 +551,13 @@ __device__ __noinline__ void stop_process(Cx c, int actor, int h, uint32_t pid)
     Cc4Dyn *s = DYN(c);
     int pi = proc_find(c, h, pid);
     if (pi < 0) return;
-    uint32_t w = WC(c)->k->procs[h][pi];
+    uint32_t w = PROCS(c, h)[pi];
     if (P_ROOT(w)) return;
     int si = session_from_pid(s, h, pid);
     /* a stopped OT service keeps Service.process; a pid collision with it takes the reference down a path that
        re-labels the killed process as the service's (StopProcess.py:37-42): not modelled */
-    _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) if (P_DEAD(WC(c)->k->procs[h][i]) && P_PID(WC(c)->k->procs[h][i]) == pid) fail(c, CC4_E_UNREACHABLE);
+    { const uint32_t *pp = PROCS(c, h); const int np = NPROC(c, h);
+      _Pragma("unroll 1") for (int i = 0; i < np; i++) if (P_DEAD(pp[i]) && P_PID(pp[i]) == pid) fail(c, CC4_E_UNREACHABLE); }
     proc_delete(c, h, pi);
     if (P_SVC(w)) {
         int np = create_pid(c, actor, h);
@@ -550,18 +577,19 @@ __device__ __noinline__ void do_restore(Cx c, int h)
     _Pragma("unroll 1") for (int i = 0; i < s->n_sess;) if (S_HOST(s->sess[i]) == (uint32_t)h) sess_delete(c, i); else i++;
     s->ev[h] = 0;
     int on = st->o_nproc[h];
-    _Pragma("unroll 1") for (int i = 0; i < on; i++) WC(c)->k->procs[h][i] = st->o_procs[h][i];
-    s->nproc[h] = (uint8_t)on;
-    s->svc64[h] = st->o_svc64[h];
+    _Pragma("unroll 1") for (int i = 0; i < on; i++) WC(c)->k->parena[h * CC4_OSLAB + i] = st->o_procs[h][i];   /* back in the home slab */
+    WC(c)->k->pdir[h] = PD_MAKE(h * CC4_OSLAB, on, 3);
+    proc_rescan_max(c, h);
+    WC(c)->k->svc64[h] = st->o_svc64[h];
 }
 
 /* DecoyAction.execute DecoyAction.py:47-112 with DeployDecoy.CANDIDATE_DECOYS DeployDecoy.py:27 */
 __device__ __noinline__ void do_decoy(Cx c, int b, int h)
 {
-    Cc4Dyn *s = DYN(c);
     int actor = A_BLUE0 + b;
     int used = 0;
-    _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) { uint32_t w = WC(c)->k->procs[h][i]; if (P_DEAD(w)) continue; int pb = c_kind_portbit[P_KIND(w)]; if (pb >= 0) used |= 1 << pb; }
+    const uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
+    _Pragma("unroll 1") for (int i = 0; i < np_h; i++) { uint32_t w = pp_h[i]; if (P_DEAD(w)) continue; int pb = c_kind_portbit[P_KIND(w)]; if (pb >= 0) used |= 1 << pb; }
     int fac[4], nf = 0;
     if (!(used & PB_80)) fac[nf++] = K_D_APACHE;
     if (!(used & PB_443)) fac[nf++] = K_D_TOMCAT;
@@ -570,13 +598,13 @@ __device__ __noinline__ void do_decoy(Cx c, int b, int h)
     int kind = fac[rng_int(c, actor, ST_DECOY_FACTORY, (uint32_t)nf)];
     int pid = create_pid(c, actor, h);
     /* host.services[name] = Service(pid): an earlier process of the same decoy stops being the service's process */
-    _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) { uint32_t w = WC(c)->k->procs[h][i]; if (P_KIND(w) == (uint32_t)kind && P_SVC(w)) WC(c)->k->procs[h][i] = w & ~(1u << 21); }
+    _Pragma("unroll 1") for (int i = 0; i < np_h; i++) { uint32_t w = pp_h[i]; if (P_KIND(w) == (uint32_t)kind && P_SVC(w)) PROCS(c, h)[i] = w & ~(1u << 21); }
     proc_append(c, h, P_MAKE(pid, kind, 0, 1));
-    uint64_t v = s->svc64[h];
+    uint64_t v = WC(c)->k->svc64[h];
     int n = svc_count(v), at = -1;
     _Pragma("unroll 1") for (int i = 0; i < n; i++) if ((SVC_ENTRY(v, i) & 15u) == (uint32_t)kind) at = i;
     if (at < 0) { if (n >= 9) { fail(c, CC4_E_CAPACITY); return; } at = n; }
-    s->svc64[h] = svc_set(v, at, (uint32_t)kind | 5u << 4);
+    WC(c)->k->svc64[h] = svc_set(v, at, (uint32_t)kind | 5u << 4);
 }
 
 __device__ __noinline__ void exec_blue(Cx c, int b, uint32_t aw)
@@ -600,11 +628,11 @@ __device__ __noinline__ void exec_blue(Cx c, int b, uint32_t aw)
 /* ------------------------------------------------------------------------------------------------ */
 /* green                                                                                            */
 /* ------------------------------------------------------------------------------------------------ */
-/* PhishingEmail._create_new_session PhishingEmail.py:42-113 (lane 0, in green-agent order); x->hostagents is current */
+/* PhishingEmail._create_new_session PhishingEmail.py:42-113 (lane 0, in green-agent order); x->g.hostagents is current */
 __device__ __noinline__ void do_phishing(Cx c, int g)
 {
     Cc4Dyn *s = DYN(c);
-    const uint8_t *ha = reinterpret_cast<const uint8_t *>(SCR(c)->hostagents);
+    const uint8_t *ha = reinterpret_cast<const uint8_t *>(SCR(c)->g.hostagents);
     int actor = A_GREEN0 + g, gh = s->green_host[g], gsn = gh >> 4;
     if (ha[gh]) return;
     /* hosts in state.hosts order (per subnet: users, then servers), agents in order on each host */
@@ -612,7 +640,7 @@ __device__ __noinline__ void do_phishing(Cx c, int g)
     uint8_t cand[CC4_SESS_CAP];
     _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) {
         int nu = s->nuser[sn], nh = nu + s->nserver[sn];
-        if (!(SCR(c)->hostagents[4 * sn] | SCR(c)->hostagents[4 * sn + 1] | SCR(c)->hostagents[4 * sn + 2] | SCR(c)->hostagents[4 * sn + 3])) continue;
+        if (!(SCR(c)->g.hostagents[4 * sn] | SCR(c)->g.hostagents[4 * sn + 1] | SCR(c)->g.hostagents[4 * sn + 2] | SCR(c)->g.hostagents[4 * sn + 3])) continue;
         _Pragma("unroll 1") for (int k = 0; k < nh; k++) {
             int h = k < nu ? sn * 16 + 6 + k : sn * 16 + (k - nu);
             uint32_t agents = ha[h];
@@ -628,14 +656,7 @@ __device__ __noinline__ void do_phishing(Cx c, int g)
     int pid = create_pid(c, actor, gh);
     proc_append(c, gh, P_MAKE(pid, K_REDABS, 0, 0));
     sess_add(c, src, gh, 1, 0, pid);
-    reinterpret_cast<uint8_t *>(SCR(c)->hostagents)[gh] |= (uint8_t)(1u << src);
-}
-
-/* k-th server (creation order: subnets ascending, server_host_0..) among the allowed subnets; GreenAccessService.py:94-115 */
-__device__ __forceinline__ int nth_allowed_server(const Cc4Dyn *s, uint32_t allowed, int k)
-{
-    _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) if (allowed >> sn & 1) { int n = s->nserver[sn]; if (k < n) return sn * 16 + k; k -= n; }
-    return 0;
+    reinterpret_cast<uint8_t *>(SCR(c)->g.hostagents)[gh] |= (uint8_t)(1u << src);
 }
 
 /* one green agent's tick (EnterpriseGreenAgent.get_action :42-78, GreenLocalWork.py:60-125, GreenAccessService.py:137-217);
@@ -659,7 +680,7 @@ __device__ __noinline__ int green_tick(Cx c, int g, uint32_t *ev_words)
     int out = 0;
     uint32_t choice = gi(ST_GREEN_ACT, 3);
     if (choice == 1) {
-        uint64_t v = s->svc64[gh];
+        uint64_t v = WC(c)->k->svc64[gh];
         int n = svc_count(v), na = 0;
         _Pragma("unroll 1") for (int i = 0; i < n; i++) na += svc_active(v, SVC_ENTRY(v, i));
         if (na == 0) out = -c_reward[s->phase][gsn][0];
@@ -673,10 +694,12 @@ __device__ __noinline__ int green_tick(Cx c, int g, uint32_t *ev_words)
             }
         }
     } else if (choice == 0) {
-        uint32_t allowed = c_green_allowed[s->phase][gsn];
-        int nd = 0;
-        _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) if (allowed >> sn & 1) nd += s->nserver[sn];
-        int d = nth_allowed_server(s, allowed, (int)gi(ST_AS_DEST, (uint32_t)nd)), dsn = d >> 4;
+        /* destination = k-th server (creation order: subnets ascending, server_host_0..) among the allowed subnets,
+           GreenAccessService.py:94-115; the cumulative counts per source subnet were tabulated by w_tick */
+        const uint64_t cum = SCR(c)->g.as_cum[gsn];
+        const uint32_t k = gi(ST_AS_DEST, (uint32_t)(cum >> 56)), kk = k * 0x01010101u;
+        const int dsn = (__popc(__vcmpleu4((uint32_t)cum, kk)) + __popc(__vcmpleu4((uint32_t)(cum >> 32), kk))) >> 3;
+        const int d = dsn * 16 + (int)(k - (dsn ? (uint32_t)(cum >> (8 * (dsn - 1))) & 0xFFu : 0u));
         if ((s->blocks[gsn] >> dsn & 1) || (s->blocks[dsn] >> gsn & 1)) { atomicOr(&ev_words[d >> 2], EV_NET << ((d & 3) * 8)); out = -c_reward[s->phase][gsn][1]; }
         else if (gf(ST_AS_FP) < 0.01) atomicOr(&ev_words[d >> 2], EV_NET << ((d & 3) * 8));
     }
@@ -717,7 +740,7 @@ __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
     Cc4Dyn *s = DYN(c);
     const Act a = unpack_act(aw);
     int actor = A_RED0 + r;
-    int si = (a.code == AC_SLEEP || a.code == AC_INVALID) ? -1 : sess_find(s, r, a.session);
+    int si = (a.code == AC_SLEEP || a.code == AC_INVALID) ? -1 : SCR(c)->sess_moved ? sess_find(s, r, a.session) : (int)SCR(c)->act_si[r];
     int S_host = si >= 0 ? (int)S_HOST(s->sess[si]) : -1, S_abs = si >= 0 ? (int)SF_ABS(s->sessf[si]) : 0;
     switch (a.code) {
     case AC_DRS: {     /* DiscoverRemoteSystems.py:39 -> Pingsweep.execute Pingsweep.py:31-64 */
@@ -735,8 +758,9 @@ __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
         double rate = a.code == AC_AGGR ? 0.75 : 0.25;
         double u = rng_f64(c, actor, ST_PORTSCAN, 0);
         int mask = 0, any = 0, h = a.host;
-        _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) {
-            uint32_t w = WC(c)->k->procs[h][i];
+        const uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
+        _Pragma("unroll 1") for (int i = 0; i < np_h; i++) {
+            uint32_t w = pp_h[i];
             if (P_DEAD(w)) continue;
             int pb = c_kind_portbit[P_KIND(w)];
             if (pb < 0) continue;
@@ -755,8 +779,9 @@ __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
     case AC_DD: {      /* DiscoverDeception.py:44-101 */
         if (si < 0) return SUCC_FALSE;
         int rep = 0, h = a.host;
-        _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) {
-            uint32_t w = WC(c)->k->procs[h][i];
+        const uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
+        _Pragma("unroll 1") for (int i = 0; i < np_h; i++) {
+            uint32_t w = pp_h[i];
             if (P_DEAD(w)) continue;
             bool decoy = P_KIND(w) >= K_D_APACHE && P_KIND(w) <= K_D_VSFTPD;
             if (rng_f64(c, actor, ST_DD_TP, 0) <= 0.5 && decoy) rep = 1;
@@ -792,7 +817,8 @@ __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
             int hops[12], nh = route(src, target, hops);
             _Pragma("unroll 1") for (int i = 0; i < nh; i++) if (0.05 < rng_f64(c, actor, ST_SSH_HOP, 0)) s->ev[hops[i]] |= EV_NET;
             int vp = -1;
-            _Pragma("unroll 1") for (int i = 0; i < s->nproc[target]; i++) { uint32_t w = WC(c)->k->procs[target][i]; if (!P_DEAD(w) && P_KIND(w) == K_SSHD) { vp = i; break; } }
+            const uint32_t *pp_target = PROCS(c, target); const int np_target = NPROC(c, target);
+            _Pragma("unroll 1") for (int i = 0; i < np_target; i++) { uint32_t w = pp_target[i]; if (!P_DEAD(w) && P_KIND(w) == K_SSHD) { vp = i; break; } }
             if (vp < 0) return SUCC_FALSE;
             s->ev[target] |= EV_NET;
             int pid = exploit_new_session(c, r, target);
@@ -803,8 +829,9 @@ __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
         }
         /* ExploitAction.sim_exploit ExploitAction.py:48-116 */
         int vk = -1;
-        _Pragma("unroll 1") for (int i = 0; i < s->nproc[target] && vk < 0; i++) {
-            uint32_t w = WC(c)->k->procs[target][i];
+        const uint32_t *pp_target = PROCS(c, target); const int np_target = NPROC(c, target);
+        _Pragma("unroll 1") for (int i = 0; i < np_target && vk < 0; i++) {
+            uint32_t w = pp_target[i];
             if (P_DEAD(w)) continue;
             int k = P_KIND(w);
             if (sel == X_HTTP && (k == K_APACHE2 || k == K_D_APACHE || k == K_D_VSFTPD)) vk = k;
@@ -835,7 +862,7 @@ __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
             if (si < 0 || !S_abs) return SUCC_FALSE;
             s->sessf[tgt] |= 1u << 4;      /* EscalateAction.__upgrade_session EscalateAction.py:54-87 */
             int pi = proc_find(c, h, S_PID(s->sess[tgt]));
-            if (pi >= 0) WC(c)->k->procs[h][pi] |= P_ROOTBIT; else fail(c, CC4_E_UNREACHABLE);
+            if (pi >= 0) PROCS(c, h)[pi] |= P_ROOTBIT; else fail(c, CC4_E_UNREACHABLE);
         }
         obs_entry(c, r, 0, h, 0, 0, 0, 1);
         if (SF_ABS(s->sessf[tgt])) know_session(c, r, S_ID(s->sess[tgt]));
@@ -849,19 +876,21 @@ __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
         int h = a.host, any = 0, root = 0;
         _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_HOST(s->sess[i]) == (uint32_t)h) { any = 1; root |= SF_ROOT(s->sessf[i]); }
         if (!any || !root) return SUCC_FALSE;
-        uint64_t v = s->svc64[h];
+        uint64_t v = WC(c)->k->svc64[h];
         int n = svc_count(v);
         if (a.code == AC_IMPACT) {
             int has_ot = 0;
             _Pragma("unroll 1") for (int i = 0; i < n; i++) has_ot |= (SVC_ENTRY(v, i) & 15u) == K_OT;
             if (!has_ot || (v & SVC_OT_STOPPED)) return SUCC_FALSE;
             if (si < 0) return SUCC_FALSE;     /* StopService is a TargetedLocalAction: TargetedLocalAction.py:14-21 */
-            s->svc64[h] = v | SVC_OT_STOPPED;  /* Host.stop_service Host.py:296-301 */
-            _Pragma("unroll 1") for (int i = 0; i < s->nproc[h]; i++) {   /* State.remove_process State.py:390-418 */
-                uint32_t w = WC(c)->k->procs[h][i];
+            WC(c)->k->svc64[h] = v | SVC_OT_STOPPED;  /* Host.stop_service Host.py:296-301 */
+            const uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
+            _Pragma("unroll 1") for (int i = 0; i < np_h; i++) {   /* State.remove_process State.py:390-418 */
+                uint32_t w = pp_h[i];
                 if (!P_DEAD(w) && P_KIND(w) == K_OT && P_SVC(w)) {
                     int s2 = session_from_pid(s, h, P_PID(w));
-                    WC(c)->k->procs[h][i] = w | P_DEADBIT;
+                    PROCS(c, h)[i] = w | P_DEADBIT;
+                    if (P_PID(w) == WC(c)->k->pmax[h]) proc_rescan_max(c, h);
                     if (s2 >= 0) sess_delete(c, s2);
                     break;
                 }
@@ -870,7 +899,7 @@ __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
             int na = 0;
             _Pragma("unroll 1") for (int i = 0; i < n; i++) { uint32_t e = SVC_ENTRY(v, i); if (!svc_active(v, e)) continue; na++; uint32_t rel = e >> 4; rel = rel > 0 ? rel - 1 : 0; v = svc_set(v, i, (e & 15u) | rel << 4); }
             if (na == 0) return SUCC_FALSE;
-            s->svc64[h] = v;
+            WC(c)->k->svc64[h] = v;
         }
         obs_entry(c, r, 0, h, 0, 0, 0, 0);
         return SUCC_TRUE;

@@ -18,10 +18,13 @@
 namespace cc4 {
 
 #ifndef CC4_WARPS_PER_BLOCK
-#define CC4_WARPS_PER_BLOCK 8
+#define CC4_WARPS_PER_BLOCK 16
 #endif
 #ifndef CC4_SYNC_MASK
 #define CC4_SYNC_MASK 0x7F      /* bit i: block barrier i of the tick is enabled (tuning knob, see PHASE_SYNC) */
+#endif
+#ifndef CC4_MIN_BLOCKS
+#define CC4_MIN_BLOCKS 3        /* __launch_bounds__ min resident blocks per SM (caps registers per thread) */
 #endif
 constexpr int WARPS_PER_BLOCK = CC4_WARPS_PER_BLOCK;
 constexpr int DYN_U4 = (int)(sizeof(Cc4Dyn) / 16);
@@ -88,11 +91,29 @@ __device__ __forceinline__ uint8_t obs_element(const Cc4Dyn *s, int b, int p)
     int k = q >> 3, other = k < b ? k : k + 1;   /* the other four agents in sorted order, SimulationController.py:781-804 */
     return (s->msgs[other] >> (q & 7)) & 1;
 }
-/* The five vectors are first assembled as bit strings (bit p of agent b = element p, the phase is added to byte 0
- * afterwards), then expanded to bytes two at a time (an episode's 1050-byte block is only 2-byte aligned). */
-__device__ void w_write_obs(const Cc4Dyn *s, uint32_t *bits /* scratch [5][8] */, uint8_t *obs /* [5][210] of this episode */)
+/* The five vectors are assembled as ONE bit string (element p of agent b = bit mis + 210*b + p), expanded eight
+ * elements at a time into a staging area that overlays the (dead) start of the scratch, and copied out with 128-bit
+ * stores.  `mis` = the episode's byte offset inside its 16-byte line (1050 B per episode is only 2-byte aligned): giving
+ * the bit string the same lead makes staging byte j and global byte (line start + j) the same element, so whole
+ * 16-byte lines move aligned on both sides; only the first and the last line are written by halfwords. */
+constexpr int OBS_BYTES = CC4_N_BLUE * CC4_OBS_LEN;               /* 1050 */
+constexpr int OBS_STAGE = (14 + OBS_BYTES + 15) / 16 * 16;          /* 1072 */
+static_assert(offsetof(Scratch, obsbits) >= OBS_STAGE, "the observation staging area must not overlap Scratch::obsbits");
+static_assert(sizeof(((Scratch *)0)->obsbits) * 8 >= 14 + OBS_BYTES, "bit string too short");
+__device__ __forceinline__ void bits_or(uint32_t *bits, int off, uint64_t v)
+{   /* OR a <= 59-bit field into the bit string at bit offset off */
+    int sh = off & 31;
+    uint32_t *w = bits + (off >> 5);
+    atomicOr(&w[0], (uint32_t)(v << sh));
+    if (sh) { atomicOr(&w[1], (uint32_t)(v >> (32 - sh))); if (sh > 5) atomicOr(&w[2], (uint32_t)(v >> (64 - sh))); }
+    else atomicOr(&w[1], (uint32_t)(v >> 32));
+}
+__device__ void w_write_obs(const Cc4Dyn *s, Scratch *x, uint8_t *obs_base /* [n][5][210] */, int env)
 {
     const int lane = lane_id();
+    uint32_t *bits = x->obsbits;
+    const size_t goff = (size_t)env * OBS_BYTES;
+    const int mis = (int)(goff & 15);
     /* per-subnet 16-bit host masks: malicious-process / network-connection alerts (old + current events) */
     uint32_t procm[4], netm[4];
 #pragma unroll
@@ -119,31 +140,39 @@ __device__ void w_write_obs(const Cc4Dyn *s, uint32_t *bits /* scratch [5][8] */
         uint32_t nw = pair == 0 ? netm[0] : pair == 1 ? netm[1] : pair == 2 ? netm[2] : netm[3];
         uint32_t pm = (sn & 1) ? pw >> 16 : pw & 0xFFFFu, nm = (sn & 1) ? nw >> 16 : nw & 0xFFFFu;
         v |= (uint64_t)pm << 27 | (uint64_t)nm << 43;
-        int off = 1 + 59 * i, sh = off & 31;
-        uint32_t *w = bits + b * 8 + (off >> 5);
-        atomicOr(&w[0], (uint32_t)(v << sh));
-        atomicOr(&w[1], (uint32_t)(v >> (32 - sh)));
-        if (sh + 59 > 64) atomicOr(&w[2], (uint32_t)(v >> (64 - sh)));
+        bits_or(bits, mis + CC4_OBS_LEN * b + 1 + 59 * i, v);
     }
     if (lane >= 8 && lane < 13) {   /* messages from the other four agents in sorted order, SimulationController.py:781-804 */
-        int b = lane - 8, off = 1 + 59 * (b == 4 ? 3 : 1), sh = off & 31;
+        int b = lane - 8;
         uint32_t m = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) m |= (uint32_t)s->msgs[k < b ? k : k + 1] << (8 * k);
-        uint32_t *w = bits + b * 8 + (off >> 5);
-        atomicOr(&w[0], m << sh);
-        if (sh) atomicOr(&w[1], m >> (32 - sh));
+        bits_or(bits, mis + CC4_OBS_LEN * b + 1 + 59 * (b == 4 ? 3 : 1), (uint64_t)m);
     }
     __syncwarp();
-    uint16_t *out = reinterpret_cast<uint16_t *>(obs);
-    const uint32_t phase = s->phase;
-    _Pragma("unroll 1") for (int hw = lane; hw < CC4_N_BLUE * CC4_OBS_LEN / 2; hw += 32) {
-        int b = hw / (CC4_OBS_LEN / 2), p = (hw - b * (CC4_OBS_LEN / 2)) * 2;
-        uint32_t two = (bits[b * 8 + (p >> 5)] >> (p & 31)) & 3u;     /* p is even, so both bits sit in one word */
-        uint32_t v = (two & 1u) | (two & 2u) << 7;
-        if (p == 0) v |= phase;
-        out[hw] = (uint16_t)v;
+    /* expand: staging byte j = bit j of the string */
+    uint8_t *stage = reinterpret_cast<uint8_t *>(x);
+    const uint8_t *bytes = reinterpret_cast<const uint8_t *>(bits);
+    _Pragma("unroll 1") for (int g = lane; g < OBS_STAGE / 8; g += 32) {
+        uint64_t t = ((uint64_t)bytes[g] * 0x0101010101010101ull) & 0x8040201008040201ull;
+        t = ((t + 0x7F7F7F7F7F7F7F7Full) >> 7) & 0x0101010101010101ull;
+        reinterpret_cast<uint64_t *>(stage)[g] = t;
     }
+    __syncwarp();
+    if (lane < CC4_N_BLUE) stage[mis + CC4_OBS_LEN * lane] = s->phase;   /* element 0 of every vector is the mission phase */
+    __syncwarp();
+    /* copy: 16-byte lines, aligned on both sides */
+    uint8_t *gline = obs_base + (goff - (size_t)mis);
+    const int end = mis + OBS_BYTES;
+    _Pragma("unroll 1") for (int q = lane; q < OBS_STAGE / 16; q += 32) {
+        int lo = q * 16;
+        if (lo >= mis && lo + 16 <= end) reinterpret_cast<uint4 *>(gline)[q] = reinterpret_cast<const uint4 *>(stage)[q];
+        else {
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) if (lo + k >= mis && lo + k < end) *reinterpret_cast<uint16_t *>(gline + lo + k) = *reinterpret_cast<const uint16_t *>(stage + lo + k);
+        }
+    }
+    __syncwarp();
 }
 __device__ void w_write_mask(const Cc4Dyn *s, uint8_t *mask)
 {
@@ -216,11 +245,11 @@ __device__ void w_scan_sessions(Cx c)
 __device__ void w_build_hostagents(Cx c)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
-    x->hostagents[lane_id()] = 0;
+    x->g.hostagents[lane_id()] = 0;
     __syncwarp();
     _Pragma("unroll 1") for (int i = lane_id(); i < s->n_sess; i += 32) {
         uint32_t h = S_HOST(s->sess[i]);
-        atomicOr(&x->hostagents[h >> 2], (1u << SF_AGENT(s->sessf[i])) << ((h & 3) * 8));
+        atomicOr(&x->g.hostagents[h >> 2], (1u << SF_AGENT(s->sessf[i])) << ((h & 3) * 8));
     }
     __syncwarp();
 }
@@ -240,7 +269,7 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
     _Pragma("unroll 1") for (int i = lane; i <= NAG; i += 32) x->ctr[i] = 0;
     if (lane < 8) { x->n_oent[lane] = 0; x->have_first[lane] = 0; x->succ0[lane] = SUCC_UNKNOWN; x->has_act0[lane] = 0; }
     (&x->ssmask[0][0])[lane] = 0;
-    if (lane < 12) x->blk_id[lane] = 0xFFFFFFFFu;
+    if (lane <= CC4_NRED) x->blk_id[lane] = 0xFFFFFFFFu;
     if (lane < 16) (&x->ssmask[0][0])[32 + lane] = 0;
     __syncwarp();
     _Pragma("unroll 1") for (int i = lane; i < CC4_NRED * CC4_SS_CAP; i += 32) {
@@ -309,6 +338,14 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
     /* green agents, lane per agent (EnterpriseGreenAgent.py:42-78); the phishing side effect is order dependent and
        replayed below in agent order */
     {
+        if (lane < 8) {     /* GreenAccessService destination table of this tick's phase, one lane per source subnet */
+            uint32_t allowed = c_green_allowed[s->phase][lane];
+            uint64_t cum = 0; uint32_t tot = 0;
+#pragma unroll
+            for (int sn = 0; sn < 8; sn++) { if (allowed >> sn & 1) tot += s->nserver[sn]; cum |= (uint64_t)tot << (8 * sn); }
+            x->g.as_cum[lane] = cum;
+        }
+        __syncwarp();
         int rew = 0;
         uint32_t *ev_words = reinterpret_cast<uint32_t *>(s->ev);
         const int ng = s->ngreen;
@@ -318,7 +355,7 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
             int gr = g < ng ? green_tick(c, g, ev_words) : 0;
             rew -= gr & 0xFF;
             uint32_t bal = __ballot_sync(0xFFFFFFFFu, (gr & GREEN_PHISH) != 0);
-            if (lane == 0) x->phish[k] = bal;
+            if (lane == 0) x->g.phish[k] = bal;
             any_phish |= bal;
         }
 #pragma unroll
@@ -328,11 +365,25 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
         if (any_phish) {
             w_build_hostagents(c);
             if (lane == 0)
-                _Pragma("unroll 1") for (int k = 0; k < 3; k++) { uint32_t m = x->phish[k]; while (m) { int b = __ffs(m) - 1; m &= m - 1; do_phishing(c, k * 32 + b); } }
+                _Pragma("unroll 1") for (int k = 0; k < 3; k++) { uint32_t m = x->g.phish[k]; while (m) { int b = __ffs(m) - 1; m &= m - 1; do_phishing(c, k * 32 + b); } }
             __syncwarp();
         }
     }
     PHASE_SYNC(3);
+    /* resolve the session each due red action names (lane per pool entry); valid until a session is deleted */
+    _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
+        uint32_t w = x->subw[A_RED0 + r], id = IP_SESSION(w);
+        int at = -1;
+        if (!x->dropped[A_RED0 + r] && IP_CODE(w) != AC_SLEEP && IP_CODE(w) != AC_INVALID)
+            _Pragma("unroll 1") for (int base = 0; base < s->n_sess && at < 0; base += 32) {
+                int i = base + lane;
+                uint32_t m = __ballot_sync(0xFFFFFFFFu, i < s->n_sess && SF_AGENT(s->sessf[i]) == (uint32_t)r && S_ID(s->sess[i]) == id);
+                if (m) at = base + __ffs(m) - 1;
+            }
+        if (lane == 0) x->act_si[r] = (int16_t)at;
+    }
+    if (lane == 0) x->sess_moved = 0;
+    __syncwarp();
     if (lane == 0) {
         _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
             int a = A_RED0 + r;
@@ -398,7 +449,7 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
 /* ------------------------------------------------------------------------------------------------ */
 /* kernels                                                                                          */
 /* ------------------------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, CC4_MIN_BLOCKS)
 k_step(Params p, int env0, const int32_t *actions, const uint8_t *msgs, uint8_t *obs, float *reward, uint8_t *done, int flags)
 {
     int env = env0 + blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);   /* env0: first episode of this launch (chunked host path) */
@@ -409,13 +460,13 @@ k_step(Params p, int env0, const int32_t *actions, const uint8_t *msgs, uint8_t 
     w_tick(c, valid ? actions + (size_t)env * 5 : nullptr, valid && msgs ? msgs + (size_t)env * 5 : nullptr,
            valid && (flags & CC4_STEP_REWARD) && reward ? reward + env : nullptr, valid && done ? done + env : nullptr);
     PHASE_SYNC(7);
-    if (valid && (flags & CC4_STEP_OBS) && obs) w_write_obs(&w->dyn, w->x.obsbits, obs + (size_t)env * CC4_N_BLUE * CC4_OBS_LEN);
+    if (valid && (flags & CC4_STEP_OBS) && obs) w_write_obs(&w->dyn, &w->x, obs, env);
     w_store(p.dyn + env, &w->dyn);
 }
 
 /* fused ticks with the benchmark's synthetic blue policy: index ~ U{0..81} (agents 0-3) / U{0..241} (agent 4),
  * Philox keyed (policy_seed, episode, tick) exactly as oracle/cc4_oracle.c cc4o_run_episodes */
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, CC4_MIN_BLOCKS)
 k_rollout(Params p, int n_ticks, uint32_t pk0, uint32_t pk1, float *reward_sum, int flags)
 {
     int env = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -473,7 +524,6 @@ __device__ int gen_pid(Cx c, ResetTmp *t)
 }
 __device__ void gen_host(Cx c, ResetTmp *t, int slot)
 {   /* _generate_linux_host_services :530-561 + _generate_linux_host_processes :580-629 */
-    Cc4Dyn *s = DYN(c);
     int sn = slot >> 4, n = 0;
     uint64_t v = SVC_EMPTY;
     uint32_t pids[9]; int codes[9];
@@ -490,7 +540,7 @@ __device__ void gen_host(Cx c, ResetTmp *t, int slot)
     }
     _Pragma("unroll 1") for (int i = 0; i < n; i++) { v = svc_set(v, i, (uint32_t)codes[i] | 5u << 4); t->procs[slot][i] = P_MAKE(pids[i], codes[i], 0, 1); }
     t->np[slot] = (uint8_t)n;
-    s->svc64[slot] = v;
+    WC(c)->k->svc64[slot] = v;
 }
 __device__ int tmp_create_pid(Cx c, ResetTmp *t, int slot)
 {
@@ -515,11 +565,11 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
     _Pragma("unroll 1") for (int i = lane_id(); i < (int)(sizeof(ResetSmem) / 4); i += 32) z[i] = 0;
     __syncwarp();
     Cx c = make_ctx(0, p, env, -1);
-    if (lane_id() < 12) SCR(c)->blk_id[lane_id()] = 0xFFFFFFFFu;
+    if (lane_id() <= CC4_NRED) SCR(c)->blk_id[lane_id()] = 0xFFFFFFFFu;
     __syncwarp();
     if (lane_id() == 0) {
         Cc4Dyn *s = DYN(c); ResetTmp *t = &rs->t; Cc4Stat *st = WC(c)->st;
-        _Pragma("unroll 1") for (int h = 0; h < 128; h++) s->svc64[h] = SVC_EMPTY;
+        _Pragma("unroll 1") for (int h = 0; h < 128; h++) WC(c)->k->svc64[h] = SVC_EMPTY;
         _Pragma("unroll 1") for (int a = 0; a < 16; a++) s->inprog[a] = IP_NONE;
         /* hosts, EnterpriseScenarioGenerator._generate_hosts :312-371 */
         _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) {
@@ -570,10 +620,14 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
         }
         /* process lists + Host.create_backup Host.py:316-371 */
         _Pragma("unroll 1") for (int h = 0; h < 128; h++) {
-            s->nproc[h] = t->np[h]; st->o_nproc[h] = t->np[h];
-            _Pragma("unroll 1") for (int i = 0; i < t->np[h]; i++) { WC(c)->k->procs[h][i] = t->procs[h][i]; st->o_procs[h][i] = t->procs[h][i]; }
-            st->o_svc64[h] = s->svc64[h];
+            st->o_nproc[h] = t->np[h];
+            WC(c)->k->pdir[h] = PD_MAKE(h * CC4_OSLAB, t->np[h], 3);
+            uint32_t mx = 0;
+            _Pragma("unroll 1") for (int i = 0; i < t->np[h]; i++) { uint32_t w = t->procs[h][i]; WC(c)->k->parena[h * CC4_OSLAB + i] = w; st->o_procs[h][i] = w; if (P_PID(w) > mx) mx = P_PID(w); }
+            WC(c)->k->pmax[h] = (uint16_t)mx;
+            st->o_svc64[h] = WC(c)->k->svc64[h];
         }
+        WC(c)->k->arena_top = 128 * CC4_OSLAB;
         _Pragma("unroll 1") for (int i = 0; i < 16; i++) st->router_pid[i] = t->router_pid[i];
         /* initial knowledge: AgentInterface.set_init_obs AgentInterface.py:110-117 with the OSINT of :784-785 */
         _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) { int h = st->red_start[r]; set128(s->ip_known[r], h); set128(s->hn_known[r], h); s->sn_known[r] |= (uint16_t)(1u << (h >> 4)); }
@@ -583,7 +637,7 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
         if (WC(c)->rng_mode == 1 && WC(c)->n_segs > 0 && SCR(c)->ctr[NAG] != WC(c)->seg[1] - WC(c)->seg[0]) fail(c, CC4_E_TAPE_LEFT);
     }
     __syncwarp();
-    if (valid && obs) w_write_obs(&w->dyn, w->x.obsbits, obs + (size_t)env * CC4_N_BLUE * CC4_OBS_LEN);
+    if (valid && obs) w_write_obs(&w->dyn, &w->x, obs, env);
     if (valid && mask) w_write_mask(&w->dyn, mask + (size_t)env * CC4_N_BLUE * CC4_MASK_LEN);
     w_store(p.dyn + env, &w->dyn);
 }
@@ -820,16 +874,18 @@ extern "C" int cc4_export_canon(cc4_handle *h, int env, int32_t *out, int cap, i
             int sn = slot >> 4, k = slot & 15;
             if (!(k < 6 ? k < d.nserver[sn] : (k - 6) < d.nuser[sn])) continue;
             PUT(slot); PUT(d.ev[slot]);
+            const uint32_t *pp = cold.parena + PD_OFF(cold.pdir[slot]);
+            const int cnt = (int)PD_CNT(cold.pdir[slot]);
             int np = 0;
-            for (int i = 0; i < d.nproc[slot]; i++) np += !P_DEAD(cold.procs[slot][i]);
+            for (int i = 0; i < cnt; i++) np += !P_DEAD(pp[i]);
             PUT(np);
-            for (int i = 0; i < d.nproc[slot]; i++) { uint32_t w = cold.procs[slot][i]; if (P_DEAD(w)) continue; PUT(P_PID(w)); PUT(P_KIND(w)); PUT(P_ROOT(w)); }
-            uint64_t v = d.svc64[slot];
+            for (int i = 0; i < cnt; i++) { uint32_t w = pp[i]; if (P_DEAD(w)) continue; PUT(P_PID(w)); PUT(P_KIND(w)); PUT(P_ROOT(w)); }
+            uint64_t v = cold.svc64[slot];
             int ns = 0; while (ns < 9 && (SVC_ENTRY(v, ns) & 15u) != 15u) ns++;
             PUT(ns);
             for (int i = 0; i < ns; i++) {
                 uint32_t e = SVC_ENTRY(v, i), code = e & 15u, pid = 0;
-                for (int j = 0; j < d.nproc[slot]; j++) if (P_KIND(cold.procs[slot][j]) == code && P_SVC(cold.procs[slot][j])) pid = P_PID(cold.procs[slot][j]);
+                for (int j = 0; j < cnt; j++) if (P_KIND(pp[j]) == code && P_SVC(pp[j])) pid = P_PID(pp[j]);
                 PUT(code); PUT(pid); PUT(!(code == K_OT && (v & SVC_OT_STOPPED))); PUT((e >> 4) * 20);
             }
         } else {

@@ -17,14 +17,14 @@
 #define CC4_NBLUE 5
 #define CC4_MAXGREEN 80
 
-#define CC4_PSLAB 24         /* process entries per host (tombstones included) */
 #define CC4_OSLAB 8          /* processes a host can have at reset: <= 5 services + blue + green + red session */
+#define CC4_ARENA 8192       /* process entries per episode: 128 home slabs of CC4_OSLAB + growth blocks (see Cc4Cold) */
 #define CC4_SESS_CAP 160     /* red sessions per episode (all six agents) */
 #define CC4_PORT_CAP 384     /* (red abstract session, host) known-port entries */
 #define CC4_SUS_CAP 256      /* blue suspicious-pid entries */
 #define CC4_FSM_CAP 64       /* hosts known to one red agent's FSM */
 #define CC4_SS_CAP 48        /* server_session ids known to one red agent */
-#define CC4_OENT_CAP 64      /* observation entries of one red agent in one tick */
+#define CC4_OENT_CAP 48      /* observation entries of one red agent in one tick */
 
 /* process entry (Simulator/Process.py:12): pid | kind<<16 | root<<20 | svc<<21 | dead<<22
  * svc  = this process backs host.services[kind] (Host.py:124);
@@ -93,7 +93,6 @@ enum { K_SSHD, K_OT, K_APACHE2, K_MYSQLD, K_SMTP, K_D_APACHE, K_D_TOMCAT, K_D_HA
 
 /* HOT record: read and written every tick, staged through shared memory by the warp that owns the episode. */
 struct __attribute__((aligned(16))) Cc4Dyn {
-    uint64_t svc64[128];
     /* ---- red sessions: one pool in creation order; an agent's state.sessions[agent] dict order is the pool order */
     uint32_t sess[CC4_SESS_CAP];
     /* ---- red knowledge (Shared/ActionSpace.py:170-212) ---- */
@@ -106,7 +105,6 @@ struct __attribute__((aligned(16))) Cc4Dyn {
     uint8_t ev[144];                    /* 137 used */
     uint8_t sessf[CC4_SESS_CAP];
     uint8_t ss[CC4_NRED][CC4_SS_CAP];   /* known server_session ids in dict order */
-    uint8_t nproc[128];                 /* entries used in Cc4Cold.procs[h] (tombstones included) */
     uint8_t green_host[CC4_MAXGREEN];   /* static after reset, staged with the record because every tick needs it */
     uint8_t n_ss[8];
     uint8_t n_fsm[8];
@@ -122,10 +120,28 @@ struct __attribute__((aligned(16))) Cc4Dyn {
 /* COLD record: dynamic state that only the rare transitions touch (process lists on exploit / decoy / remove / restore,
  * known ports on scans and exploits, suspicious pids on detection and Remove).  It stays in HBM and is accessed in place
  * by the lane that executes the transition; it is NOT streamed every tick. */
+/* process directory entry of one host: arena offset | count<<13 | log2(capacity)<<23 */
+#define PD_OFF(w) ((w) & 0x1FFFu)
+#define PD_CNT(w) (((w) >> 13) & 0x3FFu)
+#define PD_CAPL(w) (((w) >> 23) & 0xFu)
+#define PD_MAKE(off, cnt, capl) ((uint32_t)(off) | (uint32_t)(cnt) << 13 | (uint32_t)(capl) << 23)
+#define PD_MAXCNT 1023
 struct __attribute__((aligned(16))) Cc4Cold {
-    uint32_t procs[128][CC4_PSLAB];     /* host.processes in order (Host.py:117) */
+    /* host.processes in order (Host.py:117).  Host h starts in its home slab parena[h*8 .. h*8+8); a list that outgrows its
+     * block moves to a block of twice the size at arena_top (old blocks are not recycled; Restore returns the host to
+     * its home slab).  The reference puts no bound on the list: a blue agent can deploy a decoy on the same host every
+     * second tick (VsftpdDecoyFactory is always compatible, DecoyVsftpd.py:17-20), ~250 per episode; 8192 entries hold
+     * five such hosts (5 x 1008 entries of growth blocks) next to the 1024 home entries. */
+    uint32_t parena[CC4_ARENA];
+    uint32_t pdir[128];
+    /* host.services (svc64 encoding above): read by one green agent per host per tick (GreenLocalWork), written by decoys,
+     * Impact / DegradeServices and Restore: sparse, so it is accessed in place instead of being staged (1 KB of shared
+     * memory per warp buys more resident warps than the staging saved latency) */
+    uint64_t svc64[128];
     uint32_t ports[CC4_PORT_CAP];
     uint32_t sus[CC4_SUS_CAP];
+    uint16_t pmax[128];                 /* largest live pid per host (Host.create_pid Host.py:198-200 starts from it) */
+    uint32_t arena_top, pad[3];
 };
 
 struct __attribute__((aligned(16))) Cc4Stat {

@@ -24,7 +24,7 @@
 #define A_BLUE0 0
 #define A_RED0 5
 #define A_GREEN0 11
-#define MAXPROC 64
+#define MAXPROC 640    /* the reference puts no bound on host.processes: one decoy every second tick is possible (DecoyVsftpd.py:17-20) */
 #define MAXSVC 9
 #define MAXSESS 160
 #define MAXSUS 256

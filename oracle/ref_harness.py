@@ -401,6 +401,8 @@ def blue_policy(kind: str, rng: np.random.Generator, mask: np.ndarray):
     if kind == "masked":          # uniform over valid entries only
         return [int(rng.choice(np.flatnonzero(mask[i, :N_ACTIONS[i]]))) for i in range(5)], \
                [int(rng.integers(0, 256)) for _ in range(5)]
+    if kind == "decoy":           # every agent deploys a decoy on server_host_0 of its first subnet, every tick (process-list growth)
+        return [66, 66, 66, 66, 194], [0] * 5
     raise ValueError(kind)
 
 

@@ -117,6 +117,58 @@ def test_philox_mode_matches_oracle(n, ticks, seed):
     assert np.array_equal(flags & ~np.uint32(4), oflags & ~4), (flags, oflags)   # capacity limits differ by design
 
 
+def test_repeated_decoys_on_one_host_grow_the_process_list():
+    """The reference lets a blue agent deploy a decoy on the same host every second tick (VsftpdDecoyFactory is always
+    compatible, DecoyVsftpd.py:17-20): ~250 processes on one host by the end of an episode.  The engine's process arena
+    must follow the oracle exactly through that growth (constant-action policies do this, e.g. an argmax of a
+    random-init MLP), with and without other agents' random actions interleaved."""
+    n, seed, ticks = 12, 17, 499
+    env = _engine(n, device=0, seed=seed, steps=500)
+    env.reset()
+    refs = [O.OracleEnv(seed=seed, episode=i, steps=500) for i in range(n)]
+    for r in refs:
+        r.reset()
+    g = np.random.default_rng(seed)
+    decoy0 = np.array([66, 66, 66, 66, 194], dtype=np.int32)      # DeployDecoy on server_host_0 of the agent's first subnet
+    for t in range(ticks):
+        acts = np.tile(decoy0, (n, 1))
+        rnd = np.stack([g.integers(0, k, n) for k in (82, 82, 82, 82, 242)], 1).astype(np.int32)
+        acts[n // 2:, 1::2] = rnd[n // 2:, 1::2]                   # second half: agents 1 and 3 act randomly (Restore / Remove mixed in)
+        o, r, d = env.step(torch.from_numpy(acts).cuda())
+        o, r, d = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
+        for i, ref in enumerate(refs):
+            rc, oo, rr, dd = ref.step(acts[i])
+            assert np.array_equal(o[i], oo) and r[i] == rr and d[i] == dd, f"episode {i} tick {t}"
+        if t % 50 == 49 or t == ticks - 1:
+            for i in range(n):
+                exp, got = refs[i].export(), env.export_canon(i)
+                assert np.array_equal(exp, got), f"episode {i} tick {t}: {_diff(exp, got)}"
+    assert not env.error_flags().any()
+    assert all(r.error()[0] == 0 for r in refs)
+    c = canon.decode(env.export_canon(0))
+    assert max(len(h["procs"]) for h in c["hosts"].values()) > 200
+
+
+@pytest.mark.parametrize("n", [1, 5, 2049, 16389])
+def test_host_buffer_step_ragged_batches(n):
+    """cc4_step_host cuts the batch into pipelined chunks: sizes around the chunk boundaries must equal the device path."""
+    a = _engine(n, device=0, seed=3)
+    b = _engine(n, device=0, seed=3)
+    a.reset(), b.reset()
+    g = np.random.default_rng(1)
+    for t in range(6):
+        acts = np.stack([g.integers(0, k, n) for k in (82, 82, 82, 82, 242)], 1).astype(np.int32)
+        msgs = g.integers(0, 256, (n, 5)).astype(np.uint8)
+        o1, r1, d1 = a.step(torch.from_numpy(acts).cuda(), torch.from_numpy(msgs).cuda())
+        o2, r2, d2 = b.step_host(torch.from_numpy(acts).pin_memory(), torch.from_numpy(msgs).pin_memory())
+        assert torch.equal(o1.cpu(), o2) and torch.equal(r1.cpu(), r2) and torch.equal(d1.cpu(), d2)
+    for i in {0, n // 2, n - 1}:
+        assert np.array_equal(a.export_canon(i), b.export_canon(i))
+    oh, mh = b.reset_host()
+    od, md = a.reset()
+    assert torch.equal(od.cpu(), oh) and torch.equal(md.cpu(), mh.bool())
+
+
 def test_host_buffer_step_equals_device_step():
     n = 64
     a = _engine(n, device=0, seed=3)
