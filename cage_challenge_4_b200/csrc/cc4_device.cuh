@@ -134,7 +134,7 @@ struct WarpCtx {
     const cc4_draw *tape; const uint32_t *seg; uint32_t n_segs;
     int tick;                 /* state step_count at the start of the tick; -1 during reset */
     int steps, rng_mode;
-    uint32_t k0, k1, ep_lo, pad;
+    uint32_t k0, k1, ep_lo; int env;
 };
 struct __align__(16) WarpSmem {
     Cc4Dyn dyn;

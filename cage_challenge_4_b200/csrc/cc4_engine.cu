@@ -34,6 +34,7 @@ struct Params {
     int n_envs, n_alloc, steps, rng_mode;   /* n_alloc = n_envs rounded up to a whole block: every warp of the grid owns an episode */
     uint32_t k0, k1hi; uint64_t first_episode;
     const cc4_draw *tape; const uint32_t *seg_off; uint32_t n_segs;
+    unsigned long long *phase_clk;   /* [n_alloc][8][2] busy / barrier-wait cycles per phase (only in -DCC4_PHASE_CLOCKS builds) */
 };
 
 /* ---- record movement: 128-bit coalesced ---- */
@@ -63,8 +64,10 @@ __device__ __forceinline__ Cx make_ctx(int warp, const Params &p, int env, int t
         g->st = p.stat + env; g->k = p.cold + env;
         g->steps = p.steps; g->rng_mode = p.rng_mode;
         g->k0 = p.k0; g->k1 = p.k1hi ^ (uint32_t)(ep >> 32); g->ep_lo = (uint32_t)ep;
-        g->tape = p.tape; g->seg = p.seg_off ? p.seg_off + (size_t)env * (p.n_segs + 1) : nullptr; g->n_segs = p.n_segs;
-        g->tick = tick;
+        /* padding episodes (n_envs..n_alloc) have no tape: every draw of theirs fails with CC4_E_TAPE_END and yields 0 */
+        const bool has_tape = p.seg_off && env < p.n_envs;
+        g->tape = p.tape; g->seg = has_tape ? p.seg_off + (size_t)env * (p.n_segs + 1) : nullptr; g->n_segs = has_tape ? p.n_segs : 0;
+        g->tick = tick; g->env = env;
     }
     __syncwarp();
     return c;
@@ -259,12 +262,21 @@ __device__ void w_build_hostagents(Cx c)
 /* ------------------------------------------------------------------------------------------------ */
 /* PHASE_SYNC keeps the warps of a block in the same phase of the tick: they then share the instruction cache lines of
  * that phase instead of thrashing it (ncu: stall_no_inst was the top stall reason without it). */
+#ifdef CC4_PHASE_CLOCKS   /* profiling build: per-warp busy and barrier-wait cycles of every phase (tools/phase_clocks.py) */
+__device__ unsigned long long *g_phase_clk;
+#define PHASE_SYNC(i) do { if ((CC4_SYNC_MASK >> (i)) & 1) { long long t1_ = clock64(); __syncthreads(); long long t2_ = clock64(); \
+    if (lane_id() == 0 && pc_clk) { pc_clk[2 * (i)] += (unsigned long long)(t1_ - pc_t0); pc_clk[2 * (i) + 1] += (unsigned long long)(t2_ - t1_); } pc_t0 = t2_; } } while (0)
+#define PHASE_CLOCK_BEGIN(envidx) unsigned long long *pc_clk = g_phase_clk ? g_phase_clk + (size_t)(envidx) * 16 : nullptr; long long pc_t0 = clock64()
+#else
 #define PHASE_SYNC(i) do { if ((CC4_SYNC_MASK >> (i)) & 1) __syncthreads(); } while (0)
+#define PHASE_CLOCK_BEGIN(envidx) do { } while (0)
+#endif
 constexpr int N_PHASE_SYNC = __builtin_popcount(CC4_SYNC_MASK & 0x7F);
 __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep */, const uint8_t *msgs /* [5] or null */, float *reward_out, uint8_t *done_out)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     const int lane = lane_id();
+    PHASE_CLOCK_BEGIN(WC(c)->env);
     WC(c)->tick = s->step;
     _Pragma("unroll 1") for (int i = lane; i <= NAG; i += 32) x->ctr[i] = 0;
     if (lane < 8) { x->n_oent[lane] = 0; x->have_first[lane] = 0; x->succ0[lane] = SUCC_UNKNOWN; x->has_act0[lane] = 0; }
@@ -459,7 +471,10 @@ k_step(Params p, int env0, const int32_t *actions, const uint8_t *msgs, uint8_t 
     w_load(&w->dyn, p.dyn + env);
     w_tick(c, valid ? actions + (size_t)env * 5 : nullptr, valid && msgs ? msgs + (size_t)env * 5 : nullptr,
            valid && (flags & CC4_STEP_REWARD) && reward ? reward + env : nullptr, valid && done ? done + env : nullptr);
-    PHASE_SYNC(7);
+    {
+        PHASE_CLOCK_BEGIN(env);
+        PHASE_SYNC(7);      /* phase 7 of the profile = the barrier wait only; the observation writer + store follow it */
+    }
     if (valid && (flags & CC4_STEP_OBS) && obs) w_write_obs(&w->dyn, &w->x, obs, env);
     w_store(p.dyn + env, &w->dyn);
 }
@@ -833,6 +848,28 @@ extern "C" int cc4_rollout(cc4_handle *h, int n_ticks, uint64_t policy_seed, flo
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return CC4_OK;
+}
+
+/* profiling builds only (-DCC4_PHASE_CLOCKS): out_host uint64 [n_envs][8][2] accumulated busy / barrier-wait cycles */
+extern "C" int cc4_phase_clocks(cc4_handle *h, unsigned long long *out_host, int reset)
+{
+#ifdef CC4_PHASE_CLOCKS
+    if (!h || !out_host) return set_err(CC4_ERR_ARG, "cc4_phase_clocks: null%s", "");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    size_t bytes = (size_t)h->p.n_alloc * 16 * sizeof(unsigned long long);
+    if (!h->p.phase_clk) {
+        CUDA_TRY(cudaMalloc(&h->p.phase_clk, bytes));
+        CUDA_TRY(cudaMemset(h->p.phase_clk, 0, bytes));
+        CUDA_TRY(cudaMemcpyToSymbol(g_phase_clk, &h->p.phase_clk, sizeof(void *)));
+    }
+    CUDA_TRY(cudaMemcpy(out_host, h->p.phase_clk, (size_t)h->p.n_envs * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (reset) CUDA_TRY(cudaMemset(h->p.phase_clk, 0, bytes));
+    return CC4_OK;
+#else
+    (void)h; (void)out_host; (void)reset;
+    return set_err(CC4_ERR_STATE, "cc4_phase_clocks: this build has no phase clocks (-DCC4_PHASE_CLOCKS)%s", "");
+#endif
 }
 
 extern "C" int cc4_launch_count(cc4_handle *h, uint64_t *out)

@@ -110,6 +110,11 @@ int cc4_export_canon(cc4_handle *h, int env, int32_t *out_host, int cap, int *n_
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int cc4_launch_count(cc4_handle *h, uint64_t *out);
 
+/* Profiling builds only (compiled with -DCC4_PHASE_CLOCKS; otherwise CC4_ERR_STATE): accumulated busy / barrier-wait
+ * cycles of every phase of the tick per episode, out_host uint64 [n_envs][8][2]; reset != 0 clears the counters.
+ * The first call arms the counters.  Synchronises the device. */
+int cc4_phase_clocks(cc4_handle *h, unsigned long long *out_host, int reset);
+
 const char *cc4_last_error(void);
 
 #ifdef __cplusplus

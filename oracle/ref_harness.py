@@ -392,8 +392,32 @@ SLEEP_INDEX = (49, 49, 49, 49, 145)  # BlueFixedActionWrapper._populate_action_s
 N_ACTIONS = (82, 82, 82, 82, 242)
 
 
-def blue_policy(kind: str, rng: np.random.Generator, mask: np.ndarray):
+def blue_policy(kind: str, rng: np.random.Generator, mask: np.ndarray, obs: np.ndarray | None = None):
     """Synthetic blue inputs (NOT drawn from the environment RNG)."""
+    if kind in ("reactive", "lockdown"):
+        # reactive: answer alerts in the observation vector (BlueFlatWrapper.py:172-256: per own subnet 27 policy bits,
+        # 16 malicious-process flags, 16 network-connection flags) with Remove / Restore / Analyse on the flagged host,
+        # otherwise decoys and the odd traffic-control action.  lockdown: the same with frequent Block/Allow.
+        acts = []
+        for b in range(5):
+            n = 3 if b == 4 else 1
+            H, T = 16 * n, 8 * n
+            flagged = [i * 16 + h for i in range(n) for h in range(16)
+                       if obs[b, 1 + 59 * i + 27 + h] or obs[b, 1 + 59 * i + 43 + h]]
+            u = rng.random()
+            p_traffic = 0.35 if kind == "lockdown" else 0.08
+            if flagged and u < 0.7:
+                h = int(rng.choice(flagged))
+                v = rng.random()
+                a = (H + 1 + h) if v < 0.5 else (2 * H + 1 + h) if v < 0.8 else h     # Remove / Restore / Analyse
+            elif u < 0.7 + p_traffic:
+                a = 3 * H + 2 + int(rng.integers(0, 2 * T))                            # Allow / Block
+            elif u < 0.9:
+                a = 3 * H + 2 + 2 * T + int(rng.integers(0, H))                        # DeployDecoy
+            else:
+                a = H if rng.random() < 0.5 else 3 * H + 1                             # Monitor / Sleep
+            acts.append(a)
+        return acts, [int(rng.integers(0, 256)) for _ in range(5)]
     if kind == "sleep":
         return list(SLEEP_INDEX), [0] * 5
     if kind == "random":          # uniform over the whole index range (masked-out entries act as Sleep)
@@ -417,7 +441,7 @@ def run_episode(seed: int, policy: str = "sleep", steps: int = 500, n_ticks: int
     canon = [ep.canon()] if with_state else []
     acts, msgs, rews, dones = [], [], [], []
     for _ in range(n_ticks):
-        a, m = blue_policy(policy, prng, mask)
+        a, m = blue_policy(policy, prng, mask, obs[-1])
         o, r, term, trunc, _ = ep.step(a, m)
         acts.append(a)
         msgs.append(m)
