@@ -3,10 +3,14 @@
  *
  * One warp owns one episode; the record lives in shared memory for the duration of the kernel.  The functions in
  * this file fall in two groups:
- *   - warp-cooperative phases (all 32 lanes call them, names start with w_): record load/store, green agents
- *     (lane per agent), end-turn Monitor (lane per host), observation vectors (lane per element);
- *   - the order-dependent, rare transitions (blue actions, red kill chain, phishing, reassignment, RedSessionCheck,
- *     FSM bookkeeping) that the reference executes strictly in agent order: run by lane 0 only.
+ *   - lane-parallel phases (names start with w_): record load/store, green agents (lane per agent), end-turn Monitor
+ *     (lane per host), observation vectors; red policy + FSM digest (lane per red agent);
+ *   - the order-dependent transitions (blue actions, red kill chain, phishing, reassignment, RedSessionCheck) that the
+ *     reference executes strictly in agent order.  These run WARP-UNIFORM: all 32 lanes of the episode's warp execute
+ *     the same control flow on the same values (scalar stores write the same value from every lane), and every scan
+ *     over a list (session pool, process list, known ports, suspicious pids, observation entries) is done 32 entries
+ *     at a time with ballots / reductions.  Functions marked [uniform] must be called by the whole converged warp with
+ *     identical arguments; functions marked [lane] may be called by any subset of lanes.
  * Citations are file:line under /root/reference/CybORG/ (never read at run time).
  */
 #pragma once
@@ -152,6 +156,7 @@ typedef uint32_t Cx;
 #define WC(c) (&WS(c)->c)
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 __device__ __forceinline__ void fail(Cx c, uint32_t flag) { atomicOr(&DYN(c)->err, flag); }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -234,9 +239,13 @@ __device__ __forceinline__ int blue_of_subnet(int sn) { return sn <= S_OZB ? sn 
 __device__ __forceinline__ bool bit128(const uint32_t *b, int i) { return (b[i >> 5] >> (i & 31)) & 1u; }
 __device__ __forceinline__ void set128(uint32_t *b, int i) { b[i >> 5] |= 1u << (i & 31); }
 
-/* ---- process lists (lane 0; they live in the cold record's arena, cc4_state.h) ---- */
+/* ---- process lists [uniform] (they live in the cold record's arena, cc4_state.h) ---- */
+#define FULLMASK 0xFFFFFFFFu
 #define NPROC(c, h) ((int)PD_CNT(WC(c)->k->pdir[h]))
 #define PROCS(c, h) (WC(c)->k->parena + PD_OFF(WC(c)->k->pdir[h]))
+#define P_NONE P_DEADBIT    /* filler for lanes past the end of a list: looks like a tombstone */
+/* port class of a process kind (canon PORT_BIT), 15 = does not listen */
+__device__ __forceinline__ uint32_t kind_portbit(uint32_t kind) { return (uint32_t)(0xFFF245243210ull >> (4 * kind)) & 15u; }
 __device__ __noinline__ void proc_append(Cx c, int h, uint32_t w)
 {   /* host.processes.append */
     Cc4Cold *k = WC(c)->k;
@@ -244,7 +253,8 @@ __device__ __noinline__ void proc_append(Cx c, int h, uint32_t w)
     if (n == (1u << capl)) {            /* block full: move the list to a block of twice the size */
         uint32_t top = k->arena_top, ncap = 2u << capl;
         if (top + ncap > CC4_ARENA || n >= PD_MAXCNT) { fail(c, CC4_E_CAPACITY); return; }
-        _Pragma("unroll 1") for (uint32_t i = 0; i < n; i++) k->parena[top + i] = k->parena[off + i];
+        _Pragma("unroll 1") for (uint32_t i = lane_id(); i < n; i += 32) k->parena[top + i] = k->parena[off + i];
+        __syncwarp();
         k->arena_top = top + ncap; off = top; capl++;
     }
     k->parena[off + n] = w;
@@ -254,25 +264,42 @@ __device__ __noinline__ void proc_append(Cx c, int h, uint32_t w)
 __device__ __noinline__ void proc_rescan_max(Cx c, int h)
 {
     Cc4Cold *k = WC(c)->k;
-    const uint32_t *pp = k->parena + PD_OFF(k->pdir[h]); const int n = (int)PD_CNT(k->pdir[h]);
+    const uint32_t d = k->pdir[h];
+    const uint32_t *pp = k->parena + PD_OFF(d); const int n = (int)PD_CNT(d);
     uint32_t mx = 0;
-    _Pragma("unroll 1") for (int i = 0; i < n; i++) { uint32_t w = pp[i]; if (!P_DEAD(w) && P_PID(w) > mx) mx = P_PID(w); }
+    _Pragma("unroll 1") for (int i = lane_id(); i < n; i += 32) { uint32_t w = pp[i]; if (!P_DEAD(w) && P_PID(w) > mx) mx = P_PID(w); }
+    mx = __reduce_max_sync(FULLMASK, mx);
     k->pmax[h] = (uint16_t)mx;
 }
 __device__ __noinline__ void proc_delete(Cx c, int h, int idx)
 {
     Cc4Cold *k = WC(c)->k;
-    uint32_t d = k->pdir[h], *pp = k->parena + PD_OFF(d);
-    int n = (int)PD_CNT(d);
+    const uint32_t d = k->pdir[h];
+    uint32_t *pp = k->parena + PD_OFF(d);
+    const int n = (int)PD_CNT(d);
     const uint32_t gone = pp[idx];
-    _Pragma("unroll 1") for (int i = idx; i + 1 < n; i++) pp[i] = pp[i + 1];
+    _Pragma("unroll 1") for (int base = idx; base + 1 < n; base += 32) {
+        const int i = base + lane_id();
+        const bool a = i + 1 < n;
+        uint32_t v = 0;
+        if (a) v = pp[i + 1];
+        __syncwarp();
+        if (a) pp[i] = v;
+        __syncwarp();
+    }
     k->pdir[h] = PD_MAKE(PD_OFF(d), n - 1, PD_CAPL(d));
     if (!P_DEAD(gone) && P_PID(gone) == k->pmax[h]) proc_rescan_max(c, h);
 }
 __device__ __noinline__ int proc_find(Cx c, int h, uint32_t pid)
 {   /* Host.get_process Host.py:251 (tombstones are not processes) */
-    const uint32_t *pp = PROCS(c, h); const int n = NPROC(c, h);
-    _Pragma("unroll 1") for (int i = 0; i < n; i++) { uint32_t w = pp[i]; if (!P_DEAD(w) && P_PID(w) == pid) return i; }
+    const uint32_t d = WC(c)->k->pdir[h];
+    const uint32_t *pp = WC(c)->k->parena + PD_OFF(d); const int n = (int)PD_CNT(d);
+    _Pragma("unroll 1") for (int base = 0; base < n; base += 32) {
+        const int i = base + lane_id();
+        const uint32_t w = i < n ? pp[i] : P_NONE;
+        const uint32_t m = __ballot_sync(FULLMASK, !P_DEAD(w) && P_PID(w) == pid);
+        if (m) return base + __ffs(m) - 1;
+    }
     return -1;
 }
 __device__ __noinline__ int create_pid(Cx c, int actor, int h)
@@ -287,52 +314,93 @@ __device__ __forceinline__ int svc_count(uint64_t v) { int n = 0; while (n < 9 &
 __device__ __forceinline__ bool svc_active(uint64_t v, uint32_t entry) { return !((entry & 15u) == K_OT && (v & SVC_OT_STOPPED)); }
 __device__ __forceinline__ uint64_t svc_set(uint64_t v, int i, uint32_t entry) { return (v & ~(0x7Full << (7 * i))) | ((uint64_t)entry << (7 * i)); }
 
-/* ---- red session pool (lane 0) ---- */
-__device__ __noinline__ int sess_find(const Cc4Dyn *s, int r, int id)
+/* ---- red session pool [uniform] ---- */
+/* first pool index whose (word, flags) satisfies pred, -1 if none */
+template <class Pred> __device__ __forceinline__ int sess_first(const Cc4Dyn *s, Pred pred)
 {
-    _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_ID(s->sess[i]) == (uint32_t)id) return i;
+    const int n = s->n_sess;
+    _Pragma("unroll 1") for (int base = 0; base < n; base += 32) {
+        const int i = base + lane_id();
+        const uint32_t m = __ballot_sync(FULLMASK, i < n && pred(s->sess[i], (uint32_t)s->sessf[i]));
+        if (m) return base + __ffs(m) - 1;
+    }
     return -1;
 }
-__device__ __noinline__ int sess_count_agent(const Cc4Dyn *s, int r) { int n = 0; for (int i = 0; i < s->n_sess; i++) n += SF_AGENT(s->sessf[i]) == (uint32_t)r; return n; }
-__device__ __noinline__ void ports_drop(Cx c, int r, int id)
+/* pool index of the k-th (0-based) entry that satisfies pred, -1 if there are fewer */
+template <class Pred> __device__ __forceinline__ int sess_kth(const Cc4Dyn *s, int k, Pred pred)
 {
+    const int n = s->n_sess;
+    _Pragma("unroll 1") for (int base = 0; base < n; base += 32) {
+        const int i = base + lane_id();
+        const uint32_t m = __ballot_sync(FULLMASK, i < n && pred(s->sess[i], (uint32_t)s->sessf[i]));
+        const int cnt = __popc(m);
+        if (k < cnt) return base + (int)__fns(m, 0, k + 1);
+        k -= cnt;
+    }
+    return -1;
+}
+__device__ __noinline__ int sess_find(const Cc4Dyn *s, int r, int id)
+{
+    return sess_first(s, [=](uint32_t w, uint32_t f) { return SF_AGENT(f) == (uint32_t)r && S_ID(w) == (uint32_t)id; });
+}
+__device__ __noinline__ void ports_drop(Cx c, int r, int id)
+{   /* stable compaction of the known-port entries */
     Cc4Dyn *s = DYN(c);
+    uint32_t *ports = WC(c)->k->ports;
+    const int n = s->n_ports;
     int w = 0;
-    _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = WC(c)->k->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)id) continue; if (w != i) WC(c)->k->ports[w] = p; w++; }
+    _Pragma("unroll 1") for (int base = 0; base < n; base += 32) {
+        const int i = base + lane_id();
+        const uint32_t p = i < n ? ports[i] : 0u;
+        const bool keep = i < n && !(PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)id);
+        const uint32_t m = __ballot_sync(FULLMASK, keep);
+        if (keep) ports[w + __popc(m & ((1u << lane_id()) - 1u))] = p;      /* target index <= i: never ahead of an unread entry */
+        w += __popc(m);
+        __syncwarp();
+    }
     s->n_ports = (uint16_t)w;
+}
+/* remove pool entries [idx] by shifting the tail down (keeps the order) */
+__device__ __forceinline__ void sess_shift_down(Cc4Dyn *s, int idx, int n)
+{
+    _Pragma("unroll 1") for (int base = idx; base + 1 < n; base += 32) {
+        const int i = base + lane_id();
+        const bool a = i + 1 < n;
+        uint32_t v = 0; uint8_t f = 0;
+        if (a) { v = s->sess[i + 1]; f = s->sessf[i + 1]; }
+        __syncwarp();
+        if (a) { s->sess[i] = v; s->sessf[i] = f; }
+        __syncwarp();
+    }
 }
 __device__ __noinline__ void sess_delete(Cx c, int idx)
 {
     Cc4Dyn *s = DYN(c);
     if (SF_ABS(s->sessf[idx])) ports_drop(c, SF_AGENT(s->sessf[idx]), S_ID(s->sess[idx]));
-    _Pragma("unroll 1") for (int i = idx; i + 1 < s->n_sess; i++) { s->sess[i] = s->sess[i + 1]; s->sessf[i] = s->sessf[i + 1]; }
-    s->n_sess--;
+    const int n = s->n_sess;
+    sess_shift_down(s, idx, n);
+    s->n_sess = (uint16_t)(n - 1);
     SCR(c)->sess_moved = 1;
 }
 /* State.add_session State.py:305-323 for a red agent; returns the ident */
 __device__ __noinline__ int sess_add(Cx c, int r, int host, int abstract, int root, int pid)
 {
     Cc4Dyn *s = DYN(c);
-    if (s->n_sess >= CC4_SESS_CAP) { fail(c, CC4_E_CAPACITY); return 0; }
-    int id = 0, any = 0;
-    _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r) { any = 1; if ((int)S_ID(s->sess[i]) >= id) id = S_ID(s->sess[i]); }
-    id = any ? id + 1 : 0;
+    const int n = s->n_sess;
+    if (n >= CC4_SESS_CAP) { fail(c, CC4_E_CAPACITY); return 0; }
+    int mx = -1;
+    _Pragma("unroll 1") for (int i = lane_id(); i < n; i += 32) if (SF_AGENT(s->sessf[i]) == (uint32_t)r) mx = max(mx, (int)S_ID(s->sess[i]));
+    int id = __reduce_max_sync(FULLMASK, mx) + 1;       /* max ident + 1, 0 when the agent holds no session */
     if (id > 255) { fail(c, CC4_E_CAPACITY); id = 255; }
     if (s->sess_count[r] < 255) s->sess_count[r]++;
-    s->sess[s->n_sess] = S_MAKE(pid, id, host);
-    s->sessf[s->n_sess] = (uint8_t)(r | abstract << 3 | root << 4);
-    s->n_sess++;
+    s->sess[n] = S_MAKE(pid, id, host);
+    s->sessf[n] = (uint8_t)(r | abstract << 3 | root << 4);
+    s->n_sess = (uint16_t)(n + 1);
     return id;
-}
-__device__ __noinline__ bool red_on_host(const Cc4Dyn *s, int r, int host)
-{
-    _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_HOST(s->sess[i]) == (uint32_t)host) return true;
-    return false;
 }
 __device__ __noinline__ int session_from_pid(const Cc4Dyn *s, int host, uint32_t pid)
 {   /* State.get_session_from_pid State.py:420-444; blue / green session processes are never removed */
-    _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (S_HOST(s->sess[i]) == (uint32_t)host && S_PID(s->sess[i]) == pid) return i;
-    return -1;
+    return sess_first(s, [=](uint32_t w, uint32_t) { return S_HOST(w) == (uint32_t)host && S_PID(w) == pid; });
 }
 __device__ __forceinline__ bool blocking(const Cc4Dyn *s, int src_slot, int other_slot)
 {   /* RemoteAction.blocking_host Action.py:127-136 */
@@ -341,22 +409,32 @@ __device__ __forceinline__ bool blocking(const Cc4Dyn *s, int src_slot, int othe
 
 /* ---- observation bookkeeping for one red agent (ObservationSet / ActionSpace.update ActionSpace.py:170-212) ---- */
 __device__ __noinline__ void obs_entry(Cx c, int r, int key_ip, int slot, int iface, int subnet_if, int syshost, int sess)
-{
+{   /* [uniform] */
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     if (syshost) set128(s->hn_known[r], slot);
     if (iface) set128(s->ip_known[r], slot);
     if (subnet_if) s->sn_known[r] |= (uint16_t)(1u << slot_subnet(slot));
-    uint16_t key = (uint16_t)(slot | key_ip << 8), fl = (uint16_t)(iface << 9 | subnet_if << 10 | syshost << 11 | sess << 12);
-    _Pragma("unroll 1") for (int i = 0; i < x->n_oent[r]; i++) if ((x->oent[r][i] & 0x1FF) == key) { x->oent[r][i] |= fl; return; }
-    if (x->n_oent[r] >= CC4_OENT_CAP) { fail(c, CC4_E_CAPACITY); return; }
-    x->oent[r][x->n_oent[r]++] = key | fl;
+    const uint16_t key = (uint16_t)(slot | key_ip << 8), fl = (uint16_t)(iface << 9 | subnet_if << 10 | syshost << 11 | sess << 12);
+    const int n = x->n_oent[r];
+    _Pragma("unroll 1") for (int base = 0; base < n; base += 32) {
+        const int i = base + lane_id();
+        const uint32_t m = __ballot_sync(FULLMASK, i < n && (x->oent[r][i] & 0x1FF) == key);
+        if (m) { x->oent[r][base + __ffs(m) - 1] |= fl; return; }
+    }
+    if (n >= CC4_OENT_CAP) { fail(c, CC4_E_CAPACITY); return; }
+    x->oent[r][n] = key | fl;
+    x->n_oent[r] = (uint8_t)(n + 1);
 }
-__device__ __noinline__ void know_session(Cx c, int r, int id)
+/* the ident is a known server_session key: O(1) through the tick's mirror mask (rebuilt at the start of w_tick and kept
+ * current here); [uniform] and [lane] callers alike */
+__device__ __forceinline__ void know_session(Cx c, int r, int id)
 {
     Cc4Dyn *s = DYN(c);
-    _Pragma("unroll 1") for (int i = 0; i < s->n_ss[r]; i++) if (s->ss[r][i] == id) return;
-    if (s->n_ss[r] >= CC4_SS_CAP) { fail(c, CC4_E_CAPACITY); return; }
-    s->ss[r][s->n_ss[r]++] = (uint8_t)id;
+    if (SCR(c)->ssmask[r][id >> 5] >> (id & 31) & 1u) return;
+    const int n = s->n_ss[r];
+    if (n >= CC4_SS_CAP) { fail(c, CC4_E_CAPACITY); return; }
+    s->ss[r][n] = (uint8_t)id;
+    s->n_ss[r] = (uint8_t)(n + 1);
     SCR(c)->ssmask[r][id >> 5] |= 1u << (id & 31);
 }
 __device__ __forceinline__ void obs_push(Cx c, int r, int succ, bool has_act, uint32_t aw)
@@ -480,13 +558,14 @@ __device__ __noinline__ uint32_t red_policy(Cx c, int r)
     /* options in action-space order (c_red_aspace_cols); numpy Generator.choice(p): idx = searchsorted(cumsum(p) / sum, u, side='right') */
     int nc = 0, tot = 0;
     _Pragma("unroll 1") for (int i = 0; i < 9; i++) { int p = c_fsm_prob4[st][c_red_aspace_cols[i]]; if (p >= 0) { tot += p; nc++; } }
+    if (tot != 4) fail(c, CC4_E_UNREACHABLE);
     double u = rng_f64(c, actor, ST_FSM_ACTION, (uint32_t)nc);
     int col = -1, cum = 0, last = -1;
     _Pragma("unroll 1") for (int i = 0; i < 9 && col < 0; i++) {
         int cc = c_red_aspace_cols[i], p = c_fsm_prob4[st][cc];
         if (p < 0) continue;
         last = cc; cum += p;
-        if (!((double)cum / (double)tot <= u)) col = cc;
+        if (!((double)cum * 0.25 <= u)) col = cc;      /* cdf / cdf[-1]: every row of the table sums to 4 quarters, so this is exact */
     }
     if (col < 0) col = last;
     Act a = { c_fsm_col_code[col], -1, -1, 0 };
@@ -545,7 +624,7 @@ __device__ __noinline__ void ev_procpid(Cx c, int slot, int pid)
     }
 }
 
-/* StopProcess.execute_targeteted_local_action + kill_process StopProcess.py:23-58 */
+/* StopProcess.execute_targeteted_local_action + kill_process StopProcess.py:23-58 [uniform] */
 __device__ __noinline__ void stop_process(Cx c, int actor, int h, uint32_t pid)
 {
     Cc4Dyn *s = DYN(c);
@@ -557,7 +636,9 @@ __device__ __noinline__ void stop_process(Cx c, int actor, int h, uint32_t pid)
     /* a stopped OT service keeps Service.process; a pid collision with it takes the reference down a path that
        re-labels the killed process as the service's (StopProcess.py:37-42): not modelled */
     { const uint32_t *pp = PROCS(c, h); const int np = NPROC(c, h);
-      _Pragma("unroll 1") for (int i = 0; i < np; i++) if (P_DEAD(pp[i]) && P_PID(pp[i]) == pid) fail(c, CC4_E_UNREACHABLE); }
+      uint32_t clash = 0;
+      _Pragma("unroll 1") for (int i = lane_id(); i < np; i += 32) clash |= (uint32_t)(P_DEAD(pp[i]) && P_PID(pp[i]) == pid);
+      if (__any_sync(FULLMASK, clash)) fail(c, CC4_E_UNREACHABLE); }
     proc_delete(c, h, pi);
     if (P_SVC(w)) {
         int np = create_pid(c, actor, h);
@@ -570,35 +651,49 @@ __device__ __noinline__ void stop_process(Cx c, int actor, int h, uint32_t pid)
     if (s->sess_count[r] > 0) s->sess_count[r]--;
 }
 
-/* RestoreFromBackup.py:9-19 + Host.restore Host.py:373-429 */
+/* RestoreFromBackup.py:9-19 + Host.restore Host.py:373-429 [uniform] */
 __device__ __noinline__ void do_restore(Cx c, int h)
 {
     Cc4Dyn *s = DYN(c); const Cc4Stat *st = WC(c)->st;
-    _Pragma("unroll 1") for (int i = 0; i < s->n_sess;) if (S_HOST(s->sess[i]) == (uint32_t)h) sess_delete(c, i); else i++;
+    _Pragma("unroll 1") for (;;) {      /* every session on the host goes, in pool order */
+        int i = sess_first(s, [=](uint32_t w, uint32_t) { return S_HOST(w) == (uint32_t)h; });
+        if (i < 0) break;
+        sess_delete(c, i);
+    }
     s->ev[h] = 0;
-    int on = st->o_nproc[h];
-    _Pragma("unroll 1") for (int i = 0; i < on; i++) WC(c)->k->parena[h * CC4_OSLAB + i] = st->o_procs[h][i];   /* back in the home slab */
+    const int on = st->o_nproc[h];
+    if (lane_id() < on) WC(c)->k->parena[h * CC4_OSLAB + lane_id()] = st->o_procs[h][lane_id()];   /* back in the home slab (on <= CC4_OSLAB) */
+    __syncwarp();
     WC(c)->k->pdir[h] = PD_MAKE(h * CC4_OSLAB, on, 3);
     proc_rescan_max(c, h);
     WC(c)->k->svc64[h] = st->o_svc64[h];
 }
 
-/* DecoyAction.execute DecoyAction.py:47-112 with DeployDecoy.CANDIDATE_DECOYS DeployDecoy.py:27 */
+/* DecoyAction.execute DecoyAction.py:47-112 with DeployDecoy.CANDIDATE_DECOYS DeployDecoy.py:27 [uniform] */
 __device__ __noinline__ void do_decoy(Cx c, int b, int h)
 {
     int actor = A_BLUE0 + b;
-    int used = 0;
-    const uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
-    _Pragma("unroll 1") for (int i = 0; i < np_h; i++) { uint32_t w = pp_h[i]; if (P_DEAD(w)) continue; int pb = c_kind_portbit[P_KIND(w)]; if (pb >= 0) used |= 1 << pb; }
-    int fac[4], nf = 0;
-    if (!(used & PB_80)) fac[nf++] = K_D_APACHE;
-    if (!(used & PB_443)) fac[nf++] = K_D_TOMCAT;
-    if (!(used & PB_25)) fac[nf++] = K_D_HARAKA;
-    fac[nf++] = K_D_VSFTPD;     /* DecoyVsftpd.py:17-20 tests port 21, which nothing uses, and then opens port 80 */
-    int kind = fac[rng_int(c, actor, ST_DECOY_FACTORY, (uint32_t)nf)];
+    uint32_t used = 0;
+    {
+        const uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
+        _Pragma("unroll 1") for (int i = lane_id(); i < np_h; i += 32) { uint32_t w = pp_h[i]; if (P_DEAD(w)) continue; uint32_t pb = kind_portbit(P_KIND(w)); if (pb != 15u) used |= 1u << pb; }
+        used = __reduce_or_sync(FULLMASK, used);
+    }
+    /* compatible factories in CANDIDATE_DECOYS order; VsftpdDecoyFactory tests port 21, which nothing uses, and then opens
+       port 80 (DecoyVsftpd.py:17-20): always compatible */
+    uint32_t fac = 0; int nf = 0;       /* packed list, 4 bits per entry */
+    if (!(used & PB_80)) fac |= (uint32_t)K_D_APACHE << (4 * nf++);
+    if (!(used & PB_443)) fac |= (uint32_t)K_D_TOMCAT << (4 * nf++);
+    if (!(used & PB_25)) fac |= (uint32_t)K_D_HARAKA << (4 * nf++);
+    fac |= (uint32_t)K_D_VSFTPD << (4 * nf++);
+    int kind = (int)(fac >> (4 * rng_int(c, actor, ST_DECOY_FACTORY, (uint32_t)nf)) & 15u);
     int pid = create_pid(c, actor, h);
     /* host.services[name] = Service(pid): an earlier process of the same decoy stops being the service's process */
-    _Pragma("unroll 1") for (int i = 0; i < np_h; i++) { uint32_t w = pp_h[i]; if (P_KIND(w) == (uint32_t)kind && P_SVC(w)) PROCS(c, h)[i] = w & ~(1u << 21); }
+    {
+        uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
+        _Pragma("unroll 1") for (int i = lane_id(); i < np_h; i += 32) { uint32_t w = pp_h[i]; if (P_KIND(w) == (uint32_t)kind && P_SVC(w)) pp_h[i] = w & ~(1u << 21); }
+        __syncwarp();
+    }
     proc_append(c, h, P_MAKE(pid, kind, 0, 1));
     uint64_t v = WC(c)->k->svc64[h];
     int n = svc_count(v), at = -1;
@@ -607,52 +702,97 @@ __device__ __noinline__ void do_decoy(Cx c, int b, int h)
     WC(c)->k->svc64[h] = svc_set(v, at, (uint32_t)kind | 5u << 4);
 }
 
-__device__ __noinline__ void exec_blue(Cx c, int b, uint32_t aw)
+/* a blue agent's own Monitor action (Monitor.py:35-74 for one agent) [uniform] */
+__device__ __noinline__ void monitor_one(Cx c, int b)
 {
+    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
+    _Pragma("unroll 1") for (int h = lane_id(); h < CC4_NSLOT; h += 32) if (blue_of_subnet(slot_subnet(h)) == b) { uint32_t e = s->ev[h]; s->ev[h] = (uint8_t)((e & (EV_PROC | EV_NET)) << 2); }
+    __syncwarp();
+    int w = 0;
+    const int ne = x->n_evpid;
+    _Pragma("unroll 1") for (int i = 0; i < ne; i++) {
+        const uint32_t e = x->evpid[i];
+        int slot = e >> 16;
+        if (blue_of_subnet(slot_subnet(slot)) != b) { x->evpid[w++] = e; continue; }
+        if (s->n_sus >= CC4_SUS_CAP) { fail(c, CC4_E_CAPACITY); continue; }
+        WC(c)->k->sus[s->n_sus] = SU_MAKE(e & 0xFFFFu, slot, b);
+        s->n_sus++;
+    }
+    x->n_evpid = w;
+}
+
+__device__ __noinline__ void exec_blue(Cx c, int b, uint32_t aw)
+{   /* [uniform] */
     Cc4Dyn *s = DYN(c);
     const Act a = unpack_act(aw);
     switch (a.code) {
-    case AC_REMOVE: {   /* Remove.py:42-69 */
-        int n = s->n_sus;
-        _Pragma("unroll 1") for (int i = 0; i < n; i++) { uint32_t w = WC(c)->k->sus[i]; if (SU_AGENT(w) == (uint32_t)b && SU_SLOT(w) == (uint32_t)a.host) stop_process(c, A_BLUE0 + b, a.host, SU_PID(w)); }
+    case AC_REMOVE: {   /* Remove.py:42-69: StopProcess for every suspicious pid recorded for the host, in list order */
+        const int n = s->n_sus;
+        const uint32_t *sus = WC(c)->k->sus;
+        _Pragma("unroll 1") for (int base = 0; base < n; base += 32) {
+            const int i = base + lane_id();
+            const uint32_t w = i < n ? sus[i] : 0u;
+            uint32_t m = __ballot_sync(FULLMASK, i < n && SU_AGENT(w) == (uint32_t)b && SU_SLOT(w) == (uint32_t)a.host);
+            while (m) {
+                const int j = __ffs(m) - 1; m &= m - 1;
+                stop_process(c, A_BLUE0 + b, a.host, SU_PID(__shfl_sync(FULLMASK, w, j)));
+            }
+        }
         break;
     }
+    case AC_MONITOR: monitor_one(c, b); break;
     case AC_RESTORE: do_restore(c, a.host); break;        /* Restore.py:38-68 */
     case AC_DECOY: do_decoy(c, b, a.host); break;
     case AC_BLOCK: s->blocks[a.subnet] |= (uint16_t)(1u << a.host); break;     /* ControlTraffic.py:62-116 */
     case AC_ALLOW: s->blocks[a.subnet] &= (uint16_t)~(1u << a.host); break;    /* ControlTraffic.py:132-185 */
-    default: break;   /* Analyse (Analyse.py:40-71) changes no state; Monitor is handled by the caller */
+    default: break;   /* Analyse (Analyse.py:40-71) changes no state */
     }
 }
 
 /* ------------------------------------------------------------------------------------------------ */
 /* green                                                                                            */
 /* ------------------------------------------------------------------------------------------------ */
-/* PhishingEmail._create_new_session PhishingEmail.py:42-113 (lane 0, in green-agent order); x->g.hostagents is current */
+/* PhishingEmail._create_new_session PhishingEmail.py:42-113 ([uniform], in green-agent order); x->g.hostagents is current */
 __device__ __noinline__ void do_phishing(Cx c, int g)
 {
     Cc4Dyn *s = DYN(c);
     const uint8_t *ha = reinterpret_cast<const uint8_t *>(SCR(c)->g.hostagents);
     int actor = A_GREEN0 + g, gh = s->green_host[g], gsn = gh >> 4;
     if (ha[gh]) return;
-    /* hosts in state.hosts order (per subnet: users, then servers), agents in order on each host */
-    int src = -1, nc = 0;
-    uint8_t cand[CC4_SESS_CAP];
-    _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) {
-        int nu = s->nuser[sn], nh = nu + s->nserver[sn];
-        if (!(SCR(c)->g.hostagents[4 * sn] | SCR(c)->g.hostagents[4 * sn + 1] | SCR(c)->g.hostagents[4 * sn + 2] | SCR(c)->g.hostagents[4 * sn + 3])) continue;
-        _Pragma("unroll 1") for (int k = 0; k < nh; k++) {
-            int h = k < nu ? sn * 16 + 6 + k : sn * 16 + (k - nu);
-            uint32_t agents = ha[h];
-            if (!agents) continue;
-            _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
-                if (!(agents >> r & 1)) continue;
-                if (sn == gsn) { src = r; break; }
-                if (nc < CC4_SESS_CAP) cand[nc++] = (uint8_t)r;
-            }
+    /* (host, agent) pairs in state.hosts order (per subnet: users, then servers), agents ascending on each host.  A red
+       agent with a session in the green host's own subnet owns the new session (the LAST such host wins: only the inner
+       loop breaks, PhishingEmail.py:73-81); otherwise the owner is drawn uniformly from the pairs of the other subnets.
+       Lane L looks at the four hosts of order-rank 4L..4L+3 (rank = subnet*16 + {user k | 10 + server k}). */
+    const int lane = lane_id();
+    uint32_t mine = 0;      /* byte j = agent mask of the host with rank 4*lane + j */
+    _Pragma("unroll") for (int j = 0; j < 4; j++) {
+        int rank = 4 * lane + j, k = rank & 15, slot = (rank & ~15) | (k < 10 ? 6 + k : k - 10);
+        mine |= (uint32_t)ha[slot] << (8 * j);
+    }
+    const bool own = (lane >> 2) == gsn;
+    int src = -1;
+    {
+        const uint32_t m = __ballot_sync(FULLMASK, own && mine != 0);
+        if (m) {
+            const int L = 31 - __clz(m);
+            const uint32_t v = __shfl_sync(FULLMASK, mine, L);
+            const uint32_t last = v >> 24 ? v >> 24 : (v >> 16 & 0xFF) ? (v >> 16 & 0xFF) : (v >> 8 & 0xFF) ? (v >> 8 & 0xFF) : (v & 0xFF);
+            src = __ffs(last) - 1;
         }
     }
-    if (src < 0) { if (nc == 0) return; src = cand[rng_int(c, actor, ST_PHISH_AGENT, (uint32_t)nc)]; }
+    if (src < 0) {
+        const int cnt = own ? 0 : __popc(mine);
+        int incl = cnt;
+        _Pragma("unroll") for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += t; }
+        const int nc = __shfl_sync(FULLMASK, incl, 31);
+        if (nc == 0) return;
+        const int pk = (int)rng_int(c, actor, ST_PHISH_AGENT, (uint32_t)nc);
+        const uint32_t m = __ballot_sync(FULLMASK, pk < incl);
+        const int L = __ffs(m) - 1;
+        const uint32_t v = __shfl_sync(FULLMASK, mine, L);
+        const int before = __shfl_sync(FULLMASK, incl - cnt, L);
+        src = (int)__fns(v, 0, pk - before + 1) & 7;      /* bit position inside the lane's four bytes -> agent */
+    }
     int pid = create_pid(c, actor, gh);
     proc_append(c, gh, P_MAKE(pid, K_REDABS, 0, 0));
     sess_add(c, src, gh, 1, 0, pid);
@@ -669,6 +809,7 @@ __device__ __noinline__ int green_tick(Cx c, int g, uint32_t *ev_words)
     Cc4Dyn *s = DYN(c);
     const int actor = A_GREEN0 + g, gh = s->green_host[g], gsn = gh >> 4;
     const bool tape = WC(c)->rng_mode == 1;
+    const uint64_t v = WC(c)->k->svc64[gh];     /* issued ahead of the Philox rounds: only LocalWork (1 in 3) uses it, but the latency hides */
     uint4 blk = tape ? make_uint4(0, 0, 0, 0) : philox_block(c, actor, 0);
     uint32_t j = 0;
     auto word = [&]() -> uint32_t {
@@ -680,7 +821,6 @@ __device__ __noinline__ int green_tick(Cx c, int g, uint32_t *ev_words)
     int out = 0;
     uint32_t choice = gi(ST_GREEN_ACT, 3);
     if (choice == 1) {
-        uint64_t v = WC(c)->k->svc64[gh];
         int n = svc_count(v), na = 0;
         _Pragma("unroll 1") for (int i = 0; i < n; i++) na += svc_active(v, SVC_ENTRY(v, i));
         if (na == 0) out = -c_reward[s->phase][gsn][0];
@@ -726,7 +866,7 @@ __device__ __noinline__ int route(int src, int dst, int *out)
     return n;
 }
 
-/* ExploitAction._create_new_session ExploitAction.py:212-262 */
+/* ExploitAction._create_new_session ExploitAction.py:212-262 [uniform] */
 __device__ __noinline__ int exploit_new_session(Cx c, int r, int target)
 {
     int pid = create_pid(c, A_RED0 + r, target);
@@ -734,12 +874,26 @@ __device__ __noinline__ int exploit_new_session(Cx c, int r, int target)
     sess_add(c, r, target, 0, 0, pid);
     return pid;
 }
+/* index of the known-port entry of (agent, abstract session, host), -1 if none [uniform] */
+__device__ __noinline__ int ports_find(Cx c, int r, int id, int host)
+{
+    const uint32_t *ports = WC(c)->k->ports;
+    const int n = DYN(c)->n_ports;
+    const uint32_t key = PT_MAKE(0, host, id, r);
+    _Pragma("unroll 1") for (int base = 0; base < n; base += 32) {
+        const int i = base + lane_id();
+        const uint32_t m = __ballot_sync(FULLMASK, i < n && (ports[i] & ~0x3Fu) == key);
+        if (m) return base + __ffs(m) - 1;
+    }
+    return -1;
+}
 
+/* [uniform]: the whole warp executes the action; scans are lane-parallel */
 __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
 {
     Cc4Dyn *s = DYN(c);
     const Act a = unpack_act(aw);
-    int actor = A_RED0 + r;
+    const int actor = A_RED0 + r, lane = lane_id();
     int si = (a.code == AC_SLEEP || a.code == AC_INVALID) ? -1 : SCR(c)->sess_moved ? sess_find(s, r, a.session) : (int)SCR(c)->act_si[r];
     int S_host = si >= 0 ? (int)S_HOST(s->sess[si]) : -1, S_abs = si >= 0 ? (int)SF_ABS(s->sessf[si]) : 0;
     switch (a.code) {
@@ -757,44 +911,51 @@ __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
         if (blocking(s, S_host, a.host)) return SUCC_FALSE;
         double rate = a.code == AC_AGGR ? 0.75 : 0.25;
         double u = rng_f64(c, actor, ST_PORTSCAN, 0);
-        int mask = 0, any = 0, h = a.host;
+        const int h = a.host;
+        uint32_t mask = 0, alert = 0;
         const uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
-        _Pragma("unroll 1") for (int i = 0; i < np_h; i++) {
+        _Pragma("unroll 1") for (int i = lane; i < np_h; i += 32) {
             uint32_t w = pp_h[i];
             if (P_DEAD(w)) continue;
-            int pb = c_kind_portbit[P_KIND(w)];
-            if (pb < 0) continue;
-            any = 1; mask |= 1 << pb;
-            if (u <= rate || P_KIND(w) >= K_D_APACHE) s->ev[h] |= EV_NET;
+            uint32_t pb = kind_portbit(P_KIND(w));
+            if (pb == 15u) continue;
+            mask |= 1u << pb;
+            if (u <= rate || P_KIND(w) >= K_D_APACHE) alert = 1;
         }
-        if (any) {
-            int at = -1;
-            _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = WC(c)->k->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)a.session && PT_HOST(p) == (uint32_t)h) { at = i; break; } }
-            if (at < 0) { if (s->n_ports >= CC4_PORT_CAP) { fail(c, CC4_E_CAPACITY); at = 0; } else at = s->n_ports++; }
+        mask = __reduce_or_sync(FULLMASK, mask);
+        if (__any_sync(FULLMASK, alert)) s->ev[h] |= EV_NET;
+        if (mask) {
+            int at = ports_find(c, r, a.session, h);
+            if (at < 0) { if (s->n_ports >= CC4_PORT_CAP) { fail(c, CC4_E_CAPACITY); at = 0; } else { at = s->n_ports; s->n_ports = (uint16_t)(at + 1); } }
             WC(c)->k->ports[at] = PT_MAKE(mask, h, a.session, r);
             obs_entry(c, r, 1, h, 1, 0, 0, 0);
         }
         return SUCC_TRUE;
     }
-    case AC_DD: {      /* DiscoverDeception.py:44-101 */
+    case AC_DD: {      /* DiscoverDeception.py:44-101: two draws per process, in list order */
         if (si < 0) return SUCC_FALSE;
         int rep = 0, h = a.host;
         const uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
-        _Pragma("unroll 1") for (int i = 0; i < np_h; i++) {
-            uint32_t w = pp_h[i];
-            if (P_DEAD(w)) continue;
-            bool decoy = P_KIND(w) >= K_D_APACHE && P_KIND(w) <= K_D_VSFTPD;
-            if (rng_f64(c, actor, ST_DD_TP, 0) <= 0.5 && decoy) rep = 1;
-            else if (rng_f64(c, actor, ST_DD_FP, 0) <= 0.1 && !decoy) rep = 1;
+        _Pragma("unroll 1") for (int base = 0; base < np_h; base += 32) {
+            const uint32_t mine = base + lane < np_h ? pp_h[base + lane] : P_NONE;
+            const int cnt = min(32, np_h - base);
+            _Pragma("unroll 1") for (int j = 0; j < cnt; j++) {
+                uint32_t w = __shfl_sync(FULLMASK, mine, j);
+                if (P_DEAD(w)) continue;
+                bool decoy = P_KIND(w) >= K_D_APACHE && P_KIND(w) <= K_D_VSFTPD;
+                if (rng_f64(c, actor, ST_DD_TP, 0) <= 0.5 && decoy) rep = 1;
+                else if (rng_f64(c, actor, ST_DD_FP, 0) <= 0.1 && !decoy) rep = 1;
+            }
         }
         if (rep) obs_entry(c, r, 0, h, 1, 0, 0, 0);
         return SUCC_TRUE;
     }
     case AC_EXPLOIT: { /* ExploitRemoteService.py:149-202 */
         if (si < 0 || !S_abs) return SUCC_FALSE;
-        int ports = -1, target = a.host, src = S_host;
-        _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = WC(c)->k->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)a.session && PT_HOST(p) == (uint32_t)target) { ports = PT_MASK(p); break; } }
-        if (ports < 0) return SUCC_FALSE;
+        int target = a.host, src = S_host;
+        int pe = ports_find(c, r, a.session, target);
+        if (pe < 0) return SUCC_FALSE;
+        const int ports = (int)PT_MASK(WC(c)->k->ports[pe]);
         if (blocking(s, src, target)) return SUCC_FALSE;
         enum { X_HTTP, X_HTTPS, X_SSH, X_SQL, X_HARAKA };
         int opt[5], w10[5], no = 0;   /* DefaultExploitActionSelector :37-69, weights x10 */
@@ -813,13 +974,30 @@ __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
             sel = opt[rng_int(c, actor, ST_EXP_OTHER, (uint32_t)no)];
             (void)rng_f64(c, actor, ST_EXP_TOP, 0);
         }
+        /* the first live process (list order) that the chosen exploit can attack: ExploitAction._get_vulnerable_process
+           ExploitAction.py:178-200 / SSHBruteForce.py:24-84 */
+        int vk = -1;
+        {
+            const uint32_t *pp_target = PROCS(c, target); const int np_target = NPROC(c, target);
+            _Pragma("unroll 1") for (int base = 0; base < np_target && vk < 0; base += 32) {
+                const uint32_t w = base + lane < np_target ? pp_target[base + lane] : P_NONE;
+                const int k = (int)P_KIND(w);
+                bool hit = false;
+                if (!P_DEAD(w)) {
+                    if (sel == X_SSH) hit = k == K_SSHD;
+                    else if (sel == X_HTTP) hit = k == K_APACHE2 || k == K_D_APACHE || k == K_D_VSFTPD;
+                    else if (sel == X_HTTPS) hit = k == K_D_TOMCAT;
+                    else if (sel == X_SQL) hit = k == K_MYSQLD;
+                    else hit = k == K_SMTP || k == K_D_HARAKA;
+                }
+                const uint32_t m = __ballot_sync(FULLMASK, hit);
+                if (m) vk = __shfl_sync(FULLMASK, k, __ffs(m) - 1);
+            }
+        }
         if (sel == X_SSH) {   /* SSHBruteForce.execute SSHBruteForce.py:24-84 */
             int hops[12], nh = route(src, target, hops);
             _Pragma("unroll 1") for (int i = 0; i < nh; i++) if (0.05 < rng_f64(c, actor, ST_SSH_HOP, 0)) s->ev[hops[i]] |= EV_NET;
-            int vp = -1;
-            const uint32_t *pp_target = PROCS(c, target); const int np_target = NPROC(c, target);
-            _Pragma("unroll 1") for (int i = 0; i < np_target; i++) { uint32_t w = pp_target[i]; if (!P_DEAD(w) && P_KIND(w) == K_SSHD) { vp = i; break; } }
-            if (vp < 0) return SUCC_FALSE;
+            if (vk < 0) return SUCC_FALSE;
             s->ev[target] |= EV_NET;
             int pid = exploit_new_session(c, r, target);
             ev_procpid(c, target, pid);
@@ -828,17 +1006,6 @@ __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
             return SUCC_TRUE;
         }
         /* ExploitAction.sim_exploit ExploitAction.py:48-116 */
-        int vk = -1;
-        const uint32_t *pp_target = PROCS(c, target); const int np_target = NPROC(c, target);
-        _Pragma("unroll 1") for (int i = 0; i < np_target && vk < 0; i++) {
-            uint32_t w = pp_target[i];
-            if (P_DEAD(w)) continue;
-            int k = P_KIND(w);
-            if (sel == X_HTTP && (k == K_APACHE2 || k == K_D_APACHE || k == K_D_VSFTPD)) vk = k;
-            if (sel == X_HTTPS && k == K_D_TOMCAT) vk = k;
-            if (sel == X_SQL && k == K_MYSQLD) vk = k;
-            if (sel == X_HARAKA && (k == K_SMTP || k == K_D_HARAKA)) vk = k;
-        }
         if (vk < 0) return SUCC_FALSE;
         bool decoy = vk >= K_D_APACHE && vk <= K_D_VSFTPD;
         if (decoy) s->ev[target] |= EV_NET;
@@ -853,12 +1020,16 @@ __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
         return SUCC_TRUE;
     }
     case AC_PRIVESC: { /* PrivilegeEscalate.py:127-179 */
-        int h = a.host, n = 0, tgt = -1;
-        _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_HOST(s->sess[i]) == (uint32_t)h) { n++; if (tgt < 0 && SF_ROOT(s->sessf[i])) tgt = i; }
+        const int h = a.host;
+        auto on_host = [=](uint32_t w, uint32_t f) { return SF_AGENT(f) == (uint32_t)r && S_HOST(w) == (uint32_t)h; };
+        int n = 0;
+        _Pragma("unroll 1") for (int i = lane; i < s->n_sess; i += 32) n += on_host(s->sess[i], s->sessf[i]);
+        n = __reduce_add_sync(FULLMASK, n);
         if (n == 0) return SUCC_FALSE;
+        int tgt = sess_first(s, [=](uint32_t w, uint32_t f) { return on_host(w, f) && SF_ROOT(f); });
         if (tgt < 0) {
             int pk = (int)rng_int(c, actor, ST_PRIV_SESS, (uint32_t)n);
-            _Pragma("unroll 1") for (int i = 0, k = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_HOST(s->sess[i]) == (uint32_t)h) { if (k == pk) { tgt = i; break; } k++; }
+            tgt = sess_kth(s, pk, on_host);
             if (si < 0 || !S_abs) return SUCC_FALSE;
             s->sessf[tgt] |= 1u << 4;      /* EscalateAction.__upgrade_session EscalateAction.py:54-87 */
             int pi = proc_find(c, h, S_PID(s->sess[tgt]));
@@ -873,9 +1044,10 @@ __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
         return SUCC_TRUE;
     }
     case AC_IMPACT: case AC_DEGRADE: {   /* Impact.py:38-88, DegradeServices.py:38-82 */
-        int h = a.host, any = 0, root = 0;
-        _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_HOST(s->sess[i]) == (uint32_t)h) { any = 1; root |= SF_ROOT(s->sessf[i]); }
-        if (!any || !root) return SUCC_FALSE;
+        const int h = a.host;
+        uint32_t any = 0, root = 0;
+        _Pragma("unroll 1") for (int i = lane; i < s->n_sess; i += 32) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_HOST(s->sess[i]) == (uint32_t)h) { any = 1; root |= SF_ROOT(s->sessf[i]); }
+        if (!__any_sync(FULLMASK, any && root)) return SUCC_FALSE;
         uint64_t v = WC(c)->k->svc64[h];
         int n = svc_count(v);
         if (a.code == AC_IMPACT) {
@@ -884,16 +1056,20 @@ __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
             if (!has_ot || (v & SVC_OT_STOPPED)) return SUCC_FALSE;
             if (si < 0) return SUCC_FALSE;     /* StopService is a TargetedLocalAction: TargetedLocalAction.py:14-21 */
             WC(c)->k->svc64[h] = v | SVC_OT_STOPPED;  /* Host.stop_service Host.py:296-301 */
-            const uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
-            _Pragma("unroll 1") for (int i = 0; i < np_h; i++) {   /* State.remove_process State.py:390-418 */
-                uint32_t w = pp_h[i];
-                if (!P_DEAD(w) && P_KIND(w) == K_OT && P_SVC(w)) {
-                    int s2 = session_from_pid(s, h, P_PID(w));
-                    PROCS(c, h)[i] = w | P_DEADBIT;
-                    if (P_PID(w) == WC(c)->k->pmax[h]) proc_rescan_max(c, h);
-                    if (s2 >= 0) sess_delete(c, s2);
-                    break;
-                }
+            /* State.remove_process State.py:390-418: the first live OT service process becomes a tombstone */
+            uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
+            int at = -1;
+            _Pragma("unroll 1") for (int base = 0; base < np_h && at < 0; base += 32) {
+                const uint32_t w = base + lane < np_h ? pp_h[base + lane] : P_NONE;
+                const uint32_t m = __ballot_sync(FULLMASK, !P_DEAD(w) && P_KIND(w) == K_OT && P_SVC(w));
+                if (m) at = base + __ffs(m) - 1;
+            }
+            if (at >= 0) {
+                const uint32_t w = pp_h[at];
+                int s2 = session_from_pid(s, h, P_PID(w));
+                pp_h[at] = w | P_DEADBIT;
+                if (P_PID(w) == WC(c)->k->pmax[h]) proc_rescan_max(c, h);
+                if (s2 >= 0) sess_delete(c, s2);
             }
         } else {
             int na = 0;
@@ -909,31 +1085,46 @@ __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
     }
 }
 
-/* RedSessionCheck._choose_new_primary_session RedSessionCheck.py:34-55 (lane 0; agent r holds n sessions, none with ident 0) */
+/* RedSessionCheck._choose_new_primary_session RedSessionCheck.py:34-55 ([uniform]; agent r holds n sessions, none with ident 0) */
 __device__ __noinline__ void rsc_reelect(Cx c, int r, int n)
 {
     Cc4Dyn *s = DYN(c);
-    int pk = (int)rng_int(c, A_RED0 + r, ST_RSC_PRIMARY, (uint32_t)n), at = -1;
-    _Pragma("unroll 1") for (int i = 0, k = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r) { if (k == pk) { at = i; break; } k++; }
+    int pk = (int)rng_int(c, A_RED0 + r, ST_RSC_PRIMARY, (uint32_t)n);
+    int at = sess_kth(s, pk, [=](uint32_t, uint32_t f) { return SF_AGENT(f) == (uint32_t)r; });
     if (at < 0) { fail(c, CC4_E_UNREACHABLE); return; }
-    uint32_t w = s->sess[at]; uint8_t f = s->sessf[at];
-    int old_id = S_ID(w);
-    _Pragma("unroll 1") for (int i = 0; i < s->n_ports; i++) { uint32_t p = WC(c)->k->ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)old_id) WC(c)->k->ports[i] = PT_MAKE(PT_MASK(p), PT_HOST(p), 0, r); }
-    _Pragma("unroll 1") for (int i = at; i + 1 < s->n_sess; i++) { s->sess[i] = s->sess[i + 1]; s->sessf[i] = s->sessf[i + 1]; }
-    s->sess[s->n_sess - 1] = S_MAKE(S_PID(w), 0, S_HOST(w)); s->sessf[s->n_sess - 1] = f;
+    const uint32_t w = s->sess[at]; const uint8_t f = s->sessf[at];
+    const int old_id = S_ID(w);
+    {   /* the session's known ports follow it to ident 0 */
+        uint32_t *ports = WC(c)->k->ports;
+        const int np = s->n_ports;
+        _Pragma("unroll 1") for (int i = lane_id(); i < np; i += 32) { uint32_t p = ports[i]; if (PT_AGENT(p) == (uint32_t)r && PT_ID(p) == (uint32_t)old_id) ports[i] = PT_MAKE(PT_MASK(p), PT_HOST(p), 0, r); }
+        __syncwarp();
+    }
+    const int ns = s->n_sess;
+    sess_shift_down(s, at, ns);      /* the re-keyed entry moves to the end of the agent's dict */
+    s->sess[ns - 1] = S_MAKE(S_PID(w), 0, S_HOST(w)); s->sessf[ns - 1] = f;
 }
 
-/* SimulationController.different_subnet_agent_reassignment :820-903 */
+/* SimulationController.different_subnet_agent_reassignment :820-903 [uniform] */
 __device__ __noinline__ void reassign(Cx c)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     uint8_t list[32]; int n = 0;   /* (agent, ident) pairs, agents ascending then dict order */
     uint8_t lid[32];
-    _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++)
-        _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && !red_allowed(r, S_HOST(s->sess[i]) >> 4)) {
-            if (n >= 32) { fail(c, CC4_E_CAPACITY); break; }
-            list[n] = (uint8_t)r; lid[n] = (uint8_t)S_ID(s->sess[i]); n++;
+    _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
+        if (!(x->misplaced >> r & 1)) continue;
+        const int ns = s->n_sess;
+        _Pragma("unroll 1") for (int base = 0; base < ns; base += 32) {
+            const int i = base + lane_id();
+            const uint32_t w = i < ns ? s->sess[i] : 0u;
+            uint32_t m = __ballot_sync(FULLMASK, i < ns && SF_AGENT(s->sessf[i]) == (uint32_t)r && !red_allowed(r, S_HOST(w) >> 4));
+            while (m) {
+                const int j = __ffs(m) - 1; m &= m - 1;
+                if (n >= 32) { fail(c, CC4_E_CAPACITY); break; }
+                list[n] = (uint8_t)r; lid[n] = (uint8_t)S_ID(__shfl_sync(FULLMASK, w, j)); n++;
+            }
         }
+    }
     _Pragma("unroll 1") for (int k = 0; k < n; k++) {
         int r = list[k], si = sess_find(s, r, lid[k]);
         uint32_t w = s->sess[si]; uint8_t f = s->sessf[si];

@@ -208,21 +208,6 @@ __device__ void w_monitor_all(Cx c)
     }
     __syncwarp();
 }
-/* a blue agent's own Monitor action (same code path, one agent) */
-__device__ void monitor_one(Cx c, int b)
-{
-    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
-    _Pragma("unroll 1") for (int h = 0; h < CC4_NSLOT; h++) if (blue_of_subnet(slot_subnet(h)) == b) { uint32_t e = s->ev[h]; s->ev[h] = (uint8_t)((e & (EV_PROC | EV_NET)) << 2); }
-    int w = 0;
-    _Pragma("unroll 1") for (int i = 0; i < x->n_evpid; i++) {
-        int slot = x->evpid[i] >> 16;
-        if (blue_of_subnet(slot_subnet(slot)) != b) { x->evpid[w++] = x->evpid[i]; continue; }
-        if (s->n_sus >= CC4_SUS_CAP) { fail(c, CC4_E_CAPACITY); continue; }
-        WC(c)->k->sus[s->n_sus++] = SU_MAKE(x->evpid[i] & 0xFFFFu, slot, b);
-    }
-    x->n_evpid = w;
-}
-
 /* ------------------------------------------------------------------------------------------------ */
 /* session-pool digests (lane per session)                                                          */
 /* ------------------------------------------------------------------------------------------------ */
@@ -319,6 +304,26 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o);
     __syncwarp();
+    /* The due actions are known: pull the cold-record lines they will touch towards L2 now, so that the dependent reads of
+       the (serial) action code below find them there instead of in DRAM. */
+    {
+        const Cc4Cold *k = WC(c)->k;
+        if (lane < 9) {            /* the service table: green LocalWork reads one entry per agent every tick */
+            const char *b = reinterpret_cast<const char *>(k->svc64);
+            prefetch_l2(b + min(128 * lane, (int)sizeof(k->svc64) - 1));
+            if (lane * 32 < s->n_sus) prefetch_l2(k->sus + lane * 32);
+        } else if (lane < 20) {    /* one lane per blue / red actor: directory entry, home slab and largest pid of the target host */
+            const uint32_t w = x->subw[lane - 9], code = IP_CODE(w), h = IP_HOST(w);
+            const bool hosty = (code == AC_REMOVE || code == AC_RESTORE || code == AC_DECOY || (code >= AC_AGGR && code <= AC_DEGRADE)) && h < 128;
+            if (hosty) {
+                prefetch_l2(&k->pdir[h]); prefetch_l2(&k->parena[h * CC4_OSLAB]); prefetch_l2(&k->pmax[h]);
+                if (code == AC_RESTORE) { const Cc4Stat *st = WC(c)->st; prefetch_l2(&st->o_procs[h][0]); prefetch_l2(&st->o_svc64[h]); prefetch_l2(&st->o_nproc[h]); }
+            }
+        } else {                   /* known ports: 12 lines = 384 entries */
+            const int line = lane - 20;
+            if (line * 32 < s->n_ports) prefetch_l2(k->ports + line * 32);
+        }
+    }
     PHASE_SYNC(1);
     /* filter_actions (:466-486) looks at the sessions as they are BEFORE anything executes; blue / green sessions never go away */
     _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
@@ -336,15 +341,14 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
     }
     __syncwarp();
     /* ---- 3. execution: priority-1 ControlTraffic first (ControlTraffic.py:19), then agent order ---- */
-    if (lane == 0) {
-        _Pragma("unroll 1") for (int pass = 0; pass < 2; pass++)
-            _Pragma("unroll 1") for (int b = 0; b < CC4_NBLUE; b++) {
-                uint32_t aw = x->subw[b], code = IP_CODE(aw);
-                bool prio1 = code == AC_BLOCK || code == AC_ALLOW;
-                if ((pass == 0) != prio1 || code == AC_SLEEP) continue;
-                if (code == AC_MONITOR) monitor_one(c, b); else exec_blue(c, b, aw);
-            }
-    }
+    /* (warp-uniform: every lane runs the same action code, list scans inside are lane-parallel) */
+    _Pragma("unroll 1") for (int pass = 0; pass < 2; pass++)
+        _Pragma("unroll 1") for (int b = 0; b < CC4_NBLUE; b++) {
+            uint32_t aw = x->subw[b], code = IP_CODE(aw);
+            bool prio1 = code == AC_BLOCK || code == AC_ALLOW;
+            if ((pass == 0) != prio1 || code == AC_SLEEP || code == AC_ANALYSE) continue;
+            exec_blue(c, b, aw);
+        }
     __syncwarp();
     PHASE_SYNC(2);
     /* green agents, lane per agent (EnterpriseGreenAgent.py:42-78); the phishing side effect is order dependent and
@@ -376,8 +380,7 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
         __syncwarp();
         if (any_phish) {
             w_build_hostagents(c);
-            if (lane == 0)
-                _Pragma("unroll 1") for (int k = 0; k < 3; k++) { uint32_t m = x->g.phish[k]; while (m) { int b = __ffs(m) - 1; m &= m - 1; do_phishing(c, k * 32 + b); } }
+            _Pragma("unroll 1") for (int k = 0; k < 3; k++) { uint32_t m = x->g.phish[k]; while (m) { int b = __ffs(m) - 1; m &= m - 1; do_phishing(c, k * 32 + b); } }
             __syncwarp();
         }
     }
@@ -396,21 +399,19 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
     }
     if (lane == 0) x->sess_moved = 0;
     __syncwarp();
-    if (lane == 0) {
-        _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
-            int a = A_RED0 + r;
-            if (x->dropped[a]) continue;
-            uint32_t aw = x->subw[a];
-            int succ = exec_red(c, r, aw);
-            obs_push(c, r, succ, true, aw);
-        }
+    _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {      /* warp-uniform, in agent order */
+        int a = A_RED0 + r;
+        if (x->dropped[a]) continue;
+        uint32_t aw = x->subw[a];
+        int succ = exec_red(c, r, aw);
+        obs_push(c, r, succ, true, aw);
     }
     __syncwarp();
     PHASE_SYNC(4);
     /* ---- 4. reassignment (:278) ---- */
     w_scan_sessions(c);
     if (x->misplaced) {
-        if (lane == 0) reassign(c);
+        reassign(c);
         __syncwarp();
         w_scan_sessions(c);
     }
@@ -419,12 +420,10 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
     PHASE_SYNC(5);
     /* ---- 5. end-turn actions (:281-286): Monitor for blue, RedSessionCheck for active red ---- */
     w_monitor_all(c);
-    if (lane == 0) {
-        s->red_active = (uint8_t)active;
-        /* RedSessionCheck re-elects a primary session when ident 0 is gone (changes the session order: serial) */
-        _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++)
-            if ((active >> r & 1) && s->sess_count[r] != 0 && !(x->has0 >> r & 1)) rsc_reelect(c, r, x->n_red[r]);
-    }
+    s->red_active = (uint8_t)active;
+    /* RedSessionCheck re-elects a primary session when ident 0 is gone (changes the session order: agent by agent) */
+    _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++)
+        if ((active >> r & 1) && s->sess_count[r] != 0 && !(x->has0 >> r & 1)) rsc_reelect(c, r, x->n_red[r]);
     __syncwarp();
     if (lane < CC4_NRED && (active >> lane & 1)) {
         obs_push(c, lane, SUCC_TRUE, true, IP_MAKE(AC_RSC, 255, 15, 0, 0));
