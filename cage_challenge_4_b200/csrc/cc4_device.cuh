@@ -120,7 +120,8 @@ struct Scratch {
     int n_red[8];                                 /* sessions per agent */
     uint32_t has0, newss, misplaced;              /* bit r: agent r has ident 0 / has an abstract session whose id it does not know yet / has a session on a foreign subnet */
     uint32_t ssmask[CC4_NRED][8];                 /* bit id: server_session id known to agent r (mirror of Cc4Dyn.ss, rebuilt every tick) */
-    int reward;
+    int reward, cost;                             /* BlueRewardMachine sum / action cost of the tick */
+    uint32_t active;                              /* bit r: red agent r holds a session after this tick's reassignment */
     uint32_t blk_id[CC4_NRED + 1];                /* cached Philox block per serial stream: red agents 0..5, [6] = reset */
     uint32_t blk[CC4_NRED + 1][4];
     union {                                       /* three phase-local areas that are never live together */
@@ -150,10 +151,10 @@ struct __align__(16) WarpSmem {
  * context is passed through the thread stack (ncu r01a: the stack-resident context cost 24 % long-scoreboard stalls). */
 extern __shared__ __align__(16) unsigned char smem_raw[];
 typedef uint32_t Cx;
-#define WS(c) (reinterpret_cast<WarpSmem *>(smem_raw + (c)))
-#define DYN(c) (&WS(c)->dyn)
-#define SCR(c) (&WS(c)->x)
-#define WC(c) (&WS(c)->c)
+#define WS(cx_) (reinterpret_cast<WarpSmem *>(smem_raw + (cx_)))
+#define DYN(cx_) (&WS(cx_)->dyn)
+#define SCR(cx_) (&WS(cx_)->x)
+#define WC(cx_) (&WS(cx_)->c)
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }

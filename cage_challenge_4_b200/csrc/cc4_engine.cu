@@ -18,23 +18,21 @@
 namespace cc4 {
 
 #ifndef CC4_WARPS_PER_BLOCK
-#define CC4_WARPS_PER_BLOCK 16
+#define CC4_WARPS_PER_BLOCK 32  /* one block per SM: 1024 threads */
 #endif
-#ifndef CC4_SYNC_MASK
-#define CC4_SYNC_MASK 0x7F      /* bit i: block barrier i of the tick is enabled (tuning knob, see PHASE_SYNC) */
-#endif
-#ifndef CC4_MIN_BLOCKS
-#define CC4_MIN_BLOCKS 3        /* __launch_bounds__ min resident blocks per SM (caps registers per thread) */
+#ifndef CC4_EPB_MAX
+#define CC4_EPB_MAX 52          /* episodes resident in one block's shared memory (52 x 4 368 B = 222 KB of the 227 KB) */
 #endif
 constexpr int WARPS_PER_BLOCK = CC4_WARPS_PER_BLOCK;
+constexpr int EPB_MAX = CC4_EPB_MAX;
 constexpr int DYN_U4 = (int)(sizeof(Cc4Dyn) / 16);
 
 struct Params {
     Cc4Dyn *dyn; Cc4Stat *stat; Cc4Cold *cold;
-    int n_envs, n_alloc, steps, rng_mode;   /* n_alloc = n_envs rounded up to a whole block: every warp of the grid owns an episode */
+    int n_envs, steps, rng_mode;
     uint32_t k0, k1hi; uint64_t first_episode;
     const cc4_draw *tape; const uint32_t *seg_off; uint32_t n_segs;
-    unsigned long long *phase_clk;   /* [n_alloc][8][2] busy / barrier-wait cycles per phase (only in -DCC4_PHASE_CLOCKS builds) */
+    unsigned long long *phase_clk;   /* [n_envs][8][2] cycles per phase (only in -DCC4_PHASE_CLOCKS builds) */
 };
 
 /* ---- record movement: 128-bit coalesced ---- */
@@ -53,24 +51,6 @@ __device__ __forceinline__ void w_store(Cc4Dyn *dst, const Cc4Dyn *src)
     uint4 *g = reinterpret_cast<uint4 *>(dst);
 #pragma unroll 4
     for (int i = lane_id(); i < DYN_U4; i += 32) g[i] = d[i];
-}
-
-__device__ __forceinline__ Cx make_ctx(int warp, const Params &p, int env, int tick)
-{
-    Cx c = (Cx)(warp * (int)sizeof(WarpSmem));
-    if (lane_id() == 0) {
-        uint64_t ep = p.first_episode + (uint64_t)env;
-        WarpCtx *g = WC(c);
-        g->st = p.stat + env; g->k = p.cold + env;
-        g->steps = p.steps; g->rng_mode = p.rng_mode;
-        g->k0 = p.k0; g->k1 = p.k1hi ^ (uint32_t)(ep >> 32); g->ep_lo = (uint32_t)ep;
-        /* padding episodes (n_envs..n_alloc) have no tape: every draw of theirs fails with CC4_E_TAPE_END and yields 0 */
-        const bool has_tape = p.seg_off && env < p.n_envs;
-        g->tape = p.tape; g->seg = has_tape ? p.seg_off + (size_t)env * (p.n_segs + 1) : nullptr; g->n_segs = has_tape ? p.n_segs : 0;
-        g->tick = tick; g->env = env;
-    }
-    __syncwarp();
-    return c;
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -243,25 +223,21 @@ __device__ void w_build_hostagents(Cx c)
 }
 
 /* ------------------------------------------------------------------------------------------------ */
-/* one tick: SimulationController.step SimulationController.py:211-315                              */
+/* one tick: SimulationController.step SimulationController.py:211-315, cut into phases               */
 /* ------------------------------------------------------------------------------------------------ */
-/* PHASE_SYNC keeps the warps of a block in the same phase of the tick: they then share the instruction cache lines of
- * that phase instead of thrashing it (ncu: stall_no_inst was the top stall reason without it). */
-#ifdef CC4_PHASE_CLOCKS   /* profiling build: per-warp busy and barrier-wait cycles of every phase (tools/phase_clocks.py) */
-__device__ unsigned long long *g_phase_clk;
-#define PHASE_SYNC(i) do { if ((CC4_SYNC_MASK >> (i)) & 1) { long long t1_ = clock64(); __syncthreads(); long long t2_ = clock64(); \
-    if (lane_id() == 0 && pc_clk) { pc_clk[2 * (i)] += (unsigned long long)(t1_ - pc_t0); pc_clk[2 * (i) + 1] += (unsigned long long)(t2_ - t1_); } pc_t0 = t2_; } } while (0)
-#define PHASE_CLOCK_BEGIN(envidx) unsigned long long *pc_clk = g_phase_clk ? g_phase_clk + (size_t)(envidx) * 16 : nullptr; long long pc_t0 = clock64()
-#else
-#define PHASE_SYNC(i) do { if ((CC4_SYNC_MASK >> (i)) & 1) __syncthreads(); } while (0)
-#define PHASE_CLOCK_BEGIN(envidx) do { } while (0)
-#endif
-constexpr int N_PHASE_SYNC = __builtin_popcount(CC4_SYNC_MASK & 0x7F);
-__device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep */, const uint8_t *msgs /* [5] or null */, float *reward_out, uint8_t *done_out)
+/* One block per SM keeps up to CC4_EPB_MAX episodes resident in shared memory.  A tick is a sequence of PHASES separated
+ * by block barriers; inside a phase the block's warps take episodes from a shared counter, so (a) every warp of the SM
+ * executes the same phase of the tick at the same time and they share its instruction-cache lines (ncu: without
+ * barriers the kernel is 1.7x slower, stall_no_inst on top), and (b) a warp that drew a cheap episode (no action due)
+ * takes another one instead of waiting at the barrier for the warp that drew an expensive one.  Everything that lives
+ * across a phase boundary is in the episode's shared-memory record / scratch, never in registers. */
+enum { PH_SETUP, PH_POLICY, PH_BLUE, PH_GREEN, PH_RED, PH_REASSIGN, PH_ENDTURN, PH_FINISH, N_PHASES };
+
+/* ---- phase 0: per-tick scratch, known-session mirror, mission phase ---- */
+__device__ __forceinline__ void ph_setup(Cx c)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     const int lane = lane_id();
-    PHASE_CLOCK_BEGIN(WC(c)->env);
     WC(c)->tick = s->step;
     _Pragma("unroll 1") for (int i = lane; i <= NAG; i += 32) x->ctr[i] = 0;
     if (lane < 8) { x->n_oent[lane] = 0; x->have_first[lane] = 0; x->succ0[lane] = SUCC_UNKNOWN; x->has_act0[lane] = 0; }
@@ -282,14 +258,31 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
         if (np > s->phase) s->phase = (uint8_t)np;
     }
     __syncwarp();
-    PHASE_SYNC(0);
+}
 
-    /* ---- 1. policies (:236-248) and 2. duration queue (:245-265): one lane per blue / red actor.  The scripted red
-       agents only read their own knowledge and draw from their own stream, so the six run side by side. ---- */
+/* ---- phase 1: policies (:236-248) and duration queue (:245-265): one lane per blue / red actor.  The scripted red
+   agents only read their own knowledge and draw from their own stream, so the six run side by side.  `actions` = the
+   episode's five BlueFixedActionWrapper indices, or null for the benchmark's synthetic policy (k_rollout): index ~
+   U{0..81} (agents 0-3) / U{0..241} (agent 4), Philox keyed (policy_seed, episode, tick) exactly as oracle/cc4_oracle.c
+   cc4o_run_episodes ---- */
+__device__ __forceinline__ void ph_policy(Cx c, const int32_t *actions, uint32_t pk0, uint32_t pk1, uint64_t ep)
+{
+    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
+    const int lane = lane_id();
     int cost = 0;
     if (lane < 11) {
         uint32_t aw = ACT_SLEEP_WORD;
-        if (lane < A_RED0) { aw = blue_decode(s, lane, actions ? actions[lane] : (lane == 4 ? 145 : 49)) & ~ACT_VALID; if (IP_CODE(aw) == AC_RESTORE) cost = -1; }   /* Restore.py:70, :310-311 */
+        if (lane < A_RED0) {
+            int idx;
+            if (actions) idx = actions[lane];
+            else {
+                uint32_t cw[4] = { (uint32_t)s->step, lane == 4 ? 0xB10Fu : 0xB10Eu, (uint32_t)ep, (uint32_t)(ep >> 32) };
+                philox4x32_10(cw, pk0, pk1);
+                idx = lane == 4 ? (int)__umulhi(cw[0], 242u) : (int)__umulhi(lane == 0 ? cw[0] : lane == 1 ? cw[1] : lane == 2 ? cw[2] : cw[3], 82u);
+            }
+            aw = blue_decode(s, lane, idx) & ~ACT_VALID;
+            if (IP_CODE(aw) == AC_RESTORE) cost = -1;      /* Restore.py:70, charged on submission :310-311 */
+        }
         else if (s->red_active >> (lane - A_RED0) & 1) aw = red_policy(c, lane - A_RED0);
         uint32_t ip = s->inprog[lane];
         if (IP_CODE(ip) == IP_NONE) ip = aw | (uint32_t)c_duration[IP_CODE(aw)] << 26;
@@ -303,9 +296,10 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o);
+    if (lane == 0) x->cost = cost;
     __syncwarp();
     /* The due actions are known: pull the cold-record lines they will touch towards L2 now, so that the dependent reads of
-       the (serial) action code below find them there instead of in DRAM. */
+       the (serial) action code of the next phases find them there instead of in DRAM. */
     {
         const Cc4Cold *k = WC(c)->k;
         if (lane < 9) {            /* the service table: green LocalWork reads one entry per agent every tick */
@@ -324,8 +318,14 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
             if (line * 32 < s->n_ports) prefetch_l2(k->ports + line * 32);
         }
     }
-    PHASE_SYNC(1);
-    /* filter_actions (:466-486) looks at the sessions as they are BEFORE anything executes; blue / green sessions never go away */
+}
+
+/* ---- phase 2: filter_actions (:466-486), then blue execution ---- */
+__device__ __forceinline__ void ph_blue(Cx c)
+{
+    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
+    const int lane = lane_id();
+    /* filter_actions looks at the sessions as they are BEFORE anything executes; blue / green sessions never go away */
     _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
         uint32_t w = x->subw[A_RED0 + r];
         bool needs = !(IP_CODE(w) == AC_SLEEP || IP_CODE(w) == AC_INVALID), found = false;
@@ -340,8 +340,8 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
         if (lane == 0) x->dropped[A_RED0 + r] = needs && !found;
     }
     __syncwarp();
-    /* ---- 3. execution: priority-1 ControlTraffic first (ControlTraffic.py:19), then agent order ---- */
-    /* (warp-uniform: every lane runs the same action code, list scans inside are lane-parallel) */
+    /* execution: priority-1 ControlTraffic first (ControlTraffic.py:19), then agent order; warp-uniform: every lane runs the
+       same action code, list scans inside are lane-parallel */
     _Pragma("unroll 1") for (int pass = 0; pass < 2; pass++)
         _Pragma("unroll 1") for (int b = 0; b < CC4_NBLUE; b++) {
             uint32_t aw = x->subw[b], code = IP_CODE(aw);
@@ -350,41 +350,50 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
             exec_blue(c, b, aw);
         }
     __syncwarp();
-    PHASE_SYNC(2);
-    /* green agents, lane per agent (EnterpriseGreenAgent.py:42-78); the phishing side effect is order dependent and
-       replayed below in agent order */
-    {
-        if (lane < 8) {     /* GreenAccessService destination table of this tick's phase, one lane per source subnet */
-            uint32_t allowed = c_green_allowed[s->phase][lane];
-            uint64_t cum = 0; uint32_t tot = 0;
+}
+
+/* ---- phase 3: green agents, lane per agent (EnterpriseGreenAgent.py:42-78); the phishing side effect is order
+   dependent and replayed afterwards in agent order ---- */
+__device__ __forceinline__ void ph_green(Cx c)
+{
+    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
+    const int lane = lane_id();
+    if (lane < 8) {     /* GreenAccessService destination table of this tick's phase, one lane per source subnet */
+        uint32_t allowed = c_green_allowed[s->phase][lane];
+        uint64_t cum = 0; uint32_t tot = 0;
 #pragma unroll
-            for (int sn = 0; sn < 8; sn++) { if (allowed >> sn & 1) tot += s->nserver[sn]; cum |= (uint64_t)tot << (8 * sn); }
-            x->g.as_cum[lane] = cum;
-        }
-        __syncwarp();
-        int rew = 0;
-        uint32_t *ev_words = reinterpret_cast<uint32_t *>(s->ev);
-        const int ng = s->ngreen;
-        uint32_t any_phish = 0;
-        _Pragma("unroll 1") for (int k = 0; k < 3; k++) {
-            int g = k * 32 + lane;
-            int gr = g < ng ? green_tick(c, g, ev_words) : 0;
-            rew -= gr & 0xFF;
-            uint32_t bal = __ballot_sync(0xFFFFFFFFu, (gr & GREEN_PHISH) != 0);
-            if (lane == 0) x->g.phish[k] = bal;
-            any_phish |= bal;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) rew += __shfl_xor_sync(0xFFFFFFFFu, rew, o);
-        if (lane == 0) x->reward += rew;
-        __syncwarp();
-        if (any_phish) {
-            w_build_hostagents(c);
-            _Pragma("unroll 1") for (int k = 0; k < 3; k++) { uint32_t m = x->g.phish[k]; while (m) { int b = __ffs(m) - 1; m &= m - 1; do_phishing(c, k * 32 + b); } }
-            __syncwarp();
-        }
+        for (int sn = 0; sn < 8; sn++) { if (allowed >> sn & 1) tot += s->nserver[sn]; cum |= (uint64_t)tot << (8 * sn); }
+        x->g.as_cum[lane] = cum;
     }
-    PHASE_SYNC(3);
+    __syncwarp();
+    int rew = 0;
+    uint32_t *ev_words = reinterpret_cast<uint32_t *>(s->ev);
+    const int ng = s->ngreen;
+    uint32_t any_phish = 0;
+    _Pragma("unroll 1") for (int k = 0; k < 3; k++) {
+        int g = k * 32 + lane;
+        int gr = g < ng ? green_tick(c, g, ev_words) : 0;
+        rew -= gr & 0xFF;
+        uint32_t bal = __ballot_sync(0xFFFFFFFFu, (gr & GREEN_PHISH) != 0);
+        if (lane == 0) x->g.phish[k] = bal;
+        any_phish |= bal;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rew += __shfl_xor_sync(0xFFFFFFFFu, rew, o);
+    if (lane == 0) x->reward += rew;
+    __syncwarp();
+    if (any_phish) {
+        w_build_hostagents(c);
+        _Pragma("unroll 1") for (int k = 0; k < 3; k++) { uint32_t m = x->g.phish[k]; while (m) { int b = __ffs(m) - 1; m &= m - 1; do_phishing(c, k * 32 + b); } }
+        __syncwarp();
+    }
+}
+
+/* ---- phase 4: red execution in agent order ---- */
+__device__ __forceinline__ void ph_red(Cx c)
+{
+    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
+    const int lane = lane_id();
     /* resolve the session each due red action names (lane per pool entry); valid until a session is deleted */
     _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
         uint32_t w = x->subw[A_RED0 + r], id = IP_SESSION(w);
@@ -403,12 +412,17 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
         int a = A_RED0 + r;
         if (x->dropped[a]) continue;
         uint32_t aw = x->subw[a];
-        int succ = exec_red(c, r, aw);
+        int code = IP_CODE(aw);
+        int succ = code == AC_SLEEP ? SUCC_UNKNOWN : code == AC_INVALID ? SUCC_FALSE : exec_red(c, r, aw);
         obs_push(c, r, succ, true, aw);
     }
     __syncwarp();
-    PHASE_SYNC(4);
-    /* ---- 4. reassignment (:278) ---- */
+}
+
+/* ---- phase 5: reassignment (:278) ---- */
+__device__ __forceinline__ void ph_reassign(Cx c)
+{
+    Scratch *x = SCR(c);
     w_scan_sessions(c);
     if (x->misplaced) {
         reassign(c);
@@ -417,8 +431,16 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
     }
     uint32_t active = 0;
     _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) active |= (x->n_red[r] > 0) << r;    /* :896-903: active iff it holds a session */
-    PHASE_SYNC(5);
-    /* ---- 5. end-turn actions (:281-286): Monitor for blue, RedSessionCheck for active red ---- */
+    if (lane_id() == 0) x->active = active;
+    __syncwarp();
+}
+
+/* ---- phase 6: end-turn actions (:281-286): Monitor for blue, RedSessionCheck for active red ---- */
+__device__ __forceinline__ void ph_endturn(Cx c)
+{
+    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
+    const int lane = lane_id();
+    const uint32_t active = x->active;
     w_monitor_all(c);
     s->red_active = (uint8_t)active;
     /* RedSessionCheck re-elects a primary session when ident 0 is gone (changes the session order: agent by agent) */
@@ -431,10 +453,15 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
         agent_end_turn(c, lane);
     }
     __syncwarp();
-    PHASE_SYNC(6);
-    if (lane == 0) {
+}
+
+/* ---- phase 7: counters, done (:297-300), reward (BlueRewardMachine.py:70-121), messages ---- */
+__device__ __forceinline__ void ph_finish(Cx c, const uint8_t *msgs /* [5] or null */, float *reward_out, bool accumulate, uint8_t *done_out)
+{
+    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
+    if (lane_id() == 0) {
+        const uint32_t active = x->active;
         s->fsm_started |= (uint8_t)active;
-        /* ---- 6. counters, done (:297-300), reward (BlueRewardMachine.py:70-121) ---- */
         s->step++;
         s->done = s->step >= WC(c)->steps - 1;
         int rew = x->reward;
@@ -445,7 +472,7 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
             if (IP_CODE(w) == AC_IMPACT && (active >> r & 1)) rew += c_reward[s->phase][IP_HOST(w) >> 4][2];
         }
         _Pragma("unroll 1") for (int b = 0; b < CC4_NBLUE; b++) s->msgs[b] = msgs ? msgs[b] : 0;
-        if (reward_out) *reward_out = (float)(rew + cost);
+        if (reward_out) { if (accumulate) *reward_out += (float)(rew + x->cost); else *reward_out = (float)(rew + x->cost); }
         if (done_out) *done_out = s->done;
         if (WC(c)->rng_mode == 1) {
             _Pragma("unroll 1") for (int a = 0; a < NAG; a++) {
@@ -457,61 +484,121 @@ __device__ void w_tick(Cx c, const int32_t *actions /* [5] or null = all Sleep *
     __syncwarp();
 }
 
+/* ---- episode scheduling inside a phase ----
+ * (Measured alternative, r01k: per-phase work queues without block barriers — a warp that finishes phase p on one episode
+ * goes on to phase p+1 of whatever episode is ready — raise warp utilisation but let two phases be live at once; the
+ * instruction-cache misses cost more than the idle time saved: 1.08 ms against 0.97 ms per tick.) */
+#ifndef CC4_STATIC_ASSIGN
+#define CC4_STATIC_ASSIGN 0     /* 1: episode e of a block is always handled by warp e % warps (tuning knob; default: shared counter) */
+#endif
+#ifdef CC4_PHASE_CLOCKS   /* profiling build (tools/phase_clocks.py): per episode [18]: [2p] = busy cycles of phase p; [2p+1] of a block's
+                             first episode = wall cycles of phase p for the block, barrier included */
+__device__ unsigned long long *g_phase_clk;
+#define PC_STRIDE 18
+#endif
+template <class F> __device__ __forceinline__ void each_episode(int ph, int first, int n_local, int *next, F f)
+{
+#ifdef CC4_PHASE_CLOCKS
+    const long long tb0 = clock64();
+#endif
+#if CC4_STATIC_ASSIGN
+    _Pragma("unroll 1") for (int e = threadIdx.x >> 5; e < n_local; e += WARPS_PER_BLOCK) {
+#else
+    _Pragma("unroll 1") for (;;) {
+        int e = 0;
+        if (lane_id() == 0) e = atomicAdd(&next[ph], 1);
+        e = __shfl_sync(0xFFFFFFFFu, e, 0);
+        if (e >= n_local) break;
+#endif
+        const Cx c = (Cx)(e * (int)sizeof(WarpSmem));
+#ifdef CC4_PHASE_CLOCKS
+        const long long t0 = clock64();
+        f(c, e);
+        if (lane_id() == 0 && g_phase_clk) g_phase_clk[(size_t)(first + e) * PC_STRIDE + 2 * ph] += (unsigned long long)(clock64() - t0);
+#else
+        f(c, e);
+#endif
+    }
+    __syncthreads();
+#ifdef CC4_PHASE_CLOCKS
+    if (threadIdx.x == 0 && g_phase_clk && n_local > 0) g_phase_clk[(size_t)first * PC_STRIDE + 2 * ph + 1] += (unsigned long long)(clock64() - tb0);
+#endif
+}
+
+__device__ __forceinline__ void init_ctx(Cx c, const Params &p, int env, int tick)
+{
+    if (lane_id() == 0) {
+        uint64_t ep = p.first_episode + (uint64_t)env;
+        WarpCtx *g = WC(c);
+        g->st = p.stat + env; g->k = p.cold + env;
+        g->steps = p.steps; g->rng_mode = p.rng_mode;
+        g->k0 = p.k0; g->k1 = p.k1hi ^ (uint32_t)(ep >> 32); g->ep_lo = (uint32_t)ep;
+        g->tape = p.tape; g->seg = p.seg_off ? p.seg_off + (size_t)env * (p.n_segs + 1) : nullptr; g->n_segs = p.seg_off ? p.n_segs : 0;
+        g->tick = tick; g->env = env;
+    }
+    __syncwarp();
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* kernels                                                                                          */
 /* ------------------------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, CC4_MIN_BLOCKS)
-k_step(Params p, int env0, const int32_t *actions, const uint8_t *msgs, uint8_t *obs, float *reward, uint8_t *done, int flags)
+struct StepIO { const int32_t *actions; const uint8_t *msgs; uint8_t *obs; float *reward; uint8_t *done; int flags; };
+
+/* Block b owns episodes [env0 + b*epb, min(env0 + (b+1)*epb, env_end)); env0 / env_end: the slice of the batch this
+ * launch covers (the chunked host path launches several slices). */
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
+k_step(Params p, int env0, int env_end, int epb, StepIO io)
 {
-    int env = env0 + blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);   /* env0: first episode of this launch (chunked host path) */
-    const bool valid = env < p.n_envs;     /* padding episodes (n_envs..n_alloc) run with Sleep inputs and write no outputs */
-    Cx c = make_ctx(threadIdx.x >> 5, p, env, 0);
-    WarpSmem *w = WS(c);
-    w_load(&w->dyn, p.dyn + env);
-    w_tick(c, valid ? actions + (size_t)env * 5 : nullptr, valid && msgs ? msgs + (size_t)env * 5 : nullptr,
-           valid && (flags & CC4_STEP_REWARD) && reward ? reward + env : nullptr, valid && done ? done + env : nullptr);
-    {
-        PHASE_CLOCK_BEGIN(env);
-        PHASE_SYNC(7);      /* phase 7 of the profile = the barrier wait only; the observation writer + store follow it */
-    }
-    if (valid && (flags & CC4_STEP_OBS) && obs) w_write_obs(&w->dyn, &w->x, obs, env);
-    w_store(p.dyn + env, &w->dyn);
+    __shared__ int next[N_PHASES + 1];
+    const int first = env0 + blockIdx.x * epb, n_local = min(epb, env_end - first);
+    if (threadIdx.x <= N_PHASES) next[threadIdx.x] = 0;
+    __syncthreads();
+    each_episode(PH_SETUP, first, n_local, next, [&](Cx c, int e) { init_ctx(c, p, first + e, 0); w_load(DYN(c), p.dyn + first + e); ph_setup(c); });
+    each_episode(PH_POLICY, first, n_local, next, [&](Cx c, int e) { ph_policy(c, io.actions + (size_t)(first + e) * 5, 0, 0, 0); });
+    each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { ph_blue(c); });
+    each_episode(PH_GREEN, first, n_local, next, [&](Cx c, int) { ph_green(c); });
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c); });
+    each_episode(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { ph_reassign(c); });
+    each_episode(PH_ENDTURN, first, n_local, next, [&](Cx c, int) { ph_endturn(c); });
+    each_episode(PH_FINISH, first, n_local, next, [&](Cx c, int e) {
+        const int env = first + e;
+        ph_finish(c, io.msgs ? io.msgs + (size_t)env * 5 : nullptr, (io.flags & CC4_STEP_REWARD) && io.reward ? io.reward + env : nullptr, false,
+                  io.done ? io.done + env : nullptr);
+        if ((io.flags & CC4_STEP_OBS) && io.obs) w_write_obs(DYN(c), SCR(c), io.obs, env);
+        w_store(p.dyn + env, DYN(c));
+    });
 }
 
-/* fused ticks with the benchmark's synthetic blue policy: index ~ U{0..81} (agents 0-3) / U{0..241} (agent 4),
- * Philox keyed (policy_seed, episode, tick) exactly as oracle/cc4_oracle.c cc4o_run_episodes */
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, CC4_MIN_BLOCKS)
-k_rollout(Params p, int n_ticks, uint32_t pk0, uint32_t pk1, float *reward_sum, int flags)
+/* n_ticks fused ticks with the benchmark's synthetic blue policy (see ph_policy); the state stays in shared memory */
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
+k_rollout(Params p, int epb, int n_ticks, uint32_t pk0, uint32_t pk1, float *reward_sum, int flags)
 {
-    int env = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    const bool valid = env < p.n_envs;
-    Cx c = make_ctx(threadIdx.x >> 5, p, env, 0);
-    WarpSmem *w = WS(c);
-    w_load(&w->dyn, p.dyn + env);
-    uint64_t ep = p.first_episode + (uint64_t)env;
-    float total = 0.f;
-    __shared__ int32_t act_s[WARPS_PER_BLOCK][8];
-    __shared__ float rew_s[WARPS_PER_BLOCK];
-    int32_t *act = act_s[threadIdx.x >> 5];
+    __shared__ int next[N_PHASES + 1];
+    __shared__ int alive;
+    const int first = blockIdx.x * epb, n_local = min(epb, p.n_envs - first);
+    _Pragma("unroll 1") for (int e = threadIdx.x >> 5; e < n_local; e += WARPS_PER_BLOCK) { Cx c = (Cx)(e * (int)sizeof(WarpSmem)); init_ctx(c, p, first + e, 0); w_load(DYN(c), p.dyn + first + e); }
     _Pragma("unroll 1") for (int t = 0; t < n_ticks; t++) {
-        if (__syncthreads_and(w->dyn.done)) break;
-        if (w->dyn.done) {      /* this episode is over but a sibling warp still runs: keep in step with the block's barriers */
-            _Pragma("unroll 1") for (int k = 0; k < N_PHASE_SYNC; k++) __syncthreads();
-            continue;
-        }
-        if (lane_id() == 0) {
-            uint32_t tk = w->dyn.step;
-            uint32_t c1[4] = { tk, 0xB10Eu, (uint32_t)ep, (uint32_t)(ep >> 32) }, c2[4] = { tk, 0xB10Fu, (uint32_t)ep, (uint32_t)(ep >> 32) };
-            philox4x32_10(c1, pk0, pk1); philox4x32_10(c2, pk0, pk1);
-            _Pragma("unroll 1") for (int b = 0; b < 4; b++) act[b] = (int32_t)__umulhi(c1[b], 82u);
-            act[4] = (int32_t)__umulhi(c2[0], 242u);
-        }
-        __syncwarp();
-        w_tick(c, act, nullptr, &rew_s[threadIdx.x >> 5], nullptr);
-        if (lane_id() == 0) total += rew_s[threadIdx.x >> 5];
+        __syncthreads();
+        if (threadIdx.x <= N_PHASES) next[threadIdx.x] = 0;
+        if (threadIdx.x == 0) alive = 0;
+        __syncthreads();
+        /* an episode that is over keeps its state; the block stops when all of its episodes are over */
+        each_episode(PH_SETUP, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) { if (lane_id() == 0) atomicAdd(&alive, 1); ph_setup(c); } });
+        if (alive == 0) break;
+        each_episode(PH_POLICY, first, n_local, next, [&](Cx c, int e) { if (!DYN(c)->done) ph_policy(c, nullptr, pk0, pk1, p.first_episode + (uint64_t)(first + e)); });
+        each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_blue(c); });
+        each_episode(PH_GREEN, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_green(c); });
+        each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_red(c); });
+        each_episode(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_reassign(c); });
+        each_episode(PH_ENDTURN, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_endturn(c); });
+        /* `done` flips in this phase: the ticks that follow skip the episode, this tick must not look at the flag again */
+        each_episode(PH_FINISH, first, n_local, next, [&](Cx c, int e) {
+            if (DYN(c)->done) return;
+            ph_finish(c, nullptr, (flags & CC4_STEP_REWARD) && reward_sum ? reward_sum + first + e : nullptr, true, nullptr);
+        });
     }
-    if (valid && (flags & CC4_STEP_REWARD) && reward_sum && lane_id() == 0) reward_sum[env] += total;
-    w_store(p.dyn + env, &w->dyn);
+    __syncthreads();
+    _Pragma("unroll 1") for (int e = threadIdx.x >> 5; e < n_local; e += WARPS_PER_BLOCK) w_store(p.dyn + first + e, DYN((Cx)(e * (int)sizeof(WarpSmem))));
 }
 
 /* ---- reset ---- */
@@ -578,7 +665,8 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
     uint32_t *z = reinterpret_cast<uint32_t *>(rs);
     _Pragma("unroll 1") for (int i = lane_id(); i < (int)(sizeof(ResetSmem) / 4); i += 32) z[i] = 0;
     __syncwarp();
-    Cx c = make_ctx(0, p, env, -1);
+    Cx c = 0;
+    init_ctx(c, p, env, -1);
     if (lane_id() <= CC4_NRED) SCR(c)->blk_id[lane_id()] = 0xFFFFFFFFu;
     __syncwarp();
     if (lane_id() == 0) {
@@ -673,7 +761,7 @@ static int set_err(int code, const char *fmt, const char *detail)
 
 struct cc4_handle {
     Params p;
-    int device;
+    int device, n_sm;
     uint64_t launches;
     int32_t *stage_actions; uint8_t *stage_msgs, *stage_obs, *stage_mask, *stage_done; float *stage_reward;   /* device staging for cc4_step_host */
     cudaStream_t pipe[2]; cudaEvent_t ev_in, ev_out[2];   /* chunk pipeline of cc4_step_host */
@@ -689,14 +777,15 @@ extern "C" int cc4_create(int n_envs, int device, uint64_t seed, uint64_t first_
     if (!h) return set_err(CC4_ERR_STATE, "cc4_create: out of host memory%s", "");
     memset(h, 0, sizeof *h);
     h->device = device;
-    h->p.n_envs = n_envs; h->p.n_alloc = (n_envs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK * WARPS_PER_BLOCK; h->p.steps = steps; h->p.rng_mode = rng_mode;
+    h->p.n_envs = n_envs; h->p.steps = steps; h->p.rng_mode = rng_mode;
+    CUDA_TRY(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device));
     h->p.k0 = (uint32_t)seed; h->p.k1hi = (uint32_t)(seed >> 32); h->p.first_episode = first_episode;
-    CUDA_TRY(cudaMalloc(&h->p.dyn, sizeof(Cc4Dyn) * (size_t)h->p.n_alloc));
-    CUDA_TRY(cudaMalloc(&h->p.stat, sizeof(Cc4Stat) * (size_t)h->p.n_alloc));
-    CUDA_TRY(cudaMalloc(&h->p.cold, sizeof(Cc4Cold) * (size_t)h->p.n_alloc));
-    CUDA_TRY(cudaMemset(h->p.dyn, 0, sizeof(Cc4Dyn) * (size_t)h->p.n_alloc));
-    CUDA_TRY(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * WARPS_PER_BLOCK)));
-    CUDA_TRY(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * WARPS_PER_BLOCK)));
+    CUDA_TRY(cudaMalloc(&h->p.dyn, sizeof(Cc4Dyn) * (size_t)n_envs));
+    CUDA_TRY(cudaMalloc(&h->p.stat, sizeof(Cc4Stat) * (size_t)n_envs));
+    CUDA_TRY(cudaMalloc(&h->p.cold, sizeof(Cc4Cold) * (size_t)n_envs));
+    CUDA_TRY(cudaMemset(h->p.dyn, 0, sizeof(Cc4Dyn) * (size_t)n_envs));
+    CUDA_TRY(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * EPB_MAX)));
+    CUDA_TRY(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * EPB_MAX)));
     CUDA_TRY(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResetSmem)));
     *out = h;
     return CC4_OK;
@@ -742,7 +831,7 @@ extern "C" int cc4_reset(cc4_handle *h, uint8_t *obs_dev, uint8_t *mask_dev, voi
     if (!h) return set_err(CC4_ERR_ARG, "cc4_reset: null handle%s", "");
     if (h->p.rng_mode == 1 && !h->p.tape) return set_err(CC4_ERR_STATE, "cc4_reset: tape mode without cc4_set_tape%s", "");
     CUDA_TRY(cudaSetDevice(h->device));
-    k_reset<<<h->p.n_alloc, 32, sizeof(ResetSmem), (cudaStream_t)stream>>>(h->p, obs_dev, mask_dev);
+    k_reset<<<h->p.n_envs, 32, sizeof(ResetSmem), (cudaStream_t)stream>>>(h->p, obs_dev, mask_dev);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return CC4_OK;
@@ -777,13 +866,24 @@ extern "C" int cc4_reset_host(cc4_handle *h, uint8_t *obs_host, uint8_t *mask_ho
     return CC4_OK;
 }
 
+/* Episodes per block for a launch over n episodes: the fewest whole waves of one block per SM that hold them, then the
+ * episodes spread evenly over those waves (65 536 episodes on 148 SMs: 9 waves x 148 blocks x 50 episodes, the last wave
+ * 86 % full, instead of 52 per block and a 10th wave at 52 %). */
+static int episodes_per_block(const cc4_handle *h, size_t n)
+{
+    size_t per_wave = (size_t)h->n_sm * EPB_MAX, waves = (n + per_wave - 1) / per_wave;
+    size_t epb = (n + waves * h->n_sm - 1) / (waves * h->n_sm);
+    return (int)(epb < 1 ? 1 : epb > EPB_MAX ? EPB_MAX : epb);
+}
+
 extern "C" int cc4_step(cc4_handle *h, const int32_t *actions_dev, const uint8_t *msgs_dev, uint8_t *obs_dev, float *reward_dev,
                         uint8_t *done_dev, int flags, void *stream)
 {
     if (!h || !actions_dev) return set_err(CC4_ERR_ARG, "cc4_step: null handle or actions%s", "");
     CUDA_TRY(cudaSetDevice(h->device));
-    int blocks = h->p.n_alloc / WARPS_PER_BLOCK;
-    k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * WARPS_PER_BLOCK, (cudaStream_t)stream>>>(h->p, 0, actions_dev, msgs_dev, obs_dev, reward_dev, done_dev, flags);
+    const int epb = episodes_per_block(h, (size_t)h->p.n_envs), blocks = (h->p.n_envs + epb - 1) / epb;
+    StepIO io = { actions_dev, msgs_dev, obs_dev, reward_dev, done_dev, flags };
+    k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * (size_t)epb, (cudaStream_t)stream>>>(h->p, 0, h->p.n_envs, epb, io);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return CC4_OK;
@@ -812,20 +912,20 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
     for (int i = 0; i < 2; i++) CUDA_TRY(cudaStreamWaitEvent(h->pipe[i], h->ev_in, 0));
     const bool want_obs = obs_host && (flags & CC4_STEP_OBS), want_rew = reward_host && (flags & CC4_STEP_REWARD);
     size_t chunk = (n + CC4_HOST_CHUNKS - 1) / CC4_HOST_CHUNKS;
-    chunk = (chunk + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK * WARPS_PER_BLOCK;
-    if (chunk < 2048) chunk = 2048;     /* small batches: one chunk (a launch per few hundred episodes would be launch bound) */
+    {   /* whole waves of full blocks per chunk */
+        size_t wave = (size_t)h->n_sm * EPB_MAX;
+        chunk = (chunk + wave - 1) / wave * wave;
+    }
     int k = 0;
     for (size_t e0 = 0; e0 < n; e0 += chunk, k ^= 1) {
         size_t cnt = n - e0 < chunk ? n - e0 : chunk;
         cudaStream_t st = h->pipe[k];
         CUDA_TRY(cudaMemcpyAsync(h->stage_actions + e0 * 5, actions_host + e0 * 5, cnt * 5 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         if (msgs_host) CUDA_TRY(cudaMemcpyAsync(h->stage_msgs + e0 * 5, msgs_host + e0 * 5, cnt * 5, cudaMemcpyHostToDevice, st));
-        int blocks = (int)((cnt + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-        Params p = h->p;
-        if ((size_t)p.n_envs > e0 + cnt) p.n_envs = (int)(e0 + cnt);     /* episodes past the chunk belong to a later launch */
-        k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * WARPS_PER_BLOCK, st>>>(
-            p, (int)e0, h->stage_actions, msgs_host ? h->stage_msgs : nullptr, want_obs ? h->stage_obs : nullptr,
-            want_rew ? h->stage_reward : nullptr, done_host ? h->stage_done : nullptr, flags);
+        const int epb = episodes_per_block(h, cnt), blocks = (int)((cnt + epb - 1) / epb);
+        StepIO io = { h->stage_actions, msgs_host ? h->stage_msgs : nullptr, want_obs ? h->stage_obs : nullptr,
+                      want_rew ? h->stage_reward : nullptr, done_host ? h->stage_done : nullptr, flags };
+        k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * (size_t)epb, st>>>(h->p, (int)e0, (int)(e0 + cnt), epb, io);
         h->launches++;
         CUDA_TRY(cudaGetLastError());
         if (want_obs) CUDA_TRY(cudaMemcpyAsync(obs_host + e0 * CC4_N_BLUE * CC4_OBS_LEN, h->stage_obs + e0 * CC4_N_BLUE * CC4_OBS_LEN, cnt * CC4_N_BLUE * CC4_OBS_LEN, cudaMemcpyDeviceToHost, st));
@@ -841,28 +941,28 @@ extern "C" int cc4_rollout(cc4_handle *h, int n_ticks, uint64_t policy_seed, flo
 {
     if (!h || n_ticks < 0) return set_err(CC4_ERR_ARG, "cc4_rollout: bad argument%s", "");
     CUDA_TRY(cudaSetDevice(h->device));
-    int blocks = h->p.n_alloc / WARPS_PER_BLOCK;
-    k_rollout<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * WARPS_PER_BLOCK, (cudaStream_t)stream>>>(
-        h->p, n_ticks, (uint32_t)policy_seed ^ 0x5EEDu, (uint32_t)(policy_seed >> 32), reward_sum_dev, flags);
+    const int epb = episodes_per_block(h, (size_t)h->p.n_envs), blocks = (h->p.n_envs + epb - 1) / epb;
+    k_rollout<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * (size_t)epb, (cudaStream_t)stream>>>(
+        h->p, epb, n_ticks, (uint32_t)policy_seed ^ 0x5EEDu, (uint32_t)(policy_seed >> 32), reward_sum_dev, flags);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return CC4_OK;
 }
 
-/* profiling builds only (-DCC4_PHASE_CLOCKS): out_host uint64 [n_envs][8][2] accumulated busy / barrier-wait cycles */
+/* profiling builds only (-DCC4_PHASE_CLOCKS): out_host uint64 [n_envs][18], see each_episode */
 extern "C" int cc4_phase_clocks(cc4_handle *h, unsigned long long *out_host, int reset)
 {
 #ifdef CC4_PHASE_CLOCKS
     if (!h || !out_host) return set_err(CC4_ERR_ARG, "cc4_phase_clocks: null%s", "");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaDeviceSynchronize());
-    size_t bytes = (size_t)h->p.n_alloc * 16 * sizeof(unsigned long long);
+    size_t bytes = (size_t)h->p.n_envs * PC_STRIDE * sizeof(unsigned long long);
     if (!h->p.phase_clk) {
         CUDA_TRY(cudaMalloc(&h->p.phase_clk, bytes));
         CUDA_TRY(cudaMemset(h->p.phase_clk, 0, bytes));
         CUDA_TRY(cudaMemcpyToSymbol(g_phase_clk, &h->p.phase_clk, sizeof(void *)));
     }
-    CUDA_TRY(cudaMemcpy(out_host, h->p.phase_clk, (size_t)h->p.n_envs * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out_host, h->p.phase_clk, bytes, cudaMemcpyDeviceToHost));
     if (reset) CUDA_TRY(cudaMemset(h->p.phase_clk, 0, bytes));
     return CC4_OK;
 #else

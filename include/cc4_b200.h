@@ -111,7 +111,8 @@ int cc4_export_canon(cc4_handle *h, int env, int32_t *out_host, int cap, int *n_
 int cc4_launch_count(cc4_handle *h, uint64_t *out);
 
 /* Profiling builds only (compiled with -DCC4_PHASE_CLOCKS; otherwise CC4_ERR_STATE): accumulated busy / barrier-wait
- * cycles of every phase of the tick per episode, out_host uint64 [n_envs][8][2]; reset != 0 clears the counters.
+ * cycles of every phase of the tick per episode, out_host uint64 [n_envs][18] ([2p] busy cycles of phase p; [2p+1] of a
+ * block's first episode: wall cycles of phase p for the block, barrier included); reset != 0 clears the counters.
  * The first call arms the counters.  Synchronises the device. */
 int cc4_phase_clocks(cc4_handle *h, unsigned long long *out_host, int reset);
 

@@ -63,4 +63,9 @@ def main():
         st = ", ".join(f"{s[6:]} {100 * v / max(1, d[1]):.0f}%" for s, v in d[3].most_common(2))
         print(f"{k[0].split('/')[-1]}:{k[1]:4d} inst {100 * d[0] / tot_i:5.1f}% samp {100 * d[1] / tot_s:5.1f}% [{st}] {src_text.get(k, '').strip()[:110]}")
 
+    if "--by-inst" in sys.argv:
+        print("\nhot lines by instructions")
+        for k, d in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:nlines]:
+            print(f"{k[0].split('/')[-1]}:{k[1]:4d} inst {100 * d[0] / tot_i:5.1f}% samp {100 * d[1] / tot_s:5.1f}% lanes {d[2] / max(1, d[0]):4.1f} {src_text.get(k, '').strip()[:120]}")
+
 main()

@@ -5,9 +5,10 @@ build of the engine (-DCC4_PHASE_CLOCKS adds clock64() reads around the block ba
     python tools/phase_clocks.py --build          # here: nvcc the profiling variant into cage_challenge_4_b200/variants/
     python tools/phase_clocks.py [--envs 65536 --warm 150 --ticks 50]     # on the GPU box
 
-Phase i = the code between block barrier i-1 and barrier i of w_tick (cc4_engine.cu): 0 tick setup, 1 policies +
-duration queue, 2 filter + blue actions, 3 green agents + phishing, 4 red actions, 5 session scan + reassignment,
-6 Monitor + RedSessionCheck + FSM digest, 7 counters / reward (the observation writer and the store follow barrier 7).
+Phases (cc4_engine.cu, enum PH_*): 0 load + tick setup, 1 policies + duration queue, 2 filter + blue actions, 3 green
+agents + phishing, 4 red actions, 5 session scan + reassignment, 6 Monitor + RedSessionCheck + FSM digest, 7 counters /
+reward + observation vectors + store.  "busy" = cycles the warp that took an episode spent on it; "wall" = cycles of the
+whole block from the start of the phase to past its barrier; warp util = busy x episodes / (warps x wall).
 """
 import ctypes as C, json, os, subprocess, sys
 
@@ -29,7 +30,7 @@ from cage_challenge_4_b200 import BatchedCC4, _native
 def arg(name, default):
     return int(sys.argv[sys.argv.index(name) + 1]) if name in sys.argv else default
 
-n, warm, ticks, wpb = arg("--envs", 65536), arg("--warm", 150), arg("--ticks", 50), arg("--wpb", 16)
+n, warm, ticks, wpb = arg("--envs", 65536), arg("--warm", 150), arg("--ticks", 50), arg("--wpb", 32)
 env = BatchedCC4(n, device=0, seed=0)
 env.reset()
 g = torch.Generator(device="cuda").manual_seed(0)
@@ -37,19 +38,23 @@ def acts():
     return torch.stack([torch.randint(0, k, (n,), generator=g, device="cuda") for k in (82, 82, 82, 82, 242)], 1).to(torch.int32).contiguous()
 for _ in range(warm):
     env.step(acts())
-buf = np.zeros((n, 8, 2), dtype=np.uint64)
+buf = np.zeros((n, 18), dtype=np.uint64)
 _native.check(env._L.cc4_phase_clocks(env._h, buf.ctypes.data, 1), "cc4_phase_clocks")     # arms the counters
 for _ in range(ticks):
     env.step(acts())
 _native.check(env._L.cc4_phase_clocks(env._h, buf.ctypes.data, 1), "cc4_phase_clocks")
-busy, wait = buf[:, :, 0].astype(np.float64) / ticks, buf[:, :, 1].astype(np.float64) / ticks
-nb = n // wpb
-bb = busy[:nb * wpb].reshape(nb, wpb, 8)
-tot = (busy + wait).sum(1).mean()
-print(f"{n} episodes, {ticks} ticks after {warm} warm-up ticks; cycles per tick per warp (mean {tot:.0f} inside the barriers)")
-print(f"{'phase':>5} {'busy':>8} {'wait':>8} {'blkmax':>8} {'p50':>8} {'p90':>8} {'p99':>8} {'max':>8}  busy% wait%")
+busy = buf[:, 0:16:2].astype(np.float64) / ticks        # per episode: cycles the warp that took it spent on the phase
+wall = buf[:, 1:16:2].astype(np.float64) / ticks        # per block (slot of its first episode): phase start -> past the barrier
+blocks = wall.sum(1) > 0
+nblk = int(blocks.sum())
+epb = n / max(1, nblk)
+names = ["load+setup", "policies", "blue", "green", "red", "reassign", "end turn", "finish+obs+store"]
+print(f"{n} episodes in {nblk} blocks ({epb:.1f} per block, {wpb} warps), {ticks} ticks after {warm} warm-up ticks")
+print(f"block wall per tick {wall[blocks].sum(1).mean():.0f} cycles; episode busy per tick {busy.sum(1).mean():.0f} cycles")
+print(f"{'phase':>18} {'busy/ep':>9} {'p90':>8} {'p99':>8} {'max':>8} {'wall/blk':>9} {'wall%':>6} {'warp util':>9}")
 for i in range(8):
     b = busy[:, i]
-    print(f"{i:>5} {b.mean():8.0f} {wait[:, i].mean():8.0f} {bb[:, :, i].max(1).mean():8.0f} {np.percentile(b, 50):8.0f} {np.percentile(b, 90):8.0f} "
-          f"{np.percentile(b, 99):8.0f} {b.max():8.0f}  {100 * b.mean() / tot:5.1f} {100 * wait[:, i].mean() / tot:5.1f}")
-print(json.dumps({"busy_mean": busy.mean(0).tolist(), "wait_mean": wait.mean(0).tolist(), "block_max_busy_mean": bb.max(1).mean(0).tolist()}))
+    w = wall[blocks, i].mean()
+    print(f"{names[i]:>18} {b.mean():9.0f} {np.percentile(b, 90):8.0f} {np.percentile(b, 99):8.0f} {b.max():8.0f} {w:9.0f} "
+          f"{100 * w / wall[blocks].sum(1).mean():6.1f} {b.mean() * epb / (wpb * w):9.2f}")
+print(json.dumps({"busy_mean": busy.mean(0).tolist(), "block_wall_mean": wall[blocks].mean(0).tolist()}))
