@@ -118,17 +118,15 @@ struct Scratch {
     /* session-pool digests, rebuilt by w_scan_sessions */
     uint32_t sess_hosts[CC4_NRED][4];             /* hosts on which agent r holds a session */
     int n_red[8];                                 /* sessions per agent */
-    uint32_t has0, newss, misplaced;              /* bit r: agent r has ident 0 / has an abstract session whose id it does not know yet / has a session on a foreign subnet */
-    uint32_t ssmask[CC4_NRED][8];                 /* bit id: server_session id known to agent r (mirror of Cc4Dyn.ss, rebuilt every tick) */
+    uint32_t has0, newss, misplaced;              /* bit r: agent r has ident 0 / got a new abstract session this tick (set by sess_add) / has a session on a foreign subnet */
     int reward, cost;                             /* BlueRewardMachine sum / action cost of the tick */
     uint32_t active;                              /* bit r: red agent r holds a session after this tick's reassignment */
     uint32_t blk_id[CC4_NRED + 1];                /* cached Philox block per serial stream: red agents 0..5, [6] = reset */
     uint32_t blk[CC4_NRED + 1][4];
-    union {                                       /* three phase-local areas that are never live together */
+    union {                                       /* two phase-local areas that are never live together */
         struct { uint32_t hostagents[32];         /* byte h = mask of red agents with a session on host h (built on demand for phishing) */
                  uint32_t phish[3], pad;          /* green agents whose local work triggered a phishing email this tick */
                  uint64_t as_cum[8]; } g;         /* per source subnet: byte sn = number of allowed destination servers in subnets <= sn (GreenAccessService) */
-        uint32_t et[CC4_NRED][4][4];              /* agent_end_turn work masks per red agent: seen / present / hostname / user+ */
         uint32_t obsbits[40];                     /* observation vectors as one bit string (w_write_obs) */
     };
 };
@@ -397,6 +395,7 @@ __device__ __noinline__ int sess_add(Cx c, int r, int host, int abstract, int ro
     s->sess[n] = S_MAKE(pid, id, host);
     s->sessf[n] = (uint8_t)(r | abstract << 3 | root << 4);
     s->n_sess = (uint16_t)(n + 1);
+    if (abstract) SCR(c)->newss |= 1u << r;     /* its ident becomes a known server_session key with the end-turn observation */
     return id;
 }
 __device__ __noinline__ int session_from_pid(const Cc4Dyn *s, int host, uint32_t pid)
@@ -426,17 +425,16 @@ __device__ __noinline__ void obs_entry(Cx c, int r, int key_ip, int slot, int if
     x->oent[r][n] = key | fl;
     x->n_oent[r] = (uint8_t)(n + 1);
 }
-/* the ident is a known server_session key: O(1) through the tick's mirror mask (rebuilt at the start of w_tick and kept
- * current here); [uniform] and [lane] callers alike */
-__device__ __forceinline__ void know_session(Cx c, int r, int id)
+/* the ident becomes a known server_session key (ActionSpace.update ActionSpace.py:170-212: dict insertion order, no
+ * duplicates); rare, so a plain scan: [uniform] and [lane] callers alike */
+__device__ __noinline__ void know_session(Cx c, int r, int id)
 {
     Cc4Dyn *s = DYN(c);
-    if (SCR(c)->ssmask[r][id >> 5] >> (id & 31) & 1u) return;
     const int n = s->n_ss[r];
+    _Pragma("unroll 1") for (int i = 0; i < n; i++) if (s->ss[r][i] == id) return;
     if (n >= CC4_SS_CAP) { fail(c, CC4_E_CAPACITY); return; }
     s->ss[r][n] = (uint8_t)id;
     s->n_ss[r] = (uint8_t)(n + 1);
-    SCR(c)->ssmask[r][id >> 5] |= 1u << (id & 31);
 }
 __device__ __forceinline__ void obs_push(Cx c, int r, int succ, bool has_act, uint32_t aw)
 {
@@ -449,19 +447,44 @@ __device__ __forceinline__ void obs_push(Cx c, int r, int succ, bool has_act, ui
 /* ------------------------------------------------------------------------------------------------ */
 /* FiniteStateRedAgent bookkeeping, applied eagerly at the end of the tick (FiniteStateRedAgent.py:91-93) */
 /* ------------------------------------------------------------------------------------------------ */
-__device__ __noinline__ int fsm_find(const Cc4Dyn *s, int r, int slot) { for (int i = 0; i < s->n_fsm[r]; i++) if ((int)F_SLOT(s->fsm[r][i]) == slot) return i; return -1; }
+__device__ __forceinline__ int fsm_state(const Cc4Fsm *f, int slot)
+{
+    const int w = slot >> 5, b = slot & 31;
+    return (int)((f->pl[0][w] >> b & 1u) | (f->pl[1][w] >> b & 1u) << 1 | (f->pl[2][w] >> b & 1u) << 2 | (f->pl[3][w] >> b & 1u) << 3);
+}
+__device__ __forceinline__ void fsm_set_state(Cc4Fsm *f, int slot, int st)
+{
+    const int w = slot >> 5; const uint32_t bit = 1u << (slot & 31);
+    _Pragma("unroll") for (int p = 0; p < 4; p++) f->pl[p][w] = (st >> p & 1) ? f->pl[p][w] | bit : f->pl[p][w] & ~bit;
+}
+/* append host `slot` to agent r's list (state K or U); false when the list is full */
+__device__ __forceinline__ bool fsm_append(Cx c, int r, int slot, int hn, int st)
+{
+    Cc4Dyn *s = DYN(c); Cc4Fsm *f = &s->fsm[r];
+    const int n = s->n_fsm[r];
+    if (n >= CC4_FSM_CAP) { fail(c, CC4_E_CAPACITY); return false; }
+    s->fsm_order[r][n] = (uint8_t)slot; s->n_fsm[r] = (uint8_t)(n + 1);
+    const int w = slot >> 5; const uint32_t bit = 1u << (slot & 31);
+    f->present[w] |= bit;
+    if (hn) f->hn[w] |= bit;
+    if (st & 4) f->pl[2][w] |= bit;       /* K = 0, U = 4 */
+    return true;
+}
 
-/* End of tick for one ACTIVE red agent, run by lane r (agents are independent here): the RedSessionCheck observation
- * (RedSessionCheck._all_red_sessions_observation RedSessionCheck.py:57-63: one hostname-keyed entry with Sessions,
- * Interface+Subnet and System info per session host) is represented by the host mask x->sess_hosts[r] instead of
- * explicit entries; ActionSpace.update (ActionSpace.py:170-212) and the FSM bookkeeping consume the mask. */
+/* End of tick for one ACTIVE red agent, run by lane r (agents are independent here) [lane]: the RedSessionCheck
+ * observation (RedSessionCheck._all_red_sessions_observation RedSessionCheck.py:57-63: one hostname-keyed entry with
+ * Sessions, Interface+Subnet and System info per session host) is represented by the host mask x->sess_hosts[r] instead
+ * of explicit entries; ActionSpace.update (ActionSpace.py:170-212) and the FSM bookkeeping consume the mask. */
 __device__ __noinline__ void agent_end_turn(Cx c, int r)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
+    Cc4Fsm *f = &s->fsm[r];
     const uint32_t *rsc = x->sess_hosts[r];
     uint32_t snk = s->sn_known[r];
-    _Pragma("unroll 1") for (int w = 0; w < 4; w++) {
+    uint32_t seen[4];
+    _Pragma("unroll") for (int w = 0; w < 4; w++) {
         uint32_t m = rsc[w];
+        seen[w] = m;
         s->hn_known[r][w] |= m; s->ip_known[r][w] |= m;
         if (m & 0xFFFFu) snk |= 1u << (2 * w);
         if (m >> 16) snk |= 1u << (2 * w + 1);
@@ -470,35 +493,31 @@ __device__ __noinline__ void agent_end_turn(Cx c, int r)
     if (x->newss >> r & 1)
         _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && SF_ABS(s->sessf[i])) know_session(c, r, S_ID(s->sess[i]));
 
-    /* _host_state_transition :124-167, fused with one pass that digests the FSM list into host masks:
-       present / hostname known / state in {U, UD, R, RD} */
-    int started = (s->fsm_started >> r) & 1;
-    uint32_t *seen = x->et[r][0], *fa = x->et[r][1], *fh = x->et[r][2], *fu = x->et[r][3];   /* shared scratch: indexed dynamically */
-    _Pragma("unroll") for (int w = 0; w < 4; w++) { seen[w] = rsc[w]; fa[w] = 0; fh[w] = 0; fu[w] = 0; }
-    {
-        int col = -1, ahost = 0, asub = 0;
+    /* _host_state_transition :124-167 on the action the merged observation reports */
+    const int started = (s->fsm_started >> r) & 1;
+    if (x->has_act0[r] && x->succ0[r] != SUCC_INPROG) {
+        const int code = IP_CODE(x->act0[r]), ahost = IP_HOST(x->act0[r]), asub = IP_SUBNET(x->act0[r]);
         const bool succ = x->succ0[r] == SUCC_TRUE;
-        if (x->has_act0[r] && x->succ0[r] != SUCC_INPROG) {
-            int code = IP_CODE(x->act0[r]);
-            ahost = IP_HOST(x->act0[r]); asub = IP_SUBNET(x->act0[r]);
-            col = code >= AC_DRS && code <= AC_DEGRADE ? code - AC_DRS : -1;      /* columns follow the action codes; Withdraw (8) never transitions */
-        }
-        const int nf = s->n_fsm[r];
-        _Pragma("unroll 1") for (int i = 0; i < nf; i++) {
-            uint32_t f = s->fsm[r][i], slot = F_SLOT(f), st = F_STATE(f);
-            if (col >= 0) {
-                bool hit = col == 0 ? (int)(slot >> 4) == asub : col <= 4 ? (int)slot == ahost : (F_HN(f) && (int)slot == ahost);
-                if (hit) {
-                    int nx = succ ? c_fsm_succ[st][col] : c_fsm_fail[st][col];
-                    if (nx == F_U && !red_allowed(r, slot >> 4)) nx = F_F;
-                    if (nx >= 0) { st = (uint32_t)nx; s->fsm[r][i] = F_MAKE(slot, F_HN(f), st); }
-                    if (col != 0) col = -1;         /* host-targeted actions move the first matching host only */
+        const int col = code >= AC_DRS && code <= AC_DEGRADE ? code - AC_DRS : -1;      /* columns follow the action codes; Withdraw (8) never transitions */
+        if (col == 0) {
+            /* DiscoverRemoteSystems moves every known host of the subnet: success adds the 'D' suffix (K->KD, S->SD, U->UD,
+               R->RD; F stays), failure changes nothing (:441-451 / :481-491, column 0) */
+            if (succ && asub < 8) {
+                const int w = asub >> 1; const uint32_t m = f->present[w] & ~f->pl[3][w] & (0xFFFFu << ((asub & 1) * 16));
+                f->pl[0][w] |= m;
+            }
+        } else if (col > 0 && ahost < 128 && bit128(f->present, ahost) && (col <= 4 || bit128(f->hn, ahost))) {
+            /* host-targeted: ip-addressed actions (columns 1-4) find the host by address, the others by hostname */
+            const int st = fsm_state(f, ahost);
+            int nx = succ ? c_fsm_succ[st][col] : c_fsm_fail[st][col];
+            if (nx == F_U && !red_allowed(r, ahost >> 4)) nx = F_F;
+            if (nx >= 0 && nx != st) {
+                fsm_set_state(f, ahost, nx);
+                if (nx == F_F) {        /* F is absorbing: mark the list position for the host pick of the policy */
+                    const int n = s->n_fsm[r];
+                    _Pragma("unroll 1") for (int i = 0; i < n; i++) if (s->fsm_order[r][i] == ahost) { f->posF[i >> 5] |= 1u << (i & 31); break; }
                 }
             }
-            uint32_t w = slot >> 5, bit = 1u << (slot & 31);
-            fa[w] |= bit;
-            if (F_HN(f)) fh[w] |= bit;
-            if (st >= F_U && st <= F_RD) fu[w] |= bit;
         }
     }
     /* _process_new_observations :190-250, explicit entries first (they precede the RedSessionCheck observation) */
@@ -509,36 +528,26 @@ __device__ __noinline__ void agent_end_turn(Cx c, int r)
         int hn = !key_ip || syshost;
         uint32_t w = (uint32_t)slot >> 5, bit = 1u << (slot & 31);
         if ((e >> 12) & 1) { if (iface) seen[w] |= bit; else fail(c, CC4_E_UNREACHABLE); }
-        if (!(key_ip || iface || (fh[w] & bit))) { fail(c, CC4_E_UNREACHABLE); continue; }   /* would create host_states[None] */
-        if (!(fa[w] & bit)) {
-            if (s->n_fsm[r] >= CC4_FSM_CAP) { fail(c, CC4_E_CAPACITY); continue; }
-            s->fsm[r][s->n_fsm[r]++] = F_MAKE(slot, hn, started ? F_K : F_U);
-            fa[w] |= bit;
-            if (hn) fh[w] |= bit;
-            if (!started) fu[w] |= bit;
-        } else if (hn && !(fh[w] & bit)) { s->fsm[r][fsm_find(s, r, slot)] |= 1u << 7; fh[w] |= bit; }
+        if (!(key_ip || iface || (f->hn[w] & bit))) { fail(c, CC4_E_UNREACHABLE); continue; }   /* would create host_states[None] */
+        if (!(f->present[w] & bit)) fsm_append(c, r, slot, hn, started ? F_K : F_U);
+        else if (hn) f->hn[w] |= bit;
     }
     /* RedSessionCheck entries in state.sessions[agent] order: hosts the FSM has not seen yet */
-    if ((rsc[0] & ~fa[0]) | (rsc[1] & ~fa[1]) | (rsc[2] & ~fa[2]) | (rsc[3] & ~fa[3])) {
+    if ((rsc[0] & ~f->present[0]) | (rsc[1] & ~f->present[1]) | (rsc[2] & ~f->present[2]) | (rsc[3] & ~f->present[3])) {
         _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) {
             if (SF_AGENT(s->sessf[i]) != (uint32_t)r) continue;
-            uint32_t h = S_HOST(s->sess[i]), w = h >> 5, b = 1u << (h & 31);
-            if (fa[w] & b) continue;
-            if (s->n_fsm[r] >= CC4_FSM_CAP) { fail(c, CC4_E_CAPACITY); break; }
-            s->fsm[r][s->n_fsm[r]++] = F_MAKE(h, 1, started ? F_K : F_U);
-            fa[w] |= b; fh[w] |= b;
-            if (!started) fu[w] |= b;
+            uint32_t h = S_HOST(s->sess[i]);
+            if (bit128(f->present, h)) continue;
+            if (!fsm_append(c, r, h, 1, started ? F_K : F_U)) break;
         }
     }
-    /* ... and hosts whose hostname the FSM learns from them */
-    if ((rsc[0] & ~fh[0]) | (rsc[1] & ~fh[1]) | (rsc[2] & ~fh[2]) | (rsc[3] & ~fh[3]))
-        _Pragma("unroll 1") for (int i = 0; i < s->n_fsm[r]; i++) if (bit128(rsc, F_SLOT(s->fsm[r][i]))) s->fsm[r][i] |= 1u << 7;
-    /* _session_removal_state_change :169-188 */
-    if ((fu[0] & ~seen[0]) | (fu[1] & ~seen[1]) | (fu[2] & ~seen[2]) | (fu[3] & ~seen[3]))
-        _Pragma("unroll 1") for (int i = 0; i < s->n_fsm[r]; i++) {
-            uint16_t f = s->fsm[r][i];
-            if (F_STATE(f) >= F_U && F_STATE(f) <= F_RD && !bit128(seen, F_SLOT(f))) s->fsm[r][i] = F_MAKE(F_SLOT(f), F_HN(f), F_KD);
-        }
+    _Pragma("unroll") for (int w = 0; w < 4; w++) {
+        /* ... the FSM learns the hostname of every session host that has an entry (all of them, unless the list is full) */
+        f->hn[w] |= rsc[w] & f->present[w];
+        /* _session_removal_state_change :169-188: U / UD / R / RD hosts without a session in this observation fall back to KD */
+        const uint32_t m = f->pl[2][w] & ~f->pl[3][w] & ~seen[w];
+        f->pl[0][w] |= m; f->pl[1][w] &= ~m; f->pl[2][w] &= ~m;
+    }
 }
 
 /* FiniteStateRedAgent._choose_host_and_action :296-336 + replace_action_if_invalid SimulationController.py:1068-1112.
@@ -548,14 +557,15 @@ __device__ __noinline__ uint32_t red_policy(Cx c, int r)
     Cc4Dyn *s = DYN(c);
     int actor = A_RED0 + r;
     if (IP_CODE(s->inprog[actor]) != IP_NONE) return ACT_SLEEP_WORD;     /* last observation was IN_PROGRESS :100-102 */
+    const Cc4Fsm *f = &s->fsm[r];
     const int nf = s->n_fsm[r];
-    int nk = 0;
-    _Pragma("unroll 1") for (int i = 0; i < nf; i++) nk += F_STATE(s->fsm[r][i]) != F_F;
+    /* uniform over the hosts that are not in state F, in list order: positions from the position mask */
+    const uint32_t lo = ~f->posF[0] & (nf >= 32 ? 0xFFFFFFFFu : (1u << nf) - 1u), hi = nf > 32 ? ~f->posF[1] & (nf >= 64 ? 0xFFFFFFFFu : (1u << (nf - 32)) - 1u) : 0u;
+    const int nlo = __popc(lo), nk = nlo + __popc(hi);
     if (nk == 0) { fail(c, CC4_E_UNREACHABLE); return ACT_SLEEP_WORD; }
-    int pick = (int)rng_int(c, actor, ST_FSM_HOST, (uint32_t)nk);
-    uint32_t f = 0;
-    _Pragma("unroll 1") for (int i = 0, k = 0; i < nf; i++) { uint32_t e = s->fsm[r][i]; if (F_STATE(e) != F_F) { if (k == pick) { f = e; break; } k++; } }
-    int st = F_STATE(f), slot = F_SLOT(f);
+    const int pick = (int)rng_int(c, actor, ST_FSM_HOST, (uint32_t)nk);
+    const int pos = pick < nlo ? (int)__fns(lo, 0, pick + 1) : 32 + (int)__fns(hi, 0, pick - nlo + 1);
+    const int slot = s->fsm_order[r][pos], st = fsm_state(f, slot), f_hn = bit128(f->hn, slot);
     /* options in action-space order (c_red_aspace_cols); numpy Generator.choice(p): idx = searchsorted(cumsum(p) / sum, u, side='right') */
     int nc = 0, tot = 0;
     _Pragma("unroll 1") for (int i = 0; i < 9; i++) { int p = c_fsm_prob4[st][c_red_aspace_cols[i]]; if (p >= 0) { tot += p; nc++; } }
@@ -577,7 +587,7 @@ __device__ __noinline__ uint32_t red_policy(Cx c, int r)
         _Pragma("unroll 1") for (int sn = 0, j = 0; sn < 9; sn++) if (s->sn_known[r] >> sn & 1) { if (j == pk) { a.subnet = sn; break; } j++; }
         PICK_SESSION(); (void)rng_int(c, actor, ST_FSM_PARAM, 1);
     } else if (col <= 3) { PICK_SESSION(); (void)rng_int(c, actor, ST_FSM_PARAM, 1); a.host = slot; }
-    else { if (col >= 5 && !F_HN(f)) fail(c, CC4_E_UNREACHABLE); a.host = slot; PICK_SESSION(); (void)rng_int(c, actor, ST_FSM_PARAM, 1); }
+    else { if (col >= 5 && !f_hn) fail(c, CC4_E_UNREACHABLE); a.host = slot; PICK_SESSION(); (void)rng_int(c, actor, ST_FSM_PARAM, 1); }
     #undef PICK_SESSION
     if (col >= 1 && col <= 4 && !bit128(s->ip_known[r], a.host)) a.code = AC_INVALID;
     if (col >= 5 && !bit128(s->hn_known[r], a.host)) a.code = AC_INVALID;

@@ -21,7 +21,7 @@ namespace cc4 {
 #define CC4_WARPS_PER_BLOCK 32  /* one block per SM: 1024 threads */
 #endif
 #ifndef CC4_EPB_MAX
-#define CC4_EPB_MAX 52          /* episodes resident in one block's shared memory (52 x 4 368 B = 222 KB of the 227 KB) */
+#define CC4_EPB_MAX 54          /* episodes resident in one block's shared memory (54 x 4 288 B = 226 KB of the 227 KB) */
 #endif
 constexpr int WARPS_PER_BLOCK = CC4_WARPS_PER_BLOCK;
 constexpr int EPB_MAX = CC4_EPB_MAX;
@@ -197,7 +197,7 @@ __device__ void w_scan_sessions(Cx c)
     const int lane = lane_id();
     if (lane < 24) (&x->sess_hosts[0][0])[lane] = 0;
     if (lane < 8) x->n_red[lane] = 0;
-    if (lane == 8) { x->has0 = 0; x->newss = 0; x->misplaced = 0; }
+    if (lane == 8) { x->has0 = 0; x->misplaced = 0; }
     __syncwarp();
     const int n = s->n_sess;
     _Pragma("unroll 1") for (int i = lane; i < n; i += 32) {
@@ -206,7 +206,6 @@ __device__ void w_scan_sessions(Cx c)
         atomicAdd(&x->n_red[r], 1);
         if (id == 0) atomicOr(&x->has0, 1u << r);
         if (!red_allowed((int)r, (int)(h >> 4))) atomicOr(&x->misplaced, 1u << r);
-        if (SF_ABS(f) && !(x->ssmask[r][id >> 5] >> (id & 31) & 1)) atomicOr(&x->newss, 1u << r);
     }
     __syncwarp();
 }
@@ -241,16 +240,9 @@ __device__ __forceinline__ void ph_setup(Cx c)
     WC(c)->tick = s->step;
     _Pragma("unroll 1") for (int i = lane; i <= NAG; i += 32) x->ctr[i] = 0;
     if (lane < 8) { x->n_oent[lane] = 0; x->have_first[lane] = 0; x->succ0[lane] = SUCC_UNKNOWN; x->has_act0[lane] = 0; }
-    (&x->ssmask[0][0])[lane] = 0;
     if (lane <= CC4_NRED) x->blk_id[lane] = 0xFFFFFFFFu;
-    if (lane < 16) (&x->ssmask[0][0])[32 + lane] = 0;
-    __syncwarp();
-    _Pragma("unroll 1") for (int i = lane; i < CC4_NRED * CC4_SS_CAP; i += 32) {
-        int r = i / CC4_SS_CAP, k = i % CC4_SS_CAP;
-        if (k < s->n_ss[r]) { uint32_t id = s->ss[r][k]; atomicOr(&x->ssmask[r][id >> 5], 1u << (id & 31)); }
-    }
     if (lane == 0) {
-        x->n_evpid = 0; x->reward = 0;
+        x->n_evpid = 0; x->reward = 0; x->newss = 0;
         /* mission phase: State.check_next_phase_on_update_step State.py:514-544, phases EnterpriseScenarioGenerator.py:854-860 */
         int q = WC(c)->steps / 3, rem = WC(c)->steps % 3, l0 = q + (rem >= 1), l1 = q + (rem == 2);
         int np = WC(c)->tick < l0 ? 0 : WC(c)->tick < l0 + l1 ? 1 : 2;
@@ -326,18 +318,23 @@ __device__ __forceinline__ void ph_blue(Cx c)
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     const int lane = lane_id();
     /* filter_actions looks at the sessions as they are BEFORE anything executes; blue / green sessions never go away */
-    _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
-        uint32_t w = x->subw[A_RED0 + r];
-        bool needs = !(IP_CODE(w) == AC_SLEEP || IP_CODE(w) == AC_INVALID), found = false;
-        if (needs) {
-            uint32_t id = IP_SESSION(w);
-            _Pragma("unroll 1") for (int base = 0; base < s->n_sess && !found; base += 32) {
-                int i = base + lane;
-                bool m = i < s->n_sess && SF_AGENT(s->sessf[i]) == (uint32_t)r && S_ID(s->sess[i]) == id;
-                found = __any_sync(0xFFFFFFFFu, m);
+    /* (the pool index found here stays valid for the red phase unless a session is deleted in between: sess_moved) */
+    {
+        const int n = s->n_sess;
+        uint32_t want = 0;      /* lanes 0..5: agent | ident << 8 | needs << 31 */
+        if (lane < CC4_NRED) { uint32_t w = x->subw[A_RED0 + lane]; want = (uint32_t)lane | IP_SESSION(w) << 8 | (uint32_t)!(IP_CODE(w) == AC_SLEEP || IP_CODE(w) == AC_INVALID) << 31; }
+        int at = -1;            /* lane r: pool index of agent r's session */
+        _Pragma("unroll 1") for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const uint32_t key = i < n ? (SF_AGENT((uint32_t)s->sessf[i]) | S_ID(s->sess[i]) << 8) : 0xFFFFFFFFu;
+            _Pragma("unroll") for (int r = 0; r < CC4_NRED; r++) {
+                const uint32_t wr = __shfl_sync(0xFFFFFFFFu, want, r);
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, key == (wr & 0x7FFFFFFFu));
+                if (lane == r && at < 0 && m) at = base + __ffs(m) - 1;
             }
         }
-        if (lane == 0) x->dropped[A_RED0 + r] = needs && !found;
+        if (lane < CC4_NRED) { x->act_si[lane] = (int16_t)at; x->dropped[A_RED0 + lane] = (want >> 31) && at < 0; }
+        if (lane == 0) x->sess_moved = 0;
     }
     __syncwarp();
     /* execution: priority-1 ControlTraffic first (ControlTraffic.py:19), then agent order; warp-uniform: every lane runs the
@@ -392,22 +389,8 @@ __device__ __forceinline__ void ph_green(Cx c)
 /* ---- phase 4: red execution in agent order ---- */
 __device__ __forceinline__ void ph_red(Cx c)
 {
-    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
+    Scratch *x = SCR(c);
     const int lane = lane_id();
-    /* resolve the session each due red action names (lane per pool entry); valid until a session is deleted */
-    _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
-        uint32_t w = x->subw[A_RED0 + r], id = IP_SESSION(w);
-        int at = -1;
-        if (!x->dropped[A_RED0 + r] && IP_CODE(w) != AC_SLEEP && IP_CODE(w) != AC_INVALID)
-            _Pragma("unroll 1") for (int base = 0; base < s->n_sess && at < 0; base += 32) {
-                int i = base + lane;
-                uint32_t m = __ballot_sync(0xFFFFFFFFu, i < s->n_sess && SF_AGENT(s->sessf[i]) == (uint32_t)r && S_ID(s->sess[i]) == id);
-                if (m) at = base + __ffs(m) - 1;
-            }
-        if (lane == 0) x->act_si[r] = (int16_t)at;
-    }
-    if (lane == 0) x->sess_moved = 0;
-    __syncwarp();
     _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {      /* warp-uniform, in agent order */
         int a = A_RED0 + r;
         if (x->dropped[a]) continue;
@@ -735,7 +718,8 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
         _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) { int h = st->red_start[r]; set128(s->ip_known[r], h); set128(s->hn_known[r], h); s->sn_known[r] |= (uint16_t)(1u << (h >> 4)); }
         s->ss[0][0] = 0; s->n_ss[0] = 1;
         /* red_agent_0 digests its initial observation (its start host becomes 'U', FiniteStateRedAgent.py:221-224) */
-        s->fsm[0][0] = F_MAKE(st->red_start[0], 1, F_U); s->n_fsm[0] = 1; s->fsm_started = 1;
+        { int h0 = st->red_start[0]; s->fsm_order[0][0] = (uint8_t)h0; s->n_fsm[0] = 1; s->fsm_started = 1;
+          set128(s->fsm[0].present, h0); set128(s->fsm[0].hn, h0); set128(s->fsm[0].pl[2], h0); }
         if (WC(c)->rng_mode == 1 && WC(c)->n_segs > 0 && SCR(c)->ctr[NAG] != WC(c)->seg[1] - WC(c)->seg[0]) fail(c, CC4_E_TAPE_LEFT);
     }
     __syncwarp();
@@ -1042,7 +1026,12 @@ extern "C" int cc4_export_canon(cc4_handle *h, int env, int32_t *out, int cap, i
         PUT(cnt); for (int s = 0; s < 128; s++) if ((d.hn_known[r][s >> 5] >> (s & 31)) & 1) PUT(s);
         PUT(d.sn_known[r]);
         PUT(d.n_ss[r]); for (int i = 0; i < d.n_ss[r]; i++) PUT(d.ss[r][i]);
-        PUT(d.n_fsm[r]); for (int i = 0; i < d.n_fsm[r]; i++) { PUT(F_SLOT(d.fsm[r][i])); PUT(F_STATE(d.fsm[r][i])); PUT(F_HN(d.fsm[r][i])); }
+        PUT(d.n_fsm[r]);
+        for (int i = 0; i < d.n_fsm[r]; i++) {
+            int slot = d.fsm_order[r][i], w = slot >> 5, b = slot & 31, stt = 0;
+            for (int pl = 0; pl < 4; pl++) stt |= (int)(d.fsm[r].pl[pl][w] >> b & 1u) << pl;
+            PUT(slot); PUT(stt); PUT(d.fsm[r].hn[w] >> b & 1u);
+        }
         /* ports sorted by (ident, slot) */
         int np = 0;
         for (int i = 0; i < d.n_ports; i++) np += PT_AGENT(cold.ports[i]) == (uint32_t)r;

@@ -64,11 +64,20 @@ enum { K_SSHD, K_OT, K_APACHE2, K_MYSQLD, K_SMTP, K_D_APACHE, K_D_TOMCAT, K_D_HA
 #define PT_AGENT(w) (((w) >> 21) & 7u)
 #define PT_MAKE(mask, host, id, agent) ((uint32_t)(mask) | (uint32_t)(host) << 6 | (uint32_t)(id) << 13 | (uint32_t)(agent) << 21)
 
-/* FSM entry (FiniteStateRedAgent.host_states, FiniteStateRedAgent.py:36): slot | hostname_known<<7 | state<<8 */
-#define F_SLOT(w) ((w) & 0x7Fu)
-#define F_HN(w) (((w) >> 7) & 1u)
-#define F_STATE(w) (((w) >> 8) & 0xFu)
-#define F_MAKE(slot, hn, state) ((uint16_t)((slot) | (hn) << 7 | (state) << 8))
+/* FiniteStateRedAgent.host_states (FiniteStateRedAgent.py:36) of one red agent is kept as
+ *   order[i]   host slot of the i-th entry in insertion order (the order `choice` over the known hosts indexes into),
+ *   present    128-bit mask: the host has an entry,
+ *   hn         128-bit mask: the entry carries a hostname,
+ *   pl[b]      128-bit mask: bit b of the entry's 4-bit state (K KD S SD U UD R RD F = 0..8: bit 0 is the 'D' suffix,
+ *              states U..RD are exactly pl[2] & ~pl[3], F is pl[3]),
+ *   posF       64-bit mask over list POSITIONS: the entry is in state F (F is absorbing),
+ * so that the per-tick bookkeeping is mask algebra instead of a walk over the list. */
+struct Cc4Fsm {
+    uint32_t pl[4][4];
+    uint32_t present[4], hn[4];
+    uint32_t posF[2];
+    uint32_t pad[2];
+};
 
 /* in-flight action (SimulationController.actions_in_progress :246): code | host<<6 | subnet<<14 | session<<18 | ticks<<26 */
 #define IP_NONE 63u
@@ -99,7 +108,8 @@ struct __attribute__((aligned(16))) Cc4Dyn {
     uint32_t ip_known[CC4_NRED][4];
     uint32_t hn_known[CC4_NRED][4];
     uint32_t inprog[16];                /* actors 0..10 (blue 0-4, red 5-10) */
-    uint16_t fsm[CC4_NRED][CC4_FSM_CAP];
+    struct Cc4Fsm fsm[CC4_NRED];
+    uint8_t fsm_order[CC4_NRED][CC4_FSM_CAP];
     uint16_t sn_known[8];
     uint16_t blocks[12];                /* blocks[to] bit from (State.blocks State.py:148); 9 used */
     uint8_t ev[144];                    /* 137 used */
