@@ -21,7 +21,7 @@ namespace cc4 {
 #define CC4_WARPS_PER_BLOCK 32  /* one block per SM: 1024 threads */
 #endif
 #ifndef CC4_EPB_MAX
-#define CC4_EPB_MAX 54          /* episodes resident in one block's shared memory (54 x 4 288 B = 226 KB of the 227 KB) */
+#define CC4_EPB_MAX 53          /* episodes resident in one block's shared memory (53 x 4 288 B = 222 KB of the 227 KB) */
 #endif
 constexpr int WARPS_PER_BLOCK = CC4_WARPS_PER_BLOCK;
 constexpr int EPB_MAX = CC4_EPB_MAX;
@@ -231,6 +231,11 @@ __device__ void w_build_hostagents(Cx c)
  * takes another one instead of waiting at the barrier for the warp that drew an expensive one.  Everything that lives
  * across a phase boundary is in the episode's shared-memory record / scratch, never in registers. */
 enum { PH_SETUP, PH_POLICY, PH_BLUE, PH_GREEN, PH_RED, PH_REASSIGN, PH_ENDTURN, PH_FINISH, N_PHASES };
+#ifdef CC4_PHASE_CLOCKS   /* profiling build (tools/phase_clocks.py): per episode [18]: [2p] = busy cycles of phase p; [2p+1] of a block's
+                             first episode = wall cycles of phase p for the block, barrier included */
+__device__ unsigned long long *g_phase_clk;
+#define PC_STRIDE 18
+#endif
 
 /* ---- phase 0: per-tick scratch, known-session mirror, mission phase ---- */
 __device__ __forceinline__ void ph_setup(Cx c)
@@ -241,6 +246,7 @@ __device__ __forceinline__ void ph_setup(Cx c)
     _Pragma("unroll 1") for (int i = lane; i <= NAG; i += 32) x->ctr[i] = 0;
     if (lane < 8) { x->n_oent[lane] = 0; x->have_first[lane] = 0; x->succ0[lane] = SUCC_UNKNOWN; x->has_act0[lane] = 0; }
     if (lane <= CC4_NRED) x->blk_id[lane] = 0xFFFFFFFFu;
+    if (lane >= 8 && lane < 11) x->g.phish[lane - 8] = 0;
     if (lane == 0) {
         x->n_evpid = 0; x->reward = 0; x->newss = 0;
         /* mission phase: State.check_next_phase_on_update_step State.py:514-544, phases EnterpriseScenarioGenerator.py:854-860 */
@@ -248,6 +254,14 @@ __device__ __forceinline__ void ph_setup(Cx c)
         int np = WC(c)->tick < l0 ? 0 : WC(c)->tick < l0 + l1 ? 1 : 2;
         if (WC(c)->tick >= WC(c)->steps) fail(c, CC4_E_UNREACHABLE);
         if (np > s->phase) s->phase = (uint8_t)np;
+    }
+    __syncwarp();
+    if (lane < 8) {     /* GreenAccessService destination table of this tick's mission phase, one lane per source subnet */
+        uint32_t allowed = c_green_allowed[s->phase][lane];
+        uint64_t cum = 0; uint32_t tot = 0;
+#pragma unroll
+        for (int sn = 0; sn < 8; sn++) { if (allowed >> sn & 1) tot += s->nserver[sn]; cum |= (uint64_t)tot << (8 * sn); }
+        x->g.as_cum[lane] = cum;
     }
     __syncwarp();
 }
@@ -312,6 +326,41 @@ __device__ __forceinline__ void ph_policy(Cx c, const int32_t *actions, uint32_t
     }
 }
 
+/* The action phases are dominated by their most expensive episodes (an exploit or a Restore against nothing due).  The
+ * phase before sorts the block's episodes into four cost classes from the due actions; the phase hands them out heaviest
+ * class first, so the cheap episodes fill the tail instead of leaving most warps idle behind one late expensive one. */
+struct PhaseOrder { int cnt[4]; short list[4][64]; };
+__device__ __forceinline__ void order_push(PhaseOrder *o, int cls, int e)
+{
+    if (lane_id() == 0) { int k = atomicAdd(&o->cnt[cls], 1); o->list[cls][k] = (short)e; }
+}
+__device__ __forceinline__ int order_get(const PhaseOrder *o, int i)
+{
+#pragma unroll
+    for (int cls = 3; cls > 0; cls--) { int n = o->cnt[cls]; if (i < n) return o->list[cls][i]; i -= n; }
+    return o->list[0][i];
+}
+/*                                          Sl Mo An Rm Rs De Bl Al In  -  DRS Ag St DD Ex Pr Im Dg Wd */
+__constant__ uint8_t c_act_weight[32] = { 0, 2, 0, 4, 6, 4, 1, 1, 0, 0, 5, 3, 3, 3, 6, 4, 3, 3, 0 };
+/* cost classes of an episode's blue / red action phases from the actions that come due this tick (weights ~ relative cost
+   of the transition code, see each_episode) */
+__device__ __forceinline__ void classify_actions(Cx c, int e, PhaseOrder *blue, PhaseOrder *red)
+{
+    const Scratch *x = SCR(c);
+    const int lane = lane_id();
+    int wb = 0, wr = 0;
+    if (lane < 11) {
+        const uint32_t code = IP_CODE(x->subw[lane]);
+        const int wgt = c_act_weight[code & 31u];
+        if (lane < A_RED0) wb = wgt; else wr = wgt;
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) { wb += __shfl_xor_sync(0xFFFFFFFFu, wb, o); wr += __shfl_xor_sync(0xFFFFFFFFu, wr, o); }
+    /* lanes 0-15 now hold the sums over lanes 0-15 */
+    order_push(blue, wb == 0 ? 0 : wb <= 3 ? 1 : wb <= 7 ? 2 : 3, e);
+    order_push(red, wr == 0 ? 0 : wr <= 4 ? 1 : wr <= 8 ? 2 : 3, e);
+}
+
 /* ---- phase 2: filter_actions (:466-486), then blue execution ---- */
 __device__ __forceinline__ void ph_blue(Cx c)
 {
@@ -349,48 +398,73 @@ __device__ __forceinline__ void ph_blue(Cx c)
     __syncwarp();
 }
 
-/* ---- phase 3: green agents, lane per agent (EnterpriseGreenAgent.py:42-78); the phishing side effect is order
-   dependent and replayed afterwards in agent order ---- */
-__device__ __forceinline__ void ph_green(Cx c)
+/* ---- phase 3: green agents (EnterpriseGreenAgent.py:42-78).  A green agent reads its host's services and the block
+   table and ORs event bits: agents are independent of each other, also across episodes.  The block's green agents are laid
+   out as ONE flat list (episode-major) and handed out 32 at a time, so every lane of every item has an agent whatever the
+   episodes' sizes (24-80 agents) are; penalties and phishing flags go to the owning episode's scratch with shared-memory
+   atomics.  The phishing side effect is order dependent: it is replayed in agent order at the start of the red phase. ---- */
+__device__ __forceinline__ void green_items(int ph, int first, int n_local, int *next, const uint8_t *ng_s, short *gend)
 {
-    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
+#ifdef CC4_PHASE_CLOCKS
+    const long long tb0 = clock64();
+#endif
     const int lane = lane_id();
-    if (lane < 8) {     /* GreenAccessService destination table of this tick's phase, one lane per source subnet */
-        uint32_t allowed = c_green_allowed[s->phase][lane];
-        uint64_t cum = 0; uint32_t tot = 0;
+    int total;
+    {   /* inclusive prefix of the episodes' agent counts (every warp computes and writes the same values) */
+        int ca = lane < n_local ? ng_s[lane] : 0, cb = 32 + lane < n_local ? ng_s[32 + lane] : 0;
 #pragma unroll
-        for (int sn = 0; sn < 8; sn++) { if (allowed >> sn & 1) tot += s->nserver[sn]; cum |= (uint64_t)tot << (8 * sn); }
-        x->g.as_cum[lane] = cum;
-    }
-    __syncwarp();
-    int rew = 0;
-    uint32_t *ev_words = reinterpret_cast<uint32_t *>(s->ev);
-    const int ng = s->ngreen;
-    uint32_t any_phish = 0;
-    _Pragma("unroll 1") for (int k = 0; k < 3; k++) {
-        int g = k * 32 + lane;
-        int gr = g < ng ? green_tick(c, g, ev_words) : 0;
-        rew -= gr & 0xFF;
-        uint32_t bal = __ballot_sync(0xFFFFFFFFu, (gr & GREEN_PHISH) != 0);
-        if (lane == 0) x->g.phish[k] = bal;
-        any_phish |= bal;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rew += __shfl_xor_sync(0xFFFFFFFFu, rew, o);
-    if (lane == 0) x->reward += rew;
-    __syncwarp();
-    if (any_phish) {
-        w_build_hostagents(c);
-        _Pragma("unroll 1") for (int k = 0; k < 3; k++) { uint32_t m = x->g.phish[k]; while (m) { int b = __ffs(m) - 1; m &= m - 1; do_phishing(c, k * 32 + b); } }
+        for (int o = 1; o < 32; o <<= 1) { int ta = __shfl_up_sync(0xFFFFFFFFu, ca, o), tb = __shfl_up_sync(0xFFFFFFFFu, cb, o); if (lane >= o) { ca += ta; cb += tb; } }
+        cb += __shfl_sync(0xFFFFFFFFu, ca, 31);
+        total = __shfl_sync(0xFFFFFFFFu, cb, 31);
+        if (lane < n_local) gend[lane] = (short)ca;
+        if (32 + lane < n_local) gend[32 + lane] = (short)cb;
         __syncwarp();
     }
+    const int n_items = (total + 31) >> 5;
+    _Pragma("unroll 1") for (;;) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(&next[ph], 1);
+        it = __shfl_sync(0xFFFFFFFFu, it, 0);
+        if (it >= n_items) break;
+#ifdef CC4_PHASE_CLOCKS
+        const long long t0 = clock64();
+#endif
+        const int gidx = it * 32 + lane;
+        int e = 0;
+        if (gidx < total) {
+            /* episode of this agent: the item starts in the first episode whose end is past it*32 */
+            int lo = 0, hi = n_local - 1;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (gend[mid] > gidx) hi = mid; else lo = mid + 1; }
+            e = lo;
+            const Cx c = (Cx)(e * (int)sizeof(WarpSmem));
+            const int g = gidx - (e ? gend[e - 1] : 0);
+            Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
+            const int gr = green_tick(c, g, reinterpret_cast<uint32_t *>(s->ev));
+            if (gr & 0xFF) atomicSub(&x->reward, gr & 0xFF);
+            if (gr & GREEN_PHISH) atomicOr(&x->g.phish[g >> 5], 1u << (g & 31));
+        }
+        __syncwarp();
+#ifdef CC4_PHASE_CLOCKS
+        e = __shfl_sync(0xFFFFFFFFu, e, 0);
+        if (lane == 0 && g_phase_clk) g_phase_clk[(size_t)(first + e) * PC_STRIDE + 2 * ph] += (unsigned long long)(clock64() - t0);
+#endif
+    }
+    __syncthreads();
+#ifdef CC4_PHASE_CLOCKS
+    if (threadIdx.x == 0 && g_phase_clk && n_local > 0) g_phase_clk[(size_t)first * PC_STRIDE + 2 * ph + 1] += (unsigned long long)(clock64() - tb0);
+#endif
 }
 
 /* ---- phase 4: red execution in agent order ---- */
 __device__ __forceinline__ void ph_red(Cx c)
 {
     Scratch *x = SCR(c);
-    const int lane = lane_id();
+    /* phishing e-mails of this tick's green LocalWork (GreenLocalWork.py:118-124), in green-agent order */
+    if (x->g.phish[0] | x->g.phish[1] | x->g.phish[2]) {
+        w_build_hostagents(c);
+        _Pragma("unroll 1") for (int k = 0; k < 3; k++) { uint32_t m = x->g.phish[k]; while (m) { int b = __ffs(m) - 1; m &= m - 1; do_phishing(c, k * 32 + b); } }
+        __syncwarp();
+    }
     _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {      /* warp-uniform, in agent order */
         int a = A_RED0 + r;
         if (x->dropped[a]) continue;
@@ -474,12 +548,7 @@ __device__ __forceinline__ void ph_finish(Cx c, const uint8_t *msgs /* [5] or nu
 #ifndef CC4_STATIC_ASSIGN
 #define CC4_STATIC_ASSIGN 0     /* 1: episode e of a block is always handled by warp e % warps (tuning knob; default: shared counter) */
 #endif
-#ifdef CC4_PHASE_CLOCKS   /* profiling build (tools/phase_clocks.py): per episode [18]: [2p] = busy cycles of phase p; [2p+1] of a block's
-                             first episode = wall cycles of phase p for the block, barrier included */
-__device__ unsigned long long *g_phase_clk;
-#define PC_STRIDE 18
-#endif
-template <class F> __device__ __forceinline__ void each_episode(int ph, int first, int n_local, int *next, F f)
+template <class F> __device__ __forceinline__ void each_episode(int ph, int first, int n_local, int *next, F f, const PhaseOrder *order = nullptr)
 {
 #ifdef CC4_PHASE_CLOCKS
     const long long tb0 = clock64();
@@ -492,6 +561,7 @@ template <class F> __device__ __forceinline__ void each_episode(int ph, int firs
         if (lane_id() == 0) e = atomicAdd(&next[ph], 1);
         e = __shfl_sync(0xFFFFFFFFu, e, 0);
         if (e >= n_local) break;
+        if (order) e = order_get(order, e);
 #endif
         const Cx c = (Cx)(e * (int)sizeof(WarpSmem));
 #ifdef CC4_PHASE_CLOCKS
@@ -533,14 +603,21 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
 k_step(Params p, int env0, int env_end, int epb, StepIO io)
 {
     __shared__ int next[N_PHASES + 1];
+    __shared__ uint8_t ng_s[64];
+    __shared__ short gend[64];
+    __shared__ PhaseOrder ord_blue, ord_red;
     const int first = env0 + blockIdx.x * epb, n_local = min(epb, env_end - first);
     if (threadIdx.x <= N_PHASES) next[threadIdx.x] = 0;
+    if (threadIdx.x < 4) { ord_blue.cnt[threadIdx.x] = 0; ord_red.cnt[threadIdx.x] = 0; }
     __syncthreads();
-    each_episode(PH_SETUP, first, n_local, next, [&](Cx c, int e) { init_ctx(c, p, first + e, 0); w_load(DYN(c), p.dyn + first + e); ph_setup(c); });
-    each_episode(PH_POLICY, first, n_local, next, [&](Cx c, int e) { ph_policy(c, io.actions + (size_t)(first + e) * 5, 0, 0, 0); });
-    each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { ph_blue(c); });
-    each_episode(PH_GREEN, first, n_local, next, [&](Cx c, int) { ph_green(c); });
-    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c); });
+    each_episode(PH_SETUP, first, n_local, next, [&](Cx c, int e) {
+        init_ctx(c, p, first + e, 0); w_load(DYN(c), p.dyn + first + e); ph_setup(c);
+        if (lane_id() == 0) ng_s[e] = DYN(c)->ngreen;
+    });
+    each_episode(PH_POLICY, first, n_local, next, [&](Cx c, int e) { ph_policy(c, io.actions + (size_t)(first + e) * 5, 0, 0, 0); classify_actions(c, e, &ord_blue, &ord_red); });
+    each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { ph_blue(c); }, &ord_blue);
+    green_items(PH_GREEN, first, n_local, next, ng_s, gend);
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c); }, &ord_red);
     each_episode(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { ph_reassign(c); });
     each_episode(PH_ENDTURN, first, n_local, next, [&](Cx c, int) { ph_endturn(c); });
     each_episode(PH_FINISH, first, n_local, next, [&](Cx c, int e) {
@@ -557,21 +634,31 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
 k_rollout(Params p, int epb, int n_ticks, uint32_t pk0, uint32_t pk1, float *reward_sum, int flags)
 {
     __shared__ int next[N_PHASES + 1];
+    __shared__ uint8_t ng_s[64];
+    __shared__ short gend[64];
+    __shared__ PhaseOrder ord_blue, ord_red;
     __shared__ int alive;
     const int first = blockIdx.x * epb, n_local = min(epb, p.n_envs - first);
     _Pragma("unroll 1") for (int e = threadIdx.x >> 5; e < n_local; e += WARPS_PER_BLOCK) { Cx c = (Cx)(e * (int)sizeof(WarpSmem)); init_ctx(c, p, first + e, 0); w_load(DYN(c), p.dyn + first + e); }
     _Pragma("unroll 1") for (int t = 0; t < n_ticks; t++) {
         __syncthreads();
         if (threadIdx.x <= N_PHASES) next[threadIdx.x] = 0;
+        if (threadIdx.x < 4) { ord_blue.cnt[threadIdx.x] = 0; ord_red.cnt[threadIdx.x] = 0; }
         if (threadIdx.x == 0) alive = 0;
         __syncthreads();
         /* an episode that is over keeps its state; the block stops when all of its episodes are over */
-        each_episode(PH_SETUP, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) { if (lane_id() == 0) atomicAdd(&alive, 1); ph_setup(c); } });
+        each_episode(PH_SETUP, first, n_local, next, [&](Cx c, int e) {
+            if (lane_id() == 0) ng_s[e] = DYN(c)->done ? 0 : DYN(c)->ngreen;      /* an episode that is over has no green work */
+            if (!DYN(c)->done) { if (lane_id() == 0) atomicAdd(&alive, 1); ph_setup(c); }
+        });
         if (alive == 0) break;
-        each_episode(PH_POLICY, first, n_local, next, [&](Cx c, int e) { if (!DYN(c)->done) ph_policy(c, nullptr, pk0, pk1, p.first_episode + (uint64_t)(first + e)); });
-        each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_blue(c); });
-        each_episode(PH_GREEN, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_green(c); });
-        each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_red(c); });
+        each_episode(PH_POLICY, first, n_local, next, [&](Cx c, int e) {
+            if (!DYN(c)->done) { ph_policy(c, nullptr, pk0, pk1, p.first_episode + (uint64_t)(first + e)); classify_actions(c, e, &ord_blue, &ord_red); }
+            else { order_push(&ord_blue, 0, e); order_push(&ord_red, 0, e); }
+        });
+        each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_blue(c); }, &ord_blue);
+        green_items(PH_GREEN, first, n_local, next, ng_s, gend);
+        each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_red(c); }, &ord_red);
         each_episode(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_reassign(c); });
         each_episode(PH_ENDTURN, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_endturn(c); });
         /* `done` flips in this phase: the ticks that follow skip the episode, this tick must not look at the flag again */
