@@ -913,8 +913,28 @@ __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
         int sn = a.subnet;
         if (sn == S_INT) return SUCC_UNKNOWN;
         int nu = s->nuser[sn], nh = nu + s->nserver[sn];
-        if (red_allowed(r, sn))     /* _filter_obs SimulationController.py:1054 drops interfaces of foreign subnets */
-            _Pragma("unroll 1") for (int k = 0; k < nh; k++) obs_entry(c, r, 1, k < nu ? sn * 16 + 6 + k : sn * 16 + (k - nu), 1, 1, 0, 0);
+        if (red_allowed(r, sn)) {   /* _filter_obs SimulationController.py:1054 drops interfaces of foreign subnets */
+            /* one ip-keyed Interface + Subnet entry per host of the subnet, users first (state.hosts order): obs_entry for
+               all of them at once, lane k = k-th host */
+            Scratch *x = SCR(c);
+            const int slot = lane < nu ? sn * 16 + 6 + lane : sn * 16 + (lane - nu);
+            const uint16_t key = (uint16_t)(slot | 1 << 8), fl = (uint16_t)(1 << 9 | 1 << 10);
+            const uint32_t hosts = (((1u << nu) - 1u) << 6 | ((1u << s->nserver[sn]) - 1u)) << ((sn & 1) * 16);
+            s->ip_known[r][sn >> 1] |= hosts;
+            s->sn_known[r] |= (uint16_t)(1u << sn);
+            const int n = x->n_oent[r];
+            int at = -1;
+            if (lane < nh) _Pragma("unroll 1") for (int i = 0; i < n; i++) if ((x->oent[r][i] & 0x1FF) == key) { at = i; break; }
+            __syncwarp();
+            if (lane < nh && at >= 0) x->oent[r][at] |= fl;
+            const uint32_t fresh = __ballot_sync(FULLMASK, lane < nh && at < 0);
+            const int pos = n + __popc(fresh & ((1u << lane) - 1u));
+            if ((fresh >> lane & 1) && pos < CC4_OENT_CAP) x->oent[r][pos] = key | fl;
+            int nn = n + __popc(fresh);
+            if (nn > CC4_OENT_CAP) { fail(c, CC4_E_CAPACITY); nn = CC4_OENT_CAP; }
+            x->n_oent[r] = (uint8_t)nn;
+            __syncwarp();
+        }
         return SUCC_TRUE;
     }
     case AC_AGGR: case AC_STEALTH: {   /* DiscoverNetworkServices.py:44-86 -> Portscan.py:23-65 */

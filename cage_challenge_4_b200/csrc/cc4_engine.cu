@@ -23,6 +23,9 @@ namespace cc4 {
 #ifndef CC4_EPB_MAX
 #define CC4_EPB_MAX 53          /* episodes resident in one block's shared memory (53 x 4 288 B = 222 KB of the 227 KB) */
 #endif
+#ifndef CC4_ENDTURN_PER
+#define CC4_ENDTURN_PER 4       /* episodes per warp in the FSM digest phase (6 lanes of work per episode) */
+#endif
 constexpr int WARPS_PER_BLOCK = CC4_WARPS_PER_BLOCK;
 constexpr int EPB_MAX = CC4_EPB_MAX;
 constexpr int DYN_U4 = (int)(sizeof(Cc4Dyn) / 16);
@@ -231,6 +234,20 @@ __device__ void w_build_hostagents(Cx c)
  * takes another one instead of waiting at the barrier for the warp that drew an expensive one.  Everything that lives
  * across a phase boundary is in the episode's shared-memory record / scratch, never in registers. */
 enum { PH_SETUP, PH_POLICY, PH_BLUE, PH_GREEN, PH_RED, PH_REASSIGN, PH_ENDTURN, PH_FINISH, N_PHASES };
+/* The action phases are dominated by their most expensive episodes (an exploit or a Restore against nothing due).  The
+ * policy phase sorts the block's episodes into four cost classes from the due actions; the action phases hand them out
+ * heaviest class first, so the cheap episodes fill the tail instead of leaving most warps idle behind a late expensive one. */
+struct PhaseOrder { int cnt[4]; short list[4][64]; };
+__device__ __forceinline__ void order_push(PhaseOrder *o, int cls, int e)      /* one lane per episode calls this */
+{
+    int k = atomicAdd(&o->cnt[cls], 1); o->list[cls][k] = (short)e;
+}
+__device__ __forceinline__ int order_get(const PhaseOrder *o, int i)
+{
+#pragma unroll
+    for (int cls = 3; cls > 0; cls--) { int n = o->cnt[cls]; if (i < n) return o->list[cls][i]; i -= n; }
+    return o->list[0][i];
+}
 #ifdef CC4_PHASE_CLOCKS   /* profiling build (tools/phase_clocks.py): per episode [18]: [2p] = busy cycles of phase p; [2p+1] of a block's
                              first episode = wall cycles of phase p for the block, barrier included */
 __device__ unsigned long long *g_phase_clk;
@@ -267,98 +284,74 @@ __device__ __forceinline__ void ph_setup(Cx c)
 }
 
 /* ---- phase 1: policies (:236-248) and duration queue (:245-265): one lane per blue / red actor.  The scripted red
-   agents only read their own knowledge and draw from their own stream, so the six run side by side.  `actions` = the
-   episode's five BlueFixedActionWrapper indices, or null for the benchmark's synthetic policy (k_rollout): index ~
-   U{0..81} (agents 0-3) / U{0..241} (agent 4), Philox keyed (policy_seed, episode, tick) exactly as oracle/cc4_oracle.c
-   cc4o_run_episodes ---- */
-__device__ __forceinline__ void ph_policy(Cx c, const int32_t *actions, uint32_t pk0, uint32_t pk1, uint64_t ep)
+   agents only read their own knowledge and draw from their own stream, so the six run side by side.  Eleven actors leave
+   most of a warp idle, so a warp takes TWO episodes (lanes 0-15 and 16-31: `sl` = lane inside the half, `c` differs per
+   half); `live` = the half has an episode that is still running.  `actions` = the episode's five BlueFixedActionWrapper
+   indices, or null for the benchmark's synthetic policy (k_rollout): index ~ U{0..81} (agents 0-3) / U{0..241} (agent 4),
+   Philox keyed (policy_seed, episode, tick) exactly as oracle/cc4_oracle.c cc4o_run_episodes.  Also sorts the episode into
+   the cost classes of the two action phases (each_episode). ---- */
+/*                                          Sl Mo An Rm Rs De Bl Al In  -  DRS Ag St DD Ex Pr Im Dg Wd */
+__constant__ uint8_t c_act_weight[32] = { 0, 2, 0, 4, 6, 4, 1, 1, 0, 0, 5, 3, 3, 3, 6, 4, 3, 3, 0 };
+__device__ __forceinline__ void ph_policy(Cx c, int e, bool exists, bool live, int sl, const int32_t *actions, uint32_t pk0, uint32_t pk1, uint64_t ep,
+                                          PhaseOrder *ord_blue, PhaseOrder *ord_red)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
-    const int lane = lane_id();
-    int cost = 0;
-    if (lane < 11) {
+    int cost = 0, wb = 0, wr = 0;
+    if (live && sl < 11) {
         uint32_t aw = ACT_SLEEP_WORD;
-        if (lane < A_RED0) {
+        if (sl < A_RED0) {
             int idx;
-            if (actions) idx = actions[lane];
+            if (actions) idx = actions[sl];
             else {
-                uint32_t cw[4] = { (uint32_t)s->step, lane == 4 ? 0xB10Fu : 0xB10Eu, (uint32_t)ep, (uint32_t)(ep >> 32) };
+                uint32_t cw[4] = { (uint32_t)s->step, sl == 4 ? 0xB10Fu : 0xB10Eu, (uint32_t)ep, (uint32_t)(ep >> 32) };
                 philox4x32_10(cw, pk0, pk1);
-                idx = lane == 4 ? (int)__umulhi(cw[0], 242u) : (int)__umulhi(lane == 0 ? cw[0] : lane == 1 ? cw[1] : lane == 2 ? cw[2] : cw[3], 82u);
+                idx = sl == 4 ? (int)__umulhi(cw[0], 242u) : (int)__umulhi(sl == 0 ? cw[0] : sl == 1 ? cw[1] : sl == 2 ? cw[2] : cw[3], 82u);
             }
-            aw = blue_decode(s, lane, idx) & ~ACT_VALID;
+            aw = blue_decode(s, sl, idx) & ~ACT_VALID;
             if (IP_CODE(aw) == AC_RESTORE) cost = -1;      /* Restore.py:70, charged on submission :310-311 */
         }
-        else if (s->red_active >> (lane - A_RED0) & 1) aw = red_policy(c, lane - A_RED0);
-        uint32_t ip = s->inprog[lane];
+        else if (s->red_active >> (sl - A_RED0) & 1) aw = red_policy(c, sl - A_RED0);
+        uint32_t ip = s->inprog[sl], due = ACT_SLEEP_WORD;
         if (IP_CODE(ip) == IP_NONE) ip = aw | (uint32_t)c_duration[IP_CODE(aw)] << 26;
         int ticks = (int)IP_TICKS(ip) - 1;
-        if (ticks < 1) { x->subw[lane] = ip & ~(0xFu << 26); s->inprog[lane] = IP_NONE; }
+        if (ticks < 1) { due = ip & ~(0xFu << 26); s->inprog[sl] = IP_NONE; }
         else {
-            s->inprog[lane] = (ip & ~(0xFu << 26)) | (uint32_t)ticks << 26;
-            x->subw[lane] = ACT_SLEEP_WORD;
-            if (lane >= A_RED0) obs_push(c, lane - A_RED0, SUCC_INPROG, false, ACT_SLEEP_WORD);
+            s->inprog[sl] = (ip & ~(0xFu << 26)) | (uint32_t)ticks << 26;
+            if (sl >= A_RED0) obs_push(c, sl - A_RED0, SUCC_INPROG, false, ACT_SLEEP_WORD);
         }
+        x->subw[sl] = due;
+        const int wgt = c_act_weight[IP_CODE(due) & 31u];
+        if (sl < A_RED0) wb = wgt; else wr = wgt;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o);
-    if (lane == 0) x->cost = cost;
+    for (int o = 8; o > 0; o >>= 1) {       /* sums over the 16 lanes of the half */
+        cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o); wb += __shfl_xor_sync(0xFFFFFFFFu, wb, o); wr += __shfl_xor_sync(0xFFFFFFFFu, wr, o);
+    }
+    if (exists && sl == 0) {
+        if (live) x->cost = cost;
+        order_push(ord_blue, wb == 0 ? 0 : wb <= 3 ? 1 : wb <= 7 ? 2 : 3, e);
+        order_push(ord_red, wr == 0 ? 0 : wr <= 4 ? 1 : wr <= 8 ? 2 : 3, e);
+    }
     __syncwarp();
     /* The due actions are known: pull the cold-record lines they will touch towards L2 now, so that the dependent reads of
        the (serial) action code of the next phases find them there instead of in DRAM. */
-    {
+    if (live) {
         const Cc4Cold *k = WC(c)->k;
-        if (lane < 9) {            /* the service table: green LocalWork reads one entry per agent every tick */
+        if (sl < 9) {              /* the service table: green LocalWork reads one entry per agent every tick */
             const char *b = reinterpret_cast<const char *>(k->svc64);
-            prefetch_l2(b + min(128 * lane, (int)sizeof(k->svc64) - 1));
-            if (lane * 32 < s->n_sus) prefetch_l2(k->sus + lane * 32);
-        } else if (lane < 20) {    /* one lane per blue / red actor: directory entry, home slab and largest pid of the target host */
-            const uint32_t w = x->subw[lane - 9], code = IP_CODE(w), h = IP_HOST(w);
+            prefetch_l2(b + min(128 * sl, (int)sizeof(k->svc64) - 1));
+            if (sl * 32 < s->n_sus) prefetch_l2(k->sus + sl * 32);
+        }
+        if (sl < 11) {             /* one lane per blue / red actor: directory entry, home slab and largest pid of the target host */
+            const uint32_t w = x->subw[sl], code = IP_CODE(w), h = IP_HOST(w);
             const bool hosty = (code == AC_REMOVE || code == AC_RESTORE || code == AC_DECOY || (code >= AC_AGGR && code <= AC_DEGRADE)) && h < 128;
             if (hosty) {
                 prefetch_l2(&k->pdir[h]); prefetch_l2(&k->parena[h * CC4_OSLAB]); prefetch_l2(&k->pmax[h]);
                 if (code == AC_RESTORE) { const Cc4Stat *st = WC(c)->st; prefetch_l2(&st->o_procs[h][0]); prefetch_l2(&st->o_svc64[h]); prefetch_l2(&st->o_nproc[h]); }
             }
-        } else {                   /* known ports: 12 lines = 384 entries */
-            const int line = lane - 20;
-            if (line * 32 < s->n_ports) prefetch_l2(k->ports + line * 32);
         }
+        if (sl < 12 && sl * 32 < s->n_ports) prefetch_l2(k->ports + sl * 32);      /* known ports: 12 lines = 384 entries */
     }
-}
-
-/* The action phases are dominated by their most expensive episodes (an exploit or a Restore against nothing due).  The
- * phase before sorts the block's episodes into four cost classes from the due actions; the phase hands them out heaviest
- * class first, so the cheap episodes fill the tail instead of leaving most warps idle behind one late expensive one. */
-struct PhaseOrder { int cnt[4]; short list[4][64]; };
-__device__ __forceinline__ void order_push(PhaseOrder *o, int cls, int e)
-{
-    if (lane_id() == 0) { int k = atomicAdd(&o->cnt[cls], 1); o->list[cls][k] = (short)e; }
-}
-__device__ __forceinline__ int order_get(const PhaseOrder *o, int i)
-{
-#pragma unroll
-    for (int cls = 3; cls > 0; cls--) { int n = o->cnt[cls]; if (i < n) return o->list[cls][i]; i -= n; }
-    return o->list[0][i];
-}
-/*                                          Sl Mo An Rm Rs De Bl Al In  -  DRS Ag St DD Ex Pr Im Dg Wd */
-__constant__ uint8_t c_act_weight[32] = { 0, 2, 0, 4, 6, 4, 1, 1, 0, 0, 5, 3, 3, 3, 6, 4, 3, 3, 0 };
-/* cost classes of an episode's blue / red action phases from the actions that come due this tick (weights ~ relative cost
-   of the transition code, see each_episode) */
-__device__ __forceinline__ void classify_actions(Cx c, int e, PhaseOrder *blue, PhaseOrder *red)
-{
-    const Scratch *x = SCR(c);
-    const int lane = lane_id();
-    int wb = 0, wr = 0;
-    if (lane < 11) {
-        const uint32_t code = IP_CODE(x->subw[lane]);
-        const int wgt = c_act_weight[code & 31u];
-        if (lane < A_RED0) wb = wgt; else wr = wgt;
-    }
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) { wb += __shfl_xor_sync(0xFFFFFFFFu, wb, o); wr += __shfl_xor_sync(0xFFFFFFFFu, wr, o); }
-    /* lanes 0-15 now hold the sums over lanes 0-15 */
-    order_push(blue, wb == 0 ? 0 : wb <= 3 ? 1 : wb <= 7 ? 2 : 3, e);
-    order_push(red, wr == 0 ? 0 : wr <= 4 ? 1 : wr <= 8 ? 2 : 3, e);
 }
 
 /* ---- phase 2: filter_actions (:466-486), then blue execution ---- */
@@ -476,10 +469,11 @@ __device__ __forceinline__ void ph_red(Cx c)
     __syncwarp();
 }
 
-/* ---- phase 5: reassignment (:278) ---- */
+/* ---- phase 5: reassignment (:278), then the warp-wide half of the end-turn actions (:281-286): Monitor for blue,
+   the primary-session re-election of RedSessionCheck ---- */
 __device__ __forceinline__ void ph_reassign(Cx c)
 {
-    Scratch *x = SCR(c);
+    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     w_scan_sessions(c);
     if (x->misplaced) {
         reassign(c);
@@ -489,27 +483,23 @@ __device__ __forceinline__ void ph_reassign(Cx c)
     uint32_t active = 0;
     _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) active |= (x->n_red[r] > 0) << r;    /* :896-903: active iff it holds a session */
     if (lane_id() == 0) x->active = active;
-    __syncwarp();
-}
-
-/* ---- phase 6: end-turn actions (:281-286): Monitor for blue, RedSessionCheck for active red ---- */
-__device__ __forceinline__ void ph_endturn(Cx c)
-{
-    Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
-    const int lane = lane_id();
-    const uint32_t active = x->active;
     w_monitor_all(c);
     s->red_active = (uint8_t)active;
     /* RedSessionCheck re-elects a primary session when ident 0 is gone (changes the session order: agent by agent) */
     _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++)
         if ((active >> r & 1) && s->sess_count[r] != 0 && !(x->has0 >> r & 1)) rsc_reelect(c, r, x->n_red[r]);
     __syncwarp();
-    if (lane < CC4_NRED && (active >> lane & 1)) {
-        obs_push(c, lane, SUCC_TRUE, true, IP_MAKE(AC_RSC, 255, 15, 0, 0));
+}
+
+/* ---- phase 6: RedSessionCheck observation + FSM digest of every active red agent, one lane per agent; a warp takes
+   FOUR episodes (8 lanes each) ---- */
+__device__ __forceinline__ void ph_endturn(Cx c, bool live, int sl)
+{
+    if (live && sl < CC4_NRED && (SCR(c)->active >> sl & 1)) {
+        obs_push(c, sl, SUCC_TRUE, true, IP_MAKE(AC_RSC, 255, 15, 0, 0));
         /* the FSM agents digest the tick's observation now instead of at the start of the next tick */
-        agent_end_turn(c, lane);
+        agent_end_turn(c, sl);
     }
-    __syncwarp();
 }
 
 /* ---- phase 7: counters, done (:297-300), reward (BlueRewardMachine.py:70-121), messages ---- */
@@ -578,6 +568,38 @@ template <class F> __device__ __forceinline__ void each_episode(int ph, int firs
 #endif
 }
 
+/* the same for the lane-per-actor phases: a warp item = `per` consecutive episodes, 32 / per lanes each;
+ * f(c, e, exists, sl) runs on all lanes, with the lane's own episode */
+template <int per, class F> __device__ __forceinline__ void each_group(int ph, int first, int n_local, int *next, F f)
+{
+#ifdef CC4_PHASE_CLOCKS
+    const long long tb0 = clock64();
+#endif
+    const int n_items = (n_local + per - 1) / per, sub = lane_id() / (32 / per), sl = lane_id() % (32 / per);
+    _Pragma("unroll 1") for (;;) {
+        int it = 0;
+        if (lane_id() == 0) it = atomicAdd(&next[ph], 1);
+        it = __shfl_sync(0xFFFFFFFFu, it, 0);
+        if (it >= n_items) break;
+        const int e = it * per + sub;
+        const bool exists = e < n_local;
+        const Cx c = (Cx)((exists ? e : 0) * (int)sizeof(WarpSmem));
+#ifdef CC4_PHASE_CLOCKS
+        const long long t0 = clock64();
+        f(c, e, exists, sl);
+        __syncwarp();
+        if (exists && sl == 0 && g_phase_clk) g_phase_clk[(size_t)(first + e) * PC_STRIDE + 2 * ph] += (unsigned long long)(clock64() - t0) / per;
+#else
+        f(c, e, exists, sl);
+        __syncwarp();
+#endif
+    }
+    __syncthreads();
+#ifdef CC4_PHASE_CLOCKS
+    if (threadIdx.x == 0 && g_phase_clk && n_local > 0) g_phase_clk[(size_t)first * PC_STRIDE + 2 * ph + 1] += (unsigned long long)(clock64() - tb0);
+#endif
+}
+
 __device__ __forceinline__ void init_ctx(Cx c, const Params &p, int env, int tick)
 {
     if (lane_id() == 0) {
@@ -614,12 +636,14 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
         init_ctx(c, p, first + e, 0); w_load(DYN(c), p.dyn + first + e); ph_setup(c);
         if (lane_id() == 0) ng_s[e] = DYN(c)->ngreen;
     });
-    each_episode(PH_POLICY, first, n_local, next, [&](Cx c, int e) { ph_policy(c, io.actions + (size_t)(first + e) * 5, 0, 0, 0); classify_actions(c, e, &ord_blue, &ord_red); });
+    each_group<2>(PH_POLICY, first, n_local, next, [&](Cx c, int e, bool exists, int sl) {
+        ph_policy(c, e, exists, exists, sl, io.actions + (size_t)(first + (exists ? e : 0)) * 5, 0, 0, 0, &ord_blue, &ord_red);
+    });
     each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { ph_blue(c); }, &ord_blue);
     green_items(PH_GREEN, first, n_local, next, ng_s, gend);
     each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c); }, &ord_red);
     each_episode(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { ph_reassign(c); });
-    each_episode(PH_ENDTURN, first, n_local, next, [&](Cx c, int) { ph_endturn(c); });
+    each_group<CC4_ENDTURN_PER>(PH_ENDTURN, first, n_local, next, [&](Cx c, int, bool exists, int sl) { ph_endturn(c, exists, sl); });
     each_episode(PH_FINISH, first, n_local, next, [&](Cx c, int e) {
         const int env = first + e;
         ph_finish(c, io.msgs ? io.msgs + (size_t)env * 5 : nullptr, (io.flags & CC4_STEP_REWARD) && io.reward ? io.reward + env : nullptr, false,
@@ -652,15 +676,14 @@ k_rollout(Params p, int epb, int n_ticks, uint32_t pk0, uint32_t pk1, float *rew
             if (!DYN(c)->done) { if (lane_id() == 0) atomicAdd(&alive, 1); ph_setup(c); }
         });
         if (alive == 0) break;
-        each_episode(PH_POLICY, first, n_local, next, [&](Cx c, int e) {
-            if (!DYN(c)->done) { ph_policy(c, nullptr, pk0, pk1, p.first_episode + (uint64_t)(first + e)); classify_actions(c, e, &ord_blue, &ord_red); }
-            else { order_push(&ord_blue, 0, e); order_push(&ord_red, 0, e); }
+        each_group<2>(PH_POLICY, first, n_local, next, [&](Cx c, int e, bool exists, int sl) {
+            ph_policy(c, e, exists, exists && !DYN(c)->done, sl, nullptr, pk0, pk1, p.first_episode + (uint64_t)(first + e), &ord_blue, &ord_red);
         });
         each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_blue(c); }, &ord_blue);
         green_items(PH_GREEN, first, n_local, next, ng_s, gend);
         each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_red(c); }, &ord_red);
         each_episode(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_reassign(c); });
-        each_episode(PH_ENDTURN, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_endturn(c); });
+        each_group<CC4_ENDTURN_PER>(PH_ENDTURN, first, n_local, next, [&](Cx c, int, bool exists, int sl) { ph_endturn(c, exists && !DYN(c)->done, sl); });
         /* `done` flips in this phase: the ticks that follow skip the episode, this tick must not look at the flag again */
         each_episode(PH_FINISH, first, n_local, next, [&](Cx c, int e) {
             if (DYN(c)->done) return;
