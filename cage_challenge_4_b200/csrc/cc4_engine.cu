@@ -38,7 +38,36 @@ struct Params {
     unsigned long long *phase_clk;   /* [n_envs][8][2] cycles per phase (only in -DCC4_PHASE_CLOCKS builds) */
 };
 
-/* ---- record movement: 128-bit coalesced ---- */
+/* ---- record movement ----
+ * k_step moves the hot records with the bulk-copy engine (cp.async.bulk, 1-D TMA): at block start one thread per episode
+ * starts the copy of its 2.7 KB record into shared memory and arms the episode's mbarrier with the byte count; the
+ * warp that takes the episode in the first phase waits on that barrier.  All of a block's loads are in flight at once
+ * (HBM-bound instead of one round trip per 512 B), and no warp issues load/store instructions for them.  The store at
+ * the end of the tick is a bulk copy as well: the issuing lane only waits for its copies before it exits. */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst, const void *src_smem, uint32_t bytes)
+{   /* the warp's generic-proxy writes to the record must be visible to the async proxy that reads it */
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+/* plain 128-bit coalesced copies (k_rollout, k_reset: once per many ticks) */
 __device__ __forceinline__ void w_load(Cc4Dyn *dst, const Cc4Dyn *src)
 {
     const uint4 *g = reinterpret_cast<const uint4 *>(src);
@@ -628,12 +657,21 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
     __shared__ uint8_t ng_s[64];
     __shared__ short gend[64];
     __shared__ PhaseOrder ord_blue, ord_red;
+    __shared__ __align__(8) uint64_t ld_bar[64];
     const int first = env0 + blockIdx.x * epb, n_local = min(epb, env_end - first);
     if (threadIdx.x <= N_PHASES) next[threadIdx.x] = 0;
     if (threadIdx.x < 4) { ord_blue.cnt[threadIdx.x] = 0; ord_red.cnt[threadIdx.x] = 0; }
+    if ((int)threadIdx.x < n_local) mbar_init(&ld_bar[threadIdx.x], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+    if ((int)threadIdx.x < n_local) {
+        mbar_expect_tx(&ld_bar[threadIdx.x], (uint32_t)sizeof(Cc4Dyn));
+        bulk_load(DYN((Cx)(threadIdx.x * (int)sizeof(WarpSmem))), p.dyn + first + threadIdx.x, (uint32_t)sizeof(Cc4Dyn), &ld_bar[threadIdx.x]);
+    }
     each_episode(PH_SETUP, first, n_local, next, [&](Cx c, int e) {
-        init_ctx(c, p, first + e, 0); w_load(DYN(c), p.dyn + first + e); ph_setup(c);
+        init_ctx(c, p, first + e, 0);
+        mbar_wait(&ld_bar[e], 0);
+        ph_setup(c);
         if (lane_id() == 0) ng_s[e] = DYN(c)->ngreen;
     });
     each_group<2>(PH_POLICY, first, n_local, next, [&](Cx c, int e, bool exists, int sl) {
@@ -649,8 +687,10 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
         ph_finish(c, io.msgs ? io.msgs + (size_t)env * 5 : nullptr, (io.flags & CC4_STEP_REWARD) && io.reward ? io.reward + env : nullptr, false,
                   io.done ? io.done + env : nullptr);
         if ((io.flags & CC4_STEP_OBS) && io.obs) w_write_obs(DYN(c), SCR(c), io.obs, env);
-        w_store(p.dyn + env, DYN(c));
+        __syncwarp();
+        if (lane_id() == 0) bulk_store(p.dyn + env, DYN(c), (uint32_t)sizeof(Cc4Dyn));
     });
+    if (lane_id() == 0) bulk_store_wait();      /* shared memory must outlive the copies this lane started */
 }
 
 /* n_ticks fused ticks with the benchmark's synthetic blue policy (see ph_policy); the state stays in shared memory */
