@@ -160,8 +160,9 @@ __device__ __forceinline__ void fail(Cx c, uint32_t flag) { atomicOr(&DYN(c)->er
 
 /* ------------------------------------------------------------------------------------------------ */
 /* RNG.  Production: every (actor, tick) owns a stream of 32-bit words; word j is element j&3 of the    */
-/* Philox4x32-10 block with key (seed, episode) and counter (j>>2, actor, tick+1, episode).  An integer */
-/* draw consumes one word, a double two (53 bits).  Parity: replay of the reference's recorded draws.  */
+/* Philox4x32-10 block with key (seed, episode) and counter (j>>2, actor, tick+1, episode).  A draw     */
+/* consumes one word: integer = high half of word*n, double = word / 2^32 (oracle/cc4_oracle.c rng_*). */
+/* Parity: replay of the reference's recorded draws.                                                  */
 /* ------------------------------------------------------------------------------------------------ */
 __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
 {
@@ -209,7 +210,7 @@ __device__ __noinline__ uint32_t rng_word(Cx c, int actor)
     }
     return x->blk[slot][j & 3u];
 }
-__device__ __forceinline__ double f64_from_words(uint32_t hi, uint32_t lo) { return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) / 9007199254740992.0; }
+__device__ __forceinline__ double f64_from_word(uint32_t w) { return (double)w * 2.3283064365386962890625e-10; }     /* w / 2^32, exact */
 __device__ __noinline__ uint32_t rng_int(Cx c, int actor, int site, uint32_t n)
 {
     if (WC(c)->rng_mode == 1) { uint64_t v = tape_next(c, actor, site, 0, n); return v < n ? (uint32_t)v : 0u; }
@@ -218,8 +219,7 @@ __device__ __noinline__ uint32_t rng_int(Cx c, int actor, int site, uint32_t n)
 __device__ __noinline__ double rng_f64(Cx c, int actor, int site, uint32_t n)
 {
     if (WC(c)->rng_mode == 1) return __longlong_as_double((long long)tape_next(c, actor, site, 1, n));
-    uint32_t hi = rng_word(c, actor), lo = rng_word(c, actor);
-    return f64_from_words(hi, lo);
+    return f64_from_word(rng_word(c, actor));
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -821,38 +821,41 @@ __device__ __noinline__ int green_tick(Cx c, int g, uint32_t *ev_words)
     const int actor = A_GREEN0 + g, gh = s->green_host[g], gsn = gh >> 4;
     const bool tape = WC(c)->rng_mode == 1;
     const uint64_t v = WC(c)->k->svc64[gh];     /* issued ahead of the Philox rounds: only LocalWork (1 in 3) uses it, but the latency hides */
-    uint4 blk = tape ? make_uint4(0, 0, 0, 0) : philox_block(c, actor, 0);
-    uint32_t j = 0;
-    auto word = [&]() -> uint32_t {
-        if (j == 4) blk = philox_block(c, actor, 1);
-        uint32_t w = u4_word(blk, j & 3u); j++; return w;
-    };
-    auto gi = [&](int site, uint32_t n) -> uint32_t { return tape ? rng_int(c, actor, site, n) : __umulhi(word(), n); };
-    auto gf = [&](int site) -> double { if (tape) return rng_f64(c, actor, site, 0); uint32_t hi = word(), lo = word(); return f64_from_words(hi, lo); };
+    /* production mode: the agent's whole tick fits the four words of ONE Philox block (word 0: action choice and, cut from
+       its low half, the service pick; the phishing follow-up continues the stream at word j) */
+    const uint4 blk = tape ? make_uint4(0, 0, 0, 0) : philox_block(c, actor, 0);
+    uint32_t j = 1;
     int out = 0;
-    uint32_t choice = gi(ST_GREEN_ACT, 3);
+    uint32_t choice, frac = 0;
+    if (tape) choice = rng_int(c, actor, ST_GREEN_ACT, 3);
+    else { choice = __umulhi(blk.x, 3u); frac = blk.x * 3u; }
     if (choice == 1) {
-        int n = svc_count(v), na = 0;
-        _Pragma("unroll 1") for (int i = 0; i < n; i++) na += svc_active(v, SVC_ENTRY(v, i));
+        const int n = svc_count(v);
+        const bool ot_stopped = (v & SVC_OT_STOPPED) && n > 1 && (SVC_ENTRY(v, 1) & 15u) == K_OT;     /* the OT service is entry 1 wherever it exists */
+        const int na = n - (int)ot_stopped;
         if (na == 0) out = -c_reward[s->phase][gsn][0];
         else {
-            int pick = (int)gi(ST_LW_SERVICE, (uint32_t)na), rel = 0;
-            _Pragma("unroll 1") for (int i = 0, k = 0; i < n; i++) { uint32_t e = SVC_ENTRY(v, i); if (!svc_active(v, e)) continue; if (k == pick) { rel = (int)(e >> 4) * 20; break; } k++; }
-            if ((int)gi(ST_LW_RELIAB, 100) >= rel) out = -c_reward[s->phase][gsn][0];
+            int pick = tape ? (int)rng_int(c, actor, ST_LW_SERVICE, (uint32_t)na) : (int)__umulhi(frac, (uint32_t)na);
+            if (ot_stopped && pick >= 1) pick++;        /* pick-th ACTIVE service */
+            const int rel = (int)(SVC_ENTRY(v, pick) >> 4) * 20;
+            j = 2;
+            if ((int)(tape ? rng_int(c, actor, ST_LW_RELIAB, 100) : __umulhi(blk.y, 100u)) >= rel) out = -c_reward[s->phase][gsn][0];
             else {
-                if (gf(ST_LW_FP) < 0.01) atomicOr(&ev_words[gh >> 2], EV_PROC << ((gh & 3) * 8));
-                if (gf(ST_LW_PHISH) < 0.01) out = GREEN_PHISH;
+                j = 4;
+                if ((tape ? rng_f64(c, actor, ST_LW_FP, 0) : f64_from_word(blk.z)) < 0.01) atomicOr(&ev_words[gh >> 2], EV_PROC << ((gh & 3) * 8));
+                if ((tape ? rng_f64(c, actor, ST_LW_PHISH, 0) : f64_from_word(blk.w)) < 0.01) out = GREEN_PHISH;
             }
         }
     } else if (choice == 0) {
         /* destination = k-th server (creation order: subnets ascending, server_host_0..) among the allowed subnets,
            GreenAccessService.py:94-115; the cumulative counts per source subnet were tabulated by w_tick */
         const uint64_t cum = SCR(c)->g.as_cum[gsn];
-        const uint32_t k = gi(ST_AS_DEST, (uint32_t)(cum >> 56)), kk = k * 0x01010101u;
+        const uint32_t k = tape ? rng_int(c, actor, ST_AS_DEST, (uint32_t)(cum >> 56)) : __umulhi(blk.y, (uint32_t)(cum >> 56)), kk = k * 0x01010101u;
+        j = 3;
         const int dsn = (__popc(__vcmpleu4((uint32_t)cum, kk)) + __popc(__vcmpleu4((uint32_t)(cum >> 32), kk))) >> 3;
         const int d = dsn * 16 + (int)(k - (dsn ? (uint32_t)(cum >> (8 * (dsn - 1))) & 0xFFu : 0u));
         if ((s->blocks[gsn] >> dsn & 1) || (s->blocks[dsn] >> gsn & 1)) { atomicOr(&ev_words[d >> 2], EV_NET << ((d & 3) * 8)); out = -c_reward[s->phase][gsn][1]; }
-        else if (gf(ST_AS_FP) < 0.01) atomicOr(&ev_words[d >> 2], EV_NET << ((d & 3) * 8));
+        else if ((tape ? rng_f64(c, actor, ST_AS_FP, 0) : f64_from_word(blk.z)) < 0.01) atomicOr(&ev_words[d >> 2], EV_NET << ((d & 3) * 8));
     }
     if (!tape) SCR(c)->ctr[actor] = (uint16_t)j;
     return out;

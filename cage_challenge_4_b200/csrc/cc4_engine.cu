@@ -123,37 +123,40 @@ __device__ __forceinline__ void bits_or(uint32_t *bits, int off, uint64_t v)
     if (sh) { atomicOr(&w[1], (uint32_t)(v >> (32 - sh))); if (sh > 5) atomicOr(&w[2], (uint32_t)(v >> (64 - sh))); }
     else atomicOr(&w[1], (uint32_t)(v >> 32));
 }
+/* bits 0-8: one-hot own subnet, bits 18-26: "should be blocked" of the comms policy (BlueFlatWrapper.py:258-302), both in
+ * sorted-subnet order, per mission phase and per (agent, own subnet) block: agents 0-3, then agent 4's ADM / OFF / PAZ;
+ * from c_sorted_subnets and c_comms_adj (tools/gen_tables.py prints the same values) */
+__constant__ uint32_t c_obs_fixed[3][7] = {
+    { 0x2800080, 0x5FC0010, 0x4400100, 0x3FC0020, 0x0C40001, 0x0E00008, 0x1C00040 },
+    { 0x6D80080, 0x7FC0010, 0x6400100, 0x3FC0020, 0x0C40001, 0x0E00008, 0x1C00040 },
+    { 0x6800080, 0x5FC0010, 0x6D80100, 0x7FC0020, 0x0C40001, 0x0E00008, 0x1C00040 } };
 __device__ void w_write_obs(const Cc4Dyn *s, Scratch *x, uint8_t *obs_base /* [n][5][210] */, int env)
 {
     const int lane = lane_id();
     uint32_t *bits = x->obsbits;
     const size_t goff = (size_t)env * OBS_BYTES;
     const int mis = (int)(goff & 15);
-    /* per-subnet 16-bit host masks: malicious-process / network-connection alerts (old + current events) */
-    uint32_t procm[4], netm[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        int h = i * 32 + lane;
-        uint32_t e = host_exists(s, h) ? s->ev[h] : 0u;
-        procm[i] = __ballot_sync(0xFFFFFFFFu, (e & (EV_PROC | EV_OLDPROC)) != 0);
-        netm[i] = __ballot_sync(0xFFFFFFFFu, (e & (EV_NET | EV_OLDNET)) != 0);
-    }
+    /* per-subnet 16-bit host masks: malicious-process / network-connection alerts (old + current events).  Lane L looks
+       at hosts 4L..4L+3 (one word of ev), the four lanes of a quad cover one subnet. */
+    const uint32_t evw = reinterpret_cast<const uint32_t *>(s->ev)[lane];
+    uint32_t tp = (evw | evw >> 2) & 0x01010101u, tn = (evw >> 1 | evw >> 3) & 0x01010101u;       /* EV_PROC|EV_OLDPROC = bits 0,2; EV_NET|EV_OLDNET = bits 1,3 */
+    tp = (tp | tp >> 7 | tp >> 14 | tp >> 21) & 0xFu; tn = (tn | tn >> 7 | tn >> 14 | tn >> 21) & 0xFu;
+    uint32_t alerts = (tp | tn << 16) << (4 * (lane & 3));
+    alerts |= __shfl_xor_sync(0xFFFFFFFFu, alerts, 1);
+    alerts |= __shfl_xor_sync(0xFFFFFFFFu, alerts, 2);      /* low half: process alerts of the quad's subnet, high half: connection alerts */
+    const int ob = lane < 4 ? lane : 4, oi = lane < 4 ? 0 : lane - 4, osn = lane < 7 ? blue_sorted_subnet(ob, oi) : 0;
+    const uint32_t mine = __shfl_sync(0xFFFFFFFFu, alerts, 4 * osn);
     bits[lane] = 0;
     if (lane < 8) bits[32 + lane] = 0;
     __syncwarp();
     if (lane < 7) {   /* one lane per (agent, subnet) block of 59 bits */
-        int b = lane < 4 ? lane : 4, i = lane < 4 ? 0 : lane - 4, sn = blue_sorted_subnet(b, i);
-        uint32_t blk = s->blocks[sn], adj = c_comms_adj[s->phase][sn];
-        uint64_t v = 0;
+        const int b = ob, i = oi, sn = osn;
+        const uint32_t blk = s->blocks[sn];
+        uint64_t v = c_obs_fixed[s->phase][lane];       /* one-hot subnet + comms policy of the mission phase */
 #pragma unroll
-        for (int j = 0; j < 9; j++) {
-            int o = c_sorted_subnets[j];
-            v |= (uint64_t)(o == sn) << j | (uint64_t)(blk >> o & 1) << (9 + j) | (uint64_t)(!(adj >> o & 1)) << (18 + j);
-        }
-        int pair = sn >> 1;   /* select without indexing the register arrays dynamically */
-        uint32_t pw = pair == 0 ? procm[0] : pair == 1 ? procm[1] : pair == 2 ? procm[2] : procm[3];
-        uint32_t nw = pair == 0 ? netm[0] : pair == 1 ? netm[1] : pair == 2 ? netm[2] : netm[3];
-        uint32_t pm = (sn & 1) ? pw >> 16 : pw & 0xFFFFu, nm = (sn & 1) ? nw >> 16 : nw & 0xFFFFu;
+        for (int j = 0; j < 9; j++) v |= (uint64_t)(blk >> c_sorted_subnets[j] & 1) << (9 + j);
+        const uint32_t exist = ((1u << s->nuser[sn]) - 1u) << 6 | ((1u << s->nserver[sn]) - 1u);
+        const uint32_t pm = mine & exist, nm = mine >> 16 & exist;
         v |= (uint64_t)pm << 27 | (uint64_t)nm << 43;
         bits_or(bits, mis + CC4_OBS_LEN * b + 1 + 59 * i, v);
     }
@@ -169,8 +172,8 @@ __device__ void w_write_obs(const Cc4Dyn *s, Scratch *x, uint8_t *obs_base /* [n
     uint8_t *stage = reinterpret_cast<uint8_t *>(x);
     const uint8_t *bytes = reinterpret_cast<const uint8_t *>(bits);
     _Pragma("unroll 1") for (int g = lane; g < OBS_STAGE / 8; g += 32) {
-        uint64_t t = ((uint64_t)bytes[g] * 0x0101010101010101ull) & 0x8040201008040201ull;
-        t = ((t + 0x7F7F7F7F7F7F7F7Full) >> 7) & 0x0101010101010101ull;
+        const uint32_t by = bytes[g];
+        const uint64_t t = (uint64_t)(((by >> 4) * 0x00204081u) & 0x01010101u) << 32 | (((by & 15u) * 0x00204081u) & 0x01010101u);     /* bit k -> byte k */
         reinterpret_cast<uint64_t *>(stage)[g] = t;
     }
     __syncwarp();

@@ -161,7 +161,7 @@ typedef struct { int16_t slot; uint8_t state, hn; } fsm_t;
 struct cc4o_env {
     uint64_t seed, episode; int steps, rng_mode;
     const cc4o_draw *tape; const uint32_t *seg_off; uint32_t n_segs;
-    uint32_t seg_pos[NAG]; uint32_t reset_pos; uint32_t draw_ctr[NAG + 1];
+    uint32_t seg_pos[NAG]; uint32_t reset_pos; uint32_t draw_ctr[NAG + 1]; uint32_t frac[NAG + 1];
     uint32_t blk_id[NAG + 1]; uint32_t blk[NAG + 1][4];   /* cached Philox block per stream */
     int err; char errmsg[256];
     /* scenario */
@@ -234,7 +234,8 @@ static int tape_next(cc4o_env *e, int actor, int site, int kind, uint32_t n, uin
 
 /* Production RNG of the engine (not the reference's): every (actor, tick) owns a stream of 32-bit words; word j is
  * element j&3 of the Philox4x32-10 block with key (seed, episode) and counter (j>>2, actor, tick+1, episode).
- * An integer draw consumes one word, a double two. */
+ * A draw consumes one word: an integer in [0,n) is the high half of word*n (the low half is kept per actor, so that a
+ * second, dependent integer can be cut from the same word: rng_int_more), a double is word / 2^32. */
 static uint32_t rng_word(cc4o_env *e, int actor)
 {
     uint32_t j = e->draw_ctr[actor]++;
@@ -257,7 +258,19 @@ static uint32_t rng_int(cc4o_env *e, int actor, int site, uint32_t n)
         uint64_t v; tape_next(e, actor, site, 0, n, &v);
         return v < n ? (uint32_t)v : 0;
     }
-    return (uint32_t)(((uint64_t)rng_word(e, actor) * n) >> 32);
+    uint64_t p = (uint64_t)rng_word(e, actor) * n;
+    e->frac[actor] = (uint32_t)p;
+    return (uint32_t)(p >> 32);
+}
+
+/* a further integer that depends on the previous integer draw of the same actor (the reference draws twice; the tape
+ * has both draws): production mode cuts it from the unused low half of that word instead of spending a new one */
+static uint32_t rng_int_more(cc4o_env *e, int actor, int site, uint32_t n)
+{
+    if (e->rng_mode == 1) return rng_int(e, actor, site, n);
+    uint64_t p = (uint64_t)e->frac[actor] * n;
+    e->frac[actor] = (uint32_t)p;
+    return (uint32_t)(p >> 32);
 }
 
 static double rng_f64(cc4o_env *e, int actor, int site, uint32_t n)
@@ -266,8 +279,7 @@ static double rng_f64(cc4o_env *e, int actor, int site, uint32_t n)
         uint64_t v; tape_next(e, actor, site, 1, n, &v);
         double d; memcpy(&d, &v, 8); return d;
     }
-    uint32_t hi = rng_word(e, actor), lo = rng_word(e, actor);
-    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) / 9007199254740992.0;
+    return (double)rng_word(e, actor) * (1.0 / 4294967296.0);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -857,7 +869,7 @@ static int exec_green(cc4o_env *e, int g, const act_t *a)
         int act[MAXSVC], na = 0;
         for (int i = 0; i < h->nsvc; i++) if (h->svcs[i].active) act[na++] = i;
         if (na == 0) return SUCC_FALSE;
-        int si = act[rng_int(e, actor, ST_LW_SERVICE, (uint32_t)na)];
+        int si = act[rng_int_more(e, actor, ST_LW_SERVICE, (uint32_t)na)];     /* follows the actor's ST_GREEN_ACT draw */
         if ((int)rng_int(e, actor, ST_LW_RELIAB, 100) >= h->svcs[si].reliab) return SUCC_FALSE;
         if (rng_f64(e, actor, ST_LW_FP, 0) < 0.01) ev_procpid(e, gh, -1);
         if (rng_f64(e, actor, ST_LW_PHISH, 0) < 0.01) do_phishing(e, g);
