@@ -426,15 +426,36 @@ __device__ __noinline__ void obs_entry(Cx c, int r, int key_ip, int slot, int if
     x->n_oent[r] = (uint8_t)(n + 1);
 }
 /* the ident becomes a known server_session key (ActionSpace.update ActionSpace.py:170-212: dict insertion order, no
- * duplicates); rare, so a plain scan: [uniform] and [lane] callers alike */
+ * duplicates) */
 __device__ __noinline__ void know_session(Cx c, int r, int id)
-{
+{   /* [uniform] */
     Cc4Dyn *s = DYN(c);
     const int n = s->n_ss[r];
-    _Pragma("unroll 1") for (int i = 0; i < n; i++) if (s->ss[r][i] == id) return;
+    _Pragma("unroll 1") for (int base = 0; base < n; base += 32) {
+        const int i = base + lane_id();
+        if (__any_sync(FULLMASK, i < n && s->ss[r][i] == id)) return;
+    }
     if (n >= CC4_SS_CAP) { fail(c, CC4_E_CAPACITY); return; }
     s->ss[r][n] = (uint8_t)id;
     s->n_ss[r] = (uint8_t)(n + 1);
+}
+/* RedSessionCheck reports every session of the agent (RedSessionCheck.py:57-63): the idents of its abstract sessions become
+ * known server_session keys in dict (= pool) order.  Only agents that got a new abstract session this tick can learn
+ * something (sess_add sets x->newss).  [uniform]: pool scanned 32 entries at a time */
+__device__ __noinline__ void learn_new_sessions(Cx c)
+{
+    Cc4Dyn *s = DYN(c);
+    const uint32_t news = SCR(c)->newss;
+    const int n = s->n_sess;
+    _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
+        if (!(news >> r & 1)) continue;
+        _Pragma("unroll 1") for (int base = 0; base < n; base += 32) {
+            const int i = base + lane_id();
+            const uint32_t w = i < n ? s->sess[i] : 0u;
+            uint32_t m = __ballot_sync(FULLMASK, i < n && SF_AGENT((uint32_t)s->sessf[i]) == (uint32_t)r && SF_ABS((uint32_t)s->sessf[i]));
+            while (m) { const int j = __ffs(m) - 1; m &= m - 1; know_session(c, r, (int)S_ID(__shfl_sync(FULLMASK, w, j))); }
+        }
+    }
 }
 __device__ __forceinline__ void obs_push(Cx c, int r, int succ, bool has_act, uint32_t aw)
 {
@@ -490,8 +511,6 @@ __device__ __noinline__ void agent_end_turn(Cx c, int r)
         if (m >> 16) snk |= 1u << (2 * w + 1);
     }
     s->sn_known[r] = (uint16_t)snk;
-    if (x->newss >> r & 1)
-        _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && SF_ABS(s->sessf[i])) know_session(c, r, S_ID(s->sess[i]));
 
     /* _host_state_transition :124-167 on the action the merged observation reports */
     const int started = (s->fsm_started >> r) & 1;
@@ -524,6 +543,7 @@ __device__ __noinline__ void agent_end_turn(Cx c, int r)
     _Pragma("unroll 1") for (int i = 0; i < x->n_oent[r]; i++) {
         uint16_t e = x->oent[r][i];
         int slot = e & 0xFF, key_ip = (e >> 8) & 1, syshost = (e >> 11) & 1;
+        if ((e & 0x1900) == 0x0100 && bit128(f->present, slot)) continue;      /* ip-keyed, no hostname, no session, host already listed (a repeated scan): nothing to learn */
         int iface = ((e >> 9) & 1) || (!key_ip && bit128(rsc, slot));   /* a hostname-keyed entry merges with the RedSessionCheck entry of the same host */
         int hn = !key_ip || syshost;
         uint32_t w = (uint32_t)slot >> 5, bit = 1u << (slot & 31);
@@ -533,7 +553,12 @@ __device__ __noinline__ void agent_end_turn(Cx c, int r)
         else if (hn) f->hn[w] |= bit;
     }
     /* RedSessionCheck entries in state.sessions[agent] order: hosts the FSM has not seen yet */
-    if ((rsc[0] & ~f->present[0]) | (rsc[1] & ~f->present[1]) | (rsc[2] & ~f->present[2]) | (rsc[3] & ~f->present[3])) {
+    const uint32_t nw0 = rsc[0] & ~f->present[0], nw1 = rsc[1] & ~f->present[1], nw2 = rsc[2] & ~f->present[2], nw3 = rsc[3] & ~f->present[3];
+    const int n_new = __popc(nw0) + __popc(nw1) + __popc(nw2) + __popc(nw3);
+    if (n_new == 1) {       /* the usual case: one new session host, no order to respect */
+        const int h = nw0 ? __ffs(nw0) - 1 : nw1 ? 31 + __ffs(nw1) : nw2 ? 63 + __ffs(nw2) : 95 + __ffs(nw3);
+        fsm_append(c, r, h, 1, started ? F_K : F_U);
+    } else if (n_new > 1) {
         _Pragma("unroll 1") for (int i = 0; i < s->n_sess; i++) {
             if (SF_AGENT(s->sessf[i]) != (uint32_t)r) continue;
             uint32_t h = S_HOST(s->sess[i]);

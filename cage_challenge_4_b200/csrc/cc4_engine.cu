@@ -521,6 +521,8 @@ __device__ __forceinline__ void ph_reassign(Cx c)
     _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++)
         if ((active >> r & 1) && s->sess_count[r] != 0 && !(x->has0 >> r & 1)) rsc_reelect(c, r, x->n_red[r]);
     __syncwarp();
+    if (x->newss) learn_new_sessions(c);        /* the observation lists the sessions as the re-election left them */
+    __syncwarp();
 }
 
 /* ---- phase 6: RedSessionCheck observation + FSM digest of every active red agent, one lane per agent; a warp takes
