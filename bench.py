@@ -32,7 +32,7 @@ SVC_BYTES = 128 * 8                          # per-host service table: read in p
 EPISODE_TICKS = 499                          # steps=500 -> done at step_count >= 499 (EnterpriseScenarioGenerator.py:870)
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch at 65536 episodes from the committed
 # `ncu --set full` capture (profiles/), or None when no capture matches the current kernel
-NCU_TRAFFIC_BYTES_PER_LAUNCH = None
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 564_996_864      # profiles/r01t_kstep_ncu_full_summary.txt: 344.5 MB read + 220.5 MB written
 
 
 def load_peaks():
@@ -263,9 +263,9 @@ def main():
             "e2e": {"value": total_envs * args.e2e_steps * N_BLUE / (e2e_ms / 1e3), "unit": "agent-steps/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": which, "kernel": "k_step",
+                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if n == 65536 else None, "peak_source": which, "kernel": "k_step",
                          "kernel_ms": kernel_ms, "bytes_per_env_step": b_step,
-                         "formula": "2*sizeof(hot record) + 1024 B service table (read in place) + 608 B io per episode-tick; the rest of the cold record is touched by rare transitions only (DESIGN.md)"},
+                         "formula": "2*sizeof(hot record) + 1024 B service table (read in place) + 608 B io per episode-tick; the rest of the cold record is touched by rare transitions only (DESIGN.md); traffic = ncu dram bytes of one launch at 65536 episodes"},
             "state_bytes": {"hot": dyn_bytes, "cold": cold_bytes, "static": stat_bytes},
             "score": {"episodes": int(score[2].item()), "mean_return": float(score[0] / score[2])},
             "error_episodes": int((errs != 0).sum()),
