@@ -214,6 +214,7 @@ __device__ __forceinline__ double f64_from_word(uint32_t w) { return (double)w *
 __device__ __noinline__ uint32_t rng_int(Cx c, int actor, int site, uint32_t n)
 {
     if (WC(c)->rng_mode == 1) { uint64_t v = tape_next(c, actor, site, 0, n); return v < n ? (uint32_t)v : 0u; }
+    if (n == 1 && site == ST_FSM_PARAM) return 0u;      /* a one-option parameter pick spends no word (oracle: rng_int) */
     return __umulhi(rng_word(c, actor), n);
 }
 __device__ __noinline__ double rng_f64(Cx c, int actor, int site, uint32_t n)
@@ -309,7 +310,11 @@ __device__ __noinline__ int create_pid(Cx c, int actor, int h)
 }
 
 /* ---- services ---- */
-__device__ __forceinline__ int svc_count(uint64_t v) { int n = 0; while (n < 9 && (SVC_ENTRY(v, n) & 15u) != 15u) n++; return n; }
+__device__ __forceinline__ int svc_count(uint64_t v)
+{   /* entries are filled from 0: index of the first entry whose code is 15 (= empty); 9 when all are in use */
+    const uint64_t t = v & (v >> 1) & (v >> 2) & (v >> 3) & 0x0102040810204081ull;      /* bit 7i set iff the low nibble of entry i is 15 */
+    return t ? (__ffsll((long long)t) - 1) / 7 : 9;
+}
 __device__ __forceinline__ bool svc_active(uint64_t v, uint32_t entry) { return !((entry & 15u) == K_OT && (v & SVC_OT_STOPPED)); }
 __device__ __forceinline__ uint64_t svc_set(uint64_t v, int i, uint32_t entry) { return (v & ~(0x7Full << (7 * i))) | ((uint64_t)entry << (7 * i)); }
 
@@ -588,14 +593,24 @@ __device__ __noinline__ uint32_t red_policy(Cx c, int r)
     const uint32_t lo = ~f->posF[0] & (nf >= 32 ? 0xFFFFFFFFu : (1u << nf) - 1u), hi = nf > 32 ? ~f->posF[1] & (nf >= 64 ? 0xFFFFFFFFu : (1u << (nf - 32)) - 1u) : 0u;
     const int nlo = __popc(lo), nk = nlo + __popc(hi);
     if (nk == 0) { fail(c, CC4_E_UNREACHABLE); return ACT_SLEEP_WORD; }
-    const int pick = (int)rng_int(c, actor, ST_FSM_HOST, (uint32_t)nk);
+    /* production mode: host pick, action pick and at most two parameter picks fit the four words of the stream's first
+       Philox block, which stays in registers; the block is left in the stream cache for the action code that follows */
+    const bool tape = WC(c)->rng_mode == 1;
+    const uint4 blk = tape ? make_uint4(0, 0, 0, 0) : philox_block(c, actor, 0);
+    uint32_t j = 0;
+    auto ri = [&](int site, uint32_t n) -> uint32_t {
+        if (tape) return rng_int(c, actor, site, n);
+        if (n == 1 && site == ST_FSM_PARAM) return 0u;
+        return __umulhi(u4_word(blk, j++), n);
+    };
+    const int pick = (int)ri(ST_FSM_HOST, (uint32_t)nk);
     const int pos = pick < nlo ? (int)__fns(lo, 0, pick + 1) : 32 + (int)__fns(hi, 0, pick - nlo + 1);
     const int slot = s->fsm_order[r][pos], st = fsm_state(f, slot), f_hn = bit128(f->hn, slot);
     /* options in action-space order (c_red_aspace_cols); numpy Generator.choice(p): idx = searchsorted(cumsum(p) / sum, u, side='right') */
     int nc = 0, tot = 0;
     _Pragma("unroll 1") for (int i = 0; i < 9; i++) { int p = c_fsm_prob4[st][c_red_aspace_cols[i]]; if (p >= 0) { tot += p; nc++; } }
     if (tot != 4) fail(c, CC4_E_UNREACHABLE);
-    double u = rng_f64(c, actor, ST_FSM_ACTION, (uint32_t)nc);
+    const double u = tape ? rng_f64(c, actor, ST_FSM_ACTION, (uint32_t)nc) : f64_from_word(u4_word(blk, j++));
     int col = -1, cum = 0, last = -1;
     _Pragma("unroll 1") for (int i = 0; i < 9 && col < 0; i++) {
         int cc = c_red_aspace_cols[i], p = c_fsm_prob4[st][cc];
@@ -605,15 +620,20 @@ __device__ __noinline__ uint32_t red_policy(Cx c, int r)
     }
     if (col < 0) col = last;
     Act a = { c_fsm_col_code[col], -1, -1, 0 };
-    #define PICK_SESSION() do { if (s->n_ss[r] == 0) fail(c, CC4_E_UNREACHABLE); else a.session = s->ss[r][rng_int(c, actor, ST_FSM_PARAM, s->n_ss[r])]; } while (0)
+    #define PICK_SESSION() do { if (s->n_ss[r] == 0) fail(c, CC4_E_UNREACHABLE); else a.session = s->ss[r][ri(ST_FSM_PARAM, s->n_ss[r])]; } while (0)
     if (col == 0) {
-        int no = __popc(s->sn_known[r]);
-        int pk = (int)rng_int(c, actor, ST_FSM_PARAM, (uint32_t)no);
-        _Pragma("unroll 1") for (int sn = 0, j = 0; sn < 9; sn++) if (s->sn_known[r] >> sn & 1) { if (j == pk) { a.subnet = sn; break; } j++; }
-        PICK_SESSION(); (void)rng_int(c, actor, ST_FSM_PARAM, 1);
-    } else if (col <= 3) { PICK_SESSION(); (void)rng_int(c, actor, ST_FSM_PARAM, 1); a.host = slot; }
-    else { if (col >= 5 && !f_hn) fail(c, CC4_E_UNREACHABLE); a.host = slot; PICK_SESSION(); (void)rng_int(c, actor, ST_FSM_PARAM, 1); }
+        const uint32_t known = s->sn_known[r];
+        const int pk = (int)ri(ST_FSM_PARAM, (uint32_t)__popc(known));
+        a.subnet = (int)__fns(known, 0, pk + 1);        /* pk-th known subnet in creation order */
+        PICK_SESSION(); (void)ri(ST_FSM_PARAM, 1);
+    } else if (col <= 3) { PICK_SESSION(); (void)ri(ST_FSM_PARAM, 1); a.host = slot; }
+    else { if (col >= 5 && !f_hn) fail(c, CC4_E_UNREACHABLE); a.host = slot; PICK_SESSION(); (void)ri(ST_FSM_PARAM, 1); }
     #undef PICK_SESSION
+    if (!tape) {
+        Scratch *x = SCR(c);
+        x->ctr[actor] = (uint16_t)j;
+        x->blk_id[r] = 0; x->blk[r][0] = blk.x; x->blk[r][1] = blk.y; x->blk[r][2] = blk.z; x->blk[r][3] = blk.w;
+    }
     if (col >= 1 && col <= 4 && !bit128(s->ip_known[r], a.host)) a.code = AC_INVALID;
     if (col >= 5 && !bit128(s->hn_known[r], a.host)) a.code = AC_INVALID;
     return pack_act(a, 0);

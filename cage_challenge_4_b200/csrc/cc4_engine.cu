@@ -185,10 +185,11 @@ __device__ void w_write_obs(const Cc4Dyn *s, Scratch *x, uint8_t *obs_base /* [n
     _Pragma("unroll 1") for (int q = lane; q < OBS_STAGE / 16; q += 32) {
         int lo = q * 16;
         if (lo >= mis && lo + 16 <= end) reinterpret_cast<uint4 *>(gline)[q] = reinterpret_cast<const uint4 *>(stage)[q];
-        else {
-#pragma unroll
-            for (int k = 0; k < 16; k += 2) if (lo + k >= mis && lo + k < end) *reinterpret_cast<uint16_t *>(gline + lo + k) = *reinterpret_cast<const uint16_t *>(stage + lo + k);
-        }
+    }
+    {   /* the partial first and last line, by halfwords: lanes 0-7 the first, lanes 8-15 the last */
+        const int k = lane < 8 ? 2 * lane : (end & ~15) + 2 * (lane - 8);
+        const bool head = lane < 8 && mis > 0 && k >= mis, tail = lane >= 8 && lane < 16 && (end & 15) && k < end;
+        if (head || tail) *reinterpret_cast<uint16_t *>(gline + k) = *reinterpret_cast<const uint16_t *>(stage + k);
     }
     __syncwarp();
 }
@@ -231,17 +232,25 @@ __device__ void w_scan_sessions(Cx c)
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     const int lane = lane_id();
     if (lane < 24) (&x->sess_hosts[0][0])[lane] = 0;
-    if (lane < 8) x->n_red[lane] = 0;
-    if (lane == 8) { x->has0 = 0; x->misplaced = 0; }
     __syncwarp();
     const int n = s->n_sess;
-    _Pragma("unroll 1") for (int i = lane; i < n; i += 32) {
-        uint32_t w = s->sess[i], f = s->sessf[i], r = SF_AGENT(f), h = S_HOST(w), id = S_ID(w);
-        atomicOr(&x->sess_hosts[r][h >> 5], 1u << (h & 31));
-        atomicAdd(&x->n_red[r], 1);
-        if (id == 0) atomicOr(&x->has0, 1u << r);
-        if (!red_allowed((int)r, (int)(h >> 4))) atomicOr(&x->misplaced, 1u << r);
+    int cnt = 0;                        /* lane r < 6: sessions of agent r */
+    uint32_t has0 = 0, misplaced = 0;
+    _Pragma("unroll 1") for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        uint32_t r = 7, h = 0, id = 1;
+        if (i < n) { const uint32_t w = s->sess[i]; r = SF_AGENT((uint32_t)s->sessf[i]); h = S_HOST(w); id = S_ID(w); atomicOr(&x->sess_hosts[r][h >> 5], 1u << (h & 31)); }
+        const bool mis = i < n && !red_allowed((int)r, (int)(h >> 4));
+#pragma unroll
+        for (int a = 0; a < CC4_NRED; a++) {
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, r == (uint32_t)a);
+            if (lane == a) cnt += __popc(m);
+            if (__any_sync(0xFFFFFFFFu, r == (uint32_t)a && id == 0)) has0 |= 1u << a;
+            if (__any_sync(0xFFFFFFFFu, r == (uint32_t)a && mis)) misplaced |= 1u << a;
+        }
     }
+    if (lane < 8) x->n_red[lane] = lane < CC4_NRED ? cnt : 0;
+    if (lane == 8) { x->has0 = has0; x->misplaced = misplaced; }
     __syncwarp();
 }
 __device__ void w_build_hostagents(Cx c)
@@ -413,13 +422,13 @@ __device__ __forceinline__ void ph_blue(Cx c)
     __syncwarp();
     /* execution: priority-1 ControlTraffic first (ControlTraffic.py:19), then agent order; warp-uniform: every lane runs the
        same action code, list scans inside are lane-parallel */
-    _Pragma("unroll 1") for (int pass = 0; pass < 2; pass++)
-        _Pragma("unroll 1") for (int b = 0; b < CC4_NBLUE; b++) {
-            uint32_t aw = x->subw[b], code = IP_CODE(aw);
-            bool prio1 = code == AC_BLOCK || code == AC_ALLOW;
-            if ((pass == 0) != prio1 || code == AC_SLEEP || code == AC_ANALYSE) continue;
-            exec_blue(c, b, aw);
-        }
+    {
+        const uint32_t code = lane < CC4_NBLUE ? IP_CODE(x->subw[lane]) : (uint32_t)AC_SLEEP;
+        const bool prio1 = code == AC_BLOCK || code == AC_ALLOW;
+        uint32_t first = __ballot_sync(0xFFFFFFFFu, prio1), then = __ballot_sync(0xFFFFFFFFu, !prio1 && code != AC_SLEEP && code != AC_ANALYSE);
+        while (first) { const int b = __ffs(first) - 1; first &= first - 1; exec_blue(c, b, x->subw[b]); }
+        while (then) { const int b = __ffs(then) - 1; then &= then - 1; exec_blue(c, b, x->subw[b]); }
+    }
     __syncwarp();
 }
 
@@ -490,13 +499,22 @@ __device__ __forceinline__ void ph_red(Cx c)
         _Pragma("unroll 1") for (int k = 0; k < 3; k++) { uint32_t m = x->g.phish[k]; while (m) { int b = __ffs(m) - 1; m &= m - 1; do_phishing(c, k * 32 + b); } }
         __syncwarp();
     }
-    _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {      /* warp-uniform, in agent order */
-        int a = A_RED0 + r;
-        if (x->dropped[a]) continue;
-        uint32_t aw = x->subw[a];
-        int code = IP_CODE(aw);
-        int succ = code == AC_SLEEP ? SUCC_UNKNOWN : code == AC_INVALID ? SUCC_FALSE : exec_red(c, r, aw);
-        obs_push(c, r, succ, true, aw);
+    {
+        const int lane = lane_id();
+        bool real = false;
+        if (lane < CC4_NRED && !x->dropped[A_RED0 + lane]) {
+            const uint32_t aw = x->subw[A_RED0 + lane], code = IP_CODE(aw);
+            if (code == AC_SLEEP) obs_push(c, lane, SUCC_UNKNOWN, true, aw);        /* nothing to execute: the lane files the observation */
+            else if (code == AC_INVALID) obs_push(c, lane, SUCC_FALSE, true, aw);
+            else real = true;
+        }
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, real);
+        while (todo) {                  /* warp-uniform, in agent order */
+            const int r = __ffs(todo) - 1; todo &= todo - 1;
+            const uint32_t aw = x->subw[A_RED0 + r];
+            const int succ = exec_red(c, r, aw);
+            obs_push(c, r, succ, true, aw);
+        }
     }
     __syncwarp();
 }
@@ -512,14 +530,14 @@ __device__ __forceinline__ void ph_reassign(Cx c)
         __syncwarp();
         w_scan_sessions(c);
     }
-    uint32_t active = 0;
-    _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) active |= (x->n_red[r] > 0) << r;    /* :896-903: active iff it holds a session */
-    if (lane_id() == 0) x->active = active;
-    w_monitor_all(c);
-    s->red_active = (uint8_t)active;
+    const int lane = lane_id();
+    const bool holds = lane < CC4_NRED && x->n_red[lane] > 0;
+    const uint32_t active = __ballot_sync(0xFFFFFFFFu, holds);                                   /* :896-903: active iff it holds a session */
     /* RedSessionCheck re-elects a primary session when ident 0 is gone (changes the session order: agent by agent) */
-    _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++)
-        if ((active >> r & 1) && s->sess_count[r] != 0 && !(x->has0 >> r & 1)) rsc_reelect(c, r, x->n_red[r]);
+    uint32_t elect = __ballot_sync(0xFFFFFFFFu, holds && s->sess_count[lane] != 0 && !(x->has0 >> lane & 1));
+    if (lane == 0) { x->active = active; s->red_active = (uint8_t)active; }
+    w_monitor_all(c);
+    while (elect) { const int r = __ffs(elect) - 1; elect &= elect - 1; rsc_reelect(c, r, x->n_red[r]); }
     __syncwarp();
     if (x->newss) learn_new_sessions(c);        /* the observation lists the sessions as the re-election left them */
     __syncwarp();
@@ -540,27 +558,31 @@ __device__ __forceinline__ void ph_endturn(Cx c, bool live, int sl)
 __device__ __forceinline__ void ph_finish(Cx c, const uint8_t *msgs /* [5] or null */, float *reward_out, bool accumulate, uint8_t *done_out)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
-    if (lane_id() == 0) {
-        const uint32_t active = x->active;
+    const int lane = lane_id();
+    const uint32_t active = x->active;
+    int rew = 0;
+    if (lane < CC4_NRED) {
+        /* `success and isinstance(action, Impact)` BlueRewardMachine.py:118: a TernaryEnum member is always truthy
+           (Enums.py:5-24), so every Impact that comes due costs RIA while the agent holds a session */
+        const uint32_t w = x->subw[A_RED0 + lane];
+        if (IP_CODE(w) == AC_IMPACT && (active >> lane & 1)) rew = c_reward[s->phase][IP_HOST(w) >> 4][2];
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) rew += __shfl_xor_sync(0xFFFFFFFFu, rew, o);       /* lanes 0-7 */
+    if (lane >= 8 && lane < 8 + CC4_NBLUE) s->msgs[lane - 8] = msgs ? msgs[lane - 8] : 0;
+    if (WC(c)->rng_mode == 1)
+        _Pragma("unroll 1") for (int a = lane; a < NAG; a += 32) {
+            uint32_t seg = 1u + (uint32_t)WC(c)->tick * NAG + (uint32_t)a;
+            if (seg < WC(c)->n_segs && x->ctr[a] != WC(c)->seg[seg + 1] - WC(c)->seg[seg]) fail(c, CC4_E_TAPE_LEFT);
+        }
+    if (lane == 0) {
         s->fsm_started |= (uint8_t)active;
-        s->step++;
-        s->done = s->step >= WC(c)->steps - 1;
-        int rew = x->reward;
-        _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
-            /* `success and isinstance(action, Impact)` BlueRewardMachine.py:118: a TernaryEnum member is always truthy
-               (Enums.py:5-24), so every Impact that comes due costs RIA while the agent holds a session */
-            uint32_t w = x->subw[A_RED0 + r];
-            if (IP_CODE(w) == AC_IMPACT && (active >> r & 1)) rew += c_reward[s->phase][IP_HOST(w) >> 4][2];
-        }
-        _Pragma("unroll 1") for (int b = 0; b < CC4_NBLUE; b++) s->msgs[b] = msgs ? msgs[b] : 0;
-        if (reward_out) { if (accumulate) *reward_out += (float)(rew + x->cost); else *reward_out = (float)(rew + x->cost); }
+        const int step = s->step + 1;
+        s->step = (uint16_t)step;
+        s->done = step >= WC(c)->steps - 1;
+        const float r = (float)(rew + x->reward + x->cost);
+        if (reward_out) { if (accumulate) *reward_out += r; else *reward_out = r; }
         if (done_out) *done_out = s->done;
-        if (WC(c)->rng_mode == 1) {
-            _Pragma("unroll 1") for (int a = 0; a < NAG; a++) {
-                uint32_t seg = 1u + (uint32_t)WC(c)->tick * NAG + (uint32_t)a;
-                if (seg < WC(c)->n_segs && x->ctr[a] != WC(c)->seg[seg + 1] - WC(c)->seg[seg]) fail(c, CC4_E_TAPE_LEFT);
-            }
-        }
     }
     __syncwarp();
 }

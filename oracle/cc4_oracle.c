@@ -258,6 +258,7 @@ static uint32_t rng_int(cc4o_env *e, int actor, int site, uint32_t n)
         uint64_t v; tape_next(e, actor, site, 0, n, &v);
         return v < n ? (uint32_t)v : 0;
     }
+    if (n == 1 && site == ST_FSM_PARAM) return 0;       /* a one-option parameter pick spends no word */
     uint64_t p = (uint64_t)rng_word(e, actor) * n;
     e->frac[actor] = (uint32_t)p;
     return (uint32_t)(p >> 32);
