@@ -213,3 +213,73 @@ def test_sharding_invariance():
     for i in range(n // 2):
         assert np.array_equal(full.export_canon(i), lo.export_canon(i))
         assert np.array_equal(full.export_canon(n // 2 + i), hi.export_canon(i))
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json's full size: 65 536 episodes on one GPU (configs[2]); size-independent properties + oracle samples
+# ------------------------------------------------------------------------------------------------
+FULL = 65536
+
+
+def test_full_batch_step_matches_oracle_on_sampled_episodes():
+    """One 65 536-episode batch stepped through cc4_step; 96 episodes spread over the batch (first / last block, block
+    boundaries, random) are replayed by the oracle with the same actions: obs / reward / done every tick, canonical state
+    at the end.  Also: no error flags anywhere in the batch."""
+    seed, ticks = 31, 40
+    env = _engine(FULL, device=0, seed=seed, steps=500)
+    obs, mask = env.reset()
+    rng = np.random.default_rng(7)
+    sample = sorted(set([0, 1, 49, 50, 51, 99, 100, FULL - 51, FULL - 50, FULL - 1]) | set(rng.integers(0, FULL, 86).tolist()))
+    refs = {i: O.OracleEnv(seed=seed, episode=i, steps=500) for i in sample}
+    obs_h, mask_h = obs.cpu().numpy(), mask.cpu().numpy()
+    for i, r in refs.items():
+        r.reset()
+        assert np.array_equal(obs_h[i], r.observe()) and np.array_equal(mask_h[i].astype(np.uint8), r.mask()), f"reset {i}"
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for t in range(ticks):
+        acts = torch.stack([torch.randint(0, k, (FULL,), generator=g, device="cuda", dtype=torch.int32) for k in (82, 82, 82, 82, 242)], 1).contiguous()
+        msgs = torch.randint(0, 256, (FULL, 5), generator=g, device="cuda", dtype=torch.uint8)
+        o, r, d = env.step(acts, msgs)
+        idx = torch.tensor(sample, device="cuda")
+        oh, rh, dh = o[idx].cpu().numpy(), r[idx].cpu().numpy(), d[idx].cpu().numpy()
+        ah, mh = acts[idx].cpu().numpy(), msgs[idx].cpu().numpy()
+        for k, i in enumerate(sample):
+            rc, oo, rr, dd = refs[i].step(ah[k], mh[k])
+            assert np.array_equal(oh[k], oo) and rh[k] == rr and dh[k] == dd, f"episode {i} tick {t}"
+    for i in sample[::6]:
+        assert np.array_equal(env.export_canon(i), refs[i].export()), f"episode {i}: {_diff(refs[i].export(), env.export_canon(i))}"
+    assert not env.error_flags().any()
+
+
+def test_full_batch_rollout_is_tick_additive_and_sharding_invariant():
+    """65 536 episodes: (a) one fused 30-tick rollout == thirty 1-tick rollouts (state resident across ticks vs stored
+    and reloaded every tick); (b) two 32 768-episode shards keyed by global episode id == the full batch (the multi-GPU
+    split); compared by per-episode reward sums, a sum over all hot records would hide compensating errors so sampled
+    canonical states are compared too."""
+    seed, ticks = 13, 30
+    a = _engine(FULL, device=0, seed=seed)
+    b = _engine(FULL, device=0, seed=seed)
+    ra = torch.zeros(FULL, dtype=torch.float32, device="cuda")
+    rb = torch.zeros(FULL, dtype=torch.float32, device="cuda")
+    a.reset(), b.reset()
+    a.rollout(ticks, policy_seed=seed, reward_sum=ra)
+    for _ in range(ticks):
+        b.rollout(1, policy_seed=seed, reward_sum=rb)
+    torch.cuda.synchronize()
+    assert torch.equal(ra, rb)
+    for i in (0, 12345, FULL - 1):
+        assert np.array_equal(a.export_canon(i), b.export_canon(i))
+    del b
+    half = FULL // 2
+    rs = []
+    for k in range(2):
+        s = _engine(half, device=0, seed=seed, first_episode=k * half)
+        r = torch.zeros(half, dtype=torch.float32, device="cuda")
+        s.reset()
+        s.rollout(ticks, policy_seed=seed, reward_sum=r)
+        torch.cuda.synchronize()
+        rs.append(r)
+        assert np.array_equal(s.export_canon(77), a.export_canon(k * half + 77))
+        del s
+    assert torch.equal(torch.cat(rs), ra)
+    assert float(ra.sum()) < 0
