@@ -230,15 +230,15 @@ def main():
     host_pool = [p.cpu().pin_memory() for p in pool[:max(args.e2e_steps, 4)]]
     env.reset()
     for i in range(3):
-        env.step_host(host_pool[i % len(host_pool)])
+        env.step_host(host_pool[i % len(host_pool)], compact=True)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.e2e_steps):
-        o, r, d = env.step_host(host_pool[i % len(host_pool)])
+        o, r, d = env.step_host(host_pool[i % len(host_pool)], compact=True)    # obs uint8 [N, 578]: the five unpadded vectors
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     h2d = n * N_BLUE * 4
-    d2h = n * (N_BLUE * 210 + 4 + 1)
+    d2h = n * (578 + 4 + 1)
 
     t_ms = torch.tensor([ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
     score = torch.stack([ret.sum(), (ret * ret).sum(), torch.tensor(float(n), dtype=torch.float64, device=dev)])
@@ -261,7 +261,8 @@ def main():
             "env_steps_per_s": env_sps, "all_agent_steps_per_s": env_sps * 70.0,
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": total_envs * args.e2e_steps * N_BLUE / (e2e_ms / 1e3), "unit": "agent-steps/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+                    "api": "BatchedCC4.step_host(actions_pinned, compact=True) -> cc4_step_host: obs uint8 [N,578] (92 x 4 + 210, the reference's unpadded vectors) + reward f32 [N] + done u8 [N] in pinned host memory"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if n == 65536 else None, "peak_source": which, "kernel": "k_step",
                          "kernel_ms": kernel_ms, "bytes_per_env_step": b_step,

@@ -130,11 +130,14 @@ __constant__ uint32_t c_obs_fixed[3][7] = {
     { 0x2800080, 0x5FC0010, 0x4400100, 0x3FC0020, 0x0C40001, 0x0E00008, 0x1C00040 },
     { 0x6D80080, 0x7FC0010, 0x6400100, 0x3FC0020, 0x0C40001, 0x0E00008, 0x1C00040 },
     { 0x6800080, 0x5FC0010, 0x6D80100, 0x7FC0020, 0x0C40001, 0x0E00008, 0x1C00040 } };
-__device__ void w_write_obs(const Cc4Dyn *s, Scratch *x, uint8_t *obs_base /* [n][5][210] */, int env)
+/* compact: the five vectors without padding, 92 + 92 + 92 + 92 + 210 bytes per episode (CC4_STEP_OBS_COMPACT) */
+__device__ void w_write_obs(const Cc4Dyn *s, Scratch *x, uint8_t *obs_base /* [n][5][210] or [n][578] */, int env, bool compact = false)
 {
     const int lane = lane_id();
     uint32_t *bits = x->obsbits;
-    const size_t goff = (size_t)env * OBS_BYTES;
+    const int row_bytes = compact ? CC4_OBS_COMPACT_LEN : OBS_BYTES;
+    const int vec_stride = compact ? 92 : CC4_OBS_LEN;      /* agents 0-3 have 92 entries, so agent b starts at 92 b either way for b <= 4 */
+    const size_t goff = (size_t)env * row_bytes;
     const int mis = (int)(goff & 15);
     /* per-subnet 16-bit host masks: malicious-process / network-connection alerts (old + current events).  Lane L looks
        at hosts 4L..4L+3 (one word of ev), the four lanes of a quad cover one subnet. */
@@ -158,31 +161,32 @@ __device__ void w_write_obs(const Cc4Dyn *s, Scratch *x, uint8_t *obs_base /* [n
         const uint32_t exist = ((1u << s->nuser[sn]) - 1u) << 6 | ((1u << s->nserver[sn]) - 1u);
         const uint32_t pm = mine & exist, nm = mine >> 16 & exist;
         v |= (uint64_t)pm << 27 | (uint64_t)nm << 43;
-        bits_or(bits, mis + CC4_OBS_LEN * b + 1 + 59 * i, v);
+        bits_or(bits, mis + vec_stride * b + 1 + 59 * i, v);
     }
     if (lane >= 8 && lane < 13) {   /* messages from the other four agents in sorted order, SimulationController.py:781-804 */
         int b = lane - 8;
         uint32_t m = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) m |= (uint32_t)s->msgs[k < b ? k : k + 1] << (8 * k);
-        bits_or(bits, mis + CC4_OBS_LEN * b + 1 + 59 * (b == 4 ? 3 : 1), (uint64_t)m);
+        bits_or(bits, mis + vec_stride * b + 1 + 59 * (b == 4 ? 3 : 1), (uint64_t)m);
     }
     __syncwarp();
     /* expand: staging byte j = bit j of the string */
     uint8_t *stage = reinterpret_cast<uint8_t *>(x);
     const uint8_t *bytes = reinterpret_cast<const uint8_t *>(bits);
-    _Pragma("unroll 1") for (int g = lane; g < OBS_STAGE / 8; g += 32) {
+    const int stage_bytes = (mis + row_bytes + 15) & ~15;
+    _Pragma("unroll 1") for (int g = lane; g < stage_bytes / 8; g += 32) {
         const uint32_t by = bytes[g];
         const uint64_t t = (uint64_t)(((by >> 4) * 0x00204081u) & 0x01010101u) << 32 | (((by & 15u) * 0x00204081u) & 0x01010101u);     /* bit k -> byte k */
         reinterpret_cast<uint64_t *>(stage)[g] = t;
     }
     __syncwarp();
-    if (lane < CC4_N_BLUE) stage[mis + CC4_OBS_LEN * lane] = s->phase;   /* element 0 of every vector is the mission phase */
+    if (lane < CC4_N_BLUE) stage[mis + vec_stride * lane] = s->phase;   /* element 0 of every vector is the mission phase */
     __syncwarp();
     /* copy: 16-byte lines, aligned on both sides */
     uint8_t *gline = obs_base + (goff - (size_t)mis);
-    const int end = mis + OBS_BYTES;
-    _Pragma("unroll 1") for (int q = lane; q < OBS_STAGE / 16; q += 32) {
+    const int end = mis + row_bytes;
+    _Pragma("unroll 1") for (int q = lane; q < stage_bytes / 16; q += 32) {
         int lo = q * 16;
         if (lo >= mis && lo + 16 <= end) reinterpret_cast<uint4 *>(gline)[q] = reinterpret_cast<const uint4 *>(stage)[q];
     }
@@ -713,7 +717,7 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
         const int env = first + e;
         ph_finish(c, io.msgs ? io.msgs + (size_t)env * 5 : nullptr, (io.flags & CC4_STEP_REWARD) && io.reward ? io.reward + env : nullptr, false,
                   io.done ? io.done + env : nullptr);
-        if ((io.flags & CC4_STEP_OBS) && io.obs) w_write_obs(DYN(c), SCR(c), io.obs, env);
+        if ((io.flags & CC4_STEP_OBS) && io.obs) w_write_obs(DYN(c), SCR(c), io.obs, env, (io.flags & CC4_STEP_OBS_COMPACT) != 0);
         __syncwarp();
         if (lane_id() == 0) bulk_store(p.dyn + env, DYN(c), (uint32_t)sizeof(Cc4Dyn));
     });
@@ -1072,6 +1076,7 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
     CUDA_TRY(cudaEventRecord(h->ev_in, user));
     for (int i = 0; i < 2; i++) CUDA_TRY(cudaStreamWaitEvent(h->pipe[i], h->ev_in, 0));
     const bool want_obs = obs_host && (flags & CC4_STEP_OBS), want_rew = reward_host && (flags & CC4_STEP_REWARD);
+    const size_t obs_row = (flags & CC4_STEP_OBS_COMPACT) ? CC4_OBS_COMPACT_LEN : CC4_N_BLUE * CC4_OBS_LEN;
     size_t chunk = (n + CC4_HOST_CHUNKS - 1) / CC4_HOST_CHUNKS;
     {   /* whole waves of full blocks per chunk */
         size_t wave = (size_t)h->n_sm * EPB_MAX;
@@ -1089,7 +1094,7 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
         k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * (size_t)epb, st>>>(h->p, (int)e0, (int)(e0 + cnt), epb, io);
         h->launches++;
         CUDA_TRY(cudaGetLastError());
-        if (want_obs) CUDA_TRY(cudaMemcpyAsync(obs_host + e0 * CC4_N_BLUE * CC4_OBS_LEN, h->stage_obs + e0 * CC4_N_BLUE * CC4_OBS_LEN, cnt * CC4_N_BLUE * CC4_OBS_LEN, cudaMemcpyDeviceToHost, st));
+        if (want_obs) CUDA_TRY(cudaMemcpyAsync(obs_host + e0 * obs_row, h->stage_obs + e0 * obs_row, cnt * obs_row, cudaMemcpyDeviceToHost, st));
         if (want_rew) CUDA_TRY(cudaMemcpyAsync(reward_host + e0, h->stage_reward + e0, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
         if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host + e0, h->stage_done + e0, cnt, cudaMemcpyDeviceToHost, st));
     }

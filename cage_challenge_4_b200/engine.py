@@ -20,7 +20,14 @@ N_BLUE, OBS_LEN, MASK_LEN = 5, 210, 242
 N_ACTIONS = (82, 82, 82, 82, 242)
 OBS_SIZES = (92, 92, 92, 92, 210)
 SLEEP_INDEX = (49, 49, 49, 49, 145)
-STEP_OBS, STEP_REWARD, STEP_ALL = 1, 2, 3
+STEP_OBS, STEP_REWARD, STEP_ALL, STEP_OBS_COMPACT = 1, 2, 3, 4
+OBS_COMPACT_LEN = 578      # 92 + 92 + 92 + 92 + 210: the five unpadded vectors back to back (CC4_STEP_OBS_COMPACT)
+OBS_COMPACT_OFF = (0, 92, 184, 276, 368, 578)
+
+
+def split_compact(obs):
+    """[N, 578] compact observations -> the five per-agent views [N, 92] x 4 + [N, 210] (BlueFlatWrapper.py:128-170)."""
+    return [obs[:, OBS_COMPACT_OFF[b]:OBS_COMPACT_OFF[b + 1]] for b in range(N_BLUE)]
 DRAW_DTYPE = np.dtype([("val", "<u8"), ("n", "<u2"), ("site", "u1"), ("kind", "u1"), ("pad", "<u4")])
 
 
@@ -102,6 +109,7 @@ class BatchedCC4:
         return p["obs"], p["mask"]
 
     def step(self, actions: torch.Tensor, messages: torch.Tensor | None = None, flags: int = STEP_ALL):
+        assert not (flags & STEP_OBS_COMPACT), "compact observations: use step_compact() / step_host(compact=True)"
         assert actions.dtype == torch.int32 and actions.is_cuda and actions.shape == (self.num_envs, N_BLUE) and actions.is_contiguous()
         mp = 0
         if messages is not None:
@@ -111,19 +119,39 @@ class BatchedCC4:
                                        self.done.data_ptr(), flags, self._stream()), "cc4_step")
         return self.obs, self.reward, self.done
 
-    def step_host(self, actions: np.ndarray | torch.Tensor, messages=None, flags: int = STEP_ALL):
-        """The same tick with HOST buffers (pinned torch tensors or numpy arrays): H2D + kernel + D2H + sync inside."""
+    def step_host(self, actions: np.ndarray | torch.Tensor, messages=None, flags: int = STEP_ALL, compact: bool = False):
+        """The same tick with HOST buffers (pinned torch tensors or numpy arrays): H2D + kernel + D2H + sync inside.
+        compact=True returns the observations as uint8 [N, 578] (the five unpadded vectors back to back, see
+        split_compact) instead of [N, 5, 210]: 45 % fewer bytes over PCIe."""
         n = self.num_envs
         if self._pinned is None:
             self._pinned = dict(obs=torch.zeros((n, N_BLUE, OBS_LEN), dtype=torch.uint8).pin_memory(),
                                 reward=torch.zeros(n, dtype=torch.float32).pin_memory(),
                                 done=torch.zeros(n, dtype=torch.uint8).pin_memory())
         p = self._pinned
+        if compact:
+            flags |= STEP_OBS_COMPACT
+            if "obs_compact" not in p:
+                p["obs_compact"] = p["obs"].view(-1)[:n * OBS_COMPACT_LEN].view(n, OBS_COMPACT_LEN)     # same pinned storage
+            a_ptr = actions.data_ptr() if isinstance(actions, torch.Tensor) else actions.ctypes.data
+            m_ptr = 0 if messages is None else (messages.data_ptr() if isinstance(messages, torch.Tensor) else messages.ctypes.data)
+            _native.check(self._L.cc4_step_host(self._h, a_ptr, m_ptr, p["obs_compact"].data_ptr(), p["reward"].data_ptr(),
+                                                p["done"].data_ptr(), flags, self._stream()), "cc4_step_host")
+            return p["obs_compact"], p["reward"], p["done"]
         a_ptr = actions.data_ptr() if isinstance(actions, torch.Tensor) else actions.ctypes.data
         m_ptr = 0 if messages is None else (messages.data_ptr() if isinstance(messages, torch.Tensor) else messages.ctypes.data)
         _native.check(self._L.cc4_step_host(self._h, a_ptr, m_ptr, p["obs"].data_ptr(), p["reward"].data_ptr(),
                                             p["done"].data_ptr(), flags, self._stream()), "cc4_step_host")
         return p["obs"], p["reward"], p["done"]
+
+    def step_compact(self, actions: torch.Tensor, messages: torch.Tensor | None = None):
+        """step() with compact device observations uint8 [N, 578] (see split_compact)."""
+        if getattr(self, "_obs_compact", None) is None:
+            self._obs_compact = torch.zeros((self.num_envs, OBS_COMPACT_LEN), dtype=torch.uint8, device=self.device)
+        mp = 0 if messages is None else messages.data_ptr()
+        _native.check(self._L.cc4_step(self._h, actions.data_ptr(), mp, self._obs_compact.data_ptr(), self.reward.data_ptr(),
+                                       self.done.data_ptr(), STEP_ALL | STEP_OBS_COMPACT, self._stream()), "cc4_step")
+        return self._obs_compact, self.reward, self.done
 
     def rollout(self, n_ticks: int, policy_seed: int = 0, reward_sum: torch.Tensor | None = None, flags: int = STEP_REWARD):
         rp = 0 if reward_sum is None else reward_sum.data_ptr()

@@ -44,6 +44,10 @@ enum {
 #define CC4_STEP_OBS 1      /* write the 5 observation vectors            (BlueFlatWrapper.observation_change :172) */
 #define CC4_STEP_REWARD 2   /* write the team reward                      (BlueRewardMachine.calculate_reward :70) */
 #define CC4_STEP_ALL 3
+#define CC4_STEP_OBS_COMPACT 4   /* with CC4_STEP_OBS: obs rows are the five UNPADDED vectors back to back, uint8 [n_envs][578] =
+                                    92 + 92 + 92 + 92 + 210 (what BlueFlatWrapper returns without pad_spaces, BlueFlatWrapper.py:128-170);
+                                    45 % fewer bytes to move to the host */
+#define CC4_OBS_COMPACT_LEN 578
 
 /* One recorded RNG draw of the reference (tape mode; layout shared with oracle/cc4_oracle.h). */
 typedef struct {
@@ -85,7 +89,7 @@ int cc4_reset_host(cc4_handle *h, uint8_t *obs_host, uint8_t *mask_host, void *s
 /* Replaces: BlueFlatWrapper.step -> CybORG.parallel_step -> SimulationController.step (+ send_messages,
  * observation_change x5, BlueRewardMachine) for every episode of the batch.
  * actions_dev int32 [n_envs][5] BlueFixedActionWrapper indices; msgs_dev uint8 [n_envs][5] (bit i = message[i]) or NULL;
- * obs_dev uint8 [n_envs][5][210]; reward_dev float [n_envs] (team reward = BlueRewardMachine + action_cost, identical
+ * obs_dev uint8 [n_envs][5][210] (or [n_envs][578] with CC4_STEP_OBS_COMPACT); reward_dev float [n_envs] (team reward = BlueRewardMachine + action_cost, identical
  * for the 5 blue agents, SimulationController.py:1118); done_dev uint8 [n_envs].  Outputs may be NULL. */
 int cc4_step(cc4_handle *h, const int32_t *actions_dev, const uint8_t *msgs_dev, uint8_t *obs_dev, float *reward_dev,
              uint8_t *done_dev, int flags, void *stream);

@@ -11,7 +11,7 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-FILES = sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+FILES = sorted(f for f in os.listdir(GOLDEN) if f.startswith("ep_") and f.endswith(".npz"))
 
 
 def _engine(*a, **k):
@@ -283,3 +283,23 @@ def test_full_batch_rollout_is_tick_additive_and_sharding_invariant():
         del s
     assert torch.equal(torch.cat(rs), ra)
     assert float(ra.sum()) < 0
+
+
+@pytest.mark.parametrize("n", [3, 1000])
+def test_compact_observations_are_the_unpadded_vectors(n):
+    """CC4_STEP_OBS_COMPACT: row = the five vectors without padding (92 x 4 + 210 = 578 bytes), device and host path."""
+    from cage_challenge_4_b200.engine import split_compact, OBS_SIZES
+    a, b, c = (_engine(n, device=0, seed=4) for _ in range(3))
+    for e in (a, b, c):
+        e.reset()
+    g = np.random.default_rng(2)
+    for t in range(12):
+        acts = torch.from_numpy(np.stack([g.integers(0, k, n) for k in (82, 82, 82, 82, 242)], 1).astype(np.int32))
+        msgs = torch.from_numpy(g.integers(0, 256, (n, 5)).astype(np.uint8))
+        o1, r1, d1 = a.step(acts.cuda(), msgs.cuda())
+        o2, r2, d2 = b.step_compact(acts.cuda(), msgs.cuda())
+        o3, r3, d3 = c.step_host(acts.pin_memory(), msgs.pin_memory(), compact=True)
+        assert o2.shape == (n, 578) and o3.shape == (n, 578)
+        for k, v in enumerate(split_compact(o2.cpu())):
+            assert torch.equal(v, o1[:, k, :OBS_SIZES[k]].cpu()), f"tick {t} agent {k}"
+        assert torch.equal(o3, o2.cpu()) and torch.equal(r1.cpu(), r3) and torch.equal(r1, r2) and torch.equal(d1.cpu(), d3)

@@ -13,7 +13,7 @@ import canon
 import oracle_py as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-FILES = sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+FILES = sorted(f for f in os.listdir(GOLDEN) if f.startswith("ep_") and f.endswith(".npz"))
 
 
 @pytest.mark.parametrize("name", FILES)
