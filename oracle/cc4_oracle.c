@@ -162,6 +162,7 @@ struct cc4o_env {
     uint64_t seed, episode; int steps, rng_mode;
     const cc4o_draw *tape; const uint32_t *seg_off; uint32_t n_segs;
     uint32_t seg_pos[NAG]; uint32_t reset_pos; uint32_t draw_ctr[NAG + 1]; uint32_t frac[NAG + 1];
+    int32_t breakdown[3][3][NSUB];     /* reward events so far: [mission phase][LWF, ASF, RIA][subnet] (cc4o_reward_breakdown) */
     uint32_t blk_id[NAG + 1]; uint32_t blk[NAG + 1][4];   /* cached Philox block per stream */
     int err; char errmsg[256];
     /* scenario */
@@ -450,6 +451,7 @@ int cc4o_reset(cc4o_env *e)
     init_tables();
     e->err = 0; e->errmsg[0] = 0;
     e->reset_pos = 0; memset(e->seg_pos, 0, sizeof e->seg_pos); memset(e->draw_ctr, 0, sizeof e->draw_ctr); memset(e->blk_id, 0xFF, sizeof e->blk_id);
+    memset(e->breakdown, 0, sizeof e->breakdown);
     e->n_used = 0; e->norder = 0; e->ngreen = 0;
     memset(e->hosts, 0, sizeof e->hosts);
     for (int a = 0; a < NAG; a++) { e->nsess[a] = 0; e->sess_count[a] = 0; e->active[a] = 0; e->inprog[a].code = AC_NONE; e->inprog_ticks[a] = 0; e->cur_action[a].code = AC_SLEEP; }
@@ -1228,12 +1230,12 @@ int cc4o_step(cc4o_env *e, const int32_t *actions, const uint8_t *msgs, uint8_t 
     for (int g = 0; g < e->ngreen; g++) {
         int a = A_GREEN0 + g, c = e->cur_action[a].code;
         if ((c == AC_G_LOCAL || c == AC_G_ACCESS) && e->nsess[a] > 0 && e->green_succ[g] == SUCC_FALSE)
-            rew += REWARD[e->phase][slot_subnet(e->green_host[g])][c == AC_G_LOCAL ? 0 : 1];
+        { rew += REWARD[e->phase][slot_subnet(e->green_host[g])][c == AC_G_LOCAL ? 0 : 1]; e->breakdown[e->phase][c == AC_G_LOCAL ? 0 : 1][slot_subnet(e->green_host[g])]++; }
     }
     for (int r = 0; r < NRED; r++) {
         int a = A_RED0 + r;
         /* `success and isinstance(action, Impact)` :118 — a TernaryEnum member is always truthy (Enums.py:5-24) */
-        if (e->cur_action[a].code == AC_IMPACT && e->nsess[a] > 0) rew += REWARD[e->phase][slot_subnet(e->cur_action[a].host)][2];
+        if (e->cur_action[a].code == AC_IMPACT && e->nsess[a] > 0) { rew += REWARD[e->phase][slot_subnet(e->cur_action[a].host)][2]; e->breakdown[e->phase][2][slot_subnet(e->cur_action[a].host)]++; }
     }
     if (msgs) memcpy(e->msgs, msgs, NBLUE); else memset(e->msgs, 0, NBLUE);
     if (reward) *reward = (float)((double)rew + cost);
@@ -1404,3 +1406,6 @@ void cc4o_capacity_probe(uint64_t seed, uint64_t first_episode, int n_eps, int s
 #undef HW
     cc4o_destroy(e);
 }
+
+/* diagnostics: how often each BlueRewardMachine event fired since the last reset, out[3 phases][3 kinds: LWF ASF RIA][9 subnets] */
+void cc4o_reward_breakdown(cc4o_env *e, int32_t *out) { memcpy(out, e->breakdown, sizeof e->breakdown); }

@@ -73,6 +73,7 @@ int cc4o_action_mask(cc4o_env *e, uint8_t *mask);  /* [5][242] */
 /* canonical flattened state (layout: oracle/canon.py); returns number of int32 written */
 int cc4o_export(cc4o_env *e, int32_t *out, int cap);
 int cc4o_error_flags(cc4o_env *e);
+void cc4o_reward_breakdown(cc4o_env *e, int32_t *out);   /* [3 phases][LWF, ASF, RIA][9 subnets] event counts since reset */
 const char *cc4o_last_error(cc4o_env *e);
 /* bench helper: run `n_eps` whole episodes (reset + steps-1 ticks) with uniform-random blue indices drawn from
  * a Philox stream keyed like the CUDA engine's synthetic blue policy; returns total env ticks executed and the

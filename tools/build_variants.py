@@ -21,7 +21,7 @@ def build(name, defs):
 
 def bench(path, extra):
     env = dict(os.environ, CC4_B200_LIB=path)
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu", "--steps", "120", "--warmup", "5", "--e2e-steps", "10", *extra],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu", "--steps", "120", "--warmup", "5", "--e2e-steps", "40", *extra],
                        env=env, capture_output=True, text=True)
     try:
         j = json.loads(r.stdout.strip().split("\n")[-1])
