@@ -22,6 +22,36 @@
 
 namespace cc4 {
 
+/* inlining knobs (tools/build_variants.py): which helper groups are compiled inline; defaults = the fastest measured set
+ * (profiles/r01x_variants.txt: everything inline except the Philox block, the tape reader and rng_int / rng_f64: 0.62 -> 0.54 ms) */
+#ifndef CC4_RNG_INLINE
+#define CC4_RNG_INLINE __forceinline__     /* one call level less on every draw: 1.7 % (profiles/r01x_variants.txt) */
+#endif
+#ifndef CC4_INL4
+#define CC4_INL4 __forceinline__
+#endif
+#ifndef CC4_INL5
+#define CC4_INL5 __forceinline__
+#endif
+#ifndef CC4_INL6
+#define CC4_INL6 __forceinline__
+#endif
+#ifndef CC4_INL7
+#define CC4_INL7 __forceinline__
+#endif
+#ifndef CC4_INL8
+#define CC4_INL8 __forceinline__
+#endif
+#ifndef CC4_INL9
+#define CC4_INL9 __noinline__
+#endif
+#ifndef CC4_INL2
+#define CC4_INL2 __noinline__
+#endif
+#ifndef CC4_INL3
+#define CC4_INL3 __forceinline__
+#endif
+
 /* ------------------------------------------------------------------------------------------------ */
 /* constants                                                                                        */
 /* ------------------------------------------------------------------------------------------------ */
@@ -175,7 +205,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
 }
-__device__ __noinline__ uint64_t tape_next(Cx c, int actor, int site, int kind, uint32_t n)
+__device__ CC4_INL9 uint64_t tape_next(Cx c, int actor, int site, int kind, uint32_t n)
 {
     uint32_t seg = actor == NAG ? 0u : 1u + (uint32_t)WC(c)->tick * NAG + (uint32_t)actor;
     if (seg >= WC(c)->n_segs) { fail(c, CC4_E_TAPE_END); return 0; }
@@ -187,7 +217,7 @@ __device__ __noinline__ uint64_t tape_next(Cx c, int actor, int site, int kind, 
     return d.val;
 }
 /* block `blk` of the actor's stream for this tick (registers only) */
-__device__ __noinline__ uint4 philox_block(Cx c, int actor, uint32_t blk)
+__device__ CC4_INL9 uint4 philox_block(Cx c, int actor, uint32_t blk)
 {
     const WarpCtx *g = WC(c);
     uint32_t o[4] = { blk, (uint32_t)actor, actor == NAG ? 0u : (uint32_t)g->tick + 1u, g->ep_lo };
@@ -198,7 +228,7 @@ __device__ __forceinline__ uint32_t u4_word(const uint4 &v, uint32_t i) { return
 /* next word of the actor's stream.  Blue / red actors and the reset stream (serial callers) keep their current block in
  * the scratch; green actors (lane-parallel in green_tick, which keeps its block in registers) recompute on the rare
  * serial follow-ups (phishing). */
-__device__ __noinline__ uint32_t rng_word(Cx c, int actor)
+__device__ CC4_RNG_INLINE uint32_t rng_word(Cx c, int actor)
 {
     Scratch *x = SCR(c);
     uint32_t j = x->ctr[actor]++;
@@ -211,13 +241,13 @@ __device__ __noinline__ uint32_t rng_word(Cx c, int actor)
     return x->blk[slot][j & 3u];
 }
 __device__ __forceinline__ double f64_from_word(uint32_t w) { return (double)w * 2.3283064365386962890625e-10; }     /* w / 2^32, exact */
-__device__ __noinline__ uint32_t rng_int(Cx c, int actor, int site, uint32_t n)
+__device__ CC4_INL2 uint32_t rng_int(Cx c, int actor, int site, uint32_t n)
 {
     if (WC(c)->rng_mode == 1) { uint64_t v = tape_next(c, actor, site, 0, n); return v < n ? (uint32_t)v : 0u; }
     if (n == 1 && site == ST_FSM_PARAM) return 0u;      /* a one-option parameter pick spends no word (oracle: rng_int) */
     return __umulhi(rng_word(c, actor), n);
 }
-__device__ __noinline__ double rng_f64(Cx c, int actor, int site, uint32_t n)
+__device__ CC4_INL2 double rng_f64(Cx c, int actor, int site, uint32_t n)
 {
     if (WC(c)->rng_mode == 1) return __longlong_as_double((long long)tape_next(c, actor, site, 1, n));
     return f64_from_word(rng_word(c, actor));
@@ -246,7 +276,7 @@ __device__ __forceinline__ void set128(uint32_t *b, int i) { b[i >> 5] |= 1u << 
 #define P_NONE P_DEADBIT    /* filler for lanes past the end of a list: looks like a tombstone */
 /* port class of a process kind (canon PORT_BIT), 15 = does not listen */
 __device__ __forceinline__ uint32_t kind_portbit(uint32_t kind) { return (uint32_t)(0xFFF245243210ull >> (4 * kind)) & 15u; }
-__device__ __noinline__ void proc_append(Cx c, int h, uint32_t w)
+__device__ CC4_INL4 void proc_append(Cx c, int h, uint32_t w)
 {   /* host.processes.append */
     Cc4Cold *k = WC(c)->k;
     uint32_t d = k->pdir[h], off = PD_OFF(d), n = PD_CNT(d), capl = PD_CAPL(d);
@@ -261,7 +291,7 @@ __device__ __noinline__ void proc_append(Cx c, int h, uint32_t w)
     k->pdir[h] = PD_MAKE(off, n + 1, capl);
     if (P_PID(w) > k->pmax[h]) k->pmax[h] = (uint16_t)P_PID(w);
 }
-__device__ __noinline__ void proc_rescan_max(Cx c, int h)
+__device__ CC4_INL5 void proc_rescan_max(Cx c, int h)
 {
     Cc4Cold *k = WC(c)->k;
     const uint32_t d = k->pdir[h];
@@ -271,7 +301,7 @@ __device__ __noinline__ void proc_rescan_max(Cx c, int h)
     mx = __reduce_max_sync(FULLMASK, mx);
     k->pmax[h] = (uint16_t)mx;
 }
-__device__ __noinline__ void proc_delete(Cx c, int h, int idx)
+__device__ CC4_INL5 void proc_delete(Cx c, int h, int idx)
 {
     Cc4Cold *k = WC(c)->k;
     const uint32_t d = k->pdir[h];
@@ -290,7 +320,7 @@ __device__ __noinline__ void proc_delete(Cx c, int h, int idx)
     k->pdir[h] = PD_MAKE(PD_OFF(d), n - 1, PD_CAPL(d));
     if (!P_DEAD(gone) && P_PID(gone) == k->pmax[h]) proc_rescan_max(c, h);
 }
-__device__ __noinline__ int proc_find(Cx c, int h, uint32_t pid)
+__device__ CC4_INL5 int proc_find(Cx c, int h, uint32_t pid)
 {   /* Host.get_process Host.py:251 (tombstones are not processes) */
     const uint32_t d = WC(c)->k->pdir[h];
     const uint32_t *pp = WC(c)->k->parena + PD_OFF(d); const int n = (int)PD_CNT(d);
@@ -302,7 +332,7 @@ __device__ __noinline__ int proc_find(Cx c, int h, uint32_t pid)
     }
     return -1;
 }
-__device__ __noinline__ int create_pid(Cx c, int actor, int h)
+__device__ CC4_INL3 int create_pid(Cx c, int actor, int h)
 {   /* Host.create_pid Host.py:198-200 */
     uint32_t pid = (uint32_t)WC(c)->k->pmax[h] + 1 + rng_int(c, actor, ST_CREATE_PID, 9);
     if (pid > 0xFFFFu) { fail(c, CC4_E_CAPACITY); pid = 0xFFFFu; }
@@ -343,11 +373,11 @@ template <class Pred> __device__ __forceinline__ int sess_kth(const Cc4Dyn *s, i
     }
     return -1;
 }
-__device__ __noinline__ int sess_find(const Cc4Dyn *s, int r, int id)
+__device__ CC4_INL5 int sess_find(const Cc4Dyn *s, int r, int id)
 {
     return sess_first(s, [=](uint32_t w, uint32_t f) { return SF_AGENT(f) == (uint32_t)r && S_ID(w) == (uint32_t)id; });
 }
-__device__ __noinline__ void ports_drop(Cx c, int r, int id)
+__device__ CC4_INL5 void ports_drop(Cx c, int r, int id)
 {   /* stable compaction of the known-port entries */
     Cc4Dyn *s = DYN(c);
     uint32_t *ports = WC(c)->k->ports;
@@ -377,7 +407,7 @@ __device__ __forceinline__ void sess_shift_down(Cc4Dyn *s, int idx, int n)
         __syncwarp();
     }
 }
-__device__ __noinline__ void sess_delete(Cx c, int idx)
+__device__ CC4_INL5 void sess_delete(Cx c, int idx)
 {
     Cc4Dyn *s = DYN(c);
     if (SF_ABS(s->sessf[idx])) ports_drop(c, SF_AGENT(s->sessf[idx]), S_ID(s->sess[idx]));
@@ -387,7 +417,7 @@ __device__ __noinline__ void sess_delete(Cx c, int idx)
     SCR(c)->sess_moved = 1;
 }
 /* State.add_session State.py:305-323 for a red agent; returns the ident */
-__device__ __noinline__ int sess_add(Cx c, int r, int host, int abstract, int root, int pid)
+__device__ CC4_INL4 int sess_add(Cx c, int r, int host, int abstract, int root, int pid)
 {
     Cc4Dyn *s = DYN(c);
     const int n = s->n_sess;
@@ -403,7 +433,7 @@ __device__ __noinline__ int sess_add(Cx c, int r, int host, int abstract, int ro
     if (abstract) SCR(c)->newss |= 1u << r;     /* its ident becomes a known server_session key with the end-turn observation */
     return id;
 }
-__device__ __noinline__ int session_from_pid(const Cc4Dyn *s, int host, uint32_t pid)
+__device__ CC4_INL5 int session_from_pid(const Cc4Dyn *s, int host, uint32_t pid)
 {   /* State.get_session_from_pid State.py:420-444; blue / green session processes are never removed */
     return sess_first(s, [=](uint32_t w, uint32_t) { return S_HOST(w) == (uint32_t)host && S_PID(w) == pid; });
 }
@@ -413,7 +443,7 @@ __device__ __forceinline__ bool blocking(const Cc4Dyn *s, int src_slot, int othe
 }
 
 /* ---- observation bookkeeping for one red agent (ObservationSet / ActionSpace.update ActionSpace.py:170-212) ---- */
-__device__ __noinline__ void obs_entry(Cx c, int r, int key_ip, int slot, int iface, int subnet_if, int syshost, int sess)
+__device__ CC4_INL4 void obs_entry(Cx c, int r, int key_ip, int slot, int iface, int subnet_if, int syshost, int sess)
 {   /* [uniform] */
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     if (syshost) set128(s->hn_known[r], slot);
@@ -432,7 +462,7 @@ __device__ __noinline__ void obs_entry(Cx c, int r, int key_ip, int slot, int if
 }
 /* the ident becomes a known server_session key (ActionSpace.update ActionSpace.py:170-212: dict insertion order, no
  * duplicates) */
-__device__ __noinline__ void know_session(Cx c, int r, int id)
+__device__ CC4_INL4 void know_session(Cx c, int r, int id)
 {   /* [uniform] */
     Cc4Dyn *s = DYN(c);
     const int n = s->n_ss[r];
@@ -447,7 +477,7 @@ __device__ __noinline__ void know_session(Cx c, int r, int id)
 /* RedSessionCheck reports every session of the agent (RedSessionCheck.py:57-63): the idents of its abstract sessions become
  * known server_session keys in dict (= pool) order.  Only agents that got a new abstract session this tick can learn
  * something (sess_add sets x->newss).  [uniform]: pool scanned 32 entries at a time */
-__device__ __noinline__ void learn_new_sessions(Cx c)
+__device__ CC4_INL6 void learn_new_sessions(Cx c)
 {
     Cc4Dyn *s = DYN(c);
     const uint32_t news = SCR(c)->newss;
@@ -501,7 +531,7 @@ __device__ __forceinline__ bool fsm_append(Cx c, int r, int slot, int hn, int st
  * observation (RedSessionCheck._all_red_sessions_observation RedSessionCheck.py:57-63: one hostname-keyed entry with
  * Sessions, Interface+Subnet and System info per session host) is represented by the host mask x->sess_hosts[r] instead
  * of explicit entries; ActionSpace.update (ActionSpace.py:170-212) and the FSM bookkeeping consume the mask. */
-__device__ __noinline__ void agent_end_turn(Cx c, int r)
+__device__ CC4_INL8 void agent_end_turn(Cx c, int r)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     Cc4Fsm *f = &s->fsm[r];
@@ -582,7 +612,7 @@ __device__ __noinline__ void agent_end_turn(Cx c, int r)
 
 /* FiniteStateRedAgent._choose_host_and_action :296-336 + replace_action_if_invalid SimulationController.py:1068-1112.
  * Returns the packed action (ticks = 0). */
-__device__ __noinline__ uint32_t red_policy(Cx c, int r)
+__device__ CC4_INL8 uint32_t red_policy(Cx c, int r)
 {
     Cc4Dyn *s = DYN(c);
     int actor = A_RED0 + r;
@@ -644,7 +674,7 @@ __device__ __noinline__ uint32_t red_policy(Cx c, int r)
 /* ------------------------------------------------------------------------------------------------ */
 __device__ __forceinline__ int blue_sorted_subnet(int b, int i) { return b < 4 ? b : (i == 0 ? S_ADM : i == 1 ? S_OFF : S_PAZ); }
 /* index -> packed action (ticks = 0) | ACT_VALID when the index is a mask-True entry */
-__device__ __noinline__ uint32_t blue_decode(const Cc4Dyn *s, int b, int idx)
+__device__ CC4_INL8 uint32_t blue_decode(const Cc4Dyn *s, int b, int idx)
 {
     Act a = { AC_SLEEP, -1, -1, 0 };
     int n = b == 4 ? 3 : 1, H = 16 * n, T = 8 * n, m = 1, hostidx = -1, tidx = -1, code = AC_SLEEP;
@@ -671,7 +701,7 @@ __device__ __noinline__ uint32_t blue_decode(const Cc4Dyn *s, int b, int idx)
     return pack_act(a, 0) | (m ? ACT_VALID : 0u);
 }
 
-__device__ __noinline__ void ev_procpid(Cx c, int slot, int pid)
+__device__ CC4_INL4 void ev_procpid(Cx c, int slot, int pid)
 {
     DYN(c)->ev[slot] |= EV_PROC;
     /* only hosts some blue agent monitors ever have their event pids read (Monitor.py:66-70) */
@@ -681,7 +711,7 @@ __device__ __noinline__ void ev_procpid(Cx c, int slot, int pid)
 }
 
 /* StopProcess.execute_targeteted_local_action + kill_process StopProcess.py:23-58 [uniform] */
-__device__ __noinline__ void stop_process(Cx c, int actor, int h, uint32_t pid)
+__device__ CC4_INL6 void stop_process(Cx c, int actor, int h, uint32_t pid)
 {
     Cc4Dyn *s = DYN(c);
     int pi = proc_find(c, h, pid);
@@ -708,7 +738,7 @@ __device__ __noinline__ void stop_process(Cx c, int actor, int h, uint32_t pid)
 }
 
 /* RestoreFromBackup.py:9-19 + Host.restore Host.py:373-429 [uniform] */
-__device__ __noinline__ void do_restore(Cx c, int h)
+__device__ CC4_INL6 void do_restore(Cx c, int h)
 {
     Cc4Dyn *s = DYN(c); const Cc4Stat *st = WC(c)->st;
     _Pragma("unroll 1") for (;;) {      /* every session on the host goes, in pool order */
@@ -726,7 +756,7 @@ __device__ __noinline__ void do_restore(Cx c, int h)
 }
 
 /* DecoyAction.execute DecoyAction.py:47-112 with DeployDecoy.CANDIDATE_DECOYS DeployDecoy.py:27 [uniform] */
-__device__ __noinline__ void do_decoy(Cx c, int b, int h)
+__device__ CC4_INL6 void do_decoy(Cx c, int b, int h)
 {
     int actor = A_BLUE0 + b;
     uint32_t used = 0;
@@ -759,7 +789,7 @@ __device__ __noinline__ void do_decoy(Cx c, int b, int h)
 }
 
 /* a blue agent's own Monitor action (Monitor.py:35-74 for one agent) [uniform] */
-__device__ __noinline__ void monitor_one(Cx c, int b)
+__device__ CC4_INL6 void monitor_one(Cx c, int b)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     _Pragma("unroll 1") for (int h = lane_id(); h < CC4_NSLOT; h += 32) if (blue_of_subnet(slot_subnet(h)) == b) { uint32_t e = s->ev[h]; s->ev[h] = (uint8_t)((e & (EV_PROC | EV_NET)) << 2); }
@@ -777,7 +807,7 @@ __device__ __noinline__ void monitor_one(Cx c, int b)
     x->n_evpid = w;
 }
 
-__device__ __noinline__ void exec_blue(Cx c, int b, uint32_t aw)
+__device__ CC4_INL6 void exec_blue(Cx c, int b, uint32_t aw)
 {   /* [uniform] */
     Cc4Dyn *s = DYN(c);
     const Act a = unpack_act(aw);
@@ -809,7 +839,7 @@ __device__ __noinline__ void exec_blue(Cx c, int b, uint32_t aw)
 /* green                                                                                            */
 /* ------------------------------------------------------------------------------------------------ */
 /* PhishingEmail._create_new_session PhishingEmail.py:42-113 ([uniform], in green-agent order); x->g.hostagents is current */
-__device__ __noinline__ void do_phishing(Cx c, int g)
+__device__ CC4_INL6 void do_phishing(Cx c, int g)
 {
     Cc4Dyn *s = DYN(c);
     const uint8_t *ha = reinterpret_cast<const uint8_t *>(SCR(c)->g.hostagents);
@@ -860,7 +890,7 @@ __device__ __noinline__ void do_phishing(Cx c, int g)
  * dependent.  Result: bits 0-7 = reward penalty (LWF / ASF, BlueRewardMachine.py:35-65) as a positive number.
  * The agent's Philox block stays in registers: 4 words cover Sleep / AccessService, LocalWork needs a second block. */
 #define GREEN_PHISH 0x100
-__device__ __noinline__ int green_tick(Cx c, int g, uint32_t *ev_words)
+__device__ CC4_INL8 int green_tick(Cx c, int g, uint32_t *ev_words)
 {
     Cc4Dyn *s = DYN(c);
     const int actor = A_GREEN0 + g, gh = s->green_host[g], gsn = gh >> 4;
@@ -909,7 +939,7 @@ __device__ __noinline__ int green_tick(Cx c, int g, uint32_t *ev_words)
 /* ------------------------------------------------------------------------------------------------ */
 /* red actions (lane 0)                                                                             */
 /* ------------------------------------------------------------------------------------------------ */
-__device__ __noinline__ int route(int src, int dst, int *out)
+__device__ CC4_INL5 int route(int src, int dst, int *out)
 {   /* hosts on the tree path src -> dst (Action.py:101-117, topology EnterpriseScenarioGenerator.py:373-416) */
     int n = 0;
     if (src == dst) { out[n++] = src; return n; }
@@ -926,7 +956,7 @@ __device__ __noinline__ int route(int src, int dst, int *out)
 }
 
 /* ExploitAction._create_new_session ExploitAction.py:212-262 [uniform] */
-__device__ __noinline__ int exploit_new_session(Cx c, int r, int target)
+__device__ CC4_INL3 int exploit_new_session(Cx c, int r, int target)
 {
     int pid = create_pid(c, A_RED0 + r, target);
     proc_append(c, target, P_MAKE(pid, K_SHELL, 0, 0));
@@ -934,7 +964,7 @@ __device__ __noinline__ int exploit_new_session(Cx c, int r, int target)
     return pid;
 }
 /* index of the known-port entry of (agent, abstract session, host), -1 if none [uniform] */
-__device__ __noinline__ int ports_find(Cx c, int r, int id, int host)
+__device__ CC4_INL3 int ports_find(Cx c, int r, int id, int host)
 {
     const uint32_t *ports = WC(c)->k->ports;
     const int n = DYN(c)->n_ports;
@@ -948,7 +978,7 @@ __device__ __noinline__ int ports_find(Cx c, int r, int id, int host)
 }
 
 /* [uniform]: the whole warp executes the action; scans are lane-parallel */
-__device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
+__device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
 {
     Cc4Dyn *s = DYN(c);
     const Act a = unpack_act(aw);
@@ -1165,7 +1195,7 @@ __device__ __noinline__ int exec_red(Cx c, int r, uint32_t aw)
 }
 
 /* RedSessionCheck._choose_new_primary_session RedSessionCheck.py:34-55 ([uniform]; agent r holds n sessions, none with ident 0) */
-__device__ __noinline__ void rsc_reelect(Cx c, int r, int n)
+__device__ CC4_INL6 void rsc_reelect(Cx c, int r, int n)
 {
     Cc4Dyn *s = DYN(c);
     int pk = (int)rng_int(c, A_RED0 + r, ST_RSC_PRIMARY, (uint32_t)n);
@@ -1185,7 +1215,7 @@ __device__ __noinline__ void rsc_reelect(Cx c, int r, int n)
 }
 
 /* SimulationController.different_subnet_agent_reassignment :820-903 [uniform] */
-__device__ __noinline__ void reassign(Cx c)
+__device__ CC4_INL6 void reassign(Cx c)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     uint8_t list[32]; int n = 0;   /* (agent, ident) pairs, agents ascending then dict order */
