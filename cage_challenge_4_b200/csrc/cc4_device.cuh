@@ -135,12 +135,13 @@ __device__ __forceinline__ uint32_t pack_act(const Act &a, int ticks) { return I
 
 /* per-warp scratch (shared memory, not persisted) */
 struct Scratch {
-    uint16_t ctr[NAG + 1];                       /* per-actor draw counter / tape position of this tick; [NAG] = reset */
+    uint16_t ctr_br[12];                         /* draw counter / tape position of this tick: blue 0-4, red 5-10, [11] = reset stream */
+    uint8_t ctr_g[CC4_MAXGREEN];                 /* ... of the green agents (a green agent draws at most 7 times per tick) */
     uint16_t oent[CC4_NRED][CC4_OENT_CAP];       /* explicit observation entries: slot | key_ip<<8 | iface<<9 | subnet_if<<10 | syshost<<11 | sess<<12 */
     uint8_t n_oent[8];
     uint8_t have_first[8], succ0[8], has_act0[8];
     uint32_t act0[8];                             /* IP_MAKE(code, host, subnet, session, 0) */
-    uint32_t evpid[16]; int n_evpid;              /* (slot<<16 | pid) carried by this tick's process_creation events */
+    uint32_t evpid[8]; int n_evpid;               /* (slot<<16 | pid) carried by this tick's process_creation events: at most one per red agent */
     uint32_t subw[11];                            /* this tick's due action per blue / red actor (IP_MAKE, ticks = 0) */
     uint8_t dropped[16];
     int16_t act_si[8];                            /* pool index of the session each red agent's due action names, resolved lane-parallel before the red phase */
@@ -164,11 +165,20 @@ struct Scratch {
 /* per-warp context (shared memory): everything a device function needs besides the record and the scratch */
 struct WarpCtx {
     Cc4Stat *st; Cc4Cold *k;
-    const cc4_draw *tape; const uint32_t *seg; uint32_t n_segs;
+    const uint32_t *seg;      /* tape mode: this episode's segment offsets */
     int tick;                 /* state step_count at the start of the tick; -1 during reset */
-    int steps, rng_mode;
-    uint32_t k0, k1, ep_lo; int env;
+    uint32_t k1, ep_lo; int env;
 };
+/* what is the same for every episode of the block (set by the kernel prologue) */
+struct BlockCtx {
+    const cc4_draw *tape; uint32_t n_segs;
+    int steps, rng_mode;
+    uint32_t k0;
+};
+__shared__ BlockCtx g_blk;
+/* per-actor draw counters: 16 bits for the blue / red / reset streams, 8 bits for the green ones */
+__device__ __forceinline__ uint32_t ctr_get(const struct Scratch *x, int actor);
+__device__ __forceinline__ void ctr_set(struct Scratch *x, int actor, uint32_t v);
 struct __align__(16) WarpSmem {
     Cc4Dyn dyn;
     Scratch x;
@@ -179,6 +189,19 @@ struct __align__(16) WarpSmem {
  * context is passed through the thread stack (ncu r01a: the stack-resident context cost 24 % long-scoreboard stalls). */
 extern __shared__ __align__(16) unsigned char smem_raw[];
 typedef uint32_t Cx;
+__device__ __forceinline__ uint32_t ctr_get(const Scratch *x, int actor) { return actor < A_GREEN0 ? x->ctr_br[actor] : actor == NAG ? x->ctr_br[11] : x->ctr_g[actor - A_GREEN0]; }
+__device__ __forceinline__ void ctr_set(Scratch *x, int actor, uint32_t v)
+{
+    if (actor < A_GREEN0) x->ctr_br[actor] = (uint16_t)v; else if (actor == NAG) x->ctr_br[11] = (uint16_t)v; else x->ctr_g[actor - A_GREEN0] = (uint8_t)v;
+}
+/* host of green agent g (agents are numbered over the user hosts in creation order) */
+__device__ __forceinline__ int green_host_of(const Cc4Dyn *s, int g)
+{
+    const uint64_t cum = s->green_cum;
+    const uint32_t kk = (uint32_t)g * 0x01010101u;
+    const int sn = (__popc(__vcmpleu4((uint32_t)cum, kk)) + __popc(__vcmpleu4((uint32_t)(cum >> 32), kk))) >> 3;
+    return sn * 16 + 6 + (g - (sn ? (int)((cum >> (8 * (sn - 1))) & 0xFFu) : 0));
+}
 #define WS(cx_) (reinterpret_cast<WarpSmem *>(smem_raw + (cx_)))
 #define DYN(cx_) (&WS(cx_)->dyn)
 #define SCR(cx_) (&WS(cx_)->x)
@@ -208,12 +231,12 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
 __device__ CC4_INL9 uint64_t tape_next(Cx c, int actor, int site, int kind, uint32_t n)
 {
     uint32_t seg = actor == NAG ? 0u : 1u + (uint32_t)WC(c)->tick * NAG + (uint32_t)actor;
-    if (seg >= WC(c)->n_segs) { fail(c, CC4_E_TAPE_END); return 0; }
-    uint32_t i = WC(c)->seg[seg] + SCR(c)->ctr[actor];
+    if (seg >= g_blk.n_segs) { fail(c, CC4_E_TAPE_END); return 0; }
+    uint32_t i = WC(c)->seg[seg] + ctr_get(SCR(c), actor);
     if (i >= WC(c)->seg[seg + 1]) { fail(c, CC4_E_TAPE_END); return 0; }
-    cc4_draw d = WC(c)->tape[i];
+    cc4_draw d = g_blk.tape[i];
     if (d.site != site || d.kind != kind || d.n != n) fail(c, CC4_E_TAPE_SITE);
-    SCR(c)->ctr[actor]++;
+    ctr_set(SCR(c), actor, ctr_get(SCR(c), actor) + 1);
     return d.val;
 }
 /* block `blk` of the actor's stream for this tick (registers only) */
@@ -221,7 +244,7 @@ __device__ CC4_INL9 uint4 philox_block(Cx c, int actor, uint32_t blk)
 {
     const WarpCtx *g = WC(c);
     uint32_t o[4] = { blk, (uint32_t)actor, actor == NAG ? 0u : (uint32_t)g->tick + 1u, g->ep_lo };
-    philox4x32_10(o, g->k0, g->k1);
+    philox4x32_10(o, g_blk.k0, g->k1);
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 __device__ __forceinline__ uint32_t u4_word(const uint4 &v, uint32_t i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
@@ -231,7 +254,8 @@ __device__ __forceinline__ uint32_t u4_word(const uint4 &v, uint32_t i) { return
 __device__ CC4_RNG_INLINE uint32_t rng_word(Cx c, int actor)
 {
     Scratch *x = SCR(c);
-    uint32_t j = x->ctr[actor]++;
+    const uint32_t j = ctr_get(x, actor);
+    ctr_set(x, actor, j + 1);
     int slot = actor == NAG ? CC4_NRED : (actor >= A_RED0 && actor < A_GREEN0) ? actor - A_RED0 : -1;   /* blue / green draws are rare: uncached */
     if (slot < 0) { uint4 v = philox_block(c, actor, j >> 2); return u4_word(v, j & 3u); }
     if (x->blk_id[slot] != (j >> 2)) {
@@ -243,13 +267,13 @@ __device__ CC4_RNG_INLINE uint32_t rng_word(Cx c, int actor)
 __device__ __forceinline__ double f64_from_word(uint32_t w) { return (double)w * 2.3283064365386962890625e-10; }     /* w / 2^32, exact */
 __device__ CC4_INL2 uint32_t rng_int(Cx c, int actor, int site, uint32_t n)
 {
-    if (WC(c)->rng_mode == 1) { uint64_t v = tape_next(c, actor, site, 0, n); return v < n ? (uint32_t)v : 0u; }
+    if (g_blk.rng_mode == 1) { uint64_t v = tape_next(c, actor, site, 0, n); return v < n ? (uint32_t)v : 0u; }
     if (n == 1 && site == ST_FSM_PARAM) return 0u;      /* a one-option parameter pick spends no word (oracle: rng_int) */
     return __umulhi(rng_word(c, actor), n);
 }
 __device__ CC4_INL2 double rng_f64(Cx c, int actor, int site, uint32_t n)
 {
-    if (WC(c)->rng_mode == 1) return __longlong_as_double((long long)tape_next(c, actor, site, 1, n));
+    if (g_blk.rng_mode == 1) return __longlong_as_double((long long)tape_next(c, actor, site, 1, n));
     return f64_from_word(rng_word(c, actor));
 }
 
@@ -625,7 +649,7 @@ __device__ CC4_INL8 uint32_t red_policy(Cx c, int r)
     if (nk == 0) { fail(c, CC4_E_UNREACHABLE); return ACT_SLEEP_WORD; }
     /* production mode: host pick, action pick and at most two parameter picks fit the four words of the stream's first
        Philox block, which stays in registers; the block is left in the stream cache for the action code that follows */
-    const bool tape = WC(c)->rng_mode == 1;
+    const bool tape = g_blk.rng_mode == 1;
     const uint4 blk = tape ? make_uint4(0, 0, 0, 0) : philox_block(c, actor, 0);
     uint32_t j = 0;
     auto ri = [&](int site, uint32_t n) -> uint32_t {
@@ -661,7 +685,7 @@ __device__ CC4_INL8 uint32_t red_policy(Cx c, int r)
     #undef PICK_SESSION
     if (!tape) {
         Scratch *x = SCR(c);
-        x->ctr[actor] = (uint16_t)j;
+        ctr_set(x, actor, j);
         x->blk_id[r] = 0; x->blk[r][0] = blk.x; x->blk[r][1] = blk.y; x->blk[r][2] = blk.z; x->blk[r][3] = blk.w;
     }
     if (col >= 1 && col <= 4 && !bit128(s->ip_known[r], a.host)) a.code = AC_INVALID;
@@ -706,7 +730,7 @@ __device__ CC4_INL4 void ev_procpid(Cx c, int slot, int pid)
     DYN(c)->ev[slot] |= EV_PROC;
     /* only hosts some blue agent monitors ever have their event pids read (Monitor.py:66-70) */
     if (pid >= 0 && blue_of_subnet(slot_subnet(slot)) >= 0) {
-        if (SCR(c)->n_evpid < 16) SCR(c)->evpid[SCR(c)->n_evpid++] = (uint32_t)slot << 16 | (uint32_t)pid; else fail(c, CC4_E_CAPACITY);
+        if (SCR(c)->n_evpid < 8) SCR(c)->evpid[SCR(c)->n_evpid++] = (uint32_t)slot << 16 | (uint32_t)pid; else fail(c, CC4_E_CAPACITY);
     }
 }
 
@@ -843,7 +867,7 @@ __device__ CC4_INL6 void do_phishing(Cx c, int g)
 {
     Cc4Dyn *s = DYN(c);
     const uint8_t *ha = reinterpret_cast<const uint8_t *>(SCR(c)->g.hostagents);
-    int actor = A_GREEN0 + g, gh = s->green_host[g], gsn = gh >> 4;
+    int actor = A_GREEN0 + g, gh = green_host_of(s, g), gsn = gh >> 4;
     if (ha[gh]) return;
     /* (host, agent) pairs in state.hosts order (per subnet: users, then servers), agents ascending on each host.  A red
        agent with a session in the green host's own subnet owns the new session (the LAST such host wins: only the inner
@@ -893,8 +917,8 @@ __device__ CC4_INL6 void do_phishing(Cx c, int g)
 __device__ CC4_INL8 int green_tick(Cx c, int g, uint32_t *ev_words)
 {
     Cc4Dyn *s = DYN(c);
-    const int actor = A_GREEN0 + g, gh = s->green_host[g], gsn = gh >> 4;
-    const bool tape = WC(c)->rng_mode == 1;
+    const int actor = A_GREEN0 + g, gh = green_host_of(s, g), gsn = gh >> 4;
+    const bool tape = g_blk.rng_mode == 1;
     const uint64_t v = WC(c)->k->svc64[gh];     /* issued ahead of the Philox rounds: only LocalWork (1 in 3) uses it, but the latency hides */
     /* production mode: the agent's whole tick fits the four words of ONE Philox block (word 0: action choice and, cut from
        its low half, the service pick; the phishing follow-up continues the stream at word j) */
@@ -932,7 +956,7 @@ __device__ CC4_INL8 int green_tick(Cx c, int g, uint32_t *ev_words)
         if ((s->blocks[gsn] >> dsn & 1) || (s->blocks[dsn] >> gsn & 1)) { atomicOr(&ev_words[d >> 2], EV_NET << ((d & 3) * 8)); out = -c_reward[s->phase][gsn][1]; }
         else if ((tape ? rng_f64(c, actor, ST_AS_FP, 0) : f64_from_word(blk.z)) < 0.01) atomicOr(&ev_words[d >> 2], EV_NET << ((d & 3) * 8));
     }
-    if (!tape) SCR(c)->ctr[actor] = (uint16_t)j;
+    if (!tape) SCR(c)->ctr_g[g] = (uint8_t)j;
     return out;
 }
 

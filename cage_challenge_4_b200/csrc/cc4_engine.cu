@@ -21,7 +21,7 @@ namespace cc4 {
 #define CC4_WARPS_PER_BLOCK 32  /* one block per SM: 1024 threads */
 #endif
 #ifndef CC4_EPB_MAX
-#define CC4_EPB_MAX 53          /* episodes resident in one block's shared memory (53 x 4 288 B = 222 KB of the 227 KB) */
+#define CC4_EPB_MAX 64          /* episodes resident in one block's shared memory (64 x 3 600 B = 225 KB of the 227 KB): two full rounds of 32 warps */
 #endif
 #ifndef CC4_ENDTURN_PER
 #define CC4_ENDTURN_PER 4       /* episodes per warp in the FSM digest phase (6 lanes of work per episode) */
@@ -106,14 +106,12 @@ __device__ __forceinline__ uint8_t obs_element(const Cc4Dyn *s, int b, int p)
     int k = q >> 3, other = k < b ? k : k + 1;   /* the other four agents in sorted order, SimulationController.py:781-804 */
     return (s->msgs[other] >> (q & 7)) & 1;
 }
-/* The five vectors are assembled as ONE bit string (element p of agent b = bit mis + 210*b + p), expanded eight
- * elements at a time into a staging area that overlays the (dead) start of the scratch, and copied out with 128-bit
- * stores.  `mis` = the episode's byte offset inside its 16-byte line (1050 B per episode is only 2-byte aligned): giving
- * the bit string the same lead makes staging byte j and global byte (line start + j) the same element, so whole
- * 16-byte lines move aligned on both sides; only the first and the last line are written by halfwords. */
+/* The five vectors are assembled as ONE bit string (element p of agent b = bit mis + stride*b + p) and expanded into
+ * bytes in registers, sixteen elements per lane, straight into 128-bit stores.  `mis` = the episode's byte offset inside
+ * its 16-byte line (a row of 1 050 or 578 B is only 2-byte aligned): giving the bit string the same lead makes bit j and
+ * global byte (line start + j) the same element, so whole lines go out aligned; only the first and the last line are
+ * written by halfwords. */
 constexpr int OBS_BYTES = CC4_N_BLUE * CC4_OBS_LEN;               /* 1050 */
-constexpr int OBS_STAGE = (14 + OBS_BYTES + 15) / 16 * 16;          /* 1072 */
-static_assert(offsetof(Scratch, obsbits) >= OBS_STAGE, "the observation staging area must not overlap Scratch::obsbits");
 static_assert(sizeof(((Scratch *)0)->obsbits) * 8 >= 14 + OBS_BYTES, "bit string too short");
 __device__ __forceinline__ void bits_or(uint32_t *bits, int off, uint64_t v)
 {   /* OR a <= 59-bit field into the bit string at bit offset off */
@@ -171,30 +169,30 @@ __device__ void w_write_obs(const Cc4Dyn *s, Scratch *x, uint8_t *obs_base /* [n
         bits_or(bits, mis + vec_stride * b + 1 + 59 * (b == 4 ? 3 : 1), (uint64_t)m);
     }
     __syncwarp();
-    /* expand: staging byte j = bit j of the string */
-    uint8_t *stage = reinterpret_cast<uint8_t *>(x);
-    const uint8_t *bytes = reinterpret_cast<const uint8_t *>(bits);
-    const int stage_bytes = (mis + row_bytes + 15) & ~15;
-    _Pragma("unroll 1") for (int g = lane; g < stage_bytes / 8; g += 32) {
-        const uint32_t by = bytes[g];
-        const uint64_t t = (uint64_t)(((by >> 4) * 0x00204081u) & 0x01010101u) << 32 | (((by & 15u) * 0x00204081u) & 0x01010101u);     /* bit k -> byte k */
-        reinterpret_cast<uint64_t *>(stage)[g] = t;
-    }
-    __syncwarp();
-    if (lane < CC4_N_BLUE) stage[mis + vec_stride * lane] = s->phase;   /* element 0 of every vector is the mission phase */
-    __syncwarp();
-    /* copy: 16-byte lines, aligned on both sides */
+    /* expand and store: global byte (line start + j) = bit j of the string.  A lane turns 16 bits into one 16-byte line in
+       registers (4 bits -> 4 bytes by one multiply) and stores it with one 128-bit store; element 0 of every vector is
+       the mission phase, not a bit, and is patched in; the partial first and last line go out by halfwords. */
+    const uint16_t *half = reinterpret_cast<const uint16_t *>(bits);
     uint8_t *gline = obs_base + (goff - (size_t)mis);
     const int end = mis + row_bytes;
-    _Pragma("unroll 1") for (int q = lane; q < stage_bytes / 16; q += 32) {
-        int lo = q * 16;
-        if (lo >= mis && lo + 16 <= end) reinterpret_cast<uint4 *>(gline)[q] = reinterpret_cast<const uint4 *>(stage)[q];
+    auto spread4 = [](uint32_t nib) -> uint32_t { return (nib * 0x00204081u) & 0x01010101u; };
+    _Pragma("unroll 1") for (int q = lane; q * 16 < end; q += 32) {
+        const int lo = q * 16;
+        if (lo >= mis && lo + 16 <= end) {
+            const uint32_t h = half[q];
+            reinterpret_cast<uint4 *>(gline)[q] = make_uint4(spread4(h & 15u), spread4(h >> 4 & 15u), spread4(h >> 8 & 15u), spread4(h >> 12));
+        }
     }
-    {   /* the partial first and last line, by halfwords: lanes 0-7 the first, lanes 8-15 the last */
+    {   /* lanes 0-7: halfwords of the first line, lanes 8-15: of the last line */
         const int k = lane < 8 ? 2 * lane : (end & ~15) + 2 * (lane - 8);
         const bool head = lane < 8 && mis > 0 && k >= mis, tail = lane >= 8 && lane < 16 && (end & 15) && k < end;
-        if (head || tail) *reinterpret_cast<uint16_t *>(gline + k) = *reinterpret_cast<const uint16_t *>(stage + k);
+        if (head || tail) {
+            const uint32_t two = bits[k >> 5] >> (k & 31) & 3u;        /* k is even: both bits are in one word */
+            *reinterpret_cast<uint16_t *>(gline + k) = (uint16_t)((two & 1u) | (two >> 1) << 8);
+        }
     }
+    __syncwarp();       /* orders the line stores before the five byte stores below (same warp, overlapping addresses) */
+    if (lane < CC4_N_BLUE) gline[mis + vec_stride * lane] = s->phase;       /* element 0 of every vector is the mission phase, not a bit */
     __syncwarp();
 }
 __device__ void w_write_mask(const Cc4Dyn *s, uint8_t *mask)
@@ -282,10 +280,10 @@ enum { PH_SETUP, PH_POLICY, PH_BLUE, PH_GREEN, PH_RED, PH_REASSIGN, PH_ENDTURN, 
 /* The action phases are dominated by their most expensive episodes (an exploit or a Restore against nothing due).  The
  * policy phase sorts the block's episodes into four cost classes from the due actions; the action phases hand them out
  * heaviest class first, so the cheap episodes fill the tail instead of leaving most warps idle behind a late expensive one. */
-struct PhaseOrder { int cnt[4]; short list[4][64]; };
+struct PhaseOrder { int cnt[4]; uint8_t list[4][64]; };
 __device__ __forceinline__ void order_push(PhaseOrder *o, int cls, int e)      /* one lane per episode calls this */
 {
-    int k = atomicAdd(&o->cnt[cls], 1); o->list[cls][k] = (short)e;
+    int k = atomicAdd(&o->cnt[cls], 1); o->list[cls][k] = (uint8_t)e;
 }
 __device__ __forceinline__ int order_get(const PhaseOrder *o, int i)
 {
@@ -305,16 +303,20 @@ __device__ __forceinline__ void ph_setup(Cx c)
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     const int lane = lane_id();
     WC(c)->tick = s->step;
-    _Pragma("unroll 1") for (int i = lane; i <= NAG; i += 32) x->ctr[i] = 0;
+    {   /* draw counters: ctr_br (24 B) + ctr_g (80 B) are contiguous */
+        static_assert(offsetof(Scratch, ctr_g) == offsetof(Scratch, ctr_br) + 24, "counter arrays must be adjacent");
+        uint32_t *z = reinterpret_cast<uint32_t *>(x->ctr_br);
+        if (lane < 26) z[lane] = 0;
+    }
     if (lane < 8) { x->n_oent[lane] = 0; x->have_first[lane] = 0; x->succ0[lane] = SUCC_UNKNOWN; x->has_act0[lane] = 0; }
     if (lane <= CC4_NRED) x->blk_id[lane] = 0xFFFFFFFFu;
     if (lane >= 8 && lane < 11) x->g.phish[lane - 8] = 0;
     if (lane == 0) {
         x->n_evpid = 0; x->reward = 0; x->newss = 0;
         /* mission phase: State.check_next_phase_on_update_step State.py:514-544, phases EnterpriseScenarioGenerator.py:854-860 */
-        int q = WC(c)->steps / 3, rem = WC(c)->steps % 3, l0 = q + (rem >= 1), l1 = q + (rem == 2);
+        int q = g_blk.steps / 3, rem = g_blk.steps % 3, l0 = q + (rem >= 1), l1 = q + (rem == 2);
         int np = WC(c)->tick < l0 ? 0 : WC(c)->tick < l0 + l1 ? 1 : 2;
-        if (WC(c)->tick >= WC(c)->steps) fail(c, CC4_E_UNREACHABLE);
+        if (WC(c)->tick >= g_blk.steps) fail(c, CC4_E_UNREACHABLE);
         if (np > s->phase) s->phase = (uint8_t)np;
     }
     __syncwarp();
@@ -574,16 +576,16 @@ __device__ __forceinline__ void ph_finish(Cx c, const uint8_t *msgs /* [5] or nu
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) rew += __shfl_xor_sync(0xFFFFFFFFu, rew, o);       /* lanes 0-7 */
     if (lane >= 8 && lane < 8 + CC4_NBLUE) s->msgs[lane - 8] = msgs ? msgs[lane - 8] : 0;
-    if (WC(c)->rng_mode == 1)
+    if (g_blk.rng_mode == 1)
         _Pragma("unroll 1") for (int a = lane; a < NAG; a += 32) {
             uint32_t seg = 1u + (uint32_t)WC(c)->tick * NAG + (uint32_t)a;
-            if (seg < WC(c)->n_segs && x->ctr[a] != WC(c)->seg[seg + 1] - WC(c)->seg[seg]) fail(c, CC4_E_TAPE_LEFT);
+            if (seg < g_blk.n_segs && ctr_get(x, a) != WC(c)->seg[seg + 1] - WC(c)->seg[seg]) fail(c, CC4_E_TAPE_LEFT);
         }
     if (lane == 0) {
         s->fsm_started |= (uint8_t)active;
         const int step = s->step + 1;
         s->step = (uint16_t)step;
-        s->done = step >= WC(c)->steps - 1;
+        s->done = step >= g_blk.steps - 1;
         const float r = (float)(rew + x->reward + x->cost);
         if (reward_out) { if (accumulate) *reward_out += r; else *reward_out = r; }
         if (done_out) *done_out = s->done;
@@ -660,15 +662,22 @@ template <int per, class F> __device__ __forceinline__ void each_group(int ph, i
 #endif
 }
 
+/* block prologue: the context every episode of the block shares (callers synchronise before the first use) */
+__device__ __forceinline__ void init_block_ctx(const Params &p)
+{
+    if (threadIdx.x == 0) {
+        g_blk.tape = p.tape; g_blk.n_segs = p.seg_off ? p.n_segs : 0;
+        g_blk.steps = p.steps; g_blk.rng_mode = p.rng_mode; g_blk.k0 = p.k0;
+    }
+}
 __device__ __forceinline__ void init_ctx(Cx c, const Params &p, int env, int tick)
 {
     if (lane_id() == 0) {
         uint64_t ep = p.first_episode + (uint64_t)env;
         WarpCtx *g = WC(c);
         g->st = p.stat + env; g->k = p.cold + env;
-        g->steps = p.steps; g->rng_mode = p.rng_mode;
-        g->k0 = p.k0; g->k1 = p.k1hi ^ (uint32_t)(ep >> 32); g->ep_lo = (uint32_t)ep;
-        g->tape = p.tape; g->seg = p.seg_off ? p.seg_off + (size_t)env * (p.n_segs + 1) : nullptr; g->n_segs = p.seg_off ? p.n_segs : 0;
+        g->k1 = p.k1hi ^ (uint32_t)(ep >> 32); g->ep_lo = (uint32_t)ep;
+        g->seg = p.seg_off ? p.seg_off + (size_t)env * (p.n_segs + 1) : nullptr;
         g->tick = tick; g->env = env;
     }
     __syncwarp();
@@ -690,6 +699,7 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
     __shared__ PhaseOrder ord_blue, ord_red;
     __shared__ __align__(8) uint64_t ld_bar[64];
     const int first = env0 + blockIdx.x * epb, n_local = min(epb, env_end - first);
+    init_block_ctx(p);
     if (threadIdx.x <= N_PHASES) next[threadIdx.x] = 0;
     if (threadIdx.x < 4) { ord_blue.cnt[threadIdx.x] = 0; ord_red.cnt[threadIdx.x] = 0; }
     if ((int)threadIdx.x < n_local) mbar_init(&ld_bar[threadIdx.x], 1);
@@ -734,6 +744,8 @@ k_rollout(Params p, int epb, int n_ticks, uint32_t pk0, uint32_t pk1, float *rew
     __shared__ PhaseOrder ord_blue, ord_red;
     __shared__ int alive;
     const int first = blockIdx.x * epb, n_local = min(epb, p.n_envs - first);
+    init_block_ctx(p);
+    __syncthreads();
     _Pragma("unroll 1") for (int e = threadIdx.x >> 5; e < n_local; e += WARPS_PER_BLOCK) { Cx c = (Cx)(e * (int)sizeof(WarpSmem)); init_ctx(c, p, first + e, 0); w_load(DYN(c), p.dyn + first + e); }
     _Pragma("unroll 1") for (int t = 0; t < n_ticks; t++) {
         __syncthreads();
@@ -830,6 +842,7 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
     _Pragma("unroll 1") for (int i = lane_id(); i < (int)(sizeof(ResetSmem) / 4); i += 32) z[i] = 0;
     __syncwarp();
     Cx c = 0;
+    init_block_ctx(p);
     init_ctx(c, p, env, -1);
     if (lane_id() <= CC4_NRED) SCR(c)->blk_id[lane_id()] = 0xFFFFFFFFu;
     __syncwarp();
@@ -858,7 +871,7 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
         }
         /* green agents :700-749 */
         int ng = 0;
-        _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) for (int k = 0; k < s->nuser[sn]; k++) s->green_host[ng++] = (uint8_t)(sn * 16 + 6 + k);
+        { uint64_t cum = 0; _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) { ng += s->nuser[sn]; cum |= (uint64_t)ng << (8 * sn); } s->green_cum = cum; }
         s->ngreen = (uint8_t)ng;
         /* red agents :751-812 */
         _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
@@ -878,7 +891,7 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
                 _Pragma("unroll 1") for (int k = 0; k < s->nserver[sn]; k++) if (st->blue_parent[b] != sn * 16 + k) tmp_add_session_proc(c, t, sn * 16 + k, K_SESSION);
             }
         }
-        _Pragma("unroll 1") for (int g = 0; g < ng; g++) tmp_add_session_proc(c, t, s->green_host[g], K_SESSION);
+        _Pragma("unroll 1") for (int g = 0; g < ng; g++) tmp_add_session_proc(c, t, green_host_of(s, g), K_SESSION);
         {
             int h = st->red_start[0], pid = tmp_create_pid(c, t, h);
             t->procs[h][t->np[h]++] = P_MAKE(pid, K_REDABS, 0, 0);
@@ -901,7 +914,7 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
         /* red_agent_0 digests its initial observation (its start host becomes 'U', FiniteStateRedAgent.py:221-224) */
         { int h0 = st->red_start[0]; s->fsm_order[0][0] = (uint8_t)h0; s->n_fsm[0] = 1; s->fsm_started = 1;
           set128(s->fsm[0].present, h0); set128(s->fsm[0].hn, h0); set128(s->fsm[0].pl[2], h0); }
-        if (WC(c)->rng_mode == 1 && WC(c)->n_segs > 0 && SCR(c)->ctr[NAG] != WC(c)->seg[1] - WC(c)->seg[0]) fail(c, CC4_E_TAPE_LEFT);
+        if (g_blk.rng_mode == 1 && g_blk.n_segs > 0 && ctr_get(SCR(c), NAG) != WC(c)->seg[1] - WC(c)->seg[0]) fail(c, CC4_E_TAPE_LEFT);
     }
     __syncwarp();
     if (valid && obs) w_write_obs(&w->dyn, &w->x, obs, env);

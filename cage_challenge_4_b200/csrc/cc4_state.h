@@ -19,12 +19,12 @@
 
 #define CC4_OSLAB 8          /* processes a host can have at reset: <= 5 services + blue + green + red session */
 #define CC4_ARENA 8192       /* process entries per episode: 128 home slabs of CC4_OSLAB + growth blocks (see Cc4Cold) */
-#define CC4_SESS_CAP 160     /* red sessions per episode (all six agents) */
+#define CC4_SESS_CAP 128     /* red sessions per episode (all six agents; 63 at most in a 3 000-episode probe) */
 #define CC4_PORT_CAP 384     /* (red abstract session, host) known-port entries */
 #define CC4_SUS_CAP 256      /* blue suspicious-pid entries */
 #define CC4_FSM_CAP 64       /* hosts known to one red agent's FSM */
 #define CC4_SS_CAP 48        /* server_session ids known to one red agent */
-#define CC4_OENT_CAP 48      /* observation entries of one red agent in one tick */
+#define CC4_OENT_CAP 24      /* observation entries of one red agent in one tick (a Pingsweep reports <= 16 hosts) */
 
 /* process entry (Simulator/Process.py:12): pid | kind<<16 | root<<20 | svc<<21 | dead<<22
  * svc  = this process backs host.services[kind] (Host.py:124);
@@ -76,7 +76,6 @@ struct Cc4Fsm {
     uint32_t pl[4][4];
     uint32_t present[4], hn[4];
     uint32_t posF[2];
-    uint32_t pad[2];
 };
 
 /* in-flight action (SimulationController.actions_in_progress :246): code | host<<6 | subnet<<14 | session<<18 | ticks<<26 */
@@ -115,7 +114,8 @@ struct __attribute__((aligned(16))) Cc4Dyn {
     uint8_t ev[144];                    /* 137 used */
     uint8_t sessf[CC4_SESS_CAP];
     uint8_t ss[CC4_NRED][CC4_SS_CAP];   /* known server_session ids in dict order */
-    uint8_t green_host[CC4_MAXGREEN];   /* static after reset, staged with the record because every tick needs it */
+    uint64_t green_cum;                 /* byte sn = number of green agents (= user hosts, EnterpriseScenarioGenerator.py:700-749) in subnets <= sn:
+                                           green agent g sits on user host (g - byte[sn-1]) of the subnet sn whose byte first exceeds g */
     uint8_t n_ss[8];
     uint8_t n_fsm[8];
     uint8_t sess_count[8];              /* state.sessions_count[red agent] (stale after Restore, RestoreFromBackup.py:9-19) */
