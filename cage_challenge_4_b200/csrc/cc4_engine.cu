@@ -209,10 +209,12 @@ __device__ void w_write_mask(const Cc4Dyn *s, uint8_t *mask)
 __device__ void w_monitor_all(Cx c)
 {
     Cc4Dyn *s = DYN(c);
-    _Pragma("unroll 1") for (int h = lane_id(); h < CC4_NSLOT; h += 32) {
-        if (blue_of_subnet(slot_subnet(h)) < 0) continue;     /* contractor network and internet have no blue agent */
-        uint32_t e = s->ev[h];
-        s->ev[h] = (uint8_t)((e & (EV_PROC | EV_NET)) << 2);
+    {   /* events -> old events on every host some blue agent monitors, four hosts (one word of ev) per lane: all subnets
+           but the contractor network (slots 64-79, router 132) and the internet host (136) */
+        uint32_t *evw = reinterpret_cast<uint32_t *>(s->ev);
+        const int lane = lane_id();
+        if ((lane >> 2) != S_CON) evw[lane] = (evw[lane] & 0x03030303u) << 2;          /* (EV_PROC | EV_NET) -> (EV_OLDPROC | EV_OLDNET) */
+        if (lane < 2) { const uint32_t keep = lane == 1 ? 0x000000FFu : 0u, w = evw[32 + lane]; evw[32 + lane] = (w & keep) | (((w & ~keep) & 0x03030303u) << 2); }
     }
     __syncwarp();
     if (lane_id() == 0) {
@@ -234,25 +236,22 @@ __device__ void w_scan_sessions(Cx c)
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     const int lane = lane_id();
     if (lane < 24) (&x->sess_hosts[0][0])[lane] = 0;
+    if (lane < 8) x->n_red[lane] = 0;
+    if (lane == 8) { x->has0 = 0; x->misplaced = 0; }
     __syncwarp();
     const int n = s->n_sess;
-    int cnt = 0;                        /* lane r < 6: sessions of agent r */
-    uint32_t has0 = 0, misplaced = 0;
     _Pragma("unroll 1") for (int base = 0; base < n; base += 32) {
         const int i = base + lane;
         uint32_t r = 7, h = 0, id = 1;
-        if (i < n) { const uint32_t w = s->sess[i]; r = SF_AGENT((uint32_t)s->sessf[i]); h = S_HOST(w); id = S_ID(w); atomicOr(&x->sess_hosts[r][h >> 5], 1u << (h & 31)); }
-        const bool mis = i < n && !red_allowed((int)r, (int)(h >> 4));
-#pragma unroll
-        for (int a = 0; a < CC4_NRED; a++) {
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, r == (uint32_t)a);
-            if (lane == a) cnt += __popc(m);
-            if (__any_sync(0xFFFFFFFFu, r == (uint32_t)a && id == 0)) has0 |= 1u << a;
-            if (__any_sync(0xFFFFFFFFu, r == (uint32_t)a && mis)) misplaced |= 1u << a;
+        if (i < n) { const uint32_t w = s->sess[i]; r = SF_AGENT((uint32_t)s->sessf[i]); h = S_HOST(w); id = S_ID(w); }
+        const uint32_t same = __match_any_sync(0xFFFFFFFFu, r);        /* lanes whose session belongs to the same agent */
+        if (i < n) {
+            atomicOr(&x->sess_hosts[r][h >> 5], 1u << (h & 31));
+            if ((int)__ffs(same) - 1 == lane) atomicAdd(&x->n_red[r], __popc(same));    /* one add per agent and chunk */
+            if (id == 0) atomicOr(&x->has0, 1u << r);
+            if (!red_allowed((int)r, (int)(h >> 4))) atomicOr(&x->misplaced, 1u << r);
         }
     }
-    if (lane < 8) x->n_red[lane] = lane < CC4_NRED ? cnt : 0;
-    if (lane == 8) { x->has0 = has0; x->misplaced = misplaced; }
     __syncwarp();
 }
 __device__ void w_build_hostagents(Cx c)
