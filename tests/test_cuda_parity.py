@@ -303,3 +303,28 @@ def test_compact_observations_are_the_unpadded_vectors(n):
         for k, v in enumerate(split_compact(o2.cpu())):
             assert torch.equal(v, o1[:, k, :OBS_SIZES[k]].cpu()), f"tick {t} agent {k}"
         assert torch.equal(o3, o2.cpu()) and torch.equal(r1.cpu(), r3) and torch.equal(r1, r2) and torch.equal(d1.cpu(), d3)
+
+
+def test_config2_state_transition_only_4096_envs():
+    """BASELINE configs[1]: 4 096 episodes, FiniteStateRed + random blue, observation / reward outputs OFF (flags = 0):
+    the state trajectory is the same as with the outputs on, and sampled episodes match the oracle."""
+    n, seed, ticks = 4096, 17, 50
+    a = _engine(n, device=0, seed=seed)
+    b = _engine(n, device=0, seed=seed)
+    a.reset(), b.reset()
+    sample = [0, 1, 63, 64, 2047, 4095]
+    refs = {i: O.OracleEnv(seed=seed, episode=i, steps=500) for i in sample}
+    for r in refs.values():
+        r.reset()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for t in range(ticks):
+        acts = torch.stack([torch.randint(0, k, (n,), generator=g, device="cuda", dtype=torch.int32) for k in (82, 82, 82, 82, 242)], 1).contiguous()
+        a.step(acts, None, flags=0)             # no observation vectors, no reward
+        b.step(acts)
+        ah = acts[sample].cpu().numpy()
+        for k, i in enumerate(sample):
+            refs[i].step(ah[k])
+    for i in sample:
+        ca = a.export_canon(i)
+        assert np.array_equal(ca, b.export_canon(i)) and np.array_equal(ca, refs[i].export()), f"episode {i}"
+    assert not a.error_flags().any()
