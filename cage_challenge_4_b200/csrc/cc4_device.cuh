@@ -240,7 +240,10 @@ __device__ CC4_INL9 uint64_t tape_next(Cx c, int actor, int site, int kind, uint
     return d.val;
 }
 /* block `blk` of the actor's stream for this tick (registers only) */
-__device__ CC4_INL9 uint4 philox_block(Cx c, int actor, uint32_t blk)
+#ifndef CC4_INL10
+#define CC4_INL10 __forceinline__
+#endif
+__device__ CC4_INL10 uint4 philox_block(Cx c, int actor, uint32_t blk)
 {
     const WarpCtx *g = WC(c);
     uint32_t o[4] = { blk, (uint32_t)actor, actor == NAG ? 0u : (uint32_t)g->tick + 1u, g->ep_lo };

@@ -24,7 +24,7 @@ namespace cc4 {
 #define CC4_EPB_MAX 64          /* episodes resident in one block's shared memory (64 x 3 600 B = 225 KB of the 227 KB): two full rounds of 32 warps */
 #endif
 #ifndef CC4_ENDTURN_PER
-#define CC4_ENDTURN_PER 4       /* episodes per warp in the FSM digest phase (6 lanes of work per episode) */
+#define CC4_ENDTURN_PER 2       /* episodes per warp in the FSM digest phase (6 lanes of work per episode; 2 and 4 measure the same) */
 #endif
 constexpr int WARPS_PER_BLOCK = CC4_WARPS_PER_BLOCK;
 constexpr int EPB_MAX = CC4_EPB_MAX;
