@@ -23,6 +23,12 @@ namespace cc4 {
 #ifndef CC4_EPB_MAX
 #define CC4_EPB_MAX 64          /* episodes resident in one block's shared memory (64 x 3 600 B = 225 KB of the 227 KB): two full rounds of 32 warps */
 #endif
+#ifndef CC4_MERGE
+#define CC4_MERGE 0
+#endif
+#ifndef CC4_SPLIT
+#define CC4_SPLIT 0       /* bit 0: filter | blue execution, bit 1: phishing replay | red execution as separate barrier phases (k_step) */
+#endif
 #ifndef CC4_ENDTURN_PER
 #define CC4_ENDTURN_PER 2       /* episodes per warp in the FSM digest phase (6 lanes of work per episode; 2 and 4 measure the same) */
 #endif
@@ -401,7 +407,8 @@ __device__ __forceinline__ void ph_policy(Cx c, int e, bool exists, bool live, i
 }
 
 /* ---- phase 2: filter_actions (:466-486), then blue execution ---- */
-__device__ __forceinline__ void ph_blue(Cx c)
+__device__ __forceinline__ void ph_blue_exec(Cx c);
+__device__ __forceinline__ void ph_blue(Cx c, bool with_exec = true)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     const int lane = lane_id();
@@ -425,6 +432,12 @@ __device__ __forceinline__ void ph_blue(Cx c)
         if (lane == 0) x->sess_moved = 0;
     }
     __syncwarp();
+    if (with_exec) ph_blue_exec(c);
+}
+__device__ __forceinline__ void ph_blue_exec(Cx c)
+{
+    Scratch *x = SCR(c);
+    const int lane = lane_id();
     /* execution: priority-1 ControlTraffic first (ControlTraffic.py:19), then agent order; warp-uniform: every lane runs the
        same action code, list scans inside are lane-parallel */
     {
@@ -495,7 +508,7 @@ __device__ __forceinline__ void green_items(int ph, int first, int n_local, int 
 }
 
 /* ---- phase 4: red execution in agent order ---- */
-__device__ __forceinline__ void ph_red(Cx c)
+__device__ __forceinline__ void ph_phishing(Cx c)
 {
     Scratch *x = SCR(c);
     /* phishing e-mails of this tick's green LocalWork (GreenLocalWork.py:118-124), in green-agent order */
@@ -504,6 +517,11 @@ __device__ __forceinline__ void ph_red(Cx c)
         _Pragma("unroll 1") for (int k = 0; k < 3; k++) { uint32_t m = x->g.phish[k]; while (m) { int b = __ffs(m) - 1; m &= m - 1; do_phishing(c, k * 32 + b); } }
         __syncwarp();
     }
+}
+__device__ __forceinline__ void ph_red(Cx c, bool with_phishing = true)
+{
+    Scratch *x = SCR(c);
+    if (with_phishing) ph_phishing(c);
     {
         const int lane = lane_id();
         bool real = false;
@@ -618,14 +636,14 @@ template <class F> __device__ __forceinline__ void each_episode(int ph, int firs
 #ifdef CC4_PHASE_CLOCKS
         const long long t0 = clock64();
         f(c, e);
-        if (lane_id() == 0 && g_phase_clk) g_phase_clk[(size_t)(first + e) * PC_STRIDE + 2 * ph] += (unsigned long long)(clock64() - t0);
+        if (lane_id() == 0 && g_phase_clk && ph < N_PHASES) g_phase_clk[(size_t)(first + e) * PC_STRIDE + 2 * ph] += (unsigned long long)(clock64() - t0);
 #else
         f(c, e);
 #endif
     }
     __syncthreads();
 #ifdef CC4_PHASE_CLOCKS
-    if (threadIdx.x == 0 && g_phase_clk && n_local > 0) g_phase_clk[(size_t)first * PC_STRIDE + 2 * ph + 1] += (unsigned long long)(clock64() - tb0);
+    if (threadIdx.x == 0 && g_phase_clk && n_local > 0 && ph < N_PHASES) g_phase_clk[(size_t)first * PC_STRIDE + 2 * ph + 1] += (unsigned long long)(clock64() - tb0);
 #endif
 }
 
@@ -692,14 +710,14 @@ struct StepIO { const int32_t *actions; const uint8_t *msgs; uint8_t *obs; float
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
 k_step(Params p, int env0, int env_end, int epb, StepIO io)
 {
-    __shared__ int next[N_PHASES + 1];
+    __shared__ int next[N_PHASES + 4];
     __shared__ uint8_t ng_s[64];
     __shared__ short gend[64];
     __shared__ PhaseOrder ord_blue, ord_red;
     __shared__ __align__(8) uint64_t ld_bar[64];
     const int first = env0 + blockIdx.x * epb, n_local = min(epb, env_end - first);
     init_block_ctx(p);
-    if (threadIdx.x <= N_PHASES) next[threadIdx.x] = 0;
+    if (threadIdx.x < N_PHASES + 4) next[threadIdx.x] = 0;
     if (threadIdx.x < 4) { ord_blue.cnt[threadIdx.x] = 0; ord_red.cnt[threadIdx.x] = 0; }
     if ((int)threadIdx.x < n_local) mbar_init(&ld_bar[threadIdx.x], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -714,22 +732,47 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
         ph_setup(c);
         if (lane_id() == 0) ng_s[e] = DYN(c)->ngreen;
     });
-    each_group<2>(PH_POLICY, first, n_local, next, [&](Cx c, int e, bool exists, int sl) {
-        ph_policy(c, e, exists, exists, sl, io.actions + (size_t)(first + (exists ? e : 0)) * 5, 0, 0, 0, &ord_blue, &ord_red);
-    });
-    each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { ph_blue(c); }, &ord_blue);
-    green_items(PH_GREEN, first, n_local, next, ng_s, gend);
-    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c); }, &ord_red);
-    each_episode(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { ph_reassign(c); });
-    each_group<CC4_ENDTURN_PER>(PH_ENDTURN, first, n_local, next, [&](Cx c, int, bool exists, int sl) { ph_endturn(c, exists, sl); });
-    each_episode(PH_FINISH, first, n_local, next, [&](Cx c, int e) {
+    /* CC4_MERGE (tuning knob): which neighbouring per-episode phases run back to back inside one work item instead of
+       being separated by a block barrier: bit 0 red + reassign, bit 1 FSM digest + finish, bit 2 red ... finish all in
+       one item.  Every merge measures slower (profiles/r01x_variants.txt: 0.477 ms -> 0.501 / 0.487 / 0.576 ms): fewer
+       barriers mean better warp utilisation but two code regions live at once. */
+    auto finish = [&](Cx c, int e) {
         const int env = first + e;
         ph_finish(c, io.msgs ? io.msgs + (size_t)env * 5 : nullptr, (io.flags & CC4_STEP_REWARD) && io.reward ? io.reward + env : nullptr, false,
                   io.done ? io.done + env : nullptr);
         if ((io.flags & CC4_STEP_OBS) && io.obs) w_write_obs(DYN(c), SCR(c), io.obs, env, (io.flags & CC4_STEP_OBS_COMPACT) != 0);
         __syncwarp();
         if (lane_id() == 0) bulk_store(p.dyn + env, DYN(c), (uint32_t)sizeof(Cc4Dyn));
+    };
+    each_group<2>(PH_POLICY, first, n_local, next, [&](Cx c, int e, bool exists, int sl) {
+        ph_policy(c, e, exists, exists, sl, io.actions + (size_t)(first + (exists ? e : 0)) * 5, 0, 0, 0, &ord_blue, &ord_red);
     });
+#if CC4_SPLIT & 1
+    each_episode(N_PHASES + 1, first, n_local, next, [&](Cx c, int) { ph_blue(c, false); });
+    each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { ph_blue_exec(c); }, &ord_blue);
+#else
+    each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { ph_blue(c); }, &ord_blue);
+#endif
+    green_items(PH_GREEN, first, n_local, next, ng_s, gend);
+#if CC4_SPLIT & 2
+    each_episode(N_PHASES + 2, first, n_local, next, [&](Cx c, int) { ph_phishing(c); });
+#endif
+#if CC4_MERGE & 4
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int e) { ph_red(c); ph_reassign(c); ph_endturn(c, true, lane_id()); __syncwarp(); finish(c, e); }, &ord_red);
+#else
+#if CC4_MERGE & 1
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c); ph_reassign(c); }, &ord_red);
+#else
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c, !(CC4_SPLIT & 2)); }, &ord_red);
+    each_episode(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { ph_reassign(c); });
+#endif
+#if CC4_MERGE & 2
+    each_episode(PH_FINISH, first, n_local, next, [&](Cx c, int e) { ph_endturn(c, true, lane_id()); __syncwarp(); finish(c, e); });
+#else
+    each_group<CC4_ENDTURN_PER>(PH_ENDTURN, first, n_local, next, [&](Cx c, int, bool exists, int sl) { ph_endturn(c, exists, sl); });
+    each_episode(PH_FINISH, first, n_local, next, finish);
+#endif
+#endif
     if (lane_id() == 0) bulk_store_wait();      /* shared memory must outlive the copies this lane started */
 }
 
