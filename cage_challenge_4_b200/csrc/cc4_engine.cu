@@ -336,22 +336,24 @@ __device__ __forceinline__ void ph_setup(Cx c)
 }
 
 /* ---- phase 1: policies (:236-248) and duration queue (:245-265): one lane per blue / red actor.  The scripted red
-   agents only read their own knowledge and draw from their own stream, so the six run side by side.  Eleven actors leave
-   most of a warp idle, so a warp takes TWO episodes (lanes 0-15 and 16-31: `sl` = lane inside the half, `c` differs per
-   half); `live` = the half has an episode that is still running.  `actions` = the episode's five BlueFixedActionWrapper
+   agents only read their own knowledge and draw from their own stream, so the six run side by side.  A work item is the
+   blue half (index decoding, 5 lanes) or the red half (FiniteStateRed choice, 6 lanes) of FOUR episodes, 8 lanes each
+   (`sl` = lane inside the group, `c` differs per group), so a warp never mixes the two code paths; `live` = the group has
+   an episode that is still running.  `actions` = the episode's five BlueFixedActionWrapper
    indices, or null for the benchmark's synthetic policy (k_rollout): index ~ U{0..81} (agents 0-3) / U{0..241} (agent 4),
    Philox keyed (policy_seed, episode, tick) exactly as oracle/cc4_oracle.c cc4o_run_episodes.  Also sorts the episode into
    the cost classes of the two action phases (each_episode). ---- */
 /*                                          Sl Mo An Rm Rs De Bl Al In  -  DRS Ag St DD Ex Pr Im Dg Wd */
 __constant__ uint8_t c_act_weight[32] = { 0, 2, 0, 4, 6, 4, 1, 1, 0, 0, 5, 3, 3, 3, 6, 4, 3, 3, 0 };
-__device__ __forceinline__ void ph_policy(Cx c, int e, bool exists, bool live, int sl, const int32_t *actions, uint32_t pk0, uint32_t pk1, uint64_t ep,
-                                          PhaseOrder *ord_blue, PhaseOrder *ord_red)
+__device__ __forceinline__ void ph_policy(Cx c, int e, bool exists, bool live, int sl, bool red_part, const int32_t *actions, uint32_t pk0, uint32_t pk1,
+                                          uint64_t ep, PhaseOrder *ord_blue, PhaseOrder *ord_red)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
-    int cost = 0, wb = 0, wr = 0;
-    if (live && sl < 11) {
+    int cost = 0, wgt = 0;
+    if (live && sl < (red_part ? CC4_NRED : CC4_NBLUE)) {
+        const int actor = red_part ? A_RED0 + sl : sl;
         uint32_t aw = ACT_SLEEP_WORD;
-        if (sl < A_RED0) {
+        if (!red_part) {
             int idx;
             if (actions) idx = actions[sl];
             else {
@@ -362,47 +364,46 @@ __device__ __forceinline__ void ph_policy(Cx c, int e, bool exists, bool live, i
             aw = blue_decode(s, sl, idx) & ~ACT_VALID;
             if (IP_CODE(aw) == AC_RESTORE) cost = -1;      /* Restore.py:70, charged on submission :310-311 */
         }
-        else if (s->red_active >> (sl - A_RED0) & 1) aw = red_policy(c, sl - A_RED0);
-        uint32_t ip = s->inprog[sl], due = ACT_SLEEP_WORD;
+        else if (s->red_active >> sl & 1) aw = red_policy(c, sl);
+        uint32_t ip = s->inprog[actor], due = ACT_SLEEP_WORD;
         if (IP_CODE(ip) == IP_NONE) ip = aw | (uint32_t)c_duration[IP_CODE(aw)] << 26;
         int ticks = (int)IP_TICKS(ip) - 1;
-        if (ticks < 1) { due = ip & ~(0xFu << 26); s->inprog[sl] = IP_NONE; }
+        if (ticks < 1) { due = ip & ~(0xFu << 26); s->inprog[actor] = IP_NONE; }
         else {
-            s->inprog[sl] = (ip & ~(0xFu << 26)) | (uint32_t)ticks << 26;
-            if (sl >= A_RED0) obs_push(c, sl - A_RED0, SUCC_INPROG, false, ACT_SLEEP_WORD);
+            s->inprog[actor] = (ip & ~(0xFu << 26)) | (uint32_t)ticks << 26;
+            if (red_part) obs_push(c, sl, SUCC_INPROG, false, ACT_SLEEP_WORD);
         }
-        x->subw[sl] = due;
-        const int wgt = c_act_weight[IP_CODE(due) & 31u];
-        if (sl < A_RED0) wb = wgt; else wr = wgt;
+        x->subw[actor] = due;
+        wgt = c_act_weight[IP_CODE(due) & 31u];
     }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {       /* sums over the 16 lanes of the half */
-        cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o); wb += __shfl_xor_sync(0xFFFFFFFFu, wb, o); wr += __shfl_xor_sync(0xFFFFFFFFu, wr, o);
-    }
+    for (int o = 4; o > 0; o >>= 1) { cost += __shfl_xor_sync(0xFFFFFFFFu, cost, o); wgt += __shfl_xor_sync(0xFFFFFFFFu, wgt, o); }     /* sums over the episode's 8 lanes */
     if (exists && sl == 0) {
-        if (live) x->cost = cost;
-        order_push(ord_blue, wb == 0 ? 0 : wb <= 3 ? 1 : wb <= 7 ? 2 : 3, e);
-        order_push(ord_red, wr == 0 ? 0 : wr <= 4 ? 1 : wr <= 8 ? 2 : 3, e);
+        if (!red_part) { if (live) x->cost = cost; order_push(ord_blue, wgt == 0 ? 0 : wgt <= 3 ? 1 : wgt <= 7 ? 2 : 3, e); }
+        else order_push(ord_red, wgt == 0 ? 0 : wgt <= 4 ? 1 : wgt <= 8 ? 2 : 3, e);
     }
     __syncwarp();
     /* The due actions are known: pull the cold-record lines they will touch towards L2 now, so that the dependent reads of
-       the (serial) action code of the next phases find them there instead of in DRAM. */
+       the (serial) action code of the next phases find them there instead of in DRAM (worth 3 % of the blue phase). */
     if (live) {
         const Cc4Cold *k = WC(c)->k;
-        if (sl < 9) {              /* the service table: green LocalWork reads one entry per agent every tick */
-            const char *b = reinterpret_cast<const char *>(k->svc64);
-            prefetch_l2(b + min(128 * sl, (int)sizeof(k->svc64) - 1));
-            if (sl * 32 < s->n_sus) prefetch_l2(k->sus + sl * 32);
-        }
-        if (sl < 11) {             /* one lane per blue / red actor: directory entry, home slab and largest pid of the target host */
-            const uint32_t w = x->subw[sl], code = IP_CODE(w), h = IP_HOST(w);
+        if (sl < (red_part ? CC4_NRED : CC4_NBLUE)) {   /* directory entry, home slab and largest pid of the actor's target host */
+            const uint32_t w = x->subw[red_part ? A_RED0 + sl : sl], code = IP_CODE(w), h = IP_HOST(w);
             const bool hosty = (code == AC_REMOVE || code == AC_RESTORE || code == AC_DECOY || (code >= AC_AGGR && code <= AC_DEGRADE)) && h < 128;
             if (hosty) {
                 prefetch_l2(&k->pdir[h]); prefetch_l2(&k->parena[h * CC4_OSLAB]); prefetch_l2(&k->pmax[h]);
                 if (code == AC_RESTORE) { const Cc4Stat *st = WC(c)->st; prefetch_l2(&st->o_procs[h][0]); prefetch_l2(&st->o_svc64[h]); prefetch_l2(&st->o_nproc[h]); }
             }
         }
-        if (sl < 12 && sl * 32 < s->n_ports) prefetch_l2(k->ports + sl * 32);      /* known ports: 12 lines = 384 entries */
+        if (!red_part) {        /* the service table (green LocalWork reads one entry per agent every tick) and the suspicious pids */
+            const char *b = reinterpret_cast<const char *>(k->svc64);
+            prefetch_l2(b + 128 * sl);
+            if (sl == 0) prefetch_l2(b + sizeof(k->svc64) - 1);
+            if (sl * 32 < s->n_sus) prefetch_l2(k->sus + sl * 32);
+        } else {                /* known ports: 12 lines = 384 entries */
+            if (sl * 32 < s->n_ports) prefetch_l2(k->ports + sl * 32);
+            if ((sl + 8) * 32 < s->n_ports && sl < 4) prefetch_l2(k->ports + (sl + 8) * 32);
+        }
     }
 }
 
@@ -649,27 +650,28 @@ template <class F> __device__ __forceinline__ void each_episode(int ph, int firs
 
 /* the same for the lane-per-actor phases: a warp item = `per` consecutive episodes, 32 / per lanes each;
  * f(c, e, exists, sl) runs on all lanes, with the lane's own episode */
-template <int per, class F> __device__ __forceinline__ void each_group(int ph, int first, int n_local, int *next, F f)
+template <int per, int parts = 1, class F> __device__ __forceinline__ void each_group(int ph, int first, int n_local, int *next, F f)
 {
 #ifdef CC4_PHASE_CLOCKS
     const long long tb0 = clock64();
 #endif
-    const int n_items = (n_local + per - 1) / per, sub = lane_id() / (32 / per), sl = lane_id() % (32 / per);
+    const int n_per = (n_local + per - 1) / per, n_items = parts * n_per, sub = lane_id() / (32 / per), sl = lane_id() % (32 / per);
     _Pragma("unroll 1") for (;;) {
         int it = 0;
         if (lane_id() == 0) it = atomicAdd(&next[ph], 1);
         it = __shfl_sync(0xFFFFFFFFu, it, 0);
         if (it >= n_items) break;
-        const int e = it * per + sub;
+        const int part = parts > 1 ? it / n_per : 0;       /* `parts` kinds of item over the same episodes (f gets part through sl: sl + 32 * part) */
+        const int e = (it - part * n_per) * per + sub;
         const bool exists = e < n_local;
         const Cx c = (Cx)((exists ? e : 0) * (int)sizeof(WarpSmem));
 #ifdef CC4_PHASE_CLOCKS
         const long long t0 = clock64();
-        f(c, e, exists, sl);
+        f(c, e, exists, sl + 32 * part);
         __syncwarp();
         if (exists && sl == 0 && g_phase_clk) g_phase_clk[(size_t)(first + e) * PC_STRIDE + 2 * ph] += (unsigned long long)(clock64() - t0) / per;
 #else
-        f(c, e, exists, sl);
+        f(c, e, exists, sl + 32 * part);
         __syncwarp();
 #endif
     }
@@ -744,8 +746,8 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
         __syncwarp();
         if (lane_id() == 0) bulk_store(p.dyn + env, DYN(c), (uint32_t)sizeof(Cc4Dyn));
     };
-    each_group<2>(PH_POLICY, first, n_local, next, [&](Cx c, int e, bool exists, int sl) {
-        ph_policy(c, e, exists, exists, sl, io.actions + (size_t)(first + (exists ? e : 0)) * 5, 0, 0, 0, &ord_blue, &ord_red);
+    each_group<4, 2>(PH_POLICY, first, n_local, next, [&](Cx c, int e, bool exists, int sl) {
+        ph_policy(c, e, exists, exists, sl & 31, sl >= 32, io.actions + (size_t)(first + (exists ? e : 0)) * 5, 0, 0, 0, &ord_blue, &ord_red);
     });
 #if CC4_SPLIT & 1
     each_episode(N_PHASES + 1, first, n_local, next, [&](Cx c, int) { ph_blue(c, false); });
@@ -801,8 +803,8 @@ k_rollout(Params p, int epb, int n_ticks, uint32_t pk0, uint32_t pk1, float *rew
             if (!DYN(c)->done) { if (lane_id() == 0) atomicAdd(&alive, 1); ph_setup(c); }
         });
         if (alive == 0) break;
-        each_group<2>(PH_POLICY, first, n_local, next, [&](Cx c, int e, bool exists, int sl) {
-            ph_policy(c, e, exists, exists && !DYN(c)->done, sl, nullptr, pk0, pk1, p.first_episode + (uint64_t)(first + e), &ord_blue, &ord_red);
+        each_group<4, 2>(PH_POLICY, first, n_local, next, [&](Cx c, int e, bool exists, int sl) {
+            ph_policy(c, e, exists, exists && !DYN(c)->done, sl & 31, sl >= 32, nullptr, pk0, pk1, p.first_episode + (uint64_t)(first + e), &ord_blue, &ord_red);
         });
         each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_blue(c); }, &ord_blue);
         green_items(PH_GREEN, first, n_local, next, ng_s, gend);
