@@ -297,7 +297,8 @@ __device__ __forceinline__ int order_get(const PhaseOrder *o, int i)
     return o->list[0][i];
 }
 #ifdef CC4_PHASE_CLOCKS   /* profiling build (tools/phase_clocks.py): per episode [18]: [2p] = busy cycles of phase p; [2p+1] of a block's
-                             first episode = wall cycles of phase p for the block, barrier included */
+                             first episode = wall cycles of phase p for the block, barrier included; [17] = the episode's slowest red
+                             phase, [16] of a block's first episode = the block's slowest red phase */
 __device__ unsigned long long *g_phase_clk;
 #define PC_STRIDE 18
 #endif
@@ -637,7 +638,11 @@ template <class F> __device__ __forceinline__ void each_episode(int ph, int firs
 #ifdef CC4_PHASE_CLOCKS
         const long long t0 = clock64();
         f(c, e);
-        if (lane_id() == 0 && g_phase_clk && ph < N_PHASES) g_phase_clk[(size_t)(first + e) * PC_STRIDE + 2 * ph] += (unsigned long long)(clock64() - t0);
+        if (lane_id() == 0 && g_phase_clk && ph < N_PHASES) {
+            const unsigned long long dt = (unsigned long long)(clock64() - t0);
+            g_phase_clk[(size_t)(first + e) * PC_STRIDE + 2 * ph] += dt;
+            if (ph == PH_RED) { atomicMax(&g_phase_clk[(size_t)(first + e) * PC_STRIDE + 17], dt); atomicMax(&g_phase_clk[(size_t)first * PC_STRIDE + 16], dt); }     /* slowest red phase of the episode / of the block's first-episode slot */
+        }
 #else
         f(c, e);
 #endif

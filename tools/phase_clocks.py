@@ -57,4 +57,6 @@ for i in range(8):
     w = wall[blocks, i].mean()
     print(f"{names[i]:>18} {b.mean():9.0f} {np.percentile(b, 90):8.0f} {np.percentile(b, 99):8.0f} {b.max():8.0f} {w:9.0f} "
           f"{100 * w / wall[blocks].sum(1).mean():6.1f} {b.mean() * epb / (wpb * w):9.2f}")
+mx = buf[:, 17].astype(np.float64)
+print(f"red phase: slowest single episode-tick per episode over the {ticks} ticks: mean {mx.mean():.0f}, p50 {np.percentile(mx, 50):.0f}, p99 {np.percentile(mx, 99):.0f}, max {mx.max():.0f} cycles; slowest in a block (over all its episodes and ticks): mean {buf[blocks, 16].astype(np.float64).mean():.0f}")
 print(json.dumps({"busy_mean": busy.mean(0).tolist(), "block_wall_mean": wall[blocks].mean(0).tolist()}))
