@@ -81,6 +81,26 @@ class MLPPolicy(torch.nn.Module):
         return torch.stack(acts, 1).to(torch.int32).contiguous()
 
 
+class RandomBluePolicy:
+    """The reference's cc4BlueRandomAgent (CybORG/Agents/SimpleAgents/RandomAgent.py:66-69) as a device-side batched
+    policy: every blue agent draws uniformly among its VALID actions (mask True), BlockTrafficZone / AllowTrafficZone
+    excluded as in the reference (`excluded_actions`).  `policy(obs, mask) -> int32 [N, 5]`."""
+
+    def __init__(self, seed: int = 0, exclude_traffic_control: bool = True):
+        self.seed, self.exclude, self._g = seed, exclude_traffic_control, None
+
+    @torch.no_grad()
+    def __call__(self, obs: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+        if self._g is None:
+            self._g = torch.Generator(device=mask.device).manual_seed(self.seed)
+        m = mask.clone()
+        if self.exclude:     # index layout of BlueFixedActionWrapper._populate_action_space :233-309: Allow + Block follow Sleep
+            m[:, :4, 50:66] = False
+            m[:, 4, 146:194] = False
+        key = torch.rand(m.shape, generator=self._g, device=m.device).masked_fill(~m, -1.0)
+        return key.argmax(-1).to(torch.int32).contiguous()
+
+
 def shard(n_total: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous episode range [lo, hi) owned by `rank` (episodes are keyed by global id, so totals do not depend on world)."""
     base, rem = divmod(n_total, world)

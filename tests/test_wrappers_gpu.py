@@ -170,3 +170,23 @@ def test_evaluation_protocol_runs_unchanged_loop():
     b1 = run_evaluation_batched(pol, max_eps=16, seed=5)
     lo = run_evaluation_batched(pol, max_eps=16, seed=5, rank=0, world=1)
     assert b1["rewards"] == lo["rewards"] and b1["episodes"] == 16 and b1["stdev"] > 0
+
+
+def test_random_blue_policy_picks_valid_non_traffic_actions():
+    """cc4BlueRandomAgent equivalent (RandomAgent.py:66-69) on device: valid actions only, no Block / Allow."""
+    import torch
+    from cage_challenge_4_b200.engine import BatchedCC4
+    from cage_challenge_4_b200.evaluation import RandomBluePolicy, run_evaluation_batched
+    env = BatchedCC4(256, device=0, seed=5)
+    obs, mask = env.reset()
+    pol = RandomBluePolicy(seed=1)
+    seen = set()
+    for _ in range(20):
+        a = pol(obs, mask)
+        assert bool(torch.gather(mask, 2, a.long().unsqueeze(-1)).all())
+        assert not bool(((a[:, :4] >= 50) & (a[:, :4] < 66)).any()) and not bool(((a[:, 4] >= 146) & (a[:, 4] < 194)).any())
+        seen |= set(a[:, 0].tolist())
+        obs, rew, done = env.step(a)
+    assert len(seen) > 20
+    out = run_evaluation_batched(RandomBluePolicy(seed=2), max_eps=32, seed=3, steps=60)
+    assert out["episodes"] == 32 and out["mean"] < 0
