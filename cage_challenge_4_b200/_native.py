@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CC4_B200_LIB") or os.path.join(HERE, "libcc4_b200.so")
 
 EXPORTS = [
-    "cc4_create", "cc4_destroy", "cc4_set_episode_base", "cc4_state_bytes", "cc4_set_tape", "cc4_reset", "cc4_reset_host", "cc4_step", "cc4_step_host",
+    "cc4_create", "cc4_destroy", "cc4_set_episode_base", "cc4_set_red_agent", "cc4_state_bytes", "cc4_set_tape", "cc4_reset", "cc4_reset_host", "cc4_step", "cc4_step_host",
     "cc4_rollout", "cc4_error_flags", "cc4_export_canon", "cc4_launch_count", "cc4_phase_clocks", "cc4_last_error",
 ]
 
@@ -33,6 +33,7 @@ def load():
     L.cc4_create.argtypes = [i32, i32, u64, u64, i32, i32, C.POINTER(vp)]
     L.cc4_destroy.argtypes = [vp]
     L.cc4_set_episode_base.argtypes = [vp, u64, u64]
+    L.cc4_set_red_agent.argtypes = [vp, i32]
     L.cc4_state_bytes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.cc4_set_tape.argtypes = [vp, vp, vp, C.c_uint32]
     L.cc4_reset.argtypes = [vp, vp, vp, vp]

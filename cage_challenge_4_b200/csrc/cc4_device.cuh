@@ -63,8 +63,11 @@ enum {
     ST_R_NUSER = 1, ST_R_NSERVER, ST_R_NADDON, ST_R_ADDON, ST_R_PID, ST_R_BLUE_PARENT, ST_R_RED_SUBNET, ST_R_RED_HOST,
     ST_CREATE_PID, ST_GREEN_ACT, ST_LW_SERVICE, ST_LW_RELIAB, ST_LW_FP, ST_LW_PHISH, ST_PHISH_AGENT, ST_AS_DEST, ST_AS_FP,
     ST_FSM_HOST, ST_FSM_ACTION, ST_FSM_PARAM, ST_PORTSCAN, ST_EXP_OTHER, ST_EXP_TOP, ST_EXP_SUCC, ST_EXP_DETECT, ST_SSH_HOP,
-    ST_PRIV_SESS, ST_DD_TP, ST_DD_FP, ST_RSC_PRIMARY, ST_DECOY_FACTORY
+    ST_PRIV_SESS, ST_DD_TP, ST_DD_FP, ST_RSC_PRIMARY, ST_DECOY_FACTORY,
+    /* DiscoveryFSRed only (FiniteStateRedAgent._choose_host :252-293) */
+    ST_FSMD_STATE_P, ST_FSMD_STATE_U, ST_FSMD_ROLL, ST_FSMD_HOST_SRV, ST_FSMD_HOST_OTHER, ST_FSMD_HOST_SRV2, ST_FSMD_HOST_ALL
 };
+static_assert(ST_DECOY_FACTORY == 31 && ST_FSMD_HOST_ALL == 38, "draw sites must match oracle/cc4_oracle.h");
 
 /* action codes (oracle/canon.py ACTION_CODE) */
 enum { AC_SLEEP = 0, AC_MONITOR, AC_ANALYSE, AC_REMOVE, AC_RESTORE, AC_DECOY, AC_BLOCK, AC_ALLOW, AC_INVALID,
@@ -89,11 +92,18 @@ __constant__ int8_t c_fsm_fail[9][9] = {   /* :481-491 */
     { F_R, -1, -1, -1, -1, -1, F_R, F_R, F_R },   { F_RD, -1, -1, -1, -1, -1, F_RD, F_RD, F_RD },
     { F_F, -1, -1, -1, -1, -1, -1, -1, -1 } };
 /* :540-549 probabilities in quarters (-1 = None); all are multiples of 0.25, so cdf / total is exact in double */
-__constant__ int8_t c_fsm_prob4[8][9] = {
+__constant__ int8_t c_fsm_prob4[2][8][9] = { {
     { 2, 1, 1, -1, -1, -1, -1, -1, -1 },  { -1, 2, 2, -1, -1, -1, -1, -1, -1 },
     { 1, -1, -1, 1, 2, -1, -1, -1, -1 },  { -1, -1, -1, 1, 3, -1, -1, -1, -1 },
     { 2, -1, -1, -1, -1, 2, -1, -1, 0 },  { -1, -1, -1, -1, -1, 4, -1, -1, 0 },
-    { 2, -1, -1, -1, -1, -1, 1, 1, 0 },   { -1, -1, -1, -1, -1, -1, 2, 2, 0 } };
+    { 2, -1, -1, -1, -1, -1, 1, 1, 0 },   { -1, -1, -1, -1, -1, -1, 2, 2, 0 } },
+  { /* DiscoveryFSRed.state_transitions_probability FSMRedVariants.py:110-120 */
+    { 1, 3, 0, -1, -1, -1, -1, -1, -1 },  { -1, 4, 0, -1, -1, -1, -1, -1, -1 },
+    { 1, -1, -1, 0, 3, -1, -1, -1, -1 },  { -1, -1, -1, 0, 4, -1, -1, -1, -1 },
+    { 0, -1, -1, -1, -1, 4, -1, -1, 0 },  { -1, -1, -1, -1, -1, 4, -1, -1, 0 },
+    { 4, -1, -1, -1, -1, -1, 0, 0, 0 },   { -1, -1, -1, -1, -1, -1, 2, 2, 0 } } };
+/* DiscoveryFSRed.set_host_state_priority_list FSMRedVariants.py:86-99 (K KD S SD U UD R RD) */
+__constant__ uint8_t c_fsmd_priority[8] = { 20, 20, 20, 20, 10, 10, 0, 0 };
 __constant__ int8_t c_red_aspace_cols[9] = { 0, 1, 2, 4, 5, 7, 3, 6, 8 };  /* EnterpriseScenarioGenerator.py:764-768 */
 __constant__ int8_t c_reward[3][9][3] = {  /* BlueRewardMachine.py:35-65 [phase][subnet][LWF, ASF, RIA] */
     { { -1, -3, -1 }, { -1, -1, -1 }, { -1, -3, -1 }, { -1, -1, -1 }, { 0, -5, -5 }, { -1, -1, -3 }, { -1, -1, -3 }, { -1, -1, -3 }, { 0, 0, -1 } },
@@ -174,6 +184,7 @@ struct BlockCtx {
     const cc4_draw *tape; uint32_t n_segs;
     int steps, rng_mode;
     uint32_t k0;
+    int red_variant;          /* 0 FiniteStateRedAgent, 1 DiscoveryFSRed */
 };
 __shared__ BlockCtx g_blk;
 /* per-actor draw counters: 16 bits for the blue / red / reset streams, 8 bits for the green ones */
@@ -637,40 +648,22 @@ __device__ CC4_INL8 void agent_end_turn(Cx c, int r)
     }
 }
 
-/* FiniteStateRedAgent._choose_host_and_action :296-336 + replace_action_if_invalid SimulationController.py:1068-1112.
- * Returns the packed action (ticks = 0). */
-__device__ CC4_INL8 uint32_t red_policy(Cx c, int r)
+/* action class + parameters for the chosen host (FiniteStateRedAgent._choose_host_and_action :296-336 +
+ * replace_action_if_invalid SimulationController.py:1068-1112); ri / rf draw an integer / a double */
+template <class RI, class RF> __device__ __forceinline__ uint32_t fsm_choose_action(Cx c, int r, int slot, RI ri, RF rf)
 {
     Cc4Dyn *s = DYN(c);
-    int actor = A_RED0 + r;
-    if (IP_CODE(s->inprog[actor]) != IP_NONE) return ACT_SLEEP_WORD;     /* last observation was IN_PROGRESS :100-102 */
     const Cc4Fsm *f = &s->fsm[r];
-    const int nf = s->n_fsm[r];
-    /* uniform over the hosts that are not in state F, in list order: positions from the position mask */
-    const uint32_t lo = ~f->posF[0] & (nf >= 32 ? 0xFFFFFFFFu : (1u << nf) - 1u), hi = nf > 32 ? ~f->posF[1] & (nf >= 64 ? 0xFFFFFFFFu : (1u << (nf - 32)) - 1u) : 0u;
-    const int nlo = __popc(lo), nk = nlo + __popc(hi);
-    if (nk == 0) { fail(c, CC4_E_UNREACHABLE); return ACT_SLEEP_WORD; }
-    /* production mode: host pick, action pick and at most two parameter picks fit the four words of the stream's first
-       Philox block, which stays in registers; the block is left in the stream cache for the action code that follows */
-    const bool tape = g_blk.rng_mode == 1;
-    const uint4 blk = tape ? make_uint4(0, 0, 0, 0) : philox_block(c, actor, 0);
-    uint32_t j = 0;
-    auto ri = [&](int site, uint32_t n) -> uint32_t {
-        if (tape) return rng_int(c, actor, site, n);
-        if (n == 1 && site == ST_FSM_PARAM) return 0u;
-        return __umulhi(u4_word(blk, j++), n);
-    };
-    const int pick = (int)ri(ST_FSM_HOST, (uint32_t)nk);
-    const int pos = pick < nlo ? (int)__fns(lo, 0, pick + 1) : 32 + (int)__fns(hi, 0, pick - nlo + 1);
-    const int slot = s->fsm_order[r][pos], st = fsm_state(f, slot), f_hn = bit128(f->hn, slot);
+    const int st = fsm_state(f, slot), f_hn = bit128(f->hn, slot);
     /* options in action-space order (c_red_aspace_cols); numpy Generator.choice(p): idx = searchsorted(cumsum(p) / sum, u, side='right') */
     int nc = 0, tot = 0;
-    _Pragma("unroll 1") for (int i = 0; i < 9; i++) { int p = c_fsm_prob4[st][c_red_aspace_cols[i]]; if (p >= 0) { tot += p; nc++; } }
+    const int8_t (*prob4)[9] = c_fsm_prob4[g_blk.red_variant];
+    _Pragma("unroll 1") for (int i = 0; i < 9; i++) { int p = prob4[st][c_red_aspace_cols[i]]; if (p >= 0) { tot += p; nc++; } }
     if (tot != 4) fail(c, CC4_E_UNREACHABLE);
-    const double u = tape ? rng_f64(c, actor, ST_FSM_ACTION, (uint32_t)nc) : f64_from_word(u4_word(blk, j++));
+    const double u = rf(ST_FSM_ACTION, (uint32_t)nc);
     int col = -1, cum = 0, last = -1;
     _Pragma("unroll 1") for (int i = 0; i < 9 && col < 0; i++) {
-        int cc = c_red_aspace_cols[i], p = c_fsm_prob4[st][cc];
+        int cc = c_red_aspace_cols[i], p = prob4[st][cc];
         if (p < 0) continue;
         last = cc; cum += p;
         if (!((double)cum * 0.25 <= u)) col = cc;      /* cdf / cdf[-1]: every row of the table sums to 4 quarters, so this is exact */
@@ -686,14 +679,109 @@ __device__ CC4_INL8 uint32_t red_policy(Cx c, int r)
     } else if (col <= 3) { PICK_SESSION(); (void)ri(ST_FSM_PARAM, 1); a.host = slot; }
     else { if (col >= 5 && !f_hn) fail(c, CC4_E_UNREACHABLE); a.host = slot; PICK_SESSION(); (void)ri(ST_FSM_PARAM, 1); }
     #undef PICK_SESSION
+    if (col >= 1 && col <= 4 && !bit128(s->ip_known[r], a.host)) a.code = AC_INVALID;
+    if (col >= 5 && !bit128(s->hn_known[r], a.host)) a.code = AC_INVALID;
+    return pack_act(a, 0);
+}
+
+/* DiscoveryFSRed (FSMRedVariants.py:72-122), out of line: draws through the generic stream functions (the same words in
+ * the same order as the register-resident path of red_policy would take) */
+__device__ __noinline__ uint32_t red_policy_discovery(Cx c, int r, uint32_t lo, uint32_t hi)
+{
+    Cc4Dyn *s = DYN(c);
+    const int actor = A_RED0 + r;
+    const Cc4Fsm *f = &s->fsm[r];
+    const int nf = s->n_fsm[r];
+    auto ri = [&](int site, uint32_t n) -> uint32_t { return rng_int(c, actor, site, n); };
+    auto rf = [&](int site, uint32_t n) -> double { return rng_f64(c, actor, site, n); };
+    int slot;
+    {
+        /* DiscoveryFSRed: FiniteStateRedAgent._choose_host :252-293 with a host-state priority list and the server bias.
+           One walk over the list: states in order of first appearance, and per state the position masks of its hosts /
+           of its servers ('server' in hostname: the entry carries a hostname and sits in a server slot). */
+        uint32_t st_list = 0, seen = 0; int ns = 0;             /* 4 bits per listed state */
+        uint64_t pos_state[8], pos_srv[8];
+        _Pragma("unroll 1") for (int k = 0; k < 8; k++) { pos_state[k] = 0; pos_srv[k] = 0; }
+        _Pragma("unroll 1") for (int i = 0; i < nf; i++) {
+            if ((i < 32 ? lo >> i : hi >> (i - 32)) & 1u) {
+                const int sl_ = s->fsm_order[r][i], st = fsm_state(f, sl_);
+                if (!(seen >> st & 1u)) { seen |= 1u << st; st_list |= (uint32_t)st << (4 * ns); ns++; }
+                pos_state[st] |= 1ull << i;          /* (local memory: this variant only) */
+                if (bit128(f->hn, sl_) && (sl_ & 15) < 6) pos_srv[st] |= 1ull << i;
+            }
+        }
+        int total = 0;
+        _Pragma("unroll 1") for (int i = 0; i < ns; i++) total += c_fsmd_priority[st_list >> (4 * i) & 15u];
+        int pick;
+        if (total > 0) {
+            /* probs = [(p / base) * p_multiplier]; numpy choice(p=): cdf = cumsum(probs); cdf /= cdf[-1]; searchsorted(cdf, u,
+               'right'): the same double operations in the same order, no fused multiply-add */
+            const double mult = __ddiv_rn(1.0, __ddiv_rn((double)total, 100.0));
+            double last = 0.0;
+            _Pragma("unroll 1") for (int i = 0; i < ns; i++) last = __dadd_rn(last, __dmul_rn(__ddiv_rn((double)c_fsmd_priority[st_list >> (4 * i) & 15u], 100.0), mult));
+            const double u = rf(ST_FSMD_STATE_P, (uint32_t)ns);
+            double acc = 0.0;
+            _Pragma("unroll 1") for (pick = 0; pick < ns; pick++) {
+                acc = __dadd_rn(acc, __dmul_rn(__ddiv_rn((double)c_fsmd_priority[st_list >> (4 * pick) & 15u], 100.0), mult));
+                if (!(__ddiv_rn(acc, last) <= u)) break;
+            }
+            if (pick >= ns) pick = ns - 1;
+        } else pick = (int)ri(ST_FSMD_STATE_U, (uint32_t)ns);
+        const int cst = (int)(st_list >> (4 * pick) & 15u);
+        const uint64_t all = pos_state[cst], srv = pos_srv[cst];
+        const int no = __popcll(all), nsrv = __popcll(srv);
+        uint64_t from; int site, n;
+        if (no > 1) {
+            if (nsrv > 0) {
+                const double roll = rf(ST_FSMD_ROLL, 0);
+                if (roll <= 0.75) { from = srv; site = ST_FSMD_HOST_SRV; n = nsrv; }
+                else if (nsrv != no) { from = all & ~srv; site = ST_FSMD_HOST_OTHER; n = no - nsrv; }
+                else { from = srv; site = ST_FSMD_HOST_SRV2; n = nsrv; }
+            } else { from = all; site = ST_FSMD_HOST_ALL; n = no; }
+        } else { from = all; site = ST_FSM_HOST; n = no; }
+        const int kth = (int)ri(site, (uint32_t)n);
+        const uint32_t flo = (uint32_t)from, fhi = (uint32_t)(from >> 32);
+        const int cl = __popc(flo);
+        const int pos = kth < cl ? (int)__fns(flo, 0, kth + 1) : 32 + (int)__fns(fhi, 0, kth - cl + 1);
+        slot = s->fsm_order[r][pos];
+    }
+    return fsm_choose_action(c, r, slot, ri, rf);
+}
+
+/* FiniteStateRedAgent.get_action :58-123 for one red agent [lane].  Returns the packed action (ticks = 0). */
+__device__ CC4_INL8 uint32_t red_policy(Cx c, int r)
+{
+    Cc4Dyn *s = DYN(c);
+    int actor = A_RED0 + r;
+    if (IP_CODE(s->inprog[actor]) != IP_NONE) return ACT_SLEEP_WORD;     /* last observation was IN_PROGRESS :100-102 */
+    const Cc4Fsm *f = &s->fsm[r];
+    const int nf = s->n_fsm[r];
+    /* hosts that are not in state F, by list position */
+    const uint32_t lo = ~f->posF[0] & (nf >= 32 ? 0xFFFFFFFFu : (1u << nf) - 1u), hi = nf > 32 ? ~f->posF[1] & (nf >= 64 ? 0xFFFFFFFFu : (1u << (nf - 32)) - 1u) : 0u;
+    const int nlo = __popc(lo), nk = nlo + __popc(hi);
+    if (nk == 0) { fail(c, CC4_E_UNREACHABLE); return ACT_SLEEP_WORD; }
+    if (g_blk.red_variant != 0) return red_policy_discovery(c, r, lo, hi);
+    /* production mode: host pick, action pick and at most two parameter picks fit the four words of the stream's first
+       Philox block, which stays in registers; the block is left in the stream cache for the action code that follows */
+    const bool tape = g_blk.rng_mode == 1;
+    const uint4 blk = tape ? make_uint4(0, 0, 0, 0) : philox_block(c, actor, 0);
+    uint32_t j = 0;
+    auto ri = [&](int site, uint32_t n) -> uint32_t {
+        if (tape) return rng_int(c, actor, site, n);
+        if (n == 1 && site == ST_FSM_PARAM) return 0u;
+        return __umulhi(u4_word(blk, j++), n);
+    };
+    auto rf = [&](int site, uint32_t n) -> double { return tape ? rng_f64(c, actor, site, n) : f64_from_word(u4_word(blk, j++)); };
+    /* FiniteStateRedAgent: uniform over the known hosts in list order */
+    const int pick = (int)ri(ST_FSM_HOST, (uint32_t)nk);
+    const int pos = pick < nlo ? (int)__fns(lo, 0, pick + 1) : 32 + (int)__fns(hi, 0, pick - nlo + 1);
+    const uint32_t act = fsm_choose_action(c, r, s->fsm_order[r][pos], ri, rf);
     if (!tape) {
         Scratch *x = SCR(c);
         ctr_set(x, actor, j);
         x->blk_id[r] = 0; x->blk[r][0] = blk.x; x->blk[r][1] = blk.y; x->blk[r][2] = blk.z; x->blk[r][3] = blk.w;
     }
-    if (col >= 1 && col <= 4 && !bit128(s->ip_known[r], a.host)) a.code = AC_INVALID;
-    if (col >= 5 && !bit128(s->hn_known[r], a.host)) a.code = AC_INVALID;
-    return pack_act(a, 0);
+    return act;
 }
 
 /* ------------------------------------------------------------------------------------------------ */

@@ -38,7 +38,7 @@ constexpr int DYN_U4 = (int)(sizeof(Cc4Dyn) / 16);
 
 struct Params {
     Cc4Dyn *dyn; Cc4Stat *stat; Cc4Cold *cold;
-    int n_envs, steps, rng_mode;
+    int n_envs, steps, rng_mode, red_variant;
     uint32_t k0, k1hi; uint64_t first_episode;
     const cc4_draw *tape; const uint32_t *seg_off; uint32_t n_segs;
     unsigned long long *phase_clk;   /* [n_envs][8][2] cycles per phase (only in -DCC4_PHASE_CLOCKS builds) */
@@ -691,7 +691,7 @@ __device__ __forceinline__ void init_block_ctx(const Params &p)
 {
     if (threadIdx.x == 0) {
         g_blk.tape = p.tape; g_blk.n_segs = p.seg_off ? p.n_segs : 0;
-        g_blk.steps = p.steps; g_blk.rng_mode = p.rng_mode; g_blk.k0 = p.k0;
+        g_blk.steps = p.steps; g_blk.rng_mode = p.rng_mode; g_blk.k0 = p.k0; g_blk.red_variant = p.red_variant;
     }
 }
 __device__ __forceinline__ void init_ctx(Cx c, const Params &p, int env, int tick)
@@ -1034,6 +1034,13 @@ extern "C" int cc4_set_episode_base(cc4_handle *h, uint64_t seed, uint64_t first
 {
     if (!h) return set_err(CC4_ERR_ARG, "cc4_set_episode_base: null handle%s", "");
     h->p.k0 = (uint32_t)seed; h->p.k1hi = (uint32_t)(seed >> 32); h->p.first_episode = first_episode;
+    return CC4_OK;
+}
+
+extern "C" int cc4_set_red_agent(cc4_handle *h, int variant)
+{
+    if (!h || (variant != CC4_RED_FINITE_STATE && variant != CC4_RED_DISCOVERY)) return set_err(CC4_ERR_ARG, "cc4_set_red_agent: bad argument%s", "");
+    h->p.red_variant = variant;
     return CC4_OK;
 }
 

@@ -34,8 +34,10 @@ DRAW_DTYPE = np.dtype([("val", "<u8"), ("n", "<u2"), ("site", "u1"), ("kind", "u
 class BatchedCC4:
     """N independent CC4 episodes on one GPU.  Episode i draws from the RNG stream (seed, first_episode + i)."""
 
+    RED_AGENTS = {"finite_state": 0, "fsm": 0, "FiniteStateRedAgent": 0, "discovery": 1, "DiscoveryFSRed": 1}
+
     def __init__(self, num_envs: int, device: int | str | torch.device = 0, seed: int = 0, steps: int = 500,
-                 first_episode: int = 0, rng: str = "philox"):
+                 first_episode: int = 0, rng: str = "philox", red_agent: str = "finite_state"):
         if not torch.cuda.is_available():
             raise _native.NativeError("BatchedCC4 needs a CUDA device (there is no CPU fallback)")
         self._L = _native.load()
@@ -46,6 +48,8 @@ class BatchedCC4:
         _native.check(self._L.cc4_create(self.num_envs, self.device.index or 0, self.seed & (2**64 - 1), self.first_episode,
                                          self.steps, 1 if rng == "tape" else 0, C.byref(h)), "cc4_create")
         self._h = h
+        self.red_agent = red_agent
+        _native.check(self._L.cc4_set_red_agent(self._h, self.RED_AGENTS[red_agent]), "cc4_set_red_agent")
         n = self.num_envs
         self.obs = torch.zeros((n, N_BLUE, OBS_LEN), dtype=torch.uint8, device=self.device)
         self.mask = torch.zeros((n, N_BLUE, MASK_LEN), dtype=torch.uint8, device=self.device)

@@ -60,14 +60,20 @@ class FiniteStateRedAgent(BaseAgent):
     """Scripted in-kernel (FiniteStateRedAgent.py:58-336)."""
 
 
+class DiscoveryFSRed(FiniteStateRedAgent):
+    """Scripted in-kernel (FSMRedVariants.py:72-122: host-state priorities, server bias, discovery-weighted actions)."""
+
+
 class EnterpriseScenarioGenerator:
     """Same constructor as Simulator/Scenarios/EnterpriseScenarioGenerator.py:95-101."""
     MIN_USER_HOSTS, MAX_USER_HOSTS, MIN_SERVER_HOSTS, MAX_SERVER_HOSTS = 3, 10, 1, 6
     MAX_BANDWIDTH, MESSAGE_LENGTH = 100, 8
 
     def __init__(self, blue_agent_class=None, red_agent_class=None, green_agent_class=None, steps: int = 100):
-        if red_agent_class not in (None, FiniteStateRedAgent) and getattr(red_agent_class, "__name__", "") != "FiniteStateRedAgent":
-            raise NotImplementedError("the engine scripts FiniteStateRedAgent only (SURVEY.md section 8f lists the other red agents as next)")
+        red_name = "FiniteStateRedAgent" if red_agent_class is None else getattr(red_agent_class, "__name__", "")
+        if red_name not in ("FiniteStateRedAgent", "DiscoveryFSRed"):
+            raise NotImplementedError("the engine scripts FiniteStateRedAgent and DiscoveryFSRed (SURVEY.md section 8f lists the other red agents as next)")
+        self.red_agent = red_name
         if green_agent_class not in (None, EnterpriseGreenAgent) and getattr(green_agent_class, "__name__", "") != "EnterpriseGreenAgent":
             raise NotImplementedError("the engine scripts EnterpriseGreenAgent only")
         self.blue_agent_class, self.red_agent_class, self.green_agent_class, self.steps = blue_agent_class, red_agent_class, green_agent_class, steps
@@ -82,7 +88,7 @@ class CybORG:
         assert isinstance(scenario_generator, EnterpriseScenarioGenerator), "scenario_generator must be an EnterpriseScenarioGenerator"
         self.scenario_generator = scenario_generator
         self.seed = int(np.random.SeedSequence().entropy % (2**63)) if seed is None else int(seed)
-        self.engine = BatchedCC4(num_envs, device=device, seed=self.seed, steps=scenario_generator.steps)
+        self.engine = BatchedCC4(num_envs, device=device, seed=self.seed, steps=scenario_generator.steps, red_agent=scenario_generator.red_agent)
         self._episodes_started = 0
         self._last_actions = None
         self.agents = [f"blue_agent_{i}" for i in range(5)]

@@ -69,6 +69,13 @@ int cc4_destroy(cc4_handle *h);
  * produce fresh scenarios, as consecutive CybORG.reset() calls do by continuing one RNG (env.py:218-236). */
 int cc4_set_episode_base(cc4_handle *h, uint64_t seed, uint64_t first_episode);
 
+/* Scripted red agent class of every episode (EnterpriseScenarioGenerator(red_agent_class=...)): FiniteStateRedAgent
+ * (CybORG/Agents/SimpleAgents/FiniteStateRedAgent.py, the challenge default) or its DiscoveryFSRed variant
+ * (FSMRedVariants.py:72-122: host-state priority list, server bias, discovery-weighted action matrix).  Call before
+ * cc4_reset; it takes effect from the next tick on. */
+enum { CC4_RED_FINITE_STATE = 0, CC4_RED_DISCOVERY = 1 };
+int cc4_set_red_agent(cc4_handle *h, int variant);
+
 /* Packed per-episode state sizes in bytes: hot = the record streamed through shared memory every tick (read + written),
  * cold = dynamic state touched in place by rare transitions only, stat = written at reset (read on Restore / export). */
 int cc4_state_bytes(cc4_handle *h, size_t *hot_bytes, size_t *cold_bytes, size_t *stat_bytes);

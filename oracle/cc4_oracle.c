@@ -70,11 +70,18 @@ static const int8_t FSM_FAIL[9][9] = { /* :481-491 */
     { F_U, -1, -1, -1, -1, F_U, -1, -1, F_U },    { F_UD, -1, -1, -1, -1, F_UD, -1, -1, F_UD },
     { F_R, -1, -1, -1, -1, -1, F_R, F_R, F_R },   { F_RD, -1, -1, -1, -1, -1, F_RD, F_RD, F_RD },
     { F_F, -1, -1, -1, -1, -1, -1, -1, -1 } };
-static const double FSM_PROB[8][9] = { /* :540-549, <0 = None */
+static const double FSM_PROB[2][8][9] = { { /* FiniteStateRedAgent.py:540-549, <0 = None */
     { 0.5, 0.25, 0.25, -1, -1, -1, -1, -1, -1 },  { -1, 0.5, 0.5, -1, -1, -1, -1, -1, -1 },
     { 0.25, -1, -1, 0.25, 0.5, -1, -1, -1, -1 },  { -1, -1, -1, 0.25, 0.75, -1, -1, -1, -1 },
     { 0.5, -1, -1, -1, -1, 0.5, -1, -1, 0.0 },    { -1, -1, -1, -1, -1, 1.0, -1, -1, 0.0 },
-    { 0.5, -1, -1, -1, -1, -1, 0.25, 0.25, 0.0 }, { -1, -1, -1, -1, -1, -1, 0.5, 0.5, 0.0 } };
+    { 0.5, -1, -1, -1, -1, -1, 0.25, 0.25, 0.0 }, { -1, -1, -1, -1, -1, -1, 0.5, 0.5, 0.0 } },
+  { /* DiscoveryFSRed.state_transitions_probability FSMRedVariants.py:110-120 */
+    { 0.25, 0.75, 0.0, -1, -1, -1, -1, -1, -1 },  { -1, 1.0, 0.0, -1, -1, -1, -1, -1, -1 },
+    { 0.25, -1, -1, 0.0, 0.75, -1, -1, -1, -1 },  { -1, -1, -1, 0.0, 1.0, -1, -1, -1, -1 },
+    { 0.0, -1, -1, -1, -1, 1.0, -1, -1, 0.0 },    { -1, -1, -1, -1, -1, 1.0, -1, -1, 0.0 },
+    { 1.0, -1, -1, -1, -1, -1, 0.0, 0.0, 0.0 },   { -1, -1, -1, -1, -1, -1, 0.5, 0.5, 0.0 } } };
+/* DiscoveryFSRed.set_host_state_priority_list FSMRedVariants.py:86-99 (K KD S SD U UD R RD) */
+static const int FSMD_PRIORITY[8] = { 20, 20, 20, 20, 10, 10, 0, 0 };
 /* order of action_space['action'] for red = red_actions list, EnterpriseScenarioGenerator.py:764-768, as FSM columns */
 static const int RED_ASPACE_COLS[9] = { 0, 1, 2, 4, 5, 7, 3, 6, 8 };
 
@@ -159,7 +166,7 @@ typedef struct {
 typedef struct { int16_t slot; uint8_t state, hn; } fsm_t;
 
 struct cc4o_env {
-    uint64_t seed, episode; int steps, rng_mode;
+    uint64_t seed, episode; int steps, rng_mode, red_variant;
     const cc4o_draw *tape; const uint32_t *seg_off; uint32_t n_segs;
     uint32_t seg_pos[NAG]; uint32_t reset_pos; uint32_t draw_ctr[NAG + 1]; uint32_t frac[NAG + 1];
     int32_t breakdown[3][3][NSUB];     /* reward events so far: [mission phase][LWF, ASF, RIA][subnet] (cc4o_reward_breakdown) */
@@ -675,9 +682,47 @@ static act_t red_policy(cc4o_env *e, int r)
     int known[MAXFSM], nk = 0;
     for (int i = 0; i < e->n_fsm[r]; i++) if (e->fsm[r][i].state != F_F) known[nk++] = i;
     if (nk == 0) { fail(e, CC4O_E_UNREACHABLE, "fsm has no known host"); return a; }
-    fsm_t *f = &e->fsm[r][known[rng_int(e, actor, ST_FSM_HOST, (uint32_t)nk)]];
+    fsm_t *f;
+    if (e->red_variant == 0) f = &e->fsm[r][known[rng_int(e, actor, ST_FSM_HOST, (uint32_t)nk)]];
+    else {
+        /* DiscoveryFSRed: FiniteStateRedAgent._choose_host :252-293 with a host-state priority list and the server bias */
+        int states[8], ns = 0, total = 0;
+        for (int i = 0; i < nk && ns < 8; i++) {      /* states in order of first appearance among the known hosts */
+            int st = e->fsm[r][known[i]].state, seen = 0;
+            for (int j = 0; j < ns; j++) seen |= states[j] == st;
+            if (!seen) { states[ns++] = st; total += FSMD_PRIORITY[st]; }
+        }
+        int pick;
+        if (total > 0) {
+            /* probs = [(p / base) * p_multiplier]; numpy choice(p=): cdf = cumsum(probs); cdf /= cdf[-1]; searchsorted(cdf, u, 'right') */
+            volatile double mult = 1.0 / ((double)total / 100.0);
+            double cdfv[8]; volatile double acc = 0.0;
+            for (int i = 0; i < ns; i++) { volatile double pi = ((double)FSMD_PRIORITY[states[i]] / 100.0) * mult; acc = acc + pi; cdfv[i] = acc; }
+            double u = rng_f64(e, actor, ST_FSMD_STATE_P, (uint32_t)ns);
+            for (pick = 0; pick < ns; pick++) if (!(cdfv[pick] / cdfv[ns - 1] <= u)) break;
+            if (pick >= ns) pick = ns - 1;
+        } else pick = (int)rng_int(e, actor, ST_FSMD_STATE_U, (uint32_t)ns);
+        int opts[MAXFSM], no = 0, srv[MAXFSM], nsrv = 0, oth[MAXFSM], noth = 0;
+        for (int i = 0; i < nk; i++) {
+            fsm_t *g = &e->fsm[r][known[i]];
+            if (g->state != states[pick]) continue;
+            opts[no++] = known[i];
+            if (g->hn && g->slot >= 0 && g->slot < 128 && (g->slot & 15) < 6) srv[nsrv++] = known[i]; else oth[noth++] = known[i];   /* 'server' in hostname */
+        }
+        int idx;
+        if (no > 1) {
+            if (nsrv > 0) {
+                double roll = rng_f64(e, actor, ST_FSMD_ROLL, 0);
+                if (roll <= 0.75) idx = srv[rng_int(e, actor, ST_FSMD_HOST_SRV, (uint32_t)nsrv)];
+                else if (nsrv != no) idx = oth[rng_int(e, actor, ST_FSMD_HOST_OTHER, (uint32_t)noth)];
+                else idx = srv[rng_int(e, actor, ST_FSMD_HOST_SRV2, (uint32_t)nsrv)];
+            } else idx = opts[rng_int(e, actor, ST_FSMD_HOST_ALL, (uint32_t)no)];
+        } else idx = opts[rng_int(e, actor, ST_FSM_HOST, (uint32_t)no)];
+        f = &e->fsm[r][idx];
+    }
+    const double (*PROB)[9] = FSM_PROB[e->red_variant];
     int cols[9], nc = 0; double p[9];
-    for (int i = 0; i < 9; i++) { int c = RED_ASPACE_COLS[i]; if (FSM_PROB[f->state][c] >= 0) { cols[nc] = c; p[nc] = FSM_PROB[f->state][c]; nc++; } }
+    for (int i = 0; i < 9; i++) { int c = RED_ASPACE_COLS[i]; if (PROB[f->state][c] >= 0) { cols[nc] = c; p[nc] = PROB[f->state][c]; nc++; } }
     double u = rng_f64(e, actor, ST_FSM_ACTION, (uint32_t)nc);
     double cdf = 0, tot = 0; int pick = 0;
     for (int i = 0; i < nc; i++) tot += p[i];
@@ -1312,6 +1357,8 @@ int cc4o_export(cc4o_env *e, int32_t *out, int cap)
 /* ------------------------------------------------------------------------------------------------ */
 /* life cycle                                                                                       */
 /* ------------------------------------------------------------------------------------------------ */
+void cc4o_set_red_agent(cc4o_env *e, int variant) { e->red_variant = variant ? 1 : 0; }
+
 cc4o_env *cc4o_create(uint64_t seed, uint64_t episode_id, int steps, int rng_mode)
 {
     cc4o_env *e = (cc4o_env *)calloc(1, sizeof *e);

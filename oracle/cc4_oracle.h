@@ -30,7 +30,10 @@ enum {
     ST_LW_RELIAB = 12, ST_LW_FP = 13, ST_LW_PHISH = 14, ST_PHISH_AGENT = 15, ST_AS_DEST = 16, ST_AS_FP = 17,
     ST_FSM_HOST = 18, ST_FSM_ACTION = 19, ST_FSM_PARAM = 20, ST_PORTSCAN = 21, ST_EXP_OTHER = 22,
     ST_EXP_TOP = 23, ST_EXP_SUCC = 24, ST_EXP_DETECT = 25, ST_SSH_HOP = 26, ST_PRIV_SESS = 27, ST_DD_TP = 28,
-    ST_DD_FP = 29, ST_RSC_PRIMARY = 30, ST_DECOY_FACTORY = 31
+    ST_DD_FP = 29, ST_RSC_PRIMARY = 30, ST_DECOY_FACTORY = 31,
+    /* DiscoveryFSRed only (FiniteStateRedAgent._choose_host :252-293) */
+    ST_FSMD_STATE_P = 32, ST_FSMD_STATE_U = 33, ST_FSMD_ROLL = 34, ST_FSMD_HOST_SRV = 35, ST_FSMD_HOST_OTHER = 36,
+    ST_FSMD_HOST_SRV2 = 37, ST_FSMD_HOST_ALL = 38
 };
 
 /* One recorded draw. kind 0: integer in [0,n) stored in val; kind 1: double in [0,1), IEEE bits in val. */
@@ -60,6 +63,8 @@ typedef struct cc4o_env cc4o_env;
 
 /* rng_mode 0 = Philox4x32-10 keyed (seed, episode_id); 1 = tape replay */
 cc4o_env *cc4o_create(uint64_t seed, uint64_t episode_id, int steps, int rng_mode);
+/* scripted red agent class: 0 = FiniteStateRedAgent (default), 1 = DiscoveryFSRed (FSMRedVariants.py:72-122); before cc4o_reset */
+void cc4o_set_red_agent(cc4o_env *e, int variant);
 void cc4o_destroy(cc4o_env *e);
 /* tape: recs[] plus seg_off[n_segs + 1]; segment 0 = reset, 1 + t*CC4O_N_ACTORS + actor = tick t.
  * The arrays are borrowed (must outlive the env). */

@@ -66,9 +66,12 @@ def tape_from_fixture(fx, n_ticks: int | None = None):
 
 
 class OracleEnv:
-    def __init__(self, seed=0, episode=0, steps=500, tape=None):
+    def __init__(self, seed=0, episode=0, steps=500, tape=None, red="fsm"):
         self.L = lib()
         self.h = self.L.cc4o_create(seed, episode, steps, 1 if tape is not None else 0)
+        if red != "fsm":        # DiscoveryFSRed (FSMRedVariants.py:72-122)
+            self.L.cc4o_set_red_agent.argtypes = [C.c_void_p, C.c_int]
+            self.L.cc4o_set_red_agent(self.h, 1)
         self._tape = tape
         if tape is not None:
             recs, seg_off = tape

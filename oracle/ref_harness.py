@@ -85,6 +85,14 @@ SITE = {
     ("FiniteStateRedAgent.py", 291): 18,             # FSM_HOST
     ("FiniteStateRedAgent.py", 311): 19,             # FSM_ACTION (choice with p)
     ("FiniteStateRedAgent.py", 330): 20,             # FSM_PARAM
+    # --- DiscoveryFSRed only (host-state priorities + server bias, FiniteStateRedAgent._choose_host :252-293)
+    ("FiniteStateRedAgent.py", 269): 32,             # FSMD_STATE_P   choice(states, p)
+    ("FiniteStateRedAgent.py", 271): 33,             # FSMD_STATE_U   choice(states) when every priority is 0
+    ("FiniteStateRedAgent.py", 278): 34,             # FSMD_ROLL      random() <= 0.75 -> a server
+    ("FiniteStateRedAgent.py", 280): 35,             # FSMD_HOST_SRV
+    ("FiniteStateRedAgent.py", 285): 36,             # FSMD_HOST_OTHER
+    ("FiniteStateRedAgent.py", 287): 37,             # FSMD_HOST_SRV2 (only servers to pick from)
+    ("FiniteStateRedAgent.py", 289): 38,             # FSMD_HOST_ALL  (no server among the options)
     # --- red actions
     ("Portscan.py", 49): 21,                         # PORTSCAN
     ("ExploitRemoteService.py", 61): 22,             # EXP_OTHER
@@ -254,10 +262,12 @@ def _inprog(ctrl, name):
 class RefEpisode:
     """One reference environment driven through BlueFlatWrapper with index actions."""
 
-    def __init__(self, seed: int, steps: int = 500):
+    def __init__(self, seed: int, steps: int = 500, red: str = "fsm"):
         _ensure_path()
         from CybORG import CybORG
         from CybORG.Agents import SleepAgent, EnterpriseGreenAgent, FiniteStateRedAgent
+        if red == "discovery":      # CybORG/Agents/SimpleAgents/FSMRedVariants.py:72-122
+            from CybORG.Agents.SimpleAgents.FSMRedVariants import DiscoveryFSRed as FiniteStateRedAgent
         from CybORG.Agents.Wrappers import BlueFlatWrapper
         from CybORG.Simulator.Scenarios import EnterpriseScenarioGenerator
 
@@ -431,9 +441,9 @@ def blue_policy(kind: str, rng: np.random.Generator, mask: np.ndarray, obs: np.n
 
 
 def run_episode(seed: int, policy: str = "sleep", steps: int = 500, n_ticks: int | None = None,
-                with_state: bool = True) -> dict[str, np.ndarray]:
+                with_state: bool = True, red: str = "fsm") -> dict[str, np.ndarray]:
     """Run one reference episode and return the fixture arrays."""
-    ep = RefEpisode(seed, steps)
+    ep = RefEpisode(seed, steps, red)
     n_ticks = steps - 1 if n_ticks is None else n_ticks
     prng = np.random.Generator(np.random.PCG64(seed + 7919))
     mask = ep.mask_array()
@@ -460,7 +470,7 @@ def run_episode(seed: int, policy: str = "sleep", steps: int = 500, n_ticks: int
     for i, c in enumerate(canon):
         off[i + 1] = off[i] + len(c)
     return dict(
-        seed=np.int64(seed), steps=np.int32(steps), policy=np.array(policy),
+        seed=np.int64(seed), steps=np.int32(steps), policy=np.array(policy), red=np.array(red),
         t_step=np.array([x[0] for x in rec], dtype=np.int32), t_actor=np.array([x[1] for x in rec], dtype=np.uint8),
         t_site=np.array([x[2] for x in rec], dtype=np.uint8), t_kind=np.array([x[3] for x in rec], dtype=np.uint8),
         t_n=np.array([x[4] for x in rec], dtype=np.uint16), t_val=t_val,
@@ -480,10 +490,11 @@ if __name__ == "__main__":
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     for spec in args.spec:
-        seed, policy, steps = spec.split(":")
+        seed, policy, steps, *rest = spec.split(":")      # seed:policy:steps[:red]  (red = fsm | discovery)
+        red = rest[0] if rest else "fsm"
         t0 = time.time()
-        fx = run_episode(int(seed), policy, int(steps))
-        path = os.path.join(args.out, f"ep_s{seed}_{policy}_{steps}.npz")
+        fx = run_episode(int(seed), policy, int(steps), red=red)
+        path = os.path.join(args.out, f"ep_s{seed}_{policy}_{steps}{'' if red == 'fsm' else '_' + red}.npz")
         np.savez_compressed(path, **fx)
         print(f"{path}: {len(fx['t_val'])} draws, {len(fx['canon'])} state ints, return {fx['reward'].sum():.1f}, "
               f"{time.time() - t0:.1f}s, {os.path.getsize(path) / 1024:.0f} KiB")

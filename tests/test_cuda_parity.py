@@ -23,14 +23,19 @@ def _diff(exp, got):
     return "; ".join(canon.diff(canon.decode(exp), canon.decode(got))[:8])
 
 
-STEPS = sorted({int(np.load(os.path.join(GOLDEN, f))["steps"]) for f in FILES})
+def _red_of(f):
+    fx = np.load(os.path.join(GOLDEN, f))
+    return str(fx["red"]) if "red" in fx else "fsm"
 
 
-@pytest.mark.parametrize("steps", STEPS)
-def test_tape_replay_of_reference_episodes(steps):
-    """All golden episodes of one episode length in ONE batch (ragged tick counts): state, observations, reward,
-    done after every tick."""
-    names = [f for f in FILES if int(np.load(os.path.join(GOLDEN, f))["steps"]) == steps]
+STEPS = sorted({(int(np.load(os.path.join(GOLDEN, f))["steps"]), _red_of(f)) for f in FILES})
+
+
+@pytest.mark.parametrize("steps,red", STEPS)
+def test_tape_replay_of_reference_episodes(steps, red):
+    """All golden episodes of one episode length and red agent class (FiniteStateRedAgent / DiscoveryFSRed) in ONE batch
+    (ragged tick counts): state, observations, reward, done after every tick."""
+    names = [f for f in FILES if int(np.load(os.path.join(GOLDEN, f))["steps"]) == steps and _red_of(f) == red]
     fxs = [np.load(os.path.join(GOLDEN, f)) for f in names]
     n = len(fxs)
     T = max(len(fx["actions"]) for fx in fxs)
@@ -44,7 +49,7 @@ def test_tape_replay_of_reference_episodes(steps):
         segs.append(full + np.uint32(base))
         recs_all.append(recs)
         base += len(recs)
-    env = _engine(n, device=0, steps=steps, rng="tape")
+    env = _engine(n, device=0, steps=steps, rng="tape", red_agent=red)
     env.set_tape(np.concatenate(recs_all), np.stack(segs))
     obs, mask = env.reset()
     obs, mask = obs.cpu().numpy(), mask.cpu().numpy()
@@ -328,3 +333,26 @@ def test_config2_state_transition_only_4096_envs():
         ca = a.export_canon(i)
         assert np.array_equal(ca, b.export_canon(i)) and np.array_equal(ca, refs[i].export()), f"episode {i}"
     assert not a.error_flags().any()
+
+
+def test_discovery_red_agent_philox_mode_matches_oracle():
+    """DiscoveryFSRed (FSMRedVariants.py:72-122) in production mode: CUDA engine == oracle on a seeded batch."""
+    n, ticks, seed = 96, 150, 29
+    env = _engine(n, device=0, seed=seed, steps=500, red_agent="discovery")
+    env.reset()
+    refs = [O.OracleEnv(seed=seed, episode=i, steps=500, red="discovery") for i in range(n)]
+    for r in refs:
+        r.reset()
+    g = np.random.default_rng(seed)
+    for t in range(ticks):
+        acts = np.stack([g.integers(0, k, n) for k in (82, 82, 82, 82, 242)], 1).astype(np.int32)
+        if t % 2:
+            acts[:] = (49, 49, 49, 49, 145)          # let red run freely every other tick
+        o, r, d = env.step(torch.from_numpy(acts).cuda())
+        o, r, d = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
+        for i, ref in enumerate(refs):
+            rc, oo, rr, dd = ref.step(acts[i])
+            assert np.array_equal(o[i], oo) and r[i] == rr and d[i] == dd, f"episode {i} tick {t}"
+    for i in range(0, n, 7):
+        assert np.array_equal(env.export_canon(i), refs[i].export()), f"episode {i}: {_diff(refs[i].export(), env.export_canon(i))}"
+    assert not env.error_flags().any()

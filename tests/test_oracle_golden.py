@@ -19,7 +19,7 @@ FILES = sorted(f for f in os.listdir(GOLDEN) if f.startswith("ep_") and f.endswi
 @pytest.mark.parametrize("name", FILES)
 def test_oracle_replays_reference(name):
     fx = np.load(os.path.join(GOLDEN, name))
-    env = O.OracleEnv(steps=int(fx["steps"]), tape=O.tape_from_fixture(fx))
+    env = O.OracleEnv(steps=int(fx["steps"]), tape=O.tape_from_fixture(fx), red=str(fx["red"]) if "red" in fx else "fsm")
     env.reset()
     off = fx["canon_off"]
 
