@@ -224,7 +224,6 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = env.launch_count() - l0
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
-    clocks = sampler.stop()
 
     # end to end through the public host-buffer API: pinned actions in, pinned obs / reward / done out
     host_pool = [p.cpu().pin_memory() for p in pool[:max(args.e2e_steps, 4)]]
@@ -237,6 +236,7 @@ def main():
         o, r, d = env.step_host(host_pool[i % len(host_pool)], compact=True)    # obs uint8 [N, 578]: the five unpadded vectors
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()      # sampled through both timed regions (device-resident steps, then the host-buffer steps)
     h2d = n * N_BLUE * 4
     d2h = n * (578 + 4 + 1)
 

@@ -1,9 +1,10 @@
 /*
  * cc4_engine.cu — kernels and C-ABI (include/cc4_b200.h) of the B200-native batched CC4 step engine.
  *
- * Kernels (sm_100a, one warp per episode, the episode's packed record staged in shared memory):
- *   k_reset   EnterpriseScenarioGenerator.create_scenario + State.__init__ + controller reset
- *   k_step    one SimulationController.step tick for every episode (+ observation vectors, reward, done)
+ * Kernels (sm_100a):
+ *   k_reset   EnterpriseScenarioGenerator.create_scenario + State.__init__ + controller reset (one warp per episode)
+ *   k_step    one SimulationController.step tick for every episode (+ observation vectors, reward, done): one block per
+ *             SM keeps up to 64 episodes' packed records in shared memory and walks them through the phases of the tick
  *   k_rollout n fused ticks with the benchmark's synthetic random blue policy (state stays in shared memory)
  * Citations are file:line under /root/reference/CybORG/.
  */
@@ -94,24 +95,6 @@ __device__ __forceinline__ void w_store(Cc4Dyn *dst, const Cc4Dyn *src)
 /* ------------------------------------------------------------------------------------------------ */
 /* observation vectors: BlueFlatWrapper.observation_change BlueFlatWrapper.py:172-256 (lane per element) */
 /* ------------------------------------------------------------------------------------------------ */
-__device__ __forceinline__ uint8_t obs_element(const Cc4Dyn *s, int b, int p)
-{
-    int nsub = b == 4 ? 3 : 1, body = 1 + 59 * nsub;
-    if (p == 0) return s->phase;
-    if (p < body) {
-        int q = p - 1, i = q / 59, o = q % 59, sn = blue_sorted_subnet(b, i);
-        if (o < 9) return c_sorted_subnets[o] == sn;
-        if (o < 18) return (s->blocks[sn] >> c_sorted_subnets[o - 9]) & 1;
-        if (o < 27) return !((c_comms_adj[s->phase][sn] >> c_sorted_subnets[o - 18]) & 1);
-        if (o < 43) { int h = sn * 16 + (o - 27); return host_exists(s, h) && (s->ev[h] & (EV_PROC | EV_OLDPROC)) != 0; }
-        int h = sn * 16 + (o - 43);
-        return host_exists(s, h) && (s->ev[h] & (EV_NET | EV_OLDNET)) != 0;
-    }
-    int q = p - body;
-    if (q >= 32) return 0;
-    int k = q >> 3, other = k < b ? k : k + 1;   /* the other four agents in sorted order, SimulationController.py:781-804 */
-    return (s->msgs[other] >> (q & 7)) & 1;
-}
 /* The five vectors are assembled as ONE bit string (element p of agent b = bit mis + stride*b + p) and expanded into
  * bytes in registers, sixteen elements per lane, straight into 128-bit stores.  `mis` = the episode's byte offset inside
  * its 16-byte line (a row of 1 050 or 578 B is only 2-byte aligned): giving the bit string the same lead makes bit j and
