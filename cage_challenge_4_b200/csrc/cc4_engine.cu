@@ -283,6 +283,7 @@ __device__ __forceinline__ int order_get(const PhaseOrder *o, int i)
                              first episode = wall cycles of phase p for the block, barrier included; [17] = the episode's slowest red
                              phase, [16] of a block's first episode = the block's slowest red phase */
 __device__ unsigned long long *g_phase_clk;
+__device__ unsigned long long *g_action_clk;       /* [64][2]: cycles and count per action code (red and blue execution) */
 #define PC_STRIDE 18
 #endif
 
@@ -430,7 +431,16 @@ __device__ __forceinline__ void ph_blue_exec(Cx c)
         const bool prio1 = code == AC_BLOCK || code == AC_ALLOW;
         uint32_t first = __ballot_sync(0xFFFFFFFFu, prio1), then = __ballot_sync(0xFFFFFFFFu, !prio1 && code != AC_SLEEP && code != AC_ANALYSE);
         while (first) { const int b = __ffs(first) - 1; first &= first - 1; exec_blue(c, b, x->subw[b]); }
-        while (then) { const int b = __ffs(then) - 1; then &= then - 1; exec_blue(c, b, x->subw[b]); }
+        while (then) {
+            const int b = __ffs(then) - 1; then &= then - 1;
+#ifdef CC4_PHASE_CLOCKS
+            const long long ta0 = clock64();
+            exec_blue(c, b, x->subw[b]);
+            if (lane_id() == 0 && g_action_clk) { atomicAdd(&g_action_clk[2 * IP_CODE(x->subw[b])], (unsigned long long)(clock64() - ta0)); atomicAdd(&g_action_clk[2 * IP_CODE(x->subw[b]) + 1], 1ull); }
+#else
+            exec_blue(c, b, x->subw[b]);
+#endif
+        }
     }
     __syncwarp();
 }
@@ -520,7 +530,13 @@ __device__ __forceinline__ void ph_red(Cx c, bool with_phishing = true)
         while (todo) {                  /* warp-uniform, in agent order */
             const int r = __ffs(todo) - 1; todo &= todo - 1;
             const uint32_t aw = x->subw[A_RED0 + r];
+#ifdef CC4_PHASE_CLOCKS
+            const long long ta0 = clock64();
             const int succ = exec_red(c, r, aw);
+            if (lane_id() == 0 && g_action_clk) { atomicAdd(&g_action_clk[2 * IP_CODE(aw)], (unsigned long long)(clock64() - ta0)); atomicAdd(&g_action_clk[2 * IP_CODE(aw) + 1], 1ull); }
+#else
+            const int succ = exec_red(c, r, aw);
+#endif
             obs_push(c, r, succ, true, aw);
         }
     }
@@ -1179,6 +1195,10 @@ extern "C" int cc4_phase_clocks(cc4_handle *h, unsigned long long *out_host, int
         CUDA_TRY(cudaMalloc(&h->p.phase_clk, bytes));
         CUDA_TRY(cudaMemset(h->p.phase_clk, 0, bytes));
         CUDA_TRY(cudaMemcpyToSymbol(g_phase_clk, &h->p.phase_clk, sizeof(void *)));
+        unsigned long long *act = nullptr;
+        CUDA_TRY(cudaMalloc(&act, 128 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemset(act, 0, 128 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemcpyToSymbol(g_action_clk, &act, sizeof(void *)));
     }
     CUDA_TRY(cudaMemcpy(out_host, h->p.phase_clk, bytes, cudaMemcpyDeviceToHost));
     if (reset) CUDA_TRY(cudaMemset(h->p.phase_clk, 0, bytes));
@@ -1186,6 +1206,23 @@ extern "C" int cc4_phase_clocks(cc4_handle *h, unsigned long long *out_host, int
 #else
     (void)h; (void)out_host; (void)reset;
     return set_err(CC4_ERR_STATE, "cc4_phase_clocks: this build has no phase clocks (-DCC4_PHASE_CLOCKS)%s", "");
+#endif
+}
+
+/* profiling builds only: out_host uint64 [64][2] = cycles, count per action code since the counters were armed */
+extern "C" int cc4_action_clocks(cc4_handle *h, unsigned long long *out_host)
+{
+#ifdef CC4_PHASE_CLOCKS
+    if (!h || !out_host) return set_err(CC4_ERR_ARG, "cc4_action_clocks: null%s", "");
+    CUDA_TRY(cudaDeviceSynchronize());
+    unsigned long long *act = nullptr;
+    CUDA_TRY(cudaMemcpyFromSymbol(&act, g_action_clk, sizeof(void *)));
+    if (!act) return set_err(CC4_ERR_STATE, "cc4_action_clocks: call cc4_phase_clocks first%s", "");
+    CUDA_TRY(cudaMemcpy(out_host, act, 128 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return CC4_OK;
+#else
+    (void)h; (void)out_host;
+    return set_err(CC4_ERR_STATE, "cc4_action_clocks: this build has no phase clocks (-DCC4_PHASE_CLOCKS)%s", "");
 #endif
 }
 

@@ -126,6 +126,9 @@ int cc4_launch_count(cc4_handle *h, uint64_t *out);
  * block's first episode: wall cycles of phase p for the block, barrier included); reset != 0 clears the counters.
  * The first call arms the counters.  Synchronises the device. */
 int cc4_phase_clocks(cc4_handle *h, unsigned long long *out_host, int reset);
+/* Profiling builds only: out_host uint64 [64][2] = cycles spent in, and number of, executed actions per action code
+ * (oracle/canon.py ACTION_CODE) since cc4_phase_clocks armed the counters. */
+int cc4_action_clocks(cc4_handle *h, unsigned long long *out_host);
 
 const char *cc4_last_error(void);
 

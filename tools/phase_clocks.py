@@ -57,6 +57,15 @@ for i in range(8):
     w = wall[blocks, i].mean()
     print(f"{names[i]:>18} {b.mean():9.0f} {np.percentile(b, 90):8.0f} {np.percentile(b, 99):8.0f} {b.max():8.0f} {w:9.0f} "
           f"{100 * w / wall[blocks].sum(1).mean():6.1f} {b.mean() * epb / (wpb * w):9.2f}")
+ac = np.zeros((64, 2), dtype=np.uint64)
+_native.check(env._L.cc4_action_clocks(env._h, ac.ctypes.data), "cc4_action_clocks")
+names_a = {1: "Monitor", 3: "Remove", 4: "Restore", 5: "DeployDecoy", 10: "DiscoverRemoteSystems", 11: "AggressiveServiceDiscovery", 12: "StealthServiceDiscovery",
+           13: "DiscoverDeception", 14: "ExploitRemoteService", 15: "PrivilegeEscalate", 16: "Impact", 17: "DegradeServices"}
+print("executed actions (per episode-tick count, mean cycles each, share of the per-episode action time):")
+tot_a = float(ac[:, 0].sum())
+for code in sorted(names_a):
+    if ac[code, 1]:
+        print(f"  {names_a[code]:28s} {ac[code, 1] / (n * ticks):6.3f} x {ac[code, 0] / ac[code, 1]:7.0f} cycles  {100 * ac[code, 0] / tot_a:5.1f} %")
 mx = buf[:, 17].astype(np.float64)
 print(f"red phase: slowest single episode-tick per episode over the {ticks} ticks: mean {mx.mean():.0f}, p50 {np.percentile(mx, 50):.0f}, p99 {np.percentile(mx, 99):.0f}, max {mx.max():.0f} cycles; slowest in a block (over all its episodes and ticks): mean {buf[blocks, 16].astype(np.float64).mean():.0f}")
 print(json.dumps({"busy_mean": busy.mean(0).tolist(), "block_wall_mean": wall[blocks].mean(0).tolist()}))
