@@ -314,10 +314,10 @@ __device__ __forceinline__ void set128(uint32_t *b, int i) { b[i >> 5] |= 1u << 
 #define P_NONE P_DEADBIT    /* filler for lanes past the end of a list: looks like a tombstone */
 /* port class of a process kind (canon PORT_BIT), 15 = does not listen */
 __device__ __forceinline__ uint32_t kind_portbit(uint32_t kind) { return (uint32_t)(0xFFF245243210ull >> (4 * kind)) & 15u; }
-__device__ CC4_INL4 void proc_append(Cx c, int h, uint32_t w)
-{   /* host.processes.append */
+__device__ CC4_INL4 void proc_append(Cx c, int h, uint32_t w, uint32_t d, uint32_t pmax)
+{   /* host.processes.append; d = pdir[h], pmax = pmax[h] (the caller has them in registers) */
     Cc4Cold *k = WC(c)->k;
-    uint32_t d = k->pdir[h], off = PD_OFF(d), n = PD_CNT(d), capl = PD_CAPL(d);
+    uint32_t off = PD_OFF(d), n = PD_CNT(d), capl = PD_CAPL(d);
     if (n == (1u << capl)) {            /* block full: move the list to a block of twice the size */
         uint32_t top = k->arena_top, ncap = 2u << capl;
         if (top + ncap > CC4_ARENA || n >= PD_MAXCNT) { fail(c, CC4_E_CAPACITY); return; }
@@ -327,8 +327,9 @@ __device__ CC4_INL4 void proc_append(Cx c, int h, uint32_t w)
     }
     k->parena[off + n] = w;
     k->pdir[h] = PD_MAKE(off, n + 1, capl);
-    if (P_PID(w) > k->pmax[h]) k->pmax[h] = (uint16_t)P_PID(w);
+    if (P_PID(w) > pmax) k->pmax[h] = (uint16_t)P_PID(w);
 }
+__device__ CC4_INL4 void proc_append(Cx c, int h, uint32_t w) { proc_append(c, h, w, WC(c)->k->pdir[h], WC(c)->k->pmax[h]); }
 __device__ CC4_INL5 void proc_rescan_max(Cx c, int h)
 {
     Cc4Cold *k = WC(c)->k;
@@ -358,9 +359,8 @@ __device__ CC4_INL5 void proc_delete(Cx c, int h, int idx)
     k->pdir[h] = PD_MAKE(PD_OFF(d), n - 1, PD_CAPL(d));
     if (!P_DEAD(gone) && P_PID(gone) == k->pmax[h]) proc_rescan_max(c, h);
 }
-__device__ CC4_INL5 int proc_find(Cx c, int h, uint32_t pid)
-{   /* Host.get_process Host.py:251 (tombstones are not processes) */
-    const uint32_t d = WC(c)->k->pdir[h];
+__device__ CC4_INL5 int proc_find(Cx c, uint32_t pid, uint32_t d)
+{   /* Host.get_process Host.py:251 (tombstones are not processes); d = pdir[host] */
     const uint32_t *pp = WC(c)->k->parena + PD_OFF(d); const int n = (int)PD_CNT(d);
     _Pragma("unroll 1") for (int base = 0; base < n; base += 32) {
         const int i = base + lane_id();
@@ -370,12 +370,14 @@ __device__ CC4_INL5 int proc_find(Cx c, int h, uint32_t pid)
     }
     return -1;
 }
-__device__ CC4_INL3 int create_pid(Cx c, int actor, int h)
-{   /* Host.create_pid Host.py:198-200 */
-    uint32_t pid = (uint32_t)WC(c)->k->pmax[h] + 1 + rng_int(c, actor, ST_CREATE_PID, 9);
+__device__ CC4_INL5 int proc_find(Cx c, int h, uint32_t pid) { return proc_find(c, pid, WC(c)->k->pdir[h]); }
+__device__ CC4_INL3 int create_pid(Cx c, int actor, uint32_t pmax)
+{   /* Host.create_pid Host.py:198-200; pmax = pmax[h] */
+    uint32_t pid = pmax + 1 + rng_int(c, actor, ST_CREATE_PID, 9);
     if (pid > 0xFFFFu) { fail(c, CC4_E_CAPACITY); pid = 0xFFFFu; }
     return (int)pid;
 }
+__device__ CC4_INL3 int create_pid_on(Cx c, int actor, int h) { return create_pid(c, actor, (uint32_t)WC(c)->k->pmax[h]); }
 
 /* ---- services ---- */
 __device__ __forceinline__ int svc_count(uint64_t v)
@@ -398,6 +400,12 @@ template <class Pred> __device__ __forceinline__ int sess_first(const Cc4Dyn *s,
     }
     return -1;
 }
+/* position of the k-th (0-based) set bit of a warp-uniform mask with more than k bits set [uniform]: every lane tests its own bit */
+__device__ __forceinline__ int kth_bit(uint32_t m, int k)
+{
+    const int lane = lane_id();
+    return __ffs(__ballot_sync(FULLMASK, (m >> lane & 1u) && __popc(m & ((1u << lane) - 1u)) == k)) - 1;
+}
 /* pool index of the k-th (0-based) entry that satisfies pred, -1 if there are fewer */
 template <class Pred> __device__ __forceinline__ int sess_kth(const Cc4Dyn *s, int k, Pred pred)
 {
@@ -406,7 +414,7 @@ template <class Pred> __device__ __forceinline__ int sess_kth(const Cc4Dyn *s, i
         const int i = base + lane_id();
         const uint32_t m = __ballot_sync(FULLMASK, i < n && pred(s->sess[i], (uint32_t)s->sessf[i]));
         const int cnt = __popc(m);
-        if (k < cnt) return base + (int)__fns(m, 0, k + 1);
+        if (k < cnt) return base + kth_bit(m, k);
         k -= cnt;
     }
     return -1;
@@ -842,7 +850,7 @@ __device__ CC4_INL6 void stop_process(Cx c, int actor, int h, uint32_t pid)
       if (__any_sync(FULLMASK, clash)) fail(c, CC4_E_UNREACHABLE); }
     proc_delete(c, h, pi);
     if (P_SVC(w)) {
-        int np = create_pid(c, actor, h);
+        int np = create_pid_on(c, actor, h);
         proc_append(c, h, P_MAKE(np, P_KIND(w), P_ROOT(w), 1));
         if (si >= 0) fail(c, CC4_E_UNREACHABLE);   /* a session whose process is a service process */
     }
@@ -874,10 +882,16 @@ __device__ CC4_INL6 void do_restore(Cx c, int h)
 __device__ CC4_INL6 void do_decoy(Cx c, int b, int h)
 {
     int actor = A_BLUE0 + b;
+    Cc4Cold *k = WC(c)->k;
+    /* the host's cold words are requested together; the first 32 list entries stay in a register for both passes */
+    const uint32_t d = k->pdir[h], pmax = k->pmax[h];
+    uint64_t v = k->svc64[h];
+    uint32_t *pp_h = k->parena + PD_OFF(d); const int np_h = (int)PD_CNT(d);
+    const uint32_t w0 = lane_id() < np_h ? pp_h[lane_id()] : P_NONE;
     uint32_t used = 0;
     {
-        const uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
-        _Pragma("unroll 1") for (int i = lane_id(); i < np_h; i += 32) { uint32_t w = pp_h[i]; if (P_DEAD(w)) continue; uint32_t pb = kind_portbit(P_KIND(w)); if (pb != 15u) used |= 1u << pb; }
+        if (!P_DEAD(w0)) { uint32_t pb = kind_portbit(P_KIND(w0)); if (pb != 15u) used |= 1u << pb; }
+        _Pragma("unroll 1") for (int i = 32 + lane_id(); i < np_h; i += 32) { uint32_t w = pp_h[i]; if (P_DEAD(w)) continue; uint32_t pb = kind_portbit(P_KIND(w)); if (pb != 15u) used |= 1u << pb; }
         used = __reduce_or_sync(FULLMASK, used);
     }
     /* compatible factories in CANDIDATE_DECOYS order; VsftpdDecoyFactory tests port 21, which nothing uses, and then opens
@@ -888,19 +902,18 @@ __device__ CC4_INL6 void do_decoy(Cx c, int b, int h)
     if (!(used & PB_25)) fac |= (uint32_t)K_D_HARAKA << (4 * nf++);
     fac |= (uint32_t)K_D_VSFTPD << (4 * nf++);
     int kind = (int)(fac >> (4 * rng_int(c, actor, ST_DECOY_FACTORY, (uint32_t)nf)) & 15u);
-    int pid = create_pid(c, actor, h);
+    int pid = create_pid(c, actor, pmax);
     /* host.services[name] = Service(pid): an earlier process of the same decoy stops being the service's process */
     {
-        uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
-        _Pragma("unroll 1") for (int i = lane_id(); i < np_h; i += 32) { uint32_t w = pp_h[i]; if (P_KIND(w) == (uint32_t)kind && P_SVC(w)) pp_h[i] = w & ~(1u << 21); }
+        if (lane_id() < np_h && P_KIND(w0) == (uint32_t)kind && P_SVC(w0)) pp_h[lane_id()] = w0 & ~(1u << 21);
+        _Pragma("unroll 1") for (int i = 32 + lane_id(); i < np_h; i += 32) { uint32_t w = pp_h[i]; if (P_KIND(w) == (uint32_t)kind && P_SVC(w)) pp_h[i] = w & ~(1u << 21); }
         __syncwarp();
     }
-    proc_append(c, h, P_MAKE(pid, kind, 0, 1));
-    uint64_t v = WC(c)->k->svc64[h];
+    proc_append(c, h, P_MAKE(pid, kind, 0, 1), d, pmax);
     int n = svc_count(v), at = -1;
     _Pragma("unroll 1") for (int i = 0; i < n; i++) if ((SVC_ENTRY(v, i) & 15u) == (uint32_t)kind) at = i;
     if (at < 0) { if (n >= 9) { fail(c, CC4_E_CAPACITY); return; } at = n; }
-    WC(c)->k->svc64[h] = svc_set(v, at, (uint32_t)kind | 5u << 4);
+    k->svc64[h] = svc_set(v, at, (uint32_t)kind | 5u << 4);
 }
 
 /* a blue agent's own Monitor action (Monitor.py:35-74 for one agent) [uniform] */
@@ -994,7 +1007,7 @@ __device__ CC4_INL6 void do_phishing(Cx c, int g)
         const int before = __shfl_sync(FULLMASK, incl - cnt, L);
         src = (int)__fns(v, 0, pk - before + 1) & 7;      /* bit position inside the lane's four bytes -> agent */
     }
-    int pid = create_pid(c, actor, gh);
+    int pid = create_pid_on(c, actor, gh);
     proc_append(c, gh, P_MAKE(pid, K_REDABS, 0, 0));
     sess_add(c, src, gh, 1, 0, pid);
     reinterpret_cast<uint8_t *>(SCR(c)->g.hostagents)[gh] |= (uint8_t)(1u << src);
@@ -1054,42 +1067,73 @@ __device__ CC4_INL8 int green_tick(Cx c, int g, uint32_t *ev_words)
 /* ------------------------------------------------------------------------------------------------ */
 /* red actions (lane 0)                                                                             */
 /* ------------------------------------------------------------------------------------------------ */
-__device__ CC4_INL5 int route(int src, int dst, int *out)
-{   /* hosts on the tree path src -> dst (Action.py:101-117, topology EnterpriseScenarioGenerator.py:373-416) */
-    int n = 0;
-    if (src == dst) { out[n++] = src; return n; }
-    int ca[4], na = 0, cb[4], nb = 0;
-    _Pragma("unroll 1") for (int v = slot_subnet(src); v >= 0; v = c_tree_parent[v]) ca[na++] = v;
-    _Pragma("unroll 1") for (int v = slot_subnet(dst); v >= 0; v = c_tree_parent[v]) cb[nb++] = v;
-    int ia = na - 1, ib = nb - 1;
-    while (ia > 0 && ib > 0 && ca[ia - 1] == cb[ib - 1]) { ia--; ib--; }
-    if (src < CC4_SLOT_ROUTER) out[n++] = src;
-    _Pragma("unroll 1") for (int i = 0; i <= ia; i++) out[n++] = ca[i] == S_INT ? CC4_SLOT_INTERNET : CC4_SLOT_ROUTER + ca[i];
-    _Pragma("unroll 1") for (int i = ib - 1; i >= 0; i--) out[n++] = cb[i] == S_INT ? CC4_SLOT_INTERNET : CC4_SLOT_ROUTER + cb[i];
-    if (dst < CC4_SLOT_ROUTER) out[n++] = dst;
-    return n;
+/* subnets whose routers lie on the tree path between two subnets (Action.py:101-117, topology
+ * EnterpriseScenarioGenerator.py:373-416): 4 bits each from bit 0, count in bits 28-31 (tools/gen_tables.py) */
+__constant__ uint32_t c_route[9][9] = {
+    { 0x10000000u, 0x20000010u, 0x30000280u, 0x40003280u, 0x30000480u, 0x30000580u, 0x40006580u, 0x40007580u, 0x20000080u },
+    { 0x20000001u, 0x10000001u, 0x40002801u, 0x50032801u, 0x40004801u, 0x40005801u, 0x50065801u, 0x50075801u, 0x30000801u },
+    { 0x30000082u, 0x40001082u, 0x10000002u, 0x20000032u, 0x30000482u, 0x30000582u, 0x40006582u, 0x40007582u, 0x20000082u },
+    { 0x40000823u, 0x50010823u, 0x20000023u, 0x10000003u, 0x40004823u, 0x40005823u, 0x50065823u, 0x50075823u, 0x30000823u },
+    { 0x30000084u, 0x40001084u, 0x30000284u, 0x40003284u, 0x10000004u, 0x30000584u, 0x40006584u, 0x40007584u, 0x20000084u },
+    { 0x30000085u, 0x40001085u, 0x30000285u, 0x40003285u, 0x30000485u, 0x10000005u, 0x20000065u, 0x20000075u, 0x20000085u },
+    { 0x40000856u, 0x50010856u, 0x40002856u, 0x50032856u, 0x40004856u, 0x20000056u, 0x10000006u, 0x30000756u, 0x30000856u },
+    { 0x40000857u, 0x50010857u, 0x40002857u, 0x50032857u, 0x40004857u, 0x20000057u, 0x30000657u, 0x10000007u, 0x30000857u },
+    { 0x20000008u, 0x30000108u, 0x20000028u, 0x30000328u, 0x20000048u, 0x20000058u, 0x30000658u, 0x30000758u, 0x10000008u } };
+/* number of hosts on the path src -> dst (both real hosts) and the i-th of them */
+__device__ __forceinline__ int route_len(int src, int dst) { return src == dst ? 1 : 2 + (int)(c_route[src >> 4][dst >> 4] >> 28); }
+__device__ __forceinline__ int route_hop(int src, int dst, int nh, int i)
+{
+    if (i == 0) return src;
+    if (i == nh - 1) return dst;
+    const int v = (int)(c_route[src >> 4][dst >> 4] >> (4 * (i - 1)) & 15u);
+    return v == S_INT ? CC4_SLOT_INTERNET : CC4_SLOT_ROUTER + v;
 }
 
 /* ExploitAction._create_new_session ExploitAction.py:212-262 [uniform] */
-__device__ CC4_INL3 int exploit_new_session(Cx c, int r, int target)
+__device__ CC4_INL3 int exploit_new_session(Cx c, int r, int target, uint32_t pd_target, uint32_t pmax_target)
 {
-    int pid = create_pid(c, A_RED0 + r, target);
-    proc_append(c, target, P_MAKE(pid, K_SHELL, 0, 0));
+    int pid = create_pid(c, A_RED0 + r, pmax_target);
+    proc_append(c, target, P_MAKE(pid, K_SHELL, 0, 0), pd_target, pmax_target);
     sess_add(c, r, target, 0, 0, pid);
     return pid;
 }
-/* index of the known-port entry of (agent, abstract session, host), -1 if none [uniform] */
-__device__ CC4_INL3 int ports_find(Cx c, int r, int id, int host)
+/* index of the known-port entry of (agent, abstract session, host), -1 if none; *word = the entry [uniform] */
+__device__ CC4_INL3 int ports_find(Cx c, int r, int id, int host, uint32_t *word)
 {
     const uint32_t *ports = WC(c)->k->ports;
     const int n = DYN(c)->n_ports;
     const uint32_t key = PT_MAKE(0, host, id, r);
     _Pragma("unroll 1") for (int base = 0; base < n; base += 32) {
         const int i = base + lane_id();
-        const uint32_t m = __ballot_sync(FULLMASK, i < n && (ports[i] & ~0x3Fu) == key);
-        if (m) return base + __ffs(m) - 1;
+        const uint32_t v = i < n ? ports[i] : 0xFFFFFFFFu;
+        const uint32_t m = __ballot_sync(FULLMASK, (v & ~0x3Fu) == key);
+        if (m) { *word = __shfl_sync(FULLMASK, v, __ffs(m) - 1); return base + __ffs(m) - 1; }
     }
     return -1;
+}
+
+/* tape-mode (parity replay) forms of the two draw loops that production mode runs lane-parallel; out of line so that
+ * they stay out of the instruction stream of the red phase [uniform] */
+__device__ __noinline__ int dd_tape(Cx c, int actor, int h)
+{   /* DiscoverDeception.py:83-97: the second draw only happens when the first did not report */
+    const uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
+    int rep = 0;
+    _Pragma("unroll 1") for (int base = 0; base < np_h; base += 32) {
+        const uint32_t mine = base + lane_id() < np_h ? pp_h[base + lane_id()] : P_NONE;
+        const int cnt = min(32, np_h - base);
+        _Pragma("unroll 1") for (int j = 0; j < cnt; j++) {
+            uint32_t w = __shfl_sync(FULLMASK, mine, j);
+            if (P_DEAD(w)) continue;
+            bool decoy = P_KIND(w) >= K_D_APACHE && P_KIND(w) <= K_D_VSFTPD;
+            if (rng_f64(c, actor, ST_DD_TP, 0) <= 0.5 && decoy) rep = 1;
+            else if (rng_f64(c, actor, ST_DD_FP, 0) <= 0.1 && !decoy) rep = 1;
+        }
+    }
+    return rep;
+}
+__device__ __noinline__ void ssh_hops_tape(Cx c, int actor, int src, int target, int nh)
+{   /* SSHBruteForce.py:36-45 */
+    _Pragma("unroll 1") for (int i = 0; i < nh; i++) if (0.05 < rng_f64(c, actor, ST_SSH_HOP, 0)) DYN(c)->ev[route_hop(src, target, nh, i)] |= EV_NET;
 }
 
 /* [uniform]: the whole warp executes the action; scans are lane-parallel */
@@ -1149,7 +1193,8 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
         mask = __reduce_or_sync(FULLMASK, mask);
         if (__any_sync(FULLMASK, alert)) s->ev[h] |= EV_NET;
         if (mask) {
-            int at = ports_find(c, r, a.session, h);
+            uint32_t was;
+            int at = ports_find(c, r, a.session, h, &was);
             if (at < 0) { if (s->n_ports >= CC4_PORT_CAP) { fail(c, CC4_E_CAPACITY); at = 0; } else { at = s->n_ports; s->n_ports = (uint16_t)(at + 1); } }
             WC(c)->k->ports[at] = PT_MAKE(mask, h, a.session, r);
             obs_entry(c, r, 1, h, 1, 0, 0, 0);
@@ -1160,26 +1205,37 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
         if (si < 0) return SUCC_FALSE;
         int rep = 0, h = a.host;
         const uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
-        _Pragma("unroll 1") for (int base = 0; base < np_h; base += 32) {
-            const uint32_t mine = base + lane < np_h ? pp_h[base + lane] : P_NONE;
-            const int cnt = min(32, np_h - base);
-            _Pragma("unroll 1") for (int j = 0; j < cnt; j++) {
-                uint32_t w = __shfl_sync(FULLMASK, mine, j);
-                if (P_DEAD(w)) continue;
-                bool decoy = P_KIND(w) >= K_D_APACHE && P_KIND(w) <= K_D_VSFTPD;
-                if (rng_f64(c, actor, ST_DD_TP, 0) <= 0.5 && decoy) rep = 1;
-                else if (rng_f64(c, actor, ST_DD_FP, 0) <= 0.1 && !decoy) rep = 1;
+        if (g_blk.rng_mode != 1) {
+            /* production mode spends two words per live process whether or not the second is looked at (oracle: AC_DD), so
+               the q-th live process owns words p0 + 2q (decoy test) and p0 + 2q + 1 (false positive): lane per process */
+            Scratch *x = SCR(c);
+            uint32_t p0 = ctr_get(x, actor);
+            _Pragma("unroll 1") for (int base = 0; base < np_h; base += 32) {
+                const uint32_t w = base + lane < np_h ? pp_h[base + lane] : P_NONE;
+                const bool live = !P_DEAD(w);
+                const uint32_t lm = __ballot_sync(FULLMASK, live);
+                bool hit = false;
+                if (live) {
+                    const bool decoy = P_KIND(w) >= K_D_APACHE && P_KIND(w) <= K_D_VSFTPD;
+                    const uint32_t j = p0 + 2u * (uint32_t)__popc(lm & ((1u << lane) - 1u)) + (decoy ? 0u : 1u);
+                    const uint4 v = philox_block(c, actor, j >> 2);
+                    hit = f64_from_word(u4_word(v, j & 3u)) <= (decoy ? 0.5 : 0.1);
+                }
+                rep |= (int)__any_sync(FULLMASK, hit);
+                p0 += 2u * (uint32_t)__popc(lm);
             }
-        }
+            ctr_set(x, actor, p0);
+        } else rep = dd_tape(c, actor, h);
         if (rep) obs_entry(c, r, 0, h, 1, 0, 0, 0);
         return SUCC_TRUE;
     }
     case AC_EXPLOIT: { /* ExploitRemoteService.py:149-202 */
         if (si < 0 || !S_abs) return SUCC_FALSE;
         int target = a.host, src = S_host;
-        int pe = ports_find(c, r, a.session, target);
-        if (pe < 0) return SUCC_FALSE;
-        const int ports = (int)PT_MASK(WC(c)->k->ports[pe]);
+        const uint32_t pd_target = WC(c)->k->pdir[target], pmax_target = WC(c)->k->pmax[target];    /* requested ahead of the port-table scan (all cold) */
+        uint32_t pw;
+        if (ports_find(c, r, a.session, target, &pw) < 0) return SUCC_FALSE;
+        const int ports = (int)PT_MASK(pw);
         if (blocking(s, src, target)) return SUCC_FALSE;
         enum { X_HTTP, X_HTTPS, X_SSH, X_SQL, X_HARAKA };
         int opt[5], w10[5], no = 0;   /* DefaultExploitActionSelector :37-69, weights x10 */
@@ -1202,7 +1258,7 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
            ExploitAction.py:178-200 / SSHBruteForce.py:24-84 */
         int vk = -1;
         {
-            const uint32_t *pp_target = PROCS(c, target); const int np_target = NPROC(c, target);
+            const uint32_t *pp_target = WC(c)->k->parena + PD_OFF(pd_target); const int np_target = (int)PD_CNT(pd_target);
             _Pragma("unroll 1") for (int base = 0; base < np_target && vk < 0; base += 32) {
                 const uint32_t w = base + lane < np_target ? pp_target[base + lane] : P_NONE;
                 const int k = (int)P_KIND(w);
@@ -1219,11 +1275,22 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
             }
         }
         if (sel == X_SSH) {   /* SSHBruteForce.execute SSHBruteForce.py:24-84 */
-            int hops[12], nh = route(src, target, hops);
-            _Pragma("unroll 1") for (int i = 0; i < nh; i++) if (0.05 < rng_f64(c, actor, ST_SSH_HOP, 0)) s->ev[hops[i]] |= EV_NET;
+            const int nh = route_len(src, target);
+            if (g_blk.rng_mode == 1) ssh_hops_tape(c, actor, src, target, nh);
+            else {    /* lane i takes the i-th hop and the i-th next word of the stream (the same words the serial loop would take) */
+                Scratch *x = SCR(c);
+                const uint32_t p0 = ctr_get(x, actor);
+                if (lane < nh) {
+                    const uint32_t j = p0 + (uint32_t)lane;
+                    const uint4 v = philox_block(c, actor, j >> 2);
+                    if (0.05 < f64_from_word(u4_word(v, j & 3u))) s->ev[route_hop(src, target, nh, lane)] |= EV_NET;
+                }
+                __syncwarp();
+                ctr_set(x, actor, p0 + (uint32_t)nh);
+            }
             if (vk < 0) return SUCC_FALSE;
             s->ev[target] |= EV_NET;
-            int pid = exploit_new_session(c, r, target);
+            int pid = exploit_new_session(c, r, target, pd_target, pmax_target);
             ev_procpid(c, target, pid);
             obs_entry(c, r, 1, target, 1, 0, 1, 1);
             obs_entry(c, r, 1, src, 1, 0, 0, 0);
@@ -1237,7 +1304,7 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
         if (!(sel == X_SQL || decoy)) return SUCC_FALSE;
         if (0.0 >= rng_f64(c, actor, ST_EXP_SUCC, 0)) return SUCC_FALSE;
         if (decoy) { s->ev[target] |= EV_NET; return SUCC_FALSE; }
-        int pid = exploit_new_session(c, r, target);
+        int pid = exploit_new_session(c, r, target, pd_target, pmax_target);
         if (rng_f64(c, actor, ST_EXP_DETECT, 0) > 0.05) ev_procpid(c, target, pid);
         obs_entry(c, r, 1, target, 1, 0, 1, 1);
         obs_entry(c, r, 1, src, 1, 0, 0, 0);
@@ -1245,19 +1312,27 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
     }
     case AC_PRIVESC: { /* PrivilegeEscalate.py:127-179 */
         const int h = a.host;
+        const uint32_t pd_h = WC(c)->k->pdir[h];       /* cold; requested ahead of the pool scan */
+        /* one pass over the pool: how many sessions the agent holds on the host, and the first root one among them */
         auto on_host = [=](uint32_t w, uint32_t f) { return SF_AGENT(f) == (uint32_t)r && S_HOST(w) == (uint32_t)h; };
-        int n = 0;
-        _Pragma("unroll 1") for (int i = lane; i < s->n_sess; i += 32) n += on_host(s->sess[i], s->sessf[i]);
-        n = __reduce_add_sync(FULLMASK, n);
+        int n = 0, tgt = -1;
+        const int ns = s->n_sess;
+        _Pragma("unroll 1") for (int base = 0; base < ns; base += 32) {
+            const int i = base + lane;
+            const uint32_t f = i < ns ? (uint32_t)s->sessf[i] : 0u;
+            const bool o = i < ns && on_host(s->sess[i], f);
+            const uint32_t om = __ballot_sync(FULLMASK, o), rm = __ballot_sync(FULLMASK, o && SF_ROOT(f));
+            n += __popc(om);
+            if (tgt < 0 && rm) tgt = base + __ffs(rm) - 1;
+        }
         if (n == 0) return SUCC_FALSE;
-        int tgt = sess_first(s, [=](uint32_t w, uint32_t f) { return on_host(w, f) && SF_ROOT(f); });
         if (tgt < 0) {
             int pk = (int)rng_int(c, actor, ST_PRIV_SESS, (uint32_t)n);
             tgt = sess_kth(s, pk, on_host);
             if (si < 0 || !S_abs) return SUCC_FALSE;
             s->sessf[tgt] |= 1u << 4;      /* EscalateAction.__upgrade_session EscalateAction.py:54-87 */
-            int pi = proc_find(c, h, S_PID(s->sess[tgt]));
-            if (pi >= 0) PROCS(c, h)[pi] |= P_ROOTBIT; else fail(c, CC4_E_UNREACHABLE);
+            int pi = proc_find(c, S_PID(s->sess[tgt]), pd_h);
+            if (pi >= 0) (WC(c)->k->parena + PD_OFF(pd_h))[pi] |= P_ROOTBIT; else fail(c, CC4_E_UNREACHABLE);
         }
         obs_entry(c, r, 0, h, 0, 0, 0, 1);
         if (SF_ABS(s->sessf[tgt])) know_session(c, r, S_ID(s->sess[tgt]));

@@ -987,6 +987,11 @@ static int exec_red(cc4o_env *e, int r, const act_t *a)
         int rep = 0;
         for (int i = 0; i < h->nproc; i++) {
             int decoy = h->procs[i].kind >= K_D_APACHE && h->procs[i].kind <= K_D_VSFTPD;
+            if (e->rng_mode != 1) {     /* production mode: both words are spent for every process (the engine takes them lane-parallel) */
+                double u1 = rng_f64(e, actor, ST_DD_TP, 0), u2 = rng_f64(e, actor, ST_DD_FP, 0);
+                if (decoy ? u1 <= 0.5 : u2 <= 0.1) rep = 1;
+                continue;
+            }
             if (rng_f64(e, actor, ST_DD_TP, 0) <= 0.5 && decoy) rep = 1;
             else if (rng_f64(e, actor, ST_DD_FP, 0) <= 0.1 && !decoy) rep = 1;
         }

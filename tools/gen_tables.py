@@ -36,3 +36,35 @@ for ph in range(3):
     gone = {frozenset(x) for x in rm[ph]}
     comms.append(pairs_to_masks([p for p in complete if frozenset(p) not in gone]))
 print("c_comms_adj:\n" + fmt(comms))
+
+# c_route[src subnet][dst subnet]: subnets whose routers lie on the tree path (Action.py:101-117, topology
+# EnterpriseScenarioGenerator.py:373-416), 4 bits each from bit 0, count in bits 28-31; the internet "router" is subnet 8
+parent = {RZA: INT, OZA: RZA, RZB: INT, OZB: RZB, CON: INT, PAZ: INT, ADM: PAZ, OFF: PAZ, INT: None}
+
+
+def chain(v):
+    out = []
+    while v is not None:
+        out.append(v)
+        v = parent[v]
+    return out
+
+
+def route(a, b):
+    ca, cb = chain(a), chain(b)
+    ia, ib = len(ca) - 1, len(cb) - 1
+    while ia > 0 and ib > 0 and ca[ia - 1] == cb[ib - 1]:
+        ia -= 1
+        ib -= 1
+    return ca[:ia + 1] + cb[:ib][::-1]
+
+
+rows = []
+for a in range(9):
+    row = []
+    for b in range(9):
+        p = route(a, b)
+        assert len(p) <= 5
+        row.append(sum(v << (4 * i) for i, v in enumerate(p)) | len(p) << 28)
+    rows.append(row)
+print("c_route:\n" + ",\n".join("    { " + ", ".join(f"0x{v:08X}u" for v in r) + " }" for r in rows))
