@@ -250,7 +250,8 @@ def main():
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()      # sampled through both timed regions (device-resident steps, then the host-buffer steps)
     h2d = n * N_BLUE * 4
-    d2h = n * (578 + 4 + 1)
+    expand = os.environ.get("CC4_HOST_EXPAND", "1")[:1] != "0"
+    d2h = n * ((80 if expand else 578) + 4 + 1)     # observation rows cross PCIe as 80-byte bit rows and are expanded on the host
 
     t_ms = torch.tensor([ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
     score = torch.stack([ret.sum(), (ret * ret).sum(), torch.tensor(float(n), dtype=torch.float64, device=dev)])
@@ -274,7 +275,8 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": total_envs * args.e2e_steps * N_BLUE / (e2e_ms / 1e3), "unit": "agent-steps/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
-                    "api": "BatchedCC4.step_host(actions_pinned, compact=True) -> cc4_step_host: obs uint8 [N,578] (92 x 4 + 210, the reference's unpadded vectors) + reward f32 [N] + done u8 [N] in pinned host memory"},
+                    "api": "BatchedCC4.step_host(actions_pinned, compact=True) -> cc4_step_host: obs uint8 [N,578] (92 x 4 + 210, the reference's unpadded vectors) + reward f32 [N] + done u8 [N] in pinned host memory",
+                    "obs_over_pcie": "bit rows uint32 [N,20], expanded to the uint8 rows by cc4_step_host's host threads inside the timed region" if expand else "uint8 rows"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if n == 65536 else None, "peak_source": which, "kernel": "k_step",
                          "kernel_ms": kernel_ms, "bytes_per_env_step": b_step,

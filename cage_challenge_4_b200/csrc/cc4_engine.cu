@@ -10,9 +10,15 @@
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "cc4_device.cuh"
 
@@ -118,14 +124,16 @@ __constant__ uint32_t c_obs_fixed[3][7] = {
     { 0x6D80080, 0x7FC0010, 0x6400100, 0x3FC0020, 0x0C40001, 0x0E00008, 0x1C00040 },
     { 0x6800080, 0x5FC0010, 0x6D80100, 0x7FC0020, 0x0C40001, 0x0E00008, 0x1C00040 } };
 /* compact: the five vectors without padding, 92 + 92 + 92 + 92 + 210 bytes per episode (CC4_STEP_OBS_COMPACT) */
-__device__ void w_write_obs(const Cc4Dyn *s, Scratch *x, uint8_t *obs_base /* [n][5][210] or [n][578] */, int env, bool compact = false)
+/* as_bits: the compact row as a bit string, uint32 [n][20] (CC4_STEP_OBS_BITS): words 0-18 = entries, word 19 = mission phase */
+__device__ void w_write_obs(const Cc4Dyn *s, Scratch *x, uint8_t *obs_base /* [n][5][210] or [n][578] or uint32 [n][20] */, int env, bool compact = false, bool as_bits = false)
 {
     const int lane = lane_id();
     uint32_t *bits = x->obsbits;
+    if (as_bits) compact = true;
     const int row_bytes = compact ? CC4_OBS_COMPACT_LEN : OBS_BYTES;
     const int vec_stride = compact ? 92 : CC4_OBS_LEN;      /* agents 0-3 have 92 entries, so agent b starts at 92 b either way for b <= 4 */
     const size_t goff = (size_t)env * row_bytes;
-    const int mis = (int)(goff & 15);
+    const int mis = as_bits ? 0 : (int)(goff & 15);
     /* per-subnet 16-bit host masks: malicious-process / network-connection alerts (old + current events).  Lane L looks
        at hosts 4L..4L+3 (one word of ev), the four lanes of a quad cover one subnet. */
     const uint32_t evw = reinterpret_cast<const uint32_t *>(s->ev)[lane];
@@ -158,6 +166,12 @@ __device__ void w_write_obs(const Cc4Dyn *s, Scratch *x, uint8_t *obs_base /* [n
         bits_or(bits, mis + vec_stride * b + 1 + 59 * (b == 4 ? 3 : 1), (uint64_t)m);
     }
     __syncwarp();
+    if (as_bits) {      /* the string itself: 19 words + the mission phase, one 80-byte row per episode */
+        uint32_t *row = reinterpret_cast<uint32_t *>(obs_base) + (size_t)env * CC4_OBS_BITS_WORDS;
+        if (lane < CC4_OBS_BITS_WORDS) row[lane] = lane < CC4_OBS_BITS_WORDS - 1 ? bits[lane] : (uint32_t)s->phase;
+        __syncwarp();
+        return;
+    }
     /* expand and store: global byte (line start + j) = bit j of the string.  A lane turns 16 bits into one 16-byte line in
        registers (4 bits -> 4 bytes by one multiply) and stores it with one 128-bit store; element 0 of every vector is
        the mission phase, not a bit, and is patched in; the partial first and last line go out by halfwords. */
@@ -393,8 +407,8 @@ __device__ __forceinline__ void ph_policy(Cx c, int e, bool exists, bool live, i
 }
 
 /* ---- phase 2: filter_actions (:466-486), then blue execution ---- */
-__device__ __forceinline__ void ph_blue_exec(Cx c);
-__device__ __forceinline__ void ph_blue(Cx c, bool with_exec = true)
+__device__ __forceinline__ void ph_blue_exec(Cx c, uint32_t agents = 0x1Fu, bool with_prio1 = true);
+__device__ __forceinline__ void ph_blue(Cx c, bool with_exec = true, uint32_t agents = 0x1Fu)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     const int lane = lane_id();
@@ -418,9 +432,11 @@ __device__ __forceinline__ void ph_blue(Cx c, bool with_exec = true)
         if (lane == 0) x->sess_moved = 0;
     }
     __syncwarp();
-    if (with_exec) ph_blue_exec(c);
+    if (with_exec) ph_blue_exec(c, agents);
 }
-__device__ __forceinline__ void ph_blue_exec(Cx c)
+/* `agents`: the blue agents whose ordinary actions run in this call (the phase can be cut by agent, CC4_BLUE_PARTS); the
+   priority-1 actions of ALL agents run in the call that has with_prio1 */
+__device__ __forceinline__ void ph_blue_exec(Cx c, uint32_t agents, bool with_prio1)
 {
     Scratch *x = SCR(c);
     const int lane = lane_id();
@@ -429,7 +445,7 @@ __device__ __forceinline__ void ph_blue_exec(Cx c)
     {
         const uint32_t code = lane < CC4_NBLUE ? IP_CODE(x->subw[lane]) : (uint32_t)AC_SLEEP;
         const bool prio1 = code == AC_BLOCK || code == AC_ALLOW;
-        uint32_t first = __ballot_sync(0xFFFFFFFFu, prio1), then = __ballot_sync(0xFFFFFFFFu, !prio1 && code != AC_SLEEP && code != AC_ANALYSE);
+        uint32_t first = with_prio1 ? __ballot_sync(0xFFFFFFFFu, prio1) : 0u, then = __ballot_sync(0xFFFFFFFFu, !prio1 && code != AC_SLEEP && code != AC_ANALYSE) & agents;
         while (first) { const int b = __ffs(first) - 1; first &= first - 1; exec_blue(c, b, x->subw[b]); }
         while (then) {
             const int b = __ffs(then) - 1; then &= then - 1;
@@ -513,14 +529,16 @@ __device__ __forceinline__ void ph_phishing(Cx c)
         __syncwarp();
     }
 }
-__device__ __forceinline__ void ph_red(Cx c, bool with_phishing = true)
+/* `agents`: the red agents this call handles (the phase can be cut by agent, CC4_RED_PARTS: the same code runs again on
+   the next agents after a block barrier, which halves the heaviest work item of the phase) */
+__device__ __forceinline__ void ph_red(Cx c, bool with_phishing = true, uint32_t agents = 0x3Fu)
 {
     Scratch *x = SCR(c);
     if (with_phishing) ph_phishing(c);
     {
         const int lane = lane_id();
         bool real = false;
-        if (lane < CC4_NRED && !x->dropped[A_RED0 + lane]) {
+        if (lane < CC4_NRED && (agents >> lane & 1u) && !x->dropped[A_RED0 + lane]) {
             const uint32_t aw = x->subw[A_RED0 + lane], code = IP_CODE(aw);
             if (code == AC_SLEEP) obs_push(c, lane, SUCC_UNKNOWN, true, aw);        /* nothing to execute: the lane files the observation */
             else if (code == AC_INVALID) obs_push(c, lane, SUCC_FALSE, true, aw);
@@ -615,11 +633,18 @@ __device__ __forceinline__ void ph_finish(Cx c, const uint8_t *msgs /* [5] or nu
  * (Measured alternative, r01k: per-phase work queues without block barriers — a warp that finishes phase p on one episode
  * goes on to phase p+1 of whatever episode is ready — raise warp utilisation but let two phases be live at once; the
  * instruction-cache misses cost more than the idle time saved: 1.08 ms against 0.97 ms per tick.) */
+#ifndef CC4_RED_PARTS
+#define CC4_RED_PARTS 1         /* k_step: the red phase as 1, 2 or 3 passes over the episodes (2 or 3: by agent, a block barrier in between) */
+#endif
+#ifndef CC4_BLUE_PARTS
+#define CC4_BLUE_PARTS 1
+#endif
 #ifndef CC4_STATIC_ASSIGN
 #define CC4_STATIC_ASSIGN 0     /* 1: episode e of a block is always handled by warp e % warps (tuning knob; default: shared counter) */
 #endif
-template <class F> __device__ __forceinline__ void each_episode(int ph, int first, int n_local, int *next, F f, const PhaseOrder *order = nullptr)
+template <class F> __device__ __forceinline__ void each_episode(int ph, int first, int n_local, int *next, F f, const PhaseOrder *order = nullptr, int ctr = -1)
 {
+    if (ctr < 0) ctr = ph;      /* which work counter the phase uses (the parts of a cut phase share `ph`) */
 #ifdef CC4_PHASE_CLOCKS
     const long long tb0 = clock64();
 #endif
@@ -628,7 +653,7 @@ template <class F> __device__ __forceinline__ void each_episode(int ph, int firs
 #else
     _Pragma("unroll 1") for (;;) {
         int e = 0;
-        if (lane_id() == 0) e = atomicAdd(&next[ph], 1);
+        if (lane_id() == 0) e = atomicAdd(&next[ctr], 1);
         e = __shfl_sync(0xFFFFFFFFu, e, 0);
         if (e >= n_local) break;
         if (order) e = order_get(order, e);
@@ -716,14 +741,14 @@ struct StepIO { const int32_t *actions; const uint8_t *msgs; uint8_t *obs; float
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
 k_step(Params p, int env0, int env_end, int epb, StepIO io)
 {
-    __shared__ int next[N_PHASES + 4];
+    __shared__ int next[N_PHASES + 6];
     __shared__ uint8_t ng_s[64];
     __shared__ short gend[64];
     __shared__ PhaseOrder ord_blue, ord_red;
     __shared__ __align__(8) uint64_t ld_bar[64];
     const int first = env0 + blockIdx.x * epb, n_local = min(epb, env_end - first);
     init_block_ctx(p);
-    if (threadIdx.x < N_PHASES + 4) next[threadIdx.x] = 0;
+    if (threadIdx.x < N_PHASES + 6) next[threadIdx.x] = 0;
     if (threadIdx.x < 4) { ord_blue.cnt[threadIdx.x] = 0; ord_red.cnt[threadIdx.x] = 0; }
     if ((int)threadIdx.x < n_local) mbar_init(&ld_bar[threadIdx.x], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -746,7 +771,7 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
         const int env = first + e;
         ph_finish(c, io.msgs ? io.msgs + (size_t)env * 5 : nullptr, (io.flags & CC4_STEP_REWARD) && io.reward ? io.reward + env : nullptr, false,
                   io.done ? io.done + env : nullptr);
-        if ((io.flags & CC4_STEP_OBS) && io.obs) w_write_obs(DYN(c), SCR(c), io.obs, env, (io.flags & CC4_STEP_OBS_COMPACT) != 0);
+        if ((io.flags & CC4_STEP_OBS) && io.obs) w_write_obs(DYN(c), SCR(c), io.obs, env, (io.flags & CC4_STEP_OBS_COMPACT) != 0, (io.flags & CC4_STEP_OBS_BITS) != 0);
         __syncwarp();
         if (lane_id() == 0) bulk_store(p.dyn + env, DYN(c), (uint32_t)sizeof(Cc4Dyn));
     };
@@ -757,7 +782,12 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
     each_episode(N_PHASES + 1, first, n_local, next, [&](Cx c, int) { ph_blue(c, false); });
     each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { ph_blue_exec(c); }, &ord_blue);
 #else
+#if CC4_BLUE_PARTS == 2
+    each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { ph_blue(c, true, 0x07u); }, &ord_blue);
+    each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { ph_blue_exec(c, 0x18u, false); }, &ord_blue, N_PHASES + 3);
+#else
     each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { ph_blue(c); }, &ord_blue);
+#endif
 #endif
     green_items(PH_GREEN, first, n_local, next, ng_s, gend);
 #if CC4_SPLIT & 2
@@ -769,7 +799,16 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
 #if CC4_MERGE & 1
     each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c); ph_reassign(c); }, &ord_red);
 #else
+#if CC4_RED_PARTS == 2
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c, !(CC4_SPLIT & 2), 0x07u); }, &ord_red);
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c, false, 0x38u); }, &ord_red, N_PHASES + 4);
+#elif CC4_RED_PARTS == 3
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c, !(CC4_SPLIT & 2), 0x03u); }, &ord_red);
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c, false, 0x0Cu); }, &ord_red, N_PHASES + 4);
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c, false, 0x30u); }, &ord_red, N_PHASES + 5);
+#else
     each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c, !(CC4_SPLIT & 2)); }, &ord_red);
+#endif
     each_episode(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { ph_reassign(c); });
 #endif
 #if CC4_MERGE & 2
@@ -985,12 +1024,89 @@ static int set_err(int code, const char *fmt, const char *detail)
 }
 #define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return set_err(CC4_ERR_CUDA, #expr ": %s", cudaGetErrorString(e_)); } while (0)
 
+/* ---- host side of cc4_step_host: observation rows arrive as bit rows and are expanded to bytes by a few threads ---- */
+static uint64_t g_spread[256];      /* byte -> its eight bits as eight bytes (bit i -> byte i) */
+static std::once_flag g_spread_once;
+static void spread_init() { for (int v = 0; v < 256; v++) { uint64_t w = 0; for (int i = 0; i < 8; i++) w |= (uint64_t)(v >> i & 1) << (8 * i); g_spread[v] = w; } }
+/* bit rows uint32 [cnt][20] -> uint8 [cnt][578] (compact) or [cnt][5][210] (padded): the layouts w_write_obs produces */
+static void expand_rows(const uint32_t *rows, uint8_t *dst, size_t cnt, bool compact)
+{
+    for (size_t e = 0; e < cnt; e++) {
+        const uint32_t *row = rows + e * CC4_OBS_BITS_WORDS;
+        const uint8_t *b = reinterpret_cast<const uint8_t *>(row);
+        const uint8_t ph = (uint8_t)row[CC4_OBS_BITS_WORDS - 1];
+        if (compact) {
+            uint8_t *o = dst + e * CC4_OBS_COMPACT_LEN;
+            for (int k = 0; k < 72; k++) memcpy(o + 8 * k, &g_spread[b[k]], 8);
+            o[576] = b[72] & 1u; o[577] = (b[72] >> 1) & 1u;
+            o[0] = o[92] = o[184] = o[276] = o[368] = ph;
+        } else {
+            uint8_t *o = dst + e * (size_t)(CC4_N_BLUE * CC4_OBS_LEN);
+            for (int a = 0; a < CC4_N_BLUE; a++) {
+                const int len = a == 4 ? 210 : 92, bit0 = 92 * a;
+                uint8_t *oa = o + a * CC4_OBS_LEN;
+                int j = 0;
+                for (; j + 8 <= len; j += 8) {      /* eight entries from an unaligned 16-bit window (rows are 80 bytes: no read past the end) */
+                    const int pos = bit0 + j;
+                    uint16_t w16; memcpy(&w16, b + (pos >> 3), 2);
+                    memcpy(oa + j, &g_spread[(w16 >> (pos & 7)) & 0xFFu], 8);
+                }
+                for (; j < len; j++) { const int pos = bit0 + j; oa[j] = (b[pos >> 3] >> (pos & 7)) & 1u; }
+                oa[0] = ph;
+                memset(oa + len, 0, CC4_OBS_LEN - len);
+            }
+        }
+    }
+}
+struct ExpandJob { const uint32_t *rows; uint8_t *dst; size_t cnt; bool compact; };
+struct HostPool {
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv_work, cv_done;
+    std::deque<ExpandJob> q;
+    size_t pending = 0;
+    bool stop = false;
+    void run()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv_work.wait(lk, [&] { return stop || !q.empty(); });
+            if (q.empty()) return;      /* stop */
+            ExpandJob j = q.front(); q.pop_front();
+            lk.unlock();
+            expand_rows(j.rows, j.dst, j.cnt, j.compact);
+            lk.lock();
+            if (--pending == 0) cv_done.notify_all();
+        }
+    }
+    void start(int n) { for (int i = 0; i < n; i++) th.emplace_back([this] { run(); }); }
+    void submit(const uint32_t *rows, uint8_t *dst, size_t cnt, bool compact, size_t row_bytes)
+    {   /* one job per thread */
+        const size_t parts = th.size(), per = (cnt + parts - 1) / parts;
+        std::lock_guard<std::mutex> lk(m);
+        for (size_t o = 0; o < cnt; o += per) { q.push_back({ rows + o * CC4_OBS_BITS_WORDS, dst + o * row_bytes, cnt - o < per ? cnt - o : per, compact }); pending++; }
+        cv_work.notify_all();
+    }
+    void wait() { std::unique_lock<std::mutex> lk(m); cv_done.wait(lk, [&] { return pending == 0; }); }
+    ~HostPool()
+    {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv_work.notify_all();
+        for (auto &t : th) t.join();
+    }
+};
+#define CC4_MAX_CHUNKS 16
+
 struct cc4_handle {
     Params p;
     int device, n_sm;
     uint64_t launches;
     int32_t *stage_actions; uint8_t *stage_msgs, *stage_obs, *stage_mask, *stage_done; float *stage_reward;   /* device staging for cc4_step_host */
     cudaStream_t pipe[2]; cudaEvent_t ev_in, ev_out[2];   /* chunk pipeline of cc4_step_host */
+    cudaEvent_t ev_chunk[CC4_MAX_CHUNKS];                 /* ... chunk k's outputs are on the host */
+    uint32_t *host_bits;                                  /* pinned: the bit rows of the batch */
+    HostPool *pool;
+    int host_expand;                                      /* 0: byte rows over PCIe (CC4_HOST_EXPAND=0) */
 };
 
 extern "C" const char *cc4_last_error(void) { return g_err; }
@@ -1006,6 +1122,7 @@ extern "C" int cc4_create(int n_envs, int device, uint64_t seed, uint64_t first_
     h->p.n_envs = n_envs; h->p.steps = steps; h->p.rng_mode = rng_mode;
     CUDA_TRY(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device));
     h->p.k0 = (uint32_t)seed; h->p.k1hi = (uint32_t)(seed >> 32); h->p.first_episode = first_episode;
+    { const char *e = getenv("CC4_HOST_EXPAND"); h->host_expand = !(e && e[0] == '0'); }
     CUDA_TRY(cudaMalloc(&h->p.dyn, sizeof(Cc4Dyn) * (size_t)n_envs));
     CUDA_TRY(cudaMalloc(&h->p.stat, sizeof(Cc4Stat) * (size_t)n_envs));
     CUDA_TRY(cudaMalloc(&h->p.cold, sizeof(Cc4Cold) * (size_t)n_envs));
@@ -1025,6 +1142,9 @@ extern "C" int cc4_destroy(cc4_handle *h)
     for (int i = 0; i < 2; i++) { if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]); if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]); }
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     cudaFree(h->stage_actions); cudaFree(h->stage_msgs); cudaFree(h->stage_obs); cudaFree(h->stage_mask); cudaFree(h->stage_done); cudaFree(h->stage_reward);
+    for (int i = 0; i < CC4_MAX_CHUNKS; i++) if (h->ev_chunk[i]) cudaEventDestroy(h->ev_chunk[i]);
+    if (h->host_bits) cudaFreeHost(h->host_bits);
+    delete h->pool;
     delete h;
     return CC4_OK;
 }
@@ -1144,11 +1264,65 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
     CUDA_TRY(cudaEventRecord(h->ev_in, user));
     for (int i = 0; i < 2; i++) CUDA_TRY(cudaStreamWaitEvent(h->pipe[i], h->ev_in, 0));
     const bool want_obs = obs_host && (flags & CC4_STEP_OBS), want_rew = reward_host && (flags & CC4_STEP_REWARD);
-    const size_t obs_row = (flags & CC4_STEP_OBS_COMPACT) ? CC4_OBS_COMPACT_LEN : CC4_N_BLUE * CC4_OBS_LEN;
+    const bool raw_bits = (flags & CC4_STEP_OBS_BITS) != 0, compact = (flags & CC4_STEP_OBS_COMPACT) != 0;
+    const size_t obs_row = raw_bits ? CC4_OBS_BITS_WORDS * sizeof(uint32_t) : compact ? CC4_OBS_COMPACT_LEN : CC4_N_BLUE * CC4_OBS_LEN;
     size_t chunk = (n + CC4_HOST_CHUNKS - 1) / CC4_HOST_CHUNKS;
     {   /* whole waves of full blocks per chunk */
         size_t wave = (size_t)h->n_sm * EPB_MAX;
         chunk = (chunk + wave - 1) / wave * wave;
+    }
+    if (want_obs && !raw_bits && h->host_expand) {
+        /* byte rows wanted: the kernel writes bit rows (80 B per episode instead of 578 / 1 050), they cross PCIe into pinned
+           staging, and the pool expands chunk k on the host while the chunks after it are still on the device */
+        if (!h->pool) {
+            std::call_once(g_spread_once, spread_init);
+            int nt = 0;
+            if (const char *e = getenv("CC4_HOST_THREADS")) nt = atoi(e);
+            if (nt <= 0) {
+                int hw = (int)std::thread::hardware_concurrency(), lw = 1;
+                if (const char *e = getenv("LOCAL_WORLD_SIZE")) lw = atoi(e) > 0 ? atoi(e) : 1;
+                nt = hw / lw; if (nt > 16) nt = 16;
+            }
+            if (nt < 1) nt = 1;
+            h->pool = new (std::nothrow) HostPool();
+            if (!h->pool) return set_err(CC4_ERR_STATE, "cc4_step_host: out of host memory%s", "");
+            h->pool->start(nt);
+            CUDA_TRY(cudaHostAlloc(&h->host_bits, n * CC4_OBS_BITS_WORDS * sizeof(uint32_t), cudaHostAllocDefault));
+            for (int i = 0; i < CC4_MAX_CHUNKS; i++) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
+        }
+        if ((n + chunk - 1) / chunk > CC4_MAX_CHUNKS) return set_err(CC4_ERR_STATE, "cc4_step_host: too many chunks%s", "");
+        uint32_t *stage_bits = reinterpret_cast<uint32_t *>(h->stage_obs);      /* the byte staging area is larger than the bit rows */
+        const int kflags = (flags & ~CC4_STEP_OBS_COMPACT) | CC4_STEP_OBS_BITS;
+        int k = 0, nch = 0;
+        for (size_t e0 = 0; e0 < n; e0 += chunk, k ^= 1, nch++) {
+            size_t cnt = n - e0 < chunk ? n - e0 : chunk;
+            cudaStream_t st = h->pipe[k];
+            CUDA_TRY(cudaMemcpyAsync(h->stage_actions + e0 * 5, actions_host + e0 * 5, cnt * 5 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            if (msgs_host) CUDA_TRY(cudaMemcpyAsync(h->stage_msgs + e0 * 5, msgs_host + e0 * 5, cnt * 5, cudaMemcpyHostToDevice, st));
+            const int epb = episodes_per_block(h, cnt), blocks = (int)((cnt + epb - 1) / epb);
+            StepIO io = { h->stage_actions, msgs_host ? h->stage_msgs : nullptr, reinterpret_cast<uint8_t *>(stage_bits),
+                          want_rew ? h->stage_reward : nullptr, done_host ? h->stage_done : nullptr, kflags };
+            k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * (size_t)epb, st>>>(h->p, (int)e0, (int)(e0 + cnt), epb, io);
+            h->launches++;
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(h->host_bits + e0 * CC4_OBS_BITS_WORDS, stage_bits + e0 * CC4_OBS_BITS_WORDS, cnt * CC4_OBS_BITS_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            if (want_rew) CUDA_TRY(cudaMemcpyAsync(reward_host + e0, h->stage_reward + e0, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+            if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host + e0, h->stage_done + e0, cnt, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaEventRecord(h->ev_chunk[nch], st));
+        }
+        int c = 0;
+        cudaError_t err = cudaSuccess;
+        for (size_t e0 = 0; e0 < n; e0 += chunk, c++) {
+            size_t cnt = n - e0 < chunk ? n - e0 : chunk;
+            err = cudaEventSynchronize(h->ev_chunk[c]);
+            if (err != cudaSuccess) break;
+            h->pool->submit(h->host_bits + e0 * CC4_OBS_BITS_WORDS, obs_host + e0 * obs_row, cnt, compact, obs_row);
+        }
+        h->pool->wait();
+        if (err != cudaSuccess) return set_err(CC4_ERR_CUDA, "cc4_step_host: %s", cudaGetErrorString(err));
+        for (int i = 0; i < 2; i++) { CUDA_TRY(cudaEventRecord(h->ev_out[i], h->pipe[i])); CUDA_TRY(cudaStreamWaitEvent(user, h->ev_out[i], 0)); }
+        CUDA_TRY(cudaStreamSynchronize(user));
+        return CC4_OK;
     }
     int k = 0;
     for (size_t e0 = 0; e0 < n; e0 += chunk, k ^= 1) {
@@ -1168,6 +1342,15 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
     }
     for (int i = 0; i < 2; i++) { CUDA_TRY(cudaEventRecord(h->ev_out[i], h->pipe[i])); CUDA_TRY(cudaStreamWaitEvent(user, h->ev_out[i], 0)); }
     CUDA_TRY(cudaStreamSynchronize(user));
+    return CC4_OK;
+}
+
+/* host-only helper: bit rows -> byte rows, single-threaded (what the pool of cc4_step_host runs per slice) */
+extern "C" int cc4_expand_obs_bits(const uint32_t *rows_host, uint8_t *obs_host, size_t n_rows, int compact)
+{
+    if (!rows_host || !obs_host) return set_err(CC4_ERR_ARG, "cc4_expand_obs_bits: null%s", "");
+    std::call_once(g_spread_once, spread_init);
+    expand_rows(rows_host, obs_host, n_rows, compact != 0);
     return CC4_OK;
 }
 

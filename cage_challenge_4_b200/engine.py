@@ -20,7 +20,8 @@ N_BLUE, OBS_LEN, MASK_LEN = 5, 210, 242
 N_ACTIONS = (82, 82, 82, 82, 242)
 OBS_SIZES = (92, 92, 92, 92, 210)
 SLEEP_INDEX = (49, 49, 49, 49, 145)
-STEP_OBS, STEP_REWARD, STEP_ALL, STEP_OBS_COMPACT = 1, 2, 3, 4
+STEP_OBS, STEP_REWARD, STEP_ALL, STEP_OBS_COMPACT, STEP_OBS_BITS = 1, 2, 3, 4, 8
+OBS_BITS_WORDS = 20        # CC4_STEP_OBS_BITS: the compact row as 578 bits in 19 words + the mission phase in word 19
 OBS_COMPACT_LEN = 578      # 92 + 92 + 92 + 92 + 210: the five unpadded vectors back to back (CC4_STEP_OBS_COMPACT)
 OBS_COMPACT_OFF = (0, 92, 184, 276, 368, 578)
 
@@ -28,6 +29,17 @@ OBS_COMPACT_OFF = (0, 92, 184, 276, 368, 578)
 def split_compact(obs):
     """[N, 578] compact observations -> the five per-agent views [N, 92] x 4 + [N, 210] (BlueFlatWrapper.py:128-170)."""
     return [obs[:, OBS_COMPACT_OFF[b]:OBS_COMPACT_OFF[b + 1]] for b in range(N_BLUE)]
+
+
+def unpack_bits(rows: torch.Tensor) -> torch.Tensor:
+    """uint32 / int32 [N, 20] bit rows (CC4_STEP_OBS_BITS) -> uint8 [N, 578] compact observations, on the rows' device."""
+    w = rows.to(torch.int64) & 0xFFFFFFFF
+    sh = torch.arange(32, device=rows.device, dtype=torch.int64)
+    out = ((w[:, :OBS_BITS_WORDS - 1, None] >> sh) & 1).to(torch.uint8).reshape(rows.shape[0], -1)[:, :OBS_COMPACT_LEN].contiguous()
+    out[:, list(OBS_COMPACT_OFF[:N_BLUE])] = w[:, OBS_BITS_WORDS - 1, None].to(torch.uint8)
+    return out
+
+
 DRAW_DTYPE = np.dtype([("val", "<u8"), ("n", "<u2"), ("site", "u1"), ("kind", "u1"), ("pad", "<u4")])
 
 
@@ -156,6 +168,16 @@ class BatchedCC4:
         _native.check(self._L.cc4_step(self._h, actions.data_ptr(), mp, self._obs_compact.data_ptr(), self.reward.data_ptr(),
                                        self.done.data_ptr(), STEP_ALL | STEP_OBS_COMPACT, self._stream()), "cc4_step")
         return self._obs_compact, self.reward, self.done
+
+    def step_bits(self, actions: torch.Tensor, messages: torch.Tensor | None = None):
+        """step() with the observations as bit rows int32 [N, 20] on the device (CC4_STEP_OBS_BITS, 80 B per episode; see
+        unpack_bits): for device-side policies that take bits, and what step_host moves over PCIe."""
+        if getattr(self, "_obs_bits", None) is None:
+            self._obs_bits = torch.zeros((self.num_envs, OBS_BITS_WORDS), dtype=torch.int32, device=self.device)
+        mp = 0 if messages is None else messages.data_ptr()
+        _native.check(self._L.cc4_step(self._h, actions.data_ptr(), mp, self._obs_bits.data_ptr(), self.reward.data_ptr(),
+                                       self.done.data_ptr(), STEP_ALL | STEP_OBS_BITS, self._stream()), "cc4_step")
+        return self._obs_bits, self.reward, self.done
 
     def rollout(self, n_ticks: int, policy_seed: int = 0, reward_sum: torch.Tensor | None = None, flags: int = STEP_REWARD):
         rp = 0 if reward_sum is None else reward_sum.data_ptr()

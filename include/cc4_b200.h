@@ -48,6 +48,11 @@ enum {
                                     92 + 92 + 92 + 92 + 210 (what BlueFlatWrapper returns without pad_spaces, BlueFlatWrapper.py:128-170);
                                     45 % fewer bytes to move to the host */
 #define CC4_OBS_COMPACT_LEN 578
+#define CC4_STEP_OBS_BITS 8      /* with CC4_STEP_OBS: obs rows are uint32 [n_envs][20]: bit j of words 0-18 = entry j of the compact row
+                                    (every entry but the five mission-phase entries 0, 92, 184, 276, 368 is 0 / 1; those five bits are 0),
+                                    word 19 = the mission phase.  80 B per episode instead of 578: what cc4_step_host moves over PCIe
+                                    before it expands the rows on the host; a device-side policy can consume the rows as they are */
+#define CC4_OBS_BITS_WORDS 20
 
 /* One recorded RNG draw of the reference (tape mode; layout shared with oracle/cc4_oracle.h). */
 typedef struct {
@@ -102,9 +107,17 @@ int cc4_step(cc4_handle *h, const int32_t *actions_dev, const uint8_t *msgs_dev,
              uint8_t *done_dev, int flags, void *stream);
 
 /* Same call with HOST buffers: copies actions/messages host->device, steps, copies obs/reward/done back and
- * synchronises the stream (the e2e path bench.py times; host buffers should be pinned for full speed). */
+ * synchronises the stream (the e2e path bench.py times; host buffers should be pinned for full speed).  The batch is
+ * cut into chunks that are pipelined over two streams; observation rows cross PCIe as bit rows (CC4_STEP_OBS_BITS) and
+ * are expanded to the requested uint8 layout by a small pool of host threads (CC4_HOST_THREADS, default: the host's
+ * hardware threads / LOCAL_WORLD_SIZE, at most 16) while the next chunks are in flight; CC4_HOST_EXPAND=0 copies byte
+ * rows instead.  With CC4_STEP_OBS_BITS in `flags` the bit rows themselves are returned (obs_host = uint32 [n][20]). */
 int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const uint8_t *msgs_host, uint8_t *obs_host,
                   float *reward_host, uint8_t *done_host, int flags, void *stream);
+
+/* Host-only: expands bit rows uint32 [n_rows][20] (CC4_STEP_OBS_BITS) to uint8 [n_rows][578] (compact != 0) or
+ * [n_rows][5][210]; no device work.  For callers that fetch the bit rows themselves. */
+int cc4_expand_obs_bits(const uint32_t *rows_host, uint8_t *obs_host, size_t n_rows, int compact);
 
 /* n_ticks fused ticks with the synthetic uniform-random blue policy of the benchmark (indices drawn on device from
  * Philox keyed (policy_seed, episode, tick); BASELINE config "FiniteStateRed + random blue").  reward_sum_dev float

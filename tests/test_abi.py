@@ -51,3 +51,26 @@ def test_product_package_never_imports_the_oracle():
                     code = line.strip()
                     if code.startswith(("#include", "import ", "from ")) or "dlopen" in code or "CDLL" in code:
                         assert "oracle" not in code and "ref_harness" not in code, f"{f}: {code}"
+
+
+def test_host_expansion_of_bit_rows_matches_numpy():
+    """cc4_expand_obs_bits (host-only, what cc4_step_host's thread pool runs): bit rows -> compact and padded byte rows."""
+    import numpy as np
+    from cage_challenge_4_b200 import _native
+    L = _native.load()
+    g = np.random.default_rng(0)
+    n = 257
+    rows = g.integers(0, 2**32, (n, 20), dtype=np.uint64).astype(np.uint32)
+    rows[:, 19] = g.integers(0, 3, n)
+    bits = np.unpackbits(rows[:, :19].copy().view(np.uint8), axis=1, bitorder="little")[:, :578]
+    off = [0, 92, 184, 276, 368, 578]
+    want = bits.copy()
+    want[:, off[:5]] = rows[:, 19:20].astype(np.uint8)
+    got = np.full((n, 578), 7, dtype=np.uint8)
+    assert L.cc4_expand_obs_bits(rows.ctypes.data, got.ctypes.data, n, 1) == 0
+    assert np.array_equal(got, want)
+    padded = np.full((n, 5, 210), 7, dtype=np.uint8)
+    assert L.cc4_expand_obs_bits(rows.ctypes.data, padded.ctypes.data, n, 0) == 0
+    for b in range(5):
+        ln = off[b + 1] - off[b]
+        assert np.array_equal(padded[:, b, :ln], want[:, off[b]:off[b + 1]]) and not padded[:, b, ln:].any()

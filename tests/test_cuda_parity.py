@@ -310,6 +310,39 @@ def test_compact_observations_are_the_unpadded_vectors(n):
         assert torch.equal(o3, o2.cpu()) and torch.equal(r1.cpu(), r3) and torch.equal(r1, r2) and torch.equal(d1.cpu(), d3)
 
 
+@pytest.mark.parametrize("n", [3, 9473])
+def test_bit_row_observations_and_both_host_paths(n, monkeypatch):
+    """CC4_STEP_OBS_BITS: row = the compact row as bits + the mission phase; cc4_step_host moves these rows and expands them
+    on the host (default) or copies byte rows (CC4_HOST_EXPAND=0): all the same bytes, padded and compact."""
+    from cage_challenge_4_b200.engine import unpack_bits
+    a, b, c, d = (_engine(n, device=0, seed=6) for _ in range(4))
+    monkeypatch.setenv("CC4_HOST_EXPAND", "0")
+    e, f = (_engine(n, device=0, seed=6) for _ in range(2))
+    monkeypatch.delenv("CC4_HOST_EXPAND")
+    for x in (a, b, c, d, e, f):
+        x.reset()
+    g = np.random.default_rng(5)
+    for t in range(10):
+        acts = torch.from_numpy(np.stack([g.integers(0, k, n) for k in (82, 82, 82, 82, 242)], 1).astype(np.int32))
+        msgs = torch.from_numpy(g.integers(0, 256, (n, 5)).astype(np.uint8))
+        o1, r1, d1 = a.step_compact(acts.cuda(), msgs.cuda())
+        o2, r2, d2 = b.step_bits(acts.cuda(), msgs.cuda())
+        assert o2.shape == (n, 20) and torch.equal(unpack_bits(o2), o1) and torch.equal(r1, r2) and torch.equal(d1, d2)
+        o3 = c.step_host(acts.pin_memory(), msgs.pin_memory(), compact=True)[0]
+        o5 = e.step_host(acts.pin_memory(), msgs.pin_memory(), compact=True)[0]
+        assert torch.equal(o3, o1.cpu()) and torch.equal(o5, o1.cpu())
+        o4 = d.step_host(acts.pin_memory(), msgs.pin_memory())[0]
+        o6 = f.step_host(acts.pin_memory(), msgs.pin_memory())[0]
+        assert torch.equal(o4, o6)
+        for k, v in enumerate(split_compact_(o1.cpu())):
+            assert torch.equal(v, o4[:, k, :v.shape[1]]) and not o4[:, k, v.shape[1]:].any(), f"tick {t} agent {k}"
+
+
+def split_compact_(o):
+    from cage_challenge_4_b200.engine import split_compact
+    return split_compact(o)
+
+
 def test_config2_state_transition_only_4096_envs():
     """BASELINE configs[1]: 4 096 episodes, FiniteStateRed + random blue, observation / reward outputs OFF (flags = 0):
     the state trajectory is the same as with the outputs on, and sampled episodes match the oracle."""

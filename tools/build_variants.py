@@ -25,7 +25,7 @@ def bench(path, extra):
                        env=env, capture_output=True, text=True)
     try:
         j = json.loads(r.stdout.strip().split("\n")[-1])
-        return {"value": j["value"], "ms_per_step": j["ms_per_step"], "kernel_ms": j["roofline"]["kernel_ms"], "e2e": j["e2e"]["value"], "err": j["error_episodes"]}
+        return {"value": j["value"], "ms_per_step": j["ms_per_step"], "kernel_ms": j["roofline"]["kernel_ms"], "e2e": j["e2e"]["value"], "err": j["error_episodes"], "score": j["score"]["mean_return"]}
     except Exception as e:  # noqa: BLE001
         return {"error": str(e), "stderr": r.stderr[-400:]}
 
