@@ -291,6 +291,37 @@ __device__ CC4_INL2 double rng_f64(Cx c, int actor, int site, uint32_t n)
     return f64_from_word(rng_word(c, actor));
 }
 
+/* The red agents' serial draws (exec_red, re-election) in production mode: the stream position and the cached block of
+ * agent r are in the scratch, the fast path is a handful of shared-memory instructions inline, the Philox refill (once per
+ * four words; the first block comes from red_policy) is out of line.  Same words as rng_int / rng_f64 would deliver. */
+__device__ __noinline__ void red_refill(Cx c, int r, uint32_t b)
+{
+    Scratch *x = SCR(c);
+    const uint4 v = philox_block(c, A_RED0 + r, b);
+    x->blk_id[r] = b; x->blk[r][0] = v.x; x->blk[r][1] = v.y; x->blk[r][2] = v.z; x->blk[r][3] = v.w;
+}
+__device__ __forceinline__ uint32_t red_word(Cx c, int r)
+{
+    Scratch *x = SCR(c);
+    const uint32_t j = x->ctr_br[A_RED0 + r];
+    x->ctr_br[A_RED0 + r] = (uint16_t)(j + 1);
+    if (x->blk_id[r] != (j >> 2)) red_refill(c, r, j >> 2);
+    return x->blk[r][j & 3u];
+}
+#ifndef CC4_RED_RNG_INLINE
+#define CC4_RED_RNG_INLINE 1        /* 0: the red agents' serial draws go through the generic out-of-line rng_int / rng_f64 (tuning knob) */
+#endif
+__device__ __forceinline__ uint32_t rng_int_red(Cx c, int r, int site, uint32_t n)
+{
+    if (!CC4_RED_RNG_INLINE || g_blk.rng_mode == 1) return rng_int(c, A_RED0 + r, site, n);
+    return __umulhi(red_word(c, r), n);
+}
+__device__ __forceinline__ double rng_f64_red(Cx c, int r, int site)
+{
+    if (!CC4_RED_RNG_INLINE || g_blk.rng_mode == 1) return rng_f64(c, A_RED0 + r, site, 0);
+    return f64_from_word(red_word(c, r));
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* small helpers                                                                                    */
 /* ------------------------------------------------------------------------------------------------ */
@@ -374,6 +405,12 @@ __device__ CC4_INL5 int proc_find(Cx c, int h, uint32_t pid) { return proc_find(
 __device__ CC4_INL3 int create_pid(Cx c, int actor, uint32_t pmax)
 {   /* Host.create_pid Host.py:198-200; pmax = pmax[h] */
     uint32_t pid = pmax + 1 + rng_int(c, actor, ST_CREATE_PID, 9);
+    if (pid > 0xFFFFu) { fail(c, CC4_E_CAPACITY); pid = 0xFFFFu; }
+    return (int)pid;
+}
+__device__ CC4_INL3 int create_pid_red(Cx c, int r, uint32_t pmax)
+{
+    uint32_t pid = pmax + 1 + rng_int_red(c, r, ST_CREATE_PID, 9);
     if (pid > 0xFFFFu) { fail(c, CC4_E_CAPACITY); pid = 0xFFFFu; }
     return (int)pid;
 }
@@ -1092,7 +1129,7 @@ __device__ __forceinline__ int route_hop(int src, int dst, int nh, int i)
 /* ExploitAction._create_new_session ExploitAction.py:212-262 [uniform] */
 __device__ CC4_INL3 int exploit_new_session(Cx c, int r, int target, uint32_t pd_target, uint32_t pmax_target)
 {
-    int pid = create_pid(c, A_RED0 + r, pmax_target);
+    int pid = create_pid_red(c, r, pmax_target);
     proc_append(c, target, P_MAKE(pid, K_SHELL, 0, 0), pd_target, pmax_target);
     sess_add(c, r, target, 0, 0, pid);
     return pid;
@@ -1178,7 +1215,7 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
         if (si < 0 || !S_abs) return SUCC_FALSE;
         if (blocking(s, S_host, a.host)) return SUCC_FALSE;
         double rate = a.code == AC_AGGR ? 0.75 : 0.25;
-        double u = rng_f64(c, actor, ST_PORTSCAN, 0);
+        double u = rng_f64_red(c, r, ST_PORTSCAN);
         const int h = a.host;
         uint32_t mask = 0, alert = 0;
         const uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
@@ -1251,8 +1288,8 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
             _Pragma("unroll 1") for (int i = 1; i < no; i++) if (w10[i] > w10[top]) top = i;
             _Pragma("unroll 1") for (int i = top; i + 1 < no; i++) opt[i] = opt[i + 1];
             no--;
-            sel = opt[rng_int(c, actor, ST_EXP_OTHER, (uint32_t)no)];
-            (void)rng_f64(c, actor, ST_EXP_TOP, 0);
+            sel = opt[rng_int_red(c, r, ST_EXP_OTHER, (uint32_t)no)];
+            (void)rng_f64_red(c, r, ST_EXP_TOP);
         }
         /* the first live process (list order) that the chosen exploit can attack: ExploitAction._get_vulnerable_process
            ExploitAction.py:178-200 / SSHBruteForce.py:24-84 */
@@ -1302,10 +1339,10 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
         if (decoy) s->ev[target] |= EV_NET;
         obs_entry(c, r, 1, target, 1, 0, 0, 0);
         if (!(sel == X_SQL || decoy)) return SUCC_FALSE;
-        if (0.0 >= rng_f64(c, actor, ST_EXP_SUCC, 0)) return SUCC_FALSE;
+        if (0.0 >= rng_f64_red(c, r, ST_EXP_SUCC)) return SUCC_FALSE;
         if (decoy) { s->ev[target] |= EV_NET; return SUCC_FALSE; }
         int pid = exploit_new_session(c, r, target, pd_target, pmax_target);
-        if (rng_f64(c, actor, ST_EXP_DETECT, 0) > 0.05) ev_procpid(c, target, pid);
+        if (rng_f64_red(c, r, ST_EXP_DETECT) > 0.05) ev_procpid(c, target, pid);
         obs_entry(c, r, 1, target, 1, 0, 1, 1);
         obs_entry(c, r, 1, src, 1, 0, 0, 0);
         return SUCC_TRUE;
@@ -1327,7 +1364,7 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
         }
         if (n == 0) return SUCC_FALSE;
         if (tgt < 0) {
-            int pk = (int)rng_int(c, actor, ST_PRIV_SESS, (uint32_t)n);
+            int pk = (int)rng_int_red(c, r, ST_PRIV_SESS, (uint32_t)n);
             tgt = sess_kth(s, pk, on_host);
             if (si < 0 || !S_abs) return SUCC_FALSE;
             s->sessf[tgt] |= 1u << 4;      /* EscalateAction.__upgrade_session EscalateAction.py:54-87 */
@@ -1388,7 +1425,7 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
 __device__ CC4_INL6 void rsc_reelect(Cx c, int r, int n)
 {
     Cc4Dyn *s = DYN(c);
-    int pk = (int)rng_int(c, A_RED0 + r, ST_RSC_PRIMARY, (uint32_t)n);
+    int pk = (int)rng_int_red(c, r, ST_RSC_PRIMARY, (uint32_t)n);
     int at = sess_kth(s, pk, [=](uint32_t, uint32_t f) { return SF_AGENT(f) == (uint32_t)r; });
     if (at < 0) { fail(c, CC4_E_UNREACHABLE); return; }
     const uint32_t w = s->sess[at]; const uint8_t f = s->sessf[at];

@@ -498,11 +498,14 @@ __device__ __forceinline__ void green_items(int ph, int first, int n_local, int 
 #endif
         const int gidx = it * 32 + lane;
         int e = 0;
+        /* the item starts in the first episode whose end is past it * 32 (one lane-parallel look at the prefix table); an
+           episode has at least 24 agents, so a lane's own episode is at most two further on */
+        const uint32_t past_a = __ballot_sync(0xFFFFFFFFu, lane < n_local && gend[lane] > it * 32);
+        const uint32_t past_b = __ballot_sync(0xFFFFFFFFu, 32 + lane < n_local && gend[32 + lane] > it * 32);
+        const int e_first = past_a ? __ffs(past_a) - 1 : 31 + __ffs(past_b);
         if (gidx < total) {
-            /* episode of this agent: the item starts in the first episode whose end is past it*32 */
-            int lo = 0, hi = n_local - 1;
-            while (lo < hi) { int mid = (lo + hi) >> 1; if (gend[mid] > gidx) hi = mid; else lo = mid + 1; }
-            e = lo;
+            e = e_first;
+            while (gend[e] <= gidx) e++;
             const Cx c = (Cx)(e * (int)sizeof(WarpSmem));
             const int g = gidx - (e ? gend[e - 1] : 0);
             Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
