@@ -915,6 +915,19 @@ __device__ CC4_INL6 void do_restore(Cx c, int h)
     WC(c)->k->svc64[h] = st->o_svc64[h];
 }
 
+/* production mode: the next two words of a blue actor's stream from one Philox block (blue streams are not cached in the
+   scratch: a blue agent draws at most twice per tick) */
+__device__ __noinline__ uint2 blue_words2(Cx c, int actor)
+{
+    Scratch *x = SCR(c);
+    const uint32_t j = ctr_get(x, actor);
+    ctr_set(x, actor, j + 2);
+    const uint4 v = philox_block(c, actor, j >> 2);
+    const uint32_t w0 = u4_word(v, j & 3u);
+    const uint32_t w1 = (j & 3u) < 3u ? u4_word(v, (j & 3u) + 1u) : philox_block(c, actor, (j >> 2) + 1u).x;
+    return make_uint2(w0, w1);
+}
+
 /* DecoyAction.execute DecoyAction.py:47-112 with DeployDecoy.CANDIDATE_DECOYS DeployDecoy.py:27 [uniform] */
 __device__ CC4_INL6 void do_decoy(Cx c, int b, int h)
 {
@@ -938,8 +951,12 @@ __device__ CC4_INL6 void do_decoy(Cx c, int b, int h)
     if (!(used & PB_443)) fac |= (uint32_t)K_D_TOMCAT << (4 * nf++);
     if (!(used & PB_25)) fac |= (uint32_t)K_D_HARAKA << (4 * nf++);
     fac |= (uint32_t)K_D_VSFTPD << (4 * nf++);
-    int kind = (int)(fac >> (4 * rng_int(c, actor, ST_DECOY_FACTORY, (uint32_t)nf)) & 15u);
-    int pid = create_pid(c, actor, pmax);
+    uint32_t pick, pid_draw;        /* DecoyAction.py:64 choice(factories), Host.create_pid Host.py:198-200 */
+    if (g_blk.rng_mode == 1) { pick = rng_int(c, actor, ST_DECOY_FACTORY, (uint32_t)nf); pid_draw = rng_int(c, actor, ST_CREATE_PID, 9); }
+    else { const uint2 w = blue_words2(c, actor); pick = __umulhi(w.x, (uint32_t)nf); pid_draw = __umulhi(w.y, 9u); }
+    int kind = (int)(fac >> (4 * pick) & 15u);
+    int pid = (int)(pmax + 1 + pid_draw);
+    if (pid > 0xFFFF) { fail(c, CC4_E_CAPACITY); pid = 0xFFFF; }
     /* host.services[name] = Service(pid): an earlier process of the same decoy stops being the service's process */
     {
         if (lane_id() < np_h && P_KIND(w0) == (uint32_t)kind && P_SVC(w0)) pp_h[lane_id()] = w0 & ~(1u << 21);
@@ -980,9 +997,11 @@ __device__ CC4_INL6 void exec_blue(Cx c, int b, uint32_t aw)
     case AC_REMOVE: {   /* Remove.py:42-69: StopProcess for every suspicious pid recorded for the host, in list order */
         const int n = s->n_sus;
         const uint32_t *sus = WC(c)->k->sus;
+        uint32_t w_next = lane_id() < n ? sus[lane_id()] : 0u;     /* the list is cold: the next 32 entries are requested before these are looked at */
         _Pragma("unroll 1") for (int base = 0; base < n; base += 32) {
             const int i = base + lane_id();
-            const uint32_t w = i < n ? sus[i] : 0u;
+            const uint32_t w = w_next;
+            if (base + 32 < n) w_next = i + 32 < n ? sus[i + 32] : 0u;
             uint32_t m = __ballot_sync(FULLMASK, i < n && SU_AGENT(w) == (uint32_t)b && SU_SLOT(w) == (uint32_t)a.host);
             while (m) {
                 const int j = __ffs(m) - 1; m &= m - 1;
@@ -1140,9 +1159,11 @@ __device__ CC4_INL3 int ports_find(Cx c, int r, int id, int host, uint32_t *word
     const uint32_t *ports = WC(c)->k->ports;
     const int n = DYN(c)->n_ports;
     const uint32_t key = PT_MAKE(0, host, id, r);
+    uint32_t v_next = lane_id() < n ? ports[lane_id()] : 0xFFFFFFFFu;      /* cold table: the next line is requested before this one is looked at */
     _Pragma("unroll 1") for (int base = 0; base < n; base += 32) {
         const int i = base + lane_id();
-        const uint32_t v = i < n ? ports[i] : 0xFFFFFFFFu;
+        const uint32_t v = v_next;
+        if (base + 32 < n) v_next = i + 32 < n ? ports[i + 32] : 0xFFFFFFFFu;
         const uint32_t m = __ballot_sync(FULLMASK, (v & ~0x3Fu) == key);
         if (m) { *word = __shfl_sync(FULLMASK, v, __ffs(m) - 1); return base + __ffs(m) - 1; }
     }
@@ -1386,10 +1407,13 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
         if (!__any_sync(FULLMASK, any && root)) return SUCC_FALSE;
         uint64_t v = WC(c)->k->svc64[h];
         int n = svc_count(v);
+        /* all nine 7-bit entries at once: `lanes` = bit 7i of every entry in use, `ot` = of the entry that is the OT service */
+        const uint64_t SVC_ONES = 0x0102040810204081ull;
+        const uint64_t lanes = n >= 9 ? SVC_ONES : SVC_ONES & ((1ull << (7 * n)) - 1ull);
+        const uint64_t t = v ^ ((uint64_t)K_OT * SVC_ONES);
+        const uint64_t ot = ~(t | t >> 1 | t >> 2 | t >> 3) & lanes;
         if (a.code == AC_IMPACT) {
-            int has_ot = 0;
-            _Pragma("unroll 1") for (int i = 0; i < n; i++) has_ot |= (SVC_ENTRY(v, i) & 15u) == K_OT;
-            if (!has_ot || (v & SVC_OT_STOPPED)) return SUCC_FALSE;
+            if (!ot || (v & SVC_OT_STOPPED)) return SUCC_FALSE;
             if (si < 0) return SUCC_FALSE;     /* StopService is a TargetedLocalAction: TargetedLocalAction.py:14-21 */
             WC(c)->k->svc64[h] = v | SVC_OT_STOPPED;  /* Host.stop_service Host.py:296-301 */
             /* State.remove_process State.py:390-418: the first live OT service process becomes a tombstone */
@@ -1408,9 +1432,11 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
                 if (s2 >= 0) sess_delete(c, s2);
             }
         } else {
-            int na = 0;
-            _Pragma("unroll 1") for (int i = 0; i < n; i++) { uint32_t e = SVC_ENTRY(v, i); if (!svc_active(v, e)) continue; na++; uint32_t rel = e >> 4; rel = rel > 0 ? rel - 1 : 0; v = svc_set(v, i, (e & 15u) | rel << 4); }
-            if (na == 0) return SUCC_FALSE;
+            /* every active service loses one reliability step (20 %), not below 0 */
+            const uint64_t act = (v & SVC_OT_STOPPED) ? lanes & ~ot : lanes;
+            if (!act) return SUCC_FALSE;
+            const uint64_t nz = (v >> 4 | v >> 5 | v >> 6) & act;       /* reliability > 0 */
+            v -= nz << 4;
             WC(c)->k->svc64[h] = v;
         }
         obs_entry(c, r, 0, h, 0, 0, 0, 0);
