@@ -32,7 +32,7 @@ SVC_BYTES = 128 * 8                          # per-host service table: read in p
 EPISODE_TICKS = 499                          # steps=500 -> done at step_count >= 499 (EnterpriseScenarioGenerator.py:870)
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch at 65536 episodes from the committed
 # `ncu --set full` capture (profiles/), or None when no capture matches the current kernel
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 508_581_888      # profiles/r02b_kstep_ncu_full_summary.txt: 303.2 MB read + 205.4 MB written
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 501_594_624      # profiles/r02m_kstep_ncu_full_summary.txt: 303.5 MB read + 198.1 MB written
 
 
 def load_peaks():
