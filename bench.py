@@ -134,6 +134,7 @@ def workload_config(args):
                         f"EnterpriseGreen in-kernel, uniform-random blue indices, full tick incl. 5 observation vectors + "
                         f"BlueRewardMachine (BASELINE configs[2])",
             "envs_per_gpu": args.envs, "episode_steps": 500, "blue_policy": "uniform random index (masked-out = Sleep)",
+            "observations": "uint8 [envs, 578] per tick = the five blue vectors as BlueFlatWrapper returns them without pad_spaces (92 x 4 + 210), written to HBM",
             "cache": "per-tick state traffic (envs x record) is far larger than the 126 MB L2, no flush needed",
             "parallelism": f"episodes sharded over {args.gpus} GPU(s), no data-path collective"}
 
@@ -204,7 +205,7 @@ def main():
         if tick == EPISODE_TICKS:            # every episode of the batch is done: reset (inside the timed region)
             env.reset()
             tick = 0
-        obs, rew, done = env.step(pool[i % len(pool)], None, STEP_ALL)
+        obs, rew, done = env.step_compact(pool[i % len(pool)], None)     # obs uint8 [N, 578]: the five unpadded vectors (BlueFlatWrapper default, pad_spaces=False)
         ret.add_(rew)
         tick += 1
 
@@ -227,7 +228,7 @@ def main():
             env.reset()
             tick = 0
         kev[i][0].record()
-        obs, rew, done = env.step(pool[i % len(pool)], None, STEP_ALL)
+        obs, rew, done = env.step_compact(pool[i % len(pool)], None)     # obs uint8 [N, 578]: the five unpadded vectors (BlueFlatWrapper default, pad_spaces=False)
         kev[i][1].record()
         ret.add_(rew)
         tick += 1

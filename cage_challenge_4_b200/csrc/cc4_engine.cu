@@ -741,7 +741,8 @@ __device__ __forceinline__ void init_ctx(Cx c, const Params &p, int env, int tic
 /* ------------------------------------------------------------------------------------------------ */
 /* kernels                                                                                          */
 /* ------------------------------------------------------------------------------------------------ */
-struct StepIO { const int32_t *actions; const uint8_t *msgs; uint8_t *obs; float *reward; uint8_t *done; int flags; };
+struct StepIO { const int32_t *actions; const uint8_t *msgs; uint8_t *obs; float *reward; uint8_t *done; int flags;
+                int reverse; };     /* blocks take the episodes from the far end first (see cc4_step) */
 
 /* Block b owns episodes [env0 + b*epb, min(env0 + (b+1)*epb, env_end)); env0 / env_end: the slice of the batch this
  * launch covers (the chunked host path launches several slices). */
@@ -753,7 +754,7 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
     __shared__ short gend[64];
     __shared__ PhaseOrder ord_blue, ord_red;
     __shared__ __align__(8) uint64_t ld_bar[64];
-    const int first = env0 + blockIdx.x * epb, n_local = min(epb, env_end - first);
+    const int first = env0 + (int)(io.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * epb, n_local = min(epb, env_end - first);
     init_block_ctx(p);
     if (threadIdx.x < N_PHASES + 6) next[threadIdx.x] = 0;
     if (threadIdx.x < 4) { ord_blue.cnt[threadIdx.x] = 0; ord_red.cnt[threadIdx.x] = 0; }
@@ -1169,6 +1170,7 @@ struct cc4_handle {
     cudaEvent_t ev_chunk[CC4_MAX_CHUNKS];                 /* ... chunk k's outputs are on the host */
     uint32_t *host_bits;                                  /* pinned: the bit rows of the batch */
     HostPool *pool;
+    int sweep, alternate;                                 /* direction of the last cc4_step over the batch; CC4_SWEEP_ALTERNATE=0 keeps one direction */
     int host_expand;                                      /* 0: byte rows over PCIe (CC4_HOST_EXPAND=0) */
     int host_chunk;                                       /* episodes per chunk of cc4_step_host, 0 = one wave of blocks (CC4_HOST_CHUNK_EPISODES) */
 };
@@ -1187,6 +1189,7 @@ extern "C" int cc4_create(int n_envs, int device, uint64_t seed, uint64_t first_
     CUDA_TRY(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device));
     h->p.k0 = (uint32_t)seed; h->p.k1hi = (uint32_t)(seed >> 32); h->p.first_episode = first_episode;
     { const char *e = getenv("CC4_HOST_EXPAND"); h->host_expand = !(e && e[0] == '0'); }
+    { const char *e = getenv("CC4_SWEEP_ALTERNATE"); h->alternate = !(e && e[0] == '0'); }
     { const char *e = getenv("CC4_HOST_CHUNK_EPISODES"); h->host_chunk = e ? atoi(e) : 0; }
     CUDA_TRY(cudaMalloc(&h->p.dyn, sizeof(Cc4Dyn) * (size_t)n_envs));
     CUDA_TRY(cudaMalloc(&h->p.stat, sizeof(Cc4Stat) * (size_t)n_envs));
@@ -1300,7 +1303,11 @@ extern "C" int cc4_step(cc4_handle *h, const int32_t *actions_dev, const uint8_t
     if (!h || !actions_dev) return set_err(CC4_ERR_ARG, "cc4_step: null handle or actions%s", "");
     CUDA_TRY(cudaSetDevice(h->device));
     const int epb = episodes_per_block(h, (size_t)h->p.n_envs), blocks = (h->p.n_envs + epb - 1) / epb;
-    StepIO io = { actions_dev, msgs_dev, obs_dev, reward_dev, done_dev, flags };
+    /* Successive ticks walk the batch in opposite directions: the per-tick footprint (hot records + the cold lines the
+       actions touch) is larger than the 126 MB L2, so a tick that starts where the last one ended finds the most recently
+       written records still there, while a fixed direction finds none of them (cyclic sweep over an LRU-like cache). */
+    h->sweep ^= h->alternate;
+    StepIO io = { actions_dev, msgs_dev, obs_dev, reward_dev, done_dev, flags, h->sweep };
     k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * (size_t)epb, (cudaStream_t)stream>>>(h->p, 0, h->p.n_envs, epb, io);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1361,22 +1368,31 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
         const double t_start = ts0.tv_sec * 1e6 + ts0.tv_nsec * 1e-3;
         uint32_t *stage_bits = reinterpret_cast<uint32_t *>(h->stage_obs);      /* the byte staging area is larger than the bit rows */
         const int kflags = (flags & ~CC4_STEP_OBS_COMPACT) | CC4_STEP_OBS_BITS;
-        int k = 0, nch = 0;
-        for (size_t e0 = 0; e0 < n; e0 += chunk, k ^= 1, nch++) {
+        {   /* chunk order, knob CC4_SWEEP_HOST: 0 forward always (default), 1 alternate like cc4_step, 2 reversed always.
+               Alternating is SLOWER here (0.72 ms per tick against 0.55; 0 and 2 measure the same): the chunk that was expanded
+               last is then the first whose bit rows are copied to the host again, while the host threads still hold those
+               lines of the pinned staging area in their caches, and the first three chunks arrive 170 us late. */
+            static const int mode = getenv("CC4_SWEEP_HOST") ? atoi(getenv("CC4_SWEEP_HOST")) : 0;
+            h->sweep = mode == 1 ? (h->sweep ^ 1) : mode == 2 ? 1 : 0;
+        }
+        const int nch = (int)((n + chunk - 1) / chunk);
+        int k = 0;
+        for (int ci = 0; ci < nch; ci++, k ^= 1) {
+            const size_t e0 = (size_t)(h->sweep ? nch - 1 - ci : ci) * chunk;
             size_t cnt = n - e0 < chunk ? n - e0 : chunk;
             cudaStream_t st = h->pipe[k];
             CUDA_TRY(cudaMemcpyAsync(h->stage_actions + e0 * 5, actions_host + e0 * 5, cnt * 5 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
             if (msgs_host) CUDA_TRY(cudaMemcpyAsync(h->stage_msgs + e0 * 5, msgs_host + e0 * 5, cnt * 5, cudaMemcpyHostToDevice, st));
             const int epb = episodes_per_block(h, cnt), blocks = (int)((cnt + epb - 1) / epb);
             StepIO io = { h->stage_actions, msgs_host ? h->stage_msgs : nullptr, reinterpret_cast<uint8_t *>(stage_bits),
-                          want_rew ? h->stage_reward : nullptr, done_host ? h->stage_done : nullptr, kflags };
+                          want_rew ? h->stage_reward : nullptr, done_host ? h->stage_done : nullptr, kflags, h->sweep };
             k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * (size_t)epb, st>>>(h->p, (int)e0, (int)(e0 + cnt), epb, io);
             h->launches++;
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaMemcpyAsync(h->host_bits + e0 * CC4_OBS_BITS_WORDS, stage_bits + e0 * CC4_OBS_BITS_WORDS, cnt * CC4_OBS_BITS_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             if (want_rew) CUDA_TRY(cudaMemcpyAsync(reward_host + e0, h->stage_reward + e0, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
             if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host + e0, h->stage_done + e0, cnt, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaEventRecord(h->ev_chunk[nch], st));
+            CUDA_TRY(cudaEventRecord(h->ev_chunk[ci], st));
         }
         int c = 0;
         cudaError_t err = cudaSuccess;
@@ -1384,7 +1400,8 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
         auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
         const double t_enq = trace ? now_us() : 0.0;
         double t_ev[CC4_MAX_CHUNKS];
-        for (size_t e0 = 0; e0 < n; e0 += chunk, c++) {
+        for (; c < nch; c++) {
+            const size_t e0 = (size_t)(h->sweep ? nch - 1 - c : c) * chunk;
             size_t cnt = n - e0 < chunk ? n - e0 : chunk;
             err = cudaEventSynchronize(h->ev_chunk[c]);
             if (err != cudaSuccess) break;
