@@ -1160,6 +1160,8 @@ struct HostPool {
     }
 };
 #define CC4_MAX_CHUNKS 16
+constexpr size_t HOST_BITS_ROW = CC4_OBS_BITS_WORDS * sizeof(uint32_t);      /* 80 */
+constexpr size_t HOST_ROW = HOST_BITS_ROW + sizeof(float) + 1;               /* + reward + done = 85 bytes per episode through PCIe */
 
 struct cc4_handle {
     Params p;
@@ -1360,13 +1362,17 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
             h->pool = new (std::nothrow) HostPool();
             if (!h->pool) return set_err(CC4_ERR_STATE, "cc4_step_host: out of host memory%s", "");
             h->pool->start(nt);
-            CUDA_TRY(cudaHostAlloc(&h->host_bits, n * CC4_OBS_BITS_WORDS * sizeof(uint32_t), cudaHostAllocDefault));
+            CUDA_TRY(cudaHostAlloc(&h->host_bits, n * HOST_ROW, cudaHostAllocDefault));
             for (int i = 0; i < CC4_MAX_CHUNKS; i++) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
         }
         if ((n + chunk - 1) / chunk > CC4_MAX_CHUNKS) return set_err(CC4_ERR_STATE, "cc4_step_host: too many chunks%s", "");
         timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
         const double t_start = ts0.tv_sec * 1e6 + ts0.tv_nsec * 1e-3;
-        uint32_t *stage_bits = reinterpret_cast<uint32_t *>(h->stage_obs);      /* the byte staging area is larger than the bit rows */
+        /* staging (device and pinned host alike): chunk [e0, e0 + cnt) owns bytes [e0 * 85, (e0 + cnt) * 85) = its bit rows, then its
+           rewards, then its done flags, so that ONE copy brings a chunk's outputs to the host (e0 and the chunk size are
+           multiples of 64 episodes: every part stays 16-byte aligned) */
+        uint8_t *stage = h->stage_obs;          /* the byte-row staging area is larger than n * 85 */
+        uint8_t *hstage = reinterpret_cast<uint8_t *>(h->host_bits);
         const int kflags = (flags & ~CC4_STEP_OBS_COMPACT) | CC4_STEP_OBS_BITS;
         {   /* chunk order, knob CC4_SWEEP_HOST: 0 forward always (default), 1 alternate like cc4_step, 2 reversed always.
                Alternating is SLOWER here (0.72 ms per tick against 0.55; 0 and 2 measure the same): the chunk that was expanded
@@ -1384,14 +1390,14 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
             CUDA_TRY(cudaMemcpyAsync(h->stage_actions + e0 * 5, actions_host + e0 * 5, cnt * 5 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
             if (msgs_host) CUDA_TRY(cudaMemcpyAsync(h->stage_msgs + e0 * 5, msgs_host + e0 * 5, cnt * 5, cudaMemcpyHostToDevice, st));
             const int epb = episodes_per_block(h, cnt), blocks = (int)((cnt + epb - 1) / epb);
-            StepIO io = { h->stage_actions, msgs_host ? h->stage_msgs : nullptr, reinterpret_cast<uint8_t *>(stage_bits),
-                          want_rew ? h->stage_reward : nullptr, done_host ? h->stage_done : nullptr, kflags, h->sweep };
+            /* the kernel indexes rows / reward / done by global episode number: hand it bases that put episode e0 at the chunk's parts */
+            uint8_t *cb = stage + e0 * HOST_ROW;
+            StepIO io = { h->stage_actions, msgs_host ? h->stage_msgs : nullptr, cb - e0 * HOST_BITS_ROW,
+                          reinterpret_cast<float *>(cb + cnt * HOST_BITS_ROW) - e0, cb + cnt * (HOST_BITS_ROW + sizeof(float)) - e0, kflags | CC4_STEP_REWARD, h->sweep };
             k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * (size_t)epb, st>>>(h->p, (int)e0, (int)(e0 + cnt), epb, io);
             h->launches++;
             CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaMemcpyAsync(h->host_bits + e0 * CC4_OBS_BITS_WORDS, stage_bits + e0 * CC4_OBS_BITS_WORDS, cnt * CC4_OBS_BITS_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            if (want_rew) CUDA_TRY(cudaMemcpyAsync(reward_host + e0, h->stage_reward + e0, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
-            if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host + e0, h->stage_done + e0, cnt, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(hstage + e0 * HOST_ROW, cb, cnt * HOST_ROW, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaEventRecord(h->ev_chunk[ci], st));
         }
         int c = 0;
@@ -1406,7 +1412,10 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
             err = cudaEventSynchronize(h->ev_chunk[c]);
             if (err != cudaSuccess) break;
             if (trace) t_ev[c] = now_us();
-            h->pool->submit(h->host_bits + e0 * CC4_OBS_BITS_WORDS, obs_host + e0 * obs_row, cnt, compact, obs_row);
+            const uint8_t *hb = hstage + e0 * HOST_ROW;
+            h->pool->submit(reinterpret_cast<const uint32_t *>(hb), obs_host + e0 * obs_row, cnt, compact, obs_row);
+            if (want_rew) memcpy(reward_host + e0, hb + cnt * HOST_BITS_ROW, cnt * sizeof(float));
+            if (done_host) memcpy(done_host + e0, hb + cnt * (HOST_BITS_ROW + sizeof(float)), cnt);
         }
         h->pool->wait();
         if (trace) {
@@ -1416,8 +1425,8 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
             fprintf(stderr, "; expanded +%.0f us\n", t_done - t_start);
         }
         if (err != cudaSuccess) return set_err(CC4_ERR_CUDA, "cc4_step_host: %s", cudaGetErrorString(err));
-        for (int i = 0; i < 2; i++) { CUDA_TRY(cudaEventRecord(h->ev_out[i], h->pipe[i])); CUDA_TRY(cudaStreamWaitEvent(user, h->ev_out[i], 0)); }
-        CUDA_TRY(cudaStreamSynchronize(user));
+        /* every chunk's last operation has been waited for on the host: both internal streams are idle, and whatever the
+           caller queues on its stream from now on starts after this tick (no event hand-back needed) */
         return CC4_OK;
     }
     int k = 0;
