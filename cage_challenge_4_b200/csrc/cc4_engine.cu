@@ -17,8 +17,8 @@
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
+#include <atomic>
 #include <condition_variable>
-#include <deque>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -1123,39 +1123,66 @@ static void expand_rows(const uint32_t *rows, uint8_t *dst, size_t cnt, bool com
     expand_rows_generic(rows, dst, cnt, compact);
 }
 struct ExpandJob { const uint32_t *rows; uint8_t *dst; size_t cnt; bool compact; };
+/* The pool behind cc4_step_host.  Jobs go through a ring with monotonically increasing publish / claim / done counters;
+ * idle workers spin for a few hundred microseconds before they go to sleep, because within a tick the chunks arrive
+ * every ~60 us and a futex wake-up per chunk (and one more for the caller) would sit on the critical path of the call. */
 struct HostPool {
+    static constexpr unsigned RING = 512;
     std::vector<std::thread> th;
+    ExpandJob ring[RING];
+    std::atomic<unsigned> published{0}, next{0}, done{0};
+    std::atomic<int> sleepers{0};
+    std::atomic<bool> stop{false};
     std::mutex m;
-    std::condition_variable cv_work, cv_done;
-    std::deque<ExpandJob> q;
-    size_t pending = 0;
-    bool stop = false;
+    std::condition_variable cv;
+    static void relax()
+    {
+#if defined(__x86_64__)
+        _mm_pause();
+#endif
+    }
+    bool try_run()
+    {
+        unsigned i = next.load();
+        while (i != published.load()) {
+            if (next.compare_exchange_weak(i, i + 1)) {
+                const ExpandJob j = ring[i % RING];
+                expand_rows(j.rows, j.dst, j.cnt, j.compact);
+                done.fetch_add(1);
+                return true;
+            }
+        }
+        return false;
+    }
     void run()
     {
-        std::unique_lock<std::mutex> lk(m);
         for (;;) {
-            cv_work.wait(lk, [&] { return stop || !q.empty(); });
-            if (q.empty()) return;      /* stop */
-            ExpandJob j = q.front(); q.pop_front();
-            lk.unlock();
-            expand_rows(j.rows, j.dst, j.cnt, j.compact);
-            lk.lock();
-            if (--pending == 0) cv_done.notify_all();
+            int idle = 0;
+            while (!try_run()) {
+                if (stop.load()) return;
+                if (++idle < 20000) { relax(); continue; }
+                std::unique_lock<std::mutex> lk(m);         /* nothing for a while: sleep until the next submit */
+                sleepers.fetch_add(1);
+                cv.wait(lk, [&] { return stop.load() || next.load() != published.load(); });
+                sleepers.fetch_sub(1);
+                idle = 0;
+            }
         }
     }
     void start(int n) { for (int i = 0; i < n; i++) th.emplace_back([this] { run(); }); }
     void submit(const uint32_t *rows, uint8_t *dst, size_t cnt, bool compact, size_t row_bytes)
-    {   /* one job per thread */
+    {   /* one job per thread; the caller waits for every job of a tick before the next tick (at most 16 chunks x 16 jobs in flight) */
         const size_t parts = th.size(), per = (cnt + parts - 1) / parts;
-        std::lock_guard<std::mutex> lk(m);
-        for (size_t o = 0; o < cnt; o += per) { q.push_back({ rows + o * CC4_OBS_BITS_WORDS, dst + o * row_bytes, cnt - o < per ? cnt - o : per, compact }); pending++; }
-        cv_work.notify_all();
+        unsigned p = published.load();
+        for (size_t o = 0; o < cnt; o += per) ring[p++ % RING] = { rows + o * CC4_OBS_BITS_WORDS, dst + o * row_bytes, cnt - o < per ? cnt - o : per, compact };
+        published.store(p);
+        if (sleepers.load() > 0) { std::lock_guard<std::mutex> lk(m); cv.notify_all(); }
     }
-    void wait() { std::unique_lock<std::mutex> lk(m); cv_done.wait(lk, [&] { return pending == 0; }); }
+    void wait() { while (done.load() != published.load()) relax(); }
     ~HostPool()
     {
-        { std::lock_guard<std::mutex> lk(m); stop = true; }
-        cv_work.notify_all();
+        stop.store(true);
+        { std::lock_guard<std::mutex> lk(m); cv.notify_all(); }
         for (auto &t : th) t.join();
     }
 };
