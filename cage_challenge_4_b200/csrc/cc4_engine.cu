@@ -1197,7 +1197,9 @@ struct cc4_handle {
     int32_t *stage_actions; uint8_t *stage_msgs, *stage_obs, *stage_mask, *stage_done; float *stage_reward;   /* device staging for cc4_step_host */
     cudaStream_t pipe[2]; cudaEvent_t ev_in, ev_out[2];   /* chunk pipeline of cc4_step_host */
     cudaEvent_t ev_chunk[CC4_MAX_CHUNKS];                 /* ... chunk k's outputs are on the host */
-    uint32_t *host_bits;                                  /* pinned: the bit rows of the batch */
+    uint32_t *host_bits;                                  /* pinned + mapped: the bit rows (+ rewards, done flags) of the batch */
+    void *host_bits_dev;                                  /* ... as the device sees it */
+    int zero_copy;                                        /* CC4_HOST_ZEROCOPY=1: the kernel writes those outputs straight to host memory (default: staging + one copy per chunk) */
     HostPool *pool;
     int sweep, alternate;                                 /* direction of the last cc4_step over the batch; CC4_SWEEP_ALTERNATE=0 keeps one direction */
     int host_expand;                                      /* 0: byte rows over PCIe (CC4_HOST_EXPAND=0) */
@@ -1220,6 +1222,7 @@ extern "C" int cc4_create(int n_envs, int device, uint64_t seed, uint64_t first_
     { const char *e = getenv("CC4_HOST_EXPAND"); h->host_expand = !(e && e[0] == '0'); }
     { const char *e = getenv("CC4_SWEEP_ALTERNATE"); h->alternate = !(e && e[0] == '0'); }
     { const char *e = getenv("CC4_HOST_CHUNK_EPISODES"); h->host_chunk = e ? atoi(e) : 0; }
+    { const char *e = getenv("CC4_HOST_ZEROCOPY"); h->zero_copy = e && e[0] == '1'; }      /* off: measured 643 M against 663 M agent-steps/s with staging + one copy */
     CUDA_TRY(cudaMalloc(&h->p.dyn, sizeof(Cc4Dyn) * (size_t)n_envs));
     CUDA_TRY(cudaMalloc(&h->p.stat, sizeof(Cc4Stat) * (size_t)n_envs));
     CUDA_TRY(cudaMalloc(&h->p.cold, sizeof(Cc4Cold) * (size_t)n_envs));
@@ -1389,7 +1392,8 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
             h->pool = new (std::nothrow) HostPool();
             if (!h->pool) return set_err(CC4_ERR_STATE, "cc4_step_host: out of host memory%s", "");
             h->pool->start(nt);
-            CUDA_TRY(cudaHostAlloc(&h->host_bits, n * HOST_ROW, cudaHostAllocDefault));
+            CUDA_TRY(cudaHostAlloc(&h->host_bits, n * HOST_ROW, cudaHostAllocMapped));
+            CUDA_TRY(cudaHostGetDevicePointer(&h->host_bits_dev, h->host_bits, 0));
             for (int i = 0; i < CC4_MAX_CHUNKS; i++) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
         }
         if ((n + chunk - 1) / chunk > CC4_MAX_CHUNKS) return set_err(CC4_ERR_STATE, "cc4_step_host: too many chunks%s", "");
@@ -1418,13 +1422,15 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
             if (msgs_host) CUDA_TRY(cudaMemcpyAsync(h->stage_msgs + e0 * 5, msgs_host + e0 * 5, cnt * 5, cudaMemcpyHostToDevice, st));
             const int epb = episodes_per_block(h, cnt), blocks = (int)((cnt + epb - 1) / epb);
             /* the kernel indexes rows / reward / done by global episode number: hand it bases that put episode e0 at the chunk's parts */
-            uint8_t *cb = stage + e0 * HOST_ROW;
+            /* zero copy (knob, off): the 85 bytes per episode are written over PCIe by the kernel itself as it goes, so a chunk is on
+               the host when its kernel ends instead of one copy later; the kernel loses more than the copy costs */
+            uint8_t *cb = (h->zero_copy ? static_cast<uint8_t *>(h->host_bits_dev) : stage) + e0 * HOST_ROW;
             StepIO io = { h->stage_actions, msgs_host ? h->stage_msgs : nullptr, cb - e0 * HOST_BITS_ROW,
                           reinterpret_cast<float *>(cb + cnt * HOST_BITS_ROW) - e0, cb + cnt * (HOST_BITS_ROW + sizeof(float)) - e0, kflags | CC4_STEP_REWARD, h->sweep };
             k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * (size_t)epb, st>>>(h->p, (int)e0, (int)(e0 + cnt), epb, io);
             h->launches++;
             CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaMemcpyAsync(hstage + e0 * HOST_ROW, cb, cnt * HOST_ROW, cudaMemcpyDeviceToHost, st));
+            if (!h->zero_copy) CUDA_TRY(cudaMemcpyAsync(hstage + e0 * HOST_ROW, cb, cnt * HOST_ROW, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaEventRecord(h->ev_chunk[ci], st));
         }
         int c = 0;
