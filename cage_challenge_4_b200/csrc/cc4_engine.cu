@@ -1178,7 +1178,7 @@ struct HostPool {
         published.store(p);
         if (sleepers.load() > 0) { std::lock_guard<std::mutex> lk(m); cv.notify_all(); }
     }
-    void wait() { while (done.load() != published.load()) relax(); }
+    void wait() { while (done.load() != published.load()) if (!try_run()) relax(); }      /* the caller lends a hand with what is left */
     ~HostPool()
     {
         stop.store(true);

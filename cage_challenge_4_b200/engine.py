@@ -149,10 +149,13 @@ class BatchedCC4:
             flags |= STEP_OBS_COMPACT
             if "obs_compact" not in p:
                 p["obs_compact"] = p["obs"].view(-1)[:n * OBS_COMPACT_LEN].view(n, OBS_COMPACT_LEN)     # same pinned storage
+                p["ptrs"] = (p["obs_compact"].data_ptr(), p["reward"].data_ptr(), p["done"].data_ptr())
             a_ptr = actions.data_ptr() if isinstance(actions, torch.Tensor) else actions.ctypes.data
             m_ptr = 0 if messages is None else (messages.data_ptr() if isinstance(messages, torch.Tensor) else messages.ctypes.data)
-            _native.check(self._L.cc4_step_host(self._h, a_ptr, m_ptr, p["obs_compact"].data_ptr(), p["reward"].data_ptr(),
-                                                p["done"].data_ptr(), flags, self._stream()), "cc4_step_host")
+            o_ptr, r_ptr, d_ptr = p["ptrs"]
+            rc = self._L.cc4_step_host(self._h, a_ptr, m_ptr, o_ptr, r_ptr, d_ptr, flags, self._stream())
+            if rc:
+                _native.check(rc, "cc4_step_host")
             return p["obs_compact"], p["reward"], p["done"]
         a_ptr = actions.data_ptr() if isinstance(actions, torch.Tensor) else actions.ctypes.data
         m_ptr = 0 if messages is None else (messages.data_ptr() if isinstance(messages, torch.Tensor) else messages.ctypes.data)
