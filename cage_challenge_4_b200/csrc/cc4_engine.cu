@@ -1386,7 +1386,9 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
             if (nt <= 0) {
                 int hw = (int)std::thread::hardware_concurrency(), lw = 1;
                 if (const char *e = getenv("LOCAL_WORLD_SIZE")) lw = atoi(e) > 0 ? atoi(e) : 1;
-                nt = hw / lw; if (nt > 8) nt = 8;       /* 8 and 16 threads measure the same (profiles/r02j_e2e_sweep.txt) */
+                nt = hw / lw; if (nt > 8) nt = 8;       /* this rank's share of the hardware threads, at most 8: one GPU on 16 hardware threads
+                                                           measures 664 M agent-steps/s with 8 workers and 628 M with 16 (they spin while a tick is
+                                                           in flight); four ranks on 32 threads: 1.00 G with 8 workers each, 0.80 G with 4 */
             }
             if (nt < 1) nt = 1;
             h->pool = new (std::nothrow) HostPool();
