@@ -79,6 +79,20 @@ class EnterpriseScenarioGenerator:
         self.blue_agent_class, self.red_agent_class, self.green_agent_class, self.steps = blue_agent_class, red_agent_class, green_agent_class, steps
 
 
+class LastAction(int):
+    """An action index that prints as the action's label."""
+
+    def __new__(cls, index: int, label: str):
+        self = super().__new__(cls, index)
+        self.label = label
+        return self
+
+    def __repr__(self):
+        return self.label
+
+    __str__ = __repr__
+
+
 class CybORG:
     """Facade with the constructor of CybORG/env.py:53-77.  `agents` is accepted and ignored exactly as the evaluation
     script uses it (it passes "sim", evaluation.py:70).  Extra keywords choose the batch: num_envs episodes on `device`."""
@@ -91,6 +105,7 @@ class CybORG:
         self.engine = BatchedCC4(num_envs, device=device, seed=self.seed, steps=scenario_generator.steps, red_agent=scenario_generator.red_agent)
         self._episodes_started = 0
         self._last_actions = None
+        self._label_source = None       # set by the wrapper: agent name -> list of action labels
         self.agents = [f"blue_agent_{i}" for i in range(5)]
         self.reset()
 
@@ -115,10 +130,15 @@ class CybORG:
         return MultiBinary(MESSAGE_LENGTH)
 
     def get_last_action(self, agent: str):
-        """Index of the action the agent submitted last tick, as a one-element list like env.py:300 returns."""
+        """The action the agent submitted last tick, as a one-element list like env.py:300 returns: an int (the
+        BlueFixedActionWrapper index) that prints as the action's label, e.g. `Restore server_host_0`, which is what the
+        reference's Action objects print in the evaluation logs (evaluation.py:111-117)."""
         if self._last_actions is None:
             return None
-        return [int(self._last_actions[0, int(agent.rsplit("_", 1)[1])])]
+        b = int(agent.rsplit("_", 1)[1])
+        idx = int(self._last_actions[0, b])
+        labels = self._label_source(agent) if self._label_source is not None else None
+        return [LastAction(idx, labels[idx] if labels is not None and idx < len(labels) else str(idx))]
 
     @property
     def unwrapped(self):
@@ -132,6 +152,7 @@ class BlueFixedActionWrapper:
         self.env, self._pad_spaces, self.env_index = env, pad_spaces, env_index
         self.agents = self.possible_agents = [f"blue_agent_{i}" for i in range(5)]
         self._refresh_masks()
+        env._label_source = self._cached_labels
 
     # -- metadata (BlueFixedActionWrapper._create_hardcoded_metadata :200-231) ------------------------------------------
     def subnets(self, agent_name: str) -> list[str]:
@@ -151,6 +172,13 @@ class BlueFixedActionWrapper:
 
     def _refresh_masks(self):
         self._mask = self.env._mask[self.env_index].cpu().numpy().astype(bool)
+        self._labels = {}
+
+    def _cached_labels(self, agent_name: str) -> list[str]:
+        """Labels of the current episode (they only change with the masks, i.e. at reset)."""
+        if agent_name not in self._labels:
+            self._labels[agent_name] = self.action_labels(agent_name)
+        return self._labels[agent_name]
 
     def action_mask(self, agent_name: str) -> list[bool]:
         b = self._idx(agent_name)

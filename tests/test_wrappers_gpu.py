@@ -190,3 +190,18 @@ def test_random_blue_policy_picks_valid_non_traffic_actions():
     assert len(seen) > 20
     out = run_evaluation_batched(RandomBluePolicy(seed=2), max_eps=32, seed=3, steps=60)
     assert out["episodes"] == 32 and out["mean"] < 0
+
+
+def test_last_action_is_the_index_and_prints_as_the_label():
+    """env.py:300 get_last_action feeds the evaluation logs (evaluation.py:111-117): the mirrored call returns the submitted
+    index, printing as the action's label."""
+    env = make()
+    env.reset()
+    cyborg = env.env
+    assert cyborg.get_last_action("blue_agent_0") is None
+    labels = env.action_labels("blue_agent_4")
+    idx = next(i for i, l in enumerate(labels) if l.startswith("Restore") and "Invalid" not in l)
+    env.step({"blue_agent_4": idx})
+    last = cyborg.get_last_action("blue_agent_4")
+    assert last == [idx] and str(last[0]) == labels[idx] and repr(last) == f"[{labels[idx]}]"
+    assert str(cyborg.get_last_action("blue_agent_0")[0]) == "Sleep"
