@@ -665,7 +665,10 @@ __device__ CC4_INL8 void agent_end_turn(Cx c, int r)
         int iface = ((e >> 9) & 1) || (!key_ip && bit128(rsc, slot));   /* a hostname-keyed entry merges with the RedSessionCheck entry of the same host */
         int hn = !key_ip || syshost;
         uint32_t w = (uint32_t)slot >> 5, bit = 1u << (slot & 31);
-        if ((e >> 12) & 1) { if (iface) seen[w] |= bit; else fail(c, CC4_E_UNREACHABLE); }
+        if ((e >> 12) & 1) {
+            if (iface) { _Pragma("unroll") for (uint32_t q = 0; q < 4; q++) seen[q] |= w == q ? bit : 0u; }     /* static indices: seen[] stays in registers */
+            else fail(c, CC4_E_UNREACHABLE);
+        }
         if (!(key_ip || iface || (f->hn[w] & bit))) { fail(c, CC4_E_UNREACHABLE); continue; }   /* would create host_states[None] */
         if (!(f->present[w] & bit)) fsm_append(c, r, slot, hn, started ? F_K : F_U);
         else if (hn) f->hn[w] |= bit;
@@ -1296,20 +1299,20 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
         const int ports = (int)PT_MASK(pw);
         if (blocking(s, src, target)) return SUCC_FALSE;
         enum { X_HTTP, X_HTTPS, X_SSH, X_SQL, X_HARAKA };
-        int opt[5], w10[5], no = 0;   /* DefaultExploitActionSelector :37-69, weights x10 */
-        if (ports & PB_80) { opt[no] = X_HTTP; w10[no++] = 30; }
-        if (ports & PB_443) { opt[no] = X_HTTPS; w10[no++] = 40; }
-        if (ports & PB_22) { opt[no] = X_SSH; w10[no++] = 1; }
-        if ((ports & PB_3390) && (ports & (PB_80 | PB_443))) { opt[no] = X_SQL; w10[no++] = 50; }
-        if (ports & PB_25) { opt[no] = X_HARAKA; w10[no++] = 60; }
+        /* DefaultExploitActionSelector :37-69: the options in class order, packed four bits each; weights HTTP 3, HTTPS 4,
+           SSH 0.1, SQL 5, Haraka 6, so the option with the largest weight is the last one listed unless SSH is alone */
+        uint32_t opts = 0; int no = 0, top = 0;
+        if (ports & PB_80) { top = no; opts |= (uint32_t)X_HTTP << (4 * no++); }
+        if (ports & PB_443) { top = no; opts |= (uint32_t)X_HTTPS << (4 * no++); }
+        if (ports & PB_22) { opts |= (uint32_t)X_SSH << (4 * no++); }
+        if ((ports & PB_3390) && (ports & (PB_80 | PB_443))) { top = no; opts |= (uint32_t)X_SQL << (4 * no++); }
+        if (ports & PB_25) { top = no; opts |= (uint32_t)X_HARAKA << (4 * no++); }
         if (no < 1) return SUCC_FALSE;
-        int sel = opt[0];
-        if (no > 1) {
-            int top = 0;
-            _Pragma("unroll 1") for (int i = 1; i < no; i++) if (w10[i] > w10[top]) top = i;
-            _Pragma("unroll 1") for (int i = top; i + 1 < no; i++) opt[i] = opt[i + 1];
+        int sel = (int)(opts & 15u);
+        if (no > 1) {       /* the top-weighted option is popped, the choice is uniform among the rest (and one more draw is spent) */
+            const uint32_t rest = (opts & ((1u << (4 * top)) - 1u)) | (opts >> (4 * (top + 1))) << (4 * top);
             no--;
-            sel = opt[rng_int_red(c, r, ST_EXP_OTHER, (uint32_t)no)];
+            sel = (int)(rest >> (4 * rng_int_red(c, r, ST_EXP_OTHER, (uint32_t)no)) & 15u);
             (void)rng_f64_red(c, r, ST_EXP_TOP);
         }
         /* the first live process (list order) that the chosen exploit can attack: ExploitAction._get_vulnerable_process
