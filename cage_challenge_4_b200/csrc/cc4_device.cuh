@@ -418,9 +418,9 @@ __device__ CC4_INL3 int create_pid_on(Cx c, int actor, int h) { return create_pi
 
 /* ---- services ---- */
 __device__ __forceinline__ int svc_count(uint64_t v)
-{   /* entries are filled from 0: index of the first entry whose code is 15 (= empty); 9 when all are in use */
+{   /* entries are filled from 0 and never removed, so the empty ones (code 15) are a suffix: 9 - their number */
     const uint64_t t = v & (v >> 1) & (v >> 2) & (v >> 3) & 0x0102040810204081ull;      /* bit 7i set iff the low nibble of entry i is 15 */
-    return t ? (__ffsll((long long)t) - 1) / 7 : 9;
+    return 9 - __popcll(t);
 }
 __device__ __forceinline__ bool svc_active(uint64_t v, uint32_t entry) { return !((entry & 15u) == K_OT && (v & SVC_OT_STOPPED)); }
 __device__ __forceinline__ uint64_t svc_set(uint64_t v, int i, uint32_t entry) { return (v & ~(0x7Full << (7 * i))) | ((uint64_t)entry << (7 * i)); }
@@ -1077,11 +1077,12 @@ __device__ CC4_INL6 void do_phishing(Cx c, int g)
  * dependent.  Result: bits 0-7 = reward penalty (LWF / ASF, BlueRewardMachine.py:35-65) as a positive number.
  * The agent's Philox block stays in registers: 4 words cover Sleep / AccessService, LocalWork needs a second block. */
 #define GREEN_PHISH 0x100
-__device__ CC4_INL8 int green_tick(Cx c, int g, uint32_t *ev_words)
+/* tape mode (parity replay): the same tick with the recorded draws, out of line */
+__device__ __noinline__ int green_tick_tape(Cx c, int g, uint32_t *ev_words)
 {
     Cc4Dyn *s = DYN(c);
     const int actor = A_GREEN0 + g, gh = green_host_of(s, g), gsn = gh >> 4;
-    const bool tape = g_blk.rng_mode == 1;
+    const bool tape = true;
     const uint64_t v = WC(c)->k->svc64[gh];     /* issued ahead of the Philox rounds: only LocalWork (1 in 3) uses it, but the latency hides */
     /* production mode: the agent's whole tick fits the four words of ONE Philox block (word 0: action choice and, cut from
        its low half, the service pick; the phishing follow-up continues the stream at word j) */
@@ -1120,6 +1121,53 @@ __device__ CC4_INL8 int green_tick(Cx c, int g, uint32_t *ev_words)
         else if ((tape ? rng_f64(c, actor, ST_AS_FP, 0) : f64_from_word(blk.z)) < 0.01) atomicOr(&ev_words[d >> 2], EV_NET << ((d & 3) * 8));
     }
     if (!tape) SCR(c)->ctr_g[g] = (uint8_t)j;
+    return out;
+}
+
+__device__ CC4_INL8 int green_tick(Cx c, int g, uint32_t *ev_words)
+{
+    if (g_blk.rng_mode == 1) return green_tick_tape(c, g, ev_words);
+    Cc4Dyn *s = DYN(c);
+    const int actor = A_GREEN0 + g, gh = green_host_of(s, g), gsn = gh >> 4;
+    const uint64_t v = WC(c)->k->svc64[gh];     /* issued ahead of the Philox rounds: only LocalWork (1 in 3) uses it, but the latency hides */
+    /* the agent's whole tick fits the four words of ONE Philox block (word 0: action choice and, cut from its low half, the
+       service pick; the phishing follow-up continues the stream at word j).  word / 2^32 < 0.01 is the integer test
+       word < P01: the double product is exact and 0.01 * 2^32 = 42 949 672.96 */
+    const uint32_t P01 = 42949673u;
+    const uint4 blk = philox_block(c, actor, 0);
+    uint32_t j = 1;
+    int out = 0;
+    const uint32_t choice = __umulhi(blk.x, 3u);
+    if (choice == 1) {
+        const uint32_t frac = blk.x * 3u;
+        const int n = svc_count(v);
+        const bool ot_stopped = (v & SVC_OT_STOPPED) && n > 1 && (SVC_ENTRY(v, 1) & 15u) == K_OT;     /* the OT service is entry 1 wherever it exists */
+        const int na = n - (int)ot_stopped;
+        if (na == 0) out = -c_reward[s->phase][gsn][0];
+        else {
+            int pick = (int)__umulhi(frac, (uint32_t)na);
+            if (ot_stopped && pick >= 1) pick++;        /* pick-th ACTIVE service */
+            const uint32_t rel = (SVC_ENTRY(v, pick) >> 4) * 20u;
+            j = 2;
+            if (__umulhi(blk.y, 100u) >= rel) out = -c_reward[s->phase][gsn][0];
+            else {
+                j = 4;
+                if (blk.z < P01) atomicOr(&ev_words[gh >> 2], EV_PROC << ((gh & 3) * 8));
+                if (blk.w < P01) out = GREEN_PHISH;
+            }
+        }
+    } else if (choice == 0) {
+        /* destination = k-th server (creation order: subnets ascending, server_host_0..) among the allowed subnets,
+           GreenAccessService.py:94-115; the cumulative counts per source subnet were tabulated by ph_setup */
+        const uint64_t cum = SCR(c)->g.as_cum[gsn];
+        const uint32_t k = __umulhi(blk.y, (uint32_t)(cum >> 56)), kk = k * 0x01010101u;
+        j = 3;
+        const int dsn = (__popc(__vcmpleu4((uint32_t)cum, kk)) + __popc(__vcmpleu4((uint32_t)(cum >> 32), kk))) >> 3;
+        const int d = dsn * 16 + (int)(k - (dsn ? (uint32_t)(cum >> (8 * (dsn - 1))) & 0xFFu : 0u));
+        if ((s->blocks[gsn] >> dsn & 1) || (s->blocks[dsn] >> gsn & 1)) { atomicOr(&ev_words[d >> 2], EV_NET << ((d & 3) * 8)); out = -c_reward[s->phase][gsn][1]; }
+        else if (blk.z < P01) atomicOr(&ev_words[d >> 2], EV_NET << ((d & 3) * 8));
+    }
+    SCR(c)->ctr_g[g] = (uint8_t)j;
     return out;
 }
 
