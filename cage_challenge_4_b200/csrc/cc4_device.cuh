@@ -732,6 +732,40 @@ template <class RI, class RF> __device__ __forceinline__ uint32_t fsm_choose_act
     return pack_act(a, 0);
 }
 
+/* The same choice in production mode, on the words of the agent's first Philox block (`j` = next unused word, advanced):
+ * the action draw u = word / 2^32 is compared as an integer (u < cum / 4  <=>  word < cum * 2^30, both sides exact), the
+ * table sanity check is left to the tape path, a one-option parameter pick spends no word (as rng_int). */
+__device__ __forceinline__ uint32_t fsm_choose_action_words(Cx c, int r, int slot, const uint4 &blk, uint32_t &j)
+{
+    Cc4Dyn *s = DYN(c);
+    const Cc4Fsm *f = &s->fsm[r];
+    const int st = fsm_state(f, slot), f_hn = bit128(f->hn, slot);
+    const int8_t (*prob4)[9] = c_fsm_prob4[g_blk.red_variant];
+    const uint32_t wa = u4_word(blk, j++);
+    int col = -1, cum = 0, last = -1;
+    _Pragma("unroll 1") for (int i = 0; i < 9 && col < 0; i++) {
+        const int cc = c_red_aspace_cols[i], p = prob4[st][cc];
+        if (p < 0) continue;
+        last = cc; cum += p;
+        if (cum >= 4 || wa < ((uint32_t)cum << 30)) col = cc;
+    }
+    if (col < 0) col = last;
+    Act a = { c_fsm_col_code[col], -1, -1, 0 };
+    auto pick = [&](uint32_t n) -> uint32_t { return n == 1 ? 0u : __umulhi(u4_word(blk, j++), n); };
+    const int nss = s->n_ss[r];
+    if (col == 0) {
+        const uint32_t known = s->sn_known[r];
+        a.subnet = (int)__fns(known, 0, (int)pick((uint32_t)__popc(known)) + 1);        /* pk-th known subnet in creation order */
+    } else {
+        if (col >= 5 && !f_hn) fail(c, CC4_E_UNREACHABLE);
+        a.host = slot;
+    }
+    if (nss == 0) fail(c, CC4_E_UNREACHABLE); else a.session = s->ss[r][pick((uint32_t)nss)];
+    if (col >= 1 && col <= 4 && !bit128(s->ip_known[r], a.host)) a.code = AC_INVALID;
+    if (col >= 5 && !bit128(s->hn_known[r], a.host)) a.code = AC_INVALID;
+    return pack_act(a, 0);
+}
+
 /* DiscoveryFSRed (FSMRedVariants.py:72-122), out of line: draws through the generic stream functions (the same words in
  * the same order as the register-resident path of red_policy would take) */
 __device__ __noinline__ uint32_t red_policy_discovery(Cx c, int r, uint32_t lo, uint32_t hi)
@@ -823,7 +857,7 @@ __device__ CC4_INL8 uint32_t red_policy(Cx c, int r)
     /* FiniteStateRedAgent: uniform over the known hosts in list order */
     const int pick = (int)ri(ST_FSM_HOST, (uint32_t)nk);
     const int pos = pick < nlo ? (int)__fns(lo, 0, pick + 1) : 32 + (int)__fns(hi, 0, pick - nlo + 1);
-    const uint32_t act = fsm_choose_action(c, r, s->fsm_order[r][pos], ri, rf);
+    const uint32_t act = tape ? fsm_choose_action(c, r, s->fsm_order[r][pos], ri, rf) : fsm_choose_action_words(c, r, s->fsm_order[r][pos], blk, j);
     if (!tape) {
         Scratch *x = SCR(c);
         ctr_set(x, actor, j);
