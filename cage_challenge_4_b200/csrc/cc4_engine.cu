@@ -419,20 +419,25 @@ __device__ __forceinline__ void ph_blue(Cx c, bool with_exec = true, uint32_t ag
     /* filter_actions looks at the sessions as they are BEFORE anything executes; blue / green sessions never go away */
     /* (the pool index found here stays valid for the red phase unless a session is deleted in between: sess_moved) */
     {
+        /* every pool entry belongs to one red agent and (agent, ident) is unique, so a lane only compares its entry's ident
+           with the one its owner's action names and, on a match, files the pool index under that agent */
         const int n = s->n_sess;
-        uint32_t want = 0;      /* lanes 0..5: agent | ident << 8 | needs << 31 */
-        if (lane < CC4_NRED) { uint32_t w = x->subw[A_RED0 + lane]; want = (uint32_t)lane | IP_SESSION(w) << 8 | (uint32_t)!(IP_CODE(w) == AC_SLEEP || IP_CODE(w) == AC_INVALID) << 31; }
-        int at = -1;            /* lane r: pool index of agent r's session */
-        _Pragma("unroll 1") for (int base = 0; base < n; base += 32) {
-            const int i = base + lane;
-            const uint32_t key = i < n ? (SF_AGENT((uint32_t)s->sessf[i]) | S_ID(s->sess[i]) << 8) : 0xFFFFFFFFu;
-            _Pragma("unroll") for (int r = 0; r < CC4_NRED; r++) {
-                const uint32_t wr = __shfl_sync(0xFFFFFFFFu, want, r);
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, key == (wr & 0x7FFFFFFFu));
-                if (lane == r && at < 0 && m) at = base + __ffs(m) - 1;
-            }
+        uint32_t want = 0;      /* lanes 0..5: ident | needs << 8 */
+        if (lane < CC4_NRED) {
+            const uint32_t w = x->subw[A_RED0 + lane];
+            want = IP_SESSION(w) | (uint32_t)!(IP_CODE(w) == AC_SLEEP || IP_CODE(w) == AC_INVALID) << 8;
+            x->act_si[lane] = -1;
         }
-        if (lane < CC4_NRED) { x->act_si[lane] = (int16_t)at; x->dropped[A_RED0 + lane] = (want >> 31) && at < 0; }
+        const uint32_t p0 = __shfl_sync(0xFFFFFFFFu, want, 0) | __shfl_sync(0xFFFFFFFFu, want, 1) << 10 | __shfl_sync(0xFFFFFFFFu, want, 2) << 20;
+        const uint32_t p1 = __shfl_sync(0xFFFFFFFFu, want, 3) | __shfl_sync(0xFFFFFFFFu, want, 4) << 10 | __shfl_sync(0xFFFFFFFFu, want, 5) << 20;
+        __syncwarp();
+        _Pragma("unroll 1") for (int i = lane; i < n; i += 32) {
+            const uint32_t r = SF_AGENT((uint32_t)s->sessf[i]);
+            const uint32_t wr = (r < 3 ? p0 >> (10 * r) : p1 >> (10 * (r - 3))) & 0x3FFu;
+            if ((wr >> 8) && (wr & 0xFFu) == S_ID(s->sess[i])) x->act_si[r] = (int16_t)i;
+        }
+        __syncwarp();
+        if (lane < CC4_NRED) x->dropped[A_RED0 + lane] = (want >> 8) && x->act_si[lane] < 0;
         if (lane == 0) x->sess_moved = 0;
     }
     __syncwarp();
