@@ -651,25 +651,31 @@ __device__ __forceinline__ void ph_finish(Cx c, const uint8_t *msgs /* [5] or nu
 #ifndef CC4_BLUE_PARTS
 #define CC4_BLUE_PARTS 1
 #endif
+#ifndef CC4_GROUP_FIXED
+#define CC4_GROUP_FIXED 1       /* the lane-per-actor phases take item = warp instead of drawing from the shared counter */
+#endif
+#ifndef CC4_FIXED_PHASES
+#define CC4_FIXED_PHASES 5      /* k_step phases with a fixed episode -> warp map: bit 0 setup, bit 1 reassignment, bit 2 finish (profiles/r02t_variants.txt) */
+#endif
 #ifndef CC4_STATIC_ASSIGN
 #define CC4_STATIC_ASSIGN 0     /* 1: episode e of a block is always handled by warp e % warps (tuning knob; default: shared counter) */
 #endif
-template <class F> __device__ __forceinline__ void each_episode(int ph, int first, int n_local, int *next, F f, const PhaseOrder *order = nullptr, int ctr = -1)
+template <bool FIXED = false, class F> __device__ __forceinline__ void each_episode(int ph, int first, int n_local, int *next, F f, const PhaseOrder *order = nullptr, int ctr = -1)
 {
     if (ctr < 0) ctr = ph;      /* which work counter the phase uses (the parts of a cut phase share `ph`) */
 #ifdef CC4_PHASE_CLOCKS
     const long long tb0 = clock64();
 #endif
-#if CC4_STATIC_ASSIGN
-    _Pragma("unroll 1") for (int e = threadIdx.x >> 5; e < n_local; e += WARPS_PER_BLOCK) {
-#else
-    _Pragma("unroll 1") for (;;) {
-        int e = 0;
-        if (lane_id() == 0) e = atomicAdd(&next[ctr], 1);
-        e = __shfl_sync(0xFFFFFFFFu, e, 0);
-        if (e >= n_local) break;
-        if (order) e = order_get(order, e);
-#endif
+    /* FIXED: phases whose episodes cost about the same (setup, reassignment, finish) hand episode e to warp e % 32 */
+    _Pragma("unroll 1") for (int e_fixed = (int)(threadIdx.x >> 5);; e_fixed += WARPS_PER_BLOCK) {
+        int e = e_fixed;
+        if (FIXED || CC4_STATIC_ASSIGN) { if (e >= n_local) break; }
+        else {
+            if (lane_id() == 0) e = atomicAdd(&next[ctr], 1);
+            e = __shfl_sync(0xFFFFFFFFu, e, 0);
+            if (e >= n_local) break;
+            if (order) e = order_get(order, e);
+        }
         const Cx c = (Cx)(e * (int)sizeof(WarpSmem));
 #ifdef CC4_PHASE_CLOCKS
         const long long t0 = clock64();
@@ -697,10 +703,14 @@ template <int per, int parts = 1, class F> __device__ __forceinline__ void each_
     const long long tb0 = clock64();
 #endif
     const int n_per = (n_local + per - 1) / per, n_items = parts * n_per, sub = lane_id() / (32 / per), sl = lane_id() % (32 / per);
-    _Pragma("unroll 1") for (;;) {
-        int it = 0;
+    /* the items of these phases cost about the same and there are at most as many as warps (64 episodes): warp w takes
+       item w, w + 32, ... without a trip to the shared counter */
+    _Pragma("unroll 1") for (int it_fixed = (int)(threadIdx.x >> 5);; it_fixed += WARPS_PER_BLOCK) {
+        int it = it_fixed;
+#if !CC4_GROUP_FIXED
         if (lane_id() == 0) it = atomicAdd(&next[ph], 1);
         it = __shfl_sync(0xFFFFFFFFu, it, 0);
+#endif
         if (it >= n_items) break;
         const int part = parts > 1 ? it / n_per : 0;       /* `parts` kinds of item over the same episodes (f gets part through sl: sl + 32 * part) */
         const int e = (it - part * n_per) * per + sub;
@@ -770,7 +780,7 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
         mbar_expect_tx(&ld_bar[threadIdx.x], (uint32_t)sizeof(Cc4Dyn));
         bulk_load(DYN((Cx)(threadIdx.x * (int)sizeof(WarpSmem))), p.dyn + first + threadIdx.x, (uint32_t)sizeof(Cc4Dyn), &ld_bar[threadIdx.x]);
     }
-    each_episode(PH_SETUP, first, n_local, next, [&](Cx c, int e) {
+    each_episode<CC4_FIXED_PHASES & 1>(PH_SETUP, first, n_local, next, [&](Cx c, int e) {
         init_ctx(c, p, first + e, 0);
         mbar_wait(&ld_bar[e], 0);
         ph_setup(c);
@@ -822,13 +832,13 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
 #else
     each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c, !(CC4_SPLIT & 2)); }, &ord_red);
 #endif
-    each_episode(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { ph_reassign(c); });
+    each_episode<(CC4_FIXED_PHASES >> 1) & 1>(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { ph_reassign(c); });
 #endif
 #if CC4_MERGE & 2
     each_episode(PH_FINISH, first, n_local, next, [&](Cx c, int e) { ph_endturn(c, true, lane_id()); __syncwarp(); finish(c, e); });
 #else
     each_group<CC4_ENDTURN_PER>(PH_ENDTURN, first, n_local, next, [&](Cx c, int, bool exists, int sl) { ph_endturn(c, exists, sl); });
-    each_episode(PH_FINISH, first, n_local, next, finish);
+    each_episode<(CC4_FIXED_PHASES >> 2) & 1>(PH_FINISH, first, n_local, next, finish);
 #endif
 #endif
     if (lane_id() == 0) bulk_store_wait();      /* shared memory must outlive the copies this lane started */
