@@ -32,7 +32,7 @@ SVC_BYTES = 128 * 8                          # per-host service table: read in p
 EPISODE_TICKS = 499                          # steps=500 -> done at step_count >= 499 (EnterpriseScenarioGenerator.py:870)
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch at 65536 episodes from the committed
 # `ncu --set full` capture (profiles/), or None when no capture matches the current kernel
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 471_644_416      # profiles/r02p_kstep_ncu_full_summary.txt: 303.0 MB read + 168.6 MB written
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 462_498_560      # profiles/r02v_kstep_ncu_full_summary.txt: 301.0 MB read + 161.5 MB written
 
 
 def load_peaks():
