@@ -526,7 +526,10 @@ __device__ __forceinline__ bool blocking(const Cc4Dyn *s, int src_slot, int othe
 }
 
 /* ---- observation bookkeeping for one red agent (ObservationSet / ActionSpace.update ActionSpace.py:170-212) ---- */
-__device__ CC4_INL4 void obs_entry(Cx c, int r, int key_ip, int slot, int iface, int subnet_if, int syshost, int sess)
+#ifndef CC4_INL_OBS
+#define CC4_INL_OBS CC4_INL4
+#endif
+__device__ CC4_INL_OBS void obs_entry(Cx c, int r, int key_ip, int slot, int iface, int subnet_if, int syshost, int sess)
 {   /* [uniform] */
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     if (syshost) set128(s->hn_known[r], slot);
