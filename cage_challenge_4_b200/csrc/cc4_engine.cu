@@ -1083,10 +1083,8 @@ static void expand_rows_generic(const uint32_t *rows, uint8_t *dst, size_t cnt, 
     }
 }
 #if defined(__x86_64__)
-/* AVX2 form: 32 bits -> 32 bytes in four instructions.  `stream` (CC4_HOST_STREAM=1): rows are built in a cache-resident
-   block and leave it with streaming stores; off by default, because callers hand in the same output buffer every tick and
-   it then stays in the host's caches (measured on the GPU box, 16 threads: streaming stores 549 M agent-steps/s end to
-   end, ordinary stores 600 M+). */
+/* AVX2 form: 32 bits -> 32 bytes in four instructions.  `stream`: rows are built in a cache-resident block and leave it
+   with streaming stores (see stream_rows for when). */
 __attribute__((target("avx2"))) static inline __m256i spread32(uint32_t w)
 {
     const __m256i sel = _mm256_setr_epi64x(0x0000000000000000ll, 0x0101010101010101ll, 0x0202020202020202ll, 0x0303030303030303ll);
@@ -1128,16 +1126,26 @@ __attribute__((target("avx2"))) static void expand_rows_avx2(const uint32_t *row
     if (stream) _mm_sfence();       /* the streamed rows are visible before the job is reported done */
 }
 #endif
-static void expand_rows(const uint32_t *rows, uint8_t *dst, size_t cnt, bool compact)
+static void expand_rows(const uint32_t *rows, uint8_t *dst, size_t cnt, bool compact, bool stream)
 {
 #if defined(__x86_64__)
     static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("CC4_HOST_NO_AVX2");
-    static const bool stream = getenv("CC4_HOST_STREAM") && getenv("CC4_HOST_STREAM")[0] == '1';
     if (avx2) { expand_rows_avx2(rows, dst, cnt, compact, stream); return; }
 #endif
+    (void)stream;
     expand_rows_generic(rows, dst, cnt, compact);
 }
-struct ExpandJob { const uint32_t *rows; uint8_t *dst; size_t cnt; bool compact; };
+/* Streaming stores pay when the rows of one tick do not fit the host's caches: with all ranks of the node together above
+   64 MB (two or more GPUs at 65 536 episodes each; measured on four: 1.33 G agent-steps/s against 1.20 G), not for one rank
+   (38 MB: 568 M against 612 M).  CC4_HOST_STREAM=0 / 1 overrides. */
+static bool stream_rows(size_t bytes_per_tick)
+{
+    if (const char *e = getenv("CC4_HOST_STREAM")) return e[0] == '1';
+    size_t lw = 1;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) lw = atoi(e) > 0 ? (size_t)atoi(e) : 1;
+    return lw * bytes_per_tick > ((size_t)64 << 20);
+}
+struct ExpandJob { const uint32_t *rows; uint8_t *dst; size_t cnt; bool compact, stream; };
 /* The pool behind cc4_step_host.  Jobs go through a ring with monotonically increasing publish / claim / done counters;
  * idle workers spin for a few hundred microseconds before they go to sleep, because within a tick the chunks arrive
  * every ~60 us and a futex wake-up per chunk (and one more for the caller) would sit on the critical path of the call. */
@@ -1162,7 +1170,7 @@ struct HostPool {
         while (i != published.load()) {
             if (next.compare_exchange_weak(i, i + 1)) {
                 const ExpandJob j = ring[i % RING];
-                expand_rows(j.rows, j.dst, j.cnt, j.compact);
+                expand_rows(j.rows, j.dst, j.cnt, j.compact, j.stream);
                 done.fetch_add(1);
                 return true;
             }
@@ -1185,11 +1193,11 @@ struct HostPool {
         }
     }
     void start(int n) { for (int i = 0; i < n; i++) th.emplace_back([this] { run(); }); }
-    void submit(const uint32_t *rows, uint8_t *dst, size_t cnt, bool compact, size_t row_bytes)
+    void submit(const uint32_t *rows, uint8_t *dst, size_t cnt, bool compact, size_t row_bytes, bool stream)
     {   /* one job per thread; the caller waits for every job of a tick before the next tick (at most 16 chunks x 16 jobs in flight) */
         const size_t parts = th.size(), per = (cnt + parts - 1) / parts;
         unsigned p = published.load();
-        for (size_t o = 0; o < cnt; o += per) ring[p++ % RING] = { rows + o * CC4_OBS_BITS_WORDS, dst + o * row_bytes, cnt - o < per ? cnt - o : per, compact };
+        for (size_t o = 0; o < cnt; o += per) ring[p++ % RING] = { rows + o * CC4_OBS_BITS_WORDS, dst + o * row_bytes, cnt - o < per ? cnt - o : per, compact, stream };
         published.store(p);
         if (sleepers.load() > 0) { std::lock_guard<std::mutex> lk(m); cv.notify_all(); }
     }
@@ -1452,6 +1460,7 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
         }
         int c = 0;
         cudaError_t err = cudaSuccess;
+        const bool stream = stream_rows(n * obs_row);
         static const bool trace = getenv("CC4_HOST_TRACE") != nullptr;      /* diagnostics: host timeline of one call in microseconds */
         auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
         const double t_enq = trace ? now_us() : 0.0;
@@ -1463,7 +1472,7 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
             if (err != cudaSuccess) break;
             if (trace) t_ev[c] = now_us();
             const uint8_t *hb = hstage + e0 * HOST_ROW;
-            h->pool->submit(reinterpret_cast<const uint32_t *>(hb), obs_host + e0 * obs_row, cnt, compact, obs_row);
+            h->pool->submit(reinterpret_cast<const uint32_t *>(hb), obs_host + e0 * obs_row, cnt, compact, obs_row, stream);
             if (want_rew) memcpy(reward_host + e0, hb + cnt * HOST_BITS_ROW, cnt * sizeof(float));
             if (done_host) memcpy(done_host + e0, hb + cnt * (HOST_BITS_ROW + sizeof(float)), cnt);
         }
@@ -1505,7 +1514,7 @@ extern "C" int cc4_expand_obs_bits(const uint32_t *rows_host, uint8_t *obs_host,
 {
     if (!rows_host || !obs_host) return set_err(CC4_ERR_ARG, "cc4_expand_obs_bits: null%s", "");
     std::call_once(g_spread_once, spread_init);
-    expand_rows(rows_host, obs_host, n_rows, compact != 0);
+    expand_rows(rows_host, obs_host, n_rows, compact != 0, stream_rows(0));
     return CC4_OK;
 }
 

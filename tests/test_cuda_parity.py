@@ -310,8 +310,8 @@ def test_compact_observations_are_the_unpadded_vectors(n):
         assert torch.equal(o3, o2.cpu()) and torch.equal(r1.cpu(), r3) and torch.equal(r1, r2) and torch.equal(d1.cpu(), d3)
 
 
-@pytest.mark.parametrize("n", [3, 9473])
-def test_bit_row_observations_and_both_host_paths(n, monkeypatch):
+@pytest.mark.parametrize("n,stream", [(3, "0"), (9473, "0"), (9473, "1")])
+def test_bit_row_observations_and_both_host_paths(n, stream, monkeypatch):
     """CC4_STEP_OBS_BITS: row = the compact row as bits + the mission phase; cc4_step_host moves these rows and expands them
     on the host (default) or copies byte rows (CC4_HOST_EXPAND=0): all the same bytes, padded and compact."""
     from cage_challenge_4_b200.engine import unpack_bits
@@ -319,6 +319,7 @@ def test_bit_row_observations_and_both_host_paths(n, monkeypatch):
     monkeypatch.setenv("CC4_HOST_EXPAND", "0")
     e, f = (_engine(n, device=0, seed=6) for _ in range(2))
     monkeypatch.delenv("CC4_HOST_EXPAND")
+    monkeypatch.setenv("CC4_HOST_STREAM", stream)       # streaming stores of the expanded rows (the multi-rank default)
     for x in (a, b, c, d, e, f):
         x.reset()
     g = np.random.default_rng(5)
