@@ -110,9 +110,10 @@ int cc4_step(cc4_handle *h, const int32_t *actions_dev, const uint8_t *msgs_dev,
  * synchronises the stream (the e2e path bench.py times; host buffers should be pinned for full speed).  The batch is
  * cut into chunks that are pipelined over two streams; observation rows cross PCIe as bit rows (CC4_STEP_OBS_BITS) and
  * are expanded to the requested uint8 layout by a small pool of host threads (CC4_HOST_THREADS, default: the host's
- * hardware threads / LOCAL_WORLD_SIZE, at most 8) while the next chunks are in flight; CC4_HOST_STREAM=0/1 forces ordinary / streaming stores for the expanded rows (default: streaming when the node's ranks
- * together write more than 64 MB per tick); CC4_HOST_EXPAND=0 copies byte
- * rows instead.  With CC4_STEP_OBS_BITS in `flags` the bit rows themselves are returned (obs_host = uint32 [n][20]). */
+ * hardware threads / LOCAL_WORLD_SIZE, at most 8) while the next chunks are in flight.  Environment knobs:
+ * CC4_HOST_STREAM=0/1 forces ordinary / streaming stores for the expanded rows (default: streaming when the node's ranks
+ * together write more than 64 MB per tick); CC4_HOST_EXPAND=0 copies byte rows instead of bit rows.  With
+ * CC4_STEP_OBS_BITS in `flags` the bit rows themselves are returned (obs_host = uint32 [n][20]). */
 int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const uint8_t *msgs_host, uint8_t *obs_host,
                   float *reward_host, uint8_t *done_host, int flags, void *stream);
 
