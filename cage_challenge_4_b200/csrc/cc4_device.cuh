@@ -443,6 +443,17 @@ __device__ __forceinline__ int kth_bit(uint32_t m, int k)
     const int lane = lane_id();
     return __ffs(__ballot_sync(FULLMASK, (m >> lane & 1u) && __popc(m & ((1u << lane) - 1u)) == k)) - 1;
 }
+/* the same for one lane on its own mask (red policy): five popcount steps instead of __fns (65 instructions with branches) */
+__device__ __forceinline__ int nth_bit(uint32_t m, int n)
+{
+    int pos = 0, c;
+    c = __popc(m & 0xFFFFu); if (n >= c) { n -= c; pos += 16; m >>= 16; }
+    c = __popc(m & 0xFFu);   if (n >= c) { n -= c; pos += 8;  m >>= 8; }
+    c = __popc(m & 0xFu);    if (n >= c) { n -= c; pos += 4;  m >>= 4; }
+    c = __popc(m & 0x3u);    if (n >= c) { n -= c; pos += 2;  m >>= 2; }
+    c = (int)(m & 1u);       if (n >= c) pos += 1;
+    return pos;
+}
 /* pool index of the k-th (0-based) entry that satisfies pred, -1 if there are fewer */
 template <class Pred> __device__ __forceinline__ int sess_kth(const Cc4Dyn *s, int k, Pred pred)
 {
@@ -859,7 +870,7 @@ __device__ CC4_INL8 uint32_t red_policy(Cx c, int r)
     auto rf = [&](int site, uint32_t n) -> double { return tape ? rng_f64(c, actor, site, n) : f64_from_word(u4_word(blk, j++)); };
     /* FiniteStateRedAgent: uniform over the known hosts in list order */
     const int pick = (int)ri(ST_FSM_HOST, (uint32_t)nk);
-    const int pos = pick < nlo ? (int)__fns(lo, 0, pick + 1) : 32 + (int)__fns(hi, 0, pick - nlo + 1);
+    const int pos = pick < nlo ? nth_bit(lo, pick) : 32 + nth_bit(hi, pick - nlo);
     const uint32_t act = tape ? fsm_choose_action(c, r, s->fsm_order[r][pos], ri, rf) : fsm_choose_action_words(c, r, s->fsm_order[r][pos], blk, j);
     if (!tape) {
         Scratch *x = SCR(c);
@@ -1365,7 +1376,7 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
                     const bool decoy = P_KIND(w) >= K_D_APACHE && P_KIND(w) <= K_D_VSFTPD;
                     const uint32_t j = p0 + 2u * (uint32_t)__popc(lm & ((1u << lane) - 1u)) + (decoy ? 0u : 1u);
                     const uint4 v = philox_block(c, actor, j >> 2);
-                    hit = f64_from_word(u4_word(v, j & 3u)) <= (decoy ? 0.5 : 0.1);
+                    hit = u4_word(v, j & 3u) <= (decoy ? 2147483648u : 429496729u);      /* word / 2^32 <= 0.5 / 0.1, as integers (0.1 * 2^32 = 429 496 729.6) */
                 }
                 rep |= (int)__any_sync(FULLMASK, hit);
                 p0 += 2u * (uint32_t)__popc(lm);
@@ -1429,7 +1440,7 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
                 if (lane < nh) {
                     const uint32_t j = p0 + (uint32_t)lane;
                     const uint4 v = philox_block(c, actor, j >> 2);
-                    if (0.05 < f64_from_word(u4_word(v, j & 3u))) s->ev[route_hop(src, target, nh, lane)] |= EV_NET;
+                    if (u4_word(v, j & 3u) > 214748364u) s->ev[route_hop(src, target, nh, lane)] |= EV_NET;        /* 0.05 < word / 2^32 (0.05 * 2^32 = 214 748 364.8) */
                 }
                 __syncwarp();
                 ctr_set(x, actor, p0 + (uint32_t)nh);

@@ -493,10 +493,13 @@ __device__ __forceinline__ void green_items(int ph, int first, int n_local, int 
         __syncwarp();
     }
     const int n_items = (total + 31) >> 5;
-    _Pragma("unroll 1") for (;;) {
-        int it = 0;
+    /* items cost the same: warp w takes items w, w + 32, ... (CC4_GREEN_FIXED=0: from the shared counter) */
+    _Pragma("unroll 1") for (int it_fixed = (int)(threadIdx.x >> 5);; it_fixed += WARPS_PER_BLOCK) {
+        int it = it_fixed;
+#if !CC4_GREEN_FIXED
         if (lane == 0) it = atomicAdd(&next[ph], 1);
         it = __shfl_sync(0xFFFFFFFFu, it, 0);
+#endif
         if (it >= n_items) break;
 #ifdef CC4_PHASE_CLOCKS
         const long long t0 = clock64();
@@ -650,6 +653,9 @@ __device__ __forceinline__ void ph_finish(Cx c, const uint8_t *msgs /* [5] or nu
 #endif
 #ifndef CC4_BLUE_PARTS
 #define CC4_BLUE_PARTS 1
+#endif
+#ifndef CC4_GREEN_FIXED
+#define CC4_GREEN_FIXED 1
 #endif
 #ifndef CC4_GROUP_FIXED
 #define CC4_GROUP_FIXED 1       /* the lane-per-actor phases take item = warp instead of drawing from the shared counter */
