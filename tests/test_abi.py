@@ -74,3 +74,20 @@ def test_host_expansion_of_bit_rows_matches_numpy():
     for b in range(5):
         ln = off[b + 1] - off[b]
         assert np.array_equal(padded[:, b, :ln], want[:, off[b]:off[b + 1]]) and not padded[:, b, ln:].any()
+
+
+def test_unpack_bits_matches_the_host_expansion():
+    """engine.unpack_bits (torch, any device) and cc4_expand_obs_bits (C, host) are the same map."""
+    import numpy as np
+    import torch
+    from cage_challenge_4_b200 import _native
+    from cage_challenge_4_b200.engine import unpack_bits
+    L = _native.load()
+    g = np.random.default_rng(1)
+    n = 33
+    rows = g.integers(0, 2**32, (n, 20), dtype=np.uint64).astype(np.uint32)
+    rows[:, 19] = g.integers(0, 3, n)
+    want = np.zeros((n, 578), dtype=np.uint8)
+    assert L.cc4_expand_obs_bits(rows.ctypes.data, want.ctypes.data, n, 1) == 0
+    got = unpack_bits(torch.from_numpy(rows.view(np.int32)))
+    assert np.array_equal(got.numpy(), want)
