@@ -212,7 +212,12 @@ def main():
     env.reset()
     for i in range(max(3, args.warmup)):
         one_step(i)
-    env.reset()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    env.reset()                              # k_reset of the whole batch, timed on its own (reported as reset_ms)
+    r1.record()
+    torch.cuda.synchronize()
+    reset_ms = r0.elapsed_time(r1)
     tick = 0
     ret.zero_()
     barrier()
@@ -273,6 +278,10 @@ def main():
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": workload_config(args),
             "env_steps_per_s": env_sps, "all_agent_steps_per_s": env_sps * 70.0,
+            # an episode is 499 ticks and one reset of the batch (EnterpriseScenarioGenerator on device); the timed region holds a
+            # reset whenever it crosses an episode boundary (--steps > 499); the same figure with one reset per 499 ticks charged:
+            "reset_ms": reset_ms,
+            "value_incl_reset": total_envs * N_BLUE * EPISODE_TICKS / ((ms / args.steps * EPISODE_TICKS + reset_ms) / 1e3),
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": total_envs * args.e2e_steps * N_BLUE / (e2e_ms / 1e3), "unit": "agent-steps/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,

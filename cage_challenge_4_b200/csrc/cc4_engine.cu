@@ -962,9 +962,11 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
     init_ctx(c, p, env, -1);
     if (lane_id() <= CC4_NRED) SCR(c)->blk_id[lane_id()] = 0xFFFFFFFFu;
     __syncwarp();
+    _Pragma("unroll 1") for (int h = lane_id(); h < 128; h += 32) WC(c)->k->svc64[h] = SVC_EMPTY;
+    __syncwarp();
+    /* scenario generation is ONE serial random stream per episode (the reference's draw order): lane 0 */
     if (lane_id() == 0) {
         Cc4Dyn *s = DYN(c); ResetTmp *t = &rs->t; Cc4Stat *st = WC(c)->st;
-        _Pragma("unroll 1") for (int h = 0; h < 128; h++) WC(c)->k->svc64[h] = SVC_EMPTY;
         _Pragma("unroll 1") for (int a = 0; a < 16; a++) s->inprog[a] = IP_NONE;
         /* hosts, EnterpriseScenarioGenerator._generate_hosts :312-371 */
         _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) {
@@ -1013,15 +1015,6 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
             t->procs[h][t->np[h]++] = P_MAKE(pid, K_REDABS, 0, 0);
             s->sess[0] = S_MAKE(pid, 0, h); s->sessf[0] = (uint8_t)(0 | 1 << 3); s->n_sess = 1; s->sess_count[0] = 1; s->red_active = 1;
         }
-        /* process lists + Host.create_backup Host.py:316-371 */
-        _Pragma("unroll 1") for (int h = 0; h < 128; h++) {
-            st->o_nproc[h] = t->np[h];
-            WC(c)->k->pdir[h] = PD_MAKE(h * CC4_OSLAB, t->np[h], 3);
-            uint32_t mx = 0;
-            _Pragma("unroll 1") for (int i = 0; i < t->np[h]; i++) { uint32_t w = t->procs[h][i]; WC(c)->k->parena[h * CC4_OSLAB + i] = w; st->o_procs[h][i] = w; if (P_PID(w) > mx) mx = P_PID(w); }
-            WC(c)->k->pmax[h] = (uint16_t)mx;
-            st->o_svc64[h] = WC(c)->k->svc64[h];
-        }
         WC(c)->k->arena_top = 128 * CC4_OSLAB;
         _Pragma("unroll 1") for (int i = 0; i < 16; i++) st->router_pid[i] = t->router_pid[i];
         /* initial knowledge: AgentInterface.set_init_obs AgentInterface.py:110-117 with the OSINT of :784-785 */
@@ -1031,6 +1024,19 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
         { int h0 = st->red_start[0]; s->fsm_order[0][0] = (uint8_t)h0; s->n_fsm[0] = 1; s->fsm_started = 1;
           set128(s->fsm[0].present, h0); set128(s->fsm[0].hn, h0); set128(s->fsm[0].pl[2], h0); }
         if (g_blk.rng_mode == 1 && g_blk.n_segs > 0 && ctr_get(SCR(c), NAG) != WC(c)->seg[1] - WC(c)->seg[0]) fail(c, CC4_E_TAPE_LEFT);
+    }
+    __syncwarp();
+    {   /* process lists + Host.create_backup Host.py:316-371: the generated lists leave shared memory, a lane per host */
+        ResetTmp *t = &rs->t; Cc4Stat *st = WC(c)->st; Cc4Cold *k = WC(c)->k;
+        _Pragma("unroll 1") for (int h = lane_id(); h < 128; h += 32) {
+            const int np = t->np[h];
+            st->o_nproc[h] = (uint8_t)np;
+            k->pdir[h] = PD_MAKE(h * CC4_OSLAB, np, 3);
+            uint32_t mx = 0;
+            _Pragma("unroll 1") for (int i = 0; i < np; i++) { uint32_t pw = t->procs[h][i]; k->parena[h * CC4_OSLAB + i] = pw; st->o_procs[h][i] = pw; if (P_PID(pw) > mx) mx = P_PID(pw); }
+            k->pmax[h] = (uint16_t)mx;
+            st->o_svc64[h] = k->svc64[h];
+        }
     }
     __syncwarp();
     if (valid && obs) w_write_obs(&w->dyn, &w->x, obs, env);
