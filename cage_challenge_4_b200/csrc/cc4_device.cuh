@@ -322,6 +322,23 @@ __device__ __forceinline__ double rng_f64_red(Cx c, int r, int site)
     return f64_from_word(red_word(c, r));
 }
 
+/* the reset stream (scenario generation, one serial stream per episode): the same fast path, cache slot CC4_NRED */
+__device__ __noinline__ void reset_refill(Cx c, uint32_t b)
+{
+    Scratch *x = SCR(c);
+    const uint4 v = philox_block(c, NAG, b);
+    x->blk_id[CC4_NRED] = b; x->blk[CC4_NRED][0] = v.x; x->blk[CC4_NRED][1] = v.y; x->blk[CC4_NRED][2] = v.z; x->blk[CC4_NRED][3] = v.w;
+}
+__device__ __forceinline__ uint32_t rng_int_reset(Cx c, int site, uint32_t n)
+{
+    if (g_blk.rng_mode == 1) return rng_int(c, NAG, site, n);
+    Scratch *x = SCR(c);
+    const uint32_t j = x->ctr_br[11];
+    x->ctr_br[11] = (uint16_t)(j + 1);
+    if (x->blk_id[CC4_NRED] != (j >> 2)) reset_refill(c, j >> 2);
+    return __umulhi(x->blk[CC4_NRED][j & 3u], n);
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* small helpers                                                                                    */
 /* ------------------------------------------------------------------------------------------------ */

@@ -908,7 +908,7 @@ struct ResetSmem {
 __device__ int gen_pid(Cx c, ResetTmp *t)
 {
     _Pragma("unroll 1") for (int guard = 0; guard < 64; guard++) {
-        int v = (int)rng_int(c, NAG, ST_R_PID, 9000);
+        int v = (int)rng_int_reset(c, ST_R_PID, 9000);
         if (DYN(c)->err & CC4_E_TAPE_END) return 1000 + v;
         if (!(t->used[v >> 5] >> (v & 31) & 1)) { t->used[v >> 5] |= 1u << (v & 31); return 1000 + v; }
     }
@@ -924,9 +924,9 @@ __device__ void gen_host(Cx c, ResetTmp *t, int slot)
     if (sn == S_OZA || sn == S_OZB) { codes[n] = K_OT; pids[n++] = gen_pid(c, t); }
     int opt[3] = { K_APACHE2, K_MYSQLD, K_SMTP }, nopt = 3; uint32_t optpid[3];
     _Pragma("unroll 1") for (int i = 0; i < 3; i++) optpid[i] = gen_pid(c, t);
-    int nadd = (int)rng_int(c, NAG, ST_R_NADDON, 4);
+    int nadd = (int)rng_int_reset(c, ST_R_NADDON, 4);
     _Pragma("unroll 1") for (int i = 0; i < nadd; i++) {
-        int k = (int)rng_int(c, NAG, ST_R_ADDON, (uint32_t)nopt);
+        int k = (int)rng_int_reset(c, ST_R_ADDON, (uint32_t)nopt);
         codes[n] = opt[k]; pids[n++] = optpid[k];
         _Pragma("unroll 1") for (int j = k; j + 1 < nopt; j++) { opt[j] = opt[j + 1]; optpid[j] = optpid[j + 1]; }
         nopt--;
@@ -939,11 +939,11 @@ __device__ int tmp_create_pid(Cx c, ResetTmp *t, int slot)
 {
     uint32_t mx = 0;
     _Pragma("unroll 1") for (int i = 0; i < t->np[slot]; i++) if (P_PID(t->procs[slot][i]) > mx) mx = P_PID(t->procs[slot][i]);
-    return (int)(mx + 1 + rng_int(c, NAG, ST_CREATE_PID, 9));
+    return (int)(mx + 1 + rng_int_reset(c, ST_CREATE_PID, 9));
 }
 __device__ void tmp_add_session_proc(Cx c, ResetTmp *t, int slot, int kind)
 {
-    if (slot >= CC4_SLOT_ROUTER) { t->router_pid[slot - CC4_SLOT_ROUTER] = (uint16_t)(1 + rng_int(c, NAG, ST_CREATE_PID, 9)); return; }
+    if (slot >= CC4_SLOT_ROUTER) { t->router_pid[slot - CC4_SLOT_ROUTER] = (uint16_t)(1 + rng_int_reset(c, ST_CREATE_PID, 9)); return; }
     int pid = tmp_create_pid(c, t, slot);
     t->procs[slot][t->np[slot]++] = P_MAKE(pid, kind, 0, 0);
 }
@@ -970,16 +970,16 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
         _Pragma("unroll 1") for (int a = 0; a < 16; a++) s->inprog[a] = IP_NONE;
         /* hosts, EnterpriseScenarioGenerator._generate_hosts :312-371 */
         _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) {
-            s->nuser[sn] = (uint8_t)(3 + rng_int(c, NAG, ST_R_NUSER, 8));
+            s->nuser[sn] = (uint8_t)(3 + rng_int_reset(c, ST_R_NUSER, 8));
             _Pragma("unroll 1") for (int i = 0; i < s->nuser[sn]; i++) gen_host(c, t, sn * 16 + 6 + i);
-            s->nserver[sn] = (uint8_t)(1 + rng_int(c, NAG, ST_R_NSERVER, 6));
+            s->nserver[sn] = (uint8_t)(1 + rng_int_reset(c, ST_R_NSERVER, 6));
             _Pragma("unroll 1") for (int i = 0; i < s->nserver[sn]; i++) gen_host(c, t, sn * 16 + i);
         }
         /* blue agents :631-698 */
         _Pragma("unroll 1") for (int b = 0; b < CC4_NBLUE; b++) {
             int n = 0;
             _Pragma("unroll 1") for (int i = 0; i < (b == 4 ? 3 : 1); i++) { int sn = b < 4 ? b : S_PAZ + i; n += 1 + s->nuser[sn] + s->nserver[sn]; }
-            int pk = (int)rng_int(c, NAG, ST_R_BLUE_PARENT, (uint32_t)n), parent = -1;
+            int pk = (int)rng_int_reset(c, ST_R_BLUE_PARENT, (uint32_t)n), parent = -1;
             _Pragma("unroll 1") for (int i = 0, k = 0; i < (b == 4 ? 3 : 1) && parent < 0; i++) {
                 int sn = b < 4 ? b : S_PAZ + i, nu = s->nuser[sn], m = 1 + nu + s->nserver[sn];
                 if (pk < k + m) { int j = pk - k; parent = j == 0 ? CC4_SLOT_ROUTER + sn : j <= nu ? sn * 16 + 6 + (j - 1) : sn * 16 + (j - 1 - nu); }
@@ -994,9 +994,9 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
         /* red agents :751-812 */
         _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
             int ns = r == 5 ? 3 : 1;
-            int si = (int)rng_int(c, NAG, ST_R_RED_SUBNET, (uint32_t)ns);
+            int si = (int)rng_int_reset(c, ST_R_RED_SUBNET, (uint32_t)ns);
             int sn = r == 0 ? S_CON : r <= 4 ? r - 1 : S_PAZ + si;
-            int k = (int)rng_int(c, NAG, ST_R_RED_HOST, (uint32_t)(s->nuser[sn] + s->nserver[sn]));
+            int k = (int)rng_int_reset(c, ST_R_RED_HOST, (uint32_t)(s->nuser[sn] + s->nserver[sn]));
             st->red_start[r] = (uint8_t)(k < s->nuser[sn] ? sn * 16 + 6 + k : sn * 16 + (k - s->nuser[sn]));
         }
         /* State.__init__ State.py:108-134: session processes (Host.add_session Host.py:189-196) */
