@@ -919,19 +919,22 @@ __device__ void gen_host(Cx c, ResetTmp *t, int slot)
 {   /* _generate_linux_host_services :530-561 + _generate_linux_host_processes :580-629 */
     int sn = slot >> 4, n = 0;
     uint64_t v = SVC_EMPTY;
-    uint32_t pids[9]; int codes[9];
-    codes[n] = K_SSHD; pids[n++] = gen_pid(c, t);
-    if (sn == S_OZA || sn == S_OZB) { codes[n] = K_OT; pids[n++] = gen_pid(c, t); }
-    int opt[3] = { K_APACHE2, K_MYSQLD, K_SMTP }, nopt = 3; uint32_t optpid[3];
-    _Pragma("unroll 1") for (int i = 0; i < 3; i++) optpid[i] = gen_pid(c, t);
+    uint32_t *pr = t->procs[slot];      /* entries go straight to the host's list in shared memory; the option lists are packed in registers */
+    auto add = [&](uint32_t kind, uint32_t pid) { v = svc_set(v, n, kind | 5u << 4); pr[n++] = P_MAKE(pid, kind, 0, 1); };
+    add(K_SSHD, (uint32_t)gen_pid(c, t));
+    if (sn == S_OZA || sn == S_OZB) add(K_OT, (uint32_t)gen_pid(c, t));
+    uint32_t okind = K_APACHE2 | K_MYSQLD << 4 | K_SMTP << 8;      /* remaining optional services, four bits each ... */
+    uint64_t opid = 0;                                              /* ... and their pids (drawn up front, :588-590), sixteen bits each */
+    _Pragma("unroll 1") for (int i = 0; i < 3; i++) opid |= (uint64_t)(uint32_t)gen_pid(c, t) << (16 * i);
+    int nopt = 3;
     int nadd = (int)rng_int_reset(c, ST_R_NADDON, 4);
     _Pragma("unroll 1") for (int i = 0; i < nadd; i++) {
-        int k = (int)rng_int_reset(c, ST_R_ADDON, (uint32_t)nopt);
-        codes[n] = opt[k]; pids[n++] = optpid[k];
-        _Pragma("unroll 1") for (int j = k; j + 1 < nopt; j++) { opt[j] = opt[j + 1]; optpid[j] = optpid[j + 1]; }
+        const int k = (int)rng_int_reset(c, ST_R_ADDON, (uint32_t)nopt);
+        add(okind >> (4 * k) & 15u, (uint32_t)(opid >> (16 * k)) & 0xFFFFu);
+        okind = (okind & ((1u << (4 * k)) - 1u)) | (okind >> (4 * (k + 1))) << (4 * k);         /* list.pop(k) */
+        opid = (opid & ((1ull << (16 * k)) - 1ull)) | (opid >> (16 * (k + 1))) << (16 * k);
         nopt--;
     }
-    _Pragma("unroll 1") for (int i = 0; i < n; i++) { v = svc_set(v, i, (uint32_t)codes[i] | 5u << 4); t->procs[slot][i] = P_MAKE(pids[i], codes[i], 0, 1); }
     t->np[slot] = (uint8_t)n;
     WC(c)->k->svc64[slot] = v;
 }
