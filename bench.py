@@ -146,7 +146,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=65536, help="episodes per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=60)
+    ap.add_argument("--e2e-steps", type=int, default=499)     # one whole episode through the host-buffer API
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
