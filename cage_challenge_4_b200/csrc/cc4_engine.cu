@@ -1417,7 +1417,7 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
     if (want_obs && !raw_bits && h->host_expand) {
         /* byte rows wanted: the kernel writes bit rows (80 B per episode instead of 578 / 1 050), they cross PCIe into pinned
            staging, and the pool expands chunk k on the host while the chunks after it are still on the device */
-        if (!h->pool) {
+        if (!h->host_bits) {        /* first call: pool, pinned staging, per-chunk events */
             std::call_once(g_spread_once, spread_init);
             int nt = 0;
             if (const char *e = getenv("CC4_HOST_THREADS")) nt = atoi(e);
@@ -1429,12 +1429,14 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
                                                            in flight); four ranks on 32 threads: 1.00 G with 8 workers each, 0.80 G with 4 */
             }
             if (nt < 1) nt = 1;
-            h->pool = new (std::nothrow) HostPool();
-            if (!h->pool) return set_err(CC4_ERR_STATE, "cc4_step_host: out of host memory%s", "");
-            h->pool->start(nt);
+            if (!h->pool) {
+                h->pool = new (std::nothrow) HostPool();
+                if (!h->pool) return set_err(CC4_ERR_STATE, "cc4_step_host: out of host memory%s", "");
+                h->pool->start(nt);
+            }
+            for (int i = 0; i < CC4_MAX_CHUNKS; i++) if (!h->ev_chunk[i]) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
             CUDA_TRY(cudaHostAlloc(&h->host_bits, n * HOST_ROW, cudaHostAllocMapped));
             CUDA_TRY(cudaHostGetDevicePointer(&h->host_bits_dev, h->host_bits, 0));
-            for (int i = 0; i < CC4_MAX_CHUNKS; i++) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
         }
         if ((n + chunk - 1) / chunk > CC4_MAX_CHUNKS) return set_err(CC4_ERR_STATE, "cc4_step_host: too many chunks%s", "");
         timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);

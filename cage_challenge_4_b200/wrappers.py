@@ -140,6 +140,15 @@ class CybORG:
         labels = self._label_source(agent) if self._label_source is not None else None
         return [LastAction(idx, labels[idx] if labels is not None and idx < len(labels) else str(idx))]
 
+    def get_agent_state(self, agent: str = "True", env_index: int = 0) -> dict:
+        """env.py:265 `get_agent_state('True')`: the true state of one episode as a nested dict (see state.true_state; the
+        engine has no IP addresses or files, so the dict is keyed by hostnames and lists processes, services, sessions and
+        events).  Only the true state is available: per-agent dict observations are not reconstructed."""
+        if agent != "True":
+            raise NotImplementedError("only get_agent_state('True') is available; blue agents observe through the BlueFlatWrapper vectors")
+        from .state import true_state
+        return true_state(self.engine.export_canon(env_index))
+
     @property
     def unwrapped(self):
         return self

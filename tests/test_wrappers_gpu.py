@@ -205,3 +205,22 @@ def test_last_action_is_the_index_and_prints_as_the_label():
     last = cyborg.get_last_action("blue_agent_4")
     assert last == [idx] and str(last[0]) == labels[idx] and repr(last) == f"[{labels[idx]}]"
     assert str(cyborg.get_last_action("blue_agent_0")[0]) == "Sleep"
+
+
+def test_true_state_dict_of_the_wrapped_episode():
+    """env.py:265 get_agent_state('True'): hosts of the episode with their processes / services / sessions."""
+    env = make()
+    env.reset()
+    for _ in range(30):
+        env.step({})
+    st = env.env.get_agent_state("True")
+    assert st["step"] == 30 and st["mission_phase"] == 0
+    hosts = st["hosts"]
+    assert "root_internet_host_0" in hosts and "restricted_zone_a_subnet_router" in hosts
+    servers = [h for h in hosts if h.endswith("_server_host_0")]
+    assert len(servers) == 8 and all(any(p["process_name"] == "sshd" for p in hosts[h]["Processes"]) for h in servers)
+    assert sum(len(r["sessions"]) for r in st["red"].values()) >= 1
+    mask_hosts = {h for a in env.possible_agents for h, m in zip([x for x in env.hosts(a) if "router" not in x], env.action_mask(a)) if m}
+    assert {f"{h}" for h in mask_hosts} <= set(hosts)        # every host a blue agent may Analyse exists in the true state
+    with pytest.raises(NotImplementedError):
+        env.env.get_agent_state("blue_agent_0")
