@@ -187,6 +187,12 @@ struct BlockCtx {
     int red_variant;          /* 0 FiniteStateRedAgent, 1 DiscoveryFSRed */
 };
 __shared__ BlockCtx g_blk;
+/* tape mode (parity replay of the reference's recorded draws) or production mode (Philox); CC4_WITH_TAPE=0 builds a
+   library without the tape paths (experiment: what the mode checks and the tape code cost the production kernel) */
+#ifndef CC4_WITH_TAPE
+#define CC4_WITH_TAPE 1
+#endif
+#define CC4_TAPE_ON() (CC4_WITH_TAPE && g_blk.rng_mode == 1)
 /* per-actor draw counters: 16 bits for the blue / red / reset streams, 8 bits for the green ones */
 __device__ __forceinline__ uint32_t ctr_get(const struct Scratch *x, int actor);
 __device__ __forceinline__ void ctr_set(struct Scratch *x, int actor, uint32_t v);
@@ -281,13 +287,13 @@ __device__ CC4_RNG_INLINE uint32_t rng_word(Cx c, int actor)
 __device__ __forceinline__ double f64_from_word(uint32_t w) { return (double)w * 2.3283064365386962890625e-10; }     /* w / 2^32, exact */
 __device__ CC4_INL2 uint32_t rng_int(Cx c, int actor, int site, uint32_t n)
 {
-    if (g_blk.rng_mode == 1) { uint64_t v = tape_next(c, actor, site, 0, n); return v < n ? (uint32_t)v : 0u; }
+    if (CC4_TAPE_ON()) { uint64_t v = tape_next(c, actor, site, 0, n); return v < n ? (uint32_t)v : 0u; }
     if (n == 1 && site == ST_FSM_PARAM) return 0u;      /* a one-option parameter pick spends no word (oracle: rng_int) */
     return __umulhi(rng_word(c, actor), n);
 }
 __device__ CC4_INL2 double rng_f64(Cx c, int actor, int site, uint32_t n)
 {
-    if (g_blk.rng_mode == 1) return __longlong_as_double((long long)tape_next(c, actor, site, 1, n));
+    if (CC4_TAPE_ON()) return __longlong_as_double((long long)tape_next(c, actor, site, 1, n));
     return f64_from_word(rng_word(c, actor));
 }
 
@@ -313,12 +319,12 @@ __device__ __forceinline__ uint32_t red_word(Cx c, int r)
 #endif
 __device__ __forceinline__ uint32_t rng_int_red(Cx c, int r, int site, uint32_t n)
 {
-    if (!CC4_RED_RNG_INLINE || g_blk.rng_mode == 1) return rng_int(c, A_RED0 + r, site, n);
+    if (!CC4_RED_RNG_INLINE || CC4_TAPE_ON()) return rng_int(c, A_RED0 + r, site, n);
     return __umulhi(red_word(c, r), n);
 }
 __device__ __forceinline__ double rng_f64_red(Cx c, int r, int site)
 {
-    if (!CC4_RED_RNG_INLINE || g_blk.rng_mode == 1) return rng_f64(c, A_RED0 + r, site, 0);
+    if (!CC4_RED_RNG_INLINE || CC4_TAPE_ON()) return rng_f64(c, A_RED0 + r, site, 0);
     return f64_from_word(red_word(c, r));
 }
 
@@ -331,7 +337,7 @@ __device__ __noinline__ void reset_refill(Cx c, uint32_t b)
 }
 __device__ __forceinline__ uint32_t rng_int_reset(Cx c, int site, uint32_t n)
 {
-    if (g_blk.rng_mode == 1) return rng_int(c, NAG, site, n);
+    if (CC4_TAPE_ON()) return rng_int(c, NAG, site, n);
     Scratch *x = SCR(c);
     const uint32_t j = x->ctr_br[11];
     x->ctr_br[11] = (uint16_t)(j + 1);
@@ -876,7 +882,7 @@ __device__ CC4_INL8 uint32_t red_policy(Cx c, int r)
     if (g_blk.red_variant != 0) return red_policy_discovery(c, r, lo, hi);
     /* production mode: host pick, action pick and at most two parameter picks fit the four words of the stream's first
        Philox block, which stays in registers; the block is left in the stream cache for the action code that follows */
-    const bool tape = g_blk.rng_mode == 1;
+    const bool tape = CC4_TAPE_ON();
     const uint4 blk = tape ? make_uint4(0, 0, 0, 0) : philox_block(c, actor, 0);
     uint32_t j = 0;
     auto ri = [&](int site, uint32_t n) -> uint32_t {
@@ -1020,7 +1026,7 @@ __device__ CC4_INL6 void do_decoy(Cx c, int b, int h)
     if (!(used & PB_25)) fac |= (uint32_t)K_D_HARAKA << (4 * nf++);
     fac |= (uint32_t)K_D_VSFTPD << (4 * nf++);
     uint32_t pick, pid_draw;        /* DecoyAction.py:64 choice(factories), Host.create_pid Host.py:198-200 */
-    if (g_blk.rng_mode == 1) { pick = rng_int(c, actor, ST_DECOY_FACTORY, (uint32_t)nf); pid_draw = rng_int(c, actor, ST_CREATE_PID, 9); }
+    if (CC4_TAPE_ON()) { pick = rng_int(c, actor, ST_DECOY_FACTORY, (uint32_t)nf); pid_draw = rng_int(c, actor, ST_CREATE_PID, 9); }
     else { const uint2 w = blue_words2(c, actor); pick = __umulhi(w.x, (uint32_t)nf); pid_draw = __umulhi(w.y, 9u); }
     int kind = (int)(fac >> (4 * pick) & 15u);
     int pid = (int)(pmax + 1 + pid_draw);
@@ -1191,7 +1197,7 @@ __device__ __noinline__ int green_tick_tape(Cx c, int g, uint32_t *ev_words)
 
 __device__ CC4_INL8 int green_tick(Cx c, int g, uint32_t *ev_words)
 {
-    if (g_blk.rng_mode == 1) return green_tick_tape(c, g, ev_words);
+    if (CC4_TAPE_ON()) return green_tick_tape(c, g, ev_words);
     Cc4Dyn *s = DYN(c);
     const int actor = A_GREEN0 + g, gh = green_host_of(s, g), gsn = gh >> 4;
     const uint64_t v = WC(c)->k->svc64[gh];     /* issued ahead of the Philox rounds: only LocalWork (1 in 3) uses it, but the latency hides */
@@ -1379,7 +1385,7 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
         if (si < 0) return SUCC_FALSE;
         int rep = 0, h = a.host;
         const uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
-        if (g_blk.rng_mode != 1) {
+        if (!CC4_TAPE_ON()) {
             /* production mode spends two words per live process whether or not the second is looked at (oracle: AC_DD), so
                the q-th live process owns words p0 + 2q (decoy test) and p0 + 2q + 1 (false positive): lane per process */
             Scratch *x = SCR(c);
@@ -1450,7 +1456,7 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
         }
         if (sel == X_SSH) {   /* SSHBruteForce.execute SSHBruteForce.py:24-84 */
             const int nh = route_len(src, target);
-            if (g_blk.rng_mode == 1) ssh_hops_tape(c, actor, src, target, nh);
+            if (CC4_TAPE_ON()) ssh_hops_tape(c, actor, src, target, nh);
             else {    /* lane i takes the i-th hop and the i-th next word of the stream (the same words the serial loop would take) */
                 Scratch *x = SCR(c);
                 const uint32_t p0 = ctr_get(x, actor);

@@ -627,7 +627,7 @@ __device__ __forceinline__ void ph_finish(Cx c, const uint8_t *msgs /* [5] or nu
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) rew += __shfl_xor_sync(0xFFFFFFFFu, rew, o);       /* lanes 0-7 */
     if (lane >= 8 && lane < 8 + CC4_NBLUE) s->msgs[lane - 8] = msgs ? msgs[lane - 8] : 0;
-    if (g_blk.rng_mode == 1)
+    if (CC4_TAPE_ON())
         _Pragma("unroll 1") for (int a = lane; a < NAG; a += 32) {
             uint32_t seg = 1u + (uint32_t)WC(c)->tick * NAG + (uint32_t)a;
             if (seg < g_blk.n_segs && ctr_get(x, a) != WC(c)->seg[seg + 1] - WC(c)->seg[seg]) fail(c, CC4_E_TAPE_LEFT);
@@ -1026,7 +1026,7 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
         /* red_agent_0 digests its initial observation (its start host becomes 'U', FiniteStateRedAgent.py:221-224) */
         { int h0 = st->red_start[0]; s->fsm_order[0][0] = (uint8_t)h0; s->n_fsm[0] = 1; s->fsm_started = 1;
           set128(s->fsm[0].present, h0); set128(s->fsm[0].hn, h0); set128(s->fsm[0].pl[2], h0); }
-        if (g_blk.rng_mode == 1 && g_blk.n_segs > 0 && ctr_get(SCR(c), NAG) != WC(c)->seg[1] - WC(c)->seg[0]) fail(c, CC4_E_TAPE_LEFT);
+        if (CC4_TAPE_ON() && g_blk.n_segs > 0 && ctr_get(SCR(c), NAG) != WC(c)->seg[1] - WC(c)->seg[0]) fail(c, CC4_E_TAPE_LEFT);
     }
     __syncwarp();
     {   /* process lists + Host.create_backup Host.py:316-371: the generated lists leave shared memory, a lane per host */
