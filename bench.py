@@ -248,10 +248,17 @@ def main():
     env.reset()
     for i in range(3):
         env.step_host(host_pool[i % len(host_pool)], compact=True)
+    env.reset()
+    torch.cuda.synchronize()
     barrier()
+    tick = 0
     t0 = time.perf_counter()
     for i in range(args.e2e_steps):
+        if tick == EPISODE_TICKS:            # the batch has finished its episode: reset inside the timed region
+            env.reset()
+            tick = 0
         o, r, d = env.step_host(host_pool[i % len(host_pool)], compact=True)    # obs uint8 [N, 578]: the five unpadded vectors
+        tick += 1
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()      # sampled through both timed regions (device-resident steps, then the host-buffer steps)
