@@ -147,6 +147,17 @@ class TapeGenerator:
         self.step = -1          # -1 = reset segment
         self.unknown_sites: set = set()
 
+    def begin_segment(self, step: int):
+        """Called by the harness before the final reset (step = -1) and before every tick."""
+        self.step = step
+
+    # -- value source: one integer in [0, n) / one double in [0, 1) for the draw at `site` by `actor` ---------------
+    def _draw_int(self, site, actor, n: int) -> int:
+        return int(self._g.integers(0, n))
+
+    def _draw_f64(self, site, actor) -> float:
+        return float(self._g.random())
+
     # -- context -------------------------------------------------------------------------------
     def _context(self):
         f = sys._getframe(2)
@@ -174,7 +185,7 @@ class TapeGenerator:
     # -- Generator API subset used by the reference ------------------------------------------------
     def random(self):
         site, actor = self._context()
-        u = float(self._g.random())
+        u = self._draw_f64(site, actor)
         self._log(site, actor, KIND_F64, 0, u)
         return u
 
@@ -186,7 +197,7 @@ class TapeGenerator:
         if endpoint:
             high = high + 1
         n = int(high) - int(low)
-        v = int(self._g.integers(0, n))
+        v = self._draw_int(site, actor, n)
         self._log(site, actor, KIND_INT, n, v)
         return int(low) + v
 
@@ -201,7 +212,7 @@ class TapeGenerator:
         if n == 0:
             raise ValueError("a cannot be empty unless no samples are taken")
         if p is None:
-            idx = int(self._g.integers(0, n))
+            idx = self._draw_int(site, actor, n)
             self._log(site, actor, KIND_INT, n, idx)
         else:
             p = np.asarray(p, dtype=np.float64)
@@ -209,7 +220,7 @@ class TapeGenerator:
                 raise ValueError("probabilities do not sum to 1")
             cdf = p.cumsum()
             cdf /= cdf[-1]
-            u = float(self._g.random())
+            u = self._draw_f64(site, actor)
             idx = int(cdf.searchsorted(u, side="right"))
             self._log(site, actor, KIND_F64, n, u)
         return idx if seq is None else seq[idx]
@@ -224,6 +235,99 @@ class TapeGenerator:
     # gym spaces sometimes poke these
     def __getattr__(self, item):
         raise AttributeError(f"TapeGenerator has no '{item}' (reference used an RNG method the tape does not model)")
+
+
+def philox4x32_10(ctr, k0: int, k1: int):
+    """Philox4x32-10 (Salmon et al. 2011), the block function of the engine's production RNG (cc4_oracle.c philox4x32_10)."""
+    c0, c1, c2, c3 = (int(x) & 0xFFFFFFFF for x in ctr)
+    k0 &= 0xFFFFFFFF
+    k1 &= 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c0, 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c3 ^ k1) & 0xFFFFFFFF, p0 & 0xFFFFFFFF
+        k0, k1 = (k0 + 0x9E3779B9) & 0xFFFFFFFF, (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+SITE_FSM_PARAM, SITE_LW_SERVICE, SITE_DD_TP, SITE_DD_FP = 20, 11, 28, 29
+
+
+class PhiloxSeamGenerator(TapeGenerator):
+    """The engine's PRODUCTION random source, served to the live reference through the same seam (env.py:73-76).
+
+    Every mapped draw site gets the value the engine would draw at that point: stream (actor, tick) of episode
+    (seed, episode) is the sequence of 32-bit words of Philox4x32-10 blocks with key (seed lo, seed hi ^ episode hi) and
+    counter (word index / 4, actor, tick + 1 [0 for the reset stream, actor 91], episode lo) — cc4_oracle.c rng_word,
+    cc4_device.cuh philox_block.  Word rules (cc4_oracle.c rng_int / rng_int_more / rng_f64, exec_red AC_DD):
+      * integer in [0, n) = high half of word * n; double = word / 2^32; one word per draw;
+      * a one-option FSM_PARAM pick spends no word;
+      * LW_SERVICE is cut from the low half of the word the actor's GREEN_ACT draw used;
+      * DiscoverDeception owns two words per process (DD_TP, DD_FP) whether or not the reference looks at the second.
+    Draw sites the engine does not model (SITE -> None: addresses, ephemeral ports, the bandwidth shuffle, ...) are
+    served from a side PCG64 and never touch the Philox streams.  A reference episode driven by this generator must
+    therefore equal, tick for tick, the oracle and the CUDA engine running in rng="philox" mode with the same
+    (seed, episode): tests/golden/px_*.npz.
+    """
+
+    NAG = N_ACTORS      # the reset stream's actor id (cc4_oracle.c: actor == NAG)
+
+    def __init__(self, seed: int, episode: int):
+        super().__init__(seed ^ 0x5EA3)          # side stream for the unmapped sites
+        self.seed, self.episode = int(seed), int(episode)
+        self._k0 = self.seed & 0xFFFFFFFF
+        self._k1 = ((self.seed >> 32) ^ (self.episode >> 32)) & 0xFFFFFFFF
+        self.begin_segment(-1)
+
+    def begin_segment(self, step: int):
+        self.step = step
+        self._ctr: dict[int, int] = {}          # actor -> next word index of its stream for this tick
+        self._frac: dict[int, int] = {}         # actor -> low half of its last integer draw's product
+        self._dd_second: dict[int, int] = {}    # actor -> the reserved second word of the current DiscoverDeception process
+
+    def _word(self, actor: int) -> int:
+        a = self.NAG if actor == ACTOR_RESET else actor
+        j = self._ctr.get(a, 0)
+        self._ctr[a] = j + 1
+        tick = 0 if a == self.NAG else self.step + 1
+        return philox4x32_10((j >> 2, a, tick, self.episode & 0xFFFFFFFF), self._k0, self._k1)[j & 3]
+
+    def _mapped(self, site) -> int | None:
+        return SITE.get(site)
+
+    def _draw_int(self, site, actor, n: int) -> int:
+        tag = self._mapped(site)
+        if tag is None:
+            return int(self._g.integers(0, n))
+        a = self.NAG if actor == ACTOR_RESET else actor
+        if tag == SITE_FSM_PARAM and n == 1:
+            return 0
+        if tag == SITE_LW_SERVICE:
+            p = self._frac[a] * n
+        else:
+            p = self._word(actor) * n
+        self._frac[a] = p & 0xFFFFFFFF
+        return p >> 32
+
+    def _draw_f64(self, site, actor) -> float:
+        tag = self._mapped(site)
+        if tag is None:
+            return float(self._g.random())
+        a = self.NAG if actor == ACTOR_RESET else actor
+        if tag == SITE_DD_TP:
+            w = self._word(actor)
+            self._dd_second[a] = self._word(actor)
+        elif tag == SITE_DD_FP:
+            w = self._dd_second.pop(a)
+        else:
+            w = self._word(actor)
+        return w / 4294967296.0
+
+    def shuffle(self, x):
+        site, actor = self._context()
+        assert SITE.get(site) is None, "a modelled shuffle would need a word rule"
+        for i in range(len(x) - 1, 0, -1):
+            j = int(self._g.integers(0, i + 1))
+            x[i], x[j] = x[j], x[i]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -262,7 +366,7 @@ def _inprog(ctrl, name):
 class RefEpisode:
     """One reference environment driven through BlueFlatWrapper with index actions."""
 
-    def __init__(self, seed: int, steps: int = 500, red: str = "fsm"):
+    def __init__(self, seed: int, steps: int = 500, red: str = "fsm", rng: str = "pcg64", episode: int = 0):
         _ensure_path()
         from CybORG import CybORG
         from CybORG.Agents import SleepAgent, EnterpriseGreenAgent, FiniteStateRedAgent
@@ -271,7 +375,7 @@ class RefEpisode:
         from CybORG.Agents.Wrappers import BlueFlatWrapper
         from CybORG.Simulator.Scenarios import EnterpriseScenarioGenerator
 
-        self.tape = TapeGenerator(seed)
+        self.tape = TapeGenerator(seed) if rng == "pcg64" else PhiloxSeamGenerator(seed, episode)
         sg = EnterpriseScenarioGenerator(blue_agent_class=SleepAgent, green_agent_class=EnterpriseGreenAgent,
                                          red_agent_class=FiniteStateRedAgent, steps=steps)
         # construction runs create_scenario once; wrapper.reset() runs it again. Only the LAST scenario
@@ -279,7 +383,7 @@ class RefEpisode:
         self.cyborg = CybORG(sg, seed=self.tape)
         self.env = BlueFlatWrapper(self.cyborg)
         self.tape.records.clear()
-        self.tape.step = -1
+        self.tape.begin_segment(-1)
         self.obs, self.info = self.env.reset()
         self.ctrl = self.cyborg.environment_controller
         self.t = 0
@@ -290,7 +394,7 @@ class RefEpisode:
         if isinstance(messages, (list, tuple, np.ndarray)):
             messages = {f"blue_agent_{i}": np.array([(int(m) >> b) & 1 for b in range(8)], dtype=bool)
                         for i, m in enumerate(messages)}
-        self.tape.step = self.t
+        self.tape.begin_segment(self.t)
         obs, rew, term, trunc, info = self.env.step(actions, messages=messages)
         self.t += 1
         self.obs = obs
@@ -441,9 +545,10 @@ def blue_policy(kind: str, rng: np.random.Generator, mask: np.ndarray, obs: np.n
 
 
 def run_episode(seed: int, policy: str = "sleep", steps: int = 500, n_ticks: int | None = None,
-                with_state: bool = True, red: str = "fsm") -> dict[str, np.ndarray]:
-    """Run one reference episode and return the fixture arrays."""
-    ep = RefEpisode(seed, steps, red)
+                with_state: bool = True, red: str = "fsm", rng: str = "pcg64", episode: int = 0) -> dict[str, np.ndarray]:
+    """Run one reference episode and return the fixture arrays.  rng="philox": the reference draws the engine's
+    production-mode values for (seed, episode) (PhiloxSeamGenerator) instead of a seeded PCG64."""
+    ep = RefEpisode(seed, steps, red, rng, episode)
     n_ticks = steps - 1 if n_ticks is None else n_ticks
     prng = np.random.Generator(np.random.PCG64(seed + 7919))
     mask = ep.mask_array()
@@ -471,6 +576,7 @@ def run_episode(seed: int, policy: str = "sleep", steps: int = 500, n_ticks: int
         off[i + 1] = off[i] + len(c)
     return dict(
         seed=np.int64(seed), steps=np.int32(steps), policy=np.array(policy), red=np.array(red),
+        rng=np.array(rng), episode=np.int64(episode),
         t_step=np.array([x[0] for x in rec], dtype=np.int32), t_actor=np.array([x[1] for x in rec], dtype=np.uint8),
         t_site=np.array([x[2] for x in rec], dtype=np.uint8), t_kind=np.array([x[3] for x in rec], dtype=np.uint8),
         t_n=np.array([x[4] for x in rec], dtype=np.uint16), t_val=t_val,
@@ -490,11 +596,15 @@ if __name__ == "__main__":
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     for spec in args.spec:
-        seed, policy, steps, *rest = spec.split(":")      # seed:policy:steps[:red]  (red = fsm | discovery)
+        seed, policy, steps, *rest = spec.split(":")      # seed:policy:steps[:red[:episode]]  (red = fsm | discovery; episode => Philox seam)
         red = rest[0] if rest else "fsm"
         t0 = time.time()
-        fx = run_episode(int(seed), policy, int(steps), red=red)
-        path = os.path.join(args.out, f"ep_s{seed}_{policy}_{steps}{'' if red == 'fsm' else '_' + red}.npz")
+        if len(rest) > 1:       # production-mode fixture: the reference driven by the engine's Philox streams of (seed, episode)
+            fx = run_episode(int(seed), policy, int(steps), red=red, rng="philox", episode=int(rest[1]))
+            path = os.path.join(args.out, f"px_s{seed}_e{rest[1]}_{policy}_{steps}{'' if red == 'fsm' else '_' + red}.npz")
+        else:
+            fx = run_episode(int(seed), policy, int(steps), red=red)
+            path = os.path.join(args.out, f"ep_s{seed}_{policy}_{steps}{'' if red == 'fsm' else '_' + red}.npz")
         np.savez_compressed(path, **fx)
         print(f"{path}: {len(fx['t_val'])} draws, {len(fx['canon'])} state ints, return {fx['reward'].sum():.1f}, "
               f"{time.time() - t0:.1f}s, {os.path.getsize(path) / 1024:.0f} KiB")

@@ -53,13 +53,15 @@ if __name__ == "__main__":
     ap.add_argument("--episodes", type=int, default=192)
     ap.add_argument("--procs", type=int, default=os.cpu_count())
     ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--first-seed", type=int, default=1000)
+    ap.add_argument("--name", default=None, help="output file stem (default ref_rewards_<policy>)")
     ap.add_argument("--out", default=os.path.join(HERE, "..", "tests", "golden"))
     a = ap.parse_args()
     t0 = time.time()
     with mp.Pool(a.procs) as pool:
-        rows = pool.map(one, [(1000 + i, a.policy, a.steps) for i in range(a.episodes)], chunksize=1)
+        rows = pool.map(one, [(a.first_seed + i, a.policy, a.steps) for i in range(a.episodes)], chunksize=1)
     rew = np.stack(rows)
-    path = os.path.join(a.out, f"ref_rewards_{a.policy}.npz")
-    np.savez_compressed(path, reward=rew.astype(np.float16), policy=np.array(a.policy), steps=np.int32(a.steps), first_seed=np.int64(1000))
+    path = os.path.join(a.out, f"{a.name or 'ref_rewards_' + a.policy}.npz")
+    np.savez_compressed(path, reward=rew.astype(np.float16), policy=np.array(a.policy), steps=np.int32(a.steps), first_seed=np.int64(a.first_seed))
     tot = rew.sum(1)
     print(f"{path}: {a.episodes} episodes, return mean {tot.mean():.1f} sd {tot.std(ddof=1):.1f}, {time.time() - t0:.0f}s")

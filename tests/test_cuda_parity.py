@@ -87,6 +87,39 @@ def test_tape_replay_of_reference_episodes(steps, red):
                 assert np.array_equal(exp, got), f"{names[i]} tick {t}: {_diff(exp, got)}"
 
 
+PX_FILES = sorted(f for f in os.listdir(GOLDEN) if f.startswith("px_") and f.endswith(".npz"))
+
+
+@pytest.mark.parametrize("name", PX_FILES)
+def test_production_mode_equals_reference_on_the_philox_seam(name):
+    """PRODUCTION-mode parity against the LIVE reference (not only against the oracle): px_*.npz are reference episodes
+    whose random source served the engine's own Philox words (ref_harness.PhiloxSeamGenerator).  The CUDA engine in
+    rng="philox" mode with the same (seed, episode) must reproduce them: observations, reward and done after every tick,
+    canonical state every fifth tick.  The episode sits at batch index 1 of 3 where its id allows, so the keying by
+    global episode id is exercised too."""
+    fx = np.load(os.path.join(GOLDEN, name))
+    seed, episode, steps, red = int(fx["seed"]), int(fx["episode"]), int(fx["steps"]), str(fx["red"])
+    at = 1 if episode >= 1 else 0
+    env = _engine(3, device=0, seed=seed, steps=steps, first_episode=episode - at, red_agent=red)
+    obs, mask = env.reset()
+    off = fx["canon_off"]
+    assert np.array_equal(obs[at].cpu().numpy(), fx["obs"][0]) and np.array_equal(mask[at].cpu().numpy().astype(np.uint8), fx["mask"])
+    exp, got = fx["canon"][off[0]:off[1]], env.export_canon(at)
+    assert np.array_equal(exp, got), f"reset: {_diff(exp, got)}"
+    T = len(fx["actions"])
+    for t in range(T):
+        acts = np.tile(np.array([49, 49, 49, 49, 145], dtype=np.int32), (3, 1))
+        msgs = np.zeros((3, 5), dtype=np.uint8)
+        acts[at], msgs[at] = fx["actions"][t], fx["msgs"][t]
+        o, r, d = env.step(torch.from_numpy(acts).cuda(), torch.from_numpy(msgs).cuda())
+        assert np.array_equal(o[at].cpu().numpy(), fx["obs"][t + 1]), f"tick {t}: observation"
+        assert float(r[at]) == fx["reward"][t] and int(d[at]) == fx["done"][t], f"tick {t}: reward / done"
+        if t % 5 == 0 or t == T - 1:
+            exp, got = fx["canon"][off[t + 1]:off[t + 2]], env.export_canon(at)
+            assert np.array_equal(exp, got), f"tick {t}: {_diff(exp, got)}"
+    assert env.error_flags()[at] == 0
+
+
 @pytest.mark.parametrize("n,ticks,seed", [(256, 120, 11), (37, 499, 5)])
 def test_philox_mode_matches_oracle(n, ticks, seed):
     """Same seeded inputs through the CUDA path and the C oracle: bit-exact obs / reward / done every tick and
@@ -104,8 +137,6 @@ def test_philox_mode_matches_oracle(n, ticks, seed):
     g = np.random.default_rng(seed)
     for t in range(ticks):
         acts = np.stack([g.integers(0, k, n) for k in (82, 82, 82, 82, 242)], 1).astype(np.int32)
-        if t % 3 == 0:  # masked-valid actions now and then so multi-tick actions complete
-            pass
         msgs = g.integers(0, 256, (n, 5)).astype(np.uint8)
         o, r, d = env.step(torch.from_numpy(acts).cuda(), torch.from_numpy(msgs).cuda())
         o, r, d = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
@@ -197,7 +228,6 @@ def test_fused_rollout_equals_tick_by_tick_and_oracle():
     env.rollout(200, policy_seed=seed, reward_sum=total)
     env.rollout(400, policy_seed=seed, reward_sum=total)     # stops at done (tick 499)
     torch.cuda.synchronize()
-    assert env.done.sum().item() == 0 or True
     ticks, ret = O.run_episodes(seed, 0, n, 500)
     assert ticks == n * 499
     assert abs(float(total.double().sum()) - ret) < 1e-6, (float(total.sum()), ret)

@@ -42,6 +42,38 @@ def test_oracle_replays_reference(name):
     assert fx["done"][-1] == (len(fx["actions"]) == int(fx["steps"]) - 1)
 
 
+PX_FILES = sorted(f for f in os.listdir(GOLDEN) if f.startswith("px_") and f.endswith(".npz"))
+
+
+@pytest.mark.parametrize("name", PX_FILES)
+def test_oracle_in_production_mode_equals_reference_on_the_philox_seam(name):
+    """PRODUCTION-mode parity.  tests/golden/px_*.npz are episodes of the unmodified reference whose random source was
+    ref_harness.PhiloxSeamGenerator: every modelled draw site received the word the engine's Philox stream of
+    (seed, episode, actor, tick) holds for it.  The oracle in rng_mode 0 (Philox, no tape) with the same (seed, episode)
+    must then BE that episode: canonical state, observations, reward and done after every tick."""
+    fx = np.load(os.path.join(GOLDEN, name))
+    assert str(fx["rng"]) == "philox"
+    env = O.OracleEnv(seed=int(fx["seed"]), episode=int(fx["episode"]), steps=int(fx["steps"]), red=str(fx["red"]))
+    env.reset()
+    off = fx["canon_off"]
+
+    def check_state(t):
+        exp, got = fx["canon"][off[t]:off[t + 1]], env.export()
+        if len(exp) != len(got) or np.any(exp != got):
+            pytest.fail(f"{name} after tick {t - 1}: " + "; ".join(canon.diff(canon.decode(exp), canon.decode(got))[:8]))
+
+    check_state(0)
+    assert np.array_equal(env.observe(), fx["obs"][0])
+    assert np.array_equal(env.mask(), fx["mask"])
+    for t in range(len(fx["actions"])):
+        rc, obs, rew, done = env.step(fx["actions"][t], fx["msgs"][t])
+        assert env.error() == (0, ""), f"tick {t}"
+        check_state(t + 1)
+        assert np.array_equal(obs, fx["obs"][t + 1]), f"tick {t}: observation"
+        assert rew == fx["reward"][t], f"tick {t}: reward"
+        assert done == fx["done"][t], f"tick {t}: done"
+
+
 def test_oracle_detects_a_corrupted_tape():
     fx = dict(np.load(os.path.join(GOLDEN, FILES[-1])))
     recs, seg = O.tape_from_fixture(fx)
