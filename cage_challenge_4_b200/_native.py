@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("CC4_B200_LIB") or os.path.join(HERE, "libcc4_b200.so"
 
 EXPORTS = [
     "cc4_create", "cc4_destroy", "cc4_set_episode_base", "cc4_set_red_agent", "cc4_state_bytes", "cc4_set_tape", "cc4_reset", "cc4_reset_host", "cc4_step", "cc4_step_host",
-    "cc4_rollout", "cc4_expand_obs_bits", "cc4_error_flags", "cc4_export_canon", "cc4_launch_count", "cc4_phase_clocks", "cc4_action_clocks", "cc4_last_error",
+    "cc4_rollout", "cc4_expand_obs_bits", "cc4_host_write_bandwidth", "cc4_error_flags", "cc4_export_canon", "cc4_launch_count", "cc4_phase_clocks", "cc4_action_clocks", "cc4_last_error",
 ]
 
 _lib = None
@@ -45,6 +45,7 @@ def load():
     L.cc4_export_canon.argtypes = [vp, i32, vp, i32, C.POINTER(i32)]
     L.cc4_launch_count.argtypes = [vp, C.POINTER(u64)]
     L.cc4_expand_obs_bits.argtypes = [vp, vp, C.c_size_t, i32]
+    L.cc4_host_write_bandwidth.argtypes = [C.c_size_t, i32, i32, i32, C.POINTER(C.c_double)]
     L.cc4_phase_clocks.argtypes = [vp, vp, i32]
     L.cc4_action_clocks.argtypes = [vp, vp]
     L.cc4_last_error.restype = C.c_char_p

@@ -169,6 +169,7 @@ struct Scratch {
                  uint32_t phish[3], pad;          /* green agents whose local work triggered a phishing email this tick */
                  uint64_t as_cum[8]; } g;         /* per source subnet: byte sn = number of allowed destination servers in subnets <= sn (GreenAccessService) */
         uint32_t obsbits[40];                     /* observation vectors as one bit string (w_write_obs) */
+        struct { uint8_t agent[32], ident[32]; } ra;     /* the misplaced sessions different_subnet_agent_reassignment is moving (reassign) */
     };
 };
 
@@ -372,9 +373,10 @@ __device__ CC4_INL4 void proc_append(Cx c, int h, uint32_t w, uint32_t d, uint32
 {   /* host.processes.append; d = pdir[h], pmax = pmax[h] (the caller has them in registers) */
     Cc4Cold *k = WC(c)->k;
     uint32_t off = PD_OFF(d), n = PD_CNT(d), capl = PD_CAPL(d);
+    if (n >= PD_MAXCNT) { fail(c, CC4_E_CAPACITY); return; }        /* the directory's count field holds 1023 (reachable only with steps >> 500) */
     if (n == (1u << capl)) {            /* block full: move the list to a block of twice the size */
         uint32_t top = k->arena_top, ncap = 2u << capl;
-        if (top + ncap > CC4_ARENA || n >= PD_MAXCNT) { fail(c, CC4_E_CAPACITY); return; }
+        if (top + ncap > CC4_ARENA) { fail(c, CC4_E_CAPACITY); return; }
         _Pragma("unroll 1") for (uint32_t i = lane_id(); i < n; i += 32) k->parena[top + i] = k->parena[off + i];
         __syncwarp();
         k->arena_top = top + ncap; off = top; capl++;
@@ -816,17 +818,14 @@ __device__ __noinline__ uint32_t red_policy_discovery(Cx c, int r, uint32_t lo, 
     int slot;
     {
         /* DiscoveryFSRed: FiniteStateRedAgent._choose_host :252-293 with a host-state priority list and the server bias.
-           One walk over the list: states in order of first appearance, and per state the position masks of its hosts /
-           of its servers ('server' in hostname: the entry carries a hostname and sits in a server slot). */
+           First walk over the list: the states in order of first appearance; after the state is drawn, a second walk
+           collects the position masks of its hosts / of its servers ('server' in hostname: the entry carries a hostname
+           and sits in a server slot). */
         uint32_t st_list = 0, seen = 0; int ns = 0;             /* 4 bits per listed state */
-        uint64_t pos_state[8], pos_srv[8];
-        _Pragma("unroll 1") for (int k = 0; k < 8; k++) { pos_state[k] = 0; pos_srv[k] = 0; }
         _Pragma("unroll 1") for (int i = 0; i < nf; i++) {
             if ((i < 32 ? lo >> i : hi >> (i - 32)) & 1u) {
-                const int sl_ = s->fsm_order[r][i], st = fsm_state(f, sl_);
+                const int st = fsm_state(f, s->fsm_order[r][i]);
                 if (!(seen >> st & 1u)) { seen |= 1u << st; st_list |= (uint32_t)st << (4 * ns); ns++; }
-                pos_state[st] |= 1ull << i;          /* (local memory: this variant only) */
-                if (bit128(f->hn, sl_) && (sl_ & 15) < 6) pos_srv[st] |= 1ull << i;
             }
         }
         int total = 0;
@@ -847,7 +846,15 @@ __device__ __noinline__ uint32_t red_policy_discovery(Cx c, int r, uint32_t lo, 
             if (pick >= ns) pick = ns - 1;
         } else pick = (int)ri(ST_FSMD_STATE_U, (uint32_t)ns);
         const int cst = (int)(st_list >> (4 * pick) & 15u);
-        const uint64_t all = pos_state[cst], srv = pos_srv[cst];
+        uint64_t all = 0, srv = 0;      /* second walk: the position masks of the chosen state only (registers, no local arrays) */
+        _Pragma("unroll 1") for (int i = 0; i < nf; i++) {
+            if ((i < 32 ? lo >> i : hi >> (i - 32)) & 1u) {
+                const int sl_ = s->fsm_order[r][i];
+                if (fsm_state(f, sl_) != cst) continue;
+                all |= 1ull << i;
+                if (bit128(f->hn, sl_) && (sl_ & 15) < 6) srv |= 1ull << i;
+            }
+        }
         const int no = __popcll(all), nsrv = __popcll(srv);
         uint64_t from; int site, n;
         if (no > 1) {
@@ -1593,8 +1600,8 @@ __device__ CC4_INL6 void rsc_reelect(Cx c, int r, int n)
 __device__ CC4_INL6 void reassign(Cx c)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
-    uint8_t list[32]; int n = 0;   /* (agent, ident) pairs, agents ascending then dict order */
-    uint8_t lid[32];
+    uint8_t *list = x->ra.agent, *lid = x->ra.ident; int n = 0;   /* (agent, ident) pairs, agents ascending then dict order; in the
+                                                                       scratch, not in a local array: no thread stack in the hot kernel */
     _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
         if (!(x->misplaced >> r & 1)) continue;
         const int ns = s->n_sess;
@@ -1605,10 +1612,13 @@ __device__ CC4_INL6 void reassign(Cx c)
             while (m) {
                 const int j = __ffs(m) - 1; m &= m - 1;
                 if (n >= 32) { fail(c, CC4_E_CAPACITY); break; }
-                list[n] = (uint8_t)r; lid[n] = (uint8_t)S_ID(__shfl_sync(FULLMASK, w, j)); n++;
+                const uint32_t id = S_ID(__shfl_sync(FULLMASK, w, j));
+                if (lane_id() == 0) { list[n] = (uint8_t)r; lid[n] = (uint8_t)id; }
+                n++;
             }
         }
     }
+    __syncwarp();
     _Pragma("unroll 1") for (int k = 0; k < n; k++) {
         int r = list[k], si = sess_find(s, r, lid[k]);
         uint32_t w = s->sess[si]; uint8_t f = s->sessf[si];

@@ -17,7 +17,9 @@
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
+#include <sched.h>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <new>
@@ -738,6 +740,21 @@ template <int per, int parts = 1, class F> __device__ __forceinline__ void each_
 #endif
 }
 
+/* -DCC4_PHASE_WALL (profiling build, tools/phase_wall.py): thread 0 of every block reads the clock after each block barrier of
+ * the tick and adds the phase's wall cycles to g_wall[phase] with one fire-and-forget atomic; [N_PHASES] = blocks counted,
+ * [N_PHASES + 1] = whole block.  Unlike CC4_PHASE_CLOCKS (per-item clocks, global read-modify-write per item) this does not
+ * perturb what it measures. */
+#ifdef CC4_PHASE_WALL
+__device__ unsigned long long g_wall[16];
+#define PW_BEGIN() long long pw_t = clock64(); const long long pw_t0 = pw_t
+#define PW_MARK(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_wall[i], (unsigned long long)(t_ - pw_t)); pw_t = t_; } } while (0)
+#define PW_END() do { if (threadIdx.x == 0) { atomicAdd(&g_wall[N_PHASES], 1ull); atomicAdd(&g_wall[N_PHASES + 1], (unsigned long long)(clock64() - pw_t0)); } } while (0)
+#else
+#define PW_BEGIN() do { } while (0)
+#define PW_MARK(i) do { } while (0)
+#define PW_END() do { } while (0)
+#endif
+
 /* block prologue: the context every episode of the block shares (callers synchronise before the first use) */
 __device__ __forceinline__ void init_block_ctx(const Params &p)
 {
@@ -759,6 +776,40 @@ __device__ __forceinline__ void init_ctx(Cx c, const Params &p, int env, int tic
     __syncwarp();
 }
 
+/* ---- dependency-driven scheduling of the per-episode phases (CC4_FLOW) ----
+ * A block barrier between two phases makes every warp wait for the slowest item of the first one (ncu r02v: 27 % of the
+ * warp-time of k_step is barrier wait, the action phases run at 0.6 warp utilisation).  What the next phase of an episode
+ * really needs is that THIS episode has finished the previous phase.  With CC4_FLOW the phases from the blue actions to
+ * the finish are STAGES of one item list per block: items are handed out from one counter in stage-major order (all blue
+ * items, then all green items, ...), an item first waits (spinning on a shared-memory progress byte) until the episodes it
+ * touches have completed the stage before, and signals its own completion when done.  So the warps that run out of items of
+ * stage k start on stage k + 1 while the stragglers of stage k are still running: the tail of every stage is filled with
+ * the head of the next, and at any time at most two neighbouring stages (code regions) are live.  No deadlock: an item only
+ * waits for items with smaller list positions, and those have all been taken by warps that run them to completion.
+ * CC4_FLOW is a bit mask of the stage boundaries WITHOUT a block barrier: 1 blue|green, 2 green|red, 4 red|reassign,
+ * 8 reassign|end turn, 16 end turn|finish; 0 = the barrier form. */
+#ifndef CC4_FLOW
+#define CC4_FLOW 0
+#endif
+enum { FS_BLUE, FS_GREEN, FS_RED, FS_REASSIGN, FS_ENDTURN, FS_FINISH, N_FSTAGES };
+struct FlowSmem {
+    int gdone[64];              /* green agents of the episode that have had their tick */
+    uint8_t prog[64];           /* 1 + last stage the episode has completed (the green stage counts in gdone) */
+    uint8_t perm_b[64], perm_r[64];     /* item position -> episode: heaviest blue / red cost class first (PhaseOrder) */
+    short gend[64];             /* green agents up to and including list position p (positions follow perm_b) */
+    int n_green_items;
+};
+__device__ __forceinline__ void flow_wait(const volatile uint8_t *p, int v)
+{
+    if (*p < v) { while (*p < v) __nanosleep(40); }
+    __threadfence_block();
+}
+__device__ __forceinline__ void flow_signal(volatile uint8_t *p, int v)
+{
+    __syncwarp();
+    if (lane_id() == 0) { __threadfence_block(); *p = (uint8_t)v; }
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* kernels                                                                                          */
 /* ------------------------------------------------------------------------------------------------ */
@@ -776,6 +827,8 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
     __shared__ PhaseOrder ord_blue, ord_red;
     __shared__ __align__(8) uint64_t ld_bar[64];
     const int first = env0 + (int)(io.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * epb, n_local = min(epb, env_end - first);
+    (void)gend;
+    PW_BEGIN();
     init_block_ctx(p);
     if (threadIdx.x < N_PHASES + 6) next[threadIdx.x] = 0;
     if (threadIdx.x < 4) { ord_blue.cnt[threadIdx.x] = 0; ord_red.cnt[threadIdx.x] = 0; }
@@ -792,6 +845,7 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
         ph_setup(c);
         if (lane_id() == 0) ng_s[e] = DYN(c)->ngreen;
     });
+    PW_MARK(PH_SETUP);
     /* CC4_MERGE (tuning knob): which neighbouring per-episode phases run back to back inside one work item instead of
        being separated by a block barrier: bit 0 red + reassign, bit 1 FSM digest + finish, bit 2 red ... finish all in
        one item.  Every merge measures slower (profiles/r01x_variants.txt: 0.477 ms -> 0.501 / 0.487 / 0.576 ms): fewer
@@ -807,6 +861,100 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
     each_group<4, 2>(PH_POLICY, first, n_local, next, [&](Cx c, int e, bool exists, int sl) {
         ph_policy(c, e, exists, exists, sl & 31, sl >= 32, io.actions + (size_t)(first + (exists ? e : 0)) * 5, 0, 0, 0, &ord_blue, &ord_red);
     });
+    PW_MARK(PH_POLICY);
+#if CC4_FLOW
+    {
+        __shared__ FlowSmem fl;
+        if ((int)threadIdx.x < n_local) {
+            fl.perm_b[threadIdx.x] = (uint8_t)order_get(&ord_blue, (int)threadIdx.x); fl.perm_r[threadIdx.x] = (uint8_t)order_get(&ord_red, (int)threadIdx.x);
+            fl.prog[threadIdx.x] = 0; fl.gdone[threadIdx.x] = 0;
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {     /* green list over the blue order: inclusive prefix of the agent counts */
+            const int lane = lane_id();
+            int ca = lane < n_local ? ng_s[fl.perm_b[lane]] : 0, cb = 32 + lane < n_local ? ng_s[fl.perm_b[32 + lane]] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int ta = __shfl_up_sync(0xFFFFFFFFu, ca, o), tb = __shfl_up_sync(0xFFFFFFFFu, cb, o); if (lane >= o) { ca += ta; cb += tb; } }
+            cb += __shfl_sync(0xFFFFFFFFu, ca, 31);
+            if (lane < n_local) fl.gend[lane] = (short)ca;
+            if (32 + lane < n_local) fl.gend[32 + lane] = (short)cb;
+            if (lane == 31) fl.n_green_items = (cb + 31) >> 5;
+        }
+        __syncthreads();
+        const int lane = lane_id();
+        /* run stages [lo, hi] of the item list from one counter, then a block barrier */
+        auto segment = [&](const int lo, const int hi) {
+            const int cnt[N_FSTAGES] = { n_local, fl.n_green_items, n_local, n_local, (n_local + CC4_ENDTURN_PER - 1) / CC4_ENDTURN_PER, n_local };
+            _Pragma("unroll 1") for (;;) {
+                int i = 0;
+                if (lane == 0) i = atomicAdd(&next[N_PHASES + lo], 1);
+                i = __shfl_sync(0xFFFFFFFFu, i, 0);
+                int st = lo;
+                while (st <= hi && i >= cnt[st]) { i -= cnt[st]; st++; }
+                if (st > hi) break;
+                if (st == FS_BLUE) {
+                    const int e = fl.perm_b[i];
+                    ph_blue((Cx)(e * (int)sizeof(WarpSmem)));
+                    flow_signal(&fl.prog[e], 1 + FS_BLUE);
+                } else if (st == FS_GREEN) {
+                    /* 32 green agents of consecutive list positions (an episode has >= 24 agents: at most three episodes) */
+                    const uint32_t past_a = __ballot_sync(0xFFFFFFFFu, lane < n_local && fl.gend[lane] > i * 32);
+                    const uint32_t past_b = __ballot_sync(0xFFFFFFFFu, 32 + lane < n_local && fl.gend[32 + lane] > i * 32);
+                    const int p_first = past_a ? __ffs(past_a) - 1 : 31 + __ffs(past_b);
+                    const int gidx = i * 32 + lane, total = fl.gend[n_local - 1];
+                    int pos = -1;
+                    if (gidx < total) { pos = p_first; while (fl.gend[pos] <= gidx) pos++; }
+                    const int e = pos >= 0 ? (int)fl.perm_b[pos] : -1;
+                    if (lo < FS_GREEN && e >= 0) flow_wait(&fl.prog[e], 1 + FS_BLUE);
+                    __syncwarp();
+                    if (e >= 0) {
+                        const Cx c = (Cx)(e * (int)sizeof(WarpSmem));
+                        const int g = gidx - (pos ? fl.gend[pos - 1] : 0);
+                        Cc4Dyn *sd = DYN(c); Scratch *x = SCR(c);
+                        const int gr = green_tick(c, g, reinterpret_cast<uint32_t *>(sd->ev));
+                        if (gr & 0xFF) atomicSub(&x->reward, gr & 0xFF);
+                        if (gr & GREEN_PHISH) atomicOr(&x->g.phish[g >> 5], 1u << (g & 31));
+                    }
+                    __syncwarp();
+                    const uint32_t same = __match_any_sync(0xFFFFFFFFu, e);
+                    if (e >= 0 && (int)__ffs(same) - 1 == lane) { __threadfence_block(); atomicAdd(&fl.gdone[e], __popc(same)); }
+                } else if (st == FS_RED) {
+                    const int e = fl.perm_r[i];
+                    if (lo < FS_RED) { if (lane == 0) { const volatile int *gd = &fl.gdone[e]; const int need = ng_s[e]; while (*gd < need) __nanosleep(40); } __syncwarp(); __threadfence_block(); }
+                    ph_red((Cx)(e * (int)sizeof(WarpSmem)));
+                    flow_signal(&fl.prog[e], 1 + FS_RED);
+                } else if (st == FS_REASSIGN) {
+                    const int e = fl.perm_r[i];
+                    if (lo < FS_REASSIGN) { if (lane == 0) flow_wait(&fl.prog[e], 1 + FS_RED); __syncwarp(); }
+                    ph_reassign((Cx)(e * (int)sizeof(WarpSmem)));
+                    flow_signal(&fl.prog[e], 1 + FS_REASSIGN);
+                } else if (st == FS_ENDTURN) {
+                    constexpr int per = CC4_ENDTURN_PER;
+                    const int sub = lane / (32 / per), sl = lane % (32 / per), k = i * per + sub;
+                    const bool exists = k < n_local;
+                    const int e = exists ? (int)fl.perm_r[k] : 0;
+                    if (lo < FS_ENDTURN && exists && sl == 0) flow_wait(&fl.prog[e], 1 + FS_REASSIGN);
+                    __syncwarp();
+                    ph_endturn((Cx)(e * (int)sizeof(WarpSmem)), exists, sl);
+                    __syncwarp();
+                    if (exists && sl == 0) { __threadfence_block(); *(volatile uint8_t *)&fl.prog[e] = 1 + FS_ENDTURN; }
+                } else {
+                    const int e = fl.perm_r[i];
+                    if (lo < FS_FINISH) { if (lane == 0) flow_wait(&fl.prog[e], 1 + FS_ENDTURN); __syncwarp(); }
+                    finish((Cx)(e * (int)sizeof(WarpSmem)), e);
+                }
+            }
+            __syncthreads();
+        };
+        /* the boundaries whose bit is clear keep their block barrier: cut the stage list there */
+        constexpr int M = CC4_FLOW;
+        int lo = 0;
+#pragma unroll
+        for (int b = 0; b < N_FSTAGES; b++) {
+            if (b == N_FSTAGES - 1 || !(M >> b & 1)) { segment(lo, b); PW_MARK(PH_BLUE + b); lo = b + 1; }
+        }
+    }
+#else
 #if CC4_SPLIT & 1
     each_episode(N_PHASES + 1, first, n_local, next, [&](Cx c, int) { ph_blue(c, false); });
     each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { ph_blue_exec(c); }, &ord_blue);
@@ -818,7 +966,9 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
     each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { ph_blue(c); }, &ord_blue);
 #endif
 #endif
+    PW_MARK(PH_BLUE);
     green_items(PH_GREEN, first, n_local, next, ng_s, gend);
+    PW_MARK(PH_GREEN);
 #if CC4_SPLIT & 2
     each_episode(N_PHASES + 2, first, n_local, next, [&](Cx c, int) { ph_phishing(c); });
 #endif
@@ -838,16 +988,22 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
 #else
     each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c, !(CC4_SPLIT & 2)); }, &ord_red);
 #endif
+    PW_MARK(PH_RED);
     each_episode<(CC4_FIXED_PHASES >> 1) & 1>(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { ph_reassign(c); });
+    PW_MARK(PH_REASSIGN);
 #endif
 #if CC4_MERGE & 2
     each_episode(PH_FINISH, first, n_local, next, [&](Cx c, int e) { ph_endturn(c, true, lane_id()); __syncwarp(); finish(c, e); });
 #else
     each_group<CC4_ENDTURN_PER>(PH_ENDTURN, first, n_local, next, [&](Cx c, int, bool exists, int sl) { ph_endturn(c, exists, sl); });
+    PW_MARK(PH_ENDTURN);
     each_episode<(CC4_FIXED_PHASES >> 2) & 1>(PH_FINISH, first, n_local, next, finish);
+    PW_MARK(PH_FINISH);
 #endif
 #endif
+#endif  /* CC4_FLOW */
     if (lane_id() == 0) bulk_store_wait();      /* shared memory must outlive the copies this lane started */
+    PW_END();
 }
 
 /* n_ticks fused ticks with the benchmark's synthetic blue policy (see ph_policy); the state stays in shared memory */
@@ -1207,7 +1363,36 @@ struct HostPool {
             }
         }
     }
-    void start(int n) { for (int i = 0; i < n; i++) th.emplace_back([this] { run(); }); }
+    /* With several ranks on one node (LOCAL_WORLD_SIZE > 1) every rank's workers are pinned to the rank's own share of the
+       CPUs this process may run on (rank r of w takes the r-th of w equal slices of the affinity mask), so that the pools of
+       different ranks do not migrate onto each other's cores while they spin; CC4_HOST_PIN=0 / 1 overrides. */
+    void start(int n)
+    {
+        std::vector<int> cpus;
+#if defined(__linux__)
+        int lw = 1, lr = 0;
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) lw = atoi(e) > 0 ? atoi(e) : 1;
+        if (const char *e = getenv("LOCAL_RANK")) lr = atoi(e) >= 0 ? atoi(e) : 0;
+        bool pin = lw > 1;
+        if (const char *e = getenv("CC4_HOST_PIN")) pin = e[0] == '1';
+        cpu_set_t set;
+        if (pin && sched_getaffinity(0, sizeof set, &set) == 0) {
+            std::vector<int> all;
+            for (int c = 0; c < CPU_SETSIZE; c++) if (CPU_ISSET(c, &set)) all.push_back(c);
+            const size_t per = all.size() / (size_t)lw;
+            if (per >= 1 && lr < lw) cpus.assign(all.begin() + (size_t)lr * per, all.begin() + (size_t)(lr + 1) * per);
+        }
+#endif
+        for (int i = 0; i < n; i++) {
+            th.emplace_back([this] { run(); });
+#if defined(__linux__)
+            if (!cpus.empty()) {
+                cpu_set_t one; CPU_ZERO(&one); CPU_SET(cpus[(size_t)i % cpus.size()], &one);
+                pthread_setaffinity_np(th.back().native_handle(), sizeof one, &one);
+            }
+#endif
+        }
+    }
     void submit(const uint32_t *rows, uint8_t *dst, size_t cnt, bool compact, size_t row_bytes, bool stream)
     {   /* one job per thread; the caller waits for every job of a tick before the next tick (at most 16 chunks x 16 jobs in flight) */
         const size_t parts = th.size(), per = (cnt + parts - 1) / parts;
@@ -1321,6 +1506,7 @@ extern "C" int cc4_reset(cc4_handle *h, uint8_t *obs_dev, uint8_t *mask_dev, voi
 {
     if (!h) return set_err(CC4_ERR_ARG, "cc4_reset: null handle%s", "");
     if (h->p.rng_mode == 1 && !h->p.tape) return set_err(CC4_ERR_STATE, "cc4_reset: tape mode without cc4_set_tape%s", "");
+    if ((uintptr_t)obs_dev & 15u) return set_err(CC4_ERR_ARG, "cc4_reset: obs_dev must be 16-byte aligned%s", "");
     CUDA_TRY(cudaSetDevice(h->device));
     k_reset<<<h->p.n_envs, 32, sizeof(ResetSmem), (cudaStream_t)stream>>>(h->p, obs_dev, mask_dev);
     h->launches++;
@@ -1371,6 +1557,9 @@ extern "C" int cc4_step(cc4_handle *h, const int32_t *actions_dev, const uint8_t
                         uint8_t *done_dev, int flags, void *stream)
 {
     if (!h || !actions_dev) return set_err(CC4_ERR_ARG, "cc4_step: null handle or actions%s", "");
+    /* the observation writer stores whole 16-byte lines relative to obs_dev (bit rows: words); reward / actions are 4-byte items */
+    if (((uintptr_t)obs_dev & ((flags & CC4_STEP_OBS_BITS) ? 3u : 15u)) || ((uintptr_t)reward_dev & 3u) || ((uintptr_t)actions_dev & 3u))
+        return set_err(CC4_ERR_ARG, "cc4_step: misaligned buffer (obs_dev: 16 bytes, 4 for bit rows; reward_dev, actions_dev: 4 bytes)%s", "");
     CUDA_TRY(cudaSetDevice(h->device));
     const int epb = episodes_per_block(h, (size_t)h->p.n_envs), blocks = (h->p.n_envs + epb - 1) / epb;
     /* Successive ticks walk the batch in opposite directions: the per-tick footprint (hot records + the cold lines the
@@ -1535,6 +1724,43 @@ extern "C" int cc4_expand_obs_bits(const uint32_t *rows_host, uint8_t *obs_host,
     return CC4_OK;
 }
 
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static void stream_fill_avx2(uint8_t *q, size_t n, int v)
+{
+    const __m256i x = _mm256_set1_epi8((char)v);
+    for (size_t i = 0; i < n; i += 32) _mm256_stream_si256((__m256i *)(q + i), x);
+    _mm_sfence();
+}
+#endif
+/* host-only: what can `threads` host threads WRITE per second?  The bound of the host-buffer path on a node whose ranks
+   together produce hundreds of MB of uint8 observation rows per tick (bench.py reports e2e against it). */
+extern "C" int cc4_host_write_bandwidth(size_t bytes, int threads, int streaming, int iters, double *gbs_out)
+{
+    if (!gbs_out || bytes < 4096 || threads < 1 || iters < 1) return set_err(CC4_ERR_ARG, "cc4_host_write_bandwidth: bad argument%s", "");
+    bytes &= ~(size_t)4095;
+    uint8_t *buf = static_cast<uint8_t *>(aligned_alloc(4096, bytes));
+    if (!buf) return set_err(CC4_ERR_STATE, "cc4_host_write_bandwidth: out of host memory%s", "");
+    const size_t per = (bytes / (size_t)threads) & ~(size_t)63;
+    auto pass = [&](int it) {
+        std::vector<std::thread> th;
+        for (int t = 0; t < threads; t++) th.emplace_back([=] {
+            uint8_t *d = buf + (size_t)t * per;
+#if defined(__x86_64__)
+            if (streaming && __builtin_cpu_supports("avx2")) { stream_fill_avx2(d, per, it); return; }
+#endif
+            memset(d, it & 0xFF, per);
+        });
+        for (auto &x : th) x.join();
+    };
+    pass(0);        /* page faults */
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int it = 1; it <= iters; it++) pass(it);
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    *gbs_out = (double)per * threads * iters / dt / 1e9;
+    free(buf);
+    return CC4_OK;
+}
+
 extern "C" int cc4_rollout(cc4_handle *h, int n_ticks, uint64_t policy_seed, float *reward_sum_dev, int flags, void *stream)
 {
     if (!h || n_ticks < 0) return set_err(CC4_ERR_ARG, "cc4_rollout: bad argument%s", "");
@@ -1550,7 +1776,14 @@ extern "C" int cc4_rollout(cc4_handle *h, int n_ticks, uint64_t policy_seed, flo
 /* profiling builds only (-DCC4_PHASE_CLOCKS): out_host uint64 [n_envs][18], see each_episode */
 extern "C" int cc4_phase_clocks(cc4_handle *h, unsigned long long *out_host, int reset)
 {
-#ifdef CC4_PHASE_CLOCKS
+#ifdef CC4_PHASE_WALL       /* out_host uint64 [16]: wall cycles per phase summed over blocks and launches, [8] = blocks counted, [9] = whole blocks */
+    if (!h || !out_host) return set_err(CC4_ERR_ARG, "cc4_phase_clocks: null%s", "");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(out_host, g_wall, sizeof(unsigned long long) * 16));
+    if (reset) { unsigned long long z[16] = { 0 }; CUDA_TRY(cudaMemcpyToSymbol(g_wall, z, sizeof z)); }
+    return CC4_OK;
+#elif defined(CC4_PHASE_CLOCKS)
     if (!h || !out_host) return set_err(CC4_ERR_ARG, "cc4_phase_clocks: null%s", "");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaDeviceSynchronize());

@@ -97,8 +97,7 @@ class BatchedCC4:
         """recs: DRAW_DTYPE [R]; seg_off uint32 [N, n_segs + 1] absolute offsets (tape mode)."""
         assert recs.dtype == DRAW_DTYPE and seg_off.dtype == np.uint32 and seg_off.shape[0] == self.num_envs
         recs_t = torch.from_numpy(recs.view(np.uint8).reshape(-1).copy()).to(self.device)
-        seg_t = torch.from_numpy(seg_off.astype(np.int64)).to(torch.int32).to(self.device)  # same bits as uint32
-        seg_t = torch.from_numpy(seg_off.view(np.int32).copy()).to(self.device)
+        seg_t = torch.from_numpy(seg_off.view(np.int32).copy()).to(self.device)      # same bits as uint32
         self._tape = (recs_t, seg_t)
         _native.check(self._L.cc4_set_tape(self._h, recs_t.data_ptr(), seg_t.data_ptr(), seg_off.shape[1] - 1), "cc4_set_tape")
 
@@ -109,6 +108,28 @@ class BatchedCC4:
         if first_episode is not None:
             self.first_episode = int(first_episode)
         _native.check(self._L.cc4_set_episode_base(self._h, self.seed & (2**64 - 1), self.first_episode), "cc4_set_episode_base")
+
+    def _check_inputs(self, actions, messages, on_device: bool):
+        """Every entry point hands raw pointers to the C-ABI: a wrong dtype, device, shape or a non-contiguous view would be
+        reinterpreted silently (an int64 tensor reads as int32 pairs), so all of them check first.  Returns the pointers."""
+        n = self.num_envs
+
+        def ptr(x, dtype_t, dtype_np, what):
+            if isinstance(x, torch.Tensor):
+                ok = x.dtype == dtype_t and x.is_cuda == on_device and tuple(x.shape) == (n, N_BLUE) and x.is_contiguous()
+                if ok and on_device:
+                    ok = x.device == self.device
+                if not ok:
+                    raise TypeError(f"{what}: expected a contiguous {dtype_t} tensor [{n}, {N_BLUE}] on {'%s' % self.device if on_device else 'the host'}, "
+                                    f"got {x.dtype} {tuple(x.shape)} on {x.device}{'' if x.is_contiguous() else ' (not contiguous)'}")
+                return x.data_ptr()
+            if on_device or not isinstance(x, np.ndarray):
+                raise TypeError(f"{what}: expected a {'CUDA tensor' if on_device else 'host tensor or numpy array'}, got {type(x).__name__}")
+            if x.dtype != dtype_np or x.shape != (n, N_BLUE) or not x.flags["C_CONTIGUOUS"]:
+                raise TypeError(f"{what}: expected a C-contiguous {np.dtype(dtype_np).name} array [{n}, {N_BLUE}], got {x.dtype} {x.shape}")
+            return x.ctypes.data
+
+        return ptr(actions, torch.int32, np.int32, "actions"), (0 if messages is None else ptr(messages, torch.uint8, np.uint8, "messages"))
 
     def reset(self):
         _native.check(self._L.cc4_reset(self._h, self.obs.data_ptr(), self.mask.data_ptr(), self._stream()), "cc4_reset")
@@ -125,40 +146,40 @@ class BatchedCC4:
         return p["obs"], p["mask"]
 
     def step(self, actions: torch.Tensor, messages: torch.Tensor | None = None, flags: int = STEP_ALL):
-        assert not (flags & STEP_OBS_COMPACT), "compact observations: use step_compact() / step_host(compact=True)"
-        assert actions.dtype == torch.int32 and actions.is_cuda and actions.shape == (self.num_envs, N_BLUE) and actions.is_contiguous()
-        mp = 0
-        if messages is not None:
-            assert messages.dtype == torch.uint8 and messages.is_cuda and messages.shape == (self.num_envs, N_BLUE) and messages.is_contiguous()
-            mp = messages.data_ptr()
-        _native.check(self._L.cc4_step(self._h, actions.data_ptr(), mp, self.obs.data_ptr(), self.reward.data_ptr(),
+        assert not (flags & (STEP_OBS_COMPACT | STEP_OBS_BITS)), "compact / bit observations: use step_compact() / step_bits() / step_host(compact=True)"
+        ap, mp = self._check_inputs(actions, messages, True)
+        _native.check(self._L.cc4_step(self._h, ap, mp, self.obs.data_ptr(), self.reward.data_ptr(),
                                        self.done.data_ptr(), flags, self._stream()), "cc4_step")
         return self.obs, self.reward, self.done
 
-    def step_host(self, actions: np.ndarray | torch.Tensor, messages=None, flags: int = STEP_ALL, compact: bool = False):
+    def step_host(self, actions: np.ndarray | torch.Tensor, messages=None, flags: int = STEP_ALL, compact: bool = False, bits: bool = False):
         """The same tick with HOST buffers (pinned torch tensors or numpy arrays): H2D + kernel + D2H + sync inside.
         compact=True returns the observations as uint8 [N, 578] (the five unpadded vectors back to back, see
-        split_compact) instead of [N, 5, 210]: 45 % fewer bytes over PCIe."""
+        split_compact) instead of [N, 5, 210]: 45 % fewer bytes over PCIe.  bits=True returns them as bit rows int32
+        [N, 20] (CC4_STEP_OBS_BITS, see unpack_bits): 80 B per episode, nothing to expand on the host."""
         n = self.num_envs
+        a_ptr, m_ptr = self._check_inputs(actions, messages, False)
         if self._pinned is None:
             self._pinned = dict(obs=torch.zeros((n, N_BLUE, OBS_LEN), dtype=torch.uint8).pin_memory(),
                                 reward=torch.zeros(n, dtype=torch.float32).pin_memory(),
                                 done=torch.zeros(n, dtype=torch.uint8).pin_memory())
         p = self._pinned
+        if bits:
+            if "obs_bits" not in p:
+                p["obs_bits"] = p["obs"].view(-1)[:n * OBS_BITS_WORDS * 4].view(torch.int32).view(n, OBS_BITS_WORDS)     # same pinned storage
+            _native.check(self._L.cc4_step_host(self._h, a_ptr, m_ptr, p["obs_bits"].data_ptr(), p["reward"].data_ptr(), p["done"].data_ptr(),
+                                                flags | STEP_OBS_BITS, self._stream()), "cc4_step_host")
+            return p["obs_bits"], p["reward"], p["done"]
         if compact:
             flags |= STEP_OBS_COMPACT
             if "obs_compact" not in p:
                 p["obs_compact"] = p["obs"].view(-1)[:n * OBS_COMPACT_LEN].view(n, OBS_COMPACT_LEN)     # same pinned storage
                 p["ptrs"] = (p["obs_compact"].data_ptr(), p["reward"].data_ptr(), p["done"].data_ptr())
-            a_ptr = actions.data_ptr() if isinstance(actions, torch.Tensor) else actions.ctypes.data
-            m_ptr = 0 if messages is None else (messages.data_ptr() if isinstance(messages, torch.Tensor) else messages.ctypes.data)
             o_ptr, r_ptr, d_ptr = p["ptrs"]
             rc = self._L.cc4_step_host(self._h, a_ptr, m_ptr, o_ptr, r_ptr, d_ptr, flags, self._stream())
             if rc:
                 _native.check(rc, "cc4_step_host")
             return p["obs_compact"], p["reward"], p["done"]
-        a_ptr = actions.data_ptr() if isinstance(actions, torch.Tensor) else actions.ctypes.data
-        m_ptr = 0 if messages is None else (messages.data_ptr() if isinstance(messages, torch.Tensor) else messages.ctypes.data)
         _native.check(self._L.cc4_step_host(self._h, a_ptr, m_ptr, p["obs"].data_ptr(), p["reward"].data_ptr(),
                                             p["done"].data_ptr(), flags, self._stream()), "cc4_step_host")
         return p["obs"], p["reward"], p["done"]
@@ -167,18 +188,41 @@ class BatchedCC4:
         """step() with compact device observations uint8 [N, 578] (see split_compact)."""
         if getattr(self, "_obs_compact", None) is None:
             self._obs_compact = torch.zeros((self.num_envs, OBS_COMPACT_LEN), dtype=torch.uint8, device=self.device)
-        mp = 0 if messages is None else messages.data_ptr()
-        _native.check(self._L.cc4_step(self._h, actions.data_ptr(), mp, self._obs_compact.data_ptr(), self.reward.data_ptr(),
+        ap, mp = self._check_inputs(actions, messages, True)
+        _native.check(self._L.cc4_step(self._h, ap, mp, self._obs_compact.data_ptr(), self.reward.data_ptr(),
                                        self.done.data_ptr(), STEP_ALL | STEP_OBS_COMPACT, self._stream()), "cc4_step")
         return self._obs_compact, self.reward, self.done
+
+    def step_state_only(self, actions: torch.Tensor, messages: torch.Tensor | None = None):
+        """The state transition alone (BASELINE config 2: observations and reward off); `done` is still written."""
+        ap, mp = self._check_inputs(actions, messages, True)
+        _native.check(self._L.cc4_step(self._h, ap, mp, 0, 0, self.done.data_ptr(), 0, self._stream()), "cc4_step")
+        return self.done
+
+    def capture_steps(self, actions_list, mode: str = "compact", accumulate: torch.Tensor | None = None):
+        """Record len(actions_list) consecutive ticks (one k_step launch each, reading actions_list[i]) into ONE CUDA graph
+        and return it; graph.replay() then costs one launch from the host for all of them, which matters when a tick is
+        short (a sub-wave batch such as 8 192 episodes per GPU: ~0.07 ms of kernel against the per-launch cost of a Python
+        call).  The outputs of the last captured tick are in the usual buffers; `accumulate` (float64 [N]) collects the
+        reward of every tick.  Use an even number of ticks: successive ticks sweep the batch in alternating directions."""
+        step = {"compact": self.step_compact, "padded": self.step, "bits": self.step_bits, "state": self.step_state_only}[mode]
+        step(actions_list[0])                      # allocates the lazily created output buffers outside the capture
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for a in actions_list:
+                step(a)
+                if accumulate is not None:
+                    accumulate.add_(self.reward)
+        return g
 
     def step_bits(self, actions: torch.Tensor, messages: torch.Tensor | None = None):
         """step() with the observations as bit rows int32 [N, 20] on the device (CC4_STEP_OBS_BITS, 80 B per episode; see
         unpack_bits): for device-side policies that take bits, and what step_host moves over PCIe."""
         if getattr(self, "_obs_bits", None) is None:
             self._obs_bits = torch.zeros((self.num_envs, OBS_BITS_WORDS), dtype=torch.int32, device=self.device)
-        mp = 0 if messages is None else messages.data_ptr()
-        _native.check(self._L.cc4_step(self._h, actions.data_ptr(), mp, self._obs_bits.data_ptr(), self.reward.data_ptr(),
+        ap, mp = self._check_inputs(actions, messages, True)
+        _native.check(self._L.cc4_step(self._h, ap, mp, self._obs_bits.data_ptr(), self.reward.data_ptr(),
                                        self.done.data_ptr(), STEP_ALL | STEP_OBS_BITS, self._stream()), "cc4_step")
         return self._obs_bits, self.reward, self.done
 

@@ -92,7 +92,8 @@ int cc4_set_tape(cc4_handle *h, const cc4_draw *recs_dev, const uint32_t *seg_of
 /* Replaces: CybORG.reset -> SimulationController.reset -> EnterpriseScenarioGenerator.create_scenario + State.__init__
  * (env.py:218, SimulationController.py:153-209, EnterpriseScenarioGenerator.py:123, State.py:66) and the wrappers'
  * reset outputs (BlueFlatWrapper.reset :61, BlueFixedActionWrapper.reset :76).
- * obs_dev: uint8 [n_envs][5][210] or NULL; mask_dev: uint8 [n_envs][5][242] or NULL. */
+ * obs_dev: uint8 [n_envs][5][210] or NULL, 16-byte aligned (CC4_ERR_ARG otherwise: rows go out as 128-bit stores);
+ * mask_dev: uint8 [n_envs][5][242] or NULL. */
 int cc4_reset(cc4_handle *h, uint8_t *obs_dev, uint8_t *mask_dev, void *stream);
 
 /* Same call with HOST buffers (copies the outputs device->host and synchronises the stream). */
@@ -102,7 +103,8 @@ int cc4_reset_host(cc4_handle *h, uint8_t *obs_host, uint8_t *mask_host, void *s
  * observation_change x5, BlueRewardMachine) for every episode of the batch.
  * actions_dev int32 [n_envs][5] BlueFixedActionWrapper indices; msgs_dev uint8 [n_envs][5] (bit i = message[i]) or NULL;
  * obs_dev uint8 [n_envs][5][210] (or [n_envs][578] with CC4_STEP_OBS_COMPACT); reward_dev float [n_envs] (team reward = BlueRewardMachine + action_cost, identical
- * for the 5 blue agents, SimulationController.py:1118); done_dev uint8 [n_envs].  Outputs may be NULL. */
+ * for the 5 blue agents, SimulationController.py:1118); done_dev uint8 [n_envs].  Outputs may be NULL.
+ * Alignment (checked, CC4_ERR_ARG): obs_dev 16 bytes (4 with CC4_STEP_OBS_BITS), reward_dev and actions_dev 4 bytes. */
 int cc4_step(cc4_handle *h, const int32_t *actions_dev, const uint8_t *msgs_dev, uint8_t *obs_dev, float *reward_dev,
              uint8_t *done_dev, int flags, void *stream);
 
@@ -120,6 +122,11 @@ int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const uint8_t *msg
 /* Host-only: expands bit rows uint32 [n_rows][20] (CC4_STEP_OBS_BITS) to uint8 [n_rows][578] (compact != 0) or
  * [n_rows][5][210]; no device work.  For callers that fetch the bit rows themselves. */
 int cc4_expand_obs_bits(const uint32_t *rows_host, uint8_t *obs_host, size_t n_rows, int compact);
+
+/* Host-only measurement: GB/s that `threads` host threads sustain WRITING a `bytes`-sized buffer `iters` times (streaming
+ * != 0: non-temporal stores, as cc4_step_host uses when the node's ranks together write more than 64 MB per tick).  This
+ * is the bound of the host-buffer path on several GPUs (bench.py: e2e.host_write_gbs). */
+int cc4_host_write_bandwidth(size_t bytes, int threads, int streaming, int iters, double *gbs_out);
 
 /* n_ticks fused ticks with the synthetic uniform-random blue policy of the benchmark (indices drawn on device from
  * Philox keyed (policy_seed, episode, tick); BASELINE config "FiniteStateRed + random blue").  reward_sum_dev float
