@@ -267,12 +267,15 @@ def main():
     env.reset()
     for i in range(max(3, args.warmup)):
         one_step(i)
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    r0.record()
-    env.reset()                              # k_reset of the whole batch, timed on its own (reported as reset_ms)
-    r1.record()
-    torch.cuda.synchronize()
-    reset_ms = r0.elapsed_time(r1)
+    reset_times = []
+    for _ in range(3):                       # k_reset of the whole batch, timed on its own (reported as reset_ms: median of three)
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        env.reset()
+        r1.record()
+        torch.cuda.synchronize()
+        reset_times.append(r0.elapsed_time(r1))
+    reset_ms = sorted(reset_times)[1]
     tick = 0
     ret.zero_()
     barrier()
@@ -337,7 +340,8 @@ def main():
     stream_rows = lw * n * 578 > (64 << 20)
     gbs = C.c_double(0.0)
     barrier()
-    L.cc4_host_write_bandwidth(256 << 20, host_threads, 1 if stream_rows else 0, 4, C.byref(gbs))
+    # same footprint as the rows of one tick (one rank's 38 MB stay in the host's caches, eight ranks' 303 MB do not)
+    L.cc4_host_write_bandwidth(max(n * 578, 1 << 20), host_threads, 1 if stream_rows else 0, 20, C.byref(gbs))
     (host_write_gbs,) = [-x for x in reduce_max(-gbs.value)]      # the slowest rank's share while all ranks write at once
     del env
     torch.cuda.empty_cache()
@@ -469,7 +473,7 @@ def main():
             "env_steps_per_s": env_sps, "all_agent_steps_per_s": env_sps * 70.0,
             # an episode is 499 ticks and one reset of the batch (EnterpriseScenarioGenerator on device); the timed region holds a
             # reset whenever it crosses an episode boundary (--steps > 499); the same figure with one reset per 499 ticks charged:
-            "reset_ms": reset_ms,
+            "reset_ms": reset_ms, "reset_ms_samples": reset_times,
             "value_incl_reset": total_envs * N_BLUE * EPISODE_TICKS / ((ms / args.steps * EPISODE_TICKS + reset_ms) / 1e3),
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "agent-steps/s",
@@ -477,7 +481,7 @@ def main():
                     "api": "BatchedCC4.step_host(actions_pinned, compact=True) -> cc4_step_host: obs uint8 [N,578] (92 x 4 + 210, the reference's unpadded vectors) + reward f32 [N] + done u8 [N] in pinned host memory",
                     "obs_over_pcie": "bit rows uint32 [N,20], expanded to the uint8 rows by cc4_step_host's host threads inside the timed region" if expand else "uint8 rows",
                     "host_threads": host_threads, "host_write_gbs": host_write_gbs,
-                    "host_write_note": f"{'streaming' if stream_rows else 'ordinary'} stores by {host_threads} threads per rank, all {world} rank(s) at once (cc4_host_write_bandwidth); "
+                    "host_write_note": f"{'streaming' if stream_rows else 'ordinary'} stores by {host_threads} threads per rank into a buffer of one tick's rows ({n * 578 >> 20} MB), all {world} rank(s) at once (cc4_host_write_bandwidth); "
                                        f"the uint8 rows this rank writes: {e2e_bytes_per_s:.1f} GB/s = {e2e_bytes_per_s / max(host_write_gbs, 1e-9):.2f} of that",
                     "host_write_frac": e2e_bytes_per_s / max(host_write_gbs, 1e-9)},
             "e2e_bits": {"value": total_envs * min(args.e2e_steps, 200) * N_BLUE / (e2e_bits_ms / 1e3), "unit": "agent-steps/s",

@@ -989,10 +989,16 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
     each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c, !(CC4_SPLIT & 2)); }, &ord_red);
 #endif
     PW_MARK(PH_RED);
+#if CC4_MERGE & 8      /* reassignment + FSM digest + finish of an episode back to back in one item (two barriers fewer) */
+    each_episode<true>(PH_FINISH, first, n_local, next, [&](Cx c, int e) { ph_reassign(c); ph_endturn(c, true, lane_id()); __syncwarp(); finish(c, e); });
+    PW_MARK(PH_FINISH);
+#else
     each_episode<(CC4_FIXED_PHASES >> 1) & 1>(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { ph_reassign(c); });
     PW_MARK(PH_REASSIGN);
 #endif
-#if CC4_MERGE & 2
+#endif
+#if CC4_MERGE & 8
+#elif CC4_MERGE & 2
     each_episode(PH_FINISH, first, n_local, next, [&](Cx c, int e) { ph_endturn(c, true, lane_id()); __syncwarp(); finish(c, e); });
 #else
     each_group<CC4_ENDTURN_PER>(PH_ENDTURN, first, n_local, next, [&](Cx c, int, bool exists, int sl) { ph_endturn(c, exists, sl); });

@@ -20,17 +20,21 @@ EPISODE_LENGTH = 500
 
 
 def run_evaluation(submission, log_path: str | None = None, max_eps: int = 100, write_to_file: bool = False, seed=None, device: int = 0):
-    """evaluation.py:56-134 with the same bookkeeping: per-episode sum of the mean blue reward, the reward of the tick
-    on which `done` fires is not counted (evaluation.py:104-110)."""
+    """evaluation.py:56-197 with the same bookkeeping and the same outputs: per-episode sum of the mean blue reward, the reward
+    of the tick on which `done` fires is not counted (evaluation.py:104-110); with write_to_file the five log files of
+    evaluation.py:141-196 (summary.txt, full.txt, actions.txt, summary.json, scores.txt) are written to log_path."""
+    from datetime import datetime
     sg = EnterpriseScenarioGenerator(blue_agent_class=SleepAgent, green_agent_class=EnterpriseGreenAgent,
                                      red_agent_class=FiniteStateRedAgent, steps=EPISODE_LENGTH)
     cyborg = CybORG(sg, "sim", seed=seed, device=device)
     wrapped_cyborg = submission.wrap(cyborg)
-    start = time.time()
-    total_reward, actions_log = [], []
+    version_header = f"cage_challenge_4_b200 (CybORG v4.0 semantics), Scenario4"
+    author_header = f"Author: {getattr(submission, 'NAME', '?')}, Team: {getattr(submission, 'TEAM', '?')}, Technique: {getattr(submission, 'TECHNIQUE', '?')}"
+    start = datetime.now()
+    total_reward, actions_log, obs_log = [], [], []
     for _ in range(max_eps):
         observations, _ = wrapped_cyborg.reset()
-        r, a = [], []
+        r, a, o = [], [], []
         for _ in range(EPISODE_LENGTH):
             actions = {name: agent.get_action(observations[name], wrapped_cyborg.action_space(name))
                        for name, agent in submission.AGENTS.items() if name in wrapped_cyborg.agents}
@@ -41,16 +45,36 @@ def run_evaluation(submission, log_path: str | None = None, max_eps: int = 100, 
             r.append(mean(rew.values()))
             if write_to_file:
                 a.append({name: cyborg.get_last_action(name) for name in wrapped_cyborg.agents})
+                o.append({name: observations[name] for name in observations.keys()})
         total_reward.append(sum(r))
-        actions_log.append(a)
+        if write_to_file:
+            actions_log.append(a)
+            obs_log.append(o)
+    end = datetime.now()
     out = {"mean": mean(total_reward), "stdev": stdev(total_reward) if len(total_reward) > 1 else 0.0,
-           "episodes": len(total_reward), "seconds": time.time() - start, "rewards": total_reward}
+           "episodes": len(total_reward), "seconds": (end - start).total_seconds(), "rewards": total_reward}
     if write_to_file and log_path:
         import json
         import os
         os.makedirs(log_path, exist_ok=True)
+        reward_string = f"Average reward is: {out['mean']} with a standard deviation of {out['stdev']}"
+        with open(os.path.join(log_path, "summary.txt"), "w") as f:
+            f.write(version_header + "\n" + author_header + "\n" + reward_string + "\n" + f"Using agents {submission.AGENTS}")
+        with open(os.path.join(log_path, "full.txt"), "w") as f:
+            f.write(version_header + "\n" + author_header + "\n" + reward_string + "\n")
+            for act, obs, sum_rew in zip(actions_log, obs_log, total_reward):
+                f.write(f"actions: {act},\n observations: {obs},\n total reward: {sum_rew}\n")
+        with open(os.path.join(log_path, "actions.txt"), "w") as f:
+            f.write(version_header + "\n" + author_header + "\n" + reward_string + "\n")
+            for act in zip(actions_log):
+                f.write(f"actions: {act}")
         with open(os.path.join(log_path, "summary.json"), "w") as f:
-            json.dump({k: v for k, v in out.items() if k != "rewards"}, f)
+            json.dump({"submission": {"author": getattr(submission, "NAME", None), "team": getattr(submission, "TEAM", None),
+                                      "technique": getattr(submission, "TECHNIQUE", None)},
+                       "parameters": {"seed": seed, "episode_length": EPISODE_LENGTH, "max_episodes": max_eps},
+                       "time": {"start": str(start), "end": str(end), "elapsed": str(end - start)},
+                       "reward": {"mean": out["mean"], "stdev": out["stdev"]},
+                       "agents": {agent: str(submission.AGENTS[agent]) for agent in submission.AGENTS}}, f)
         with open(os.path.join(log_path, "scores.txt"), "w") as f:
             f.write(f"reward_mean: {out['mean']}\nreward_stdev: {out['stdev']}\n")
     return out
@@ -82,23 +106,35 @@ class MLPPolicy(torch.nn.Module):
 
 
 class RandomBluePolicy:
-    """The reference's cc4BlueRandomAgent (CybORG/Agents/SimpleAgents/RandomAgent.py:66-69) as a device-side batched
-    policy: every blue agent draws uniformly among its VALID actions (mask True), BlockTrafficZone / AllowTrafficZone
-    excluded as in the reference (`excluded_actions`).  `policy(obs, mask) -> int32 [N, 5]`."""
+    """The reference's cc4BlueRandomAgent (CybORG/Agents/SimpleAgents/RandomAgent.py:28-56, 66-69) as a device-side batched policy
+    over the wrapper's index space: every blue agent first draws the action CLASS uniformly among Sleep, Monitor, Analyse,
+    Remove, DeployDecoy and Restore (BlockTrafficZone / AllowTrafficZone are its `excluded_actions`), then the class's
+    parameter uniformly among the known entries: here the host, uniform over the agent's existing hosts (mask True).  So
+    Sleep and Monitor come up one time in six each, as under the reference agent, not once per index.  One difference
+    remains: the reference agent's hostname dict also holds the subnet routers, which BlueFixedActionWrapper indices cannot
+    address (BlueFixedActionWrapper.py:290).  `policy(obs, mask) -> int32 [N, 5]`."""
 
-    def __init__(self, seed: int = 0, exclude_traffic_control: bool = True):
-        self.seed, self.exclude, self._g = seed, exclude_traffic_control, None
+    CLASSES = ("Sleep", "Monitor", "Analyse", "Remove", "DeployDecoy", "Restore")
+
+    def __init__(self, seed: int = 0):
+        self.seed, self._g = seed, None
 
     @torch.no_grad()
     def __call__(self, obs: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
         if self._g is None:
             self._g = torch.Generator(device=mask.device).manual_seed(self.seed)
-        m = mask.clone()
-        if self.exclude:     # index layout of BlueFixedActionWrapper._populate_action_space :233-309: Allow + Block follow Sleep
-            m[:, :4, 50:66] = False
-            m[:, 4, 146:194] = False
-        key = torch.rand(m.shape, generator=self._g, device=m.device).masked_fill(~m, -1.0)
-        return key.argmax(-1).to(torch.int32).contiguous()
+        n = mask.shape[0]
+        cls = torch.randint(0, 6, (n, 5), generator=self._g, device=mask.device)
+        out = torch.empty((n, 5), dtype=torch.int64, device=mask.device)
+        for b in range(5):
+            H, T = (48, 24) if b == 4 else (16, 8)
+            # index layout of BlueFixedActionWrapper._populate_action_space :233-309
+            fixed = torch.tensor([3 * H + 1, H, 0, H + 1, 3 * H + 2 + 2 * T, 2 * H + 1], device=mask.device)     # Sleep, Monitor, base of Analyse / Remove / DeployDecoy / Restore
+            valid = mask[:, b, :H]                                    # the host blocks all carry the same mask: the host exists
+            host = torch.rand((n, H), generator=self._g, device=mask.device).masked_fill(~valid, -1.0).argmax(-1)
+            c = cls[:, b]
+            out[:, b] = fixed[c] + torch.where(c >= 2, host, torch.zeros_like(host))
+        return out.to(torch.int32).contiguous()
 
 
 def shard(n_total: int, rank: int, world: int) -> tuple[int, int]:
@@ -126,23 +162,72 @@ def aggregate_scores(local_totals: torch.Tensor, n_total: int, rank: int, world:
 
 
 def run_evaluation_batched(policy, max_eps: int = 100, seed: int = 0, device: int = 0, rank: int = 0, world: int = 1,
-                           steps: int = EPISODE_LENGTH) -> dict:
+                           steps: int = EPISODE_LENGTH, graph: bool = True, return_actions: bool = False) -> dict:
     """The protocol with every episode of this rank's shard stepped concurrently; `policy(obs, mask) -> int32 [N,5]`
-    runs on device (no host round trip per tick)."""
+    runs on device and nothing crosses to the host during the episode: every episode ends on tick steps - 1
+    (EnterpriseScenarioGenerator.determine_done :862-871), whose reward the protocol drops (evaluation.py:104-110), so the loop
+    is steps - 2 counted ticks plus the final one, with no per-tick `done` read.  graph=True records one tick (policy, step,
+    accumulation) into a CUDA graph and replays it: a 100-episode batch is launch-bound (about twenty small kernels per tick);
+    a policy that cannot be captured (host synchronisation, dynamic shapes) falls back to eager ticks.
+    return_actions=True adds the submitted actions int32 [ticks, N, 5] (tests replay them through the oracle)."""
     lo, hi = shard(max_eps, rank, world)
     n = hi - lo
     dev = torch.device("cuda", device)
     totals = torch.zeros(max(n, 0), dtype=torch.float64, device=dev)
     t0 = time.time()
+    log = None
     if n > 0:
         env = BatchedCC4(n, device=device, seed=seed, steps=steps, first_episode=lo)
         obs, mask = env.reset()
-        for _ in range(steps):
-            acts = policy(obs, mask)
-            obs, rew, done = env.step(acts)
-            if bool(done[0]):          # every episode has the same length; the done tick's reward is dropped
-                break
-            totals += rew.double()
-    out = aggregate_scores(totals, max_eps, rank, world)
+        acts = torch.zeros((n, 5), dtype=torch.int32, device=dev)
+        counted = steps - 2                   # ticks 0 .. steps - 3 count; tick steps - 2 sets done and its reward is dropped
+        log = torch.zeros((counted + 1, n, 5), dtype=torch.int32, device=dev) if return_actions else None
+
+        def tick(count: bool):
+            acts.copy_(policy(env.obs, mask))
+            env.step(acts)
+            if count:
+                totals.add_(env.reward)
+
+        g = None
+        if graph and counted > 2 and log is None:
+            tick(True)                        # warm-up outside the capture (lazy allocations, cuBLAS handles); it is tick 0
+            done_ticks = 1
+            try:
+                torch.cuda.synchronize(dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    tick(True)
+            except Exception:               # noqa: BLE001  (policy not capturable)
+                g = None
+                torch.cuda.synchronize(dev)
+                env = BatchedCC4(n, device=device, seed=seed, steps=steps, first_episode=lo)       # start over, eagerly
+                obs, mask = env.reset()
+                totals.zero_()
+                done_ticks = 0
+            if g is not None:
+                for _ in range(counted - done_ticks):
+                    g.replay()
+                done_ticks = counted
+        else:
+            done_ticks = 0
+        for t in range(done_ticks, counted):
+            tick(True)
+            if log is not None:
+                log[t] = acts
+        tick(False)
+        if log is not None:
+            log[counted] = acts
+        assert bool(env.done.all()), "episodes must end on tick steps - 1"
+    import torch.distributed as dist
+    if world > 1 and not (dist.is_available() and dist.is_initialized()):
+        # a shard evaluated on its own (no process group): its totals only; the caller combines them (aggregate_scores needs the group)
+        vals = totals.cpu().tolist()
+        out = {"mean": mean(vals) if vals else 0.0, "stdev": stdev(vals) if len(vals) > 1 else 0.0, "episodes": len(vals), "rewards": vals}
+    else:
+        out = aggregate_scores(totals, max_eps, rank, world)
+    out["local_rewards"] = totals.cpu().tolist()
     out["seconds"] = time.time() - t0
+    if return_actions:
+        out["actions"] = log
     return out

@@ -39,6 +39,7 @@ def lib():
         L.cc4o_error_flags.argtypes = [C.c_void_p]
         L.cc4o_last_error.restype = C.c_char_p
         L.cc4o_last_error.argtypes = [C.c_void_p]
+        L.cc4o_reward_breakdown.argtypes = [C.c_void_p, C.c_void_p]
         L.cc4o_run_episodes.restype = C.c_long
         L.cc4o_run_episodes.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double)]
         _lib = L
@@ -112,6 +113,12 @@ class OracleEnv:
 
     def error(self):
         return self.L.cc4o_error_flags(self.h), self.L.cc4o_last_error(self.h).decode()
+
+    def reward_breakdown(self):
+        """int32 [3 mission phases][3 kinds: LWF, ASF, RIA][9 subnets, creation order]: BlueRewardMachine events since the reset."""
+        out = np.zeros((3, 3, 9), dtype=np.int32)
+        self.L.cc4o_reward_breakdown(self.h, out.ctypes.data)
+        return out
 
 
 def run_episodes(seed, first_episode, n_eps, steps=500):

@@ -366,7 +366,7 @@ def _inprog(ctrl, name):
 class RefEpisode:
     """One reference environment driven through BlueFlatWrapper with index actions."""
 
-    def __init__(self, seed: int, steps: int = 500, red: str = "fsm", rng: str = "pcg64", episode: int = 0):
+    def __init__(self, seed: int, steps: int = 500, red: str = "fsm", rng: str = "pcg64", episode: int = 0, pad_spaces: bool = False):
         _ensure_path()
         from CybORG import CybORG
         from CybORG.Agents import SleepAgent, EnterpriseGreenAgent, FiniteStateRedAgent
@@ -381,7 +381,7 @@ class RefEpisode:
         # construction runs create_scenario once; wrapper.reset() runs it again. Only the LAST scenario
         # matters; the tape keeps only the draws made after the final reset started.
         self.cyborg = CybORG(sg, seed=self.tape)
-        self.env = BlueFlatWrapper(self.cyborg)
+        self.env = BlueFlatWrapper(self.cyborg, pad_spaces=pad_spaces)
         self.tape.records.clear()
         self.tape.begin_segment(-1)
         self.obs, self.info = self.env.reset()
@@ -586,6 +586,59 @@ def run_episode(seed: int, policy: str = "sleep", steps: int = 500, n_ticks: int
     )
 
 
+def run_padded_episode(seed: int, steps: int, n_ticks: int, episode: int = 0) -> dict[str, np.ndarray]:
+    """BlueFlatWrapper(pad_spaces=True) of the live reference on the Philox seam (BlueFixedActionWrapper.py:311-328,
+    BlueFlatWrapper.py:251-254): every agent sees 210 observation entries and 242 actions; indices are drawn over the whole
+    padded range, so the `[Padding] Sleep` entries are exercised."""
+    import json
+    ep = RefEpisode(seed, steps, "fsm", "philox", episode, pad_spaces=True)
+    prng = np.random.Generator(np.random.PCG64(seed + 7919))
+    mask = ep.mask_array()
+    obs, acts, rews = [ep.obs_array()], [], []
+    for _ in range(n_ticks):
+        a = [int(prng.integers(0, 242)) for _ in range(5)]
+        _, r, _, _, _ = ep.step(a, [0] * 5)
+        acts.append(a)
+        rews.append(r["blue_agent_0"])
+        obs.append(ep.obs_array())
+    labels = [ep.env.action_labels(f"blue_agent_{b}") for b in range(5)]
+    spaces = [[int(ep.env.action_space(f"blue_agent_{b}").n), len(ep.env.observation_space(f"blue_agent_{b}"))] for b in range(5)]
+    return dict(seed=np.int64(seed), episode=np.int64(episode), steps=np.int32(steps), rng=np.array("philox"),
+                actions=np.array(acts, dtype=np.int16), obs=np.stack(obs), reward=np.array(rews, dtype=np.float32), mask=mask,
+                labels=np.array(json.dumps(labels)), spaces=np.array(spaces, dtype=np.int32))
+
+
+def dict_obs_summary(obs: dict) -> dict:
+    """The reconstructible part of a blue agent's dict observation (env.py:245): success, the action as it prints, the hosts
+    that carry an entry and, per host, the pids of its `Processes` entries (process-creation events, decoys)."""
+    hosts = {}
+    for k, v in obs.items():
+        if k in ("success", "action", "message"):
+            continue
+        hosts[str(k)] = sorted(int(p["PID"]) for p in v.get("Processes", []) if "PID" in p)
+    return {"success": obs["success"].name, "action": str(obs.get("action")), "hosts": hosts}
+
+
+def run_dictobs_episode(seed: int, policy: str, steps: int, episode: int = 0) -> dict[str, np.ndarray]:
+    """A reference episode on the Philox seam (so that the facade's production mode with the same seed IS this episode) with
+    the per-tick summaries of the five blue dict observations: fixture for cage_challenge_4_b200/observations.py."""
+    import json
+    ep = RefEpisode(seed, steps, "fsm", "philox", episode)
+    prng = np.random.Generator(np.random.PCG64(seed + 7919))
+    mask = ep.mask_array()
+    acts, msgs, summ, rews = [], [], [], []
+    for _ in range(steps - 1):
+        a, m = blue_policy(policy, prng, mask, ep.obs_array())
+        _, r, _, _, _ = ep.step(a, m)
+        acts.append(a)
+        msgs.append(m)
+        rews.append(r["blue_agent_0"])
+        summ.append([dict_obs_summary(ep.cyborg.get_observation(f"blue_agent_{b}")) for b in range(5)])
+    return dict(seed=np.int64(seed), episode=np.int64(episode), steps=np.int32(steps), policy=np.array(policy), rng=np.array("philox"),
+                actions=np.array(acts, dtype=np.int16), msgs=np.array(msgs, dtype=np.uint8), reward=np.array(rews, dtype=np.float32),
+                mask=mask, summaries=np.array(json.dumps(summ)))
+
+
 if __name__ == "__main__":
     import argparse
     import time
@@ -593,8 +646,24 @@ if __name__ == "__main__":
     ap.add_argument("--out", default=os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden"))
     ap.add_argument("--spec", nargs="*", default=["0:sleep:500", "1:sleep:500", "2:random:500", "3:random:500",
                                                   "4:masked:500", "5:masked:500"])
+    ap.add_argument("--padded", nargs="*", default=[], help="seed:steps:ticks fixtures of BlueFlatWrapper(pad_spaces=True) (Philox seam, episode 0)")
+    ap.add_argument("--dictobs", nargs="*", default=[], help="seed:policy:steps fixtures of the blue dict observations (Philox seam, episode 0)")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
+    for spec in args.dictobs:
+        seed, policy, steps = spec.split(":")
+        fx = run_dictobs_episode(int(seed), policy, int(steps))
+        path = os.path.join(args.out, f"dictobs_s{seed}_{policy}_{steps}.npz")
+        np.savez_compressed(path, **fx)
+        print(f"{path}: {len(fx['actions'])} ticks, {os.path.getsize(path) / 1024:.0f} KiB")
+    for spec in args.padded:
+        seed, steps, ticks = (int(x) for x in spec.split(":"))
+        fx = run_padded_episode(seed, steps, ticks)
+        path = os.path.join(args.out, f"pad_s{seed}_{steps}_{ticks}.npz")
+        np.savez_compressed(path, **fx)
+        print(f"{path}: {ticks} ticks, {os.path.getsize(path) / 1024:.0f} KiB")
+    if args.dictobs or args.padded:
+        sys.exit(0)
     for spec in args.spec:
         seed, policy, steps, *rest = spec.split(":")      # seed:policy:steps[:red[:episode]]  (red = fsm | discovery; episode => Philox seam)
         red = rest[0] if rest else "fsm"

@@ -86,10 +86,44 @@ def test_oracle_detects_a_corrupted_tape():
 
 
 def test_reward_table_matches_reference_tables():
-    """BlueRewardMachine.py:35-65 == README tables; checked through the oracle's observable reward: a failing
-    GreenLocalWork / GreenAccessService can only produce values from the table."""
-    fx = np.load(os.path.join(GOLDEN, FILES[0]))
-    assert set(np.unique(fx["reward"])) <= set(float(x) for x in range(-200, 1)) | {-0.5}
+    """The 81 values of BlueRewardMachine.get_phase_rewards (BlueRewardMachine.py:35-65), read from the LIVE reference into
+    tests/golden/ref_tables.json (oracle/ref_tables.py calls the reference's method), against what the oracle charges.  The
+    oracle counts its reward events per (mission phase, kind, subnet); on every tick of 240 production-mode episodes the
+    reward must equal sum(new events x the reference's value) + the action cost (-1 per Restore submitted, Restore.py:70),
+    and every cell of the eight populated subnets that carries a non-zero value must have been exercised."""
+    import json
+    tab = json.load(open(os.path.join(GOLDEN, "ref_tables.json")))
+    ref = np.zeros((3, 3, 9))
+    for p in range(3):
+        for sn, v in tab["reward"][str(p)].items():
+            ref[p, :, canon.SUBNET_IDX[sn]] = v
+    assert tab["cost"]["Restore"] == -1.0 and all(v == 0.0 for k, v in tab["cost"].items() if k != "Restore")
+    hit = np.zeros((3, 3, 9), dtype=np.int64)
+    g = np.random.default_rng(5)
+    for ep in range(240):
+        env = O.OracleEnv(seed=31, episode=ep, steps=500)
+        env.reset()
+        last = env.reward_breakdown().astype(np.int64)
+        mask = env.mask()
+        for t in range(499):
+            if ep % 3 == 0:
+                a = [49, 49, 49, 49, 145]                                     # all Sleep: red reaches the operational zones
+            elif ep % 3 == 1:
+                a = [int(g.integers(0, k)) for k in (82, 82, 82, 82, 242)]    # uniform indices: Restores, Blocks
+            else:                                                             # traffic control only: blocked green access (ASF) everywhere
+                a = [int(g.integers(50, 66)) for _ in range(4)] + [int(g.integers(146, 194))]
+            rc, _, rew, _ = env.step(a)
+            now = env.reward_breakdown().astype(np.int64)
+            d = now - last
+            last = now
+            restores = sum(1 for b, i in enumerate(a) if (2 * (48 if b == 4 else 16) + 1 <= i < 3 * (48 if b == 4 else 16) + 1) and mask[b, i])
+            assert rew == float((d * ref).sum()) - restores, f"episode {ep} tick {t}: reward {rew}, events {np.argwhere(d)}"
+            hit += d
+        assert env.error()[0] == 0
+    missing = [(p, "LWF ASF RIA".split()[k], canon.SUBNETS_CREATION[s]) for p in range(3) for k in range(3) for s in range(8)
+               if ref[p, k, s] != 0 and hit[p, k, s] == 0]
+    assert not missing, f"reward cells never exercised: {missing}"
+    assert hit[:, :, 8].sum() == 0          # nothing ever happens in the internet subnet (no green agents, no OT service, no red target)
 
 
 def test_philox_mode_is_deterministic_and_sharding_invariant():

@@ -1,5 +1,9 @@
 """The mirrored wrapper API, checked the way the reference checks its own wrappers
 (CybORG/Tests/test_cc4/test_BlueEnterpriseWrapper.py, test_mission_phase.py, test_cc4_seed.py)."""
+import json
+import os
+import re
+
 import numpy as np
 import pytest
 
@@ -11,6 +15,7 @@ from cage_challenge_4_b200.wrappers import (BlueEnterpriseWrapper, BlueFlatWrapp
                                             SUBNETS_SORTED)
 
 NUM_SUBNETS, MAX_HOSTS, MESSAGE_LENGTH, NUM_MESSAGES = 9, 16, 8, 4
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def make(seed=123, steps=100, cls=BlueEnterpriseWrapper, **kw):
@@ -79,8 +84,10 @@ def test_block_and_allow_show_up_in_the_vector():
     env.reset()
     a = "blue_agent_0"
     labels = env.action_labels(a)
-    blk = labels.index("BlockTrafficZone restricted_zone_a_subnet <- contractor_network_subnet")
-    alw = labels.index("AllowTrafficZone restricted_zone_a_subnet <- contractor_network_subnet")
+    strip = [re.sub(r" \([0-9./]+\)", "", l) for l in labels]        # labels carry the CIDRs like the reference's (BlueFixedActionWrapper.py:283)
+    blk = strip.index("BlockTrafficZone restricted_zone_a_subnet <- contractor_network_subnet")
+    alw = strip.index("AllowTrafficZone restricted_zone_a_subnet <- contractor_network_subnet")
+    assert labels[blk] == "BlockTrafficZone restricted_zone_a_subnet (10.0.0.0/24) <- contractor_network_subnet (10.0.4.0/24)"
     obs, *_ = env.step({a: blk})
     pos = 1 + 9 + SUBNETS_SORTED.index("contractor_network_subnet")
     assert obs[a][pos] == 1 and obs[a][1 + 9:1 + 18].sum() == 1
@@ -140,12 +147,27 @@ def test_episode_ends_and_agents_list_empties():
         EnterpriseScenarioGenerator(red_agent_class=SleepAgent)
 
 
-def test_pad_spaces():
-    env = make(cls=BlueFlatWrapper, pad_spaces=True)
+def test_pad_spaces_against_the_reference():
+    """BlueFlatWrapper(pad_spaces=True) (BlueFixedActionWrapper.py:311-328, BlueFlatWrapper.py:251-254) against the live
+    reference on the Philox seam (tests/golden/pad_*.npz, oracle/ref_harness.py --padded): spaces, masks, labels (CIDRs aside),
+    and every padded observation vector of 99 ticks of indices drawn over the whole padded range."""
+    fx = np.load(os.path.join(GOLDEN, "pad_s35_100_99.npz"))
+    env = make(seed=int(fx["seed"]), steps=int(fx["steps"]), cls=BlueFlatWrapper, pad_spaces=True)
     obs, info = env.reset()
-    assert all(len(v) == 210 for v in obs.values()) and all(len(i["action_mask"]) == 242 for i in info.values())
-    obs, rew, *_ = env.step({"blue_agent_0": 241})       # padding index acts as Sleep
-    assert all(len(v) == 210 for v in obs.values())
+    ref_labels = json.loads(str(fx["labels"]))
+    for b, a in enumerate(env.possible_agents):
+        assert [env.action_space(a).n, len(env.observation_space(a))] == fx["spaces"][b].tolist() == [242, 210]
+        assert info[a]["action_mask"] == fx["mask"][b].astype(bool).tolist() == env.action_mask(a)
+        strip = lambda ls: [re.sub(r" \([0-9./]+\)", "", l) for l in ls]
+        assert strip(env.action_labels(a)) == strip(ref_labels[b])
+        assert np.array_equal(obs[a], fx["obs"][0][b]) and obs[a].dtype == np.int64
+    for t in range(len(fx["actions"])):
+        obs, rew, term, trunc, info = env.step({a: int(fx["actions"][t][b]) for b, a in enumerate(env.possible_agents)})
+        for b, a in enumerate(env.possible_agents):
+            assert np.array_equal(obs[a], fx["obs"][t + 1][b]), (t, a)
+        assert rew["blue_agent_0"] == fx["reward"][t]
+    with pytest.raises(IndexError):
+        env.step({"blue_agent_0": 242})
 
 
 def test_evaluation_protocol_runs_unchanged_loop():
@@ -164,30 +186,78 @@ def test_evaluation_protocol_runs_unchanged_loop():
         def wrap(env):
             return EnterpriseMAE(env)
 
-    out = run_evaluation(Submission, max_eps=2, seed=3)
-    assert out["episodes"] == 2 and out["mean"] < 0
-    pol = MLPPolicy().cuda()
-    b1 = run_evaluation_batched(pol, max_eps=16, seed=5)
-    lo = run_evaluation_batched(pol, max_eps=16, seed=5, rank=0, world=1)
-    assert b1["rewards"] == lo["rewards"] and b1["episodes"] == 16 and b1["stdev"] > 0
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        out = run_evaluation(Submission, log_path=tmp, max_eps=2, seed=3, write_to_file=True)
+        assert out["episodes"] == 2 and out["mean"] < 0
+        # the five log files of evaluation.py:141-196
+        assert sorted(os.listdir(tmp)) == ["actions.txt", "full.txt", "scores.txt", "summary.json", "summary.txt"]
+        summary = json.load(open(os.path.join(tmp, "summary.json")))
+        assert summary["reward"]["mean"] == out["mean"] and summary["parameters"] == {"seed": 3, "episode_length": 500, "max_episodes": 2}
+        full = open(os.path.join(tmp, "full.txt")).read()
+        assert "DeployDecoy" in full and "observations:" in full and f"total reward: {out['rewards'][0]}" in full
 
 
-def test_random_blue_policy_picks_valid_non_traffic_actions():
-    """cc4BlueRandomAgent equivalent (RandomAgent.py:66-69) on device: valid actions only, no Block / Allow."""
+def test_batched_evaluation_totals_equal_an_oracle_replay_and_do_not_depend_on_sharding():
+    """run_evaluation_batched(MLPPolicy): the per-episode totals must be what the C oracle computes when it is fed the very
+    actions the policy emitted (evaluation.py:104-110 bookkeeping: the done tick's reward is dropped), with and without the
+    CUDA graph; and two shards (the ranks of a 2-GPU run, here run one after the other) must give the one-shard totals."""
+    import oracle_py as O
+    from cage_challenge_4_b200.evaluation import MLPPolicy, run_evaluation_batched
+    pol = MLPPolicy(seed=4).cuda()
+    n, steps, seed = 12, 120, 5
+    eager = run_evaluation_batched(pol, max_eps=n, seed=seed, steps=steps, graph=False, return_actions=True)
+    acts = eager["actions"].cpu().numpy()
+    assert acts.shape == (steps - 1, n, 5)
+    for i in range(n):
+        env = O.OracleEnv(seed=seed, episode=i, steps=steps)
+        env.reset()
+        total = 0.0
+        for t in range(steps - 1):
+            rc, _, r, d = env.step(acts[t, i])
+            assert d == (t == steps - 2)
+            if not d:
+                total += r
+        assert total == eager["rewards"][i], (i, total, eager["rewards"][i])
+    graphed = run_evaluation_batched(pol, max_eps=n, seed=seed, steps=steps, graph=True)
+    assert graphed["rewards"] == eager["rewards"] and graphed["stdev"] > 0
+    lo = run_evaluation_batched(pol, max_eps=n, seed=seed, steps=steps, rank=0, world=2)
+    hi = run_evaluation_batched(pol, max_eps=n, seed=seed, steps=steps, rank=1, world=2)
+    # world=2 without a process group: aggregate_scores is exercised by tests/test_sharding_cpu.py; here the shards' own totals
+    from cage_challenge_4_b200.evaluation import shard
+    assert shard(n, 0, 2) == (0, 6) and shard(n, 1, 2) == (6, 12)
+    assert lo["local_rewards"] + hi["local_rewards"] == eager["rewards"]
+
+
+def test_random_blue_policy_samples_class_then_parameter():
+    """cc4BlueRandomAgent (RandomAgent.py:28-56, 66-69) on device: the action CLASS is uniform over Sleep / Monitor / Analyse /
+    Remove / DeployDecoy / Restore (Block / Allow excluded), then the host is uniform over the existing ones."""
     import torch
     from cage_challenge_4_b200.engine import BatchedCC4
     from cage_challenge_4_b200.evaluation import RandomBluePolicy, run_evaluation_batched
-    env = BatchedCC4(256, device=0, seed=5)
+    env = BatchedCC4(4096, device=0, seed=5)
     obs, mask = env.reset()
     pol = RandomBluePolicy(seed=1)
-    seen = set()
-    for _ in range(20):
+    counts = np.zeros((2, 6))
+    for _ in range(10):
         a = pol(obs, mask)
         assert bool(torch.gather(mask, 2, a.long().unsqueeze(-1)).all())
-        assert not bool(((a[:, :4] >= 50) & (a[:, :4] < 66)).any()) and not bool(((a[:, 4] >= 146) & (a[:, 4] < 194)).any())
-        seen |= set(a[:, 0].tolist())
+        for k, (agents, H, T) in enumerate(((slice(0, 4), 16, 8), (slice(4, 5), 48, 24))):
+            x = a[:, agents].cpu().numpy().ravel()
+            assert not ((x >= 3 * H + 2) & (x < 3 * H + 2 + 2 * T)).any()          # no Allow / Block
+            cls = np.select([x == 3 * H + 1, x == H, x < H, x < 2 * H + 1, x < 3 * H + 1], [0, 1, 2, 3, 5], default=4)
+            counts[k] += np.bincount(cls, minlength=6)
         obs, rew, done = env.step(a)
-    assert len(seen) > 20
+    freq = counts / counts.sum(1, keepdims=True)
+    assert np.abs(freq - 1 / 6).max() < 0.01, freq              # 163 840 / 40 960 draws: three sigma is 0.003 / 0.006
+    # hosts uniform over the existing ones: every valid Analyse index of agent 0 in episode 0 comes up
+    valid = torch.nonzero(mask[0, 0, :16]).ravel().tolist()
+    seen = set()
+    for _ in range(300):
+        x = int(pol(obs, mask)[0, 0])
+        if x < 16:
+            seen.add(x)
+    assert seen == set(valid)
     out = run_evaluation_batched(RandomBluePolicy(seed=2), max_eps=32, seed=3, steps=60)
     assert out["episodes"] == 32 and out["mean"] < 0
 
@@ -222,5 +292,84 @@ def test_true_state_dict_of_the_wrapped_episode():
     assert sum(len(r["sessions"]) for r in st["red"].values()) >= 1
     mask_hosts = {h for a in env.possible_agents for h, m in zip([x for x in env.hosts(a) if "router" not in x], env.action_mask(a)) if m}
     assert {f"{h}" for h in mask_hosts} <= set(hosts)        # every host a blue agent may Analyse exists in the true state
-    with pytest.raises(NotImplementedError):
-        env.env.get_agent_state("blue_agent_0")
+    assert set(env.env.get_agent_state("blue_agent_0")) >= {"success", "message"}
+
+
+def test_facade_surface_of_env_py():
+    """CybORG/env.py: parallel_step :95, step :125, get_observation :245, get_action_space :266, get_last_action :300,
+    get_ip_map :327, get_rewards :348, get_attr :374, agents :394 — and BlueFixedActionWrapper.actions() :360."""
+    from cage_challenge_4_b200.wrappers import ActionDescriptor, BlueFixedActionWrapper, TernaryEnum
+    sg = EnterpriseScenarioGenerator(blue_agent_class=SleepAgent, green_agent_class=EnterpriseGreenAgent, red_agent_class=FiniteStateRedAgent, steps=100)
+    cy = CybORG(sg, seed=11)
+    assert cy.agents == cy.active_agents == [f"blue_agent_{i}" for i in range(5)]
+    fixed = BlueFixedActionWrapper(cy)
+    acts = fixed.actions("blue_agent_4")
+    labels = fixed.action_labels("blue_agent_4")
+    assert len(acts) == 242 and all(isinstance(a, ActionDescriptor) for a in acts)
+    i_restore = next(i for i, l in enumerate(labels) if l.startswith("Restore"))
+    assert str(acts[i_restore]) == labels[i_restore] and acts[i_restore].get_params()["session"] == 0
+    assert str(acts[145]) == "Sleep" and str(acts[48]) == "Monitor" and acts[146].name == "AllowTrafficZone"
+    assert fixed.get_action_space("blue_agent_4")["actions"] is acts
+    # parallel_step with indices: dict observations, team reward dicts, done flags (env.py:95-123)
+    obs, rew, done, info = cy.parallel_step({"blue_agent_4": i_restore, "blue_agent_0": 49})
+    assert set(obs) == set(cy.agents) and info == {}
+    assert obs["blue_agent_4"]["success"] is TernaryEnum.IN_PROGRESS                      # Restore takes 5 ticks (Restore.py:36)
+    assert obs["blue_agent_0"]["success"] is TernaryEnum.UNKNOWN and str(obs["blue_agent_0"]["action"]) == "Sleep"
+    assert rew["blue_agent_0"]["action_cost"] == -1.0 and set(rew["blue_agent_0"]) == {"BlueRewardMachine", "action_cost"}
+    assert cy.get_rewards()["Blue"] == rew["blue_agent_3"] and cy.get_rewards()["Red"] == {"None": 0.0, "action_cost": 0}
+    assert done["blue_agent_1"] is False
+    for _ in range(4):
+        obs, *_ = cy.parallel_step({})
+    assert obs["blue_agent_4"]["success"] is TernaryEnum.TRUE and str(obs["blue_agent_4"]["action"]) == labels[i_restore]
+    assert str(cy.get_last_action("blue_agent_4")[0]) == "Sleep"
+    res = cy.step("blue_agent_1", 16)                                                      # CC1/CC2-style call: Monitor
+    assert res.observation["success"] is TernaryEnum.TRUE and str(res.observation["action"]) == "Monitor" and res.done is False
+    # maps and action space dicts
+    ipm, space = cy.get_ip_map(), cy.get_action_space("blue_agent_0")
+    assert "root_internet_host_0" in ipm and len(set(ipm.values())) == len(ipm)
+    mine = [h for h, known in space["hostname"].items() if known]
+    assert mine and all(h.startswith("restricted_zone_a_subnet") for h in mine) and set(space["hostname"]) == set(ipm)
+    assert sum(space["subnet"].values()) == 1 and space["session"] == {0: True} and len(space["action"]) == 8
+    assert cy.get_attr("seed") == 11 and cy.get_attr("nonexistent") is None and fixed.get_attr("env") is cy
+    # the dict-observation wrapper (BlueFixedActionWrapper.reset :76 / step :101)
+    o, info = fixed.reset()
+    assert set(o["blue_agent_2"]) >= {"success", "message"} and len(info["blue_agent_2"]["action_mask"]) == 82
+    o, r, term, trunc, info = fixed.step({"blue_agent_2": 16})
+    assert str(o["blue_agent_2"]["action"]) == "Monitor" and isinstance(r["blue_agent_2"], float)
+
+
+def test_per_episode_wrappers_refuse_a_batch():
+    """A wrapper presents ONE episode: on a batch it would advance the other episodes with Sleep and drop their outputs."""
+    sg = EnterpriseScenarioGenerator(steps=50)
+    cy = CybORG(sg, seed=1, num_envs=4)
+    assert cy.engine.num_envs == 4
+    for cls in (BlueFlatWrapper, BlueEnterpriseWrapper, EnterpriseMAE):
+        with pytest.raises(ValueError, match="ONE episode"):
+            cls(cy)
+    with pytest.raises(ValueError):
+        cy.parallel_step({})
+    obs, rew, done = cy.engine.step(torch.tensor([[49, 49, 49, 49, 145]] * 4, dtype=torch.int32, device="cuda"))     # the batch API still works
+    assert obs.shape == (4, 5, 210)
+
+
+def test_dict_observations_against_the_reference():
+    """GPU twin of tests/test_state_cpu.py::test_dict_observations_match_the_reference_cpu: the real facade in production
+    mode with the fixture's seed IS the reference episode recorded on the Philox seam, so CybORG.get_observation must report
+    the reference's success / action / hosts / pids on every tick."""
+    for name in sorted(f for f in os.listdir(GOLDEN) if f.startswith("dictobs_")):
+        fx = np.load(os.path.join(GOLDEN, name))
+        expected = json.loads(str(fx["summaries"]))
+        sg = EnterpriseScenarioGenerator(steps=int(fx["steps"]))
+        cy = CybORG(sg, seed=int(fx["seed"]))
+        cy.enable_dict_observations()
+        for t in range(len(fx["actions"])):
+            msgs = {f"blue_agent_{b}": np.array([(int(fx["msgs"][t][b]) >> i) & 1 for i in range(8)], dtype=bool) for b in range(5)}
+            obs, rew, done, _ = cy.parallel_step({f"blue_agent_{b}": int(fx["actions"][t][b]) for b in range(5)}, messages=msgs)
+            assert round(sum(rew["blue_agent_0"].values()), 1) == fx["reward"][t]
+            for b in range(5):
+                got, exp = obs[f"blue_agent_{b}"], expected[t][b]
+                assert got["success"].name == exp["success"], (name, t, b)
+                if exp["success"] != "IN_PROGRESS":
+                    assert str(got["action"]) == exp["action"], (name, t, b)
+                hosts = {k: sorted(p["PID"] for p in v.get("Processes", []) if "PID" in p) for k, v in got.items() if k not in ("success", "action", "message")}
+                assert hosts == exp["hosts"], (name, t, b, hosts, exp["hosts"])
