@@ -153,7 +153,7 @@ def test_pad_spaces_against_the_reference():
     and every padded observation vector of 99 ticks of indices drawn over the whole padded range."""
     fx = np.load(os.path.join(GOLDEN, "pad_s35_100_99.npz"))
     env = make(seed=int(fx["seed"]), steps=int(fx["steps"]), cls=BlueFlatWrapper, pad_spaces=True)
-    obs, info = env.reset()
+    obs, info = env.reset(seed=int(fx["seed"]))         # re-seeding restarts the episode numbering: (seed, episode 0), the fixture's episode
     ref_labels = json.loads(str(fx["labels"]))
     for b, a in enumerate(env.possible_agents):
         assert [env.action_space(a).n, len(env.observation_space(a))] == fx["spaces"][b].tolist() == [242, 210]
