@@ -65,9 +65,11 @@ enum {
     ST_FSM_HOST, ST_FSM_ACTION, ST_FSM_PARAM, ST_PORTSCAN, ST_EXP_OTHER, ST_EXP_TOP, ST_EXP_SUCC, ST_EXP_DETECT, ST_SSH_HOP,
     ST_PRIV_SESS, ST_DD_TP, ST_DD_FP, ST_RSC_PRIMARY, ST_DECOY_FACTORY,
     /* DiscoveryFSRed only (FiniteStateRedAgent._choose_host :252-293) */
-    ST_FSMD_STATE_P, ST_FSMD_STATE_U, ST_FSMD_ROLL, ST_FSMD_HOST_SRV, ST_FSMD_HOST_OTHER, ST_FSMD_HOST_SRV2, ST_FSMD_HOST_ALL
+    ST_FSMD_STATE_P, ST_FSMD_STATE_U, ST_FSMD_ROLL, ST_FSMD_HOST_SRV, ST_FSMD_HOST_OTHER, ST_FSMD_HOST_SRV2, ST_FSMD_HOST_ALL,
+    /* RandomSelectRedAgent only (RandomSelectRedAgent.get_action :37-92) */
+    ST_RS_COMMAND, ST_RS_PARAM
 };
-static_assert(ST_DECOY_FACTORY == 31 && ST_FSMD_HOST_ALL == 38, "draw sites must match oracle/cc4_oracle.h");
+static_assert(ST_DECOY_FACTORY == 31 && ST_FSMD_HOST_ALL == 38 && ST_RS_PARAM == 40, "draw sites must match oracle/cc4_oracle.h");
 
 /* action codes (oracle/canon.py ACTION_CODE) */
 enum { AC_SLEEP = 0, AC_MONITOR, AC_ANALYSE, AC_REMOVE, AC_RESTORE, AC_DECOY, AC_BLOCK, AC_ALLOW, AC_INVALID,
@@ -185,7 +187,7 @@ struct BlockCtx {
     const cc4_draw *tape; uint32_t n_segs;
     int steps, rng_mode;
     uint32_t k0;
-    int red_variant;          /* 0 FiniteStateRedAgent, 1 DiscoveryFSRed */
+    int red_variant;          /* 0 FiniteStateRedAgent, 1 DiscoveryFSRed, 2 RandomSelectRedAgent */
 };
 __shared__ BlockCtx g_blk;
 /* tape mode (parity replay of the reference's recorded draws) or production mode (Philox); CC4_WITH_TAPE=0 builds a
@@ -536,7 +538,7 @@ __device__ CC4_INL5 void sess_delete(Cx c, int idx)
     SCR(c)->sess_moved = 1;
 }
 /* State.add_session State.py:305-323 for a red agent; returns the ident */
-__device__ CC4_INL4 int sess_add(Cx c, int r, int host, int abstract, int root, int pid)
+__device__ CC4_INL4 int sess_add(Cx c, int r, int host, int abstract, int root, int pid, int has_parent = 0)
 {
     Cc4Dyn *s = DYN(c);
     const int n = s->n_sess;
@@ -547,7 +549,7 @@ __device__ CC4_INL4 int sess_add(Cx c, int r, int host, int abstract, int root, 
     if (id > 255) { fail(c, CC4_E_CAPACITY); id = 255; }
     if (s->sess_count[r] < 255) s->sess_count[r]++;
     s->sess[n] = S_MAKE(pid, id, host);
-    s->sessf[n] = (uint8_t)(r | abstract << 3 | root << 4);
+    s->sessf[n] = (uint8_t)(r | abstract << 3 | root << 4 | has_parent << 5);
     s->n_sess = (uint16_t)(n + 1);
     if (abstract) SCR(c)->newss |= 1u << r;     /* its ident becomes a known server_session key with the end-turn observation */
     return id;
@@ -668,6 +670,7 @@ __device__ CC4_INL8 void agent_end_turn(Cx c, int r)
         if (m >> 16) snk |= 1u << (2 * w + 1);
     }
     s->sn_known[r] = (uint16_t)snk;
+    if (g_blk.red_variant == 2) return;       /* RandomSelectRedAgent keeps no host states: the action-space update above is all */
 
     /* _host_state_transition :124-167 on the action the merged observation reports */
     const int started = (s->fsm_started >> r) & 1;
@@ -874,11 +877,62 @@ __device__ __noinline__ uint32_t red_policy_discovery(Cx c, int r, uint32_t lo, 
     return fsm_choose_action(c, r, slot, ri, rf);
 }
 
+/* RandomSelectRedAgent.get_action RandomSelectRedAgent.py:37-92 [lane], out of line: a uniformly drawn valid command, then one
+ * uniform draw per parameter that has more than one known option.  Options come in action-space dict order: subnets and
+ * hosts in creation order (per subnet the user hosts, then the servers: EnterpriseScenarioGenerator.py:342-366), sessions in the
+ * order they became known.  The words are those of the generic stream functions (oracle: red_policy_random). */
+__device__ __noinline__ uint32_t red_policy_random(Cx c, int r)
+{
+    Cc4Dyn *s = DYN(c);
+    const int actor = A_RED0 + r;
+    auto ri = [&](int site, uint32_t n) -> uint32_t { return rng_int(c, actor, site, n); };
+    /* a known-host mask by creation rank: inside every 16-bit subnet group the ten user slots (6..15) come before the six servers */
+    auto ranked = [](uint32_t w) -> uint32_t {
+        const uint32_t lo = w & 0xFFFFu, hi = w >> 16;
+        return ((lo >> 6) | (lo & 0x3Fu) << 10) | ((hi >> 6) | (hi & 0x3Fu) << 10) << 16;
+    };
+    auto nth_host = [&](const uint32_t *known, int k) -> int {        /* k-th known host in creation order -> slot */
+        _Pragma("unroll 1") for (int w = 0; w < 4; w++) {
+            const uint32_t m = ranked(known[w]);
+            const int cnt = __popc(m);
+            if (k < cnt) { const int rank = w * 32 + nth_bit(m, k), j = rank & 15; return (rank & ~15) | (j < 10 ? 6 + j : j - 10); }
+            k -= cnt;
+        }
+        return 0;
+    };
+    const int nss = s->n_ss[r], nsub = __popc((uint32_t)s->sn_known[r]);
+    const int nip = __popc(s->ip_known[r][0]) + __popc(s->ip_known[r][1]) + __popc(s->ip_known[r][2]) + __popc(s->ip_known[r][3]);
+    const int nhn = __popc(s->hn_known[r][0]) + __popc(s->hn_known[r][1]) + __popc(s->hn_known[r][2]) + __popc(s->hn_known[r][3]);
+    /* action_space['action'] order = red_actions (EnterpriseScenarioGenerator.py:764-768), four bits each; valid = every parameter has an option */
+    const uint64_t cmds = (uint64_t)AC_DRS | (uint64_t)AC_AGGR << 5 | (uint64_t)AC_STEALTH << 10 | (uint64_t)AC_EXPLOIT << 15 | (uint64_t)AC_PRIVESC << 20 |
+                          (uint64_t)AC_DEGRADE << 25 | (uint64_t)AC_DD << 30 | (uint64_t)AC_IMPACT << 35 | (uint64_t)AC_WITHDRAW << 40 | (uint64_t)AC_SLEEP << 45;
+    uint64_t list = 0; int n = 0;
+    _Pragma("unroll 1") for (int i = 0; i < 10; i++) {
+        const int cd = (int)(cmds >> (5 * i) & 31u);
+        const bool ok = cd == AC_SLEEP ? true : cd == AC_DRS ? (nss && nsub) : (cd == AC_PRIVESC || cd == AC_DEGRADE || cd == AC_IMPACT) ? (nss && nhn)
+                        : cd == AC_WITHDRAW ? (nss && nip && nhn) : (nss && nip);
+        if (ok) list |= (uint64_t)cd << (5 * n++);
+    }
+    Act a = { (int)(list >> (5 * ri(ST_RS_COMMAND, (uint32_t)n)) & 31u), -1, -1, 0 };
+    auto pick = [&](int cnt) -> int { return cnt > 1 ? (int)ri(ST_RS_PARAM, (uint32_t)cnt) : 0; };
+    auto session = [&]() { a.session = s->ss[r][pick(nss)]; };
+    switch (a.code) {       /* parameters in constructor-signature order */
+    case AC_DRS: a.subnet = (int)__fns((uint32_t)s->sn_known[r], 0, pick(nsub) + 1); session(); break;
+    case AC_AGGR: case AC_STEALTH: case AC_DD: session(); a.host = nth_host(s->ip_known[r], pick(nip)); break;
+    case AC_EXPLOIT: a.host = nth_host(s->ip_known[r], pick(nip)); session(); break;
+    case AC_PRIVESC: case AC_DEGRADE: case AC_IMPACT: a.host = nth_host(s->hn_known[r], pick(nhn)); session(); break;
+    case AC_WITHDRAW: session(); (void)pick(nip); a.host = nth_host(s->hn_known[r], pick(nhn)); break;     /* ip_address only routes the RemoteAction */
+    default: break;
+    }
+    return pack_act(a, 0);
+}
+
 /* FiniteStateRedAgent.get_action :58-123 for one red agent [lane].  Returns the packed action (ticks = 0). */
 __device__ CC4_INL8 uint32_t red_policy(Cx c, int r)
 {
     Cc4Dyn *s = DYN(c);
     int actor = A_RED0 + r;
+    if (g_blk.red_variant == 2) return red_policy_random(c, r);         /* draws every tick, also while an action is in flight */
     if (IP_CODE(s->inprog[actor]) != IP_NONE) return ACT_SLEEP_WORD;     /* last observation was IN_PROGRESS :100-102 */
     const Cc4Fsm *f = &s->fsm[r];
     const int nf = s->n_fsm[r];
@@ -952,13 +1006,13 @@ __device__ CC4_INL4 void ev_procpid(Cx c, int slot, int pid)
 }
 
 /* StopProcess.execute_targeteted_local_action + kill_process StopProcess.py:23-58 [uniform] */
-__device__ CC4_INL6 void stop_process(Cx c, int actor, int h, uint32_t pid)
+__device__ CC4_INL6 bool stop_process(Cx c, int actor, int h, uint32_t pid, bool stop_all = false)
 {
     Cc4Dyn *s = DYN(c);
     int pi = proc_find(c, h, pid);
-    if (pi < 0) return;
+    if (pi < 0) return false;
     uint32_t w = PROCS(c, h)[pi];
-    if (P_ROOT(w)) return;
+    if (!stop_all && P_ROOT(w)) return false;
     int si = session_from_pid(s, h, pid);
     /* a stopped OT service keeps Service.process; a pid collision with it takes the reference down a path that
        re-labels the killed process as the service's (StopProcess.py:37-42): not modelled */
@@ -972,10 +1026,11 @@ __device__ CC4_INL6 void stop_process(Cx c, int actor, int h, uint32_t pid)
         proc_append(c, h, P_MAKE(np, P_KIND(w), P_ROOT(w), 1));
         if (si >= 0) fail(c, CC4_E_UNREACHABLE);   /* a session whose process is a service process */
     }
-    if (si < 0) return;
+    if (si < 0) return true;
     int r = SF_AGENT(s->sessf[si]);
     sess_delete(c, si);
     if (s->sess_count[r] > 0) s->sess_count[r]--;
+    return true;
 }
 
 /* RestoreFromBackup.py:9-19 + Host.restore Host.py:373-429 [uniform] */
@@ -1279,7 +1334,7 @@ __device__ CC4_INL3 int exploit_new_session(Cx c, int r, int target, uint32_t pd
 {
     int pid = create_pid_red(c, r, pmax_target);
     proc_append(c, target, P_MAKE(pid, K_SHELL, 0, 0), pd_target, pmax_target);
-    sess_add(c, r, target, 0, 0, pid);
+    sess_add(c, r, target, 0, 0, pid, 1);      /* parent = the acting session, ExploitAction.py:256 */
     return pid;
 }
 /* index of the known-port entry of (agent, abstract session, host), -1 if none; *word = the entry [uniform] */
@@ -1571,6 +1626,37 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
         obs_entry(c, r, 0, h, 0, 0, 0, 0);
         return SUCC_TRUE;
     }
+    case AC_WITHDRAW: {    /* Withdraw.py:38-91 (RandomSelectRedAgent only): every session of the agent on the host goes */
+        if (si < 0) return SUCC_FALSE;
+        const int h = a.host;
+        /* the sessions to stop, as idents in the scratch: those with a parent first, then the parentless ones except ident 0, both in
+           dict (= pool) order; the acting session last when it sits on the host (a second time when its ident is not 0) */
+        uint8_t *ids = SCR(c)->ra.ident;
+        int n = 0;
+        const int ns = s->n_sess;
+        _Pragma("unroll 1") for (int pass = 0; pass < 2; pass++)
+            _Pragma("unroll 1") for (int base = 0; base < ns; base += 32) {
+                const int i = base + lane;
+                const uint32_t w = i < ns ? s->sess[i] : 0u, f = i < ns ? (uint32_t)s->sessf[i] : 0u;
+                const bool on = i < ns && SF_AGENT(f) == (uint32_t)r && S_HOST(w) == (uint32_t)h;
+                const uint32_t m = __ballot_sync(FULLMASK, on && (pass == 0 ? SF_PARENT(f) != 0u : (!SF_PARENT(f) && S_ID(w) != 0u)));
+                const int at = n + __popc(m & ((1u << lane) - 1u));
+                if ((m >> lane & 1u) && at < 31) ids[at] = (uint8_t)S_ID(w);
+                n += __popc(m);
+            }
+        if (n > 30) { fail(c, CC4_E_CAPACITY); n = 30; }
+        __syncwarp();
+        if (S_host == h) { if (lane == 0) ids[n] = (uint8_t)a.session; n++; }
+        __syncwarp();
+        if (n == 0) return SUCC_FALSE;
+        _Pragma("unroll 1") for (int k = 0; k < n; k++) {
+            /* StopProcess(stop_all=True): TargetedLocalAction.py:14-21 needs the acting and the target session, StopProcess.py:23-33 the process */
+            const int ti = sess_find(s, r, ids[k]);
+            if (ti < 0 || sess_find(s, r, a.session) < 0) return SUCC_FALSE;
+            if (!stop_process(c, actor, h, S_PID(s->sess[ti]), true)) return SUCC_FALSE;
+        }
+        return SUCC_TRUE;
+    }
     case AC_INVALID: return SUCC_FALSE;
     default: return SUCC_UNKNOWN;
     }
@@ -1594,6 +1680,10 @@ __device__ CC4_INL6 void rsc_reelect(Cx c, int r, int n)
     const int ns = s->n_sess;
     sess_shift_down(s, at, ns);      /* the re-keyed entry moves to the end of the agent's dict */
     s->sess[ns - 1] = S_MAKE(S_PID(w), 0, S_HOST(w)); s->sessf[ns - 1] = f;
+    __syncwarp();
+    /* every session of the agent now hangs under the new primary, whose name is None (RedSessionCheck.py:50-54): no parents left */
+    _Pragma("unroll 1") for (int i = lane_id(); i < ns; i += 32) if (SF_AGENT((uint32_t)s->sessf[i]) == (uint32_t)r) s->sessf[i] &= (uint8_t)~SF_PARENTBIT;
+    __syncwarp();
 }
 
 /* SimulationController.different_subnet_agent_reassignment :820-903 [uniform] */

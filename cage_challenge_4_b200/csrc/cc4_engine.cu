@@ -349,7 +349,7 @@ __device__ __forceinline__ void ph_setup(Cx c)
    Philox keyed (policy_seed, episode, tick) exactly as oracle/cc4_oracle.c cc4o_run_episodes.  Also sorts the episode into
    the cost classes of the two action phases (each_episode). ---- */
 /*                                          Sl Mo An Rm Rs De Bl Al In  -  DRS Ag St DD Ex Pr Im Dg Wd */
-__constant__ uint8_t c_act_weight[32] = { 0, 2, 0, 4, 6, 4, 1, 1, 0, 0, 5, 3, 3, 3, 6, 4, 3, 3, 0 };
+__constant__ uint8_t c_act_weight[32] = { 0, 2, 0, 4, 6, 4, 1, 1, 0, 0, 5, 3, 3, 3, 6, 4, 3, 3, 4 };
 __device__ __forceinline__ void ph_policy(Cx c, int e, bool exists, bool live, int sl, bool red_part, const int32_t *actions, uint32_t pk0, uint32_t pk1,
                                           uint64_t ep, PhaseOrder *ord_blue, PhaseOrder *ord_red)
 {
@@ -394,7 +394,7 @@ __device__ __forceinline__ void ph_policy(Cx c, int e, bool exists, bool live, i
         const Cc4Cold *k = WC(c)->k;
         if (sl < (red_part ? CC4_NRED : CC4_NBLUE)) {   /* directory entry, home slab and largest pid of the actor's target host */
             const uint32_t w = x->subw[red_part ? A_RED0 + sl : sl], code = IP_CODE(w), h = IP_HOST(w);
-            const bool hosty = (code == AC_REMOVE || code == AC_RESTORE || code == AC_DECOY || (code >= AC_AGGR && code <= AC_DEGRADE)) && h < 128;
+            const bool hosty = (code == AC_REMOVE || code == AC_RESTORE || code == AC_DECOY || (code >= AC_AGGR && code <= AC_WITHDRAW)) && h < 128;
             if (hosty) {
                 prefetch_l2(&k->pdir[h]); prefetch_l2(&k->parena[h * CC4_OSLAB]); prefetch_l2(&k->pmax[h]);
                 if (code == AC_RESTORE) { const Cc4Stat *st = WC(c)->st; prefetch_l2(&st->o_procs[h][0]); prefetch_l2(&st->o_svc64[h]); prefetch_l2(&st->o_nproc[h]); }
@@ -1487,7 +1487,7 @@ extern "C" int cc4_set_episode_base(cc4_handle *h, uint64_t seed, uint64_t first
 
 extern "C" int cc4_set_red_agent(cc4_handle *h, int variant)
 {
-    if (!h || (variant != CC4_RED_FINITE_STATE && variant != CC4_RED_DISCOVERY)) return set_err(CC4_ERR_ARG, "cc4_set_red_agent: bad argument%s", "");
+    if (!h || (variant != CC4_RED_FINITE_STATE && variant != CC4_RED_DISCOVERY && variant != CC4_RED_RANDOM_SELECT)) return set_err(CC4_ERR_ARG, "cc4_set_red_agent: bad argument%s", "");
     h->p.red_variant = variant;
     return CC4_OK;
 }
@@ -1900,8 +1900,9 @@ extern "C" int cc4_export_canon(cc4_handle *h, int env, int32_t *out, int cap, i
         PUT(cnt); for (int s = 0; s < 128; s++) if ((d.hn_known[r][s >> 5] >> (s & 31)) & 1) PUT(s);
         PUT(d.sn_known[r]);
         PUT(d.n_ss[r]); for (int i = 0; i < d.n_ss[r]; i++) PUT(d.ss[r][i]);
-        PUT(d.n_fsm[r]);
-        for (int i = 0; i < d.n_fsm[r]; i++) {
+        const int nfsm = h->p.red_variant == CC4_RED_RANDOM_SELECT ? 0 : d.n_fsm[r];      /* RandomSelectRedAgent keeps no host states */
+        PUT(nfsm);
+        for (int i = 0; i < nfsm; i++) {
             int slot = d.fsm_order[r][i], w = slot >> 5, b = slot & 31, stt = 0;
             for (int pl = 0; pl < 4; pl++) stt |= (int)(d.fsm[r].pl[pl][w] >> b & 1u) << pl;
             PUT(slot); PUT(stt); PUT(d.fsm[r].hn[w] >> b & 1u);

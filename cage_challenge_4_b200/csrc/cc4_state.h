@@ -48,7 +48,9 @@ enum { K_SSHD, K_OT, K_APACHE2, K_MYSQLD, K_SMTP, K_D_APACHE, K_D_TOMCAT, K_D_HA
 #define SVC_ENTRY(v, i) ((uint32_t)((v) >> (7 * (i))) & 0x7Fu)
 #define SVC_OT_STOPPED (1ull << 63)
 
-/* red session (Shared/Session.py:6,120): pid | ident<<16 | host<<24 ; flags: agent | abstract<<3 | root<<4 */
+/* red session (Shared/Session.py:6,120): pid | ident<<16 | host<<24 ; flags: agent | abstract<<3 | root<<4 | has-parent<<5
+ * (Session.parent is not None: set by an exploit, ExploitAction.py:256; reset by a re-election, RedSessionCheck.py:50-54; only
+ * Withdraw, i.e. the RandomSelectRedAgent, looks at it) */
 #define S_PID(w) ((w) & 0xFFFFu)
 #define S_ID(w) (((w) >> 16) & 0xFFu)
 #define S_HOST(w) (((w) >> 24) & 0x7Fu)
@@ -56,6 +58,8 @@ enum { K_SSHD, K_OT, K_APACHE2, K_MYSQLD, K_SMTP, K_D_APACHE, K_D_TOMCAT, K_D_HA
 #define SF_AGENT(f) ((f) & 7u)
 #define SF_ABS(f) (((f) >> 3) & 1u)
 #define SF_ROOT(f) (((f) >> 4) & 1u)
+#define SF_PARENT(f) (((f) >> 5) & 1u)
+#define SF_PARENTBIT (1u << 5)
 
 /* known ports of a RedAbstractSession (Session.py:125-133): mask | host<<6 | ident<<13 | agent<<21 */
 #define PT_MASK(w) ((w) & 0x3Fu)

@@ -46,7 +46,8 @@ DRAW_DTYPE = np.dtype([("val", "<u8"), ("n", "<u2"), ("site", "u1"), ("kind", "u
 class BatchedCC4:
     """N independent CC4 episodes on one GPU.  Episode i draws from the RNG stream (seed, first_episode + i)."""
 
-    RED_AGENTS = {"finite_state": 0, "fsm": 0, "FiniteStateRedAgent": 0, "discovery": 1, "DiscoveryFSRed": 1}
+    RED_AGENTS = {"finite_state": 0, "fsm": 0, "FiniteStateRedAgent": 0, "discovery": 1, "DiscoveryFSRed": 1,
+                  "random_select": 2, "RandomSelectRedAgent": 2}
 
     def __init__(self, num_envs: int, device: int | str | torch.device = 0, seed: int = 0, steps: int = 500,
                  first_episode: int = 0, rng: str = "philox", red_agent: str = "finite_state"):

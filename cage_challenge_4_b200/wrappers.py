@@ -9,7 +9,7 @@ Each wrapper object presents ONE episode of a `BatchedCC4` batch (index `env_ind
 
 What is NOT mirrored (out of the hot path): executable `Action` objects (actions are the wrapper's
 integer indices; `BlueFixedActionWrapper.actions()` returns descriptors that print like the reference's objects) and
-user-supplied red / green agent classes (the engine scripts FiniteStateRedAgent, DiscoveryFSRed and EnterpriseGreenAgent;
+user-supplied red / green agent classes (the engine scripts FiniteStateRedAgent, DiscoveryFSRed, RandomSelectRedAgent and EnterpriseGreenAgent;
 anything else raises).  The engine's state has no IP addresses (in the reference they are random labels that never
 influence a transition): `get_ip_map` / `get_cidr_map` and the labels use a fixed synthetic numbering (10.0.<subnet>.0/24,
 host k of a subnet at .k+2) instead.  The per-episode classes present ONE episode and therefore require `num_envs == 1`;
@@ -70,6 +70,10 @@ class DiscoveryFSRed(FiniteStateRedAgent):
     """Scripted in-kernel (FSMRedVariants.py:72-122: host-state priorities, server bias, discovery-weighted actions)."""
 
 
+class RandomSelectRedAgent(BaseAgent):
+    """Scripted in-kernel (RandomSelectRedAgent.py:8-139: uniformly random valid command and parameters, Withdraw included)."""
+
+
 class EnterpriseScenarioGenerator:
     """Same constructor as Simulator/Scenarios/EnterpriseScenarioGenerator.py:95-101."""
     MIN_USER_HOSTS, MAX_USER_HOSTS, MIN_SERVER_HOSTS, MAX_SERVER_HOSTS = 3, 10, 1, 6
@@ -77,8 +81,8 @@ class EnterpriseScenarioGenerator:
 
     def __init__(self, blue_agent_class=None, red_agent_class=None, green_agent_class=None, steps: int = 100):
         red_name = "FiniteStateRedAgent" if red_agent_class is None else getattr(red_agent_class, "__name__", "")
-        if red_name not in ("FiniteStateRedAgent", "DiscoveryFSRed"):
-            raise NotImplementedError("the engine scripts FiniteStateRedAgent and DiscoveryFSRed (SURVEY.md section 8f lists the other red agents as next)")
+        if red_name not in ("FiniteStateRedAgent", "DiscoveryFSRed", "RandomSelectRedAgent"):
+            raise NotImplementedError("the engine scripts FiniteStateRedAgent, DiscoveryFSRed and RandomSelectRedAgent; other red agent classes cannot run in the kernel")
         self.red_agent = red_name
         if green_agent_class not in (None, EnterpriseGreenAgent) and getattr(green_agent_class, "__name__", "") != "EnterpriseGreenAgent":
             raise NotImplementedError("the engine scripts EnterpriseGreenAgent only")

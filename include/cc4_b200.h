@@ -76,9 +76,11 @@ int cc4_set_episode_base(cc4_handle *h, uint64_t seed, uint64_t first_episode);
 
 /* Scripted red agent class of every episode (EnterpriseScenarioGenerator(red_agent_class=...)): FiniteStateRedAgent
  * (CybORG/Agents/SimpleAgents/FiniteStateRedAgent.py, the challenge default) or its DiscoveryFSRed variant
- * (FSMRedVariants.py:72-122: host-state priority list, server bias, discovery-weighted action matrix).  Call before
- * cc4_reset; it takes effect from the next tick on. */
-enum { CC4_RED_FINITE_STATE = 0, CC4_RED_DISCOVERY = 1 };
+ * (FSMRedVariants.py:72-122: host-state priority list, server bias, discovery-weighted action matrix), or the
+ * RandomSelectRedAgent (RandomSelectRedAgent.py:8-139: a uniformly drawn valid command with uniformly drawn parameters every
+ * tick; the only scripted agent that uses Withdraw, Withdraw.py:38-91).  Call before cc4_reset; it takes effect from the
+ * next tick on. */
+enum { CC4_RED_FINITE_STATE = 0, CC4_RED_DISCOVERY = 1, CC4_RED_RANDOM_SELECT = 2 };
 int cc4_set_red_agent(cc4_handle *h, int variant);
 
 /* Packed per-episode state sizes in bytes: hot = the record streamed through shared memory every tick (read + written),

@@ -153,6 +153,8 @@ typedef struct {
 } host_t;
 typedef struct {
     int id, host, pid; uint8_t type /*0 Session, 1 RedAbstractSession, 2 VelociraptorServer*/, root;
+    uint8_t has_parent;    /* Session.parent is not None (Session.py:53): set by an exploit (ExploitAction.py:256), reset by a re-election
+                              (RedSessionCheck.py:50-54: parent = the new primary's name, which is None); only Withdraw looks at it */
     uint8_t has_ports[NSLOT], ports[NSLOT];                           /* Shared/Session.py:125-133 */
 } sess_t;
 typedef struct { int code, host, subnet, session; } act_t;            /* an Action instance: type + parameters */
@@ -783,12 +785,12 @@ static void do_monitor(cc4o_env *e, int b)
 }
 
 /* StopProcess.execute_targeteted_local_action + kill_process StopProcess.py:23-58 */
-static void stop_process(cc4o_env *e, int actor, int slot, int pid)
+static int stop_process(cc4o_env *e, int actor, int slot, int pid, int stop_all)
 {
     host_t *h = &e->hosts[slot];
     int pi = find_proc(h, pid);
-    if (pi < 0) return;
-    if (h->procs[pi].root) return;
+    if (pi < 0) return 0;
+    if (!stop_all && h->procs[pi].root) return 0;
     proc_t p = h->procs[pi];
     int ag = -1, si = session_from_pid(e, slot, pid, &ag);
     del_proc(h, pi);
@@ -799,13 +801,14 @@ static void stop_process(cc4o_env *e, int actor, int slot, int pid)
         add_proc(e, slot, np, p.kind, p.root);
         h->svcs[svc].pid = np;
     }
-    if (si < 0) return;
+    if (si < 0) return 1;
     sess_t old = e->sess[ag][si];
     del_sess(e, ag, si);
     e->sess_count[ag]--;
-    if (svc < 0) return;
+    if (svc < 0) return 1;
     /* a session whose process is also a service process: re-created with a fresh pid (StopProcess.py:48-58) */
     add_session(e, actor, ag, slot, old.type, old.root, -1, old.type == 1 ? K_REDABS : K_SESSION, -1);
+    return 1;
 }
 
 /* RestoreFromBackup.py:9-19 + Host.restore Host.py:373-429 */
@@ -867,7 +870,7 @@ static int exec_blue(cc4o_env *e, int b, const act_t *a)
     case AC_REMOVE: {   /* Remove.py:42-69 */
         if (!blue_has_session(e, b, a->host)) return SUCC_FALSE;
         int n = e->n_sus[b];
-        for (int i = 0; i < n; i++) if (e->sus[b][i].slot == a->host) stop_process(e, actor, a->host, e->sus[b][i].pid);
+        for (int i = 0; i < n; i++) if (e->sus[b][i].slot == a->host) stop_process(e, actor, a->host, e->sus[b][i].pid, 0);
         return SUCC_TRUE;
     }
     case AC_RESTORE:    /* Restore.py:38-68 */
@@ -943,7 +946,9 @@ static int exploit_new_session(cc4o_env *e, int r, int target, int parent_sessio
     int actor = A_RED0 + r;
     int pid = create_pid(e, actor, target);
     add_proc(e, target, pid, K_SHELL, 0);
-    add_session(e, actor, actor, target, 0, 0, pid, K_SHELL, -1);
+    int id = add_session(e, actor, actor, target, 0, 0, pid, K_SHELL, -1);
+    int at = find_sess(e, actor, id);
+    if (at >= 0) e->sess[actor][at].has_parent = 1;     /* parent = the acting session, ExploitAction.py:256 */
     return pid;
 }
 
@@ -1114,9 +1119,71 @@ static int exec_red(cc4o_env *e, int r, const act_t *a)
         obs_entry(e, r, 0, a->host, 0, 0, 0, 0);
         return SUCC_TRUE;
     }
+    case AC_WITHDRAW: {   /* Withdraw.py:38-91 (RandomSelectRedAgent only): every session of the agent on the host goes, children first */
+        if (!S) return SUCC_FALSE;
+        int ids[MAXSESS + 1], n = 0;
+        for (int i = 0; i < e->nsess[actor]; i++) if (e->sess[actor][i].host == a->host && e->sess[actor][i].has_parent) ids[n++] = e->sess[actor][i].id;
+        for (int i = 0; i < e->nsess[actor]; i++) if (e->sess[actor][i].host == a->host && !e->sess[actor][i].has_parent && e->sess[actor][i].id != 0) ids[n++] = e->sess[actor][i].id;
+        if (S->host == a->host) ids[n++] = a->session;     /* the acting session last (a second time when its ident is not 0) */
+        if (n == 0) return SUCC_FALSE;
+        for (int k = 0; k < n; k++) {
+            /* StopProcess(stop_all=True): TargetedLocalAction.py:14-21 needs the acting and the target session, StopProcess.py:23-33 the process */
+            int ti = find_sess(e, actor, ids[k]);
+            if (find_sess(e, actor, a->session) < 0 || ti < 0) return SUCC_FALSE;
+            if (!stop_process(e, actor, a->host, e->sess[actor][ti].pid, 1)) return SUCC_FALSE;
+        }
+        return SUCC_TRUE;
+    }
     case AC_INVALID: return SUCC_FALSE;
     default: return SUCC_UNKNOWN;
     }
+}
+
+/* RandomSelectRedAgent.get_action RandomSelectRedAgent.py:37-92: a uniformly drawn valid command, then one uniform draw per
+   parameter that has more than one known option (options in action-space dict order: subnets and hosts in creation order,
+   sessions in the order they became known) */
+static int nth_known_host(cc4o_env *e, const uint8_t *known, int k)
+{
+    for (int oi = 0; oi < e->norder; oi++) { int s = e->order[oi]; if (known[s] && k-- == 0) return s; }
+    return -1;
+}
+static act_t red_policy_random(cc4o_env *e, int r)
+{
+    int actor = A_RED0 + r;
+    act_t a = { AC_SLEEP, -1, -1, 0 };
+    int nss = e->n_ss[r], nsub = 0, nip = 0, nhn = 0;
+    for (int s = 0; s < NSUB; s++) nsub += e->sn_known[r] >> s & 1;
+    for (int s = 0; s < NSLOT; s++) { nip += e->ip_known[r][s]; nhn += e->hn_known[r][s]; }
+    /* action_space['action'] order = red_actions, EnterpriseScenarioGenerator.py:764-768; a command is valid when every parameter has an option */
+    static const int cmds[10] = { AC_DRS, AC_AGGR, AC_STEALTH, AC_EXPLOIT, AC_PRIVESC, AC_DEGRADE, AC_DD, AC_IMPACT, AC_WITHDRAW, AC_SLEEP };
+    int list[10], n = 0;
+    for (int i = 0; i < 10; i++) {
+        int c = cmds[i], ok;
+        if (c == AC_SLEEP) ok = 1;
+        else if (c == AC_DRS) ok = nss && nsub;
+        else if (c == AC_PRIVESC || c == AC_DEGRADE || c == AC_IMPACT) ok = nss && nhn;
+        else if (c == AC_WITHDRAW) ok = nss && nip && nhn;
+        else ok = nss && nip;
+        if (ok) list[n++] = c;
+    }
+    a.code = list[rng_int(e, actor, ST_RS_COMMAND, (uint32_t)n)];
+    #define RS_PICK(cnt) ((cnt) > 1 ? (int)rng_int(e, actor, ST_RS_PARAM, (uint32_t)(cnt)) : 0)
+    #define RS_SESSION() (a.session = e->ss[r][RS_PICK(nss)])
+    #define RS_IP() nth_known_host(e, e->ip_known[r], RS_PICK(nip))
+    #define RS_HOSTNAME() nth_known_host(e, e->hn_known[r], RS_PICK(nhn))
+    switch (a.code) {   /* parameters in constructor-signature order */
+    case AC_DRS: { int k = RS_PICK(nsub); for (int s = 0; s < NSUB; s++) if ((e->sn_known[r] >> s & 1) && k-- == 0) { a.subnet = s; break; } RS_SESSION(); break; }
+    case AC_AGGR: case AC_STEALTH: case AC_DD: RS_SESSION(); a.host = RS_IP(); break;
+    case AC_EXPLOIT: a.host = RS_IP(); RS_SESSION(); break;
+    case AC_PRIVESC: case AC_DEGRADE: case AC_IMPACT: a.host = RS_HOSTNAME(); RS_SESSION(); break;
+    case AC_WITHDRAW: RS_SESSION(); (void)RS_IP(); a.host = RS_HOSTNAME(); break;      /* ip_address only routes the RemoteAction */
+    default: break;
+    }
+    #undef RS_PICK
+    #undef RS_SESSION
+    #undef RS_IP
+    #undef RS_HOSTNAME
+    return a;
 }
 
 /* RedSessionCheck.execute RedSessionCheck.py:9-63 */
@@ -1131,8 +1198,9 @@ static void red_session_check(cc4o_env *e, int r)
         int i = (int)rng_int(e, actor, ST_RSC_PRIMARY, (uint32_t)e->nsess[actor]);
         sess_t s = e->sess[actor][i];
         del_sess(e, actor, i);
-        s.id = 0;
+        s.id = 0; s.has_parent = 0;
         e->sess[actor][e->nsess[actor]++] = s;
+        for (int k = 0; k < e->nsess[actor]; k++) e->sess[actor][k].has_parent = 0;     /* parent = new primary's name = None, :50-54 */
     }
     for (int i = 0; i < e->nsess[actor]; i++) {
         sess_t *s = &e->sess[actor][i];
@@ -1229,7 +1297,7 @@ int cc4o_step(cc4o_env *e, const int32_t *actions, const uint8_t *msgs, uint8_t 
     }
     for (int r = 0; r < NRED; r++) {
         act_t x = { AC_SLEEP, -1, -1, 0 };
-        if (e->active[A_RED0 + r]) x = red_policy(e, r);
+        if (e->active[A_RED0 + r]) x = e->red_variant == 2 ? red_policy_random(e, r) : red_policy(e, r);
         sub[A_RED0 + r] = x;
     }
     /* clear old observations :251 */
@@ -1336,7 +1404,7 @@ int cc4o_export(cc4o_env *e, int32_t *out, int cap)
                tick, FiniteStateRedAgent.py:91-93); inactive agents are not asked (AgentInterface.py:133-136) */
             static fsm_t sv[MAXFSM]; int sn_ = e->n_fsm[r], serr = e->err; char smsg[256];
             memcpy(sv, e->fsm[r], sizeof sv); memcpy(smsg, e->errmsg, sizeof smsg);
-            if (e->active[a]) { fsm_transition(e, r); fsm_process_obs(e, r); fsm_session_removal(e, r); }
+            if (e->active[a] && e->red_variant != 2) { fsm_transition(e, r); fsm_process_obs(e, r); fsm_session_removal(e, r); }
             PUT(e->n_fsm[r]); for (int i = 0; i < e->n_fsm[r]; i++) { PUT(e->fsm[r][i].slot); PUT(e->fsm[r][i].state); PUT(e->fsm[r][i].hn); }
             memcpy(e->fsm[r], sv, sizeof sv); e->n_fsm[r] = sn_; e->err = serr; memcpy(e->errmsg, smsg, sizeof smsg);
         }
@@ -1362,7 +1430,7 @@ int cc4o_export(cc4o_env *e, int32_t *out, int cap)
 /* ------------------------------------------------------------------------------------------------ */
 /* life cycle                                                                                       */
 /* ------------------------------------------------------------------------------------------------ */
-void cc4o_set_red_agent(cc4o_env *e, int variant) { e->red_variant = variant ? 1 : 0; }
+void cc4o_set_red_agent(cc4o_env *e, int variant) { e->red_variant = variant == 2 ? 2 : variant ? 1 : 0; }
 
 cc4o_env *cc4o_create(uint64_t seed, uint64_t episode_id, int steps, int rng_mode)
 {

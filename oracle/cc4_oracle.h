@@ -33,7 +33,9 @@ enum {
     ST_DD_FP = 29, ST_RSC_PRIMARY = 30, ST_DECOY_FACTORY = 31,
     /* DiscoveryFSRed only (FiniteStateRedAgent._choose_host :252-293) */
     ST_FSMD_STATE_P = 32, ST_FSMD_STATE_U = 33, ST_FSMD_ROLL = 34, ST_FSMD_HOST_SRV = 35, ST_FSMD_HOST_OTHER = 36,
-    ST_FSMD_HOST_SRV2 = 37, ST_FSMD_HOST_ALL = 38
+    ST_FSMD_HOST_SRV2 = 37, ST_FSMD_HOST_ALL = 38,
+    /* RandomSelectRedAgent only (RandomSelectRedAgent.get_action :37-92) */
+    ST_RS_COMMAND = 39, ST_RS_PARAM = 40
 };
 
 /* One recorded draw. kind 0: integer in [0,n) stored in val; kind 1: double in [0,1), IEEE bits in val. */
@@ -63,7 +65,8 @@ typedef struct cc4o_env cc4o_env;
 
 /* rng_mode 0 = Philox4x32-10 keyed (seed, episode_id); 1 = tape replay */
 cc4o_env *cc4o_create(uint64_t seed, uint64_t episode_id, int steps, int rng_mode);
-/* scripted red agent class: 0 = FiniteStateRedAgent (default), 1 = DiscoveryFSRed (FSMRedVariants.py:72-122); before cc4o_reset */
+/* scripted red agent class: 0 = FiniteStateRedAgent (default), 1 = DiscoveryFSRed (FSMRedVariants.py:72-122),
+ * 2 = RandomSelectRedAgent (RandomSelectRedAgent.py:8-139, the agent that uses Withdraw); before cc4o_reset */
 void cc4o_set_red_agent(cc4o_env *e, int variant);
 void cc4o_destroy(cc4o_env *e);
 /* tape: recs[] plus seg_off[n_segs + 1]; segment 0 = reset, 1 + t*CC4O_N_ACTORS + actor = tick t.

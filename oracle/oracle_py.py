@@ -70,9 +70,9 @@ class OracleEnv:
     def __init__(self, seed=0, episode=0, steps=500, tape=None, red="fsm"):
         self.L = lib()
         self.h = self.L.cc4o_create(seed, episode, steps, 1 if tape is not None else 0)
-        if red != "fsm":        # DiscoveryFSRed (FSMRedVariants.py:72-122)
+        if red != "fsm":        # DiscoveryFSRed (FSMRedVariants.py:72-122) / RandomSelectRedAgent (RandomSelectRedAgent.py:8-139)
             self.L.cc4o_set_red_agent.argtypes = [C.c_void_p, C.c_int]
-            self.L.cc4o_set_red_agent(self.h, 1)
+            self.L.cc4o_set_red_agent(self.h, {"discovery": 1, "random_select": 2}[red])
         self._tape = tape
         if tape is not None:
             recs, seg_off = tape

@@ -93,6 +93,9 @@ SITE = {
     ("FiniteStateRedAgent.py", 285): 36,             # FSMD_HOST_OTHER
     ("FiniteStateRedAgent.py", 287): 37,             # FSMD_HOST_SRV2 (only servers to pick from)
     ("FiniteStateRedAgent.py", 289): 38,             # FSMD_HOST_ALL  (no server among the options)
+    # --- RandomSelectRedAgent only (RandomSelectRedAgent.get_action :37-92)
+    ("RandomSelectRedAgent.py", 68): 39,             # RS_COMMAND     integers(0, len(list_commands))
+    ("RandomSelectRedAgent.py", 81): 40,             # RS_PARAM       integers(0, len(param_opts)), only drawn for > 1 option
     # --- red actions
     ("Portscan.py", 49): 21,                         # PORTSCAN
     ("ExploitRemoteService.py", 61): 22,             # EXP_OTHER
@@ -372,6 +375,8 @@ class RefEpisode:
         from CybORG.Agents import SleepAgent, EnterpriseGreenAgent, FiniteStateRedAgent
         if red == "discovery":      # CybORG/Agents/SimpleAgents/FSMRedVariants.py:72-122
             from CybORG.Agents.SimpleAgents.FSMRedVariants import DiscoveryFSRed as FiniteStateRedAgent
+        if red == "random_select":  # CybORG/Agents/SimpleAgents/RandomSelectRedAgent.py:8-139 (the only agent that uses Withdraw)
+            from CybORG.Agents.SimpleAgents.RandomSelectRedAgent import RandomSelectRedAgent as FiniteStateRedAgent
         from CybORG.Agents.Wrappers import BlueFlatWrapper
         from CybORG.Simulator.Scenarios import EnterpriseScenarioGenerator
 
@@ -665,7 +670,7 @@ if __name__ == "__main__":
     if args.dictobs or args.padded:
         sys.exit(0)
     for spec in args.spec:
-        seed, policy, steps, *rest = spec.split(":")      # seed:policy:steps[:red[:episode]]  (red = fsm | discovery; episode => Philox seam)
+        seed, policy, steps, *rest = spec.split(":")      # seed:policy:steps[:red[:episode]]  (red = fsm | discovery | random_select; episode => Philox seam)
         red = rest[0] if rest else "fsm"
         t0 = time.time()
         if len(rest) > 1:       # production-mode fixture: the reference driven by the engine's Philox streams of (seed, episode)

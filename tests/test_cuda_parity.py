@@ -420,3 +420,30 @@ def test_discovery_red_agent_philox_mode_matches_oracle():
     for i in range(0, n, 7):
         assert np.array_equal(env.export_canon(i), refs[i].export()), f"episode {i}: {_diff(refs[i].export(), env.export_canon(i))}"
     assert not env.error_flags().any()
+
+
+def test_random_select_red_agent_philox_mode_matches_oracle():
+    """RandomSelectRedAgent + Withdraw (RandomSelectRedAgent.py:37-92, Withdraw.py:38-91) in production mode: CUDA engine ==
+    oracle on a seeded batch over a whole episode, state compared at checkpoints (the tape and Philox-seam fixtures of this agent
+    are replayed by the parametrised tests above)."""
+    n, ticks, seed = 64, 499, 41
+    env = _engine(n, device=0, seed=seed, steps=500, red_agent="random_select")
+    env.reset()
+    refs = [O.OracleEnv(seed=seed, episode=i, steps=500, red="random_select") for i in range(n)]
+    for r in refs:
+        r.reset()
+    g = np.random.default_rng(seed)
+    for t in range(ticks):
+        acts = np.stack([g.integers(0, k, n) for k in (82, 82, 82, 82, 242)], 1).astype(np.int32)
+        if t % 3:
+            acts[:] = (49, 49, 49, 49, 145)          # let red keep most of what it takes, so that it has sessions to withdraw
+        o, r, d = env.step(torch.from_numpy(acts).cuda())
+        o, r, d = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
+        for i, ref in enumerate(refs):
+            rc, oo, rr, dd = ref.step(acts[i])
+            assert np.array_equal(o[i], oo) and r[i] == rr and d[i] == dd, f"episode {i} tick {t}"
+        if t % 50 == 0 or t == ticks - 1:
+            for i in range(0, n, 5):
+                assert np.array_equal(env.export_canon(i), refs[i].export()), f"episode {i} tick {t}: {_diff(refs[i].export(), env.export_canon(i))}"
+    flags = env.error_flags()
+    assert np.array_equal(flags & ~np.uint32(4), np.array([r.error()[0] for r in refs]) & ~4)

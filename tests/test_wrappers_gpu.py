@@ -145,6 +145,13 @@ def test_episode_ends_and_agents_list_empties():
     assert env.agents == []
     with pytest.raises(NotImplementedError):
         EnterpriseScenarioGenerator(red_agent_class=SleepAgent)
+    from cage_challenge_4_b200.wrappers import DiscoveryFSRed, RandomSelectRedAgent
+    for cls_ in (DiscoveryFSRed, RandomSelectRedAgent):        # the other scripted red agents run through the same facade
+        e2 = BlueFlatWrapper(CybORG(EnterpriseScenarioGenerator(red_agent_class=cls_, steps=30), seed=5))
+        e2.reset()
+        for _ in range(29):
+            _, rew, term, *_ = e2.step({})
+        assert term["blue_agent_0"] is True and e2.env.engine.error_flags()[0] == 0
 
 
 def test_pad_spaces_against_the_reference():
