@@ -1378,6 +1378,42 @@ __device__ __noinline__ void ssh_hops_tape(Cx c, int actor, int src, int target,
     _Pragma("unroll 1") for (int i = 0; i < nh; i++) if (0.05 < rng_f64(c, actor, ST_SSH_HOP, 0)) DYN(c)->ev[route_hop(src, target, nh, i)] |= EV_NET;
 }
 
+/* Withdraw.py:38-91 (RandomSelectRedAgent only) [uniform], out of line so that the FiniteStateRedAgent instruction stream does
+ * not carry it: every session of the agent on the host goes; si / S_host = pool index / host of the acting session */
+__device__ __noinline__ int exec_withdraw(Cx c, int r, int h, int acting, int si, int S_host)
+{
+    Cc4Dyn *s = DYN(c);
+    const int actor = A_RED0 + r, lane = lane_id();
+    if (si < 0) return SUCC_FALSE;
+    /* the sessions to stop, as idents in the scratch: those with a parent first, then the parentless ones except ident 0, both in
+       dict (= pool) order; the acting session last when it sits on the host (a second time when its ident is not 0) */
+    uint8_t *ids = SCR(c)->ra.ident;
+    int n = 0;
+    const int ns = s->n_sess;
+    _Pragma("unroll 1") for (int pass = 0; pass < 2; pass++)
+        _Pragma("unroll 1") for (int base = 0; base < ns; base += 32) {
+            const int i = base + lane;
+            const uint32_t w = i < ns ? s->sess[i] : 0u, f = i < ns ? (uint32_t)s->sessf[i] : 0u;
+            const bool on = i < ns && SF_AGENT(f) == (uint32_t)r && S_HOST(w) == (uint32_t)h;
+            const uint32_t m = __ballot_sync(FULLMASK, on && (pass == 0 ? SF_PARENT(f) != 0u : (!SF_PARENT(f) && S_ID(w) != 0u)));
+            const int at = n + __popc(m & ((1u << lane) - 1u));
+            if ((m >> lane & 1u) && at < 31) ids[at] = (uint8_t)S_ID(w);
+            n += __popc(m);
+        }
+    if (n > 30) { fail(c, CC4_E_CAPACITY); n = 30; }
+    __syncwarp();
+    if (S_host == h) { if (lane == 0) ids[n] = (uint8_t)acting; n++; }
+    __syncwarp();
+    if (n == 0) return SUCC_FALSE;
+    _Pragma("unroll 1") for (int k = 0; k < n; k++) {
+        /* StopProcess(stop_all=True): TargetedLocalAction.py:14-21 needs the acting and the target session, StopProcess.py:23-33 the process */
+        const int ti = sess_find(s, r, ids[k]);
+        if (ti < 0 || sess_find(s, r, acting) < 0) return SUCC_FALSE;
+        if (!stop_process(c, actor, h, S_PID(s->sess[ti]), true)) return SUCC_FALSE;
+    }
+    return SUCC_TRUE;
+}
+
 /* [uniform]: the whole warp executes the action; scans are lane-parallel */
 __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
 {
@@ -1626,37 +1662,7 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
         obs_entry(c, r, 0, h, 0, 0, 0, 0);
         return SUCC_TRUE;
     }
-    case AC_WITHDRAW: {    /* Withdraw.py:38-91 (RandomSelectRedAgent only): every session of the agent on the host goes */
-        if (si < 0) return SUCC_FALSE;
-        const int h = a.host;
-        /* the sessions to stop, as idents in the scratch: those with a parent first, then the parentless ones except ident 0, both in
-           dict (= pool) order; the acting session last when it sits on the host (a second time when its ident is not 0) */
-        uint8_t *ids = SCR(c)->ra.ident;
-        int n = 0;
-        const int ns = s->n_sess;
-        _Pragma("unroll 1") for (int pass = 0; pass < 2; pass++)
-            _Pragma("unroll 1") for (int base = 0; base < ns; base += 32) {
-                const int i = base + lane;
-                const uint32_t w = i < ns ? s->sess[i] : 0u, f = i < ns ? (uint32_t)s->sessf[i] : 0u;
-                const bool on = i < ns && SF_AGENT(f) == (uint32_t)r && S_HOST(w) == (uint32_t)h;
-                const uint32_t m = __ballot_sync(FULLMASK, on && (pass == 0 ? SF_PARENT(f) != 0u : (!SF_PARENT(f) && S_ID(w) != 0u)));
-                const int at = n + __popc(m & ((1u << lane) - 1u));
-                if ((m >> lane & 1u) && at < 31) ids[at] = (uint8_t)S_ID(w);
-                n += __popc(m);
-            }
-        if (n > 30) { fail(c, CC4_E_CAPACITY); n = 30; }
-        __syncwarp();
-        if (S_host == h) { if (lane == 0) ids[n] = (uint8_t)a.session; n++; }
-        __syncwarp();
-        if (n == 0) return SUCC_FALSE;
-        _Pragma("unroll 1") for (int k = 0; k < n; k++) {
-            /* StopProcess(stop_all=True): TargetedLocalAction.py:14-21 needs the acting and the target session, StopProcess.py:23-33 the process */
-            const int ti = sess_find(s, r, ids[k]);
-            if (ti < 0 || sess_find(s, r, a.session) < 0) return SUCC_FALSE;
-            if (!stop_process(c, actor, h, S_PID(s->sess[ti]), true)) return SUCC_FALSE;
-        }
-        return SUCC_TRUE;
-    }
+    case AC_WITHDRAW: return exec_withdraw(c, r, a.host, a.session, si, S_host);
     case AC_INVALID: return SUCC_FALSE;
     default: return SUCC_UNKNOWN;
     }

@@ -1209,6 +1209,190 @@ __global__ void __launch_bounds__(32) k_reset(Params p, uint8_t *obs, uint8_t *m
     w_store(p.dyn + env, &w->dyn);
 }
 
+
+/* ---- reset, production mode: one THREAD per episode ----
+ * Scenario generation is one serial random stream per episode (the reference's draw order, ~1 000 draws with data-dependent
+ * counts), so an episode cannot use more than one lane; k_reset (above, kept for tape replay) therefore runs one warp per
+ * episode with 31 idle lanes, 25 episodes in flight per SM.  In production mode nothing of the generation needs the
+ * per-episode shared-memory context: the Philox stream lives in registers, the generated lists go straight to their
+ * place in the cold / static records, and what the chain itself reads back (the bitmap of used pids, the largest pid and the
+ * process count of every host) is 1.5 KB of shared memory per lane.  So a block of 128 threads generates 128 episodes side
+ * by side (lanes diverge only in loop trip counts), the hot records are zero-filled by the whole block with coalesced
+ * stores first, and the observation rows and masks are written afterwards by k_reset_outputs (warp per episode, coalesced).
+ * Same words, same order, same results as k_reset (tests: production-mode parity with the oracle and the Philox-seam
+ * fixtures of the live reference compare the state after reset). */
+struct ResetLane {
+    uint32_t used[288];          /* bitmap over pids 1000..9999 (EnterpriseScenarioGenerator._generate_pid :563-578) */
+    uint16_t pmax[128];          /* largest pid on the host so far (Host.create_pid Host.py:198-200) */
+    uint8_t np[128];             /* processes on the host so far */
+    uint16_t router_pid[16];
+    uint32_t pad;                /* stride = 393 words: lanes hit different banks at equal offsets */
+};
+static_assert(sizeof(ResetLane) == 393 * 4, "ResetLane stride");
+constexpr int RESET_FAST_THREADS = 128;
+
+__global__ void __launch_bounds__(RESET_FAST_THREADS) k_reset_fast(Params p)
+{
+    ResetLane *t = reinterpret_cast<ResetLane *>(smem_raw) + threadIdx.x;
+    const int first = (int)blockIdx.x * RESET_FAST_THREADS, env = first + (int)threadIdx.x;
+    {   /* the block's hot records start from zero: coalesced 128-bit stores */
+        uint4 *d4 = reinterpret_cast<uint4 *>(p.dyn + first);
+        const int n4 = min(RESET_FAST_THREADS, p.n_envs - first) * DYN_U4;
+        _Pragma("unroll 4") for (int i = (int)threadIdx.x; i < n4; i += RESET_FAST_THREADS) d4[i] = make_uint4(0, 0, 0, 0);
+        uint32_t *z = reinterpret_cast<uint32_t *>(t);
+        _Pragma("unroll 1") for (int i = 0; i < (int)(sizeof(ResetLane) / 4); i++) z[i] = 0;
+    }
+    __syncthreads();
+    if (env >= p.n_envs) return;
+    Cc4Dyn *s = p.dyn + env; Cc4Stat *st = p.stat + env; Cc4Cold *k = p.cold + env;
+    /* the reset stream of the episode (cc4_device.cuh philox_block with actor NAG, tick -1): registers only */
+    const uint64_t ep = p.first_episode + (uint64_t)env;
+    const uint32_t k1 = p.k1hi ^ (uint32_t)(ep >> 32), ep_lo = (uint32_t)ep;
+    uint32_t j = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    auto ri = [&](uint32_t n) -> uint32_t {
+        if ((j & 3u) == 0u) { uint32_t o[4] = { j >> 2, (uint32_t)NAG, 0u, ep_lo }; philox4x32_10(o, p.k0, k1); b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3]; }
+        const uint32_t w = (j & 3u) == 0u ? b0 : (j & 3u) == 1u ? b1 : (j & 3u) == 2u ? b2 : b3;
+        j++;
+        return __umulhi(w, n);
+    };
+    uint32_t err = 0;
+    auto gen_pid = [&]() -> uint32_t {
+        _Pragma("unroll 1") for (int guard = 0; guard < 64; guard++) {
+            const uint32_t v = ri(9000);
+            if (!(t->used[v >> 5] >> (v & 31) & 1u)) { t->used[v >> 5] |= 1u << (v & 31); return 1000u + v; }
+        }
+        err |= CC4_E_CAPACITY;
+        return 1000u;
+    };
+    uint64_t nu64 = 0, ns64 = 0;        /* users / servers per subnet, one byte each (registers, no local arrays) */
+    #define NUSER(sn_) ((int)(nu64 >> (8 * (sn_)) & 0xFFu))
+    #define NSERVER(sn_) ((int)(ns64 >> (8 * (sn_)) & 0xFFu))
+    auto gen_host = [&](int slot) {     /* _generate_linux_host_services :530-561 + _generate_linux_host_processes :580-629 */
+        const int sn = slot >> 4;
+        int n = 0;
+        uint64_t v = SVC_EMPTY;
+        uint32_t mx = 0;
+        auto add = [&](uint32_t kind, uint32_t pid) {
+            v = svc_set(v, n, kind | 5u << 4);
+            const uint32_t pw = P_MAKE(pid, kind, 0, 1);
+            k->parena[slot * CC4_OSLAB + n] = pw; st->o_procs[slot][n] = pw;
+            if (pid > mx) mx = pid;
+            n++;
+        };
+        add(K_SSHD, gen_pid());
+        if (sn == S_OZA || sn == S_OZB) add(K_OT, gen_pid());
+        uint32_t okind = K_APACHE2 | K_MYSQLD << 4 | K_SMTP << 8;
+        uint64_t opid = 0;
+        _Pragma("unroll 1") for (int i = 0; i < 3; i++) opid |= (uint64_t)gen_pid() << (16 * i);
+        int nopt = 3;
+        const int nadd = (int)ri(4);
+        _Pragma("unroll 1") for (int i = 0; i < nadd; i++) {
+            const int q = (int)ri((uint32_t)nopt);
+            add(okind >> (4 * q) & 15u, (uint32_t)(opid >> (16 * q)) & 0xFFFFu);
+            okind = (okind & ((1u << (4 * q)) - 1u)) | (okind >> (4 * (q + 1))) << (4 * q);         /* list.pop(q) */
+            opid = (opid & ((1ull << (16 * q)) - 1ull)) | (opid >> (16 * (q + 1))) << (16 * q);
+            nopt--;
+        }
+        t->np[slot] = (uint8_t)n; t->pmax[slot] = (uint16_t)mx;
+        k->svc64[slot] = v; st->o_svc64[slot] = v;
+    };
+    /* hosts, EnterpriseScenarioGenerator._generate_hosts :312-371 */
+    _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) {
+        nu64 |= (uint64_t)(3 + ri(8)) << (8 * sn);
+        _Pragma("unroll 1") for (int i = 0; i < NUSER(sn); i++) gen_host(sn * 16 + 6 + i);
+        ns64 |= (uint64_t)(1 + ri(6)) << (8 * sn);
+        _Pragma("unroll 1") for (int i = 0; i < NSERVER(sn); i++) gen_host(sn * 16 + i);
+        _Pragma("unroll 1") for (int q = 0; q < 16; q++) {       /* the slots without a host */
+            const bool exists = q < 6 ? q < NSERVER(sn) : (q - 6) < NUSER(sn);
+            if (!exists) { k->svc64[sn * 16 + q] = SVC_EMPTY; st->o_svc64[sn * 16 + q] = SVC_EMPTY; }
+        }
+    }
+    /* blue agents :631-698 */
+    uint64_t bp64 = 0, rs64 = 0;        /* blue parent hosts / red start hosts, one byte each */
+    #define BLUE_PARENT(b_) ((int)(bp64 >> (8 * (b_)) & 0xFFu))
+    #define RED_START(r_) ((int)(rs64 >> (8 * (r_)) & 0xFFu))
+    _Pragma("unroll 1") for (int b = 0; b < CC4_NBLUE; b++) {
+        int n = 0;
+        _Pragma("unroll 1") for (int i = 0; i < (b == 4 ? 3 : 1); i++) { const int sn = b < 4 ? b : S_PAZ + i; n += 1 + NUSER(sn) + NSERVER(sn); }
+        const int pk = (int)ri((uint32_t)n);
+        int parent = -1;
+        _Pragma("unroll 1") for (int i = 0, q = 0; i < (b == 4 ? 3 : 1) && parent < 0; i++) {
+            const int sn = b < 4 ? b : S_PAZ + i, nu = NUSER(sn), m = 1 + nu + NSERVER(sn);
+            if (pk < q + m) { const int jj = pk - q; parent = jj == 0 ? CC4_SLOT_ROUTER + sn : jj <= nu ? sn * 16 + 6 + (jj - 1) : sn * 16 + (jj - 1 - nu); }
+            q += m;
+        }
+        bp64 |= (uint64_t)(uint8_t)parent << (8 * b);
+    }
+    /* green agents :700-749 */
+    int ng = 0;
+    uint64_t cum = 0;
+    _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) { ng += NUSER(sn); cum |= (uint64_t)ng << (8 * sn); }
+    /* red agents :751-812 */
+    _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) {
+        const int si = (int)ri(r == 5 ? 3u : 1u);
+        const int sn = r == 0 ? S_CON : r <= 4 ? r - 1 : S_PAZ + si;
+        const int q = (int)ri((uint32_t)(NUSER(sn) + NSERVER(sn)));
+        rs64 |= (uint64_t)(uint8_t)(q < NUSER(sn) ? sn * 16 + 6 + q : sn * 16 + (q - NUSER(sn))) << (8 * r);
+    }
+    /* State.__init__ State.py:108-134: session processes (Host.add_session Host.py:189-196) */
+    auto add_session_proc = [&](int slot, uint32_t kind) -> uint32_t {
+        if (slot >= CC4_SLOT_ROUTER) { const uint32_t pid = 1u + ri(9); t->router_pid[slot - CC4_SLOT_ROUTER] = (uint16_t)pid; return pid; }
+        const uint32_t pid = (uint32_t)t->pmax[slot] + 1u + ri(9);
+        const int n = t->np[slot];
+        const uint32_t pw = P_MAKE(pid, kind, 0, 0);
+        k->parena[slot * CC4_OSLAB + n] = pw; st->o_procs[slot][n] = pw;
+        t->np[slot] = (uint8_t)(n + 1); t->pmax[slot] = (uint16_t)pid;
+        return pid;
+    };
+    _Pragma("unroll 1") for (int b = 0; b < CC4_NBLUE; b++) {
+        add_session_proc(BLUE_PARENT(b), K_SESSION);
+        _Pragma("unroll 1") for (int i = 0; i < (b == 4 ? 3 : 1); i++) {
+            const int sn = b < 4 ? b : S_PAZ + i;
+            if (BLUE_PARENT(b) != CC4_SLOT_ROUTER + sn) add_session_proc(CC4_SLOT_ROUTER + sn, K_SESSION);
+            _Pragma("unroll 1") for (int q = 0; q < NUSER(sn); q++) if (BLUE_PARENT(b) != sn * 16 + 6 + q) add_session_proc(sn * 16 + 6 + q, K_SESSION);
+            _Pragma("unroll 1") for (int q = 0; q < NSERVER(sn); q++) if (BLUE_PARENT(b) != sn * 16 + q) add_session_proc(sn * 16 + q, K_SESSION);
+        }
+    }
+    _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++)         /* one green agent per user host, creation order */
+        _Pragma("unroll 1") for (int q = 0; q < NUSER(sn); q++) add_session_proc(sn * 16 + 6 + q, K_SESSION);
+    const int h0 = RED_START(0);
+    const uint32_t pid0 = add_session_proc(h0, K_REDABS);
+    /* ---- the records ---- */
+    _Pragma("unroll 1") for (int h = 0; h < 128; h++) {
+        const int n = t->np[h];
+        k->pdir[h] = PD_MAKE(h * CC4_OSLAB, n, 3); k->pmax[h] = t->pmax[h]; st->o_nproc[h] = (uint8_t)n;
+    }
+    k->arena_top = 128 * CC4_OSLAB;
+    _Pragma("unroll 1") for (int i = 0; i < 16; i++) st->router_pid[i] = t->router_pid[i];
+    _Pragma("unroll 1") for (int b = 0; b < CC4_NBLUE; b++) st->blue_parent[b] = (uint8_t)BLUE_PARENT(b);
+    _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) st->red_start[r] = (uint8_t)RED_START(r);
+    _Pragma("unroll 1") for (int a = 0; a < 16; a++) s->inprog[a] = IP_NONE;
+    _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) { s->nuser[sn] = (uint8_t)NUSER(sn); s->nserver[sn] = (uint8_t)NSERVER(sn); }
+    s->green_cum = cum; s->ngreen = (uint8_t)ng;
+    s->sess[0] = S_MAKE(pid0, 0, h0); s->sessf[0] = (uint8_t)(0 | 1 << 3); s->n_sess = 1; s->sess_count[0] = 1; s->red_active = 1;
+    /* initial knowledge: AgentInterface.set_init_obs AgentInterface.py:110-117 with the OSINT of :784-785 */
+    _Pragma("unroll 1") for (int r = 0; r < CC4_NRED; r++) { const int h = RED_START(r); set128(s->ip_known[r], h); set128(s->hn_known[r], h); s->sn_known[r] = (uint16_t)(1u << (h >> 4)); }
+    s->ss[0][0] = 0; s->n_ss[0] = 1;
+    /* red_agent_0 digests its initial observation (its start host becomes 'U', FiniteStateRedAgent.py:221-224) */
+    s->fsm_order[0][0] = (uint8_t)h0; s->n_fsm[0] = 1; s->fsm_started = 1;
+    set128(s->fsm[0].present, h0); set128(s->fsm[0].hn, h0); set128(s->fsm[0].pl[2], h0);
+    s->err = err;
+    #undef NUSER
+    #undef NSERVER
+    #undef BLUE_PARENT
+    #undef RED_START
+}
+
+/* observation rows and action masks of freshly reset episodes: warp per episode, the record comes back through shared memory */
+__global__ void __launch_bounds__(32) k_reset_outputs(Params p, uint8_t *obs, uint8_t *mask)
+{
+    WarpSmem *w = reinterpret_cast<WarpSmem *>(smem_raw);
+    const int env = blockIdx.x;
+    w_load(&w->dyn, p.dyn + env);
+    if (obs) w_write_obs(&w->dyn, &w->x, obs, env);
+    if (mask) w_write_mask(&w->dyn, mask + (size_t)env * CC4_N_BLUE * CC4_MASK_LEN);
+}
+
 }  // namespace cc4
 
 /* ================================================================================================ */
@@ -1433,6 +1617,7 @@ struct cc4_handle {
     int sweep, alternate;                                 /* direction of the last cc4_step over the batch; CC4_SWEEP_ALTERNATE=0 keeps one direction */
     int host_expand;                                      /* 0: byte rows over PCIe (CC4_HOST_EXPAND=0) */
     int host_chunk;                                       /* episodes per chunk of cc4_step_host, 0 = one wave of blocks (CC4_HOST_CHUNK_EPISODES) */
+    int reset_serial;                                     /* CC4_RESET_SERIAL=1: k_reset (warp per episode) also in production mode */
 };
 
 extern "C" const char *cc4_last_error(void) { return g_err; }
@@ -1459,6 +1644,9 @@ extern "C" int cc4_create(int n_envs, int device, uint64_t seed, uint64_t first_
     CUDA_TRY(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * EPB_MAX)));
     CUDA_TRY(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * EPB_MAX)));
     CUDA_TRY(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResetSmem)));
+    CUDA_TRY(cudaFuncSetAttribute(k_reset_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ResetLane) * RESET_FAST_THREADS)));
+    CUDA_TRY(cudaFuncSetAttribute(k_reset_outputs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem)));
+    { const char *e = getenv("CC4_RESET_SERIAL"); h->reset_serial = e && e[0] == '1'; }      /* diagnostics: the warp-per-episode reset in production mode too */
     *out = h;
     return CC4_OK;
 }
@@ -1514,7 +1702,12 @@ extern "C" int cc4_reset(cc4_handle *h, uint8_t *obs_dev, uint8_t *mask_dev, voi
     if (h->p.rng_mode == 1 && !h->p.tape) return set_err(CC4_ERR_STATE, "cc4_reset: tape mode without cc4_set_tape%s", "");
     if ((uintptr_t)obs_dev & 15u) return set_err(CC4_ERR_ARG, "cc4_reset: obs_dev must be 16-byte aligned%s", "");
     CUDA_TRY(cudaSetDevice(h->device));
-    k_reset<<<h->p.n_envs, 32, sizeof(ResetSmem), (cudaStream_t)stream>>>(h->p, obs_dev, mask_dev);
+    if (h->p.rng_mode == 1 || h->reset_serial) {
+        k_reset<<<h->p.n_envs, 32, sizeof(ResetSmem), (cudaStream_t)stream>>>(h->p, obs_dev, mask_dev);
+    } else {        /* production mode: thread per episode, then the observation rows / masks (see k_reset_fast) */
+        k_reset_fast<<<(h->p.n_envs + RESET_FAST_THREADS - 1) / RESET_FAST_THREADS, RESET_FAST_THREADS, sizeof(ResetLane) * RESET_FAST_THREADS, (cudaStream_t)stream>>>(h->p);
+        if (obs_dev || mask_dev) { k_reset_outputs<<<h->p.n_envs, 32, sizeof(WarpSmem), (cudaStream_t)stream>>>(h->p, obs_dev, mask_dev); h->launches++; }
+    }
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return CC4_OK;

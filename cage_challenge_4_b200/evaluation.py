@@ -83,6 +83,8 @@ def run_evaluation(submission, log_path: str | None = None, max_eps: int = 100, 
 class MLPPolicy(torch.nn.Module):
     """BASELINE config 5: one random-init MLP per blue agent (obs -> 256 -> 256 -> n_actions), masked argmax."""
 
+    cuda_graph_capturable = True        # static shapes, no host round trip, no private generator: run_evaluation_batched may graph it
+
     def __init__(self, hidden: int = 256, seed: int = 0):
         super().__init__()
         g = torch.Generator().manual_seed(seed)
@@ -162,13 +164,15 @@ def aggregate_scores(local_totals: torch.Tensor, n_total: int, rank: int, world:
 
 
 def run_evaluation_batched(policy, max_eps: int = 100, seed: int = 0, device: int = 0, rank: int = 0, world: int = 1,
-                           steps: int = EPISODE_LENGTH, graph: bool = True, return_actions: bool = False) -> dict:
+                           steps: int = EPISODE_LENGTH, graph: bool | None = None, return_actions: bool = False) -> dict:
     """The protocol with every episode of this rank's shard stepped concurrently; `policy(obs, mask) -> int32 [N,5]`
     runs on device and nothing crosses to the host during the episode: every episode ends on tick steps - 1
     (EnterpriseScenarioGenerator.determine_done :862-871), whose reward the protocol drops (evaluation.py:104-110), so the loop
     is steps - 2 counted ticks plus the final one, with no per-tick `done` read.  graph=True records one tick (policy, step,
-    accumulation) into a CUDA graph and replays it: a 100-episode batch is launch-bound (about twenty small kernels per tick);
-    a policy that cannot be captured (host synchronisation, dynamic shapes) falls back to eager ticks.
+    accumulation) into a CUDA graph and replays it: a 100-episode batch is launch-bound (about twenty small kernels per tick).
+    Only a policy that is safe to capture may be graphed (static shapes, no host synchronisation, no private torch.Generator):
+    the default (graph=None) graphs a policy that says so with a true `cuda_graph_capturable` attribute (MLPPolicy does) and runs
+    every other policy eagerly; a capture that raises falls back to eager ticks.
     return_actions=True adds the submitted actions int32 [ticks, N, 5] (tests replay them through the oracle)."""
     lo, hi = shard(max_eps, rank, world)
     n = hi - lo
@@ -190,6 +194,8 @@ def run_evaluation_batched(policy, max_eps: int = 100, seed: int = 0, device: in
                 totals.add_(env.reward)
 
         g = None
+        if graph is None:
+            graph = bool(getattr(policy, "cuda_graph_capturable", False))
         if graph and counted > 2 and log is None:
             tick(True)                        # warm-up outside the capture (lazy allocations, cuBLAS handles); it is tick 0
             done_ticks = 1

@@ -91,3 +91,23 @@ def test_unpack_bits_matches_the_host_expansion():
     assert L.cc4_expand_obs_bits(rows.ctypes.data, want.ctypes.data, n, 1) == 0
     got = unpack_bits(torch.from_numpy(rows.view(np.int32)))
     assert np.array_equal(got.numpy(), want)
+
+
+def test_compat_package_resolves_the_reference_import_paths():
+    """compat/CybORG: `from CybORG import CybORG`, `CybORG.Agents...`, `CybORG.Simulator.Scenarios...` (the imports of the
+    reference's Evaluation/evaluation.py:5-7 and example_submission/submission.py:1-5) resolve to the mirrored API."""
+    import subprocess
+    import sys
+    code = ("from CybORG import CybORG, CYBORG_VERSION\n"
+            "from CybORG.Agents import SleepAgent, EnterpriseGreenAgent, FiniteStateRedAgent, BaseAgent, RandomSelectRedAgent, DiscoveryFSRed, cc4BlueRandomAgent\n"
+            "from CybORG.Agents.Wrappers import BlueFixedActionWrapper, BlueFlatWrapper, BlueEnterpriseWrapper, EnterpriseMAE\n"
+            "from CybORG.Agents.Wrappers.EnterpriseMAE import EnterpriseMAE as E2\n"
+            "from CybORG.Simulator.Scenarios import EnterpriseScenarioGenerator\n"
+            "from CybORG.Shared.Enums import TernaryEnum\n"
+            "import cage_challenge_4_b200.wrappers as w\n"
+            "assert CybORG is w.CybORG and E2 is w.EnterpriseMAE and EnterpriseScenarioGenerator is w.EnterpriseScenarioGenerator\n"
+            "sg = EnterpriseScenarioGenerator(blue_agent_class=SleepAgent, green_agent_class=EnterpriseGreenAgent, red_agent_class=FiniteStateRedAgent, steps=500)\n"
+            "print('ok', CYBORG_VERSION)\n")
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "compat"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
+    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stderr[-800:]

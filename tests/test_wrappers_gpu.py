@@ -380,3 +380,31 @@ def test_dict_observations_against_the_reference():
                     assert str(got["action"]) == exp["action"], (name, t, b)
                 hosts = {k: sorted(p["PID"] for p in v.get("Processes", []) if "PID" in p) for k, v in got.items() if k not in ("success", "action", "message")}
                 assert hosts == exp["hosts"], (name, t, b, hosts, exp["hosts"])
+
+
+def test_the_reference_evaluation_script_runs_unchanged_on_the_compat_package():
+    """CybORG/Evaluation/evaluation.py of the UNMODIFIED reference (baseline/_ref, present when the build container installed it)
+    with `compat/` first on sys.path: its own run_evaluation + load_submission + example submission drive the B200 engine and
+    write the five log files.  Nothing of the reference's simulator is imported: `CybORG` resolves to compat/CybORG."""
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_eval = os.path.join(root, "baseline", "_ref", "CybORG", "Evaluation")
+    if not os.path.exists(os.path.join(ref_eval, "evaluation.py")):
+        pytest.skip("baseline/_ref is not installed on this box")
+    code = ("import importlib.util, sys\n"
+            f"spec = importlib.util.spec_from_file_location('ref_evaluation', {os.path.join(ref_eval, 'evaluation.py')!r})\n"
+            "m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)\n"
+            "import CybORG; assert 'compat' in CybORG.__file__, CybORG.__file__\n"
+            f"sub = m.load_submission({os.path.join(ref_eval, 'example_submission')!r})\n"
+            "m.run_evaluation(sub, log_path=sys.argv[1], max_eps=2, write_to_file=True, seed=7)\n")
+    # the example submission imports ray's MultiAgentEnv and gym's Space for type annotations: stand-ins from the test infrastructure
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "compat"), os.path.join(root, "oracle", "refshim")]))
+    with tempfile.TemporaryDirectory() as tmp:
+        out = subprocess.run([sys.executable, "-c", code, tmp + "/"], capture_output=True, text=True, env=env, cwd=tmp)
+        assert out.returncode == 0, out.stderr[-1500:]
+        assert "Average reward is:" in out.stdout
+        assert sorted(os.listdir(tmp)) == ["actions.txt", "full.txt", "scores.txt", "summary.json", "summary.txt"]
+        summary = json.load(open(os.path.join(tmp, "summary.json")))
+        assert summary["parameters"] == {"seed": 7, "episode_length": 500, "max_episodes": 2} and summary["reward"]["mean"] < 0
