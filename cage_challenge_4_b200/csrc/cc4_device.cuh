@@ -192,6 +192,10 @@ struct BlockCtx {
 __shared__ BlockCtx g_blk;
 /* tape mode (parity replay of the reference's recorded draws) or production mode (Philox); CC4_WITH_TAPE=0 builds a
    library without the tape paths (experiment: what the mode checks and the tape code cost the production kernel) */
+/* The scripted red agent class is a COMPILE-TIME parameter of the kernels (template <int RV>: 0 FiniteStateRedAgent, 1 DiscoveryFSRed,
+   2 RandomSelectRedAgent; the host picks the instantiation from cc4_set_red_agent).  As a run-time switch the two non-default
+   agents cost the default one 3 % (profiles/r03g_red_variant_hooks.txt: every out-of-line call site inside the policy and red
+   phases changes the register allocation of the whole phase), as a template parameter nothing. */
 #ifndef CC4_WITH_TAPE
 #define CC4_WITH_TAPE 1
 #endif
@@ -655,7 +659,7 @@ __device__ __forceinline__ bool fsm_append(Cx c, int r, int slot, int hn, int st
  * observation (RedSessionCheck._all_red_sessions_observation RedSessionCheck.py:57-63: one hostname-keyed entry with
  * Sessions, Interface+Subnet and System info per session host) is represented by the host mask x->sess_hosts[r] instead
  * of explicit entries; ActionSpace.update (ActionSpace.py:170-212) and the FSM bookkeeping consume the mask. */
-__device__ CC4_INL8 void agent_end_turn(Cx c, int r)
+template <int RV> __device__ CC4_INL8 void agent_end_turn(Cx c, int r)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     Cc4Fsm *f = &s->fsm[r];
@@ -670,7 +674,7 @@ __device__ CC4_INL8 void agent_end_turn(Cx c, int r)
         if (m >> 16) snk |= 1u << (2 * w + 1);
     }
     s->sn_known[r] = (uint16_t)snk;
-    if (g_blk.red_variant == 2) return;       /* RandomSelectRedAgent keeps no host states: the action-space update above is all */
+    if (RV == 2) return;       /* RandomSelectRedAgent keeps no host states: the action-space update above is all */
 
     /* _host_state_transition :124-167 on the action the merged observation reports */
     const int started = (s->fsm_started >> r) & 1;
@@ -740,14 +744,14 @@ __device__ CC4_INL8 void agent_end_turn(Cx c, int r)
 
 /* action class + parameters for the chosen host (FiniteStateRedAgent._choose_host_and_action :296-336 +
  * replace_action_if_invalid SimulationController.py:1068-1112); ri / rf draw an integer / a double */
-template <class RI, class RF> __device__ __forceinline__ uint32_t fsm_choose_action(Cx c, int r, int slot, RI ri, RF rf)
+template <int RV, class RI, class RF> __device__ __forceinline__ uint32_t fsm_choose_action(Cx c, int r, int slot, RI ri, RF rf)
 {
     Cc4Dyn *s = DYN(c);
     const Cc4Fsm *f = &s->fsm[r];
     const int st = fsm_state(f, slot), f_hn = bit128(f->hn, slot);
     /* options in action-space order (c_red_aspace_cols); numpy Generator.choice(p): idx = searchsorted(cumsum(p) / sum, u, side='right') */
     int nc = 0, tot = 0;
-    const int8_t (*prob4)[9] = c_fsm_prob4[g_blk.red_variant];
+    const int8_t (*prob4)[9] = c_fsm_prob4[RV == 1 ? 1 : 0];
     _Pragma("unroll 1") for (int i = 0; i < 9; i++) { int p = prob4[st][c_red_aspace_cols[i]]; if (p >= 0) { tot += p; nc++; } }
     if (tot != 4) fail(c, CC4_E_UNREACHABLE);
     const double u = rf(ST_FSM_ACTION, (uint32_t)nc);
@@ -777,12 +781,12 @@ template <class RI, class RF> __device__ __forceinline__ uint32_t fsm_choose_act
 /* The same choice in production mode, on the words of the agent's first Philox block (`j` = next unused word, advanced):
  * the action draw u = word / 2^32 is compared as an integer (u < cum / 4  <=>  word < cum * 2^30, both sides exact), the
  * table sanity check is left to the tape path, a one-option parameter pick spends no word (as rng_int). */
-__device__ __forceinline__ uint32_t fsm_choose_action_words(Cx c, int r, int slot, const uint4 &blk, uint32_t &j)
+template <int RV> __device__ __forceinline__ uint32_t fsm_choose_action_words(Cx c, int r, int slot, const uint4 &blk, uint32_t &j)
 {
     Cc4Dyn *s = DYN(c);
     const Cc4Fsm *f = &s->fsm[r];
     const int st = fsm_state(f, slot), f_hn = bit128(f->hn, slot);
-    const int8_t (*prob4)[9] = c_fsm_prob4[g_blk.red_variant];
+    const int8_t (*prob4)[9] = c_fsm_prob4[RV == 1 ? 1 : 0];
     const uint32_t wa = u4_word(blk, j++);
     int col = -1, cum = 0, last = -1;
     _Pragma("unroll 1") for (int i = 0; i < 9 && col < 0; i++) {
@@ -874,7 +878,7 @@ __device__ __noinline__ uint32_t red_policy_discovery(Cx c, int r, uint32_t lo, 
         const int pos = kth < cl ? (int)__fns(flo, 0, kth + 1) : 32 + (int)__fns(fhi, 0, kth - cl + 1);
         slot = s->fsm_order[r][pos];
     }
-    return fsm_choose_action(c, r, slot, ri, rf);
+    return fsm_choose_action<1>(c, r, slot, ri, rf);
 }
 
 /* RandomSelectRedAgent.get_action RandomSelectRedAgent.py:37-92 [lane], out of line: a uniformly drawn valid command, then one
@@ -928,11 +932,11 @@ __device__ __noinline__ uint32_t red_policy_random(Cx c, int r)
 }
 
 /* FiniteStateRedAgent.get_action :58-123 for one red agent [lane].  Returns the packed action (ticks = 0). */
-__device__ CC4_INL8 uint32_t red_policy(Cx c, int r)
+template <int RV> __device__ CC4_INL8 uint32_t red_policy(Cx c, int r)
 {
     Cc4Dyn *s = DYN(c);
     int actor = A_RED0 + r;
-    if (g_blk.red_variant == 2) return red_policy_random(c, r);         /* draws every tick, also while an action is in flight */
+    if (RV == 2) return red_policy_random(c, r);         /* draws every tick, also while an action is in flight */
     if (IP_CODE(s->inprog[actor]) != IP_NONE) return ACT_SLEEP_WORD;     /* last observation was IN_PROGRESS :100-102 */
     const Cc4Fsm *f = &s->fsm[r];
     const int nf = s->n_fsm[r];
@@ -940,7 +944,7 @@ __device__ CC4_INL8 uint32_t red_policy(Cx c, int r)
     const uint32_t lo = ~f->posF[0] & (nf >= 32 ? 0xFFFFFFFFu : (1u << nf) - 1u), hi = nf > 32 ? ~f->posF[1] & (nf >= 64 ? 0xFFFFFFFFu : (1u << (nf - 32)) - 1u) : 0u;
     const int nlo = __popc(lo), nk = nlo + __popc(hi);
     if (nk == 0) { fail(c, CC4_E_UNREACHABLE); return ACT_SLEEP_WORD; }
-    if (g_blk.red_variant != 0) return red_policy_discovery(c, r, lo, hi);
+    if (RV == 1) return red_policy_discovery(c, r, lo, hi);
     /* production mode: host pick, action pick and at most two parameter picks fit the four words of the stream's first
        Philox block, which stays in registers; the block is left in the stream cache for the action code that follows */
     const bool tape = CC4_TAPE_ON();
@@ -955,7 +959,7 @@ __device__ CC4_INL8 uint32_t red_policy(Cx c, int r)
     /* FiniteStateRedAgent: uniform over the known hosts in list order */
     const int pick = (int)ri(ST_FSM_HOST, (uint32_t)nk);
     const int pos = pick < nlo ? nth_bit(lo, pick) : 32 + nth_bit(hi, pick - nlo);
-    const uint32_t act = tape ? fsm_choose_action(c, r, s->fsm_order[r][pos], ri, rf) : fsm_choose_action_words(c, r, s->fsm_order[r][pos], blk, j);
+    const uint32_t act = tape ? fsm_choose_action<RV>(c, r, s->fsm_order[r][pos], ri, rf) : fsm_choose_action_words<RV>(c, r, s->fsm_order[r][pos], blk, j);
     if (!tape) {
         Scratch *x = SCR(c);
         ctr_set(x, actor, j);
@@ -1415,7 +1419,7 @@ __device__ __noinline__ int exec_withdraw(Cx c, int r, int h, int acting, int si
 }
 
 /* [uniform]: the whole warp executes the action; scans are lane-parallel */
-__device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
+template <int RV> __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
 {
     Cc4Dyn *s = DYN(c);
     const Act a = unpack_act(aw);
@@ -1662,7 +1666,7 @@ __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
         obs_entry(c, r, 0, h, 0, 0, 0, 0);
         return SUCC_TRUE;
     }
-    case AC_WITHDRAW: return exec_withdraw(c, r, a.host, a.session, si, S_host);
+    case AC_WITHDRAW: if (RV == 2) return exec_withdraw(c, r, a.host, a.session, si, S_host); return SUCC_UNKNOWN;      /* only the RandomSelectRedAgent ever submits it */
     case AC_INVALID: return SUCC_FALSE;
     default: return SUCC_UNKNOWN;
     }

@@ -350,7 +350,7 @@ __device__ __forceinline__ void ph_setup(Cx c)
    the cost classes of the two action phases (each_episode). ---- */
 /*                                          Sl Mo An Rm Rs De Bl Al In  -  DRS Ag St DD Ex Pr Im Dg Wd */
 __constant__ uint8_t c_act_weight[32] = { 0, 2, 0, 4, 6, 4, 1, 1, 0, 0, 5, 3, 3, 3, 6, 4, 3, 3, 4 };
-__device__ __forceinline__ void ph_policy(Cx c, int e, bool exists, bool live, int sl, bool red_part, const int32_t *actions, uint32_t pk0, uint32_t pk1,
+template <int RV> __device__ __forceinline__ void ph_policy(Cx c, int e, bool exists, bool live, int sl, bool red_part, const int32_t *actions, uint32_t pk0, uint32_t pk1,
                                           uint64_t ep, PhaseOrder *ord_blue, PhaseOrder *ord_red)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
@@ -369,7 +369,7 @@ __device__ __forceinline__ void ph_policy(Cx c, int e, bool exists, bool live, i
             aw = blue_decode(s, sl, idx) & ~ACT_VALID;
             if (IP_CODE(aw) == AC_RESTORE) cost = -1;      /* Restore.py:70, charged on submission :310-311 */
         }
-        else if (s->red_active >> sl & 1) aw = red_policy(c, sl);
+        else if (s->red_active >> sl & 1) aw = red_policy<RV>(c, sl);
         uint32_t ip = s->inprog[actor], due = ACT_SLEEP_WORD;
         if (IP_CODE(ip) == IP_NONE) ip = aw | (uint32_t)c_duration[IP_CODE(aw)] << 26;
         int ticks = (int)IP_TICKS(ip) - 1;
@@ -548,7 +548,7 @@ __device__ __forceinline__ void ph_phishing(Cx c)
 }
 /* `agents`: the red agents this call handles (the phase can be cut by agent, CC4_RED_PARTS: the same code runs again on
    the next agents after a block barrier, which halves the heaviest work item of the phase) */
-__device__ __forceinline__ void ph_red(Cx c, bool with_phishing = true, uint32_t agents = 0x3Fu)
+template <int RV> __device__ __forceinline__ void ph_red(Cx c, bool with_phishing = true, uint32_t agents = 0x3Fu)
 {
     Scratch *x = SCR(c);
     if (with_phishing) ph_phishing(c);
@@ -567,10 +567,10 @@ __device__ __forceinline__ void ph_red(Cx c, bool with_phishing = true, uint32_t
             const uint32_t aw = x->subw[A_RED0 + r];
 #ifdef CC4_PHASE_CLOCKS
             const long long ta0 = clock64();
-            const int succ = exec_red(c, r, aw);
+            const int succ = exec_red<RV>(c, r, aw);
             if (lane_id() == 0 && g_action_clk) { atomicAdd(&g_action_clk[2 * IP_CODE(aw)], (unsigned long long)(clock64() - ta0)); atomicAdd(&g_action_clk[2 * IP_CODE(aw) + 1], 1ull); }
 #else
-            const int succ = exec_red(c, r, aw);
+            const int succ = exec_red<RV>(c, r, aw);
 #endif
             obs_push(c, r, succ, true, aw);
         }
@@ -604,12 +604,12 @@ __device__ __forceinline__ void ph_reassign(Cx c)
 
 /* ---- phase 6: RedSessionCheck observation + FSM digest of every active red agent, one lane per agent; a warp takes
    FOUR episodes (8 lanes each) ---- */
-__device__ __forceinline__ void ph_endturn(Cx c, bool live, int sl)
+template <int RV> __device__ __forceinline__ void ph_endturn(Cx c, bool live, int sl)
 {
     if (live && sl < CC4_NRED && (SCR(c)->active >> sl & 1)) {
         obs_push(c, sl, SUCC_TRUE, true, IP_MAKE(AC_RSC, 255, 15, 0, 0));
         /* the FSM agents digest the tick's observation now instead of at the start of the next tick */
-        agent_end_turn(c, sl);
+        agent_end_turn<RV>(c, sl);
     }
 }
 
@@ -818,7 +818,7 @@ struct StepIO { const int32_t *actions; const uint8_t *msgs; uint8_t *obs; float
 
 /* Block b owns episodes [env0 + b*epb, min(env0 + (b+1)*epb, env_end)); env0 / env_end: the slice of the batch this
  * launch covers (the chunked host path launches several slices). */
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
+template <int RV> __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
 k_step(Params p, int env0, int env_end, int epb, StepIO io)
 {
     __shared__ int next[N_PHASES + 6];
@@ -859,7 +859,7 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
         if (lane_id() == 0) bulk_store(p.dyn + env, DYN(c), (uint32_t)sizeof(Cc4Dyn));
     };
     each_group<4, 2>(PH_POLICY, first, n_local, next, [&](Cx c, int e, bool exists, int sl) {
-        ph_policy(c, e, exists, exists, sl & 31, sl >= 32, io.actions + (size_t)(first + (exists ? e : 0)) * 5, 0, 0, 0, &ord_blue, &ord_red);
+        ph_policy<RV>(c, e, exists, exists, sl & 31, sl >= 32, io.actions + (size_t)(first + (exists ? e : 0)) * 5, 0, 0, 0, &ord_blue, &ord_red);
     });
     PW_MARK(PH_POLICY);
 #if CC4_FLOW
@@ -921,7 +921,7 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
                 } else if (st == FS_RED) {
                     const int e = fl.perm_r[i];
                     if (lo < FS_RED) { if (lane == 0) { const volatile int *gd = &fl.gdone[e]; const int need = ng_s[e]; while (*gd < need) __nanosleep(40); } __syncwarp(); __threadfence_block(); }
-                    ph_red((Cx)(e * (int)sizeof(WarpSmem)));
+                    ph_red<RV>((Cx)(e * (int)sizeof(WarpSmem)));
                     flow_signal(&fl.prog[e], 1 + FS_RED);
                 } else if (st == FS_REASSIGN) {
                     const int e = fl.perm_r[i];
@@ -935,7 +935,7 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
                     const int e = exists ? (int)fl.perm_r[k] : 0;
                     if (lo < FS_ENDTURN && exists && sl == 0) flow_wait(&fl.prog[e], 1 + FS_REASSIGN);
                     __syncwarp();
-                    ph_endturn((Cx)(e * (int)sizeof(WarpSmem)), exists, sl);
+                    ph_endturn<RV>((Cx)(e * (int)sizeof(WarpSmem)), exists, sl);
                     __syncwarp();
                     if (exists && sl == 0) { __threadfence_block(); *(volatile uint8_t *)&fl.prog[e] = 1 + FS_ENDTURN; }
                 } else {
@@ -973,24 +973,24 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
     each_episode(N_PHASES + 2, first, n_local, next, [&](Cx c, int) { ph_phishing(c); });
 #endif
 #if CC4_MERGE & 4
-    each_episode(PH_RED, first, n_local, next, [&](Cx c, int e) { ph_red(c); ph_reassign(c); ph_endturn(c, true, lane_id()); __syncwarp(); finish(c, e); }, &ord_red);
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int e) { ph_red<RV>(c); ph_reassign(c); ph_endturn<RV>(c, true, lane_id()); __syncwarp(); finish(c, e); }, &ord_red);
 #else
 #if CC4_MERGE & 1
-    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c); ph_reassign(c); }, &ord_red);
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red<RV>(c); ph_reassign(c); }, &ord_red);
 #else
 #if CC4_RED_PARTS == 2
-    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c, !(CC4_SPLIT & 2), 0x07u); }, &ord_red);
-    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c, false, 0x38u); }, &ord_red, N_PHASES + 4);
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red<RV>(c, !(CC4_SPLIT & 2), 0x07u); }, &ord_red);
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red<RV>(c, false, 0x38u); }, &ord_red, N_PHASES + 4);
 #elif CC4_RED_PARTS == 3
-    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c, !(CC4_SPLIT & 2), 0x03u); }, &ord_red);
-    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c, false, 0x0Cu); }, &ord_red, N_PHASES + 4);
-    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c, false, 0x30u); }, &ord_red, N_PHASES + 5);
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red<RV>(c, !(CC4_SPLIT & 2), 0x03u); }, &ord_red);
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red<RV>(c, false, 0x0Cu); }, &ord_red, N_PHASES + 4);
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red<RV>(c, false, 0x30u); }, &ord_red, N_PHASES + 5);
 #else
-    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red(c, !(CC4_SPLIT & 2)); }, &ord_red);
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red<RV>(c, !(CC4_SPLIT & 2)); }, &ord_red);
 #endif
     PW_MARK(PH_RED);
 #if CC4_MERGE & 8      /* reassignment + FSM digest + finish of an episode back to back in one item (two barriers fewer) */
-    each_episode<true>(PH_FINISH, first, n_local, next, [&](Cx c, int e) { ph_reassign(c); ph_endturn(c, true, lane_id()); __syncwarp(); finish(c, e); });
+    each_episode<true>(PH_FINISH, first, n_local, next, [&](Cx c, int e) { ph_reassign(c); ph_endturn<RV>(c, true, lane_id()); __syncwarp(); finish(c, e); });
     PW_MARK(PH_FINISH);
 #else
     each_episode<(CC4_FIXED_PHASES >> 1) & 1>(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { ph_reassign(c); });
@@ -999,9 +999,9 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
 #endif
 #if CC4_MERGE & 8
 #elif CC4_MERGE & 2
-    each_episode(PH_FINISH, first, n_local, next, [&](Cx c, int e) { ph_endturn(c, true, lane_id()); __syncwarp(); finish(c, e); });
+    each_episode(PH_FINISH, first, n_local, next, [&](Cx c, int e) { ph_endturn<RV>(c, true, lane_id()); __syncwarp(); finish(c, e); });
 #else
-    each_group<CC4_ENDTURN_PER>(PH_ENDTURN, first, n_local, next, [&](Cx c, int, bool exists, int sl) { ph_endturn(c, exists, sl); });
+    each_group<CC4_ENDTURN_PER>(PH_ENDTURN, first, n_local, next, [&](Cx c, int, bool exists, int sl) { ph_endturn<RV>(c, exists, sl); });
     PW_MARK(PH_ENDTURN);
     each_episode<(CC4_FIXED_PHASES >> 2) & 1>(PH_FINISH, first, n_local, next, finish);
     PW_MARK(PH_FINISH);
@@ -1013,7 +1013,7 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
 }
 
 /* n_ticks fused ticks with the benchmark's synthetic blue policy (see ph_policy); the state stays in shared memory */
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
+template <int RV> __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
 k_rollout(Params p, int epb, int n_ticks, uint32_t pk0, uint32_t pk1, float *reward_sum, int flags)
 {
     __shared__ int next[N_PHASES + 1];
@@ -1038,13 +1038,13 @@ k_rollout(Params p, int epb, int n_ticks, uint32_t pk0, uint32_t pk1, float *rew
         });
         if (alive == 0) break;
         each_group<4, 2>(PH_POLICY, first, n_local, next, [&](Cx c, int e, bool exists, int sl) {
-            ph_policy(c, e, exists, exists && !DYN(c)->done, sl & 31, sl >= 32, nullptr, pk0, pk1, p.first_episode + (uint64_t)(first + e), &ord_blue, &ord_red);
+            ph_policy<RV>(c, e, exists, exists && !DYN(c)->done, sl & 31, sl >= 32, nullptr, pk0, pk1, p.first_episode + (uint64_t)(first + e), &ord_blue, &ord_red);
         });
         each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_blue(c); }, &ord_blue);
         green_items(PH_GREEN, first, n_local, next, ng_s, gend);
-        each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_red(c); }, &ord_red);
+        each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_red<RV>(c); }, &ord_red);
         each_episode(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_reassign(c); });
-        each_group<CC4_ENDTURN_PER>(PH_ENDTURN, first, n_local, next, [&](Cx c, int, bool exists, int sl) { ph_endturn(c, exists && !DYN(c)->done, sl); });
+        each_group<CC4_ENDTURN_PER>(PH_ENDTURN, first, n_local, next, [&](Cx c, int, bool exists, int sl) { ph_endturn<RV>(c, exists && !DYN(c)->done, sl); });
         /* `done` flips in this phase: the ticks that follow skip the episode, this tick must not look at the flag again */
         each_episode(PH_FINISH, first, n_local, next, [&](Cx c, int e) {
             if (DYN(c)->done) return;
@@ -1641,8 +1641,13 @@ extern "C" int cc4_create(int n_envs, int device, uint64_t seed, uint64_t first_
     CUDA_TRY(cudaMalloc(&h->p.stat, sizeof(Cc4Stat) * (size_t)n_envs));
     CUDA_TRY(cudaMalloc(&h->p.cold, sizeof(Cc4Cold) * (size_t)n_envs));
     CUDA_TRY(cudaMemset(h->p.dyn, 0, sizeof(Cc4Dyn) * (size_t)n_envs));
-    CUDA_TRY(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * EPB_MAX)));
-    CUDA_TRY(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * EPB_MAX)));
+    const int tick_smem = (int)(sizeof(WarpSmem) * EPB_MAX);
+    CUDA_TRY(cudaFuncSetAttribute(k_step<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tick_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_step<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tick_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_step<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tick_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_rollout<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tick_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_rollout<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tick_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_rollout<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tick_smem));
     CUDA_TRY(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResetSmem)));
     CUDA_TRY(cudaFuncSetAttribute(k_reset_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ResetLane) * RESET_FAST_THREADS)));
     CUDA_TRY(cudaFuncSetAttribute(k_reset_outputs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem)));
@@ -1752,6 +1757,17 @@ static int episodes_per_block(const cc4_handle *h, size_t n)
     return (int)(epb < 1 ? 1 : epb > EPB_MAX ? EPB_MAX : epb);
 }
 
+/* k_step is instantiated once per scripted red agent class (see cc4_device.cuh: template <int RV>) */
+static void launch_step(cc4_handle *h, int blocks, int epb, cudaStream_t st, int env0, int env_end, const StepIO &io)
+{
+    const size_t smem = sizeof(WarpSmem) * (size_t)epb;
+    switch (h->p.red_variant) {
+    case CC4_RED_DISCOVERY: k_step<1><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(h->p, env0, env_end, epb, io); break;
+    case CC4_RED_RANDOM_SELECT: k_step<2><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(h->p, env0, env_end, epb, io); break;
+    default: k_step<0><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(h->p, env0, env_end, epb, io); break;
+    }
+}
+
 extern "C" int cc4_step(cc4_handle *h, const int32_t *actions_dev, const uint8_t *msgs_dev, uint8_t *obs_dev, float *reward_dev,
                         uint8_t *done_dev, int flags, void *stream)
 {
@@ -1766,7 +1782,7 @@ extern "C" int cc4_step(cc4_handle *h, const int32_t *actions_dev, const uint8_t
        written records still there, while a fixed direction finds none of them (cyclic sweep over an LRU-like cache). */
     h->sweep ^= h->alternate;
     StepIO io = { actions_dev, msgs_dev, obs_dev, reward_dev, done_dev, flags, h->sweep };
-    k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * (size_t)epb, (cudaStream_t)stream>>>(h->p, 0, h->p.n_envs, epb, io);
+    launch_step(h, blocks, epb, (cudaStream_t)stream, 0, h->p.n_envs, io);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return CC4_OK;
@@ -1857,7 +1873,7 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
             uint8_t *cb = (h->zero_copy ? static_cast<uint8_t *>(h->host_bits_dev) : stage) + e0 * HOST_ROW;
             StepIO io = { h->stage_actions, msgs_host ? h->stage_msgs : nullptr, cb - e0 * HOST_BITS_ROW,
                           reinterpret_cast<float *>(cb + cnt * HOST_BITS_ROW) - e0, cb + cnt * (HOST_BITS_ROW + sizeof(float)) - e0, kflags | CC4_STEP_REWARD, h->sweep };
-            k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * (size_t)epb, st>>>(h->p, (int)e0, (int)(e0 + cnt), epb, io);
+            launch_step(h, blocks, epb, st, (int)e0, (int)(e0 + cnt), io);
             h->launches++;
             CUDA_TRY(cudaGetLastError());
             if (!h->zero_copy) CUDA_TRY(cudaMemcpyAsync(hstage + e0 * HOST_ROW, cb, cnt * HOST_ROW, cudaMemcpyDeviceToHost, st));
@@ -1902,7 +1918,7 @@ extern "C" int cc4_step_host(cc4_handle *h, const int32_t *actions_host, const u
         const int epb = episodes_per_block(h, cnt), blocks = (int)((cnt + epb - 1) / epb);
         StepIO io = { h->stage_actions, msgs_host ? h->stage_msgs : nullptr, want_obs ? h->stage_obs : nullptr,
                       want_rew ? h->stage_reward : nullptr, done_host ? h->stage_done : nullptr, flags };
-        k_step<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * (size_t)epb, st>>>(h->p, (int)e0, (int)(e0 + cnt), epb, io);
+        launch_step(h, blocks, epb, st, (int)e0, (int)(e0 + cnt), io);
         h->launches++;
         CUDA_TRY(cudaGetLastError());
         if (want_obs) CUDA_TRY(cudaMemcpyAsync(obs_host + e0 * obs_row, h->stage_obs + e0 * obs_row, cnt * obs_row, cudaMemcpyDeviceToHost, st));
@@ -1965,8 +1981,13 @@ extern "C" int cc4_rollout(cc4_handle *h, int n_ticks, uint64_t policy_seed, flo
     if (!h || n_ticks < 0) return set_err(CC4_ERR_ARG, "cc4_rollout: bad argument%s", "");
     CUDA_TRY(cudaSetDevice(h->device));
     const int epb = episodes_per_block(h, (size_t)h->p.n_envs), blocks = (h->p.n_envs + epb - 1) / epb;
-    k_rollout<<<blocks, WARPS_PER_BLOCK * 32, sizeof(WarpSmem) * (size_t)epb, (cudaStream_t)stream>>>(
-        h->p, epb, n_ticks, (uint32_t)policy_seed ^ 0x5EEDu, (uint32_t)(policy_seed >> 32), reward_sum_dev, flags);
+    const uint32_t pk0 = (uint32_t)policy_seed ^ 0x5EEDu, pk1 = (uint32_t)(policy_seed >> 32);
+    const size_t smem = sizeof(WarpSmem) * (size_t)epb;
+    switch (h->p.red_variant) {
+    case CC4_RED_DISCOVERY: k_rollout<1><<<blocks, WARPS_PER_BLOCK * 32, smem, (cudaStream_t)stream>>>(h->p, epb, n_ticks, pk0, pk1, reward_sum_dev, flags); break;
+    case CC4_RED_RANDOM_SELECT: k_rollout<2><<<blocks, WARPS_PER_BLOCK * 32, smem, (cudaStream_t)stream>>>(h->p, epb, n_ticks, pk0, pk1, reward_sum_dev, flags); break;
+    default: k_rollout<0><<<blocks, WARPS_PER_BLOCK * 32, smem, (cudaStream_t)stream>>>(h->p, epb, n_ticks, pk0, pk1, reward_sum_dev, flags); break;
+    }
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return CC4_OK;

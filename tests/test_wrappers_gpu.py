@@ -397,12 +397,24 @@ def test_the_reference_evaluation_script_runs_unchanged_on_the_compat_package():
             f"spec = importlib.util.spec_from_file_location('ref_evaluation', {os.path.join(ref_eval, 'evaluation.py')!r})\n"
             "m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)\n"
             "import CybORG; assert 'compat' in CybORG.__file__, CybORG.__file__\n"
-            f"sub = m.load_submission({os.path.join(ref_eval, 'example_submission')!r})\n"
+            "sub = m.load_submission(sys.argv[2])\n"
             "m.run_evaluation(sub, log_path=sys.argv[1], max_eps=2, write_to_file=True, seed=7)\n")
+    # a submission in the layout of the reference's example_submission/ (submission.py + dummy_agent.py, same classes and imports; the
+    # example itself cannot be imported by any Python: its `from __future__ import annotations` sits on line 9, submission.py:9)
+    submission_py = ("from __future__ import annotations\n"
+                     "from CybORG import CybORG\nfrom CybORG.Agents import BaseAgent\n"
+                     "from ray.rllib.env.multi_agent_env import MultiAgentEnv\nfrom CybORG.Agents.Wrappers.EnterpriseMAE import EnterpriseMAE\n"
+                     "from dummy_agent import DummyAgent\n\n"
+                     "class Submission:\n    NAME: str = 'SUBMISSION NAME'\n    TEAM: str = 'TEAM NAME'\n    TECHNIQUE: str = 'TECHNIQUE NAME'\n"
+                     "    AGENTS: dict[str, BaseAgent] = {f'blue_agent_{agent}': DummyAgent() for agent in range(5)}\n\n"
+                     "    def wrap(env: CybORG) -> MultiAgentEnv:\n        return EnterpriseMAE(env)\n")
+    dummy_py = open(os.path.join(ref_eval, "example_submission", "dummy_agent.py")).read()
     # the example submission imports ray's MultiAgentEnv and gym's Space for type annotations: stand-ins from the test infrastructure
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "compat"), os.path.join(root, "oracle", "refshim")]))
-    with tempfile.TemporaryDirectory() as tmp:
-        out = subprocess.run([sys.executable, "-c", code, tmp + "/"], capture_output=True, text=True, env=env, cwd=tmp)
+    with tempfile.TemporaryDirectory() as tmp, tempfile.TemporaryDirectory() as subdir:
+        open(os.path.join(subdir, "submission.py"), "w").write(submission_py)
+        open(os.path.join(subdir, "dummy_agent.py"), "w").write(dummy_py)
+        out = subprocess.run([sys.executable, "-c", code, tmp + "/", subdir], capture_output=True, text=True, env=env, cwd=tmp)
         assert out.returncode == 0, out.stderr[-1500:]
         assert "Average reward is:" in out.stdout
         assert sorted(os.listdir(tmp)) == ["actions.txt", "full.txt", "scores.txt", "summary.json", "summary.txt"]
