@@ -1673,7 +1673,7 @@ template <int RV> __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
 }
 
 /* RedSessionCheck._choose_new_primary_session RedSessionCheck.py:34-55 ([uniform]; agent r holds n sessions, none with ident 0) */
-__device__ CC4_INL6 void rsc_reelect(Cx c, int r, int n)
+template <int RV> __device__ CC4_INL6 void rsc_reelect(Cx c, int r, int n)
 {
     Cc4Dyn *s = DYN(c);
     int pk = (int)rng_int_red(c, r, ST_RSC_PRIMARY, (uint32_t)n);
@@ -1690,10 +1690,12 @@ __device__ CC4_INL6 void rsc_reelect(Cx c, int r, int n)
     const int ns = s->n_sess;
     sess_shift_down(s, at, ns);      /* the re-keyed entry moves to the end of the agent's dict */
     s->sess[ns - 1] = S_MAKE(S_PID(w), 0, S_HOST(w)); s->sessf[ns - 1] = f;
-    __syncwarp();
-    /* every session of the agent now hangs under the new primary, whose name is None (RedSessionCheck.py:50-54): no parents left */
-    _Pragma("unroll 1") for (int i = lane_id(); i < ns; i += 32) if (SF_AGENT((uint32_t)s->sessf[i]) == (uint32_t)r) s->sessf[i] &= (uint8_t)~SF_PARENTBIT;
-    __syncwarp();
+    if (RV == 2) {      /* only Withdraw (RandomSelectRedAgent) ever looks at the parent flag */
+        __syncwarp();
+        /* every session of the agent now hangs under the new primary, whose name is None (RedSessionCheck.py:50-54): no parents left */
+        _Pragma("unroll 1") for (int i = lane_id(); i < ns; i += 32) if (SF_AGENT((uint32_t)s->sessf[i]) == (uint32_t)r) s->sessf[i] &= (uint8_t)~SF_PARENTBIT;
+        __syncwarp();
+    }
 }
 
 /* SimulationController.different_subnet_agent_reassignment :820-903 [uniform] */

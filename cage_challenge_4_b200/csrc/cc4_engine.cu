@@ -580,7 +580,7 @@ template <int RV> __device__ __forceinline__ void ph_red(Cx c, bool with_phishin
 
 /* ---- phase 5: reassignment (:278), then the warp-wide half of the end-turn actions (:281-286): Monitor for blue,
    the primary-session re-election of RedSessionCheck ---- */
-__device__ __forceinline__ void ph_reassign(Cx c)
+template <int RV> __device__ __forceinline__ void ph_reassign(Cx c)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     w_scan_sessions(c);
@@ -596,7 +596,7 @@ __device__ __forceinline__ void ph_reassign(Cx c)
     uint32_t elect = __ballot_sync(0xFFFFFFFFu, holds && s->sess_count[lane] != 0 && !(x->has0 >> lane & 1));
     if (lane == 0) { x->active = active; s->red_active = (uint8_t)active; }
     w_monitor_all(c);
-    while (elect) { const int r = __ffs(elect) - 1; elect &= elect - 1; rsc_reelect(c, r, x->n_red[r]); }
+    while (elect) { const int r = __ffs(elect) - 1; elect &= elect - 1; rsc_reelect<RV>(c, r, x->n_red[r]); }
     __syncwarp();
     if (x->newss) learn_new_sessions(c);        /* the observation lists the sessions as the re-election left them */
     __syncwarp();
@@ -926,7 +926,7 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
                 } else if (st == FS_REASSIGN) {
                     const int e = fl.perm_r[i];
                     if (lo < FS_REASSIGN) { if (lane == 0) flow_wait(&fl.prog[e], 1 + FS_RED); __syncwarp(); }
-                    ph_reassign((Cx)(e * (int)sizeof(WarpSmem)));
+                    ph_reassign<RV>((Cx)(e * (int)sizeof(WarpSmem)));
                     flow_signal(&fl.prog[e], 1 + FS_REASSIGN);
                 } else if (st == FS_ENDTURN) {
                     constexpr int per = CC4_ENDTURN_PER;
@@ -973,10 +973,10 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
     each_episode(N_PHASES + 2, first, n_local, next, [&](Cx c, int) { ph_phishing(c); });
 #endif
 #if CC4_MERGE & 4
-    each_episode(PH_RED, first, n_local, next, [&](Cx c, int e) { ph_red<RV>(c); ph_reassign(c); ph_endturn<RV>(c, true, lane_id()); __syncwarp(); finish(c, e); }, &ord_red);
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int e) { ph_red<RV>(c); ph_reassign<RV>(c); ph_endturn<RV>(c, true, lane_id()); __syncwarp(); finish(c, e); }, &ord_red);
 #else
 #if CC4_MERGE & 1
-    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red<RV>(c); ph_reassign(c); }, &ord_red);
+    each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red<RV>(c); ph_reassign<RV>(c); }, &ord_red);
 #else
 #if CC4_RED_PARTS == 2
     each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red<RV>(c, !(CC4_SPLIT & 2), 0x07u); }, &ord_red);
@@ -990,10 +990,10 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
 #endif
     PW_MARK(PH_RED);
 #if CC4_MERGE & 8      /* reassignment + FSM digest + finish of an episode back to back in one item (two barriers fewer) */
-    each_episode<true>(PH_FINISH, first, n_local, next, [&](Cx c, int e) { ph_reassign(c); ph_endturn<RV>(c, true, lane_id()); __syncwarp(); finish(c, e); });
+    each_episode<true>(PH_FINISH, first, n_local, next, [&](Cx c, int e) { ph_reassign<RV>(c); ph_endturn<RV>(c, true, lane_id()); __syncwarp(); finish(c, e); });
     PW_MARK(PH_FINISH);
 #else
-    each_episode<(CC4_FIXED_PHASES >> 1) & 1>(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { ph_reassign(c); });
+    each_episode<(CC4_FIXED_PHASES >> 1) & 1>(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { ph_reassign<RV>(c); });
     PW_MARK(PH_REASSIGN);
 #endif
 #endif
@@ -1043,7 +1043,7 @@ k_rollout(Params p, int epb, int n_ticks, uint32_t pk0, uint32_t pk1, float *rew
         each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_blue(c); }, &ord_blue);
         green_items(PH_GREEN, first, n_local, next, ng_s, gend);
         each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_red<RV>(c); }, &ord_red);
-        each_episode(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_reassign(c); });
+        each_episode(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_reassign<RV>(c); });
         each_group<CC4_ENDTURN_PER>(PH_ENDTURN, first, n_local, next, [&](Cx c, int, bool exists, int sl) { ph_endturn<RV>(c, exists && !DYN(c)->done, sl); });
         /* `done` flips in this phase: the ticks that follow skip the episode, this tick must not look at the flag again */
         each_episode(PH_FINISH, first, n_local, next, [&](Cx c, int e) {
