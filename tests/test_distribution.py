@@ -1,20 +1,20 @@
 """Distributional parity of the production RNG mode against the live reference (tertiary parity).
 
-Trajectory parity is pinned by tape replay (test_oracle_golden.py, test_cuda_parity.py).  In production mode the engine
-draws from counter-based Philox streams, by design not the reference's PCG64 program-order stream, so what must agree is
-the DISTRIBUTION of outcomes.  tests/golden/ref_rewards_{sleep,random}.npz hold the per-tick team reward of full episodes
-of the unmodified reference (oracle/ref_returns.py: 192 episodes under uniform-random blue; 872 under all-Sleep blue, pooled
-from four runs whose seeds are listed in the file); the oracle (bit-exact with the CUDA engine in this mode,
-test_cuda_parity.py::test_philox_mode_matches_oracle) is run on other episodes and compared: episode return overall and
-per mission phase (Welch z-score), and the shape of the return distribution (two-sample KS).
+What makes production mode exact is elsewhere: tests/golden/px_*.npz are episodes of the unmodified reference driven by the
+engine's own Philox words (ref_harness.PhiloxSeamGenerator), reproduced bit for bit by the oracle and the CUDA engine in
+production mode; oracle/seam_semantics_check.py shows that the recording generator behaves exactly like numpy's Generator on
+the same stream.  Given that, the engine's outcomes are the reference's outcomes under a different but equally uniform stream,
+and this test only guards the remaining assumption (the words are uniform and independent) the statistical way.
 
-What this guards against is a wrong rate or a wrong branch in production mode (a 1 % -> 2 % phishing rate moves the
-return by > 10 sigma), hence the wide |z| < 5 gate.  Observed: random blue z = -0.2 (return -5113 vs -5100, KS p = 0.49;
-the 65 536-episode GPU bench gives -5115); all-Sleep blue z = -3.1 overall, -4.2 in mission phase 1.  The reference's own
-four all-Sleep runs disagree with each other at that level (phase-1 means -2552, -2563, -2387, -2322 with standard
-errors 40-68; the reference is deterministic per seed and has no hash-seed dependence, so this is sampling spread of
-a heavy-tailed statistic), and a 196-episode event-by-event breakdown (LWF / ASF / RIA per subnet and phase, 48
-categories) shows no category beyond 2.3 sigma.  DESIGN.md section 2 records this.
+tests/golden/ref_rewards_{sleep,random}.npz hold the per-tick team reward of full episodes of the unmodified reference under
+numpy PCG64 (oracle/ref_returns.py): 192 episodes under uniform-random blue, 2 072 under all-Sleep blue (five runs, seeds
+listed in the file).  The oracle (bit-exact with the CUDA engine in this mode) runs 2 500 other episodes; compared are the
+episode return overall and per mission phase (Welch z, gate |z| < 3), the spread, and the shape (two-sample KS).
+
+History of the all-Sleep comparison: round 1 had 872 reference episodes (-6 831 +- 47) against 768 engine episodes (-6 622 +- 49),
+z = -3.1 overall and -4.2 in mission phase 1.  Both samples turned out to sit in the tails: 1 200 further reference episodes
+give -6 670 +- 40, and 9 000 further engine episodes (seeds 1234 and 77) give -6 770 +- 18 / -6 756 (phase 1: -2 392 +- 10 against
+the reference's pooled -2 383 +- 18, z = +0.4).  Pooled reference (2 072) against the 6 000-episode engine run: z = +0.95.
 """
 import os
 import sys
@@ -27,7 +27,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import oracle_py as O  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-N_ENGINE = 768
+N_ENGINE = 2500
 PHASES = [(0, 167), (167, 334), (334, 499)]     # EnterpriseScenarioGenerator._generate_mission_phases :854-860 (500 -> 167/167/166)
 
 
@@ -36,7 +36,7 @@ def _engine_rewards(policy, n):
     out = np.zeros((n, 499), dtype=np.float32)
     g = np.random.default_rng(12345)
     for i in range(n):
-        env = O.OracleEnv(seed=77, episode=5000 + i, steps=500)
+        env = O.OracleEnv(seed=1234, episode=i, steps=500)
         env.reset()
         for t in range(499):
             a = (49, 49, 49, 49, 145) if policy == "sleep" else [int(g.integers(0, k)) for k in (82, 82, 82, 82, 242)]
@@ -68,7 +68,7 @@ def test_episode_return_distribution_matches_reference(policy):
         r, e = ref[:, lo:hi].sum(1), eng[:, lo:hi].sum(1)
         z = (r.mean() - e.mean()) / np.sqrt(r.var(ddof=1) / len(r) + e.var(ddof=1) / len(e))
         report.append(f"{name}: reference {r.mean():.1f} +- {r.std(ddof=1):.1f}, engine {e.mean():.1f} +- {e.std(ddof=1):.1f}, z = {z:.2f}")
-        assert abs(z) < 5.0, "; ".join(report)
+        assert abs(z) < 3.0, "; ".join(report)
         # the spread must agree as well (ratio of standard deviations; 192 samples give ~ +-10 % at 2 sigma)
         assert 0.75 < r.std(ddof=1) / e.std(ddof=1) < 1.33, "; ".join(report)
     d, p = _ks(ref.sum(1), eng.sum(1))
