@@ -45,6 +45,9 @@ namespace cc4 {
 #ifndef CC4_ENDTURN_PER
 #define CC4_ENDTURN_PER 2       /* episodes per warp in the FSM digest phase (6 lanes of work per episode; 2 and 4 measure the same) */
 #endif
+#ifndef CC4_MIN_BLOCKS
+#define CC4_MIN_BLOCKS 1        /* blocks of k_step per SM (tuning knob: 2 with CC4_WARPS_PER_BLOCK=16 CC4_EPB_MAX=32) */
+#endif
 constexpr int WARPS_PER_BLOCK = CC4_WARPS_PER_BLOCK;
 constexpr int EPB_MAX = CC4_EPB_MAX;
 constexpr int DYN_U4 = (int)(sizeof(Cc4Dyn) / 16);
@@ -818,7 +821,7 @@ struct StepIO { const int32_t *actions; const uint8_t *msgs; uint8_t *obs; float
 
 /* Block b owns episodes [env0 + b*epb, min(env0 + (b+1)*epb, env_end)); env0 / env_end: the slice of the batch this
  * launch covers (the chunked host path launches several slices). */
-template <int RV> __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
+template <int RV> __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, CC4_MIN_BLOCKS)
 k_step(Params p, int env0, int env_end, int epb, StepIO io)
 {
     __shared__ int next[N_PHASES + 6];
@@ -1013,7 +1016,7 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
 }
 
 /* n_ticks fused ticks with the benchmark's synthetic blue policy (see ph_policy); the state stays in shared memory */
-template <int RV> __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 1)
+template <int RV> __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, CC4_MIN_BLOCKS)
 k_rollout(Params p, int epb, int n_ticks, uint32_t pk0, uint32_t pk1, float *reward_sum, int flags)
 {
     __shared__ int next[N_PHASES + 1];
@@ -1225,11 +1228,13 @@ struct ResetLane {
     uint32_t used[288];          /* bitmap over pids 1000..9999 (EnterpriseScenarioGenerator._generate_pid :563-578) */
     uint16_t pmax[128];          /* largest pid on the host so far (Host.create_pid Host.py:198-200) */
     uint8_t np[128];             /* processes on the host so far */
-    uint16_t router_pid[16];
-    uint32_t pad;                /* stride = 393 words: lanes hit different banks at equal offsets */
+    uint8_t router_pid[16];      /* 1..9: a router's only process is the blue session's (Host.create_pid on an empty list) */
+    uint32_t pad;                /* stride = 389 words (odd): lanes hit different banks at equal offsets */
 };
-static_assert(sizeof(ResetLane) == 393 * 4, "ResetLane stride");
-constexpr int RESET_FAST_THREADS = 128;
+static_assert(sizeof(ResetLane) == 389 * 4, "ResetLane stride");
+/* 148 lanes x 1 556 B = 225 KB of shared memory: one block per SM, and 65 536 episodes are 443 blocks = three full waves of 148
+   (128 threads per block were 512 blocks = 3.5 waves, i.e. four: 1.61 ms against 1.2 ms) */
+constexpr int RESET_FAST_THREADS = 148;
 
 __global__ void __launch_bounds__(RESET_FAST_THREADS) k_reset_fast(Params p)
 {
@@ -1336,7 +1341,7 @@ __global__ void __launch_bounds__(RESET_FAST_THREADS) k_reset_fast(Params p)
     }
     /* State.__init__ State.py:108-134: session processes (Host.add_session Host.py:189-196) */
     auto add_session_proc = [&](int slot, uint32_t kind) -> uint32_t {
-        if (slot >= CC4_SLOT_ROUTER) { const uint32_t pid = 1u + ri(9); t->router_pid[slot - CC4_SLOT_ROUTER] = (uint16_t)pid; return pid; }
+        if (slot >= CC4_SLOT_ROUTER) { const uint32_t pid = 1u + ri(9); t->router_pid[slot - CC4_SLOT_ROUTER] = (uint8_t)pid; return pid; }
         const uint32_t pid = (uint32_t)t->pmax[slot] + 1u + ri(9);
         const int n = t->np[slot];
         const uint32_t pw = P_MAKE(pid, kind, 0, 0);
@@ -1387,8 +1392,15 @@ __global__ void __launch_bounds__(RESET_FAST_THREADS) k_reset_fast(Params p)
 __global__ void __launch_bounds__(32) k_reset_outputs(Params p, uint8_t *obs, uint8_t *mask)
 {
     WarpSmem *w = reinterpret_cast<WarpSmem *>(smem_raw);
-    const int env = blockIdx.x;
-    w_load(&w->dyn, p.dyn + env);
+    const int env = blockIdx.x, lane = lane_id();
+    {   /* of a freshly reset record the writers only look at the host counts; events, blocks, messages and the phase are zero */
+        Cc4Dyn *d = &w->dyn; const Cc4Dyn *g = p.dyn + env;
+        for (int i = lane; i < (int)(sizeof(d->ev) / 4); i += 32) reinterpret_cast<uint32_t *>(d->ev)[i] = 0;
+        if (lane < 12) d->blocks[lane] = 0;
+        if (lane < 8) { d->msgs[lane] = 0; d->nuser[lane] = g->nuser[lane]; d->nserver[lane] = g->nserver[lane]; }
+        if (lane == 0) d->phase = 0;
+        __syncwarp();
+    }
     if (obs) w_write_obs(&w->dyn, &w->x, obs, env);
     if (mask) w_write_mask(&w->dyn, mask + (size_t)env * CC4_N_BLUE * CC4_MASK_LEN);
 }
@@ -1751,8 +1763,8 @@ extern "C" int cc4_reset_host(cc4_handle *h, uint8_t *obs_host, uint8_t *mask_ho
  * 86 % full, instead of 52 per block and a 10th wave at 52 %). */
 static int episodes_per_block(const cc4_handle *h, size_t n)
 {
-    size_t per_wave = (size_t)h->n_sm * EPB_MAX, waves = (n + per_wave - 1) / per_wave;
-    size_t epb = (n + waves * h->n_sm - 1) / (waves * h->n_sm);
+    size_t per_wave = (size_t)h->n_sm * EPB_MAX * CC4_MIN_BLOCKS, waves = (n + per_wave - 1) / per_wave;
+    size_t epb = (n + waves * h->n_sm * CC4_MIN_BLOCKS - 1) / (waves * h->n_sm * CC4_MIN_BLOCKS);
     return (int)(epb < 1 ? 1 : epb > EPB_MAX ? EPB_MAX : epb);
 }
 

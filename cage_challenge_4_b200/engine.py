@@ -134,7 +134,7 @@ class BatchedCC4:
 
     def reset(self):
         _native.check(self._L.cc4_reset(self._h, self.obs.data_ptr(), self.mask.data_ptr(), self._stream()), "cc4_reset")
-        return self.obs, self.mask.bool()
+        return self.obs, self.mask.view(torch.bool)       # the kernel writes 0 / 1 bytes: a view, not a conversion kernel over 79 MB
 
     def reset_host(self):
         """reset() with HOST outputs (pinned): obs uint8 [N,5,210], mask uint8 [N,5,242]."""
