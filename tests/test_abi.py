@@ -43,14 +43,17 @@ def test_engine_refuses_to_run_without_cuda():
 
 
 def test_product_package_never_imports_the_oracle():
-    pkg = os.path.join(ROOT, "cage_challenge_4_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                for line in open(os.path.join(dirpath, f)):
-                    code = line.strip()
-                    if code.startswith(("#include", "import ", "from ")) or "dlopen" in code or "CDLL" in code:
-                        assert "oracle" not in code and "ref_harness" not in code, f"{f}: {code}"
+    """Neither the engine package nor the compat alias package may import, include or load anything of oracle/ (or baseline/)."""
+    sources = []
+    for pkg in (os.path.join(ROOT, "cage_challenge_4_b200"), os.path.join(ROOT, "compat")):
+        for dirpath, _, files in os.walk(pkg):
+            sources += [os.path.join(dirpath, f) for f in files if f.endswith((".py", ".cu", ".cuh", ".h"))]
+    assert len(sources) > 20
+    for path in sources:
+        for line in open(path):
+            code = line.strip()
+            if code.startswith(("#include", "import ", "from ")) or "dlopen" in code or "CDLL" in code:
+                assert "oracle" not in code and "ref_harness" not in code and "baseline" not in code, f"{path}: {code}"
 
 
 def test_host_expansion_of_bit_rows_matches_numpy():
