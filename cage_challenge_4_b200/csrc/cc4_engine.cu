@@ -2,10 +2,13 @@
  * cc4_engine.cu — kernels and C-ABI (include/cc4_b200.h) of the B200-native batched CC4 step engine.
  *
  * Kernels (sm_100a):
- *   k_reset   EnterpriseScenarioGenerator.create_scenario + State.__init__ + controller reset (one warp per episode)
- *   k_step    one SimulationController.step tick for every episode (+ observation vectors, reward, done): one block per
- *             SM keeps up to 64 episodes' packed records in shared memory and walks them through the phases of the tick
- *   k_rollout n fused ticks with the benchmark's synthetic random blue policy (state stays in shared memory)
+ *   k_reset_fast + k_reset_outputs   EnterpriseScenarioGenerator.create_scenario + State.__init__ + controller reset in production
+ *             mode: one THREAD per episode (the reset stream is one serial chain), then the observation rows and masks
+ *   k_reset   the same with one warp per episode and the per-episode shared-memory context the tape reader needs (tape mode)
+ *   k_step<RV>    one SimulationController.step tick for every episode (+ observation vectors, reward, done): one block per
+ *             SM keeps up to 64 episodes' packed records in shared memory and walks them through the phases of the tick;
+ *             RV = the scripted red agent class (FiniteStateRedAgent, DiscoveryFSRed, RandomSelectRedAgent), a template parameter
+ *   k_rollout<RV> n fused ticks with the benchmark's synthetic random blue policy (state stays in shared memory)
  * Citations are file:line under /root/reference/CybORG/.
  */
 #include <cuda_runtime.h>
