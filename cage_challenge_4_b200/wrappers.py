@@ -233,10 +233,29 @@ class CybORG:
         assert m.shape == (MESSAGE_LENGTH,), f"{agent} attempting to send message {m} that is not in the message space"  # SimulationController.py:797
         return int(sum(int(x) << i for i, x in enumerate(m)))
 
+    def action_index(self, agent: str, action) -> int:
+        """The BlueFixedActionWrapper index of an action given as an index, as a descriptor of `actions()`, or as any object that
+        looks like one of the reference's blue Action objects (class name + `hostname` or `from_subnet` / `to_subnet` attributes:
+        Analyse / Remove / Restore / DeployDecoy / Monitor / Sleep / BlockTrafficZone / AllowTrafficZone)."""
+        if isinstance(action, (int, np.integer)):
+            return int(action)
+        name = action.name if isinstance(action, ActionDescriptor) else type(action).__name__
+        want = {k: getattr(action, k) for k in ("hostname", "from_subnet", "to_subnet") if getattr(action, k, None) is not None}
+        b = int(agent.rsplit("_", 1)[1])
+        if name == "Sleep":
+            return SLEEP_INDEX[b]
+        if name == "Monitor":
+            return 48 if b == 4 else 16
+        for i, d in enumerate(self._labels().actions(agent)):
+            if want and d.name == name and all(d.params.get(k) == v for k, v in want.items()):
+                return i
+        raise ValueError(f"{agent}: {name} {want} is not one of the agent's actions (BlueFixedActionWrapper.actions); a host that does not exist in this "
+                         f"episode has no action, and only blue actions can be submitted")
+
     # env.py:95
     def parallel_step(self, actions: dict | None = None, messages: dict | None = None, skip_valid_action_check: bool = False):
-        """`actions`: {blue agent: BlueFixedActionWrapper index} (the engine executes indices, not Action objects; agents left
-        out Sleep, as the reference's SleepAgent default does).  Returns (observations, rewards, dones, {}) with the reference's
+        """`actions`: {blue agent: BlueFixedActionWrapper index, or a descriptor / reference-style Action object that `action_index`
+        can map to one} (the engine executes indices; agents left out Sleep, as the reference's SleepAgent default does).  Returns (observations, rewards, dones, {}) with the reference's
         structure: dict observations (see get_observation), the team reward dict per agent, one done flag per agent."""
         self._single("CybORG.parallel_step")
         if self._tracker is None:
@@ -244,13 +263,7 @@ class CybORG:
                 raise RuntimeError("parallel_step returns dict observations, which follow the episode from its first tick: call "
                                    "enable_dict_observations() (or parallel_step) before the episode's first tick")
             self.enable_dict_observations()
-        idx = {}
-        for a, v in (actions or {}).items():
-            if isinstance(v, ActionDescriptor):
-                raise TypeError(f"{a}: pass the action's index (wrapper.actions(agent).index(action)), not the descriptor")
-            if not isinstance(v, (int, np.integer)):
-                raise TypeError(f"{a}: the engine takes BlueFixedActionWrapper indices, got {type(v).__name__}")
-            idx[a] = int(v)
+        idx = {a: self.action_index(a, v) for a, v in (actions or {}).items()}
         self._tick(idx, {a: self._message_byte(a, m) for a, m in (messages or {}).items()})
         agents = list(dict.fromkeys(list(idx) + self.active_agents))
         return ({a: self.get_observation(a) for a in agents}, {a: dict(self._rewards["Blue"]) for a in agents},

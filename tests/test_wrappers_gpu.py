@@ -329,6 +329,15 @@ def test_facade_surface_of_env_py():
         obs, *_ = cy.parallel_step({})
     assert obs["blue_agent_4"]["success"] is TernaryEnum.TRUE and str(obs["blue_agent_4"]["action"]) == labels[i_restore]
     assert str(cy.get_last_action("blue_agent_4")[0]) == "Sleep"
+    # descriptors and reference-style Action objects (class name + attributes) are mapped to their index
+    class Analyse:                                                                         # what a reference Action object looks like from outside
+        def __init__(self, hostname, session=0, agent=None):
+            self.hostname, self.session, self.agent = hostname, session, agent
+    host = fixed.actions("blue_agent_2")[0].hostname
+    assert cy.action_index("blue_agent_2", Analyse(host)) == 0 == cy.action_index("blue_agent_2", fixed.actions("blue_agent_2")[0])
+    assert cy.action_index("blue_agent_4", acts[146]) == 146 and cy.action_index("blue_agent_4", acts[145]) == 145
+    with pytest.raises(ValueError):
+        cy.action_index("blue_agent_2", Analyse("no_such_host"))
     res = cy.step("blue_agent_1", 16)                                                      # CC1/CC2-style call: Monitor
     assert res.observation["success"] is TernaryEnum.TRUE and str(res.observation["action"]) == "Monitor" and res.done is False
     # maps and action space dicts

@@ -21,6 +21,18 @@ for t in range(60):
     o3, r3, d3 = envs[3].step_host(acts.pin_memory(), msgs.pin_memory(), compact=True)
     assert torch.equal(unpack_bits(o2), o1) and torch.equal(o3, o1.cpu()) and torch.equal(r0, r2)
 envs[0].rollout(40, policy_seed=3)
+# the other scripted red agents (their own instantiations of k_step), bit rows to the host, a second reset (k_reset_fast + k_reset_outputs)
+for red in ("discovery", "random_select"):
+    e = BatchedCC4(150, device=0, seed=4, red_agent=red)
+    e.reset()
+    for t in range(80):
+        acts = torch.from_numpy(np.stack([g.integers(0, k, 150) for k in (82, 82, 82, 82, 242)], 1).astype(np.int32))
+        if t % 3:
+            acts[:] = torch.tensor([49, 49, 49, 49, 145], dtype=torch.int32)
+        e.step_host(acts.pin_memory(), bits=True)
+    e.reset()
+    e.step_state_only(acts.cuda())
+    envs.append(e)
 torch.cuda.synchronize()
 assert not any(e.error_flags().any() for e in envs)
 print("sanitizer smoke ok")
