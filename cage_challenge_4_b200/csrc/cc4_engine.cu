@@ -483,23 +483,25 @@ __device__ __forceinline__ void ph_blue_exec(Cx c, uint32_t agents, bool with_pr
    out as ONE flat list (episode-major) and handed out 32 at a time, so every lane of every item has an agent whatever the
    episodes' sizes (24-80 agents) are; penalties and phishing flags go to the owning episode's scratch with shared-memory
    atomics.  The phishing side effect is order dependent: it is replayed in agent order at the start of the red phase. ---- */
+/* inclusive prefix of the episodes' green-agent counts, by ONE warp, at least one block barrier before green_items reads it
+   (called between the policy and the blue phase: the counts are final after setup) */
+__device__ __forceinline__ void green_prefix(int n_local, const uint8_t *ng_s, short *gend)
+{
+    const int lane = lane_id();
+    int ca = lane < n_local ? ng_s[lane] : 0, cb = 32 + lane < n_local ? ng_s[32 + lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int ta = __shfl_up_sync(0xFFFFFFFFu, ca, o), tb = __shfl_up_sync(0xFFFFFFFFu, cb, o); if (lane >= o) { ca += ta; cb += tb; } }
+    cb += __shfl_sync(0xFFFFFFFFu, ca, 31);
+    if (lane < n_local) gend[lane] = (short)ca;
+    if (32 + lane < n_local) gend[32 + lane] = (short)cb;
+}
 __device__ __forceinline__ void green_items(int ph, int first, int n_local, int *next, const uint8_t *ng_s, short *gend)
 {
 #ifdef CC4_PHASE_CLOCKS
     const long long tb0 = clock64();
 #endif
     const int lane = lane_id();
-    int total;
-    {   /* inclusive prefix of the episodes' agent counts (every warp computes and writes the same values) */
-        int ca = lane < n_local ? ng_s[lane] : 0, cb = 32 + lane < n_local ? ng_s[32 + lane] : 0;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int ta = __shfl_up_sync(0xFFFFFFFFu, ca, o), tb = __shfl_up_sync(0xFFFFFFFFu, cb, o); if (lane >= o) { ca += ta; cb += tb; } }
-        cb += __shfl_sync(0xFFFFFFFFu, ca, 31);
-        total = __shfl_sync(0xFFFFFFFFu, cb, 31);
-        if (lane < n_local) gend[lane] = (short)ca;
-        if (32 + lane < n_local) gend[32 + lane] = (short)cb;
-        __syncwarp();
-    }
+    const int total = n_local > 0 ? gend[n_local - 1] : 0;        /* the prefix table was written by green_prefix, a block barrier ago */
     const int n_items = (total + 31) >> 5;
     /* items cost the same: warp w takes items w, w + 32, ... (CC4_GREEN_FIXED=0: from the shared counter) */
     _Pragma("unroll 1") for (int it_fixed = (int)(threadIdx.x >> 5);; it_fixed += WARPS_PER_BLOCK) {
@@ -833,7 +835,6 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
     __shared__ PhaseOrder ord_blue, ord_red;
     __shared__ __align__(8) uint64_t ld_bar[64];
     const int first = env0 + (int)(io.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * epb, n_local = min(epb, env_end - first);
-    (void)gend;
     PW_BEGIN();
     init_block_ctx(p);
     if (threadIdx.x < N_PHASES + 6) next[threadIdx.x] = 0;
@@ -868,6 +869,7 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
         ph_policy<RV>(c, e, exists, exists, sl & 31, sl >= 32, io.actions + (size_t)(first + (exists ? e : 0)) * 5, 0, 0, 0, &ord_blue, &ord_red);
     });
     PW_MARK(PH_POLICY);
+    if (threadIdx.x < 32) green_prefix(n_local, ng_s, gend);        /* read after the blue phase's barrier */
 #if CC4_FLOW
     {
         __shared__ FlowSmem fl;
@@ -1046,6 +1048,7 @@ k_rollout(Params p, int epb, int n_ticks, uint32_t pk0, uint32_t pk1, float *rew
         each_group<4, 2>(PH_POLICY, first, n_local, next, [&](Cx c, int e, bool exists, int sl) {
             ph_policy<RV>(c, e, exists, exists && !DYN(c)->done, sl & 31, sl >= 32, nullptr, pk0, pk1, p.first_episode + (uint64_t)(first + e), &ord_blue, &ord_red);
         });
+        if (threadIdx.x < 32) green_prefix(n_local, ng_s, gend);
         each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_blue(c); }, &ord_blue);
         green_items(PH_GREEN, first, n_local, next, ng_s, gend);
         each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { if (!DYN(c)->done) ph_red<RV>(c); }, &ord_red);
