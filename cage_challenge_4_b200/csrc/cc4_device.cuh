@@ -13,14 +13,17 @@
  *     identical arguments; functions marked [lane] may be called by any subset of lanes.
  * Citations are file:line under /root/reference/CybORG/ (never read at run time).
  */
-#pragma once
+/* no include guard: cc4_engine.cu includes this file once per namespace (CC4_NS, CC4_WITH_TAPE) */
+#ifndef CC4_NS
+#define CC4_NS cc4
+#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/cc4_b200.h"
 #include "cc4_state.h"
 
-namespace cc4 {
+namespace CC4_NS {
 
 /* inlining knobs (tools/build_variants.py): which helper groups are compiled inline; defaults = the fastest measured set
  * (profiles/r01x_variants.txt: everything inline except the Philox block, the tape reader and rng_int / rng_f64: 0.62 -> 0.54 ms) */
@@ -50,6 +53,9 @@ namespace cc4 {
 #endif
 #ifndef CC4_INL3
 #define CC4_INL3 __forceinline__
+#endif
+#ifndef CC4_INL_RARE
+#define CC4_INL_RARE CC4_INL6      /* transitions that most ticks do not execute: reassignment, re-election, new server sessions, phishing */
 #endif
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -265,7 +271,8 @@ __device__ CC4_INL9 uint64_t tape_next(Cx c, int actor, int site, int kind, uint
 }
 /* block `blk` of the actor's stream for this tick (registers only) */
 #ifndef CC4_INL10
-#define CC4_INL10 __forceinline__
+#define CC4_INL10 __noinline__      /* ONE copy of the ten Philox rounds instead of five inlined ones: the kernel is bound by instruction
+                                       supply (its executed code does not fit the SM's instruction cache), -4.3 % (profiles/r04_variants.txt) */
 #endif
 __device__ CC4_INL10 uint4 philox_block(Cx c, int actor, uint32_t blk)
 {
@@ -311,7 +318,10 @@ __device__ __noinline__ void red_refill(Cx c, int r, uint32_t b)
 {
     Scratch *x = SCR(c);
     const uint4 v = philox_block(c, A_RED0 + r, b);
-    x->blk_id[r] = b; x->blk[r][0] = v.x; x->blk[r][1] = v.y; x->blk[r][2] = v.z; x->blk[r][3] = v.w;
+    /* every calling lane holds the same block: one of them files it, the others read it back after the warp barrier */
+    const uint32_t am = __activemask();
+    if (lane_id() == __ffs(am) - 1) { x->blk_id[r] = b; x->blk[r][0] = v.x; x->blk[r][1] = v.y; x->blk[r][2] = v.z; x->blk[r][3] = v.w; }
+    __syncwarp(am);
 }
 __device__ __forceinline__ uint32_t red_word(Cx c, int r)
 {
@@ -605,7 +615,7 @@ __device__ CC4_INL4 void know_session(Cx c, int r, int id)
 /* RedSessionCheck reports every session of the agent (RedSessionCheck.py:57-63): the idents of its abstract sessions become
  * known server_session keys in dict (= pool) order.  Only agents that got a new abstract session this tick can learn
  * something (sess_add sets x->newss).  [uniform]: pool scanned 32 entries at a time */
-__device__ CC4_INL6 void learn_new_sessions(Cx c)
+__device__ CC4_INL_RARE void learn_new_sessions(Cx c)
 {
     Cc4Dyn *s = DYN(c);
     const uint32_t news = SCR(c)->newss;
@@ -1163,7 +1173,7 @@ __device__ CC4_INL6 void exec_blue(Cx c, int b, uint32_t aw)
 /* green                                                                                            */
 /* ------------------------------------------------------------------------------------------------ */
 /* PhishingEmail._create_new_session PhishingEmail.py:42-113 ([uniform], in green-agent order); x->g.hostagents is current */
-__device__ CC4_INL6 void do_phishing(Cx c, int g)
+__device__ CC4_INL_RARE void do_phishing(Cx c, int g)
 {
     Cc4Dyn *s = DYN(c);
     const uint8_t *ha = reinterpret_cast<const uint8_t *>(SCR(c)->g.hostagents);
@@ -1673,7 +1683,7 @@ template <int RV> __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
 }
 
 /* RedSessionCheck._choose_new_primary_session RedSessionCheck.py:34-55 ([uniform]; agent r holds n sessions, none with ident 0) */
-template <int RV> __device__ CC4_INL6 void rsc_reelect(Cx c, int r, int n)
+template <int RV> __device__ CC4_INL_RARE void rsc_reelect(Cx c, int r, int n)
 {
     Cc4Dyn *s = DYN(c);
     int pk = (int)rng_int_red(c, r, ST_RSC_PRIMARY, (uint32_t)n);
@@ -1699,7 +1709,7 @@ template <int RV> __device__ CC4_INL6 void rsc_reelect(Cx c, int r, int n)
 }
 
 /* SimulationController.different_subnet_agent_reassignment :820-903 [uniform] */
-__device__ CC4_INL6 void reassign(Cx c)
+__device__ CC4_INL_RARE void reassign(Cx c)
 {
     Cc4Dyn *s = DYN(c); Scratch *x = SCR(c);
     uint8_t *list = x->ra.agent, *lid = x->ra.ident; int n = 0;   /* (agent, ident) pairs, agents ascending then dict order; in the
@@ -1742,4 +1752,4 @@ __device__ CC4_INL6 void reassign(Cx c)
     }
 }
 
-}  // namespace cc4
+}  // namespace CC4_NS
