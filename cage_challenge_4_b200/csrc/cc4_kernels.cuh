@@ -1016,11 +1016,20 @@ k_step(Params p, int env0, int env_end, int epb, StepIO io)
             __syncthreads();
         };
         /* the boundaries whose bit is clear keep their block barrier: cut the stage list there */
+        /* a stage with a barrier on both sides runs in its barrier form (fixed item -> warp maps where the items cost the same) */
+        auto alone = [&](const int b) {
+            if (b == FS_BLUE) each_episode(PH_BLUE, first, n_local, next, [&](Cx c, int) { ph_blue(c); }, &ord_blue);
+            else if (b == FS_GREEN) green_items(PH_GREEN, first, n_local, next, ng_s, gend);
+            else if (b == FS_RED) each_episode(PH_RED, first, n_local, next, [&](Cx c, int) { ph_red<RV>(c); }, &ord_red);
+            else if (b == FS_REASSIGN) each_episode<(CC4_FIXED_PHASES >> 1) & 1>(PH_REASSIGN, first, n_local, next, [&](Cx c, int) { ph_reassign<RV>(c); });
+            else if (b == FS_ENDTURN) each_group<CC4_ENDTURN_PER>(PH_ENDTURN, first, n_local, next, [&](Cx c, int, bool exists, int sl) { ph_endturn<RV>(c, exists, sl); });
+            else each_episode<(CC4_FIXED_PHASES >> 2) & 1>(PH_FINISH, first, n_local, next, finish);
+        };
         constexpr int M = CC4_FLOW & 31;
         int lo = 0;
 #pragma unroll
         for (int b = 0; b < N_FSTAGES; b++) {
-            if (b == N_FSTAGES - 1 || !(M >> b & 1)) { segment(lo, b); PW_MARK(PH_BLUE + b); lo = b + 1; }
+            if (b == N_FSTAGES - 1 || !(M >> b & 1)) { if (lo == b) alone(b); else segment(lo, b); PW_MARK(PH_BLUE + b); lo = b + 1; }
         }
     }
 #else

@@ -16,6 +16,7 @@ def main():
     files_seen, cur, hdr = set(), None, None
     per_line = collections.defaultdict(lambda: [0, 0, 0, collections.Counter()])   # inst, samples, thread-inst, stalls
     src_text, line_no = {}, None
+    foot = collections.defaultdict(lambda: [0, 0])      # SASS instructions of the line: all, executed at least once
     for r in rows:
         if r and r[0] == "File Path":
             if files_seen and r[1] == first:   # the second captured kernel starts
@@ -33,6 +34,8 @@ def main():
             line_no = int(r[0]); src_text[(cur, line_no)] = r[1]; continue
         if not r[ix["Instructions Executed"]].isdigit(): continue
         d = per_line[(cur, line_no)]
+        foot[(cur, line_no)][0] += 1
+        if int(r[ix["Instructions Executed"]]) > 0: foot[(cur, line_no)][1] += 1
         d[0] += int(r[ix["Instructions Executed"]]); d[1] += int(r[ix["# Samples"]]); d[2] += int(r[ix["Thread Instructions Executed"]])
         for s in stalls:
             v = int(r[ix[s]])
@@ -53,6 +56,12 @@ def main():
         fn = func_of.get(k, k[0].split("/")[-1])
         b = by_f[fn]; b[0] += d[0]; b[1] += d[1]; b[2] += d[2]; b[3].update(d[3])
     launches = None
+    foot_f = collections.defaultdict(lambda: [0, 0])
+    for k, (a, e) in foot.items():
+        fn = func_of.get(k, k[0].split("/")[-1]); foot_f[fn][0] += a; foot_f[fn][1] += e
+    fa, fe = sum(v[0] for v in foot_f.values()), sum(v[1] for v in foot_f.values())
+    print(f"static code {fa} instructions = {fa * 16 / 1024:.1f} KB, executed at least once in this launch {fe} = {fe * 16 / 1024:.1f} KB (the SM's instruction cache has to supply these every block-tick)")
+    print("executed footprint by function (KB): " + ", ".join(f"{fn} {v[1] * 16 / 1024:.1f}/{v[0] * 16 / 1024:.1f}" for fn, v in sorted(foot_f.items(), key=lambda kv: -kv[1][1])[:30]))
     print(f"total warp-instructions {tot_i}  samples {tot_s}")
     print(f"{'function':28s} {'inst%':>6s} {'samp%':>6s} {'lanes':>5s}  top stalls")
     for fn, b in sorted(by_f.items(), key=lambda kv: -kv[1][1])[:40]:
