@@ -20,4 +20,10 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_st
     python bench.py --steps 40 --warmup 3 --no-cpu --no-configs --e2e-steps 3 > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 timeout 600 ncu --set full --clock-control none -k regex:k_reset_fast -c 1 -o $OUT/prof_kreset_$TAG -f \
     python bench.py --steps 5 --warmup 3 --no-cpu --no-configs --e2e-steps 3 > $OUT/ncu_reset_$TAG.log 2>&1; echo "ncu reset rc=$?"
-ls -la $OUT
+# digests kept under profiles/ (the .ncu-rep files stay in gpurun_out/)
+python tools/ncu_summary.py $OUT/prof_kstep_$TAG.ncu-rep > $OUT/kstep_ncu_full_summary_$TAG.txt 2>&1
+python tools/ncu_by_function.py $OUT/prof_kstep_$TAG.ncu-rep --lines 40 > $OUT/kstep_by_function_$TAG.txt 2>&1
+python tools/ncu_summary.py $OUT/prof_kreset_$TAG.ncu-rep > $OUT/kreset_ncu_full_summary_$TAG.txt 2>&1
+python tools/sass_evidence.py > $OUT/sass_$TAG.txt 2>&1
+head -25 $OUT/kstep_ncu_full_summary_$TAG.txt
+ls -la $OUT | tail -20
