@@ -1436,11 +1436,17 @@ template <int RV> __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
     const int actor = A_RED0 + r, lane = lane_id();
     int si = (a.code == AC_SLEEP || a.code == AC_INVALID) ? -1 : SCR(c)->sess_moved ? sess_find(s, r, a.session) : (int)SCR(c)->act_si[r];
     int S_host = si >= 0 ? (int)S_HOST(s->sess[si]) : -1, S_abs = si >= 0 ? (int)SF_ABS(s->sessf[si]) : 0;
+    /* The observation entries an action reports are filed by ONE copy of obs_entry after the switch (the action bodies only
+       queue them, 16 bits each, in report order): ten inlined copies were 4.6 KB of the red phase's executed code. */
+    uint64_t pend = 0; int npend = 0, succ = SUCC_UNKNOWN;
+    #define OBS_Q(key_ip, slot, iface, subnet_if, syshost, sess) do { pend |= (uint64_t)(0x8000u | (uint32_t)(slot) | (uint32_t)(key_ip) << 8 | (uint32_t)(iface) << 9 | \
+        (uint32_t)(subnet_if) << 10 | (uint32_t)(syshost) << 11 | (uint32_t)(sess) << 12) << (16 * npend); npend++; } while (0)
+    #define RET(v) do { succ = (v); goto done; } while (0)
     switch (a.code) {
     case AC_DRS: {     /* DiscoverRemoteSystems.py:39 -> Pingsweep.execute Pingsweep.py:31-64 */
-        if (si < 0) return SUCC_FALSE;
+        if (si < 0) RET(SUCC_FALSE);
         int sn = a.subnet;
-        if (sn == S_INT) return SUCC_UNKNOWN;
+        if (sn == S_INT) RET(SUCC_UNKNOWN);
         int nu = s->nuser[sn], nh = nu + s->nserver[sn];
         if (red_allowed(r, sn)) {   /* _filter_obs SimulationController.py:1054 drops interfaces of foreign subnets */
             /* one ip-keyed Interface + Subnet entry per host of the subnet, users first (state.hosts order): obs_entry for
@@ -1464,11 +1470,11 @@ template <int RV> __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
             x->n_oent[r] = (uint8_t)nn;
             __syncwarp();
         }
-        return SUCC_TRUE;
+        RET(SUCC_TRUE);
     }
     case AC_AGGR: case AC_STEALTH: {   /* DiscoverNetworkServices.py:44-86 -> Portscan.py:23-65 */
-        if (si < 0 || !S_abs) return SUCC_FALSE;
-        if (blocking(s, S_host, a.host)) return SUCC_FALSE;
+        if (si < 0 || !S_abs) RET(SUCC_FALSE);
+        if (blocking(s, S_host, a.host)) RET(SUCC_FALSE);
         double rate = a.code == AC_AGGR ? 0.75 : 0.25;
         double u = rng_f64_red(c, r, ST_PORTSCAN);
         const int h = a.host;
@@ -1489,12 +1495,12 @@ template <int RV> __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
             int at = ports_find(c, r, a.session, h, &was);
             if (at < 0) { if (s->n_ports >= CC4_PORT_CAP) { fail(c, CC4_E_CAPACITY); at = 0; } else { at = s->n_ports; s->n_ports = (uint16_t)(at + 1); } }
             WC(c)->k->ports[at] = PT_MAKE(mask, h, a.session, r);
-            obs_entry(c, r, 1, h, 1, 0, 0, 0);
+            OBS_Q(1, h, 1, 0, 0, 0);
         }
-        return SUCC_TRUE;
+        RET(SUCC_TRUE);
     }
     case AC_DD: {      /* DiscoverDeception.py:44-101: two draws per process, in list order */
-        if (si < 0) return SUCC_FALSE;
+        if (si < 0) RET(SUCC_FALSE);
         int rep = 0, h = a.host;
         const uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
         if (!CC4_TAPE_ON()) {
@@ -1518,17 +1524,17 @@ template <int RV> __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
             }
             ctr_set(x, actor, p0);
         } else rep = dd_tape(c, actor, h);
-        if (rep) obs_entry(c, r, 0, h, 1, 0, 0, 0);
-        return SUCC_TRUE;
+        if (rep) OBS_Q(0, h, 1, 0, 0, 0);
+        RET(SUCC_TRUE);
     }
     case AC_EXPLOIT: { /* ExploitRemoteService.py:149-202 */
-        if (si < 0 || !S_abs) return SUCC_FALSE;
+        if (si < 0 || !S_abs) RET(SUCC_FALSE);
         int target = a.host, src = S_host;
         const uint32_t pd_target = WC(c)->k->pdir[target], pmax_target = WC(c)->k->pmax[target];    /* requested ahead of the port-table scan (all cold) */
         uint32_t pw;
-        if (ports_find(c, r, a.session, target, &pw) < 0) return SUCC_FALSE;
+        if (ports_find(c, r, a.session, target, &pw) < 0) RET(SUCC_FALSE);
         const int ports = (int)PT_MASK(pw);
-        if (blocking(s, src, target)) return SUCC_FALSE;
+        if (blocking(s, src, target)) RET(SUCC_FALSE);
         enum { X_HTTP, X_HTTPS, X_SSH, X_SQL, X_HARAKA };
         /* DefaultExploitActionSelector :37-69: the options in class order, packed four bits each; weights HTTP 3, HTTPS 4,
            SSH 0.1, SQL 5, Haraka 6, so the option with the largest weight is the last one listed unless SSH is alone */
@@ -1538,7 +1544,7 @@ template <int RV> __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
         if (ports & PB_22) { opts |= (uint32_t)X_SSH << (4 * no++); }
         if ((ports & PB_3390) && (ports & (PB_80 | PB_443))) { top = no; opts |= (uint32_t)X_SQL << (4 * no++); }
         if (ports & PB_25) { top = no; opts |= (uint32_t)X_HARAKA << (4 * no++); }
-        if (no < 1) return SUCC_FALSE;
+        if (no < 1) RET(SUCC_FALSE);
         int sel = (int)(opts & 15u);
         if (no > 1) {       /* the top-weighted option is popped, the choice is uniform among the rest (and one more draw is spent) */
             const uint32_t rest = (opts & ((1u << (4 * top)) - 1u)) | (opts >> (4 * (top + 1))) << (4 * top);
@@ -1580,27 +1586,25 @@ template <int RV> __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
                 __syncwarp();
                 ctr_set(x, actor, p0 + (uint32_t)nh);
             }
-            if (vk < 0) return SUCC_FALSE;
+            if (vk < 0) RET(SUCC_FALSE);
             s->ev[target] |= EV_NET;
-            int pid = exploit_new_session(c, r, target, pd_target, pmax_target);
-            ev_procpid(c, target, pid);
-            obs_entry(c, r, 1, target, 1, 0, 1, 1);
-            obs_entry(c, r, 1, src, 1, 0, 0, 0);
-            return SUCC_TRUE;
+        } else {
+            /* ExploitAction.sim_exploit ExploitAction.py:48-116 */
+            if (vk < 0) RET(SUCC_FALSE);
+            const bool decoy = vk >= K_D_APACHE && vk <= K_D_VSFTPD;
+            if (decoy) s->ev[target] |= EV_NET;
+            OBS_Q(1, target, 1, 0, 0, 0);
+            if (!(sel == X_SQL || decoy)) RET(SUCC_FALSE);
+            if (0.0 >= rng_f64_red(c, r, ST_EXP_SUCC)) RET(SUCC_FALSE);
+            if (decoy) { s->ev[target] |= EV_NET; RET(SUCC_FALSE); }
         }
-        /* ExploitAction.sim_exploit ExploitAction.py:48-116 */
-        if (vk < 0) return SUCC_FALSE;
-        bool decoy = vk >= K_D_APACHE && vk <= K_D_VSFTPD;
-        if (decoy) s->ev[target] |= EV_NET;
-        obs_entry(c, r, 1, target, 1, 0, 0, 0);
-        if (!(sel == X_SQL || decoy)) return SUCC_FALSE;
-        if (0.0 >= rng_f64_red(c, r, ST_EXP_SUCC)) return SUCC_FALSE;
-        if (decoy) { s->ev[target] |= EV_NET; return SUCC_FALSE; }
-        int pid = exploit_new_session(c, r, target, pd_target, pmax_target);
-        if (rng_f64_red(c, r, ST_EXP_DETECT) > 0.05) ev_procpid(c, target, pid);
-        obs_entry(c, r, 1, target, 1, 0, 1, 1);
-        obs_entry(c, r, 1, src, 1, 0, 0, 0);
-        return SUCC_TRUE;
+        /* both ways in end here (one copy of the session / process creation): the brute force is always noticed, the exploit
+           with probability 0.95 (its draw comes after the new pid's) */
+        const int pid = exploit_new_session(c, r, target, pd_target, pmax_target);
+        if (sel == X_SSH || rng_f64_red(c, r, ST_EXP_DETECT) > 0.05) ev_procpid(c, target, pid);
+        OBS_Q(1, target, 1, 0, 1, 1);
+        OBS_Q(1, src, 1, 0, 0, 0);
+        RET(SUCC_TRUE);
     }
     case AC_PRIVESC: { /* PrivilegeEscalate.py:127-179 */
         const int h = a.host;
@@ -1617,28 +1621,28 @@ template <int RV> __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
             n += __popc(om);
             if (tgt < 0 && rm) tgt = base + __ffs(rm) - 1;
         }
-        if (n == 0) return SUCC_FALSE;
+        if (n == 0) RET(SUCC_FALSE);
         if (tgt < 0) {
             int pk = (int)rng_int_red(c, r, ST_PRIV_SESS, (uint32_t)n);
             tgt = sess_kth(s, pk, on_host);
-            if (si < 0 || !S_abs) return SUCC_FALSE;
+            if (si < 0 || !S_abs) RET(SUCC_FALSE);
             s->sessf[tgt] |= 1u << 4;      /* EscalateAction.__upgrade_session EscalateAction.py:54-87 */
             int pi = proc_find(c, S_PID(s->sess[tgt]), pd_h);
             if (pi >= 0) (WC(c)->k->parena + PD_OFF(pd_h))[pi] |= P_ROOTBIT; else fail(c, CC4_E_UNREACHABLE);
         }
-        obs_entry(c, r, 0, h, 0, 0, 0, 1);
+        OBS_Q(0, h, 0, 0, 0, 1);
         if (SF_ABS(s->sessf[tgt])) know_session(c, r, S_ID(s->sess[tgt]));
         if (si >= 0 && (h & 15) == 0) {   /* ExploreHost EscalateAction.py:90-106, Host.info = _between_subnet_links :418-468 */
             uint32_t lk = c_links[h >> 4];
-            _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) if (lk >> sn & 1) obs_entry(c, r, 0, sn * 16, 1, 0, 0, 0);
+            _Pragma("unroll 1") for (int sn = 0; sn < 8; sn++) if (lk >> sn & 1) OBS_Q(0, sn * 16, 1, 0, 0, 0);
         }
-        return SUCC_TRUE;
+        RET(SUCC_TRUE);
     }
     case AC_IMPACT: case AC_DEGRADE: {   /* Impact.py:38-88, DegradeServices.py:38-82 */
         const int h = a.host;
         uint32_t any = 0, root = 0;
         _Pragma("unroll 1") for (int i = lane; i < s->n_sess; i += 32) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_HOST(s->sess[i]) == (uint32_t)h) { any = 1; root |= SF_ROOT(s->sessf[i]); }
-        if (!__any_sync(FULLMASK, any && root)) return SUCC_FALSE;
+        if (!__any_sync(FULLMASK, any && root)) RET(SUCC_FALSE);
         uint64_t v = WC(c)->k->svc64[h];
         int n = svc_count(v);
         /* all nine 7-bit entries at once: `lanes` = bit 7i of every entry in use, `ot` = of the entry that is the OT service */
@@ -1647,8 +1651,8 @@ template <int RV> __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
         const uint64_t t = v ^ ((uint64_t)K_OT * SVC_ONES);
         const uint64_t ot = ~(t | t >> 1 | t >> 2 | t >> 3) & lanes;
         if (a.code == AC_IMPACT) {
-            if (!ot || (v & SVC_OT_STOPPED)) return SUCC_FALSE;
-            if (si < 0) return SUCC_FALSE;     /* StopService is a TargetedLocalAction: TargetedLocalAction.py:14-21 */
+            if (!ot || (v & SVC_OT_STOPPED)) RET(SUCC_FALSE);
+            if (si < 0) RET(SUCC_FALSE);     /* StopService is a TargetedLocalAction: TargetedLocalAction.py:14-21 */
             WC(c)->k->svc64[h] = v | SVC_OT_STOPPED;  /* Host.stop_service Host.py:296-301 */
             /* State.remove_process State.py:390-418: the first live OT service process becomes a tombstone */
             uint32_t *pp_h = PROCS(c, h); const int np_h = NPROC(c, h);
@@ -1668,19 +1672,28 @@ template <int RV> __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
         } else {
             /* every active service loses one reliability step (20 %), not below 0 */
             const uint64_t act = (v & SVC_OT_STOPPED) ? lanes & ~ot : lanes;
-            if (!act) return SUCC_FALSE;
+            if (!act) RET(SUCC_FALSE);
             const uint64_t nz = (v >> 4 | v >> 5 | v >> 6) & act;       /* reliability > 0 */
             v -= nz << 4;
             WC(c)->k->svc64[h] = v;
         }
-        obs_entry(c, r, 0, h, 0, 0, 0, 0);
-        return SUCC_TRUE;
+        OBS_Q(0, h, 0, 0, 0, 0);
+        RET(SUCC_TRUE);
     }
-    case AC_WITHDRAW: if (RV == 2) return exec_withdraw(c, r, a.host, a.session, si, S_host); return SUCC_UNKNOWN;      /* only the RandomSelectRedAgent ever submits it */
-    case AC_INVALID: return SUCC_FALSE;
-    default: return SUCC_UNKNOWN;
+    case AC_WITHDRAW: if (RV == 2) RET(exec_withdraw(c, r, a.host, a.session, si, S_host)); RET(SUCC_UNKNOWN);      /* only the RandomSelectRedAgent ever submits it */
+    case AC_INVALID: RET(SUCC_FALSE);
+    default: RET(SUCC_UNKNOWN);
     }
+done:
+    _Pragma("unroll 1") for (; pend; pend >>= 16) {
+        const uint32_t e = (uint32_t)pend & 0xFFFFu;
+        obs_entry(c, r, (int)(e >> 8 & 1u), (int)(e & 0xFFu), (int)(e >> 9 & 1u), (int)(e >> 10 & 1u), (int)(e >> 11 & 1u), (int)(e >> 12 & 1u));
+    }
+    #undef OBS_Q
+    #undef RET
+    return succ;
 }
+
 
 /* RedSessionCheck._choose_new_primary_session RedSessionCheck.py:34-55 ([uniform]; agent r holds n sessions, none with ident 0) */
 template <int RV> __device__ CC4_INL_RARE void rsc_reelect(Cx c, int r, int n)
