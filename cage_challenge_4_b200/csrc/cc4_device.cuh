@@ -1680,7 +1680,7 @@ template <int RV> __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
         OBS_Q(0, h, 0, 0, 0, 0);
         RET(SUCC_TRUE);
     }
-    case AC_WITHDRAW: if (RV == 2) RET(exec_withdraw(c, r, a.host, a.session, si, S_host)); RET(SUCC_UNKNOWN);      /* only the RandomSelectRedAgent ever submits it */
+    case AC_WITHDRAW: RET(RV == 2 ? exec_withdraw(c, r, a.host, a.session, si, S_host) : (int)SUCC_UNKNOWN);      /* only the RandomSelectRedAgent ever submits it */
     case AC_INVALID: RET(SUCC_FALSE);
     default: RET(SUCC_UNKNOWN);
     }

@@ -1,5 +1,5 @@
 #!/bin/bash
-# scratch GPU call: instruction-cache and stall metrics of k_step for several variants
+# GPU: instruction-cache (SM ICC, GPC L1.5) and stall counters of k_step for the named variants.  bash tools/gpu_icache.sh tag variant ...
 TAG=${1:-r04j}; shift
 OUT=gpurun_out; mkdir -p $OUT
 M=sm__icc_requests.sum,sm__icc_requests_lookup_hit.sum,sm__icc_requests_lookup_miss_tag_hit.sum,sm__icc_requests_lookup_miss_tag_miss.sum,gcc__cache_requests_type_instruction.sum,gcc__cache_requests_type_instruction_lookup_miss.sum

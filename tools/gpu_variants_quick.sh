@@ -1,5 +1,5 @@
 #!/bin/bash
-# scratch GPU call: time the tuning variants twice (drift check), parity-test the given ones
+# GPU: time every tuning variant under cage_challenge_4_b200/variants twice (drift check) and parity-test the named ones.  bash tools/gpu_variants_quick.sh tag [variant ...]
 TAG=${1:-r04a}; shift
 OUT=gpurun_out; mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi_$TAG.txt 2>&1
