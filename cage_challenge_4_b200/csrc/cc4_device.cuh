@@ -1051,18 +1051,22 @@ __device__ CC4_INL6 bool stop_process(Cx c, int actor, int h, uint32_t pid, bool
 __device__ CC4_INL6 void do_restore(Cx c, int h)
 {
     Cc4Dyn *s = DYN(c); const Cc4Stat *st = WC(c)->st;
+    /* the backup (static record, cold) is requested before the pool scan: three independent loads in flight instead of three
+       round trips one after the other; the largest pid comes from the same registers instead of a read-back of the arena */
+    const int on = st->o_nproc[h];
+    const uint32_t mine = lane_id() < CC4_OSLAB ? st->o_procs[h][lane_id()] : 0u;
+    const uint64_t svc0 = st->o_svc64[h];
     _Pragma("unroll 1") for (;;) {      /* every session on the host goes, in pool order */
         int i = sess_first(s, [=](uint32_t w, uint32_t) { return S_HOST(w) == (uint32_t)h; });
         if (i < 0) break;
         sess_delete(c, i);
     }
     s->ev[h] = 0;
-    const int on = st->o_nproc[h];
-    if (lane_id() < on) WC(c)->k->parena[h * CC4_OSLAB + lane_id()] = st->o_procs[h][lane_id()];   /* back in the home slab (on <= CC4_OSLAB) */
-    __syncwarp();
-    WC(c)->k->pdir[h] = PD_MAKE(h * CC4_OSLAB, on, 3);
-    proc_rescan_max(c, h);
-    WC(c)->k->svc64[h] = st->o_svc64[h];
+    Cc4Cold *k = WC(c)->k;
+    if (lane_id() < on) k->parena[h * CC4_OSLAB + lane_id()] = mine;   /* back in the home slab (on <= CC4_OSLAB) */
+    k->pdir[h] = PD_MAKE(h * CC4_OSLAB, on, 3);
+    k->pmax[h] = (uint16_t)__reduce_max_sync(FULLMASK, lane_id() < on && !P_DEAD(mine) ? P_PID(mine) : 0u);      /* proc_rescan_max of the restored list */
+    k->svc64[h] = svc0;
 }
 
 /* production mode: the next two words of a blue actor's stream from one Philox block (blue streams are not cached in the
@@ -1640,10 +1644,10 @@ template <int RV> __device__ CC4_INL7 int exec_red(Cx c, int r, uint32_t aw)
     }
     case AC_IMPACT: case AC_DEGRADE: {   /* Impact.py:38-88, DegradeServices.py:38-82 */
         const int h = a.host;
+        uint64_t v = WC(c)->k->svc64[h];        /* cold; requested ahead of the pool scan */
         uint32_t any = 0, root = 0;
         _Pragma("unroll 1") for (int i = lane; i < s->n_sess; i += 32) if (SF_AGENT(s->sessf[i]) == (uint32_t)r && S_HOST(s->sess[i]) == (uint32_t)h) { any = 1; root |= SF_ROOT(s->sessf[i]); }
         if (!__any_sync(FULLMASK, any && root)) RET(SUCC_FALSE);
-        uint64_t v = WC(c)->k->svc64[h];
         int n = svc_count(v);
         /* all nine 7-bit entries at once: `lanes` = bit 7i of every entry in use, `ot` = of the entry that is the OT service */
         const uint64_t SVC_ONES = 0x0102040810204081ull;
