@@ -54,6 +54,9 @@ namespace CC4_NS {
 #ifndef CC4_INL3
 #define CC4_INL3 __forceinline__
 #endif
+#ifndef CC4_GREEN_PHILOX_INLINE
+#define CC4_GREEN_PHILOX_INLINE 1     /* the green agents keep their own inlined Philox rounds: their service-word load stays in flight across them (-1.4 %) */
+#endif
 #ifndef CC4_INL_RARE
 #define CC4_INL_RARE CC4_INL6      /* transitions that most ticks do not execute: reassignment, re-election, new server sessions, phishing */
 #endif
@@ -275,6 +278,14 @@ __device__ CC4_INL9 uint64_t tape_next(Cx c, int actor, int site, int kind, uint
                                        supply (its executed code does not fit the SM's instruction cache), -4.3 % (profiles/r04_variants.txt) */
 #endif
 __device__ CC4_INL10 uint4 philox_block(Cx c, int actor, uint32_t blk)
+{
+    const WarpCtx *g = WC(c);
+    uint32_t o[4] = { blk, (uint32_t)actor, actor == NAG ? 0u : (uint32_t)g->tick + 1u, g->ep_lo };
+    philox4x32_10(o, g_blk.k0, g->k1);
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+/* the same, always inline: for the green agents, whose service-word load stays in flight across the rounds (a call would wait for it) */
+__device__ __forceinline__ uint4 philox_block_inl(Cx c, int actor, uint32_t blk)
 {
     const WarpCtx *g = WC(c);
     uint32_t o[4] = { blk, (uint32_t)actor, actor == NAG ? 0u : (uint32_t)g->tick + 1u, g->ep_lo };
@@ -1285,7 +1296,11 @@ __device__ CC4_INL8 int green_tick(Cx c, int g, uint32_t *ev_words)
        service pick; the phishing follow-up continues the stream at word j).  word / 2^32 < 0.01 is the integer test
        word < P01: the double product is exact and 0.01 * 2^32 = 42 949 672.96 */
     const uint32_t P01 = 42949673u;
+#if CC4_GREEN_PHILOX_INLINE
+    const uint4 blk = philox_block_inl(c, actor, 0);
+#else
     const uint4 blk = philox_block(c, actor, 0);
+#endif
     uint32_t j = 1;
     int out = 0;
     const uint32_t choice = __umulhi(blk.x, 3u);
