@@ -54,6 +54,9 @@ namespace CC4_NS {
 #ifndef CC4_INL3
 #define CC4_INL3 __forceinline__
 #endif
+#ifndef CC4_POLICY_PHILOX_INLINE
+#define CC4_POLICY_PHILOX_INLINE 0
+#endif
 #ifndef CC4_GREEN_PHILOX_INLINE
 #define CC4_GREEN_PHILOX_INLINE 1     /* the green agents keep their own inlined Philox rounds: their service-word load stays in flight across them (-1.4 %) */
 #endif
@@ -969,7 +972,11 @@ template <int RV> __device__ CC4_INL8 uint32_t red_policy(Cx c, int r)
     /* production mode: host pick, action pick and at most two parameter picks fit the four words of the stream's first
        Philox block, which stays in registers; the block is left in the stream cache for the action code that follows */
     const bool tape = CC4_TAPE_ON();
+#if CC4_POLICY_PHILOX_INLINE
+    const uint4 blk = tape ? make_uint4(0, 0, 0, 0) : philox_block_inl(c, actor, 0);
+#else
     const uint4 blk = tape ? make_uint4(0, 0, 0, 0) : philox_block(c, actor, 0);
+#endif
     uint32_t j = 0;
     auto ri = [&](int site, uint32_t n) -> uint32_t {
         if (tape) return rng_int(c, actor, site, n);
@@ -1082,6 +1089,21 @@ __device__ CC4_INL6 void do_restore(Cx c, int h)
 
 /* production mode: the next two words of a blue actor's stream from one Philox block (blue streams are not cached in the
    scratch: a blue agent draws at most twice per tick) */
+#ifndef CC4_BLUE_PHILOX_INLINE
+#define CC4_BLUE_PHILOX_INLINE 1     /* -2.7 %: DeployDecoy sits in the heaviest blue chains */
+#endif
+#if CC4_BLUE_PHILOX_INLINE     /* inline rounds: the decoy's cold loads stay in flight across them (a call waits for loads in flight) */
+__device__ __forceinline__ uint2 blue_words2(Cx c, int actor)
+{
+    Scratch *x = SCR(c);
+    const uint32_t j = ctr_get(x, actor);
+    ctr_set(x, actor, j + 2);
+    const uint4 v = philox_block_inl(c, actor, j >> 2);
+    const uint32_t w0 = u4_word(v, j & 3u);
+    const uint32_t w1 = (j & 3u) < 3u ? u4_word(v, (j & 3u) + 1u) : philox_block(c, actor, (j >> 2) + 1u).x;
+    return make_uint2(w0, w1);
+}
+#else
 __device__ __noinline__ uint2 blue_words2(Cx c, int actor)
 {
     Scratch *x = SCR(c);
@@ -1092,6 +1114,7 @@ __device__ __noinline__ uint2 blue_words2(Cx c, int actor)
     const uint32_t w1 = (j & 3u) < 3u ? u4_word(v, (j & 3u) + 1u) : philox_block(c, actor, (j >> 2) + 1u).x;
     return make_uint2(w0, w1);
 }
+#endif
 
 /* DecoyAction.execute DecoyAction.py:47-112 with DeployDecoy.CANDIDATE_DECOYS DeployDecoy.py:27 [uniform] */
 __device__ CC4_INL6 void do_decoy(Cx c, int b, int h)
@@ -1101,6 +1124,9 @@ __device__ CC4_INL6 void do_decoy(Cx c, int b, int h)
     /* the host's cold words are requested together; the first 32 list entries stay in a register for both passes */
     const uint32_t d = k->pdir[h], pmax = k->pmax[h];
     uint64_t v = k->svc64[h];
+    /* production mode: the two words of the draws below are taken now, while the cold words are on their way */
+    uint2 dw = make_uint2(0u, 0u);
+    if (CC4_BLUE_PHILOX_INLINE && !CC4_TAPE_ON()) dw = blue_words2(c, actor);
     uint32_t *pp_h = k->parena + PD_OFF(d); const int np_h = (int)PD_CNT(d);
     const uint32_t w0 = lane_id() < np_h ? pp_h[lane_id()] : P_NONE;
     uint32_t used = 0;
@@ -1118,7 +1144,7 @@ __device__ CC4_INL6 void do_decoy(Cx c, int b, int h)
     fac |= (uint32_t)K_D_VSFTPD << (4 * nf++);
     uint32_t pick, pid_draw;        /* DecoyAction.py:64 choice(factories), Host.create_pid Host.py:198-200 */
     if (CC4_TAPE_ON()) { pick = rng_int(c, actor, ST_DECOY_FACTORY, (uint32_t)nf); pid_draw = rng_int(c, actor, ST_CREATE_PID, 9); }
-    else { const uint2 w = blue_words2(c, actor); pick = __umulhi(w.x, (uint32_t)nf); pid_draw = __umulhi(w.y, 9u); }
+    else { const uint2 w = CC4_BLUE_PHILOX_INLINE ? dw : blue_words2(c, actor); pick = __umulhi(w.x, (uint32_t)nf); pid_draw = __umulhi(w.y, 9u); }
     int kind = (int)(fac >> (4 * pick) & 15u);
     int pid = (int)(pmax + 1 + pid_draw);
     if (pid > 0xFFFF) { fail(c, CC4_E_CAPACITY); pid = 0xFFFF; }
@@ -1194,6 +1220,7 @@ __device__ CC4_INL_RARE void do_phishing(Cx c, int g)
     const uint8_t *ha = reinterpret_cast<const uint8_t *>(SCR(c)->g.hostagents);
     int actor = A_GREEN0 + g, gh = green_host_of(s, g), gsn = gh >> 4;
     if (ha[gh]) return;
+    const uint32_t pd_gh = WC(c)->k->pdir[gh], pmax_gh = WC(c)->k->pmax[gh];      /* cold; requested ahead of the owner search */
     /* (host, agent) pairs in state.hosts order (per subnet: users, then servers), agents ascending on each host.  A red
        agent with a session in the green host's own subnet owns the new session (the LAST such host wins: only the inner
        loop breaks, PhishingEmail.py:73-81); otherwise the owner is drawn uniformly from the pairs of the other subnets.
@@ -1228,8 +1255,8 @@ __device__ CC4_INL_RARE void do_phishing(Cx c, int g)
         const int before = __shfl_sync(FULLMASK, incl - cnt, L);
         src = (int)__fns(v, 0, pk - before + 1) & 7;      /* bit position inside the lane's four bytes -> agent */
     }
-    int pid = create_pid_on(c, actor, gh);
-    proc_append(c, gh, P_MAKE(pid, K_REDABS, 0, 0));
+    int pid = create_pid(c, actor, pmax_gh);
+    proc_append(c, gh, P_MAKE(pid, K_REDABS, 0, 0), pd_gh, pmax_gh);
     sess_add(c, src, gh, 1, 0, pid);
     reinterpret_cast<uint8_t *>(SCR(c)->g.hostagents)[gh] |= (uint8_t)(1u << src);
 }
