@@ -281,7 +281,7 @@ enum { PH_SETUP, PH_POLICY, PH_BLUE, PH_GREEN, PH_RED, PH_REASSIGN, PH_ENDTURN, 
 #define CC4_TYPE_ORDER 0        /* 1 (with CC4_ORDER_CLASSES=8): order the action phases by the kind of the first due action instead of by summed cost */
 #endif
 #ifndef CC4_ORDER_CLASSES
-#define CC4_ORDER_CLASSES 4     /* cost classes of the two action phases: 4 (coarse weights) or 8 (measured action costs, profiles/r02s_phase_clocks.txt) */
+#define CC4_ORDER_CLASSES 8     /* cost classes of the two action phases: 8 (measured action costs, profiles/r02s_phase_clocks.txt; -0.6 %) or 4 (coarse weights) */
 #endif
 constexpr int NCLS = CC4_ORDER_CLASSES;
 struct PhaseOrder { int cnt[NCLS]; uint8_t list[NCLS][64]; };
