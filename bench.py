@@ -37,9 +37,9 @@ EPISODE_TICKS = 499                          # steps=500 -> done at step_count >
 N_SM, ISSUE_PER_SM = 148, 4                  # B200: 148 SMs, 4 warp schedulers each, one warp-instruction per scheduler and cycle
 # From the committed `ncu --set full` capture of one k_step launch at 65 536 episodes (profiles/, see NCU_SOURCE):
 # dram__bytes_read.sum + dram__bytes_write.sum, and smsp__inst_executed.sum (warp-instructions).
-NCU_SOURCE = "profiles/r04w_kstep_ncu_full_summary.txt"
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 459_495_680      # 300.04 MB read + 159.46 MB written
-NCU_WARP_INST_PER_LAUNCH = 199_785_216
+NCU_SOURCE = "profiles/r05w_kstep_ncu_full_summary.txt"
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 456_952_064      # 299.90 MB read + 157.05 MB written
+NCU_WARP_INST_PER_LAUNCH = 203_514_083
 
 
 def load_peaks():
