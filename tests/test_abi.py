@@ -114,3 +114,24 @@ def test_compat_package_resolves_the_reference_import_paths():
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "compat"))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
     assert out.returncode == 0 and out.stdout.startswith("ok"), out.stderr[-800:]
+
+
+def test_production_kernels_carry_no_tape_code():
+    """The device code is compiled into two namespaces (csrc/cc4_engine.cu): `cc4` with the tape paths (parity replay) and the
+    reset kernels, `cc4p` = k_step / k_rollout of production mode without them.  The shipped library must hold both sets of
+    kernels, and no tape-mode function may exist in the production namespace."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    from cage_challenge_4_b200 import _native
+    out = subprocess.run(["cuobjdump", "-symbols", _native.LIB_PATH], capture_output=True, text=True).stdout
+    names = [l.split()[-1] for l in out.splitlines() if "STT_FUNC" in l]
+    for rv in range(3):
+        assert any(f"N4cc4p6k_stepILi{rv}E" in n for n in names), f"production k_step<{rv}> missing"
+        assert any(f"N3cc46k_stepILi{rv}E" in n for n in names), f"tape-mode k_step<{rv}> missing"
+        assert any(f"N4cc4p9k_rolloutILi{rv}E" in n for n in names), f"production k_rollout<{rv}> missing"
+    assert any("N3cc412k_reset_fast" in n for n in names) and any("N3cc47k_reset" in n for n in names)
+    tape_in_prod = [n for n in names if "N4cc4p" in n and "tape" in n]
+    assert not tape_in_prod, tape_in_prod
+    assert any("N3cc4" in n and "tape_next" in n for n in names), "the tape reader must exist in the parity namespace"
